@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py -- PDHG iterations/s on ROF-TV 4096^2 (BASELINE.json metric) with roofline evidence.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A *step* is one PDHG iteration (BackendPDHG::PerformIteration, backend_pdhg.cu:311-381) on the
+metric config of SURVEY.md section 8(d): ROF 4096 x 4096 gray, BlockGradient2D + 1d:square +
+norm2:ind_leq0, alpha = 1 preconditioning, Alg1 steps, residuals every 10 iterations.
+Rank 0 prints ONE JSON line (contract in the task statement):
+
+  value      iterations/s with all inputs resident in HBM, CUDA-event timed over K iterations
+  e2e        iterations/s of a whole solve through the public Solver API with pinned HOST
+             buffers: problem upload (H2D), K iterations, solution download (D2H)
+  roofline   dominant kernel (fused dual pass): algorithmic bytes / event-timed duration vs the
+             measured HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline  the OpenMP oracle port of the same iteration on the host cores (bounded sample)
+
+--impl reference times the reference algorithm's CPU restatement (prost has no CPU path of its
+own; oracle/prost_oracle.cpp, kind "port") on all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NX = NY = 4096
+LAM = 10.0
+RESIDUAL_ITER = 10
+# primal pass reads y (2N) + x (N) + f (N), writes x+ (N); dual pass reads x+, x (2N),
+# y (2N), writes y+ (2N): 11 floats = 44 B per pixel per iteration, 20 B primal + 24 B dual.
+BYTES_PER_PX_ITER = 44
+BYTES_PER_PX_PRIMAL = 20
+BYTES_PER_PX_DUAL = 24
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.lines = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_problem(pb, syn, ctx, f):
+    desc = syn.rof(NX, NY, LAM, f=f)
+    prob = pb.create_problem(ctx, desc)
+    return prob
+
+
+def run_reference_arm(args, rank, world):
+    """Reference arm for this tier: the CPU restatement of prost's PDHG iteration on host cores."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_binding import OracleProblem, OraclePDHG, num_threads
+    from prost_b200 import synthetic as syn
+    threads = num_threads()
+    # bounded sample: a slab of columns sized so that K+W iterations take about two minutes;
+    # the iteration is bandwidth-bound on the host, so iterations/s scales with 1/columns.
+    probe_cols = 256
+    desc = syn.rof(probe_cols, NY, LAM)
+    o = OraclePDHG(OracleProblem(desc), stepsize="alg1", residual_iter=RESIDUAL_ITER,
+                   tol_rel_primal=0, tol_rel_dual=0, tol_abs_primal=0, tol_abs_dual=0)
+    o.initialize()
+    o.iterate(2)
+    t0 = time.perf_counter()
+    o.iterate(3)
+    t_iter_probe = (time.perf_counter() - t0) / 3
+    budget = 120.0
+    cols = int(min(NX, max(64, probe_cols * budget / max(t_iter_probe * (args.steps + args.warmup), 1e-9))))
+    cols = max(64, (cols // 64) * 64)
+    if cols != probe_cols:
+        desc = syn.rof(cols, NY, LAM)
+        o = OraclePDHG(OracleProblem(desc), stepsize="alg1", residual_iter=RESIDUAL_ITER,
+                       tol_rel_primal=0, tol_rel_dual=0, tol_abs_primal=0, tol_abs_dual=0)
+        o.initialize()
+    o.iterate(args.warmup)
+    t0 = time.perf_counter()
+    o.iterate(args.steps)
+    dt = time.perf_counter() - t0
+    frac = cols / NX
+    value = args.steps / dt * frac            # iterations/s of the FULL 4096^2 image
+    sample = f"{args.steps} iterations on a {cols}x{NY} column slab ({frac:.4f} of the image), scaled by area"
+    line = {
+        "impl": "reference", "metric": "pdhg_iterations_per_second", "value": value, "unit": "iter/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps / frac * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "iter/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    return {"workload": f"ROF-TV {NX}x{NY} gray, PDHG Alg1, BlockGradient2D + 1d:square(lambda={LAM:g}) + "
+                        f"norm2:ind_leq0, alpha=1 preconditioning, residual_iter={RESIDUAL_ITER}",
+            "n_pixels": NX * NY, "bytes_per_iteration_algorithmic": BYTES_PER_PX_ITER * NX * NY,
+            "cache": "state (x,x_prev,y,y_prev,f = 448 MB) exceeds the 126 MB L2; no flush needed",
+            "parallelism": f"slab{n_gpus}" if n_gpus > 1 else "single"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import prost_b200 as pb
+    from prost_b200 import synthetic as syn
+
+    if world > 1:
+        raise SystemExit("bench.py: the multi-GPU slab path is not built yet (round-1 work in progress)")
+
+    torch.cuda.set_device(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx = pb.Context(local_rank, stream.cuda_stream)
+
+    f = syn.image(NX, NY)
+    n, m = NX * NY, 2 * NX * NY
+
+    # ---------------- device-resident throughput (value) ----------------------------------------
+    prob = build_problem(pb, syn, ctx, f)
+    prob.Initialize()
+    popts = pb.pdhg_options(scale_steps_operator=0, stepsize="alg1", residual_iter=RESIDUAL_ITER)
+    sopts = pb.solver_options(verbose=0, max_iters=args.steps, tol_rel_primal=0, tol_rel_dual=0,
+                              tol_abs_primal=0, tol_abs_dual=0)
+    be = pb.BackendPDHG(ctx, prob, popts, sopts)
+    be.Initialize()
+    assert be.is_fused, "fused PDHG path not selected"
+    be.PerformIteration(args.warmup)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    launches0 = be.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    be.PerformIteration(args.steps)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = be.launch_count - launches0
+    clocks = sampler.stop()
+    value = args.steps / (ms * 1e-3)
+
+    # ---------------- per-kernel timing for the roofline (events around each pass) ------------------
+    prof_iters = min(200, max(20, args.steps // 10))
+    t_primal, t_dual, t_fin = be.profile(prof_iters)
+    peak, peak_src = measured_peak()
+    dual_bytes = BYTES_PER_PX_DUAL * n
+    primal_bytes = BYTES_PER_PX_PRIMAL * n
+    achieved_dual = dual_bytes / (t_dual * 1e-3) / 1e9
+    achieved_primal = primal_bytes / (t_primal * 1e-3) / 1e9
+    achieved_iter = BYTES_PER_PX_ITER * n * value / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": "prox_pass_kernel<2, DualSource> (fused dual pass)",
+        "achieved": achieved_dual, "peak": peak, "unit": "GB/s", "frac": achieved_dual / peak,
+        "traffic": None, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": dual_bytes, "ms_per_launch": t_dual,
+        "primal_pass": {"achieved": achieved_primal, "frac": achieved_primal / peak,
+                        "algorithmic_bytes_per_launch": primal_bytes, "ms_per_launch": t_primal},
+        "whole_iteration": {"achieved": achieved_iter, "frac": achieved_iter / peak,
+                            "frac_of_8TBs_nominal": achieved_iter / 8000.0},
+        "finalize_ms": t_fin,
+    }
+    res = be.residuals()
+    del be
+
+    # ---------------- end to end through the public API with host buffers (e2e) --------------------
+    f_pin = torch.from_numpy(f).pin_memory()
+    x0_pin = torch.zeros(n, dtype=torch.float32).pin_memory()
+    y0_pin = torch.zeros(m, dtype=torch.float32).pin_memory()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    prob2 = build_problem(pb, syn, ctx, f_pin.numpy())           # H2D: f (prox coefficient b)
+    be2 = pb.BackendPDHG(ctx, prob2, popts, sopts)
+    solver = pb.Solver(prob2, be2)
+    solver.SetOptions(sopts, x0=x0_pin.numpy(), y0=y0_pin.numpy())
+    solver.Initialize()                                          # scaling upload, x0 / y0 H2D
+    solver.Solve()                                               # K iterations + D2H of x, z, y, w
+    ctx.synchronize()
+    t_e2e = time.perf_counter() - t0
+    h2d = 4 * (n + n + m) + 4 * (n + m)          # f, x0 (x2 buffers share one upload each), y0, scaling
+    d2h = 4 * (2 * n + 2 * m)                    # x, w, y, z
+    e2e = {"value": args.steps / t_e2e, "unit": "iter/s", "h2d_bytes_per_step": h2d / args.steps,
+           "d2h_bytes_per_step": d2h / args.steps, "seconds_total": t_e2e,
+           "what": "Problem build + Solver.Initialize + Solver.Solve(max_iters=K) + solution copy-back"}
+    del be2, solver
+
+    # ---------------- CPU baseline (oracle port, bounded sample) ------------------------------------
+    cpu = None
+    if not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from oracle_binding import OracleProblem, OraclePDHG, num_threads
+        cols = 1024
+        o = OraclePDHG(OracleProblem(syn.rof(cols, NY, LAM)), stepsize="alg1", residual_iter=RESIDUAL_ITER,
+                       tol_rel_primal=0, tol_rel_dual=0, tol_abs_primal=0, tol_abs_dual=0)
+        o.initialize()
+        o.iterate(2)
+        t0 = time.perf_counter()
+        its = 0
+        while time.perf_counter() - t0 < 12.0:
+            o.iterate(5)
+            its += 5
+        dt = time.perf_counter() - t0
+        cpu = {"value": its / dt * cols / NX, "unit": "iter/s", "cores": num_threads(), "kind": "port",
+               "sample": f"{its} iterations of the OpenMP oracle on a {cols}x{NY} slab (1/{NX // cols} of the "
+                         f"image), scaled by area"}
+
+    line = {
+        "metric": "pdhg_iterations_per_second", "value": value, "unit": "iter/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(1), "clocks": clocks, "e2e": e2e,
+        "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        "residuals_after_run": res,
+    }
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,819 @@
+// oracle/prost_oracle.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// CPU restatement (C++/OpenMP) of the reference's PDHG hot path, used ONLY as the checker in
+// tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.  The
+// product (prost_b200/) never links, imports or calls anything in this directory.
+//
+// It follows the reference's UNFUSED structure and operation order (9 state vectors, one loop
+// per reference kernel) so that it can be read side by side with /root/reference:
+//   operators   src/linop/block_gradient2d.cu:25-139, block_gradient3d.cu:25-150,
+//               block_diags.cu:36-119, block_sparse.cu:33-68 (+ common.cu:54-82), block_dense.cu:82-188,
+//               linearoperator.cu:134-170, block.cu:46-68
+//   proxes      include/prost/prox/elemop/function_1d.hpp:34-326, elem_operation_1d.hpp:36-59,
+//               elem_operation_norm2.hpp:39-88, elem_operation_ind_simplex.hpp:47-115,
+//               src/prox/prox_ind_epi_quad.cu:42-79 + include/prost/prox/helper.hpp:44-105,
+//               src/prox/prox_moreau.cu:29-134, prox_permute.cu:30-145, prox_zero.cu:36-48,
+//               include/prost/prox/vector.hpp:42-48, prox_elem_operation.inl:32-94
+//   problem     src/problem.cu:92-158 (zero fill), :262-306 (scaling), :502-536 (averaging)
+//   PDHG        src/backend/backend_pdhg.cu:38-186, 199-309, 311-489, 513-563; backend.hpp:71-74
+// Parity pinning: against outputs of the reference itself (oracle/_ref, run on the GPU box) stored
+// under tests/golden/, and against the closed forms of the reference's MATLAB tests
+// (matlab/+prost/+test/*.m) restated in numpy inside tests/.
+//
+// Build: g++ -O2 -ffp-contract=off -fopenmp -shared -fPIC (see oracle/Makefile).
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace orc {
+
+typedef std::vector<float> vec;
+static thread_local std::string g_err;
+
+// ------------------------------------------------------------------------------------------------
+// Function1D family (function_1d.hpp)
+// ------------------------------------------------------------------------------------------------
+enum Fn { ZERO, ABS, SQUARE, IND_LEQ0, IND_GEQ0, IND_EQ0, IND_BOX01, MAX_POS0, L0, HUBER, LQ,
+          LQ_PLUS_EPS, TRUNC_QUAD, TRUNC_LINEAR };
+
+static float fn_abs(float x0, float tau) {                 // :50-62
+  if (x0 >= tau) return x0 - tau;
+  else if (x0 <= -tau) return x0 + tau;
+  return 0;
+}
+static float fn_square(float x0, float tau) { return x0 / (1. + tau); }   // :64-74 (double literal)
+static float fn_l0(float x0, float tau) { return (x0 * x0 > 2 * tau) ? x0 : 0; }   // :143-155
+
+static float lq_newton(float t0, float alpha, float q, float eps) {       // :171-191
+  float t = t0, delta = 0;
+  do {
+    const float power = std::pow(t, q);
+    const float dF1 = t - 1 + alpha * q * power / t;
+    const float dF2 = 1 + alpha * q * (q - 1) * power / (t * t);
+    delta = dF1 / dF2;
+    t = t - delta;
+  } while (delta > eps);
+  return t;
+}
+static float lq_half(float alpha) {                                        // :193-202
+  const float sqrt3 = std::sqrt(3.f);
+  const float PI_half = 1.5707963267948966192313216916397514420985846996875529f;
+  const float s = 2 * (std::sin((std::acos(alpha * 3 * sqrt3 / 4) + PI_half) / 3)) / sqrt3;
+  return s * s;
+}
+static float fn_lq(float x0, float tau, float alpha) {                     // :204-257
+  if (alpha == 1) return fn_abs(x0, tau);
+  if (alpha == 0) return fn_l0(x0, tau);
+  const float eps = 1e-5f;
+  float t = 0;
+  if (std::fabs(x0) > 0) {
+    float factor = tau * std::pow(std::fabs(x0), alpha - 2);
+    if (alpha < 1) {
+      const float t2 = 2 * (alpha - 1) / (alpha - 2);
+      if (factor < 0.5 * (1 - (t2 - 1) * (t2 - 1)) / std::pow(t2, alpha)) {
+        if (alpha == 0.5) t = lq_half(factor);
+        else t = lq_newton(1, factor, alpha, eps);
+      }
+    } else {
+      t = lq_newton(1, factor, alpha, eps);
+    }
+  }
+  return t * std::fabs(x0);
+}
+
+static float fn_eval(int fn, float x0, float tau, float alpha, float beta) {
+  switch (fn) {
+    case ZERO: return x0;
+    case ABS: return fn_abs(x0, tau);
+    case SQUARE: return fn_square(x0, tau);
+    case IND_LEQ0: return x0 > 0. ? 0.f : x0;
+    case IND_GEQ0: return x0 < 0. ? 0.f : x0;
+    case IND_EQ0: return 0;
+    case IND_BOX01: return x0 > 1. ? 1.f : (x0 < 0. ? 0.f : x0);
+    case MAX_POS0: return x0 > tau ? x0 - tau : (x0 < 0. ? x0 : 0.f);
+    case L0: return fn_l0(x0, tau);
+    case HUBER: {                                                          // :157-169
+      float result = (x0 / tau) / (1. + alpha / tau);
+      result /= std::max(1.f, std::fabs(result));
+      return x0 - tau * result;
+    }
+    case LQ: return fn_lq(x0, tau, alpha);
+    case LQ_PLUS_EPS: return 0;                                            // :293-306 (stub)
+    case TRUNC_QUAD: {                                                     // :273-291
+      const float x_sq = fn_square(x0, 2 * tau * alpha);
+      const float en_sq = alpha * x_sq * x_sq + (x_sq - x0) * (x_sq - x0) / (2 * tau);
+      return en_sq < beta ? x_sq : x0;
+    }
+    case TRUNC_LINEAR: {                                                   // :308-326
+      const float x_shrink = fn_abs(x0, tau * alpha);
+      const float en = (x_shrink - x0) * (x_shrink - x0) / (2 * tau) + alpha * std::fabs(x_shrink);
+      return en < beta ? x_shrink : x0;
+    }
+  }
+  return x0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Blocks
+// ------------------------------------------------------------------------------------------------
+struct Block {
+  size_t row, col, nrows, ncols;
+  Block(size_t r, size_t c, size_t nr, size_t nc) : row(r), col(c), nrows(nr), ncols(nc) {}
+  virtual ~Block() {}
+  virtual void eval_add(float* res, const float* rhs) const = 0;          // res += K rhs (local ptrs)
+  virtual void eval_adj_add(float* res, const float* rhs) const = 0;      // res += K^T rhs
+  virtual float row_sum(size_t r, float alpha) const = 0;
+  virtual float col_sum(size_t c, float alpha) const = 0;
+};
+
+struct BlockGradient : Block {      // block_gradient2d.cu / block_gradient3d.cu
+  size_t nx, ny, L;
+  bool label_first, three_d;
+  BlockGradient(size_t r, size_t c, size_t nx_, size_t ny_, size_t L_, bool lf, bool td)
+      : Block(r, c, nx_ * ny_ * L_ * (td ? 3 : 2), nx_ * ny_ * L_), nx(nx_), ny(ny_), L(L_),
+        label_first(lf), three_d(td) {}
+  void eval_add(float* res, const float* rhs) const override {
+    const size_t N = nx * ny * L;
+#pragma omp parallel for collapse(2) schedule(static)
+    for (size_t x = 0; x < nx; ++x)
+      for (size_t yt = 0; yt < ny * L; ++yt) {
+        size_t y, l, idx, idx_gx, idx_gy, idx_gl;
+        if (label_first) { l = yt % L; y = yt / L; idx = l + y * L + x * ny * L; idx_gy = idx + L; idx_gx = idx + ny * L; idx_gl = idx + 1; }
+        else { y = yt % ny; l = yt / ny; idx = y + x * ny + l * nx * ny; idx_gy = idx + 1; idx_gx = idx + ny; idx_gl = idx + ny * nx; }
+        const float val_pt = rhs[idx];
+        float gx = 0, gy = 0;
+        if (y < ny - 1) gy = rhs[idx_gy] - val_pt;
+        if (x < nx - 1) gx = rhs[idx_gx] - val_pt;
+        res[idx] += gx;
+        res[idx + N] += gy;
+        if (three_d) {
+          float gl;
+          if (l < L - 1) gl = rhs[idx_gl] - val_pt;
+          else gl = -val_pt;                                                // Dirichlet (3d:73-76)
+          res[idx + 2 * N] += gl;
+        }
+      }
+  }
+  void eval_adj_add(float* res, const float* rhs) const override {
+    const size_t N = nx * ny * L;
+#pragma omp parallel for collapse(2) schedule(static)
+    for (size_t x = 0; x < nx; ++x)
+      for (size_t yt = 0; yt < ny * L; ++yt) {
+        size_t y, l, idx, sy, sx, sl;
+        if (label_first) { y = yt / L; l = yt % L; idx = l + y * L + x * ny * L; sy = L; sx = ny * L; sl = 1; }
+        else { y = yt % ny; l = yt / ny; idx = y + x * ny + l * nx * ny; sy = 1; sx = ny; sl = nx * ny; }
+        float divx, divy;
+        if (y < ny - 1) divy = rhs[idx + N]; else divy = 0;
+        if (y > 0) divy -= rhs[idx + N - sy];
+        if (x < nx - 1) divx = rhs[idx]; else divx = 0;
+        if (x > 0) divx -= rhs[idx - sx];
+        if (!three_d) {
+          res[idx] -= (divx + divy);
+        } else {
+          float divl = rhs[idx + 2 * N];
+          if (l > 0) divl -= rhs[idx + 2 * N - sl];
+          res[idx] -= (divx + divy + divl);
+        }
+      }
+  }
+  float row_sum(size_t, float) const override { return 2; }
+  float col_sum(size_t, float) const override { return three_d ? 6 : 4; }
+};
+
+struct BlockDiags : Block {         // block_diags.cu
+  std::vector<long long> ofs;
+  std::vector<float> fac;
+  BlockDiags(size_t r, size_t c, size_t nr, size_t nc, size_t nd, const int64_t* o, const float* f)
+      : Block(r, c, nr, nc), ofs(o, o + nd), fac(f, f + nd) {
+    for (size_t i = 0; i < nd; i++)                                        // :110-118
+      for (size_t j = i; j < nd; j++)
+        if (ofs[i] > ofs[j]) { std::swap(ofs[i], ofs[j]); std::swap(fac[i], fac[j]); }
+  }
+  void eval_add(float* res, const float* rhs) const override {
+#pragma omp parallel for schedule(static)
+    for (size_t r = 0; r < nrows; ++r) {
+      float result = 0;
+      for (size_t i = 0; i < ofs.size(); i++) {
+        const long long c = (long long)r + ofs[i];
+        if (c < 0) continue;
+        if (c >= (long long)ncols) break;
+        result += rhs[c] * fac[i];
+      }
+      res[r] += result;
+    }
+  }
+  void eval_adj_add(float* res, const float* rhs) const override {
+    // all ncols columns (the reference launch is sized by nrows, block_diags.cu:211)
+#pragma omp parallel for schedule(static)
+    for (size_t c = 0; c < ncols; ++c) {
+      float result = 0;
+      for (size_t i = 0; i < ofs.size(); i++) {
+        const long long o = ofs[i], cc = (long long)c;
+        if (o <= cc && (cc - o) < (long long)nrows && (cc - o) >= 0) result += rhs[cc - o] * fac[i];
+        if (o > cc) break;
+      }
+      res[c] += result;
+    }
+  }
+  float row_sum(size_t r, float alpha) const override {
+    float sum = 0;
+    for (size_t i = 0; i < ofs.size(); i++) {
+      const long long c = (long long)r + ofs[i];
+      if (c < 0) continue;
+      if ((size_t)c >= ncols) break;
+      sum += std::pow(std::abs(fac[i]), alpha);
+    }
+    return sum;
+  }
+  float col_sum(size_t c, float alpha) const override {
+    float sum = 0;
+    const long long sc = (long long)c;
+    for (size_t i = 0; i < ofs.size(); i++) {
+      const long long o = ofs[i];
+      if (o <= sc && (sc - o) < (long long)nrows && (sc - o) >= 0) sum += std::pow(std::abs(fac[i]), alpha);
+      if (o > sc) break;
+    }
+    return sum;
+  }
+};
+
+struct BlockSparse : Block {        // block_sparse.cu (CSC in, CSR of K and of K^T kept)
+  std::vector<int> ptr, ind, ptr_t, ind_t;
+  vec val, val_t;
+  BlockSparse(size_t r, size_t c, int m, int n, int nnz, const float* v, const int32_t* p, const int32_t* i)
+      : Block(r, c, m, n), ptr_t(p, p + n + 1), ind_t(i, i + nnz), val_t(v, v + nnz) {
+    ptr.assign(m + 1, 0);
+    ind.resize(nnz);
+    val.resize(nnz);
+    for (int k = 0; k < nnz; ++k) ptr[ind_t[k] + 1]++;
+    for (int q = 0; q < m; ++q) ptr[q + 1] += ptr[q];
+    std::vector<int> pos(ptr.begin(), ptr.end() - 1);
+    for (int col_ = 0; col_ < n; ++col_)
+      for (int k = ptr_t[col_]; k < ptr_t[col_ + 1]; ++k) {
+        const int d = pos[ind_t[k]]++;
+        ind[d] = col_;
+        val[d] = val_t[k];
+      }
+  }
+  static void spmv(const std::vector<int>& p, const std::vector<int>& i, const vec& v, size_t rows,
+                   float* res, const float* x) {
+#pragma omp parallel for schedule(static)
+    for (size_t r = 0; r < rows; ++r) {
+      float acc = 0;
+      for (int k = p[r]; k < p[r + 1]; ++k) acc += v[k] * x[i[k]];
+      res[r] += acc;
+    }
+  }
+  void eval_add(float* res, const float* rhs) const override { spmv(ptr, ind, val, nrows, res, rhs); }
+  void eval_adj_add(float* res, const float* rhs) const override { spmv(ptr_t, ind_t, val_t, ncols, res, rhs); }
+  float row_sum(size_t r, float alpha) const override {
+    float s = 0;
+    for (int k = ptr[r]; k < ptr[r + 1]; ++k) s += std::pow(std::abs(val[k]), alpha);
+    return s;
+  }
+  float col_sum(size_t c, float alpha) const override {
+    float s = 0;
+    for (int k = ptr_t[c]; k < ptr_t[c + 1]; ++k) s += std::pow(std::abs(val_t[k]), alpha);
+    return s;
+  }
+};
+
+struct BlockDense : Block {         // block_dense.cu (column-major, gemv N / T)
+  vec a;
+  BlockDense(size_t r, size_t c, size_t nr, size_t nc, const float* d) : Block(r, c, nr, nc), a(d, d + nr * nc) {}
+  void eval_add(float* res, const float* rhs) const override {
+#pragma omp parallel for schedule(static)
+    for (size_t r = 0; r < nrows; ++r) {
+      double acc = 0;
+      for (size_t c = 0; c < ncols; ++c) acc += (double)a[c * nrows + r] * rhs[c];
+      res[r] += (float)acc;
+    }
+  }
+  void eval_adj_add(float* res, const float* rhs) const override {
+#pragma omp parallel for schedule(static)
+    for (size_t c = 0; c < ncols; ++c) {
+      double acc = 0;
+      for (size_t r = 0; r < nrows; ++r) acc += (double)a[c * nrows + r] * rhs[r];
+      res[c] += (float)acc;
+    }
+  }
+  float row_sum(size_t r, float alpha) const override {
+    float s = 0;
+    for (size_t c = 0; c < ncols; ++c) s += std::pow(std::abs(a[c * nrows + r]), alpha);
+    return s;
+  }
+  float col_sum(size_t c, float alpha) const override {
+    float s = 0;
+    for (size_t r = 0; r < nrows; ++r) s += std::pow(std::abs(a[c * nrows + r]), alpha);
+    return s;
+  }
+};
+
+struct BlockZero : Block {
+  using Block::Block;
+  void eval_add(float*, const float*) const override {}
+  void eval_adj_add(float*, const float*) const override {}
+  float row_sum(size_t, float) const override { return 0; }
+  float col_sum(size_t, float) const override { return 0; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Proxes
+// ------------------------------------------------------------------------------------------------
+struct Prox {
+  size_t index, size;
+  bool diagsteps;
+  Prox(size_t i, size_t s, bool d) : index(i), size(s), diagsteps(d) {}
+  virtual ~Prox() {}
+  size_t end() const { return index + size - 1; }
+  // local pointers (already offset by index), like Prox::EvalLocal
+  virtual void eval_local(float* res, const float* arg, const float* tau_diag, float tau, bool invert) = 0;
+  virtual void sep(std::vector<std::tuple<size_t, size_t, size_t>>& s) const { s.emplace_back(index, size, 1); }
+  void eval(float* res, const float* arg, const float* td, float tau, bool invert) {   // prox.cu:26-43
+    eval_local(res + index, arg + index, td + index, tau, invert);
+  }
+};
+
+struct ProxZero : Prox {            // prox_zero.cu
+  ProxZero(size_t i, size_t s) : Prox(i, s, true) {}
+  void eval_local(float* res, const float* arg, const float*, float, bool) override {
+    std::copy(arg, arg + size, res);
+  }
+};
+
+struct ProxSeparable : Prox {       // prox_separable_sum.hpp
+  size_t count, dim;
+  bool interleaved;
+  ProxSeparable(size_t i, size_t c, size_t d, bool il, bool ds) : Prox(i, c * d, ds), count(c), dim(d), interleaved(il) {}
+  size_t at(size_t tx, size_t i) const { return interleaved ? (tx * dim + i) : (tx + count * i); }   // vector.hpp:42-48
+  void sep(std::vector<std::tuple<size_t, size_t, size_t>>& s) const override {
+    for (size_t i = 0; i < count; i++) {
+      if (interleaved) s.emplace_back(index + i * dim, dim, 1);
+      else s.emplace_back(index + i, dim, count);
+    }
+  }
+};
+
+struct ProxElem7 : ProxSeparable {  // 1D and Norm2 families with 7 coefficients
+  int fn;
+  bool norm2;
+  vec coeffs[7];
+  ProxElem7(bool n2, size_t i, size_t c, size_t d, bool il, bool ds, int f, const float* const* co, const size_t* len)
+      : ProxSeparable(i, c, n2 ? d : 1, il, ds), fn(f), norm2(n2) {
+    for (int k = 0; k < 7; ++k) coeffs[k].assign(co[k], co[k] + len[k]);
+  }
+  void eval_local(float* res, const float* arg, const float* td, float tau_scal, bool invert) override {
+#pragma omp parallel for schedule(static)
+    for (size_t tx = 0; tx < count; ++tx) {
+      float c[7];
+      for (int k = 0; k < 7; ++k) c[k] = coeffs[k].size() > 1 ? coeffs[k][tx] : coeffs[k][0];   // inl:82-89
+      if (!norm2) {                                                        // elem_operation_1d.hpp:36-59
+        const size_t e = at(tx, 0);
+        float tau = invert ? (1. / (tau_scal * td[e])) : (tau_scal * td[e]);
+        if (c[0] == 0 || c[2] == 0) {
+          res[e] = (arg[e] - tau * c[3]) / (1 + tau * c[4]);
+        } else {
+          const float prox_arg = ((c[0] * (arg[e] - c[3] * tau)) / (1. + tau * c[4])) - c[1];
+          const float step = (c[2] * c[0] * c[0] * tau) / (1. + tau * c[4]);
+          res[e] = (fn_eval(fn, prox_arg, step, c[5], c[6]) + c[1]) / c[0];
+        }
+      } else {                                                             // elem_operation_norm2.hpp:39-88
+        float norm = 0;
+        for (size_t i = 0; i < dim; i++) { const float v = arg[at(tx, i)]; norm += v * v; }
+        if (norm > 0) {
+          norm = std::sqrt(norm);
+          const float t0 = td[at(tx, 0)];
+          float tau = invert ? (1. / (tau_scal * t0)) : (tau_scal * t0);
+          const float prox_arg = ((c[0] * (norm - c[3] * tau)) / (1. + tau * c[4])) - c[1];
+          const float step = (c[2] * c[0] * c[0] * tau) / (1. + tau * c[4]);
+          const float prox_result = (fn_eval(fn, prox_arg, step, c[5], c[6]) + c[1]) / c[0];
+          for (size_t i = 0; i < dim; i++) res[at(tx, i)] = prox_result * arg[at(tx, i)] / norm;
+        } else {
+          for (size_t i = 0; i < dim; i++) res[at(tx, i)] = 0;
+        }
+      }
+    }
+  }
+};
+
+struct ProxSimplex : ProxSeparable {   // elem_operation_ind_simplex.hpp:47-115
+  using ProxSeparable::ProxSeparable;
+  void eval_local(float* res, const float* arg, const float*, float, bool) override {
+#pragma omp parallel
+    {
+      vec local(dim);
+#pragma omp for schedule(static)
+      for (size_t tx = 0; tx < count; ++tx) {
+        for (size_t i = 0; i < dim; i++) local[i] = arg[at(tx, i)];
+        // descending shell sort with the reference's gap sequence (:94-115)
+        const int gaps[6] = {132, 57, 23, 10, 4, 1};
+        for (int k = 0; k < 6; k++) {
+          const int gap = gaps[k];
+          for (int i = gap; i < (int)dim; i++) {
+            const float temp = local[i];
+            int j = i;
+            for (; (j >= gap) && (local[j - gap] <= temp); j -= gap) local[j] = local[j - gap];
+            local[j] = temp;
+          }
+        }
+        bool bget = false;
+        float tmpsum = 0, tmax = 0;
+        for (int ii = 1; ii <= (int)dim - 1; ii++) {
+          tmpsum += local[ii - 1];
+          tmax = (tmpsum - 1.) / (float)ii;
+          if (tmax >= local[ii]) { bget = true; break; }
+        }
+        if (!bget) tmax = (tmpsum + local[dim - 1] - 1.0) / (float)dim;
+        for (size_t i = 0; i < dim; i++) res[at(tx, i)] = std::max(arg[at(tx, i)] - tmax, 0.f);
+      }
+    }
+  }
+};
+
+// helper.hpp:44-105 (x0 and x alias the same planar storage in the caller, like the reference)
+static void project_epi_quad_nd(float* xbase, size_t stride, size_t dim, float y0, float alpha, float& y) {
+  float sq_norm_x0 = 0;
+  for (size_t i = 0; i < dim; i++) sq_norm_x0 += xbase[i * stride] * xbase[i * stride];
+  const float norm_x0 = std::sqrt(sq_norm_x0);
+  if (y0 >= alpha * sq_norm_x0) { y = y0; return; }
+  const float a = 2. * alpha * norm_x0;
+  const float b = 2. * (1. - 2. * alpha * y0) / 3.;
+  float d, v;
+  if (b < 0) {
+    const float sq = std::pow(-b, static_cast<float>(3. / 2.));
+    d = (a - sq) * (a + sq);
+  } else {
+    d = a * a + b * b * b;
+  }
+  if (d >= 0) {
+    const float c = std::pow(a + std::sqrt(d), static_cast<float>(1. / 3.));
+    if (std::fabs(c) > 1e-6) v = c - b / c;
+    else v = 0;
+  } else {
+    v = 2 * std::sqrt(-b) * std::cos(std::acos(a / std::pow(-b, static_cast<float>(3. / 2.))) / static_cast<float>(3.));
+  }
+  if (norm_x0 > 0) {
+    for (size_t i = 0; i < dim; i++) xbase[i * stride] = (v / (2. * alpha)) * (xbase[i * stride] / norm_x0);
+  } else {
+    for (size_t i = 0; i < dim; i++) xbase[i * stride] = 0;
+  }
+  float sq_norm_x = 0;
+  for (size_t i = 0; i < dim; i++) sq_norm_x += xbase[i * stride] * xbase[i * stride];
+  y = alpha * sq_norm_x;
+}
+
+struct ProxEpiQuad : ProxSeparable {   // prox_ind_epi_quad.cu:42-79 (always planar)
+  vec a, b, c;
+  ProxEpiQuad(size_t i, size_t cnt, size_t d, bool il, bool ds, const float* a_, size_t na, const float* b_,
+              size_t nb, const float* c_, size_t nc)
+      : ProxSeparable(i, cnt, d, il, ds), a(a_, a_ + na), b(b_, b_ + nb), c(c_, c_ + nc) {}
+  void eval_local(float* res, const float* arg, const float*, float, bool) override {
+#pragma omp parallel for schedule(static)
+    for (size_t tx = 0; tx < count; ++tx) {
+      const size_t dx = dim - 1;
+      float* x = res + tx;                       // stride count
+      const float y0 = arg[count * dx + tx];
+      const float av = a.size() == 1 ? a[0] : a[tx];
+      const float cv = c.size() == 1 ? c[0] : c[tx];
+      float sq_norm_b = 0;
+      for (size_t i = 0; i < dx; i++) {
+        const float val = b[tx + count * i];
+        x[i * count] = arg[tx + count * i] + (val / (2 * av));
+        sq_norm_b += val * val;
+      }
+      float y;
+      project_epi_quad_nd(x, count, dx, y0 - cv + (sq_norm_b / (4 * av)), av, y);
+      for (size_t i = 0; i < dx; i++) x[i * count] -= b[tx + count * i] / (2 * av);
+      res[count * dx + tx] = y + cv - (sq_norm_b / (4 * av));
+    }
+  }
+};
+
+struct ProxMoreau : Prox {          // prox_moreau.cu:98-134
+  std::shared_ptr<Prox> inner;
+  vec scaled;
+  explicit ProxMoreau(std::shared_ptr<Prox> p) : Prox(p->index, p->size, p->diagsteps), inner(p), scaled(p->size) {}
+  void sep(std::vector<std::tuple<size_t, size_t, size_t>>& s) const override { inner->sep(s); }
+  void eval_local(float* res, const float* arg, const float* td, float tau, bool invert) override {
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < size; ++i) scaled[i] = invert ? arg[i] * (tau * td[i]) : arg[i] / (tau * td[i]);
+    inner->eval_local(res, scaled.data(), td, tau, !invert);
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < size; ++i) {
+      if (invert) res[i] = arg[i] - res[i] / (tau * td[i]);
+      else res[i] = arg[i] - tau * td[i] * res[i];
+    }
+  }
+};
+
+struct ProxPermute : Prox {         // prox_permute.cu:101-145
+  std::shared_ptr<Prox> inner;
+  std::vector<int> perm;
+  vec permuted;
+  ProxPermute(std::shared_ptr<Prox> p, const int* pm, size_t n)
+      : Prox(p->index, p->size, p->diagsteps), inner(p), perm(pm, pm + n), permuted(n) {}
+  void sep(std::vector<std::tuple<size_t, size_t, size_t>>& s) const override { inner->sep(s); }
+  void eval_local(float* res, const float* arg, const float* td, float tau, bool invert) override {
+    for (size_t i = 0; i < perm.size(); ++i) res[i] = arg[perm[i]];
+    inner->eval_local(permuted.data(), res, td, tau, invert);
+    for (size_t i = 0; i < perm.size(); ++i) res[perm[i]] = permuted[i];
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Problem + PDHG
+// ------------------------------------------------------------------------------------------------
+struct Problem {
+  std::vector<std::shared_ptr<Block>> blocks;
+  std::vector<std::shared_ptr<Prox>> pool;                  // every prox ever created (ids)
+  std::vector<std::shared_ptr<Prox>> prox[4];               // g, f, gstar, fstar
+  size_t nrows = 0, ncols = 0, lin_rows = 0, lin_cols = 0;
+  bool dims_set = false;
+  int scaling = 1;                                          // 0 identity, 1 alpha, 2 custom
+  float alpha = 1;
+  vec left, right;
+
+  void linop(float* res, const float* rhs, bool transpose) const {     // linearoperator.cu:134-170, beta = 0
+    std::fill(res, res + (transpose ? ncols : nrows), 0.f);
+    for (auto& b : blocks) {
+      if (transpose) b->eval_adj_add(res + b->col, rhs + b->row);
+      else b->eval_add(res + b->row, rhs + b->col);
+    }
+  }
+  float row_sum(size_t r, float al) const {
+    float s = 0;
+    for (auto& b : blocks) { if (r < b->row || r >= b->row + b->nrows) continue; s += b->row_sum(r - b->row, al); }
+    return s;
+  }
+  float col_sum(size_t c, float al) const {
+    float s = 0;
+    for (auto& b : blocks) { if (c < b->col || c >= b->col + b->ncols) continue; s += b->col_sum(c - b->col, al); }
+    return s;
+  }
+  static void add_zero(std::vector<std::shared_ptr<Prox>>& ps, size_t n) {   // problem.cu:92-158
+    if (ps.empty()) return;
+    auto s = ps;
+    std::sort(s.begin(), s.end(), [](auto& a, auto& b) { return a->index < b->index; });
+    if (s[0]->index > 0) ps.push_back(std::make_shared<ProxZero>(0, s[0]->index));
+    for (size_t i = 0; i + 1 < s.size(); i++)
+      if (s[i]->end() < s[i + 1]->index - 1)
+        ps.push_back(std::make_shared<ProxZero>(s[i]->end() + 1, s[i + 1]->index - s[i]->end() - 1));
+    if (s.back()->end() < n - 1) ps.push_back(std::make_shared<ProxZero>(s.back()->end() + 1, (n - 1) - s.back()->end()));
+  }
+  static void average(vec& pre, const std::vector<std::shared_ptr<Prox>>& ps) {   // problem.cu:502-536
+    std::vector<std::tuple<size_t, size_t, size_t>> ics;
+    for (auto& p : ps) if (!p->diagsteps) p->sep(ics);
+    for (auto& t : ics) {
+      const size_t idx = std::get<0>(t), cnt = std::get<1>(t), st = std::get<2>(t);
+      float avg = 0;
+      for (size_t c = 0; c < cnt; c++) avg += pre[idx + c * st];
+      avg /= static_cast<float>(cnt);
+      for (size_t c = 0; c < cnt; c++) pre[idx + c * st] = avg;
+    }
+  }
+  int initialize() {
+    lin_rows = lin_cols = 0;
+    for (auto& b : blocks) { lin_rows = std::max(lin_rows, b->row + b->nrows); lin_cols = std::max(lin_cols, b->col + b->ncols); }
+    if (!dims_set) { nrows = lin_rows; ncols = lin_cols; }
+    if (lin_rows > nrows || lin_cols > ncols) { g_err = "linear operator larger than variables"; return -1; }
+    add_zero(prox[1], nrows); add_zero(prox[0], ncols); add_zero(prox[3], nrows); add_zero(prox[2], ncols);
+    if (scaling == 1) {                                     // problem.cu:262-287
+      left.assign(nrows, 0); right.assign(ncols, 0);
+      float value = 1;
+      for (size_t r = 0; r < nrows; r++) { const float rs = row_sum(r, alpha); if (rs > 0) value = 1. / rs; left[r] = value; }
+      for (size_t c = 0; c < ncols; c++) { const float cs = col_sum(c, 2. - alpha); if (cs > 0) value = 1. / cs; right[c] = value; }
+    } else if (scaling == 0) {
+      left.assign(nrows, 1); right.assign(ncols, 1);
+    } else if (left.size() != nrows || right.size() != ncols) {
+      g_err = "custom scaling has wrong size"; return -1;
+    }
+    average(right, prox[0].empty() ? prox[2] : prox[0]);
+    average(left, prox[1].empty() ? prox[3] : prox[1]);
+    return 0;
+  }
+};
+
+struct Pdhg {
+  Problem* P;
+  // options
+  double tau0, sigma0; int residual_iter; float alg2_gamma, arg_alpha0, arg_nu, arg_delta, arb_delta, arb_tau; int variant;
+  float tol_rel_p, tol_rel_d, tol_abs_p, tol_abs_d;
+  // state (backend_pdhg.hpp:105-156)
+  vec x, y, x_prev, y_prev, temp, kx, kty, kx_prev, kty_prev;
+  float tau, sigma, theta, arg_alpha; int arb_l, arb_u; size_t iteration;
+  float primal_residual = 0, dual_residual = 0, primal_var_norm = 0, dual_var_norm = 0;
+  std::vector<std::shared_ptr<Prox>> prox_g, prox_fstar;
+
+  float eps_primal() const { return std::sqrt(P->nrows) * tol_abs_p + tol_rel_p * primal_var_norm; }   // backend.hpp:71
+  float eps_dual() const { return std::sqrt(P->ncols) * tol_abs_d + tol_rel_d * dual_var_norm; }       // backend.hpp:74
+
+  int init(const float* x0, size_t nx0, const float* y0, size_t ny0) {     // :199-309 (no normest)
+    const size_t m = P->nrows, n = P->ncols;
+    x.assign(n, 0); x_prev.assign(n, 0); kty.assign(n, 0); kty_prev.assign(n, 0);
+    y.assign(m, 0); y_prev.assign(m, 0); kx.assign(m, 0); kx_prev.assign(m, 0); temp.assign(std::max(m, n), 0);
+    iteration = 0; tau = tau0; sigma = sigma0; theta = 1; arb_l = arb_u = 0; arg_alpha = arg_alpha0;
+    prox_g.clear(); prox_fstar.clear();
+    if (P->prox[0].empty()) { if (P->prox[2].empty()) { g_err = "Neither prox_g nor prox_gstar specified."; return -1; }
+      for (auto& p : P->prox[2]) prox_g.push_back(std::make_shared<ProxMoreau>(p)); } else prox_g = P->prox[0];
+    if (P->prox[3].empty()) { if (P->prox[1].empty()) { g_err = "Neither prox_f nor prox_fstar specified."; return -1; }
+      for (auto& p : P->prox[1]) prox_fstar.push_back(std::make_shared<ProxMoreau>(p)); } else prox_fstar = P->prox[3];
+    if (nx0) { if (nx0 != n) { g_err = "Initial primal solution has wrong size."; return -1; } x.assign(x0, x0 + n); x_prev = x; }
+    if (ny0) { if (ny0 != m) { g_err = "Initial dual solution has wrong size."; return -1; } y.assign(y0, y0 + m); y_prev = y; }
+    return 0;
+  }
+
+  void iterate() {                                          // PerformIteration :311-381
+    const size_t m = P->nrows, n = P->ncols;
+    const float* T = P->right.data();
+    const float* S = P->left.data();
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; ++i) temp[i] = x[i] - tau * T[i] * kty[i];                       // :38-51
+    x.swap(x_prev);
+    for (auto& p : prox_g) p->eval(x.data(), temp.data(), T, tau, false);
+    kx.swap(kx_prev);
+    P->linop(kx.data(), x.data(), false);
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < m; ++i) temp[i] = y[i] + sigma * S[i] * ((1 + theta) * kx[i] - theta * kx_prev[i]);   // :54-70
+    y.swap(y_prev);
+    for (auto& p : prox_fstar) p->eval(y.data(), temp.data(), S, sigma, false);
+    update_residuals_and_stepsizes();
+    iteration++;
+    kty.swap(kty_prev);
+    P->linop(kty.data(), y.data(), true);
+  }
+
+  void update_residuals_and_stepsizes() {                   // :383-489
+    const size_t m = P->nrows, n = P->ncols;
+    const float* T = P->right.data();
+    const float* S = P->left.data();
+    if (iteration == 0 || (iteration % (size_t)(long long)residual_iter) == 0) {
+      double p0 = 0, p1 = 0, d0 = 0, d1 = 0;
+#pragma omp parallel for schedule(static) reduction(+ : p0, p1)
+      for (size_t i = 0; i < m; ++i) {                      // primal_residual_transform :97-120
+        const float sd = S[i];
+        const float z_hat = (y_prev[i] - y[i]) / (sigma * std::sqrt(sd)) + std::sqrt(sd) * ((1 + theta) * kx[i] - theta * kx_prev[i]);
+        const float diff = z_hat - std::sqrt(sd) * kx[i];
+        p0 += diff * diff; p1 += z_hat * z_hat;
+      }
+#pragma omp parallel for schedule(static) reduction(+ : d0, d1)
+      for (size_t i = 0; i < n; ++i) {                      // dual_residual_transform :73-94
+        const float td = T[i];
+        const float w_hat = (x_prev[i] - x[i]) / (tau * std::sqrt(td)) - std::sqrt(td) * kty_prev[i];
+        const float diff = w_hat + std::sqrt(td) * kty[i];
+        d0 += diff * diff; d1 += w_hat * w_hat;
+      }
+      primal_residual = std::sqrt((float)p0); primal_var_norm = std::sqrt((float)p1);
+      dual_residual = std::sqrt((float)d0); dual_var_norm = std::sqrt((float)d1);
+      const float eps_p = eps_primal(), eps_d = eps_dual();
+      if (variant == 3) {                                   // Goldstein :443-460
+        const float scale = eps_d / eps_p;
+        if (dual_residual > (scale * primal_residual * arg_delta)) { tau = tau / (1 - arg_alpha); sigma = sigma * (1 - arg_alpha); arg_alpha = arg_alpha * arg_nu; }
+        if (dual_residual < (scale * primal_residual / arg_delta)) { tau = tau * (1 - arg_alpha); sigma = sigma / (1 - arg_alpha); arg_alpha = arg_alpha * arg_nu; }
+      } else if (variant == 4) {                            // Boyd :462-476
+        if ((dual_residual < eps_d) && (arb_tau * iteration > arb_l)) { tau /= arb_delta; sigma *= arb_delta; arb_u = iteration; }
+        else if ((primal_residual < eps_p) && (arb_tau * iteration > arb_u)) { tau *= arb_delta; sigma /= arb_delta; arb_l = iteration; }
+      }
+    }
+    if (variant == 2) {                                     // Alg2 :483-488
+      theta = 1. / std::sqrt(1. + 2. * alg2_gamma * tau);
+      tau = theta * tau;
+      sigma = sigma / theta;
+    }
+  }
+
+  void solution(float* hx, float* hz, float* hy, float* hw) {   // current_solution :513-563
+    const size_t m = P->nrows, n = P->ncols;
+    if (hx) std::copy(x.begin(), x.end(), hx);
+    if (hy) std::copy(y.begin(), y.end(), hy);
+    if (hw) for (size_t i = 0; i < n; ++i) hw[i] = (x_prev[i] - x[i]) / (P->right[i] * tau) - kty_prev[i];
+    if (hz) for (size_t i = 0; i < m; ++i) hz[i] = (y_prev[i] - y[i]) / (sigma * P->left[i]) + (1 + theta) * kx[i] - theta * kx_prev[i];
+  }
+};
+
+}  // namespace orc
+
+// ------------------------------------------------------------------------------------------------
+// C interface for ctypes
+// ------------------------------------------------------------------------------------------------
+using namespace orc;
+extern "C" {
+
+const char* orc_last_error() { return g_err.c_str(); }
+int orc_num_threads() {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
+void* orc_problem_new() { return new Problem(); }
+void orc_problem_free(void* p) { delete static_cast<Problem*>(p); }
+#define PP static_cast<Problem*>(p)
+
+void orc_add_gradient(void* p, int three_d, size_t row, size_t col, size_t nx, size_t ny, size_t L, int lf) {
+  PP->blocks.push_back(std::make_shared<BlockGradient>(row, col, nx, ny, L, lf != 0, three_d != 0));
+}
+void orc_add_diags(void* p, size_t row, size_t col, size_t nr, size_t nc, size_t nd, const int64_t* o, const float* f) {
+  PP->blocks.push_back(std::make_shared<BlockDiags>(row, col, nr, nc, nd, o, f));
+}
+void orc_add_sparse_csc(void* p, size_t row, size_t col, int m, int n, int nnz, const float* v, const int32_t* ptr, const int32_t* ind) {
+  PP->blocks.push_back(std::make_shared<BlockSparse>(row, col, m, n, nnz, v, ptr, ind));
+}
+void orc_add_dense(void* p, size_t row, size_t col, size_t nr, size_t nc, const float* d) {
+  PP->blocks.push_back(std::make_shared<BlockDense>(row, col, nr, nc, d));
+}
+void orc_add_zero(void* p, size_t row, size_t col, size_t nr, size_t nc) {
+  PP->blocks.push_back(std::make_shared<BlockZero>(row, col, nr, nc));
+}
+
+static int push(Problem* P, std::shared_ptr<Prox> q) { P->pool.push_back(q); return (int)P->pool.size() - 1; }
+int orc_prox_elem(void* p, int norm2, size_t idx, size_t count, size_t dim, int il, int ds, int fn,
+                  const float* const* coeffs, const size_t* len) {
+  return push(PP, std::make_shared<ProxElem7>(norm2 != 0, idx, count, dim, il != 0, ds != 0, fn, coeffs, len));
+}
+int orc_prox_simplex(void* p, size_t idx, size_t count, size_t dim, int il, int ds) {
+  return push(PP, std::make_shared<ProxSimplex>(idx, count, dim, il != 0, ds != 0));
+}
+int orc_prox_epi_quad(void* p, size_t idx, size_t count, size_t dim, int il, int ds, const float* a, size_t na,
+                      const float* b, size_t nb, const float* c, size_t nc) {
+  return push(PP, std::make_shared<ProxEpiQuad>(idx, count, dim, il != 0, ds != 0, a, na, b, nb, c, nc));
+}
+int orc_prox_moreau(void* p, int inner) { return push(PP, std::make_shared<ProxMoreau>(PP->pool[inner])); }
+int orc_prox_permute(void* p, int inner, const int* perm, size_t n) {
+  return push(PP, std::make_shared<ProxPermute>(PP->pool[inner], perm, n));
+}
+int orc_prox_zero(void* p, size_t idx, size_t size) { return push(PP, std::make_shared<ProxZero>(idx, size)); }
+void orc_set_prox(void* p, int which, int id) { PP->prox[which].push_back(PP->pool[id]); }
+void orc_set_dims(void* p, size_t nrows, size_t ncols) { PP->nrows = nrows; PP->ncols = ncols; PP->dims_set = true; }
+void orc_set_scaling_alpha(void* p, float a) { PP->scaling = 1; PP->alpha = a; }
+void orc_set_scaling_identity(void* p) { PP->scaling = 0; }
+void orc_set_scaling_custom(void* p, const float* l, size_t nl, const float* r, size_t nr) {   // problem.cu:344-364
+  PP->scaling = 2;
+  PP->left.resize(nl); PP->right.resize(nr);
+  for (size_t i = 0; i < nl; ++i) PP->left[i] = l[i] * l[i];
+  for (size_t i = 0; i < nr; ++i) PP->right[i] = r[i] * r[i];
+}
+int orc_initialize(void* p) { return PP->initialize(); }
+size_t orc_nrows(void* p) { return PP->nrows; }
+size_t orc_ncols(void* p) { return PP->ncols; }
+// sizes of the operator alone (usable before orc_initialize)
+void orc_linop_size(void* p, size_t* nrows, size_t* ncols) {
+  size_t r = 0, c = 0;
+  for (auto& b : PP->blocks) { r = std::max(r, b->row + b->nrows); c = std::max(c, b->col + b->ncols); }
+  *nrows = r; *ncols = c;
+}
+void orc_linop_eval(void* p, float* res, const float* rhs, int transpose) {
+  if (PP->nrows == 0 && PP->ncols == 0) orc_linop_size(p, &PP->nrows, &PP->ncols);
+  PP->linop(res, rhs, transpose != 0);
+}
+void orc_row_sums(void* p, float alpha, float* out, size_t n) { for (size_t r = 0; r < n; ++r) out[r] = PP->row_sum(r, alpha); }
+void orc_col_sums(void* p, float alpha, float* out, size_t n) { for (size_t c = 0; c < n; ++c) out[c] = PP->col_sum(c, alpha); }
+void orc_get_scaling(void* p, float* l, float* r) {
+  std::copy(PP->left.begin(), PP->left.end(), l);
+  std::copy(PP->right.begin(), PP->right.end(), r);
+}
+void orc_prox_eval(void* p, int id, float* res, const float* arg, const float* td, float tau, int invert) {
+  PP->pool[id]->eval(res, arg, td, tau, invert != 0);
+}
+
+void* orc_pdhg_new(void* p, double tau0, double sigma0, int residual_iter, float alg2_gamma, float arg_alpha0,
+                   float arg_nu, float arg_delta, float arb_delta, float arb_tau, int variant, float tol_rel_p,
+                   float tol_rel_d, float tol_abs_p, float tol_abs_d) {
+  Pdhg* s = new Pdhg();
+  s->P = PP;
+  s->tau0 = tau0; s->sigma0 = sigma0; s->residual_iter = residual_iter; s->alg2_gamma = alg2_gamma;
+  s->arg_alpha0 = arg_alpha0; s->arg_nu = arg_nu; s->arg_delta = arg_delta; s->arb_delta = arb_delta;
+  s->arb_tau = arb_tau; s->variant = variant;
+  s->tol_rel_p = tol_rel_p; s->tol_rel_d = tol_rel_d; s->tol_abs_p = tol_abs_p; s->tol_abs_d = tol_abs_d;
+  return s;
+}
+#define SS static_cast<Pdhg*>(s)
+void orc_pdhg_free(void* s) { delete SS; }
+int orc_pdhg_init(void* s, const float* x0, size_t nx0, const float* y0, size_t ny0) { return SS->init(x0, nx0, y0, ny0); }
+void orc_pdhg_iterate(void* s, int n) { for (int i = 0; i < n; ++i) SS->iterate(); }
+void orc_pdhg_residuals(void* s, float* out) {
+  out[0] = SS->primal_residual; out[1] = SS->dual_residual; out[2] = SS->primal_var_norm; out[3] = SS->dual_var_norm;
+  out[4] = SS->eps_primal(); out[5] = SS->eps_dual();
+}
+void orc_pdhg_stepsizes(void* s, double* out) { out[0] = SS->tau; out[1] = SS->sigma; out[2] = SS->theta; }
+void orc_pdhg_solution(void* s, float* x, float* z, float* y, float* w) { SS->solution(x, z, y, w); }
+
+}  // extern "C"

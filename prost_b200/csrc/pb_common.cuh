@@ -1,0 +1,151 @@
+// pb_common.cuh -- context, error plumbing and device buffers shared by all translation units.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <memory>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "prost_b200.h"
+
+namespace pb {
+
+// Host-side error type; converted to pb_status + pb_last_error() at the C boundary.
+// The message prefixes follow the strings the reference throws (exception.hpp:29-41).
+struct Error : public std::runtime_error {
+  int status;
+  Error(int st, const std::string& msg) : std::runtime_error(msg), status(st) {}
+};
+
+[[noreturn]] inline void fail(int status, const std::string& msg) { throw Error(status, msg); }
+
+#define PB_CUDA(expr)                                                                   \
+  do {                                                                                  \
+    cudaError_t pb_err__ = (expr);                                                      \
+    if (pb_err__ != cudaSuccess) {                                                      \
+      std::ostringstream pb_ss__;                                                       \
+      pb_ss__ << "CUDA error: " << cudaGetErrorString(pb_err__) << " (" << #expr << " at " \
+              << __FILE__ << ":" << __LINE__ << ")";                                    \
+      ::pb::fail(pb_err__ == cudaErrorMemoryAllocation ? PB_ERR_OOM : PB_ERR_CUDA,      \
+                 pb_ss__.str());                                                        \
+    }                                                                                   \
+  } while (0)
+
+#define PB_CHECK_LAUNCH() PB_CUDA(cudaGetLastError())
+
+constexpr int kNumSMs = 148;          // B200: 2 dies x 74 SMs
+constexpr int kBlock = 256;           // threads per CTA for the streaming kernels
+
+struct Context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool owns_stream = false;
+  int num_sms = kNumSMs;
+  unsigned long long launches = 0;    // kernels launched through this context
+
+  void bind() const { PB_CUDA(cudaSetDevice(device)); }
+};
+
+// RAII device allocation (replaces thrust::device_vector members of the reference).
+template <typename T>
+class DeviceBuffer {
+ public:
+  DeviceBuffer() = default;
+  explicit DeviceBuffer(size_t n) { resize(n); }
+  DeviceBuffer(const DeviceBuffer&) = delete;
+  DeviceBuffer& operator=(const DeviceBuffer&) = delete;
+  DeviceBuffer(DeviceBuffer&& o) noexcept : ptr_(o.ptr_), n_(o.n_) { o.ptr_ = nullptr; o.n_ = 0; }
+  DeviceBuffer& operator=(DeviceBuffer&& o) noexcept {
+    if (this != &o) { release(); ptr_ = o.ptr_; n_ = o.n_; o.ptr_ = nullptr; o.n_ = 0; }
+    return *this;
+  }
+  ~DeviceBuffer() { release(); }
+
+  void resize(size_t n) {
+    release();
+    if (n == 0) return;
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      std::ostringstream ss;
+      ss << "Out of memory: cudaMalloc of " << n * sizeof(T) << " bytes failed ("
+         << cudaGetErrorString(e) << ")";
+      fail(e == cudaErrorMemoryAllocation ? PB_ERR_OOM : PB_ERR_CUDA, ss.str());
+    }
+    ptr_ = static_cast<T*>(p);
+    n_ = n;
+  }
+  void release() {
+    if (ptr_) cudaFree(ptr_);
+    ptr_ = nullptr;
+    n_ = 0;
+  }
+  void zero(cudaStream_t s) { if (n_) PB_CUDA(cudaMemsetAsync(ptr_, 0, n_ * sizeof(T), s)); }
+  void upload(const T* h, size_t n, cudaStream_t s) {
+    if (n > n_) fail(PB_ERR_INVALID, "DeviceBuffer::upload: size mismatch");
+    if (n) PB_CUDA(cudaMemcpyAsync(ptr_, h, n * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  void download(T* h, size_t n, cudaStream_t s) const {
+    if (n > n_) fail(PB_ERR_INVALID, "DeviceBuffer::download: size mismatch");
+    if (n) PB_CUDA(cudaMemcpyAsync(h, ptr_, n * sizeof(T), cudaMemcpyDeviceToHost, s));
+  }
+  void assign(const std::vector<T>& h, cudaStream_t s) {
+    resize(h.size());
+    upload(h.data(), h.size(), s);
+    PB_CUDA(cudaStreamSynchronize(s));   // h may be a temporary
+  }
+  T* data() { return ptr_; }
+  const T* data() const { return ptr_; }
+  size_t size() const { return n_; }
+  void swap(DeviceBuffer& o) { std::swap(ptr_, o.ptr_); std::swap(n_, o.n_); }
+
+ private:
+  T* ptr_ = nullptr;
+  size_t n_ = 0;
+};
+
+// grid size for a 1-thread-per-item streaming kernel
+inline unsigned grid_for(size_t items, int block = kBlock) {
+  size_t g = (items + block - 1) / block;
+  if (g == 0) g = 1;
+  if (g > 0x7fffffffull) fail(PB_ERR_INVALID, "problem too large for a 1-D grid");
+  return static_cast<unsigned>(g);
+}
+
+// 31-bit division by a runtime constant via multiply-high (Granlund-Montgomery): with
+// s = ceil(log2 d) and m = ceil(2^(31+s) / d) (fits 32 bits), n / d == umulhi(n, m) >> (s-1)
+// exactly for every n < 2^31.  Used to decode (x, y, l) from linear indices without the
+// ~20-instruction hardware udiv sequence per element.
+struct FastDiv {
+  uint32_t d = 1, mul = 0, shift = 0;
+  FastDiv() = default;
+  explicit FastDiv(uint64_t div64) {
+    if (div64 == 0 || div64 >= (1ull << 31)) fail(PB_ERR_INVALID, "FastDiv: divisor out of range");
+    d = static_cast<uint32_t>(div64);
+    if (d == 1) return;
+    uint32_t s = 0;
+    while ((1ull << s) < d) ++s;
+    mul = static_cast<uint32_t>(((1ull << (31 + s)) + d - 1) / d);
+    shift = s - 1;
+  }
+  __host__ __device__ __forceinline__ uint32_t div(uint32_t n) const {
+    if (d == 1) return n;
+#ifdef __CUDA_ARCH__
+    return __umulhi(n, mul) >> shift;
+#else
+    return static_cast<uint32_t>((static_cast<uint64_t>(n) * mul) >> 32) >> shift;
+#endif
+  }
+  __host__ __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const {
+    q = div(n);
+    r = n - q * d;
+  }
+};
+
+}  // namespace pb

@@ -1,0 +1,584 @@
+// pb_linop.cu -- block objects and the unfused operator applies (LinearOperator::Eval /
+// EvalAdjoint of the reference, linearoperator.cu:134-170).  The fused PDHG passes in
+// pb_fused.cu evaluate the same pointwise products from pb_linop.cuh directly.
+#include "pb_linop.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+namespace pb {
+
+// ---- kernels ----------------------------------------------------------------------------------
+
+// res[i] += (K rhs)[i] or (K^T rhs)[i], one thread per output element.
+template <bool kTranspose>
+__global__ void __launch_bounds__(kBlock) block_apply_add_kernel(BlockDesc b, float* __restrict__ res,
+                                                                  const float* __restrict__ rhs,
+                                                                  float sign) {
+  const uint32_t n = kTranspose ? b.ncols : b.nrows;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float v = kTranspose ? block_col_dot(b, i, rhs) : block_row_dot(b, i, rhs);
+    res[i] += sign * v;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) scale_kernel(float* __restrict__ v, size_t n, float beta) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x)
+    v[i] = beta * v[i];
+}
+
+// CSR SpMV, one warp per row: lanes stride the row's nonzeros (coalesced val/ind reads),
+// shuffle-reduce, lane 0 accumulates.  res[r] += sign * sum_k val[k] * x[ind[k]].
+__global__ void __launch_bounds__(kBlock) csr_spmv_add_kernel(const int* __restrict__ ptr,
+                                                               const int* __restrict__ ind,
+                                                               const float* __restrict__ val,
+                                                               uint32_t nrows, float* __restrict__ res,
+                                                               const float* __restrict__ x, float sign) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < nrows; r += warps_per_grid) {
+    const int beg = ptr[r], end = ptr[r + 1];
+    float acc = 0.f;
+    for (int k = beg + lane; k < end; k += 32) acc += val[k] * __ldg(x + ind[k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if (lane == 0) res[r] += sign * acc;
+  }
+}
+
+// CSR SpMV for short rows: `kGroup` lanes per row.
+template <int kGroup>
+__global__ void __launch_bounds__(kBlock) csr_spmv_add_group_kernel(
+    const int* __restrict__ ptr, const int* __restrict__ ind, const float* __restrict__ val,
+    uint32_t nrows, float* __restrict__ res, const float* __restrict__ x, float sign) {
+  const uint32_t sub = threadIdx.x % kGroup;
+  const uint32_t groups_per_grid = (gridDim.x * blockDim.x) / kGroup;
+  // all lanes of a warp iterate the same number of times so the shuffles stay converged
+  const uint32_t first = (blockIdx.x * blockDim.x + threadIdx.x) / kGroup;
+  const uint32_t iters = (nrows + groups_per_grid - 1) / groups_per_grid;
+  for (uint32_t it = 0; it < iters; ++it) {
+    const uint32_t r = first + it * groups_per_grid;
+    float acc = 0.f;
+    if (r < nrows) {
+      const int beg = ptr[r], end = ptr[r + 1];
+      for (int k = beg + sub; k < end; k += kGroup) acc += val[k] * __ldg(x + ind[k]);
+    }
+#pragma unroll
+    for (int o = kGroup / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, kGroup);
+    if (sub == 0 && r < nrows) res[r] += sign * acc;
+  }
+}
+
+// Dense y += A x, A column-major (lda = M).  Thread per row (coalesced down a column),
+// columns split over blockIdx.y; partials land in `part[split][M]` and are folded in a fixed
+// order by dense_fold_kernel, so the result is deterministic.
+__global__ void __launch_bounds__(kBlock) dense_gemv_n_kernel(const float* __restrict__ A, uint32_t M,
+                                                               uint32_t N, uint32_t cols_per_split,
+                                                               const float* __restrict__ x,
+                                                               float* __restrict__ part) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= M) return;
+  const uint32_t c0 = blockIdx.y * cols_per_split;
+  const uint32_t c1 = min(N, c0 + cols_per_split);
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+  uint32_t c = c0;
+  for (; c + 3 < c1; c += 4) {
+    acc0 += A[(size_t)c * M + r] * x[c];
+    acc1 += A[(size_t)(c + 1) * M + r] * x[c + 1];
+    acc2 += A[(size_t)(c + 2) * M + r] * x[c + 2];
+    acc3 += A[(size_t)(c + 3) * M + r] * x[c + 3];
+  }
+  for (; c < c1; ++c) acc0 += A[(size_t)c * M + r] * x[c];
+  part[(size_t)blockIdx.y * M + r] = (acc0 + acc1) + (acc2 + acc3);
+}
+
+__global__ void __launch_bounds__(kBlock) dense_fold_kernel(const float* __restrict__ part, uint32_t M,
+                                                             uint32_t splits, float* __restrict__ res,
+                                                             float sign) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= M) return;
+  float acc = 0.f;
+  for (uint32_t s = 0; s < splits; ++s) acc += part[(size_t)s * M + r];
+  res[r] += sign * acc;
+}
+
+// Dense y += A^T x: one warp per column (contiguous in memory), shuffle-reduce.
+__global__ void __launch_bounds__(kBlock) dense_gemv_t_kernel(const float* __restrict__ A, uint32_t M,
+                                                               uint32_t N, const float* __restrict__ x,
+                                                               float* __restrict__ res, float sign) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < N; c += warps_per_grid) {
+    const float* col = A + (size_t)c * M;
+    float acc0 = 0.f, acc1 = 0.f;
+    uint32_t r = lane;
+    for (; r + 32 < M; r += 64) {
+      acc0 += col[r] * x[r];
+      acc1 += col[r + 32] * x[r + 32];
+    }
+    if (r < M) acc0 += col[r] * x[r];
+    float acc = acc0 + acc1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if (lane == 0) res[c] += sign * acc;
+  }
+}
+
+// ---- Block base -------------------------------------------------------------------------------
+
+static uint32_t checked_u32(size_t v, const char* what) {
+  if (v >= (1ull << 31)) fail(PB_ERR_UNSUPPORTED, std::string(what) + " exceeds 2^31-1 elements");
+  return static_cast<uint32_t>(v);
+}
+
+BlockDesc Block::desc() const {
+  BlockDesc d;
+  d.kind = kind();
+  d.row = checked_u32(row_, "block row offset");
+  d.col = checked_u32(col_, "block column offset");
+  d.nrows = checked_u32(nrows_, "block rows");
+  d.ncols = checked_u32(ncols_, "block columns");
+  return d;
+}
+
+static void launch_generic_add(Context* ctx, const BlockDesc& d, bool transpose, float* res,
+                               const float* rhs, float sign) {
+  const size_t n = transpose ? d.ncols : d.nrows;
+  if (n == 0) return;
+  const unsigned grid = std::min<size_t>(grid_for(n), (size_t)ctx->num_sms * 32);
+  if (transpose)
+    block_apply_add_kernel<true><<<grid, kBlock, 0, ctx->stream>>>(d, res, rhs, sign);
+  else
+    block_apply_add_kernel<false><<<grid, kBlock, 0, ctx->stream>>>(d, res, rhs, sign);
+  PB_CHECK_LAUNCH();
+  ctx->launches++;
+}
+
+// ---- gradient (2-D and 3-D) -----------------------------------------------------------------------
+
+class BlockGradient : public Block {
+ public:
+  BlockGradient(Context* ctx, bool three_d, size_t row, size_t col, size_t nx, size_t ny, size_t L,
+                bool label_first)
+      : Block(ctx, row, col, nx * ny * L * (three_d ? 3 : 2), nx * ny * L),
+        three_d_(three_d), nx_(nx), ny_(ny), L_(L), label_first_(label_first) {
+    if (nx == 0 || ny == 0 || L == 0) fail(PB_ERR_INVALID, "BlockGradient: empty grid");
+    checked_u32(nrows_, "gradient block rows");
+  }
+  int kind() const override { return three_d_ ? kBlockGradient3D : kBlockGradient2D; }
+  // constants, independent of the boundary rows (block_gradient2d.cu:153-163, 3d:164-174)
+  float row_sum(size_t, float) const override { return 2.f; }
+  float col_sum(size_t, float) const override { return three_d_ ? 6.f : 4.f; }
+  bool uniform_sums() const override { return true; }
+
+  BlockDesc desc() const override {
+    BlockDesc d = Block::desc();
+    d.label_first = label_first_ ? 1 : 0;
+    d.nx = (uint32_t)nx_; d.ny = (uint32_t)ny_; d.L = (uint32_t)L_;
+    d.plane = (uint32_t)(nx_ * ny_ * L_);
+    d.div_ny = FastDiv(ny_);
+    d.div_L = FastDiv(L_);
+    d.div_nxny = FastDiv(nx_ * ny_);
+    d.div_nyL = FastDiv(ny_ * L_);
+    d.div_plane = FastDiv(nx_ * ny_ * L_);
+    return d;
+  }
+  void eval_local_add(float* res, const float* rhs) override {
+    launch_generic_add(ctx_, desc(), false, res, rhs, 1.f);
+  }
+  void eval_adjoint_local_add(float* res, const float* rhs) override {
+    launch_generic_add(ctx_, desc(), true, res, rhs, 1.f);
+  }
+
+ private:
+  bool three_d_;
+  size_t nx_, ny_, L_;
+  bool label_first_;
+};
+
+// ---- diagonals ------------------------------------------------------------------------------------
+
+class BlockDiags : public Block {
+ public:
+  BlockDiags(Context* ctx, size_t row, size_t col, size_t nrows, size_t ncols, size_t ndiags,
+             const int64_t* offsets, const float* factors)
+      : Block(ctx, row, col, nrows, ncols) {
+    // sort by offset (the forward loop stops at the first out-of-range column and relies on
+    // ascending offsets: block_diags.cu:58-59,110-118); factors are always float (hpp:82)
+    std::vector<size_t> order(ndiags);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(),
+                     [&](size_t a, size_t b) { return offsets[a] < offsets[b]; });
+    offsets_.resize(ndiags);
+    factors_.resize(ndiags);
+    for (size_t i = 0; i < ndiags; ++i) {
+      offsets_[i] = offsets[order[i]];
+      factors_[i] = factors[order[i]];
+    }
+    d_offsets_.assign(offsets_, ctx->stream);
+    d_factors_.assign(factors_, ctx->stream);
+  }
+  int kind() const override { return kBlockDiags; }
+  float row_sum(size_t row, float alpha) const override {
+    float sum = 0;
+    for (size_t i = 0; i < offsets_.size(); ++i) {
+      const long long c = (long long)row + offsets_[i];
+      if (c < 0) continue;
+      if (c >= (long long)ncols_) break;
+      sum += std::pow(std::abs(factors_[i]), alpha);
+    }
+    return sum;
+  }
+  float col_sum(size_t col, float alpha) const override {
+    float sum = 0;
+    for (size_t i = 0; i < offsets_.size(); ++i) {
+      const long long ofs = offsets_[i];
+      if (ofs > (long long)col) break;
+      if ((long long)col - ofs < (long long)nrows_) sum += std::pow(std::abs(factors_[i]), alpha);
+    }
+    return sum;
+  }
+  size_t gpu_mem_amount() const override {
+    return offsets_.size() * (sizeof(long long) + sizeof(float));
+  }
+  BlockDesc desc() const override {
+    BlockDesc d = Block::desc();
+    d.ndiags = (int)offsets_.size();
+    d.offsets = d_offsets_.data();
+    d.factors = d_factors_.data();
+    return d;
+  }
+  void eval_local_add(float* res, const float* rhs) override {
+    launch_generic_add(ctx_, desc(), false, res, rhs, 1.f);
+  }
+  void eval_adjoint_local_add(float* res, const float* rhs) override {
+    // NOTE: the reference sizes this launch by nrows (block_diags.cu:211) and silently skips
+    // columns >= nrows; all ncols columns are computed here.
+    launch_generic_add(ctx_, desc(), true, res, rhs, 1.f);
+  }
+
+ private:
+  std::vector<long long> offsets_;
+  std::vector<float> factors_;
+  DeviceBuffer<long long> d_offsets_;
+  DeviceBuffer<float> d_factors_;
+};
+
+// ---- sparse ---------------------------------------------------------------------------------------
+
+class BlockSparse : public Block {
+ public:
+  BlockSparse(Context* ctx, size_t row, size_t col, int m, int n, int nnz, const float* val,
+              const int32_t* ptr, const int32_t* ind)
+      : Block(ctx, row, col, (size_t)m, (size_t)n), nnz_(nnz) {
+    if (m < 0 || n < 0 || nnz < 0) fail(PB_ERR_INVALID, "BlockSparse: negative size");
+    if (ptr[0] != 0 || ptr[n] != nnz) fail(PB_ERR_INVALID, "BlockSparse: inconsistent CSC column pointer");
+    // CSC of K == CSR of K^T
+    ptr_t_.assign(ptr, ptr + n + 1);
+    ind_t_.assign(ind, ind + nnz);
+    val_t_.assign(val, val + nnz);
+    for (int k = 0; k < nnz; ++k)
+      if (ind[k] < 0 || ind[k] >= m) fail(PB_ERR_INVALID, "BlockSparse: row index out of range");
+    // CSR of K by a counting-sort transpose; within a row the entries come out in ascending
+    // column order, like the reference's host csr2csc (common.cu:54-82)
+    ptr_.assign(m + 1, 0);
+    for (int k = 0; k < nnz; ++k) ptr_[ind[k] + 1]++;
+    for (int r = 0; r < m; ++r) ptr_[r + 1] += ptr_[r];
+    ind_.resize(nnz);
+    val_.resize(nnz);
+    std::vector<int> fill(ptr_.begin(), ptr_.end() - 1);
+    for (int c = 0; c < n; ++c)
+      for (int k = ptr[c]; k < ptr[c + 1]; ++k) {
+        const int dst = fill[ind[k]]++;
+        ind_[dst] = c;
+        val_[dst] = val[k];
+      }
+    d_ptr_.assign(ptr_, ctx->stream);
+    d_ind_.assign(ind_, ctx->stream);
+    d_val_.assign(val_, ctx->stream);
+    d_ptr_t_.assign(ptr_t_, ctx->stream);
+    d_ind_t_.assign(ind_t_, ctx->stream);
+    d_val_t_.assign(val_t_, ctx->stream);
+  }
+  int kind() const override { return kBlockSparse; }
+  float row_sum(size_t row, float alpha) const override {
+    float sum = 0;
+    for (int k = ptr_[row]; k < ptr_[row + 1]; ++k) sum += std::pow(std::abs(val_[k]), alpha);
+    return sum;
+  }
+  float col_sum(size_t col, float alpha) const override {
+    float sum = 0;
+    for (int k = ptr_t_[col]; k < ptr_t_[col + 1]; ++k) sum += std::pow(std::abs(val_t_[k]), alpha);
+    return sum;
+  }
+  size_t gpu_mem_amount() const override {
+    return 2 * (size_t)nnz_ * (sizeof(int32_t) + sizeof(float)) +
+           (nrows_ + ncols_ + 2) * sizeof(int32_t);
+  }
+  BlockDesc desc() const override {
+    BlockDesc d = Block::desc();
+    d.ptr = d_ptr_.data(); d.ind = d_ind_.data(); d.val = d_val_.data();
+    d.ptr_t = d_ptr_t_.data(); d.ind_t = d_ind_t_.data(); d.val_t = d_val_t_.data();
+    return d;
+  }
+  void spmv(const DeviceBuffer<int>& ptr, const DeviceBuffer<int>& ind, const DeviceBuffer<float>& val,
+            size_t rows, float* res, const float* x) {
+    if (rows == 0) return;
+    const double avg = rows ? (double)nnz_ / (double)rows : 0.0;
+    const unsigned cap = ctx_->num_sms * 16;
+    if (avg <= 6.0) {
+      const unsigned grid = std::min<size_t>(grid_for(rows * 4), cap);
+      csr_spmv_add_group_kernel<4><<<grid, kBlock, 0, ctx_->stream>>>(ptr.data(), ind.data(), val.data(),
+                                                                      (uint32_t)rows, res, x, 1.f);
+    } else if (avg <= 24.0) {
+      const unsigned grid = std::min<size_t>(grid_for(rows * 8), cap);
+      csr_spmv_add_group_kernel<8><<<grid, kBlock, 0, ctx_->stream>>>(ptr.data(), ind.data(), val.data(),
+                                                                      (uint32_t)rows, res, x, 1.f);
+    } else {
+      const unsigned grid = std::min<size_t>(grid_for(rows * 32), cap);
+      csr_spmv_add_kernel<<<grid, kBlock, 0, ctx_->stream>>>(ptr.data(), ind.data(), val.data(),
+                                                             (uint32_t)rows, res, x, 1.f);
+    }
+    PB_CHECK_LAUNCH();
+    ctx_->launches++;
+  }
+  void eval_local_add(float* res, const float* rhs) override {
+    spmv(d_ptr_, d_ind_, d_val_, nrows_, res, rhs);
+  }
+  void eval_adjoint_local_add(float* res, const float* rhs) override {
+    spmv(d_ptr_t_, d_ind_t_, d_val_t_, ncols_, res, rhs);
+  }
+
+ private:
+  int nnz_;
+  std::vector<int> ptr_, ind_, ptr_t_, ind_t_;
+  std::vector<float> val_, val_t_;
+  DeviceBuffer<int> d_ptr_, d_ind_, d_ptr_t_, d_ind_t_;
+  DeviceBuffer<float> d_val_, d_val_t_;
+};
+
+// ---- dense ----------------------------------------------------------------------------------------
+
+class BlockDense : public Block {
+ public:
+  BlockDense(Context* ctx, size_t row, size_t col, size_t nrows, size_t ncols, const float* data)
+      : Block(ctx, row, col, nrows, ncols), host_(data, data + nrows * ncols) {
+    checked_u32(nrows, "dense rows");
+    checked_u32(ncols, "dense columns");
+    d_data_.assign(host_, ctx->stream);
+    // column splits so that a 4096x4096 block still fills the machine
+    const size_t row_ctas = (nrows + kBlock - 1) / kBlock;
+    size_t want = ((size_t)ctx->num_sms * 4 + row_ctas - 1) / std::max<size_t>(row_ctas, 1);
+    splits_ = (uint32_t)std::max<size_t>(1, std::min<size_t>(want, std::max<size_t>(1, ncols / 64)));
+    cols_per_split_ = (uint32_t)((ncols + splits_ - 1) / splits_);
+    splits_ = (uint32_t)((ncols + cols_per_split_ - 1) / std::max<uint32_t>(cols_per_split_, 1));
+    if (splits_ == 0) splits_ = 1;
+    d_part_.resize((size_t)splits_ * nrows);
+  }
+  int kind() const override { return kBlockDense; }
+  float row_sum(size_t row, float alpha) const override {
+    float sum = 0;
+    for (size_t c = 0; c < ncols_; ++c) sum += std::pow(std::abs(host_[c * nrows_ + row]), alpha);
+    return sum;
+  }
+  float col_sum(size_t col, float alpha) const override {
+    float sum = 0;
+    for (size_t r = 0; r < nrows_; ++r) sum += std::pow(std::abs(host_[col * nrows_ + r]), alpha);
+    return sum;
+  }
+  size_t gpu_mem_amount() const override { return nrows_ * ncols_ * sizeof(float); }
+  BlockDesc desc() const override {
+    BlockDesc d = Block::desc();
+    d.dense = d_data_.data();
+    return d;
+  }
+  void eval_local_add(float* res, const float* rhs) override {
+    if (nrows_ == 0 || ncols_ == 0) return;
+    dim3 grid(grid_for(nrows_), splits_);
+    dense_gemv_n_kernel<<<grid, kBlock, 0, ctx_->stream>>>(d_data_.data(), (uint32_t)nrows_,
+                                                           (uint32_t)ncols_, cols_per_split_, rhs,
+                                                           d_part_.data());
+    PB_CHECK_LAUNCH();
+    dense_fold_kernel<<<grid_for(nrows_), kBlock, 0, ctx_->stream>>>(d_part_.data(), (uint32_t)nrows_,
+                                                                     splits_, res, 1.f);
+    PB_CHECK_LAUNCH();
+    ctx_->launches += 2;
+  }
+  void eval_adjoint_local_add(float* res, const float* rhs) override {
+    if (nrows_ == 0 || ncols_ == 0) return;
+    const unsigned grid = std::min<size_t>(grid_for(ncols_ * 32), (size_t)ctx_->num_sms * 16);
+    dense_gemv_t_kernel<<<grid, kBlock, 0, ctx_->stream>>>(d_data_.data(), (uint32_t)nrows_,
+                                                           (uint32_t)ncols_, rhs, res, 1.f);
+    PB_CHECK_LAUNCH();
+    ctx_->launches++;
+  }
+
+ private:
+  std::vector<float> host_;
+  DeviceBuffer<float> d_data_, d_part_;
+  uint32_t splits_ = 1, cols_per_split_ = 0;
+};
+
+// ---- zero -----------------------------------------------------------------------------------------
+
+class BlockZero : public Block {
+ public:
+  using Block::Block;
+  int kind() const override { return kBlockZero; }
+  float row_sum(size_t, float) const override { return 0.f; }
+  float col_sum(size_t, float) const override { return 0.f; }
+  bool uniform_sums() const override { return true; }
+  void eval_local_add(float*, const float*) override {}
+  void eval_adjoint_local_add(float*, const float*) override {}
+};
+
+// ---- factories ------------------------------------------------------------------------------------
+
+std::shared_ptr<Block> make_block_gradient(Context* ctx, bool three_d, size_t row, size_t col,
+                                           size_t nx, size_t ny, size_t L, bool label_first) {
+  return std::make_shared<BlockGradient>(ctx, three_d, row, col, nx, ny, L, label_first);
+}
+std::shared_ptr<Block> make_block_diags(Context* ctx, size_t row, size_t col, size_t nrows,
+                                        size_t ncols, size_t ndiags, const int64_t* offsets,
+                                        const float* factors) {
+  return std::make_shared<BlockDiags>(ctx, row, col, nrows, ncols, ndiags, offsets, factors);
+}
+std::shared_ptr<Block> make_block_sparse_csc(Context* ctx, size_t row, size_t col, int m, int n,
+                                             int nnz, const float* val, const int32_t* ptr,
+                                             const int32_t* ind) {
+  return std::make_shared<BlockSparse>(ctx, row, col, m, n, nnz, val, ptr, ind);
+}
+std::shared_ptr<Block> make_block_dense(Context* ctx, size_t row, size_t col, size_t nrows,
+                                        size_t ncols, const float* data) {
+  return std::make_shared<BlockDense>(ctx, row, col, nrows, ncols, data);
+}
+std::shared_ptr<Block> make_block_zero(Context* ctx, size_t row, size_t col, size_t nrows,
+                                       size_t ncols) {
+  return std::make_shared<BlockZero>(ctx, row, col, nrows, ncols);
+}
+
+// ---- LinearOperator -------------------------------------------------------------------------------
+
+static bool rect_overlap(size_t x1, size_t y1, size_t x2, size_t y2, size_t a1, size_t b1, size_t a2,
+                         size_t b2) {
+  return (x1 <= a2) && (x2 >= a1) && (y1 <= b2) && (y2 >= b1);
+}
+
+void LinearOperator::initialize() {
+  nrows_ = ncols_ = 0;
+  bool overlap = false;
+  for (size_t i = 0; i < blocks_.size(); ++i) {
+    const Block& a = *blocks_[i];
+    nrows_ = std::max(nrows_, a.row() + a.nrows());
+    ncols_ = std::max(ncols_, a.col() + a.ncols());
+    for (size_t j = i + 1; j < blocks_.size(); ++j) {
+      const Block& b = *blocks_[j];
+      if (a.nrows() == 0 || a.ncols() == 0 || b.nrows() == 0 || b.ncols() == 0) continue;
+      overlap |= rect_overlap(a.col(), a.row(), a.col() + a.ncols() - 1, a.row() + a.nrows() - 1,
+                              b.col(), b.row(), b.col() + b.ncols() - 1, b.row() + b.nrows() - 1);
+    }
+  }
+  if (overlap)
+    fail(PB_ERR_INVALID, "Blocks are overlapping inside the linear operator. Recheck the indices.");
+}
+
+void LinearOperator::eval(float* d_result, const float* d_rhs, float beta, bool transpose, bool negate) {
+  ctx_->bind();
+  const size_t nout = transpose ? ncols_ : nrows_;
+  if (nout == 0) return;
+  if (beta == 0.f) {
+    PB_CUDA(cudaMemsetAsync(d_result, 0, nout * sizeof(float), ctx_->stream));
+  } else if (beta != 1.f) {
+    const unsigned grid = std::min<size_t>(grid_for(nout), (size_t)ctx_->num_sms * 32);
+    scale_kernel<<<grid, kBlock, 0, ctx_->stream>>>(d_result, nout, beta);
+    PB_CHECK_LAUNCH();
+    ctx_->launches++;
+  }
+  if (!negate) {
+    for (auto& b : blocks_) {
+      if (transpose)
+        b->eval_adjoint_local_add(d_result + b->col(), d_rhs + b->row());
+      else
+        b->eval_local_add(d_result + b->row(), d_rhs + b->col());
+    }
+  } else {
+    // DualLinearOperator (dual_linearoperator.cu:38-80): result = beta*result - K^T rhs, realised
+    // as  result <- -( -beta*result + K^T rhs ).  Only used when solve_dual_problem is set.
+    const unsigned grid = std::min<size_t>(grid_for(nout), (size_t)ctx_->num_sms * 32);
+    if (beta != 0.f) {
+      scale_kernel<<<grid, kBlock, 0, ctx_->stream>>>(d_result, nout, -1.f);
+      PB_CHECK_LAUNCH();
+      ctx_->launches++;
+    }
+    for (auto& b : blocks_) {
+      if (transpose)
+        b->eval_adjoint_local_add(d_result + b->col(), d_rhs + b->row());
+      else
+        b->eval_local_add(d_result + b->row(), d_rhs + b->col());
+    }
+    scale_kernel<<<grid, kBlock, 0, ctx_->stream>>>(d_result, nout, -1.f);
+    PB_CHECK_LAUNCH();
+    ctx_->launches++;
+  }
+}
+
+float LinearOperator::row_sum(size_t row, float alpha) const {
+  float sum = 0;
+  for (auto& b : blocks_) {
+    if (row < b->row() || row >= b->row() + b->nrows()) continue;
+    sum += b->row_sum(row - b->row(), alpha);
+  }
+  return sum;
+}
+
+float LinearOperator::col_sum(size_t col, float alpha) const {
+  float sum = 0;
+  for (auto& b : blocks_) {
+    if (col < b->col() || col >= b->col() + b->ncols()) continue;
+    sum += b->col_sum(col - b->col(), alpha);
+  }
+  return sum;
+}
+
+// All sums in one sweep per block (the reference makes nrows+ncols virtual calls through
+// LinearOperator::row_sum, problem.cu:262-287; the accumulation order per row -- block list
+// order -- is the same).
+void LinearOperator::row_sums(float alpha, std::vector<float>& out) const {
+  out.assign(nrows_, 0.f);
+  for (auto& b : blocks_) {
+    if (b->uniform_sums()) {
+      const float v = b->nrows() ? b->row_sum(0, alpha) : 0.f;
+      for (size_t r = 0; r < b->nrows(); ++r) out[b->row() + r] += v;
+    } else {
+      for (size_t r = 0; r < b->nrows(); ++r) out[b->row() + r] += b->row_sum(r, alpha);
+    }
+  }
+}
+
+void LinearOperator::col_sums(float alpha, std::vector<float>& out) const {
+  out.assign(ncols_, 0.f);
+  for (auto& b : blocks_) {
+    if (b->uniform_sums()) {
+      const float v = b->ncols() ? b->col_sum(0, alpha) : 0.f;
+      for (size_t c = 0; c < b->ncols(); ++c) out[b->col() + c] += v;
+    } else {
+      for (size_t c = 0; c < b->ncols(); ++c) out[b->col() + c] += b->col_sum(c, alpha);
+    }
+  }
+}
+
+size_t LinearOperator::gpu_mem_amount() const {
+  size_t mem = 0;
+  for (auto& b : blocks_) mem += b->gpu_mem_amount();
+  return mem;
+}
+
+bool LinearOperator::all_stencil() const {
+  for (auto& b : blocks_)
+    if (!block_is_stencil(b->kind())) return false;
+  return true;
+}
+
+}  // namespace pb

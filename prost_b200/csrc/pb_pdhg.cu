@@ -1,0 +1,519 @@
+// pb_pdhg.cu -- BackendPDHG: the primal-dual hybrid gradient iteration.
+// Reference: src/backend/backend_pdhg.cu (Initialize :199-309, PerformIteration :311-381,
+// UpdateResidualsAndStepsizes :383-489, current_solution :513-563).
+//
+// Two execution modes with identical semantics:
+//  * fused   -- two passes per iteration (pb_fused.cuh), 4 state vectors, step sizes and residual
+//               bookkeeping in device memory, no host synchronisation inside iterate();
+//  * unfused -- the reference's kernel sequence over 9 state vectors, used when the planner
+//               cannot fuse (sparse/dense blocks, permuted or oversized prox groups, dualised
+//               problems) and as an A/B check of the fused passes.
+#include <algorithm>
+#include <cmath>
+#include <iostream>
+
+#include "pb_backend.cuh"
+#include "pb_fused.cuh"
+#include "pb_reduce.cuh"
+
+namespace pb {
+
+// ---- unfused kernels ----------------------------------------------------------------------------
+
+// temp = x - tau * T * kty          (primal_proxarg_functor, backend_pdhg.cu:38-51)
+__global__ void __launch_bounds__(kBlock) primal_proxarg_kernel(float* __restrict__ temp,
+                                                                const float* __restrict__ x,
+                                                                const float* __restrict__ T,
+                                                                const float* __restrict__ kty, size_t n,
+                                                                float tau) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x)
+    temp[i] = x[i] - tau * T[i] * kty[i];
+}
+
+// temp = y + sigma * S * ((1+theta) kx - theta kx_prev)   (dual_proxarg_functor, :54-70)
+__global__ void __launch_bounds__(kBlock) dual_proxarg_kernel(float* __restrict__ temp,
+                                                              const float* __restrict__ y,
+                                                              const float* __restrict__ S,
+                                                              const float* __restrict__ kx,
+                                                              const float* __restrict__ kx_prev, size_t m,
+                                                              float sigma, float theta) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < m;
+       i += (size_t)gridDim.x * blockDim.x)
+    temp[i] = y[i] + sigma * S[i] * ((1 + theta) * kx[i] - theta * kx_prev[i]);
+}
+
+// primal_residual_transform (:97-120): per-CTA partial (sum diff^2, sum z_hat^2)
+__global__ void __launch_bounds__(kBlock) primal_residual_kernel(
+    const float* __restrict__ y_prev, const float* __restrict__ y, const float* __restrict__ S,
+    const float* __restrict__ kx_prev, const float* __restrict__ kx, size_t m, float sigma, float theta,
+    double* __restrict__ part) {
+  double a = 0.0, b = 0.0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < m;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const float sq = sqrtf(S[i]);
+    const float z_hat = (y_prev[i] - y[i]) / (sigma * sq) + sq * ((1 + theta) * kx[i] - theta * kx_prev[i]);
+    const float diff = z_hat - sq * kx[i];
+    a += static_cast<double>(diff * diff);
+    b += static_cast<double>(z_hat * z_hat);
+  }
+  block_sum2(a, b);
+  if (threadIdx.x == 0) { part[2 * blockIdx.x] = a; part[2 * blockIdx.x + 1] = b; }
+}
+
+// dual_residual_transform (:73-94)
+__global__ void __launch_bounds__(kBlock) dual_residual_kernel(
+    const float* __restrict__ x_prev, const float* __restrict__ x, const float* __restrict__ T,
+    const float* __restrict__ kty_prev, const float* __restrict__ kty, size_t n, float tau,
+    double* __restrict__ part) {
+  double a = 0.0, b = 0.0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const float sq = sqrtf(T[i]);
+    const float w_hat = (x_prev[i] - x[i]) / (tau * sq) - sq * kty_prev[i];
+    const float diff = w_hat + sq * kty[i];
+    a += static_cast<double>(diff * diff);
+    b += static_cast<double>(w_hat * w_hat);
+  }
+  block_sum2(a, b);
+  if (threadIdx.x == 0) { part[2 * blockIdx.x] = a; part[2 * blockIdx.x + 1] = b; }
+}
+
+// folds the primal and the dual partials into sums[0..3] (one CTA, index order)
+__global__ void __launch_bounds__(kBlock) fold_residuals_kernel(const double* __restrict__ part_p,
+                                                                unsigned np,
+                                                                const double* __restrict__ part_d,
+                                                                unsigned nd, double* __restrict__ sums) {
+  double a, b;
+  fold_partials2(part_p, np, a, b);
+  if (threadIdx.x == 0) { sums[0] = a; sums[1] = b; }
+  fold_partials2(part_d, nd, a, b);
+  if (threadIdx.x == 0) { sums[2] = a; sums[3] = b; }
+}
+
+// fused mode: fold + step-size state machine on the device (one CTA)
+__global__ void __launch_bounds__(kBlock) pdhg_finalize_kernel(PdhgState* __restrict__ st, PdhgParams prm,
+                                                               const double* __restrict__ part_p,
+                                                               unsigned np,
+                                                               const double* __restrict__ part_d,
+                                                               unsigned nd, unsigned long long iteration,
+                                                               int check) {
+  __shared__ double sums[4];
+  if (check) {
+    double a, b;
+    fold_partials2(part_p, np, a, b);
+    if (threadIdx.x == 0) { sums[0] = a; sums[1] = b; }
+    fold_partials2(part_d, nd, a, b);
+    if (threadIdx.x == 0) { sums[2] = a; sums[3] = b; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    PdhgState s = *st;
+    s.iteration = iteration;
+    pdhg_update(s, prm, sums, check != 0);
+    *st = s;
+  }
+}
+
+// w = (x_prev - x) / (T tau) - kty_prev     (compute_w_variable_functor, :146-160)
+__global__ void __launch_bounds__(kBlock) w_variable_kernel(float* __restrict__ w,
+                                                            const float* __restrict__ x_prev,
+                                                            const float* __restrict__ x,
+                                                            const float* __restrict__ T,
+                                                            const float* __restrict__ kty_prev, size_t n,
+                                                            float tau) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x)
+    w[i] = (x_prev[i] - x[i]) / (T[i] * tau) - kty_prev[i];
+}
+
+// z = (y_prev - y) / (sigma S) + (1+theta) kx - theta kx_prev   (compute_z_variable_functor, :170-186)
+__global__ void __launch_bounds__(kBlock) z_variable_kernel(float* __restrict__ z,
+                                                            const float* __restrict__ y_prev,
+                                                            const float* __restrict__ y,
+                                                            const float* __restrict__ S,
+                                                            const float* __restrict__ kx,
+                                                            const float* __restrict__ kx_prev, size_t m,
+                                                            float sigma, float theta) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < m;
+       i += (size_t)gridDim.x * blockDim.x)
+    z[i] = (y_prev[i] - y[i]) / (sigma * S[i]) + (1 + theta) * kx[i] - theta * kx_prev[i];
+}
+
+// ---- backend -------------------------------------------------------------------------------------
+
+class BackendPDHG : public Backend {
+ public:
+  BackendPDHG(Context* ctx, std::shared_ptr<Problem> prob, const pb_pdhg_options& opts,
+              const pb_solver_options& sopts)
+      : Backend(ctx, std::move(prob), sopts), opts_(opts) {
+    if (opts_.residual_iter == 0) fail(PB_ERR_INVALID, "residual_iter must not be 0");
+    if (opts_.stepsize_variant < PB_PDHG_ALG1 || opts_.stepsize_variant > PB_PDHG_BOYD)
+      fail(PB_ERR_INVALID, "unknown PDHG step size variant");
+  }
+
+  void initialize(const float* h_x0, size_t nx0, const float* h_y0, size_t ny0) override;
+  void iterate(int n_iters) override;
+  void profile(int n_iters, float out_ms[3]) override;
+  void residuals(float out[6]) override;
+  void stepsizes(double out[3]) override;
+  size_t iteration() const override { return iteration_; }
+  void current_solution(float* h_x, float* h_z, float* h_y, float* h_w) override;
+  size_t gpu_mem_amount() const override {
+    const size_t m = problem_->nrows(), n = problem_->ncols();
+    if (fused_) return 2 * (n + m) * sizeof(float);
+    return (4 * (n + m) + std::max(n, m)) * sizeof(float);     // backend_pdhg.cu:503-511
+  }
+  bool is_fused() const override { return fused_; }
+  void device_iterates(float** d_x, float** d_y) override { *d_x = x_.data(); *d_y = y_.data(); }
+  int residual_iter() const override { return opts_.residual_iter; }
+
+ private:
+  bool is_check_iteration() const {
+    // size_t % int of the reference: a negative residual_iter wraps to a huge modulus, i.e.
+    // "only at iteration 0" (Appendix B #4)
+    const unsigned long long mod = static_cast<unsigned long long>(static_cast<long long>(opts_.residual_iter));
+    return iteration_ == 0 || (iteration_ % mod) == 0;
+  }
+  bool plan_fused();
+  void iteration_fused();
+  cudaEvent_t* prof_ev_ = nullptr;     // 4 events when profiling, else null
+  void iteration_unfused();
+  PdhgState fetch_state();
+  unsigned sgrid(size_t n) const { return (unsigned)std::min<size_t>(grid_for(n), (size_t)ctx_->num_sms * 32); }
+
+  pb_pdhg_options opts_;
+  PdhgParams params_;
+  ProxList prox_g_, prox_fstar_;
+  bool fused_ = false;
+  unsigned long long iteration_ = 0;
+
+  // iterates: x_/y_ current, x_prev_/y_prev_ previous (ping-pong in fused mode)
+  DeviceBuffer<float> x_, x_prev_, y_, y_prev_;
+  // unfused only
+  DeviceBuffer<float> temp_, kx_, kx_prev_, kty_, kty_prev_;
+  // fused plan
+  BlockList blocks_;
+  std::vector<ProxDesc> g_descs_, f_descs_;
+  unsigned part_p_cap_ = 0, part_d_cap_ = 0;
+  // state + reductions
+  PdhgState h_state_;                  // master copy in unfused mode
+  DeviceBuffer<PdhgState> d_state_;    // master copy in fused mode
+  DeviceBuffer<double> part_p_, part_d_, d_sums_;
+  // scratch for current_solution in fused mode
+  DeviceBuffer<float> sol_a_, sol_b_, sol_c_;
+};
+
+bool BackendPDHG::plan_fused() {
+  if (!opts_.fuse) return false;
+  if (problem_->dualized()) return false;
+  LinearOperator* K = problem_->linop();
+  if (!K->all_stencil()) return false;
+  if (K->blocks().size() > (size_t)kMaxFusedBlocks) return false;
+  blocks_.n = 0;
+  for (auto& b : K->blocks()) {
+    if (b->kind() == kBlockZero) continue;       // contributes nothing
+    blocks_.b[blocks_.n++] = b->desc();
+  }
+  auto collect = [](const ProxList& list, std::vector<ProxDesc>& out) {
+    out.clear();
+    for (auto& p : list) {
+      ProxDesc d;
+      if (!p->leaf_desc(d, 0)) return false;
+      if (dim_cap(d.dim, d.kind) == 0) return false;
+      out.push_back(d);
+    }
+    return true;
+  };
+  return collect(prox_g_, g_descs_) && collect(prox_fstar_, f_descs_);
+}
+
+void BackendPDHG::initialize(const float* h_x0, size_t nx0, const float* h_y0, size_t ny0) {
+  ctx_->bind();
+  if (!problem_->initialized()) fail(PB_ERR_INVALID, "Problem has not been initialized.");
+  const size_t m = problem_->nrows(), n = problem_->ncols();
+  cudaStream_t s = ctx_->stream;
+
+  iteration_ = 0;
+  PdhgState st{};
+  st.tau = static_cast<float>(opts_.tau0);
+  st.sigma = static_cast<float>(opts_.sigma0);
+  st.theta = 1;
+  st.arb_l = st.arb_u = 0;
+  st.arg_alpha = opts_.arg_alpha0;
+  st.iteration = 0;
+  params_.stepsize_variant = opts_.stepsize_variant;
+  params_.alg2_gamma = opts_.alg2_gamma;
+  params_.arg_nu = opts_.arg_nu;
+  params_.arg_delta = opts_.arg_delta;
+  params_.arb_delta = opts_.arb_delta;
+  params_.arb_tau = opts_.arb_tau;
+  params_.tol_rel_primal = sopts_.tol_rel_primal;
+  params_.tol_rel_dual = sopts_.tol_rel_dual;
+  params_.tol_abs_primal = sopts_.tol_abs_primal;
+  params_.tol_abs_dual = sopts_.tol_abs_dual;
+  params_.nrows = m;
+  params_.ncols = n;
+  st.eps_primal = pdhg_eps(m, sopts_.tol_abs_primal, sopts_.tol_rel_primal, 0.f);
+  st.eps_dual = pdhg_eps(n, sopts_.tol_abs_dual, sopts_.tol_rel_dual, 0.f);
+
+  // proxes, conjugated through Moreau where only the other form was given (:236-266)
+  prox_g_.clear();
+  prox_fstar_.clear();
+  if (problem_->prox_g().empty()) {
+    if (problem_->prox_gstar().empty()) fail(PB_ERR_INVALID, "Neither prox_g nor prox_gstar specified.");
+    for (auto& p : problem_->prox_gstar()) prox_g_.push_back(make_prox_moreau(ctx_, p));
+  } else {
+    prox_g_ = problem_->prox_g();
+  }
+  if (problem_->prox_fstar().empty()) {
+    if (problem_->prox_f().empty()) fail(PB_ERR_INVALID, "Neither prox_f nor prox_fstar specified.");
+    for (auto& p : problem_->prox_f()) prox_fstar_.push_back(make_prox_moreau(ctx_, p));
+  } else {
+    prox_fstar_ = problem_->prox_fstar();
+  }
+
+  if (opts_.scale_steps_operator) {                      // :274-286
+    const float norm = problem_->normest(1e-6f, 100, opts_.normest_x0);
+    if (std::abs(norm - 1) > 0.1) {
+      st.tau /= norm;
+      st.sigma /= norm;
+      if (sopts_.verbose)
+        std::cout << "|K|=" << norm << " => Rescaled tau=" << st.tau << ", sigma=" << st.sigma << "."
+                  << std::endl;
+    }
+  }
+
+  if (nx0 > 0 && nx0 != n) fail(PB_ERR_INVALID, "Initial primal solution has wrong size.");
+  if (ny0 > 0 && ny0 != m) fail(PB_ERR_INVALID, "Initial dual solution has wrong size.");
+
+  fused_ = plan_fused();
+  try {
+    x_.resize(n); x_prev_.resize(n); y_.resize(m); y_prev_.resize(m);
+    if (!fused_) {
+      temp_.resize(std::max(m, n));
+      kx_.resize(m); kx_prev_.resize(m); kty_.resize(n); kty_prev_.resize(n);
+    }
+    d_state_.resize(1);
+    d_sums_.resize(4);
+  } catch (Error& e) {
+    if (e.status == PB_ERR_OOM) fail(PB_ERR_OOM, std::string("Out of memory: ") + e.what());
+    throw;
+  }
+  x_.zero(s); x_prev_.zero(s); y_.zero(s); y_prev_.zero(s);
+  if (!fused_) { temp_.zero(s); kx_.zero(s); kx_prev_.zero(s); kty_.zero(s); kty_prev_.zero(s); }
+  if (nx0 > 0) { x_.upload(h_x0, n, s); x_prev_.upload(h_x0, n, s); }   // :288-308
+  if (ny0 > 0) { y_.upload(h_y0, m, s); y_prev_.upload(h_y0, m, s); }
+
+  // partial-sum buffers: one (a, b) pair per CTA of every launch of a pass
+  if (fused_) {
+    part_d_cap_ = part_p_cap_ = 0;
+    for (auto& d : g_descs_) part_d_cap_ += fused_grid(ctx_, d);
+    for (auto& d : f_descs_) part_p_cap_ += fused_grid(ctx_, d);
+  } else {
+    part_p_cap_ = std::min<size_t>(grid_for(m), (size_t)ctx_->num_sms * 8);
+    part_d_cap_ = std::min<size_t>(grid_for(n), (size_t)ctx_->num_sms * 8);
+  }
+  part_p_.resize(2 * (size_t)std::max(part_p_cap_, 1u));
+  part_d_.resize(2 * (size_t)std::max(part_d_cap_, 1u));
+
+  h_state_ = st;
+  d_state_.upload(&h_state_, 1, s);
+  PB_CUDA(cudaStreamSynchronize(s));
+}
+
+void BackendPDHG::iteration_fused() {
+  const bool check = is_check_iteration();
+  const ScaleRef T = problem_->right_ref(), S = problem_->left_ref();
+  const PdhgState* st = d_state_.data();
+
+  // primal pass: x_prev_ <- prox_g(x_ - tau T K^T y_), then swap so that x_ is x^{k+1}
+  unsigned off = 0;
+  for (auto& d : g_descs_)
+    off += fused_primal_launch(ctx_, d, blocks_, x_.data(), y_.data(), y_prev_.data(), T, st,
+                               iteration_ == 0, iteration_ <= 1, check, part_d_.data() + 2 * (size_t)off,
+                               x_prev_.data());
+  const unsigned nd = off;
+  x_.swap(x_prev_);
+  if (prof_ev_) PB_CUDA(cudaEventRecord(prof_ev_[1], ctx_->stream));
+
+  // dual pass: y_prev_ <- prox_f*(y_ + sigma S K(2x^{k+1} - x^k)) (theta-extrapolated), then swap
+  off = 0;
+  for (auto& d : f_descs_)
+    off += fused_dual_launch(ctx_, d, blocks_, y_.data(), x_.data(), x_prev_.data(), S, st,
+                             iteration_ == 0, check, part_p_.data() + 2 * (size_t)off, y_prev_.data());
+  const unsigned np = off;
+  y_.swap(y_prev_);
+  if (prof_ev_) PB_CUDA(cudaEventRecord(prof_ev_[2], ctx_->stream));
+
+  if (check || opts_.stepsize_variant == PB_PDHG_ALG2) {
+    pdhg_finalize_kernel<<<1, kBlock, 0, ctx_->stream>>>(d_state_.data(), params_, part_p_.data(), np,
+                                                         part_d_.data(), nd, iteration_, check ? 1 : 0);
+    PB_CHECK_LAUNCH();
+    ctx_->launches++;
+  }
+  iteration_++;
+}
+
+void BackendPDHG::iteration_unfused() {
+  const size_t m = problem_->nrows(), n = problem_->ncols();
+  cudaStream_t s = ctx_->stream;
+  const float* T = problem_->scaling_right();
+  const float* S = problem_->scaling_left();
+  PdhgState& st = h_state_;
+
+  primal_proxarg_kernel<<<sgrid(n), kBlock, 0, s>>>(temp_.data(), x_.data(), T, kty_.data(), n, st.tau);
+  PB_CHECK_LAUNCH();
+  x_.swap(x_prev_);
+  for (auto& p : prox_g_) p->eval(x_.data(), temp_.data(), T, st.tau, false);
+  kx_.swap(kx_prev_);
+  problem_->apply_K(kx_.data(), x_.data(), false);
+  dual_proxarg_kernel<<<sgrid(m), kBlock, 0, s>>>(temp_.data(), y_.data(), S, kx_.data(), kx_prev_.data(),
+                                                  m, st.sigma, st.theta);
+  PB_CHECK_LAUNCH();
+  y_.swap(y_prev_);
+  for (auto& p : prox_fstar_) p->eval(y_.data(), temp_.data(), S, st.sigma, false);
+  ctx_->launches += 2;
+
+  const bool check = is_check_iteration();
+  double sums[4] = {0, 0, 0, 0};
+  if (check) {
+    primal_residual_kernel<<<part_p_cap_, kBlock, 0, s>>>(y_prev_.data(), y_.data(), S, kx_prev_.data(),
+                                                          kx_.data(), m, st.sigma, st.theta, part_p_.data());
+    PB_CHECK_LAUNCH();
+    dual_residual_kernel<<<part_d_cap_, kBlock, 0, s>>>(x_prev_.data(), x_.data(), T, kty_prev_.data(),
+                                                        kty_.data(), n, st.tau, part_d_.data());
+    PB_CHECK_LAUNCH();
+    fold_residuals_kernel<<<1, kBlock, 0, s>>>(part_p_.data(), part_p_cap_, part_d_.data(), part_d_cap_,
+                                               d_sums_.data());
+    PB_CHECK_LAUNCH();
+    ctx_->launches += 3;
+    d_sums_.download(sums, 4, s);
+    PB_CUDA(cudaStreamSynchronize(s));
+  }
+  st.iteration = iteration_;
+  pdhg_update(st, params_, sums, check);
+  iteration_++;
+
+  kty_.swap(kty_prev_);
+  problem_->apply_K(kty_.data(), y_.data(), true);
+}
+
+void BackendPDHG::profile(int n_iters, float out_ms[3]) {
+  ctx_->bind();
+  out_ms[0] = out_ms[1] = out_ms[2] = 0.f;
+  if (!fused_ || n_iters <= 0) { iterate(n_iters); return; }
+  cudaEvent_t ev[4];
+  for (auto& e : ev) PB_CUDA(cudaEventCreate(&e));
+  prof_ev_ = ev;
+  double acc[3] = {0, 0, 0};
+  for (int i = 0; i < n_iters; ++i) {
+    PB_CUDA(cudaEventRecord(ev[0], ctx_->stream));
+    iteration_fused();
+    PB_CUDA(cudaEventRecord(ev[3], ctx_->stream));
+    PB_CUDA(cudaEventSynchronize(ev[3]));
+    for (int k = 0; k < 3; ++k) {
+      float ms = 0.f;
+      PB_CUDA(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
+      acc[k] += ms;
+    }
+  }
+  prof_ev_ = nullptr;
+  for (auto& e : ev) cudaEventDestroy(e);
+  for (int k = 0; k < 3; ++k) out_ms[k] = static_cast<float>(acc[k] / n_iters);
+}
+
+void BackendPDHG::iterate(int n_iters) {
+  ctx_->bind();
+  for (int i = 0; i < n_iters; ++i) {
+    if (fused_) iteration_fused();
+    else iteration_unfused();
+  }
+}
+
+PdhgState BackendPDHG::fetch_state() {
+  if (fused_) {
+    d_state_.download(&h_state_, 1, ctx_->stream);
+    PB_CUDA(cudaStreamSynchronize(ctx_->stream));
+  }
+  return h_state_;
+}
+
+void BackendPDHG::residuals(float out[6]) {
+  ctx_->bind();
+  const PdhgState st = fetch_state();
+  out[0] = st.primal_residual;
+  out[1] = st.dual_residual;
+  out[2] = st.primal_var_norm;
+  out[3] = st.dual_var_norm;
+  out[4] = st.eps_primal;
+  out[5] = st.eps_dual;
+}
+
+void BackendPDHG::stepsizes(double out[3]) {
+  ctx_->bind();
+  const PdhgState st = fetch_state();
+  out[0] = st.tau;
+  out[1] = st.sigma;
+  out[2] = st.theta;
+}
+
+void BackendPDHG::current_solution(float* h_x, float* h_z, float* h_y, float* h_w) {
+  ctx_->bind();
+  const size_t m = problem_->nrows(), n = problem_->ncols();
+  cudaStream_t s = ctx_->stream;
+  const PdhgState st = fetch_state();
+  if (h_x) x_.download(h_x, n, s);
+  if (h_y) y_.download(h_y, m, s);
+  if (h_w || h_z) {
+    const float* T = problem_->scaling_right();
+    const float* S = problem_->scaling_left();
+    if (fused_) {
+      // K x, K x_prev and K^T y_prev are not stored in fused mode: rebuild them with the
+      // unfused operator, honouring the zero-initialised history of the reference
+      if (h_w) {
+        if (sol_a_.size() != n) { sol_a_.resize(n); sol_b_.resize(n); }
+        if (iteration_ <= 1) sol_a_.zero(s);
+        else problem_->apply_K(sol_a_.data(), y_prev_.data(), true);
+        w_variable_kernel<<<sgrid(n), kBlock, 0, s>>>(sol_b_.data(), x_prev_.data(), x_.data(), T,
+                                                      sol_a_.data(), n, st.tau);
+        PB_CHECK_LAUNCH();
+        sol_b_.download(h_w, n, s);
+        PB_CUDA(cudaStreamSynchronize(s));
+      }
+      if (h_z) {
+        if (sol_a_.size() != m) { sol_a_.resize(m); sol_b_.resize(m); }
+        if (sol_c_.size() != m) sol_c_.resize(m);
+        if (iteration_ == 0) sol_a_.zero(s);
+        else problem_->apply_K(sol_a_.data(), x_.data(), false);
+        if (iteration_ <= 1) sol_b_.zero(s);
+        else problem_->apply_K(sol_b_.data(), x_prev_.data(), false);
+        z_variable_kernel<<<sgrid(m), kBlock, 0, s>>>(sol_c_.data(), y_prev_.data(), y_.data(), S,
+                                                      sol_a_.data(), sol_b_.data(), m, st.sigma, st.theta);
+        PB_CHECK_LAUNCH();
+        sol_c_.download(h_z, m, s);
+      }
+    } else {
+      if (h_w) {
+        w_variable_kernel<<<sgrid(n), kBlock, 0, s>>>(temp_.data(), x_prev_.data(), x_.data(), T,
+                                                      kty_prev_.data(), n, st.tau);
+        PB_CHECK_LAUNCH();
+        temp_.download(h_w, n, s);
+      }
+      if (h_z) {
+        z_variable_kernel<<<sgrid(m), kBlock, 0, s>>>(temp_.data(), y_prev_.data(), y_.data(), S,
+                                                      kx_.data(), kx_prev_.data(), m, st.sigma, st.theta);
+        PB_CHECK_LAUNCH();
+        temp_.download(h_z, m, s);
+      }
+    }
+  }
+  PB_CUDA(cudaStreamSynchronize(s));
+}
+
+std::shared_ptr<Backend> make_backend_pdhg(Context* ctx, std::shared_ptr<Problem> prob,
+                                           const pb_pdhg_options& opts, const pb_solver_options& sopts) {
+  return std::make_shared<BackendPDHG>(ctx, std::move(prob), opts, sopts);
+}
+
+}  // namespace pb

@@ -1,0 +1,294 @@
+// pb_problem.cu -- Problem::Initialize (prox domain checks, zero-prox fill, Pock-Chambolle
+// diagonal preconditioning, preconditioner averaging), normest and Dualize.
+// Reference: src/problem.cu:47-158 (domain), :195-323 (Initialize), :428-500 (normest),
+// :502-536 (AveragePreconditioners), :538-547 (Dualize).
+#include "pb_problem.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <iostream>
+
+#include "pb_reduce.cuh"
+
+namespace pb {
+
+// ---- small kernels for normest -------------------------------------------------------------------
+
+// out = sqrt(scale) * in   (normest_multiplies_sqrt, problem.cu:417-426)
+__global__ void __launch_bounds__(kBlock) mul_sqrt_kernel(float* __restrict__ out,
+                                                          const float* __restrict__ scale,
+                                                          const float* __restrict__ in, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x)
+    out[i] = sqrtf(scale[i]) * in[i];
+}
+
+__global__ void __launch_bounds__(kBlock) divide_kernel(float* __restrict__ v, size_t n, float fac) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x)
+    v[i] = v[i] / fac;
+}
+
+__global__ void __launch_bounds__(kBlock) sumsq_partial_kernel(const float* __restrict__ v, size_t n,
+                                                               double* __restrict__ part) {
+  double a = 0.0, b = 0.0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const float x = v[i];
+    a += static_cast<double>(x * x);
+  }
+  block_sum2(a, b);
+  if (threadIdx.x == 0) { part[2 * blockIdx.x] = a; part[2 * blockIdx.x + 1] = 0.0; }
+}
+
+__global__ void __launch_bounds__(kBlock) fold_kernel(const double* __restrict__ part, unsigned n,
+                                                      double* __restrict__ out) {
+  double a, b;
+  fold_partials2(part, n, a, b);
+  if (threadIdx.x == 0) { out[0] = a; out[1] = b; }
+}
+
+static double device_sumsq(Context* ctx, const float* v, size_t n, DeviceBuffer<double>& scratch) {
+  const unsigned grid = std::min<size_t>(grid_for(n), (size_t)ctx->num_sms * 8);
+  if (scratch.size() < 2 * (size_t)grid + 2) scratch.resize(2 * (size_t)grid + 2);
+  sumsq_partial_kernel<<<grid, kBlock, 0, ctx->stream>>>(v, n, scratch.data() + 2);
+  PB_CHECK_LAUNCH();
+  fold_kernel<<<1, kBlock, 0, ctx->stream>>>(scratch.data() + 2, grid, scratch.data());
+  PB_CHECK_LAUNCH();
+  ctx->launches += 2;
+  double h[2];
+  PB_CUDA(cudaMemcpyAsync(h, scratch.data(), sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  PB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return h[0];
+}
+
+// ---- domain checks ---------------------------------------------------------------------------------
+
+static ProxList sorted_by_index(const ProxList& proxs) {
+  ProxList s = proxs;
+  std::sort(s.begin(), s.end(), [](const std::shared_ptr<Prox>& a, const std::shared_ptr<Prox>& b) {
+    return a->index() < b->index();
+  });
+  return s;
+}
+
+// AddZeroProx (problem.cu:92-158): fill uncovered index ranges with identity proxes
+static void add_zero_prox(Context* ctx, ProxList& proxs, size_t n, const std::string& name) {
+  if (proxs.empty()) return;
+  ProxList s = sorted_by_index(proxs);
+  if (s[0]->index() > 0) proxs.push_back(make_prox_zero(ctx, 0, s[0]->index()));
+  for (size_t i = 0; i + 1 < s.size(); ++i) {
+    if (s[i]->end() + 1 < s[i + 1]->index()) {
+      const size_t start = s[i]->end() + 1;
+      proxs.push_back(make_prox_zero(ctx, start, s[i + 1]->index() - start));
+    }
+  }
+  const auto& last = s.back();
+  if (last->end() != n - 1) {
+    if (last->end() < n - 1) {
+      const size_t start = last->end() + 1;
+      proxs.push_back(make_prox_zero(ctx, start, (n - 1) - last->end()));
+    } else {
+      std::ostringstream ss;
+      ss << name << " (AddZeroProx): Last prox operator ends after the domain: [" << last->index()
+         << ", " << last->end() << "], end = " << n - 1 << "." << std::endl;
+      fail(PB_ERR_INVALID, ss.str());
+    }
+  }
+}
+
+// CheckDomainProx (problem.cu:47-89)
+static void check_domain_prox(const ProxList& proxs, size_t n, const std::string& name) {
+  if (proxs.empty()) return;
+  ProxList s = sorted_by_index(proxs);
+  for (size_t i = 0; i + 1 < s.size(); ++i) {
+    if (s[i]->end() != s[i + 1]->index() - 1) {
+      std::ostringstream ss;
+      ss << name << " (CheckDomainProx): Prox operators are overlapping: [" << s[i]->index() << ", "
+         << s[i]->end() << "] and [" << s[i + 1]->index() << ", " << s[i + 1]->end() << "]." << std::endl;
+      fail(PB_ERR_INVALID, ss.str());
+    }
+  }
+  const auto& last = s.back();
+  if (last->end() != n - 1) {
+    std::ostringstream ss;
+    ss << name << " (CheckDomainProx): Last prox operator "
+       << (last->end() < n - 1 ? "ends too early: [" : "ends after the domain: [") << last->index()
+       << ", " << last->end() << "], end = " << n - 1 << "." << std::endl;
+    fail(PB_ERR_INVALID, ss.str());
+  }
+}
+
+// ---- Problem ---------------------------------------------------------------------------------------
+
+void Problem::set_scaling_custom(const float* left, size_t nl, const float* right, size_t nr) {
+  scaling_type_ = kScalingCustom;
+  // the reference stores the SQUARES of the user vectors (problem.cu:344-364)
+  left_host_.resize(nl);
+  right_host_.resize(nr);
+  for (size_t i = 0; i < nl; ++i) left_host_[i] = left[i] * left[i];
+  for (size_t i = 0; i < nr; ++i) right_host_[i] = right[i] * right[i];
+}
+
+static bool is_uniform(const std::vector<float>& v) {
+  for (size_t i = 1; i < v.size(); ++i)
+    if (v[i] != v[0]) return false;
+  return true;
+}
+
+void Problem::initialize() {
+  ctx_->bind();
+  linop_->initialize();
+  if (!dims_set_) {
+    nrows_ = linop_->nrows();
+    ncols_ = linop_->ncols();
+  }
+  if (linop_->nrows() > nrows_ || linop_->ncols() > ncols_)
+    fail(PB_ERR_INVALID, "Size of linear operator exceeds the size of the variables.");
+  if (linop_->nrows() != nrows_ || linop_->ncols() != ncols_)
+    std::cout << "Size of linear operator (ncols=" << linop_->ncols() << ", nrows=" << linop_->nrows()
+              << ") doesn't match size of variables. There might be some unnecessary variables in the problem.\n";
+  if (nrows_ >= (1ull << 31) || ncols_ >= (1ull << 31))
+    fail(PB_ERR_UNSUPPORTED, "problem dimensions exceed 2^31-1");
+
+  if (prox_f_.empty() && prox_fstar_.empty())
+    fail(PB_ERR_INVALID, "No proximal operator for f or fstar specified.");
+  if (prox_g_.empty() && prox_gstar_.empty())
+    fail(PB_ERR_INVALID, "No proximal operator for g or gstar specified.");
+  if (!prox_f_.empty() && !prox_fstar_.empty())
+    fail(PB_ERR_INVALID, "Proximal operator for f AND fstar specified. Only set one!");
+  if (!prox_g_.empty() && !prox_gstar_.empty())
+    fail(PB_ERR_INVALID, "Proximal operator for g AND gstar specified. Only set one!");
+
+  add_zero_prox(ctx_, prox_f_, nrows_, "prox_f");
+  add_zero_prox(ctx_, prox_g_, ncols_, "prox_g");
+  add_zero_prox(ctx_, prox_fstar_, nrows_, "prox_fstar");
+  add_zero_prox(ctx_, prox_gstar_, ncols_, "prox_gstar");
+  check_domain_prox(prox_g_, ncols_, "prox_g");
+  check_domain_prox(prox_f_, nrows_, "prox_f");
+  check_domain_prox(prox_gstar_, ncols_, "prox_gstar");
+  check_domain_prox(prox_fstar_, nrows_, "prox_fstar");
+
+  if (scaling_type_ == kScalingAlpha) {
+    // Pock-Chambolle: Sigma_r = 1 / sum_c |K_rc|^alpha, T_c = 1 / sum_r |K_rc|^(2-alpha).
+    // An empty row/column reuses the previous value, and the carry runs from the last row
+    // into the first column because the reference uses one variable (problem.cu:262-287).
+    std::vector<float> rs, cs;
+    linop_->row_sums(scaling_alpha_, rs);
+    linop_->col_sums(static_cast<float>(2. - scaling_alpha_), cs);
+    left_host_.assign(nrows_, 0.f);
+    right_host_.assign(ncols_, 0.f);
+    float value = 1;
+    for (size_t r = 0; r < nrows_; ++r) {
+      const float s = r < rs.size() ? rs[r] : 0.f;
+      if (s > 0) value = static_cast<float>(1. / s);
+      left_host_[r] = value;
+    }
+    for (size_t c = 0; c < ncols_; ++c) {
+      const float s = c < cs.size() ? cs[c] : 0.f;
+      if (s > 0) value = static_cast<float>(1. / s);
+      right_host_[c] = value;
+    }
+  } else if (scaling_type_ == kScalingIdentity) {
+    left_host_.assign(nrows_, 1.f);
+    right_host_.assign(ncols_, 1.f);
+  } else {
+    if (left_host_.size() != nrows_ || right_host_.size() != ncols_)
+      fail(PB_ERR_INVALID,
+           "Preconditioners/diagonal scaling vectors do not fit the size of linear operator.");
+  }
+
+  average_preconditioners(right_host_, prox_g_.empty() ? prox_gstar_ : prox_g_);
+  average_preconditioners(left_host_, prox_f_.empty() ? prox_fstar_ : prox_f_);
+
+  left_uniform_ = is_uniform(left_host_);
+  right_uniform_ = is_uniform(right_host_);
+  d_left_.assign(left_host_, ctx_->stream);
+  d_right_.assign(right_host_, ctx_->stream);
+  dualized_ = false;
+  initialized_ = true;
+}
+
+// AveragePreconditioners (problem.cu:502-536): float running sum in group order, then divide.
+void Problem::average_preconditioners(std::vector<float>& precond, const ProxList& prox) {
+  std::vector<std::tuple<size_t, size_t, size_t>> groups;
+  for (auto& p : prox) {
+    if (p->diagsteps()) continue;
+    groups.clear();
+    p->get_separable_structure(groups);
+    for (auto& g : groups) {
+      const size_t idx = std::get<0>(g), cnt = std::get<1>(g), str = std::get<2>(g);
+      float avg = 0;
+      for (size_t c = 0; c < cnt; ++c) avg += precond[idx + c * str];
+      avg /= static_cast<float>(cnt);
+      for (size_t c = 0; c < cnt; ++c) precond[idx + c * str] = avg;
+    }
+  }
+}
+
+void Problem::dualize() {
+  prox_g_.swap(prox_fstar_);
+  prox_gstar_.swap(prox_f_);
+  std::swap(nrows_, ncols_);
+  d_left_.swap(d_right_);
+  std::swap(left_host_, right_host_);
+  std::swap(left_uniform_, right_uniform_);
+  dualized_ = !dualized_;
+}
+
+void Problem::apply_K(float* d_res, const float* d_rhs, bool adjoint) {
+  if (!dualized_) linop_->eval(d_res, d_rhs, 0.f, adjoint);
+  else linop_->eval(d_res, d_rhs, 0.f, !adjoint, /*negate=*/true);   // dual operator is -K^T
+}
+
+size_t Problem::gpu_mem_amount() const {
+  size_t mem = 0;
+  for (auto& p : prox_f_) mem += p->gpu_mem_amount();
+  for (auto& p : prox_g_) mem += p->gpu_mem_amount();
+  for (auto& p : prox_fstar_) mem += p->gpu_mem_amount();
+  for (auto& p : prox_gstar_) mem += p->gpu_mem_amount();
+  mem += linop_->gpu_mem_amount();
+  mem += sizeof(float) * (nrows_ + ncols_);
+  return mem;
+}
+
+// Power iteration on Sigma^1/2 K T^1/2 (problem.cu:428-500).
+float Problem::normest(float tol, int max_iters, const float* h_x0) {
+  ctx_->bind();
+  const size_t n = ncols_, m = nrows_;
+  DeviceBuffer<float> x(n), Ax(m), x_temp(n), Ax_temp(m);
+  DeviceBuffer<double> scratch;
+  std::vector<float> x_host(n);
+  if (h_x0) {
+    std::copy(h_x0, h_x0 + n, x_host.begin());
+  } else {
+    std::srand(0);   // the reference does not seed; a fixed seed keeps runs reproducible
+    for (auto& v : x_host) v = (float)std::rand() / (float)RAND_MAX;
+  }
+  x.upload(x_host.data(), n, ctx_->stream);
+  auto sgrid = [&](size_t k) { return (unsigned)std::min<size_t>(grid_for(k), (size_t)ctx_->num_sms * 32); };
+
+  float norm = 0, norm_prev;
+  for (int i = 0; i < max_iters; ++i) {
+    norm_prev = norm;
+    mul_sqrt_kernel<<<sgrid(n), kBlock, 0, ctx_->stream>>>(x_temp.data(), d_right_.data(), x.data(), n);
+    apply_K(Ax_temp.data(), x_temp.data(), false);
+    mul_sqrt_kernel<<<sgrid(m), kBlock, 0, ctx_->stream>>>(Ax.data(), d_left_.data(), Ax_temp.data(), m);
+    const float norm_Ax = std::sqrt(static_cast<float>(device_sumsq(ctx_, Ax.data(), m, scratch)));
+    mul_sqrt_kernel<<<sgrid(m), kBlock, 0, ctx_->stream>>>(Ax_temp.data(), d_left_.data(), Ax.data(), m);
+    apply_K(x_temp.data(), Ax_temp.data(), true);
+    mul_sqrt_kernel<<<sgrid(n), kBlock, 0, ctx_->stream>>>(x.data(), d_right_.data(), x_temp.data(), n);
+    PB_CHECK_LAUNCH();
+    ctx_->launches += 4;
+    const float norm_x = std::sqrt(static_cast<float>(device_sumsq(ctx_, x.data(), n, scratch)));
+    norm = norm_x / norm_Ax;
+    if (std::abs(norm_prev - norm) < tol * norm) break;
+    divide_kernel<<<sgrid(n), kBlock, 0, ctx_->stream>>>(x.data(), n, norm_x);
+    PB_CHECK_LAUNCH();
+    ctx_->launches++;
+  }
+  return norm;
+}
+
+}  // namespace pb

@@ -1,0 +1,418 @@
+// pb_prox.cu -- host-side prox objects and the unfused Prox::Eval path.
+#include "pb_prox.cuh"
+
+#include <algorithm>
+#include <cstring>
+
+namespace pb {
+
+// ---- slow path for groups that do not fit in registers (dim > kMaxRegDim) ---------------------
+// One thread per group, arguments re-read from memory (L1/L2 resident) instead of staged in a
+// per-thread local array like the reference's T[1024] (elem_operation_ind_simplex.hpp:28,63).
+
+__global__ void __launch_bounds__(kBlock) prox_large_kernel(ProxDesc p, float* __restrict__ res,
+                                                            const float* __restrict__ arg,
+                                                            const float* __restrict__ tdiag,
+                                                            float tau_scal, bool invert) {
+  const uint32_t tx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tx >= p.count) return;
+  const uint32_t dim = p.dim;
+  const bool moreau = p.moreau != 0;
+  const bool inv = moreau ? !invert : invert;
+  // argument as seen by the leaf (Moreau pre-scaling applied on the fly)
+  auto leaf_arg = [&](uint32_t i) -> float {
+    const uint32_t e = elem_index(p, tx, i);
+    const float a = arg[e];
+    if (!moreau) return a;
+    const float t = tau_scal * tdiag[e];
+    return invert ? a * t : a / t;
+  };
+  auto store = [&](uint32_t i, float r) {
+    const uint32_t e = elem_index(p, tx, i);
+    if (moreau) {
+      const float t = tau_scal * tdiag[e];
+      r = invert ? arg[e] - r / t : arg[e] - t * r;
+    }
+    res[e] = r;
+  };
+  const float td0 = tdiag[elem_index(p, tx, 0)];
+
+  if (p.kind == kProxNorm2) {
+    float sq = 0.f;
+    for (uint32_t i = 0; i < dim; ++i) { const float v = leaf_arg(i); sq += v * v; }
+    if (sq > 0.f) {
+      const float norm = sqrtf(sq);
+      Coeffs7 c;
+      load_coeffs(p.coeffs, tx, c);
+      const float tau = effective_tau(tau_scal, td0, inv);
+      const float r = scaled_fun_prox(p.fn, norm, tau, c);
+      for (uint32_t i = 0; i < dim; ++i) store(i, r * leaf_arg(i) / norm);
+    } else {
+      for (uint32_t i = 0; i < dim; ++i) store(i, 0.f);
+    }
+  } else if (p.kind == kProxSimplex) {
+    // Michelot's fixed point on the active set; same unique threshold as the sort-based scan.
+    float sum = 0.f;
+    for (uint32_t i = 0; i < dim; ++i) sum += leaf_arg(i);
+    uint32_t cnt = dim;
+    float t = static_cast<float>((static_cast<double>(sum) - 1.0) / static_cast<double>((float)cnt));
+    for (uint32_t it = 0; it < dim; ++it) {
+      float s2 = 0.f;
+      uint32_t c2 = 0;
+      for (uint32_t i = 0; i < dim; ++i) {
+        const float v = leaf_arg(i);
+        if (v > t) { s2 += v; ++c2; }
+      }
+      if (c2 == cnt || c2 == 0) break;
+      cnt = c2;
+      t = static_cast<float>((static_cast<double>(s2) - 1.0) / static_cast<double>((float)cnt));
+    }
+    for (uint32_t i = 0; i < dim; ++i) store(i, fmaxf(leaf_arg(i) - t, 0.f));
+  } else if (p.kind == kProxEpiQuad) {
+    const float a = p.epi_a ? p.epi_a[tx] : p.epi_a_val;
+    const float c = p.epi_c ? p.epi_c[tx] : p.epi_c_val;
+    float sqb = 0.f, sqx = 0.f;
+    for (uint32_t i = 0; i + 1 < dim; ++i) {
+      const float b = p.epi_b[tx + (size_t)p.count * i];
+      const float xs = leaf_arg(i) + b / (2 * a);
+      sqb += b * b;
+      sqx += xs * xs;
+    }
+    const float shift = sqb / (4 * a);
+    const float ys = leaf_arg(dim - 1) - c + shift;
+    float vv;
+    bool inside;
+    project_epi_quad(sqx, ys, a, vv, inside);
+    float y = ys;
+    const float norm = sqrtf(sqx);
+    const double scale = static_cast<double>(vv) / (2.0 * static_cast<double>(a));
+    float sq_new = 0.f;
+    for (uint32_t i = 0; i + 1 < dim; ++i) {
+      const float b = p.epi_b[tx + (size_t)p.count * i];
+      float xs = leaf_arg(i) + b / (2 * a);
+      if (!inside) {
+        xs = (norm > 0.f) ? static_cast<float>(scale * static_cast<double>(xs / norm)) : 0.f;
+        sq_new += xs * xs;
+      }
+      store(i, xs - b / (2 * a));
+    }
+    if (!inside) y = a * sq_new;
+    store(dim - 1, y + c - shift);
+  } else {   // 1D ops and zero have dim == 1 and never come here
+    for (uint32_t i = 0; i < dim; ++i) store(i, leaf_arg(i));
+  }
+}
+
+// ---- unfused leaf launch ------------------------------------------------------------------------
+
+template <int CAP>
+static void launch_cap(Context* ctx, const ProxDesc& d, float* res, const float* arg, const float* tdiag,
+                       float tau, bool invert) {
+  MemSource src{arg, tau};
+  ScaleRef sr{tdiag, 1.f};
+  const unsigned grid = std::min<size_t>(grid_for(d.count), (size_t)ctx->num_sms * 16);
+  prox_pass_kernel<CAP, MemSource><<<grid, kBlock, 0, ctx->stream>>>(d, src, res, sr, invert);
+  PB_CHECK_LAUNCH();
+  ctx->launches++;
+}
+
+void launch_leaf_unfused(Context* ctx, const ProxDesc& d, float* res, const float* arg,
+                         const float* tdiag, float tau, bool invert) {
+  if (d.count == 0) return;
+  switch (dim_cap(d.dim, d.kind)) {
+    case 1: launch_cap<1>(ctx, d, res, arg, tdiag, tau, invert); break;
+    case 2: launch_cap<2>(ctx, d, res, arg, tdiag, tau, invert); break;
+    case 4: launch_cap<4>(ctx, d, res, arg, tdiag, tau, invert); break;
+    case 8: launch_cap<8>(ctx, d, res, arg, tdiag, tau, invert); break;
+    case 16: launch_cap<16>(ctx, d, res, arg, tdiag, tau, invert); break;
+    case 32: launch_cap<32>(ctx, d, res, arg, tdiag, tau, invert); break;
+    case 64: launch_cap<64>(ctx, d, res, arg, tdiag, tau, invert); break;
+    default: {
+      prox_large_kernel<<<grid_for(d.count), kBlock, 0, ctx->stream>>>(d, res, arg, tdiag, tau, invert);
+      PB_CHECK_LAUNCH();
+      ctx->launches++;
+    }
+  }
+}
+
+// ---- small helper kernels ---------------------------------------------------------------------
+
+__global__ void __launch_bounds__(kBlock) moreau_prescale_kernel(float* __restrict__ out,
+                                                                 const float* __restrict__ arg,
+                                                                 const float* __restrict__ td, size_t n,
+                                                                 float tau, bool invert) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const float t = tau * td[i];
+    out[i] = invert ? arg[i] * t : arg[i] / t;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) moreau_postscale_kernel(float* __restrict__ res,
+                                                                  const float* __restrict__ arg,
+                                                                  const float* __restrict__ td, size_t n,
+                                                                  float tau, bool invert) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    if (invert) res[i] = arg[i] - res[i] / (tau * td[i]);
+    else res[i] = arg[i] - tau * td[i] * res[i];
+  }
+}
+
+// res[i] = arg[perm[i]]  /  res[perm[i]] = arg[i]   (prox_permute.cu:30-48)
+__global__ void __launch_bounds__(kBlock) permute_kernel(float* __restrict__ res,
+                                                         const float* __restrict__ arg,
+                                                         const int* __restrict__ perm, size_t n,
+                                                         bool inverse) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    if (inverse) res[perm[i]] = arg[i];
+    else res[i] = arg[perm[i]];
+  }
+}
+
+static unsigned stream_grid(Context* ctx, size_t n) {
+  return std::min<size_t>(grid_for(n), (size_t)ctx->num_sms * 32);
+}
+
+// ---- leaf proxes --------------------------------------------------------------------------------
+
+class ProxLeaf : public Prox {
+ public:
+  ProxLeaf(Context* ctx, int kind, size_t index, size_t count, size_t dim, bool interleaved,
+           bool diagsteps)
+      : Prox(ctx, index, count * dim, diagsteps), kind_(kind), count_(count), dim_(dim),
+        interleaved_(interleaved) {
+    if (index + count * dim >= (1ull << 31)) fail(PB_ERR_UNSUPPORTED, "prox range exceeds 2^31-1");
+  }
+  int kind() const override { return kind_; }
+  void get_separable_structure(std::vector<std::tuple<size_t, size_t, size_t>>& sep) const override {
+    if (kind_ == kProxZero) { sep.emplace_back(index_, size_, 1); return; }
+    // ProxSeparableSum (prox_separable_sum.hpp:65-77)
+    for (size_t i = 0; i < count_; ++i) {
+      if (interleaved_) sep.emplace_back(index_ + i * dim_, dim_, 1);
+      else sep.emplace_back(index_ + i, dim_, count_);
+    }
+  }
+  bool leaf_desc(ProxDesc& d, size_t base) const override {
+    d = ProxDesc();
+    d.kind = kind_;
+    d.index = (uint32_t)(index_ - base);
+    d.count = (uint32_t)count_;
+    d.dim = (uint32_t)dim_;
+    d.interleaved = interleaved_ ? 1 : 0;
+    fill_desc(d);
+    return true;
+  }
+  void eval_local(float* res, const float* arg, const float* td, float tau, bool invert) override {
+    ctx_->bind();
+    ProxDesc d;
+    leaf_desc(d, index_);
+    launch_leaf_unfused(ctx_, d, res, arg, td, tau, invert);
+  }
+
+ protected:
+  virtual void fill_desc(ProxDesc&) const {}
+  int kind_;
+  size_t count_, dim_;
+  bool interleaved_;
+};
+
+// ProxElemOperation with 7 coefficients (1D / Norm2 families) or none (simplex)
+class ProxElem : public ProxLeaf {
+ public:
+  ProxElem(Context* ctx, int kind, size_t index, size_t count, size_t dim, bool interleaved,
+           bool diagsteps, int function, const float* const coeffs[7], const size_t coeff_len[7])
+      : ProxLeaf(ctx, kind, index, count, kind == kProxElem1D ? 1 : dim, interleaved, diagsteps),
+        fn_(function) {
+    if (function < 0 || function >= PB_FUN_COUNT_) fail(PB_ERR_INVALID, "unknown Function1D id");
+    for (int k = 0; k < 7; ++k) {
+      const size_t len = coeffs ? coeff_len[k] : 0;
+      if (len == 0) fail(PB_ERR_INVALID, "ProxElemOperation: empty coefficient array");
+      if (len > 1) {
+        // reference: coeffs_[i].size() > 1 => device vector indexed by the group id
+        // (prox_elem_operation.inl:82-89,156-167)
+        if (len < count) fail(PB_ERR_INVALID, "ProxElemOperation: coefficient array shorter than count");
+        d_coeffs_[k].assign(std::vector<float>(coeffs[k], coeffs[k] + len), ctx->stream);
+        val_[k] = 0.f;
+      } else {
+        val_[k] = coeffs[k][0];
+      }
+    }
+  }
+  size_t gpu_mem_amount() const override {
+    size_t mem = 0;
+    for (int k = 0; k < 7; ++k)
+      if (d_coeffs_[k].size()) mem += count_ * sizeof(float);
+    return mem;
+  }
+
+ protected:
+  void fill_desc(ProxDesc& d) const override {
+    d.fn = fn_;
+    for (int k = 0; k < 7; ++k) {
+      d.coeffs.ptr[k] = d_coeffs_[k].size() ? d_coeffs_[k].data() : nullptr;
+      d.coeffs.val[k] = val_[k];
+    }
+  }
+
+ private:
+  int fn_;
+  float val_[7];
+  DeviceBuffer<float> d_coeffs_[7];
+};
+
+class ProxEpiQuad : public ProxLeaf {
+ public:
+  ProxEpiQuad(Context* ctx, size_t index, size_t count, size_t dim, bool interleaved, bool diagsteps,
+              const float* a, size_t na, const float* b, size_t nb, const float* c, size_t nc)
+      : ProxLeaf(ctx, kProxEpiQuad, index, count, dim, interleaved, diagsteps) {
+    // checks and messages of ProxIndEpiQuad::Initialize (prox_ind_epi_quad.cu:135-151)
+    if (dim < 2) fail(PB_ERR_INVALID, "Wrong input: ind_epi_quad needs dim >= 2!");
+    if (na != count && na != 1)
+      fail(PB_ERR_INVALID, "Wrong input: Coefficient a has to have dimension count or 1!");
+    for (size_t i = 0; i < na; ++i)
+      if (a[i] <= 0) fail(PB_ERR_INVALID, "Wrong input: Coefficient a must be greater 0!");
+    if (nb != count * (dim - 1))
+      fail(PB_ERR_INVALID, "Wrong input: Coefficient b has to have dimension count*(dim-1)!");
+    if (nc != count && nc != 1)
+      fail(PB_ERR_INVALID, "Wrong input: Coefficient c has to have dimension count or 1!");
+    if (na != 1) d_a_.assign(std::vector<float>(a, a + na), ctx->stream); else a_val_ = a[0];
+    if (nc != 1) d_c_.assign(std::vector<float>(c, c + nc), ctx->stream); else c_val_ = c[0];
+    d_b_.assign(std::vector<float>(b, b + nb), ctx->stream);
+  }
+  size_t gpu_mem_amount() const override {
+    return (d_a_.size() + d_b_.size() + d_c_.size()) * sizeof(float);
+  }
+
+ protected:
+  void fill_desc(ProxDesc& d) const override {
+    d.interleaved = 0;   // the kernel addresses planar regardless (prox_ind_epi_quad.cu:54-57)
+    d.epi_a = d_a_.size() ? d_a_.data() : nullptr;
+    d.epi_b = d_b_.data();
+    d.epi_c = d_c_.size() ? d_c_.data() : nullptr;
+    d.epi_a_val = a_val_;
+    d.epi_c_val = c_val_;
+  }
+
+ private:
+  DeviceBuffer<float> d_a_, d_b_, d_c_;
+  float a_val_ = 1.f, c_val_ = 0.f;
+};
+
+// ---- wrappers -----------------------------------------------------------------------------------
+
+class ProxMoreau : public Prox {
+ public:
+  ProxMoreau(Context* ctx, std::shared_ptr<Prox> inner)
+      : Prox(ctx, inner->index(), inner->size(), inner->diagsteps()), inner_(std::move(inner)) {}
+  int kind() const override { return kProxMoreau; }
+  size_t gpu_mem_amount() const override {
+    ProxDesc d;
+    const bool folded = inner_->leaf_desc(d, 0) && !d.moreau;
+    return (folded ? 0 : size_ * sizeof(float)) + inner_->gpu_mem_amount();
+  }
+  void get_separable_structure(std::vector<std::tuple<size_t, size_t, size_t>>& sep) const override {
+    inner_->get_separable_structure(sep);
+  }
+  bool leaf_desc(ProxDesc& d, size_t base) const override {
+    if (!inner_->leaf_desc(d, base)) return false;
+    if (d.moreau) return false;          // Moreau of Moreau: generic path
+    d.moreau = 1;
+    return true;
+  }
+  void eval_local(float* res, const float* arg, const float* td, float tau, bool invert) override {
+    ctx_->bind();
+    ProxDesc d;
+    if (leaf_desc(d, index_)) {          // pre/post scaling folded into the leaf kernel
+      launch_leaf_unfused(ctx_, d, res, arg, td, tau, invert);
+      return;
+    }
+    // generic: the reference's three steps (prox_moreau.cu:98-134)
+    if (scaled_.size() != size_) scaled_.resize(size_);
+    if (size_ == 0) return;
+    const unsigned grid = stream_grid(ctx_, size_);
+    moreau_prescale_kernel<<<grid, kBlock, 0, ctx_->stream>>>(scaled_.data(), arg, td, size_, tau, invert);
+    PB_CHECK_LAUNCH();
+    inner_->eval_local(res, scaled_.data(), td, tau, !invert);
+    moreau_postscale_kernel<<<grid, kBlock, 0, ctx_->stream>>>(res, arg, td, size_, tau, invert);
+    PB_CHECK_LAUNCH();
+    ctx_->launches += 2;
+  }
+
+ private:
+  std::shared_ptr<Prox> inner_;
+  DeviceBuffer<float> scaled_;
+};
+
+class ProxPermute : public Prox {
+ public:
+  ProxPermute(Context* ctx, std::shared_ptr<Prox> inner, const int* perm, size_t n)
+      : Prox(ctx, inner->index(), inner->size(), inner->diagsteps()), inner_(std::move(inner)) {
+    if (n != inner_->size()) {
+      std::ostringstream ss;
+      ss << "Permutation vector has wrong size (" << n << ") instead of " << inner_->size() << ".";
+      fail(PB_ERR_INVALID, ss.str());
+    }
+    for (size_t i = 0; i < n; ++i)
+      if (perm[i] < 0 || (size_t)perm[i] >= n) fail(PB_ERR_INVALID, "Permutation index out of range.");
+    d_perm_.assign(std::vector<int>(perm, perm + n), ctx->stream);
+    permuted_.resize(n);
+  }
+  int kind() const override { return kProxPermute; }
+  size_t gpu_mem_amount() const override {
+    return size_ * (sizeof(float) + sizeof(int)) + inner_->gpu_mem_amount();
+  }
+  void get_separable_structure(std::vector<std::tuple<size_t, size_t, size_t>>& sep) const override {
+    inner_->get_separable_structure(sep);
+  }
+  void eval_local(float* res, const float* arg, const float* td, float tau, bool invert) override {
+    ctx_->bind();
+    if (size_ == 0) return;
+    const unsigned grid = stream_grid(ctx_, size_);
+    // gather into res, inner prox res -> permuted_ with the UN-permuted tau (Appendix B #12),
+    // scatter back (prox_permute.cu:101-145)
+    permute_kernel<<<grid, kBlock, 0, ctx_->stream>>>(res, arg, d_perm_.data(), size_, false);
+    PB_CHECK_LAUNCH();
+    inner_->eval_local(permuted_.data(), res, td, tau, invert);
+    permute_kernel<<<grid, kBlock, 0, ctx_->stream>>>(res, permuted_.data(), d_perm_.data(), size_, true);
+    PB_CHECK_LAUNCH();
+    ctx_->launches += 2;
+  }
+
+ private:
+  std::shared_ptr<Prox> inner_;
+  DeviceBuffer<int> d_perm_;
+  DeviceBuffer<float> permuted_;
+};
+
+// ---- factories --------------------------------------------------------------------------------
+
+std::shared_ptr<Prox> make_prox_elem(Context* ctx, int kind, size_t index, size_t count, size_t dim,
+                                     bool interleaved, bool diagsteps, int function,
+                                     const float* const coeffs[7], const size_t coeff_len[7]) {
+  return std::make_shared<ProxElem>(ctx, kind, index, count, dim, interleaved, diagsteps, function,
+                                    coeffs, coeff_len);
+}
+std::shared_ptr<Prox> make_prox_simplex(Context* ctx, size_t index, size_t count, size_t dim,
+                                        bool interleaved, bool diagsteps) {
+  return std::make_shared<ProxLeaf>(ctx, kProxSimplex, index, count, dim, interleaved, diagsteps);
+}
+std::shared_ptr<Prox> make_prox_epi_quad(Context* ctx, size_t index, size_t count, size_t dim,
+                                         bool interleaved, bool diagsteps, const float* a, size_t na,
+                                         const float* b, size_t nb, const float* c, size_t nc) {
+  return std::make_shared<ProxEpiQuad>(ctx, index, count, dim, interleaved, diagsteps, a, na, b, nb, c, nc);
+}
+std::shared_ptr<Prox> make_prox_moreau(Context* ctx, std::shared_ptr<Prox> inner) {
+  return std::make_shared<ProxMoreau>(ctx, std::move(inner));
+}
+std::shared_ptr<Prox> make_prox_permute(Context* ctx, std::shared_ptr<Prox> inner, const int* perm,
+                                        size_t n) {
+  return std::make_shared<ProxPermute>(ctx, std::move(inner), perm, n);
+}
+std::shared_ptr<Prox> make_prox_zero(Context* ctx, size_t index, size_t size) {
+  // ProxZero(index,size): diagsteps = true (prox_zero.cu:27-30); modelled as a dim-1 identity leaf
+  return std::make_shared<ProxLeaf>(ctx, kProxZero, index, size, 1, false, true);
+}
+
+}  // namespace pb

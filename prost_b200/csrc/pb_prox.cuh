@@ -1,0 +1,357 @@
+// pb_prox.cuh -- separable proximal operators: POD descriptors, the in-register group
+// operations, the generic pass kernel (shared by the unfused Prox::Eval path and the fused
+// PDHG passes) and the host-side prox objects.
+//
+// Reference: ProxElemOperationKernel + Vector<T> addressing (prox_elem_operation.inl:32-94,
+// vector.hpp:42-48), one thread per group of `dim` elements; ProxMoreau (prox_moreau.cu:98-134)
+// is folded into the same kernel as a pre/post scaling in registers instead of two extra
+// passes over a scratch vector.
+#pragma once
+
+#include <memory>
+#include <tuple>
+#include <vector>
+
+#include "pb_common.cuh"
+#include "pb_math.cuh"
+
+namespace pb {
+
+enum ProxKind : int {
+  kProxZero = 0,
+  kProxElem1D = 1,
+  kProxNorm2 = 2,
+  kProxSimplex = 3,
+  kProxEpiQuad = 4,
+  kProxMoreau = 5,
+  kProxPermute = 6,
+};
+
+// per-element vector or scalar (ElemOpCoefficients: prox_elem_operation.hpp:104-109)
+struct CoeffRef {
+  const float* ptr[7];
+  float val[7];
+};
+
+// diagonal preconditioner entries: per-element vector, or one scalar when uniform
+struct ScaleRef {
+  const float* ptr;
+  float val;
+  __device__ __forceinline__ float at(uint32_t e) const { return ptr ? __ldg(ptr + e) : val; }
+};
+
+// POD view of a leaf prox (optionally evaluated through Moreau's identity)
+struct ProxDesc {
+  int kind = kProxZero;
+  int fn = 0;                 // pb_function1d for Elem1D / Norm2
+  uint32_t index = 0, count = 0, dim = 1;
+  int interleaved = 0;
+  int moreau = 0;
+  CoeffRef coeffs = {};
+  // epigraph-quadratic coefficients: a, c scalar-or-vector (count), b vector count*(dim-1), planar
+  const float* epi_a = nullptr; const float* epi_b = nullptr; const float* epi_c = nullptr;
+  float epi_a_val = 0.f, epi_c_val = 0.f;
+};
+
+constexpr int kMaxRegDim = 64;   // largest group held in registers; larger dims use the slow path
+constexpr int kMaxEpiRegDim = 8; // epigraph projections are instantiated for dim <= 8 only
+
+// smallest instantiated register capacity >= dim for a prox kind, 0 if none
+inline int dim_cap(size_t dim, int kind = kProxZero) {
+  if (kind == kProxEpiQuad && dim > (size_t)kMaxEpiRegDim) return 0;
+  const int caps[] = {1, 2, 4, 8, 16, 32, 64};
+  for (int c : caps)
+    if ((size_t)c >= dim) return c;
+  return 0;
+}
+
+#ifdef __CUDACC__
+
+// global element index of component i of group tx (Vector<T>::operator[], vector.hpp:42-48;
+// ProxIndEpiQuad is always planar, prox_ind_epi_quad.cu:54-57)
+__device__ __forceinline__ uint32_t elem_index(const ProxDesc& p, uint32_t tx, uint32_t i) {
+  const bool il = p.interleaved && p.kind != kProxEpiQuad;
+  return p.index + (il ? tx * p.dim + i : tx + p.count * i);
+}
+
+__device__ __forceinline__ void load_coeffs(const CoeffRef& c, uint32_t tx, Coeffs7& out) {
+#pragma unroll
+  for (int k = 0; k < 7; ++k) out.v[k] = c.ptr[k] ? __ldg(c.ptr[k] + tx) : c.val[k];
+}
+
+// Simplex projection of v[0:dim] (elem_operation_ind_simplex.hpp:47-115): sort descending,
+// first i with (sum_{k<i} s_k - 1)/i >= s_i, else (sum - 1)/dim; result max(v - t, 0).
+// The sort is a compare-exchange network on a register copy (the reference shell-sorts a
+// 4 KB per-thread local array); the scan is the reference's, including the double `1.`.
+template <int CAP>
+__device__ __forceinline__ float simplex_threshold(const float (&v)[CAP], uint32_t dim) {
+  float s[CAP];
+#pragma unroll
+  for (int i = 0; i < CAP; ++i) s[i] = (i < (int)dim) ? v[i] : -INFINITY;
+  // odd-even merge sort would be fewer exchanges; bitonic keeps the index math trivial and
+  // fully unrollable: CAP is a power of two.
+#pragma unroll
+  for (int k = 2; k <= CAP; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int i = 0; i < CAP; ++i) {
+        const int l = i ^ j;
+        if (l > i) {
+          const bool desc = ((i & k) == 0);     // descending overall
+          const float a = s[i], b = s[l];
+          const float hi = fmaxf(a, b), lo = fminf(a, b);
+          s[i] = desc ? hi : lo;
+          s[l] = desc ? lo : hi;
+        }
+      }
+    }
+  }
+  bool found = false;
+  float tmpsum = 0.f, tmax = 0.f;
+#pragma unroll
+  for (int ii = 1; ii < CAP; ++ii) {
+    if (!found && ii <= (int)dim - 1) {
+      tmpsum += s[ii - 1];
+      tmax = static_cast<float>((static_cast<double>(tmpsum) - 1.0) / static_cast<double>((float)ii));
+      if (tmax >= s[ii]) found = true;
+    }
+  }
+  if (!found) {
+    float last = s[0];
+#pragma unroll
+    for (int i = 1; i < CAP; ++i)
+      if (i == (int)dim - 1) last = s[i];
+    tmax = static_cast<float>((static_cast<double>(tmpsum + last) - 1.0) /
+                              static_cast<double>((float)dim));
+  }
+  return tmax;
+}
+
+// Leaf operation on one group held in registers: v (argument) is replaced by the prox.
+// td0 = tau_diag of the group's first component (all in-tree ops read only tau_diag[0],
+// Appendix B #10).
+template <int CAP>
+__device__ __forceinline__ void leaf_apply(const ProxDesc& p, uint32_t tx, float (&v)[CAP],
+                                           float tau_scal, float td0, bool invert) {
+  const uint32_t dim = p.dim;
+  switch (p.kind) {
+    case kProxElem1D: {
+      if (CAP == 1) {                       // dim is always 1 (ElemOperation1D::kDim)
+        Coeffs7 c;
+        load_coeffs(p.coeffs, tx, c);
+        v[0] = elem1d_apply(p.fn, v[0], tau_scal, td0, invert, c);
+      }
+      break;
+    }
+    case kProxNorm2: {
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < CAP; ++i)
+        if (i < (int)dim) sq += v[i] * v[i];
+      if (sq > 0.f) {
+        const float norm = sqrtf(sq);
+        Coeffs7 c;
+        load_coeffs(p.coeffs, tx, c);
+        const float tau = effective_tau(tau_scal, td0, invert);
+        const float r = scaled_fun_prox(p.fn, norm, tau, c);
+#pragma unroll
+        for (int i = 0; i < CAP; ++i)
+          if (i < (int)dim) v[i] = r * v[i] / norm;
+      } else {
+#pragma unroll
+        for (int i = 0; i < CAP; ++i) v[i] = 0.f;
+      }
+      break;
+    }
+    case kProxSimplex: {
+      const float t = simplex_threshold<CAP>(v, dim);
+#pragma unroll
+      for (int i = 0; i < CAP; ++i)
+        if (i < (int)dim) v[i] = fmaxf(v[i] - t, 0.f);
+      break;
+    }
+    case kProxEpiQuad: if (CAP >= 2 && CAP <= kMaxEpiRegDim) {
+      // prox_ind_epi_quad.cu:42-79: shift by b/(2a), project onto y >= a|x|^2, shift back.
+      // components 0..dim-2 are x, component dim-1 is y.
+      const float a = p.epi_a ? __ldg(p.epi_a + tx) : p.epi_a_val;
+      const float c = p.epi_c ? __ldg(p.epi_c + tx) : p.epi_c_val;
+      float bb[CAP];
+      float sqb = 0.f, sqx = 0.f, y0 = 0.f;
+#pragma unroll
+      for (int i = 0; i < CAP; ++i) {
+        bb[i] = 0.f;
+        if (i < (int)dim - 1) {
+          bb[i] = __ldg(p.epi_b + tx + (size_t)p.count * i);
+          v[i] = v[i] + bb[i] / (2 * a);
+          sqb += bb[i] * bb[i];
+          sqx += v[i] * v[i];
+        } else if (i == (int)dim - 1) {
+          y0 = v[i];
+        }
+      }
+      const float shift = sqb / (4 * a);
+      const float ys = y0 - c + shift;
+      float vv;
+      bool inside;
+      project_epi_quad(sqx, ys, a, vv, inside);
+      float y;
+      if (inside) {
+        y = ys;
+      } else {
+        const float norm = sqrtf(sqx);
+        float sq_new = 0.f;
+        const double scale = static_cast<double>(vv) / (2.0 * static_cast<double>(a));
+#pragma unroll
+        for (int i = 0; i < CAP; ++i)
+          if (i < (int)dim - 1) {
+            v[i] = (norm > 0.f) ? static_cast<float>(scale * static_cast<double>(v[i] / norm)) : 0.f;
+            sq_new += v[i] * v[i];
+          }
+        y = a * sq_new;
+      }
+#pragma unroll
+      for (int i = 0; i < CAP; ++i) {
+        if (i < (int)dim - 1) v[i] -= bb[i] / (2 * a);
+        else if (i == (int)dim - 1) v[i] = y + c - shift;
+      }
+      break;
+    } else break;
+    default: break;   // kProxZero: identity
+  }
+}
+
+// Leaf, or Moreau's identity around the leaf (prox_moreau.cu:29-61, 110-133):
+//   s = arg / (tau T)  (arg * tau T when inverted);  r = prox_leaf(s; !invert);
+//   res = arg - tau T r  (arg - r / (tau T) when inverted),  T per component.
+template <int CAP>
+__device__ __forceinline__ void group_apply(const ProxDesc& p, uint32_t tx, float (&v)[CAP],
+                                            const float (&td)[CAP], float tau_scal, bool invert) {
+  if (!p.moreau) {
+    leaf_apply<CAP>(p, tx, v, tau_scal, td[0], invert);
+    return;
+  }
+  float a[CAP];
+#pragma unroll
+  for (int i = 0; i < CAP; ++i) {
+    a[i] = v[i];
+    const float t = tau_scal * td[i];
+    v[i] = invert ? v[i] * t : v[i] / t;
+  }
+  leaf_apply<CAP>(p, tx, v, tau_scal, td[0], !invert);
+#pragma unroll
+  for (int i = 0; i < CAP; ++i) {
+    if (invert) v[i] = a[i] - v[i] / (tau_scal * td[i]);
+    else v[i] = a[i] - tau_scal * td[i] * v[i];
+  }
+}
+
+// Generic pass kernel.  `Src` supplies the prox argument of every element and may observe the
+// result (residual accumulation in the fused passes).  The source itself stays in the kernel
+// parameter (constant) space; its mutable per-thread part is `Src::Regs`:
+//   float  begin(r)                 scalar step for this pass, resets accumulators
+//   float  load(r, e, i)            argument of global element e (component slot i)
+//   void   post(r, e, i, result)    called after the prox
+//   void   finish(r)                block-level epilogue (residual partials)
+template <int CAP, class Src>
+__global__ void __launch_bounds__(kBlock) prox_pass_kernel(const ProxDesc p, const Src src,
+                                                           float* __restrict__ out,
+                                                           const ScaleRef tdiag, const bool invert) {
+  typename Src::Regs r;
+  const float tau = src.begin(r);
+  for (uint32_t tx = blockIdx.x * blockDim.x + threadIdx.x; tx < p.count;
+       tx += gridDim.x * blockDim.x) {
+    float v[CAP], td[CAP];
+#pragma unroll
+    for (int i = 0; i < CAP; ++i) {
+      v[i] = 0.f;
+      td[i] = 1.f;
+      if (i < (int)p.dim) {
+        const uint32_t e = elem_index(p, tx, i);
+        td[i] = tdiag.at(e);
+        v[i] = src.load(r, e, i);
+      }
+    }
+    group_apply<CAP>(p, tx, v, td, tau, invert);
+#pragma unroll
+    for (int i = 0; i < CAP; ++i) {
+      if (i < (int)p.dim) {
+        const uint32_t e = elem_index(p, tx, i);
+        out[e] = v[i];
+        src.post(r, e, i, v[i]);
+      }
+    }
+  }
+  src.finish(r);
+}
+
+// argument read from memory: the unfused Prox::Eval path
+struct MemSource {
+  const float* __restrict__ arg;
+  float tau_scal;
+  struct Regs {};
+  __device__ __forceinline__ float begin(Regs&) const { return tau_scal; }
+  __device__ __forceinline__ float load(Regs&, uint32_t e, int) const { return arg[e]; }
+  __device__ __forceinline__ void post(Regs&, uint32_t, int, float) const {}
+  __device__ __forceinline__ void finish(Regs&) const {}
+};
+
+#endif  // __CUDACC__
+
+// ---- host-side prox objects -------------------------------------------------------------------
+
+class Prox {
+ public:
+  Prox(Context* ctx, size_t index, size_t size, bool diagsteps)
+      : ctx_(ctx), index_(index), size_(size), diagsteps_(diagsteps) {}
+  virtual ~Prox() {}
+
+  size_t index() const { return index_; }
+  size_t size() const { return size_; }
+  size_t end() const { return index_ + size_ - 1; }
+  bool diagsteps() const { return diagsteps_; }
+  virtual int kind() const = 0;
+  virtual size_t gpu_mem_amount() const { return 0; }
+  // (index, count, stride) groups over which preconditioners are averaged (prox.cu:73-78,
+  // prox_separable_sum.hpp:65-77)
+  virtual void get_separable_structure(std::vector<std::tuple<size_t, size_t, size_t>>& sep) const {
+    sep.emplace_back(index_, size_, 1);
+  }
+
+  // Prox::Eval (prox.cu:26-43): full-length device vectors; slices by index.
+  void eval(float* d_result, const float* d_arg, const float* d_tau_diag, float tau, bool invert) {
+    eval_local(d_result + index_, d_arg + index_, d_tau_diag + index_, tau, invert);
+  }
+  // pointers already offset to the prox' first element
+  virtual void eval_local(float* d_res, const float* d_arg, const float* d_tau, float tau,
+                          bool invert) = 0;
+
+  // Descriptor with index relative to a vector that starts at element `base` of the global
+  // one (0 for full vectors, index() for local pointers).  Returns false when the prox is not
+  // a register-resident leaf (then only eval_local can evaluate it).
+  virtual bool leaf_desc(ProxDesc& out, size_t base) const { (void)out; (void)base; return false; }
+
+ protected:
+  Context* ctx_;
+  size_t index_, size_;
+  bool diagsteps_;
+};
+
+std::shared_ptr<Prox> make_prox_elem(Context* ctx, int kind, size_t index, size_t count, size_t dim,
+                                     bool interleaved, bool diagsteps, int function,
+                                     const float* const coeffs[7], const size_t coeff_len[7]);
+std::shared_ptr<Prox> make_prox_simplex(Context* ctx, size_t index, size_t count, size_t dim,
+                                        bool interleaved, bool diagsteps);
+std::shared_ptr<Prox> make_prox_epi_quad(Context* ctx, size_t index, size_t count, size_t dim,
+                                         bool interleaved, bool diagsteps, const float* a, size_t na,
+                                         const float* b, size_t nb, const float* c, size_t nc);
+std::shared_ptr<Prox> make_prox_moreau(Context* ctx, std::shared_ptr<Prox> inner);
+std::shared_ptr<Prox> make_prox_permute(Context* ctx, std::shared_ptr<Prox> inner, const int* perm,
+                                        size_t n);
+std::shared_ptr<Prox> make_prox_zero(Context* ctx, size_t index, size_t size);
+
+// launches prox_pass_kernel<CAP, MemSource> for a leaf descriptor (used by pb_prox.cu)
+void launch_leaf_unfused(Context* ctx, const ProxDesc& d, float* d_res, const float* d_arg,
+                         const float* d_tau, float tau, bool invert);
+
+}  // namespace pb

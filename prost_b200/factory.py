@@ -1,0 +1,91 @@
+"""MATLAB-free factory: builds blocks / proxes / problems from descriptions that use the
+reference's mex registry names and argument order (matlab/+prost/private/factory.cpp:18-134,
+288-445, 575-656, 820-882).
+
+  prox  description = (name, idx, size, diagsteps, data)      -- the 5-cell of factory.cpp:820-837
+  block description = (name, row, col, data)                  -- the 4-cell of factory.cpp:869-882
+
+``data`` per name (same order as the cell arrays the MATLAB front end sends):
+  elem_operation:1d:<fun>, elem_operation:norm2:<fun> : [count, dim, interleaved, [a,b,c,d,e,alpha,beta]]
+  elem_operation:ind_simplex                           : [count, dim, interleaved]
+  ind_epi_quad                                         : [count, dim, interleaved, [a, b, c]]
+  moreau                                               : [child description]
+  permute                                              : [child description, perm]
+  zero                                                 : []
+  gradient2d / gradient3d : [nx, ny, L, label_first]     diags : [nrows, ncols, factors, offsets]
+  dense : [A]     sparse : [A]     zero : [nrows, ncols]
+"""
+from . import api
+
+
+def create_prox(ctx, desc):
+    name, idx, size, diagsteps, data = desc
+    if name.startswith("elem_operation:1d:"):
+        count, dim, interleaved, coeffs = data
+        return api.ProxElemOperation1D(ctx, name.split(":")[2], idx, count, dim, interleaved, diagsteps, coeffs)
+    if name.startswith("elem_operation:norm2:"):
+        count, dim, interleaved, coeffs = data
+        return api.ProxElemOperationNorm2(ctx, name.split(":")[2], idx, count, dim, interleaved, diagsteps, coeffs)
+    if name == "elem_operation:ind_simplex":
+        count, dim, interleaved = data[:3]
+        return api.ProxElemOperationIndSimplex(ctx, idx, count, dim, interleaved, diagsteps)
+    if name == "ind_epi_quad":
+        count, dim, interleaved, (a, b, c) = data
+        return api.ProxIndEpiQuad(ctx, idx, count, dim, interleaved, diagsteps, a, b, c)
+    if name == "moreau":
+        return api.ProxMoreau(ctx, create_prox(ctx, data[0]))
+    if name == "permute":
+        return api.ProxPermute(ctx, create_prox(ctx, data[0]), data[1])
+    if name == "zero":
+        return api.ProxZero(ctx, idx, size)
+    raise api.ProstError(-4, f"Unknown prox '{name}'")
+
+
+def create_block(ctx, desc):
+    name, row, col, data = desc
+    if name == "gradient2d":
+        return api.BlockGradient2D(ctx, row, col, *data)
+    if name == "gradient3d":
+        return api.BlockGradient3D(ctx, row, col, *data)
+    if name == "diags":
+        nrows, ncols, factors, offsets = data
+        return api.BlockDiags(ctx, row, col, nrows, ncols, offsets, factors)
+    if name == "dense":
+        return api.BlockDense(ctx, row, col, data[0])
+    if name == "sparse":
+        return api.BlockSparse(ctx, row, col, data[0])
+    if name == "zero":
+        return api.BlockZero(ctx, row, col, *data)
+    raise api.ProstError(-4, f"Unknown block '{name}'")
+
+
+def create_linop(ctx, block_descs):
+    op = api.LinearOperator(ctx)
+    for d in block_descs:
+        op.AddBlock(create_block(ctx, d))
+    op.Initialize()
+    return op
+
+
+def create_problem(ctx, desc):
+    """desc: dict(nrows, ncols, blocks=[...], prox_g/prox_f/prox_gstar/prox_fstar=[...],
+    scaling=("alpha", a) | ("identity",) | ("custom", left, right))  (factory.cpp:950-1012)."""
+    p = api.Problem(ctx)
+    for b in desc.get("blocks", []):
+        p.AddBlock(create_block(ctx, b))
+    for key, add in (("prox_g", p.AddProx_g), ("prox_f", p.AddProx_f),
+                     ("prox_gstar", p.AddProx_gstar), ("prox_fstar", p.AddProx_fstar)):
+        for d in desc.get(key, []):
+            add(create_prox(ctx, d))
+    if "nrows" in desc:
+        p.SetDimensions(desc["nrows"], desc["ncols"])
+    sc = desc.get("scaling", ("alpha", 1.0))
+    if sc[0] == "alpha":
+        p.SetScalingAlpha(sc[1])
+    elif sc[0] == "identity":
+        p.SetScalingIdentity()
+    elif sc[0] == "custom":
+        p.SetScalingCustom(sc[1], sc[2])
+    else:
+        raise api.ProstError(-1, "Problem scaling variant not recognized.")
+    return p

@@ -1,0 +1,165 @@
+"""Shared test cases: operator and prox descriptions with the shapes the reference's own unit
+tests use (matlab/+prost/+test/*.m), plus edge cases."""
+import numpy as np
+import scipy.sparse as sp
+
+from prost_b200 import synthetic as syn
+
+
+def rng(seed):
+    return np.random.default_rng(seed)
+
+
+def coeffs(a=1, b=0, c=1, d=0, e=0, alpha=0, beta=0):
+    return [np.atleast_1d(np.asarray(v, dtype=np.float32)) for v in (a, b, c, d, e, alpha, beta)]
+
+
+# ---- linear operators: name -> list of block descriptions ----------------------------------------
+def linop_cases(small=False):
+    r = rng(7)
+    cases = {}
+    # test_linop_gradient2d.m:3-5 / test_linop_gradient3d.m (151 x 291 x 7)
+    g2 = (307, 229, 8) if not small else (13, 9, 3)
+    g3 = (151, 291, 7) if not small else (7, 11, 4)
+    for lf in (False, True):
+        cases[f"gradient2d_lf{int(lf)}"] = [("gradient2d", 0, 0, [g2[0], g2[1], g2[2], lf])]
+        cases[f"gradient3d_lf{int(lf)}"] = [("gradient3d", 0, 0, [g3[0], g3[1], g3[2], lf])]
+    cases["gradient2d_1x1"] = [("gradient2d", 0, 0, [1, 1, 1, False])]
+    cases["gradient2d_row"] = [("gradient2d", 0, 0, [1, 17, 2, False])]
+    cases["gradient3d_L1"] = [("gradient3d", 0, 0, [5, 6, 1, False])]
+    # test_linop_diags.m: 29 diagonals, 3 x 9 grid of blocks of size 5912 x 1131 (nrows >= ncols:
+    # the reference's adjoint launch is sized by nrows, block_diags.cu:211)
+    nr, nc, nd = (5912, 1131, 29) if not small else (97, 31, 5)
+    grid = (3, 9) if not small else (2, 3)
+    blocks = []
+    for i in range(grid[0]):
+        for j in range(grid[1]):
+            ofs = r.choice(np.arange(-(nr - 1), nc), size=nd, replace=False).astype(np.int64)
+            fac = r.standard_normal(nd).astype(np.float32)
+            blocks.append(("diags", i * nr, j * nc, [nr, nc, fac, ofs]))
+    cases["diags_grid"] = blocks
+    cases["diags_identity"] = [("diags", 0, 0, [50, 50, [1.0], [0]])]
+    cases["diags_wide"] = [("diags", 0, 0, [20, 45, [2.0, -1.0, 0.5], [0, 30, -3]])]   # ncols > nrows
+    # test_linop_dense.m: 718 x 534
+    dm, dn = (718, 534) if not small else (37, 21)
+    cases["dense"] = [("dense", 0, 0, [r.standard_normal((dm, dn)).astype(np.float32)])]
+    # test_linop_sparse_zero.m: random grid of sparse / zero blocks
+    sm, sn = (431, 257) if not small else (23, 17)
+    blocks = []
+    for i in range(3):
+        for j in range(2):
+            if (i + j) % 3 == 2:
+                blocks.append(("zero", i * sm, j * sn, [sm, sn]))
+            else:
+                A = sp.random(sm, sn, density=0.05, random_state=int(r.integers(1 << 30)), format="csc",
+                              dtype=np.float32)
+                blocks.append(("sparse", i * sm, j * sn, [A]))
+    cases["sparse_zero_grid"] = blocks
+    empty = sp.csc_matrix((11, 7), dtype=np.float32)
+    cases["sparse_empty"] = [("sparse", 0, 0, [empty])]
+    # mixed operator of the lifting config: gradient over labels + identity rows
+    nx, ny, L = (24, 20, 8) if not small else (6, 5, 3)
+    NL = nx * ny * L
+    cases["lifting_K"] = [("gradient2d", 0, 0, [nx, ny, L, False]), ("diags", 2 * NL, 0, [NL, NL, [1.0], [0]])]
+    return cases
+
+
+def linop_matrix(blocks):
+    """scipy matrix of a block list (float64), built from the closed forms in refmath."""
+    import refmath
+    mats, m, n = [], 0, 0
+    for name, row, col, data in blocks:
+        if name == "gradient2d":
+            nx, ny, L, lf = data
+            K = refmath.spmat_gradient2d(nx, ny, L)
+            if lf:
+                K = _label_first_perm(K, nx, ny, L, 2)
+        elif name == "gradient3d":
+            nx, ny, L, lf = data
+            K = refmath.spmat_gradient3d(nx, ny, L)
+            if lf:
+                K = _label_first_perm(K, nx, ny, L, 3)
+        elif name == "diags":
+            nr, nc, fac, ofs = data
+            K = refmath.spdiags_matrix(nr, nc, list(ofs), list(np.asarray(fac, dtype=np.float64)))
+        elif name == "dense":
+            K = sp.csr_matrix(np.asarray(data[0], dtype=np.float64))
+        elif name == "sparse":
+            K = sp.csr_matrix(data[0]).astype(np.float64)
+        elif name == "zero":
+            K = sp.csr_matrix((data[0], data[1]))
+        mats.append((row, col, K.tocoo()))
+        m, n = max(m, row + K.shape[0]), max(n, col + K.shape[1])
+    rows = np.concatenate([k.row + r for r, c, k in mats])
+    cols = np.concatenate([k.col + c for r, c, k in mats])
+    vals = np.concatenate([k.data for r, c, k in mats])
+    return sp.csr_matrix((vals, (rows, cols)), shape=(m, n))
+
+
+def _label_first_perm(K, nx, ny, L, ncomp):
+    """Re-index a planar (y + x*ny + l*nx*ny) gradient matrix to the label-first layout
+    (l + y*L + x*ny*L) on both sides (block_gradient2d.cu:55-58)."""
+    N = nx * ny * L
+    idx = np.arange(N)
+    l, rem = idx // (nx * ny), idx % (nx * ny)
+    x, y = rem // ny, rem % ny
+    lf = l + y * L + x * ny * L                # planar index -> label-first index
+    P = sp.csr_matrix((np.ones(N), (lf, idx)), shape=(N, N))     # v_lf = P v_planar
+    Pr = sp.block_diag([P] * ncomp)
+    return (Pr @ K @ P.T).tocsr()
+
+
+# ---- proxes: name -> (description, n) --------------------------------------------------------------
+def prox_cases(small=False):
+    r = rng(11)
+    cases = {}
+    N1 = 5000 if not small else 257
+    for fun in ["zero", "abs", "square", "ind_leq0", "ind_geq0", "ind_eq0", "ind_box01", "max_pos0", "l0",
+                "huber", "lq", "truncquad", "trunclin", "lq_plus_eps"]:
+        c = coeffs(a=r.uniform(0.5, 2, N1), b=r.standard_normal(N1), c=r.uniform(0.5, 2, N1),
+                   d=r.standard_normal(N1) * 0.3, e=r.uniform(0, 1, N1),
+                   alpha=(0.5 if fun == "lq" else r.uniform(0.1, 1)), beta=r.uniform(0.1, 1))
+        cases[f"1d_{fun}_vec"] = (("elem_operation:1d:" + fun, 0, N1, True, [N1, 1, False, c]), N1)
+        cases[f"1d_{fun}_scalar"] = (("elem_operation:1d:" + fun, 0, N1, True,
+                                      [N1, 1, False, coeffs(a=1, b=0.3, c=0.7, d=0, e=0, alpha=0.6, beta=0.4)]), N1)
+    cases["1d_lq_q03"] = (("elem_operation:1d:lq", 0, N1, True, [N1, 1, False, coeffs(c=0.5, alpha=0.3)]), N1)
+    cases["1d_lq_q15"] = (("elem_operation:1d:lq", 0, N1, True, [N1, 1, False, coeffs(c=0.5, alpha=1.5)]), N1)
+    cases["1d_a0"] = (("elem_operation:1d:abs", 0, N1, True, [N1, 1, False, coeffs(a=0, d=0.2, e=0.5)]), N1)
+    # test_prox_sum_norm2.m: N = 6000, d = 7, planar, ind_leq0 with b = 1  (projection on unit balls)
+    N2, d2 = (6000, 7) if not small else (101, 7)
+    cases["norm2_ball_d7"] = (("elem_operation:norm2:ind_leq0", 0, N2 * d2, False,
+                               [N2, d2, False, coeffs(a=1, b=1, c=1)]), N2 * d2)
+    for d in (1, 2, 3, 6, 64, 70):
+        for il in (False, True):
+            n = (2000 if not small else 53)
+            cases[f"norm2_abs_d{d}_il{int(il)}"] = (
+                ("elem_operation:norm2:abs", 0, n * d, False,
+                 [n, d, il, coeffs(a=r.uniform(0.5, 2, n), b=0.1, c=r.uniform(0.2, 1, n), d=0.05, e=0.3)]), n * d)
+    # test_prox_sum_ind_simplex.m: N = 1000, d = 289, planar
+    Ns, ds = (1000, 289) if not small else (37, 289)
+    cases["simplex_d289"] = (("elem_operation:ind_simplex", 0, Ns * ds, False, [Ns, ds, False]), Ns * ds)
+    for d in (1, 2, 5, 32, 64):
+        for il in (False, True):
+            n = 1500 if not small else 41
+            cases[f"simplex_d{d}_il{int(il)}"] = (("elem_operation:ind_simplex", 0, n * d, False, [n, d, il]), n * d)
+    # ind_epi_quad (sum_ind_epi_quad.m): dim 2, 3 and 9, scalar and per-element a / c
+    for d in (2, 3, 9):
+        n = 3000 if not small else 67
+        b = r.standard_normal(n * (d - 1)).astype(np.float32)
+        cases[f"epi_quad_d{d}_vec"] = (("ind_epi_quad", 0, n * d, False,
+                                        [n, d, False, [r.uniform(0.3, 2, n), b, r.standard_normal(n)]]), n * d)
+        cases[f"epi_quad_d{d}_scalar"] = (("ind_epi_quad", 0, n * d, False, [n, d, False, [[1.0], b, [0.0]]]), n * d)
+    # wrappers
+    n = 1200 if not small else 45
+    inner = ("elem_operation:norm2:abs", 0, n * 3, False, [n, 3, False, coeffs(c=0.8)])
+    cases["moreau_norm2"] = (("moreau", 0, n * 3, False, [inner]), n * 3)
+    cases["moreau_moreau"] = (("moreau", 0, n * 3, False, [("moreau", 0, n * 3, False, [inner])]), n * 3)
+    cases["moreau_simplex289"] = (("moreau", 0, 20 * 289, False,
+                                   [("elem_operation:ind_simplex", 0, 20 * 289, False, [20, 289, False])]), 20 * 289)
+    perm = r.permutation(n * 3).astype(np.int32)
+    cases["permute_norm2"] = (("permute", 0, n * 3, False, [inner, perm]), n * 3)
+    cases["permute_moreau"] = (("permute", 0, n * 3, False, [("moreau", 0, n * 3, False, [inner]), perm]), n * 3)
+    # a prox that does not start at 0 (Prox::Eval slices by index, prox.cu:26-43)
+    cases["offset_1d"] = (("elem_operation:1d:abs", 17, n, True, [n, 1, False, coeffs(c=0.5)]), n + 40)
+    cases["zero"] = (("zero", 5, n, True, []), n + 9)
+    return cases

@@ -1,0 +1,61 @@
+"""Helpers shared by the PDHG parity tests: run one description through the CUDA backend and
+through the oracle with identical options."""
+import numpy as np
+
+import prost_b200 as pb
+from oracle_binding import OracleProblem, OraclePDHG
+
+TOL = dict(tol_rel_primal=0.0, tol_rel_dual=0.0, tol_abs_primal=0.0, tol_abs_dual=0.0)
+
+
+def run_cuda(ctx, desc, iters, fuse=True, x0=None, y0=None, tol=None, **opts):
+    prob = pb.create_problem(ctx, desc)
+    prob.Initialize()
+    popts = pb.pdhg_options(scale_steps_operator=0, fuse=int(fuse), **opts)
+    sopts = pb.solver_options(verbose=0, max_iters=iters, **(tol or TOL))
+    be = pb.BackendPDHG(ctx, prob, popts, sopts)
+    be.Initialize(x0, y0)
+    be.PerformIteration(iters)
+    x, z, y, w = be.current_solution()
+    return dict(x=x, z=z, y=y, w=w, res=be.residuals(), steps=be.stepsizes(), fused=be.is_fused, backend=be,
+                problem=prob)
+
+
+def run_oracle(desc, iters, x0=None, y0=None, tol=None, **opts):
+    prob = OracleProblem(desc)
+    o = OraclePDHG(prob, **opts, **(tol or TOL))
+    o.initialize(x0, y0)
+    o.iterate(iters)
+    x, z, y, w = o.solution()
+    return dict(x=x, z=z, y=y, w=w, res=o.residuals(), steps=o.stepsizes())
+
+
+def rel_err(a, b):
+    """max |a - b| / max(|b|_inf, tiny): the north star's per-element relative agreement."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def assert_parity(got, want, iter_tol=1e-5, res_tol=1e-4, label=""):
+    for k in ("x", "y"):
+        e = rel_err(got[k], want[k])
+        assert e <= iter_tol, f"{label}: iterate {k} rel err {e:.3e}"
+    for k in ("z", "w"):
+        e = rel_err(got[k], want[k])
+        assert e <= 20 * iter_tol, f"{label}: {k} rel err {e:.3e}"
+    for k in ("primal_residual", "dual_residual", "primal_var_norm", "dual_var_norm", "eps_primal", "eps_dual"):
+        a, b = got["res"][k], want["res"][k]
+        assert abs(a - b) <= res_tol * max(abs(b), 1e-6) + 1e-7, f"{label}: {k} {a} vs {b}"
+    for a, b in zip(got["steps"], want["steps"]):
+        assert abs(a - b) <= 1e-6 * max(abs(b), 1e-12), f"{label}: step sizes {got['steps']} vs {want['steps']}"
+
+
+def rof_energy(desc, x, lam=10.0):
+    """Primal ROF objective (lam/2)|u - f|^2 + sum |grad u|_2 (example_rof_pdgap.m)."""
+    nx, ny = desc["blocks"][0][3][0], desc["blocks"][0][3][1]
+    f = desc["data"]["f"].astype(np.float64).reshape(nx, ny)
+    u = x.astype(np.float64).reshape(nx, ny)
+    gx = np.zeros_like(u); gy = np.zeros_like(u)
+    gx[:-1, :] = u[1:, :] - u[:-1, :]
+    gy[:, :-1] = u[:, 1:] - u[:, :-1]
+    return 0.5 * lam * ((u - f) ** 2).sum() + np.sqrt(gx * gx + gy * gy).sum()

@@ -1,0 +1,203 @@
+"""GPU suite: the PDHG iteration (BackendPDHG::PerformIteration, backend_pdhg.cu:311-489) through
+the C ABI, fused and unfused, against the CPU oracle on identical synthetic inputs and iteration
+counts.  Bars (north star): iterates within 1e-5 relative, residuals/objective within 1e-4."""
+import numpy as np
+import pytest
+
+import prost_b200 as pb
+from prost_b200 import synthetic as syn
+from pdhg_util import assert_parity, rel_err, rof_energy, run_cuda, run_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("fuse", [True, False])
+@pytest.mark.parametrize("stepsize", ["alg1", "alg2", "goldstein", "boyd"])
+def test_rof_small_all_stepsizes(ctx, fuse, stepsize):
+    desc = syn.rof(48, 37)
+    opts = dict(stepsize=stepsize, residual_iter=3, alg2_gamma=0.5)
+    tol = dict(tol_rel_primal=1e-4, tol_rel_dual=1e-4, tol_abs_primal=1e-4, tol_abs_dual=1e-4)
+    got = run_cuda(ctx, desc, 150, fuse=fuse, tol=tol, **opts)
+    want = run_oracle(desc, 150, tol=tol, **opts)
+    assert got["fused"] == fuse
+    assert_parity(got, want, label=f"rof {stepsize} fuse={fuse}")
+
+
+def test_rof_c1_512_1000_iterations(ctx):
+    """BASELINE config 1: ROF 512 x 512, PDHG (Alg1), 1000 iterations."""
+    desc = syn.rof(512, 512)
+    got = run_cuda(ctx, desc, 1000, stepsize="alg1", residual_iter=10)
+    want = run_oracle(desc, 1000, stepsize="alg1", residual_iter=10)
+    assert got["fused"]
+    assert_parity(got, want, label="C1")
+    e_got, e_want = rof_energy(desc, got["x"]), rof_energy(desc, want["x"])
+    assert abs(e_got - e_want) <= 1e-4 * abs(e_want)
+
+
+@pytest.mark.parametrize("fuse", [True, False])
+def test_fused_equals_unfused(ctx, fuse):
+    """Both execution modes compute the same float operations; they must agree far below 1e-5."""
+    desc = syn.tvl1(40, 33, nc=3)
+    a = run_cuda(ctx, desc, 120, fuse=True, stepsize="boyd", residual_iter=5)
+    b = run_cuda(ctx, desc, 120, fuse=False, stepsize="boyd", residual_iter=5)
+    assert a["fused"] and not b["fused"]
+    for k in ("x", "y", "z", "w"):
+        assert rel_err(a[k], b[k]) <= 2e-6, k
+
+
+@pytest.mark.parametrize("name,desc_fn,iters", [
+    ("tvl1_color", lambda: syn.tvl1(64, 48, nc=3), 200),
+    ("tv3d", lambda: syn.tv3d(20, 24, 16), 200),
+    ("lifting", lambda: syn.lifting(24, 20, 8), 200),
+    ("lifting_L32", lambda: syn.lifting(16, 12, 32), 100),
+])
+@pytest.mark.parametrize("fuse", [True, False])
+def test_baseline_configs_small(ctx, name, desc_fn, iters, fuse):
+    """Configs 2-4 of BASELINE.json at oracle-friendly sizes, Boyd steps + diagonal preconditioning."""
+    desc = desc_fn()
+    tol = dict(tol_rel_primal=1e-4, tol_rel_dual=1e-4, tol_abs_primal=1e-4, tol_abs_dual=1e-4)
+    got = run_cuda(ctx, desc, iters, fuse=fuse, tol=tol, stepsize="boyd", residual_iter=10)
+    want = run_oracle(desc, iters, tol=tol, stepsize="boyd", residual_iter=10)
+    assert got["fused"] == fuse
+    assert_parity(got, want, label=name)
+
+
+def test_warm_start_quirks(ctx):
+    """x0/y0 != 0: the reference never applies K to x0 nor K^T to y0 (kx = kty = 0 during
+    iteration 0, backend_pdhg.cu:288-308); fused and unfused must both reproduce that."""
+    desc = syn.rof(32, 24)
+    r = np.random.default_rng(0)
+    x0 = r.random(desc["ncols"]).astype(np.float32)
+    y0 = (0.3 * r.standard_normal(desc["nrows"])).astype(np.float32)
+    for iters in (1, 2, 3, 25):
+        want = run_oracle(desc, iters, x0=x0, y0=y0, stepsize="alg1", residual_iter=1)
+        for fuse in (True, False):
+            got = run_cuda(ctx, desc, iters, fuse=fuse, x0=x0, y0=y0, stepsize="alg1", residual_iter=1)
+            assert_parity(got, want, label=f"warm start iters={iters} fuse={fuse}")
+
+
+def test_residual_iter_minus_one(ctx):
+    """residual_iter = -1 refreshes residuals at iteration 0 only (size_t % int, Appendix B #4)."""
+    desc = syn.rof(24, 24)
+    got = run_cuda(ctx, desc, 30, stepsize="alg1", residual_iter=-1)
+    want = run_oracle(desc, 30, stepsize="alg1", residual_iter=-1)
+    assert_parity(got, want, label="residual_iter=-1")
+
+
+def test_prox_f_given_instead_of_fstar(ctx):
+    """Problem with prox_g and prox_f: the backend conjugates through Moreau (backend_pdhg.cu:236-266)."""
+    N = 30 * 20
+    desc = syn.rof(30, 20)
+    desc = dict(desc)
+    desc.pop("prox_fstar")
+    c = syn._coeffs(a=1, b=0, c=1)
+    desc["prox_f"] = [("elem_operation:norm2:abs", 0, 2 * N, False, [N, 2, False, c])]   # TV = sum |.|_2
+    for fuse in (True, False):
+        got = run_cuda(ctx, desc, 100, fuse=fuse, stepsize="alg1", residual_iter=5)
+        want = run_oracle(desc, 100, stepsize="alg1", residual_iter=5)
+        assert_parity(got, want, label=f"moreau fuse={fuse}")
+    # and it is the same problem as the fstar formulation
+    ref = run_cuda(ctx, syn.rof(30, 20), 100, stepsize="alg1", residual_iter=5)
+    assert rel_err(got["x"], ref["x"]) < 1e-4
+
+
+def test_zero_prox_fill_and_dimension_mismatch(ctx):
+    """Uncovered index ranges get identity proxes (problem.cu:92-158); overlapping proxes throw."""
+    N = 16 * 16
+    desc = syn.rof(16, 16)
+    desc = dict(desc, nrows=2 * N + 10, ncols=N + 5)       # variables beyond the operator
+    got = run_cuda(ctx, desc, 40, stepsize="alg1", residual_iter=4)
+    want = run_oracle(desc, 40, stepsize="alg1", residual_iter=4)
+    assert_parity(got, want, label="zero fill")
+    bad = dict(syn.rof(16, 16))
+    bad["prox_g"] = bad["prox_g"] + [("zero", N - 3, 10, True, [])]
+    prob = pb.create_problem(ctx, bad)
+    with pytest.raises(pb.ProstError):
+        prob.Initialize()
+
+
+def test_solver_loop_convergence_and_callbacks(ctx):
+    """Solver::Solve (solver.cu:122-209): callback schedule, convergence on residuals, final copies."""
+    desc = syn.rof(64, 64)
+    prob = pb.create_problem(ctx, desc)
+    popts = pb.pdhg_options(scale_steps_operator=0, stepsize="alg2", alg2_gamma=0.5, residual_iter=10)
+    sopts = pb.solver_options(verbose=0, max_iters=5000, num_cback_calls=7, tol_rel_primal=1e-4, tol_rel_dual=1e-4,
+                              tol_abs_primal=1e-4, tol_abs_dual=1e-4)
+    be = pb.BackendPDHG(ctx, prob, popts, sopts)
+    solver = pb.Solver(prob, be)
+    calls = []
+    solver.SetIntermCallback(lambda it, x, y: calls.append((it, float(x.mean()))) or False)
+    nstop = [0]
+
+    def stop():
+        nstop[0] += 1
+        return False
+    solver.SetStoppingCallback(stop)
+    solver.Initialize()
+    result = solver.Solve()
+    assert result == pb.Solver.CONVERGED
+    assert 10 < solver.iterations < 5000 and nstop[0] == solver.iterations
+    assert calls[0][0] == 1 and calls[-1][0] == solver.iterations
+    res = be.residuals()
+    assert res["primal_residual"] < res["eps_primal"] and res["dual_residual"] < res["eps_dual"]
+    # same stopping iteration as the oracle running the same loop
+    o = __import__("oracle_binding")
+    op = o.OracleProblem(desc)
+    od = o.OraclePDHG(op, stepsize="alg2", alg2_gamma=0.5, residual_iter=10)
+    od.initialize()
+    it = 0
+    while it < 5000:
+        od.iterate(1)
+        it += 1
+        r = od.residuals()
+        if r["primal_residual"] < r["eps_primal"] and r["dual_residual"] < r["eps_dual"]:
+            break
+    assert abs(it - solver.iterations) <= 10
+    assert rel_err(solver.cur_primal_sol, od.solution()[0]) < 1e-3
+    # user stop
+    be2 = pb.BackendPDHG(ctx, prob, popts, sopts)
+    s2 = pb.Solver(prob, be2)
+    s2.SetStoppingCallback(lambda: True)
+    s2.Initialize()
+    assert s2.Solve() == pb.Solver.STOPPED_USER and s2.iterations == 1
+
+
+def test_normest_and_step_rescaling(ctx):
+    """scale_steps_operator: power iteration on Sigma^1/2 K T^1/2 (problem.cu:428-500); with
+    alpha = 1 preconditioning the estimate is <= 1."""
+    desc = syn.rof(40, 40)
+    prob = pb.create_problem(ctx, desc)
+    prob.Initialize()
+    x0 = np.random.default_rng(0).random(desc["ncols"]).astype(np.float32)
+    est = prob.normest(1e-6, 100, x0)
+    assert 0.9 < est <= 1.0 + 1e-4
+    prob2 = pb.create_problem(ctx, dict(desc, scaling=("identity",)))
+    prob2.Initialize()
+    est2 = prob2.normest(1e-6, 100, x0)
+    assert abs(est2 - np.sqrt(8)) < 0.15          # |grad| -> sqrt(8)
+
+
+@pytest.mark.parametrize("size", [(4096, 4096)])
+def test_full_size_properties(ctx, size):
+    """BASELINE metric config (ROF 4096^2) through size-independent properties: fused == unfused
+    after k iterations, dual feasibility |y|_2 <= 1, adjointness <Kx,y> == <x,K^T y>, and the ROF
+    energy decreases."""
+    nx, ny = size
+    desc = syn.rof(nx, ny)
+    a = run_cuda(ctx, desc, 30, fuse=True, stepsize="alg1", residual_iter=10)
+    b = run_cuda(ctx, desc, 30, fuse=False, stepsize="alg1", residual_iter=10)
+    assert a["fused"] and not b["fused"]
+    assert rel_err(a["x"], b["x"]) <= 2e-6 and rel_err(a["y"], b["y"]) <= 2e-6
+    for k in ("primal_residual", "dual_residual", "primal_var_norm", "dual_var_norm"):
+        assert abs(a["res"][k] - b["res"][k]) <= 1e-4 * abs(b["res"][k])
+    N = nx * ny
+    y = a["y"].astype(np.float64)
+    assert np.sqrt(y[:N] ** 2 + y[N:] ** 2).max() <= 1 + 1e-5
+    op = pb.create_linop(ctx, desc["blocks"])
+    r = np.random.default_rng(0)
+    u, p = r.standard_normal(N).astype(np.float32), r.standard_normal(2 * N).astype(np.float32)
+    lhs = float(np.dot(op.Eval(u).astype(np.float64), p))
+    rhs = float(np.dot(u.astype(np.float64), op.EvalAdjoint(p)))
+    assert abs(lhs - rhs) <= 1e-5 * abs(lhs)
+    f = desc["data"]["f"]
+    assert rof_energy(desc, a["x"]) < rof_energy(desc, f)
