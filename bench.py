@@ -189,7 +189,11 @@ def main():
         raise SystemExit("bench.py: the multi-GPU slab path is not built yet (round-1 work in progress)")
 
     torch.cuda.set_device(local_rank)
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) stream: the context launches on it and the CUDA events below are
+    # recorded on it, so the events bracket exactly the kernels of the timed region
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx = pb.Context(local_rank, stream.cuda_stream)
 
     f = syn.image(NX, NY)

@@ -223,7 +223,9 @@ typedef struct pb_pdhg_options {
   int stepsize_variant;       /* pb_pdhg_stepsize */
   /* extensions (not in the reference): */
   int fuse;                   /* 1 (default via pb_pdhg_default_options): fused passes where the
-                                 planner can; 0: reference-shaped unfused kernels */
+                                 planner can, specialised stencil kernels where the operator is a
+                                 planar gradient; 2: generic fused kernels only; 0: reference-shaped
+                                 unfused kernels */
   const float* normest_x0;    /* optional ncols-vector start for normest (parity runs) */
 } pb_pdhg_options;
 void pb_solver_default_options(pb_solver_options* o);   /* matlab/+prost/options.m:3-14 */

@@ -25,8 +25,11 @@ __device__ __forceinline__ float f1d_abs(float x0, float tau) {
 }
 
 __device__ __forceinline__ float f1d_square(float x0, float tau) {
-  // x0 / (1. + tau): the literal makes this a double division in the reference
-  return static_cast<float>(static_cast<double>(x0) / (1.0 + static_cast<double>(tau)));
+  // x0 / (1. + tau): the literal makes this a DOUBLE division in the reference.  It is evaluated
+  // as x0 * (1 / (1 + tau)) in double: the reciprocal is loop-invariant wherever tau is (uniform
+  // lambda and preconditioner), and the float result differs from the true double quotient only
+  // when that quotient lies within 2^-52 of a float rounding boundary (probability ~2^-28).
+  return static_cast<float>(static_cast<double>(x0) * (1.0 / (1.0 + static_cast<double>(tau))));
 }
 
 __device__ __forceinline__ float f1d_l0(float x0, float tau) {
@@ -134,11 +137,12 @@ __device__ __forceinline__ float scaled_fun_prox(int fn, float r, float tau, con
     prox_arg = __fsub_rn(num_arg, b);
     step = num_step;
   } else {
-    const double den = 1.0 + static_cast<double>(tau * e);
-    prox_arg = static_cast<float>(static_cast<double>(num_arg) / den - static_cast<double>(b));
-    step = static_cast<float>(static_cast<double>(num_step) / den);
+    const double rden = 1.0 / (1.0 + static_cast<double>(tau * e));     // shared by both quotients
+    prox_arg = static_cast<float>(static_cast<double>(num_arg) * rden - static_cast<double>(b));
+    step = static_cast<float>(static_cast<double>(num_step) * rden);
   }
-  return (fun1d(fn, prox_arg, step, c.v[5], c.v[6]) + b) / a;
+  const float res = fun1d(fn, prox_arg, step, c.v[5], c.v[6]) + b;
+  return a == 1.f ? res : res / a;        // res / 1 == res exactly
 }
 
 // ElemOperation1D::operator() on one element

@@ -15,6 +15,7 @@
 #include "pb_backend.cuh"
 #include "pb_fused.cuh"
 #include "pb_reduce.cuh"
+#include "pb_stencil.cuh"
 
 namespace pb {
 
@@ -193,6 +194,7 @@ class BackendPDHG : public Backend {
   // unfused only
   DeviceBuffer<float> temp_, kx_, kx_prev_, kty_, kty_prev_;
   // fused plan
+  StencilPlan stencil_;                // specialised gradient passes where the structure matches
   BlockList blocks_;
   std::vector<ProxDesc> g_descs_, f_descs_;
   unsigned part_p_cap_ = 0, part_d_cap_ = 0;
@@ -225,7 +227,9 @@ bool BackendPDHG::plan_fused() {
     }
     return true;
   };
-  return collect(prox_g_, g_descs_) && collect(prox_fstar_, f_descs_);
+  if (!(collect(prox_g_, g_descs_) && collect(prox_fstar_, f_descs_))) return false;
+  stencil_ = opts_.fuse >= 2 ? StencilPlan() : plan_stencil(K->blocks(), problem_->nrows(), problem_->ncols());
+  return true;
 }
 
 void BackendPDHG::initialize(const float* h_x0, size_t nx0, const float* h_y0, size_t ny0) {
@@ -308,8 +312,17 @@ void BackendPDHG::initialize(const float* h_x0, size_t nx0, const float* h_y0, s
   // partial-sum buffers: one (a, b) pair per CTA of every launch of a pass
   if (fused_) {
     part_d_cap_ = part_p_cap_ = 0;
-    for (auto& d : g_descs_) part_d_cap_ += fused_grid(ctx_, d);
-    for (auto& d : f_descs_) part_p_cap_ += fused_grid(ctx_, d);
+    const ScaleRef Tr = problem_->right_ref(), Sr = problem_->left_ref();
+    for (auto& d : g_descs_) {
+      const unsigned sg = stencil_primal_launch(ctx_, stencil_, d, x_.data(), y_.data(), y_prev_.data(), Tr,
+                                                nullptr, false, false, true, nullptr, x_prev_.data(), true);
+      part_d_cap_ += std::max(sg, fused_grid(ctx_, d));
+    }
+    for (auto& d : f_descs_) {
+      const unsigned sg = stencil_dual_launch(ctx_, stencil_, d, y_.data(), x_.data(), x_prev_.data(), Sr,
+                                              nullptr, false, true, nullptr, y_prev_.data(), true);
+      part_p_cap_ += std::max(sg, fused_grid(ctx_, d));
+    }
   } else {
     part_p_cap_ = std::min<size_t>(grid_for(m), (size_t)ctx_->num_sms * 8);
     part_d_cap_ = std::min<size_t>(grid_for(n), (size_t)ctx_->num_sms * 8);
@@ -329,19 +342,29 @@ void BackendPDHG::iteration_fused() {
 
   // primal pass: x_prev_ <- prox_g(x_ - tau T K^T y_), then swap so that x_ is x^{k+1}
   unsigned off = 0;
-  for (auto& d : g_descs_)
-    off += fused_primal_launch(ctx_, d, blocks_, x_.data(), y_.data(), y_prev_.data(), T, st,
-                               iteration_ == 0, iteration_ <= 1, check, part_d_.data() + 2 * (size_t)off,
-                               x_prev_.data());
+  for (auto& d : g_descs_) {
+    unsigned g = stencil_primal_launch(ctx_, stencil_, d, x_.data(), y_.data(), y_prev_.data(), T, st,
+                                       iteration_ == 0, iteration_ <= 1, check,
+                                       part_d_.data() + 2 * (size_t)off, x_prev_.data());
+    if (g == 0)
+      g = fused_primal_launch(ctx_, d, blocks_, x_.data(), y_.data(), y_prev_.data(), T, st, iteration_ == 0,
+                              iteration_ <= 1, check, part_d_.data() + 2 * (size_t)off, x_prev_.data());
+    off += g;
+  }
   const unsigned nd = off;
   x_.swap(x_prev_);
   if (prof_ev_) PB_CUDA(cudaEventRecord(prof_ev_[1], ctx_->stream));
 
   // dual pass: y_prev_ <- prox_f*(y_ + sigma S K(2x^{k+1} - x^k)) (theta-extrapolated), then swap
   off = 0;
-  for (auto& d : f_descs_)
-    off += fused_dual_launch(ctx_, d, blocks_, y_.data(), x_.data(), x_prev_.data(), S, st,
-                             iteration_ == 0, check, part_p_.data() + 2 * (size_t)off, y_prev_.data());
+  for (auto& d : f_descs_) {
+    unsigned g = stencil_dual_launch(ctx_, stencil_, d, y_.data(), x_.data(), x_prev_.data(), S, st,
+                                     iteration_ == 0, check, part_p_.data() + 2 * (size_t)off, y_prev_.data());
+    if (g == 0)
+      g = fused_dual_launch(ctx_, d, blocks_, y_.data(), x_.data(), x_prev_.data(), S, st, iteration_ == 0,
+                            check, part_p_.data() + 2 * (size_t)off, y_prev_.data());
+    off += g;
+  }
   const unsigned np = off;
   y_.swap(y_prev_);
   if (prof_ev_) PB_CUDA(cudaEventRecord(prof_ev_[2], ctx_->stream));

@@ -238,8 +238,15 @@ void Problem::dualize() {
 }
 
 void Problem::apply_K(float* d_res, const float* d_rhs, bool adjoint) {
+  const bool transpose = dualized_ ? !adjoint : adjoint;
   if (!dualized_) linop_->eval(d_res, d_rhs, 0.f, adjoint);
   else linop_->eval(d_res, d_rhs, 0.f, !adjoint, /*negate=*/true);   // dual operator is -K^T
+  // variables beyond the operator's extent (SetDimensions larger than the blocks) see K = 0: the
+  // reference zero-fills the whole result vector (linearoperator.cu:140-141)
+  const size_t covered = transpose ? linop_->ncols() : linop_->nrows();
+  const size_t total = adjoint ? ncols_ : nrows_;
+  if (total > covered)
+    PB_CUDA(cudaMemsetAsync(d_res + covered, 0, (total - covered) * sizeof(float), ctx_->stream));
 }
 
 size_t Problem::gpu_mem_amount() const {

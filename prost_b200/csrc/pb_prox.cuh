@@ -131,16 +131,24 @@ __device__ __forceinline__ float simplex_threshold(const float (&v)[CAP], uint32
 // Leaf operation on one group held in registers: v (argument) is replaced by the prox.
 // td0 = tau_diag of the group's first component (all in-tree ops read only tau_diag[0],
 // Appendix B #10).
-template <int CAP>
+// KIND >= 0 fixes the prox kind at compile time (specialised kernels); KIND < 0 dispatches on
+// p.kind at run time (generic kernels).
+// FN >= 0 likewise fixes the Function1D member of the 1D / Norm2 families.
+// `pre` (optional) supplies coefficients already held in registers (uniform scalars in the
+// specialised kernels); otherwise they are fetched per group with load_coeffs.
+template <int CAP, int KIND = -1, int FN = -1>
 __device__ __forceinline__ void leaf_apply(const ProxDesc& p, uint32_t tx, float (&v)[CAP],
-                                           float tau_scal, float td0, bool invert) {
+                                           float tau_scal, float td0, bool invert,
+                                           const Coeffs7* pre = nullptr) {
   const uint32_t dim = p.dim;
-  switch (p.kind) {
+  const int kind = KIND >= 0 ? KIND : p.kind;
+  const int fn = FN >= 0 ? FN : p.fn;
+  switch (kind) {
     case kProxElem1D: {
       if (CAP == 1) {                       // dim is always 1 (ElemOperation1D::kDim)
         Coeffs7 c;
-        load_coeffs(p.coeffs, tx, c);
-        v[0] = elem1d_apply(p.fn, v[0], tau_scal, td0, invert, c);
+        if (pre) c = *pre; else load_coeffs(p.coeffs, tx, c);
+        v[0] = elem1d_apply(fn, v[0], tau_scal, td0, invert, c);
       }
       break;
     }
@@ -152,9 +160,9 @@ __device__ __forceinline__ void leaf_apply(const ProxDesc& p, uint32_t tx, float
       if (sq > 0.f) {
         const float norm = sqrtf(sq);
         Coeffs7 c;
-        load_coeffs(p.coeffs, tx, c);
+        if (pre) c = *pre; else load_coeffs(p.coeffs, tx, c);
         const float tau = effective_tau(tau_scal, td0, invert);
-        const float r = scaled_fun_prox(p.fn, norm, tau, c);
+        const float r = scaled_fun_prox(fn, norm, tau, c);
 #pragma unroll
         for (int i = 0; i < CAP; ++i)
           if (i < (int)dim) v[i] = r * v[i] / norm;
@@ -224,11 +232,12 @@ __device__ __forceinline__ void leaf_apply(const ProxDesc& p, uint32_t tx, float
 // Leaf, or Moreau's identity around the leaf (prox_moreau.cu:29-61, 110-133):
 //   s = arg / (tau T)  (arg * tau T when inverted);  r = prox_leaf(s; !invert);
 //   res = arg - tau T r  (arg - r / (tau T) when inverted),  T per component.
-template <int CAP>
+template <int CAP, int KIND = -1, int FN = -1>
 __device__ __forceinline__ void group_apply(const ProxDesc& p, uint32_t tx, float (&v)[CAP],
-                                            const float (&td)[CAP], float tau_scal, bool invert) {
+                                            const float (&td)[CAP], float tau_scal, bool invert,
+                                            const Coeffs7* pre = nullptr) {
   if (!p.moreau) {
-    leaf_apply<CAP>(p, tx, v, tau_scal, td[0], invert);
+    leaf_apply<CAP, KIND, FN>(p, tx, v, tau_scal, td[0], invert, pre);
     return;
   }
   float a[CAP];
@@ -238,7 +247,7 @@ __device__ __forceinline__ void group_apply(const ProxDesc& p, uint32_t tx, floa
     const float t = tau_scal * td[i];
     v[i] = invert ? v[i] * t : v[i] / t;
   }
-  leaf_apply<CAP>(p, tx, v, tau_scal, td[0], !invert);
+  leaf_apply<CAP, KIND, FN>(p, tx, v, tau_scal, td[0], !invert, pre);
 #pragma unroll
   for (int i = 0; i < CAP; ++i) {
     if (invert) v[i] = a[i] - v[i] / (tau_scal * td[i]);

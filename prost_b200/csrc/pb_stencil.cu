@@ -1,0 +1,307 @@
+// pb_stencil.cu -- pattern matching and launch of the specialised gradient passes (pb_stencil.cuh).
+// Compiled once per PB_STENCIL_PART (0..3) so the instantiations build in parallel:
+//   part 0  planner + primal kernels with one-element groups (Elem1D / Zero)
+//   part 1  primal kernels with per-pixel label groups (simplex)
+//   part 2  dual Norm2 kernels on the gradient rows
+//   part 3  dual pass on identity rows (generic leaf prox, no stencil)
+#include "pb_stencil.cuh"
+
+#include <algorithm>
+
+#ifndef PB_STENCIL_PART
+#error "compile with -DPB_STENCIL_PART=<0..3>"
+#endif
+
+namespace pb {
+
+// implemented in the other parts
+unsigned stencil_primal_simplex_launch(Context* ctx, const GradGeom& g, bool three_d, const ProxDesc& d,
+                                       const float* x, const float* y, const float* y_prev, ScaleRef T,
+                                       const PdhgState* st, bool kty_zero, bool ktyprev_zero, bool check,
+                                       double* partials, float* x_out, bool dry_run);
+unsigned stencil_dual_norm2_launch(Context* ctx, const GradGeom& g, bool three_d, const ProxDesc& d,
+                                   const float* y, const float* x_new, const float* x_old, ScaleRef S,
+                                   const PdhgState* st, bool kxprev_zero, bool check, double* partials,
+                                   float* y_out, bool dry_run);
+unsigned stencil_dual_identity_launch(Context* ctx, const GradGeom& g, const ProxDesc& d, const float* y,
+                                      const float* x_new, const float* x_old, ScaleRef S, const PdhgState* st,
+                                      bool kxprev_zero, bool check, double* partials, float* y_out,
+                                      bool dry_run);
+
+static inline GradGeom with_vec(GradGeom g, int vec) {
+  g.q = g.ny / vec;
+  g.div_q = FastDiv(g.q);
+  g.div_nx = FastDiv(g.nx);
+  return g;
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static inline unsigned grid_threads(size_t threads) {
+  return (unsigned)((threads + kStencilBlock - 1) / kStencilBlock);
+}
+
+#if PB_STENCIL_PART == 0
+
+StencilPlan plan_stencil(const std::vector<std::shared_ptr<Block>>& blocks, size_t nrows, size_t ncols) {
+  StencilPlan plan;
+  const Block* grad = nullptr;
+  const Block* ident = nullptr;
+  for (auto& b : blocks) {
+    if (b->kind() == kBlockZero) continue;
+    if ((b->kind() == kBlockGradient2D || b->kind() == kBlockGradient3D) && !grad) grad = b.get();
+    else if (b->kind() == kBlockDiags && !ident) ident = b.get();
+    else return plan;
+  }
+  if (!grad) return plan;
+  const BlockDesc gd = grad->desc();
+  if (gd.label_first || gd.row != 0 || gd.col != 0 || gd.ncols != ncols) return plan;
+  plan.three_d = grad->kind() == kBlockGradient3D;
+  GradGeom& g = plan.geom;
+  g.nx = gd.nx; g.ny = gd.ny; g.L = gd.L; g.nxny = gd.nx * gd.ny; g.plane = gd.plane;
+  if (ident) {
+    // exactly  f * I  over all columns, directly below the gradient rows
+    const BlockDesc id = ident->desc();
+    if (id.ndiags != 1 || id.col != 0 || id.ncols != gd.ncols || id.nrows != gd.ncols ||
+        id.row != gd.nrows)
+      return plan;
+    long long ofs = 0;
+    float fac = 0.f;
+    if (cudaMemcpy(&ofs, id.offsets, sizeof(ofs), cudaMemcpyDeviceToHost) != cudaSuccess) return plan;
+    if (cudaMemcpy(&fac, id.factors, sizeof(fac), cudaMemcpyDeviceToHost) != cudaSuccess) return plan;
+    if (ofs != 0) return plan;
+    g.has_id = 1;
+    g.id_row = id.row;
+    g.id_factor = fac;
+    if (nrows < (size_t)id.row + id.nrows) return plan;
+  }
+  plan.ok = true;
+  return plan;
+}
+
+template <int VEC, int KIND, int FN, bool THREE_D, bool HAS_ID>
+static void primal1_launch(Context* ctx, unsigned grid, const GradGeom& g, const ProxDesc& d, const float* x,
+                           const float* y, const float* y_prev, ScaleRef T, const PdhgState* st,
+                           bool kty_zero, bool ktyprev_zero, bool check, double* partials, float* x_out) {
+  if (check)
+    grad_primal_kernel<VEC, 1, KIND, FN, THREE_D, HAS_ID, true><<<grid, kStencilBlock, 0, ctx->stream>>>(
+        g, d, x, y, y_prev, T, st, kty_zero, ktyprev_zero, partials, x_out);
+  else
+    grad_primal_kernel<VEC, 1, KIND, FN, THREE_D, HAS_ID, false><<<grid, kStencilBlock, 0, ctx->stream>>>(
+        g, d, x, y, y_prev, T, st, kty_zero, ktyprev_zero, partials, x_out);
+}
+
+template <int VEC, int KIND, int FN>
+static void primal1_geom(Context* ctx, unsigned grid, const GradGeom& g, bool three_d, const ProxDesc& d,
+                         const float* x, const float* y, const float* y_prev, ScaleRef T, const PdhgState* st,
+                         bool kty_zero, bool ktyprev_zero, bool check, double* partials, float* x_out) {
+#define PB_ARGS ctx, grid, g, d, x, y, y_prev, T, st, kty_zero, ktyprev_zero, check, partials, x_out
+  if (three_d) {
+    if (g.has_id) primal1_launch<VEC, KIND, FN, true, true>(PB_ARGS);
+    else primal1_launch<VEC, KIND, FN, true, false>(PB_ARGS);
+  } else {
+    if (g.has_id) primal1_launch<VEC, KIND, FN, false, true>(PB_ARGS);
+    else primal1_launch<VEC, KIND, FN, false, false>(PB_ARGS);
+  }
+#undef PB_ARGS
+}
+
+unsigned stencil_primal_launch(Context* ctx, const StencilPlan& plan, const ProxDesc& d, const float* x,
+                               const float* y, const float* y_prev, ScaleRef T, const PdhgState* st,
+                               bool kty_zero, bool ktyprev_zero, bool check, double* partials, float* x_out,
+                               bool dry_run) {
+  if (!plan.ok || d.index != 0) return 0;
+  const GradGeom& g0 = plan.geom;
+  if (d.kind == kProxSimplex)
+    return stencil_primal_simplex_launch(ctx, g0, plan.three_d, d, x, y, y_prev, T, st, kty_zero,
+                                         ktyprev_zero, check, partials, x_out, dry_run);
+  if (d.kind != kProxElem1D && d.kind != kProxZero) return 0;
+  if (d.dim != 1 || d.count != g0.plane) return 0;
+  bool vec4 = (g0.ny % 4 == 0) && aligned16(x) && aligned16(y) && aligned16(y_prev) && aligned16(x_out) &&
+              (!T.ptr || aligned16(T.ptr)) && (!g0.has_id || g0.id_row % 4 == 0);
+  for (int k = 0; k < 7; ++k)
+    if (d.coeffs.ptr[k] && !aligned16(d.coeffs.ptr[k])) vec4 = false;
+  const int vec = vec4 ? 4 : 1;
+  const GradGeom g = with_vec(g0, vec);
+  const unsigned grid = grid_threads((size_t)g.q * g.nx * g.L);
+  if (dry_run || grid == 0) return grid;
+#define PB_ARGS ctx, grid, g, plan.three_d, d, x, y, y_prev, T, st, kty_zero, ktyprev_zero, check, partials, x_out
+  // Function1D members with their own instantiation (the data terms of the reference's examples:
+  // quadratic for ROF, abs for TV-L1); every other member dispatches at run time (FN = -1)
+  if (d.kind == kProxElem1D) {
+    if (d.fn == PB_FUN_SQUARE) {
+      if (vec == 4) primal1_geom<4, kProxElem1D, PB_FUN_SQUARE>(PB_ARGS); else primal1_geom<1, kProxElem1D, PB_FUN_SQUARE>(PB_ARGS);
+    } else if (d.fn == PB_FUN_ABS) {
+      if (vec == 4) primal1_geom<4, kProxElem1D, PB_FUN_ABS>(PB_ARGS); else primal1_geom<1, kProxElem1D, PB_FUN_ABS>(PB_ARGS);
+    } else {
+      if (vec == 4) primal1_geom<4, kProxElem1D, -1>(PB_ARGS); else primal1_geom<1, kProxElem1D, -1>(PB_ARGS);
+    }
+  } else {
+    if (vec == 4) primal1_geom<4, kProxZero, -1>(PB_ARGS); else primal1_geom<1, kProxZero, -1>(PB_ARGS);
+  }
+#undef PB_ARGS
+  PB_CHECK_LAUNCH();
+  ctx->launches++;
+  return grid;
+}
+
+unsigned stencil_dual_launch(Context* ctx, const StencilPlan& plan, const ProxDesc& d, const float* y,
+                             const float* x_new, const float* x_old, ScaleRef S, const PdhgState* st,
+                             bool kxprev_zero, bool check, double* partials, float* y_out, bool dry_run) {
+  if (!plan.ok) return 0;
+  const GradGeom& g = plan.geom;
+  const uint32_t grad_rows = (plan.three_d ? 3u : 2u) * g.plane;
+  if (d.index == 0 && d.kind == kProxNorm2 && (size_t)d.count * d.dim == grad_rows)
+    return stencil_dual_norm2_launch(ctx, g, plan.three_d, d, y, x_new, x_old, S, st, kxprev_zero, check,
+                                     partials, y_out, dry_run);
+  if (g.has_id && d.index == g.id_row && (size_t)d.count * d.dim == g.plane)
+    return stencil_dual_identity_launch(ctx, g, d, y, x_new, x_old, S, st, kxprev_zero, check, partials,
+                                        y_out, dry_run);
+  return 0;
+}
+
+#elif PB_STENCIL_PART == 1
+
+template <int CAPL, bool HAS_ID>
+static void simplex_launch(Context* ctx, unsigned grid, const GradGeom& g, const ProxDesc& d, const float* x,
+                           const float* y, const float* y_prev, ScaleRef T, const PdhgState* st,
+                           bool kty_zero, bool ktyprev_zero, bool check, double* partials, float* x_out) {
+  if (check)
+    grad_primal_kernel<1, CAPL, kProxSimplex, -1, false, HAS_ID, true><<<grid, kStencilBlock, 0, ctx->stream>>>(
+        g, d, x, y, y_prev, T, st, kty_zero, ktyprev_zero, partials, x_out);
+  else
+    grad_primal_kernel<1, CAPL, kProxSimplex, -1, false, HAS_ID, false><<<grid, kStencilBlock, 0, ctx->stream>>>(
+        g, d, x, y, y_prev, T, st, kty_zero, ktyprev_zero, partials, x_out);
+}
+
+unsigned stencil_primal_simplex_launch(Context* ctx, const GradGeom& g0, bool three_d, const ProxDesc& d,
+                                       const float* x, const float* y, const float* y_prev, ScaleRef T,
+                                       const PdhgState* st, bool kty_zero, bool ktyprev_zero, bool check,
+                                       double* partials, float* x_out, bool dry_run) {
+  // simplex over the labels of a pixel: planar, count = nx*ny, dim = L (2-D gradient only)
+  if (three_d || d.interleaved || d.moreau || d.count != g0.nxny || d.dim != g0.L || g0.L < 2 || g0.L > 32)
+    return 0;
+  const GradGeom g = with_vec(g0, 1);
+  const unsigned grid = grid_threads((size_t)g.q * g.nx);
+  if (dry_run || grid == 0) return grid;
+  const int cap = g.L <= 4 ? 4 : g.L <= 8 ? 8 : g.L <= 16 ? 16 : 32;
+#define PB_ARGS ctx, grid, g, d, x, y, y_prev, T, st, kty_zero, ktyprev_zero, check, partials, x_out
+#define PB_CASE(C) \
+  case C: if (g.has_id) simplex_launch<C, true>(PB_ARGS); else simplex_launch<C, false>(PB_ARGS); break;
+  switch (cap) { PB_CASE(4) PB_CASE(8) PB_CASE(16) PB_CASE(32) }
+#undef PB_CASE
+#undef PB_ARGS
+  PB_CHECK_LAUNCH();
+  ctx->launches++;
+  return grid;
+}
+
+#elif PB_STENCIL_PART == 2
+
+template <int VEC, int CAPL, int FN, bool THREE_D>
+static void dual_launch_fn(Context* ctx, unsigned grid, const GradGeom& g, const ProxDesc& d, const float* y,
+                           const float* x_new, const float* x_old, ScaleRef S, const PdhgState* st,
+                           bool kxprev_zero, bool check, double* partials, float* y_out) {
+  if (check)
+    grad_dual_norm2_kernel<VEC, CAPL, FN, THREE_D, true><<<grid, kStencilBlock, 0, ctx->stream>>>(
+        g, d, y, x_new, x_old, S, st, kxprev_zero, partials, y_out);
+  else
+    grad_dual_norm2_kernel<VEC, CAPL, FN, THREE_D, false><<<grid, kStencilBlock, 0, ctx->stream>>>(
+        g, d, y, x_new, x_old, S, st, kxprev_zero, partials, y_out);
+}
+
+// ind_leq0 (projection onto norm balls, the f* of TV) and abs (TV given as f, through Moreau) get
+// their own instantiation; other Function1D members dispatch at run time
+template <int VEC, int CAPL, bool THREE_D>
+static void dual_launch(Context* ctx, unsigned grid, const GradGeom& g, const ProxDesc& d, const float* y,
+                        const float* x_new, const float* x_old, ScaleRef S, const PdhgState* st,
+                        bool kxprev_zero, bool check, double* partials, float* y_out) {
+  if (d.fn == PB_FUN_IND_LEQ0)
+    dual_launch_fn<VEC, CAPL, PB_FUN_IND_LEQ0, THREE_D>(ctx, grid, g, d, y, x_new, x_old, S, st, kxprev_zero, check, partials, y_out);
+  else if (d.fn == PB_FUN_ABS)
+    dual_launch_fn<VEC, CAPL, PB_FUN_ABS, THREE_D>(ctx, grid, g, d, y, x_new, x_old, S, st, kxprev_zero, check, partials, y_out);
+  else
+    dual_launch_fn<VEC, CAPL, -1, THREE_D>(ctx, grid, g, d, y, x_new, x_old, S, st, kxprev_zero, check, partials, y_out);
+}
+
+unsigned stencil_dual_norm2_launch(Context* ctx, const GradGeom& g0, bool three_d, const ProxDesc& d,
+                                   const float* y, const float* x_new, const float* x_old, ScaleRef S,
+                                   const PdhgState* st, bool kxprev_zero, bool check, double* partials,
+                                   float* y_out, bool dry_run) {
+  if (d.interleaved) return 0;
+  const uint32_t ncomp = three_d ? 3u : 2u;
+  const bool per_voxel = d.count == g0.plane && d.dim == ncomp;
+  const bool per_pixel = !three_d && g0.L > 1 && d.count == g0.nxny && d.dim == ncomp * g0.L && g0.L <= 32;
+  if (!per_voxel && !per_pixel) return 0;
+  bool vec4 = (g0.ny % 4 == 0) && aligned16(y) && aligned16(x_new) && aligned16(x_old) && aligned16(y_out) &&
+              (!S.ptr || aligned16(S.ptr)) && (g0.plane % 4 == 0);
+  for (int k = 0; k < 7; ++k)
+    if (d.coeffs.ptr[k] && !aligned16(d.coeffs.ptr[k])) vec4 = false;
+  if (per_pixel && g0.L > 4) vec4 = false;             // keep the group within the register budget
+  const int vec = vec4 ? 4 : 1;
+  const GradGeom g = with_vec(g0, vec);
+  const unsigned grid = grid_threads((size_t)g.q * g.nx * (per_voxel ? g.L : 1u));
+  if (dry_run || grid == 0) return grid;
+#define PB_ARGS ctx, grid, g, d, y, x_new, x_old, S, st, kxprev_zero, check, partials, y_out
+  if (per_voxel) {
+    if (three_d) { if (vec == 4) dual_launch<4, 1, true>(PB_ARGS); else dual_launch<1, 1, true>(PB_ARGS); }
+    else { if (vec == 4) dual_launch<4, 1, false>(PB_ARGS); else dual_launch<1, 1, false>(PB_ARGS); }
+  } else {
+    const int cap = g.L <= 2 ? 2 : g.L <= 4 ? 4 : g.L <= 8 ? 8 : g.L <= 16 ? 16 : 32;
+    if (vec == 4) {
+      if (cap == 2) dual_launch<4, 2, false>(PB_ARGS); else dual_launch<4, 4, false>(PB_ARGS);
+    } else {
+      switch (cap) {
+        case 2: dual_launch<1, 2, false>(PB_ARGS); break;
+        case 4: dual_launch<1, 4, false>(PB_ARGS); break;
+        case 8: dual_launch<1, 8, false>(PB_ARGS); break;
+        case 16: dual_launch<1, 16, false>(PB_ARGS); break;
+        default: dual_launch<1, 32, false>(PB_ARGS); break;
+      }
+    }
+  }
+#undef PB_ARGS
+  PB_CHECK_LAUNCH();
+  ctx->launches++;
+  return grid;
+}
+
+#elif PB_STENCIL_PART == 3
+
+template <int CAP>
+static void ident_launch(Context* ctx, unsigned grid, const GradGeom& g, const ProxDesc& d, const float* y,
+                         const float* x_new, const float* x_old, ScaleRef S, const PdhgState* st,
+                         bool kxprev_zero, bool check, double* partials, float* y_out) {
+  if (check) {
+    IdentityDualSource<CAP, true> src{y, x_new, x_old, S, st, g.id_factor, g.id_row, kxprev_zero, partials};
+    prox_pass_kernel<CAP, IdentityDualSource<CAP, true>><<<grid, kBlock, 0, ctx->stream>>>(d, src, y_out, S, false);
+  } else {
+    IdentityDualSource<CAP, false> src{y, x_new, x_old, S, st, g.id_factor, g.id_row, kxprev_zero, partials};
+    prox_pass_kernel<CAP, IdentityDualSource<CAP, false>><<<grid, kBlock, 0, ctx->stream>>>(d, src, y_out, S, false);
+  }
+}
+
+unsigned stencil_dual_identity_launch(Context* ctx, const GradGeom& g, const ProxDesc& d, const float* y,
+                                      const float* x_new, const float* x_old, ScaleRef S, const PdhgState* st,
+                                      bool kxprev_zero, bool check, double* partials, float* y_out,
+                                      bool dry_run) {
+  const int cap = dim_cap(d.dim, d.kind);
+  if (cap == 0 || cap > 8) return 0;
+  const unsigned grid = (unsigned)std::min<size_t>(grid_for(d.count), (size_t)ctx->num_sms * 16);
+  if (dry_run || d.count == 0) return d.count ? grid : 0;
+#define PB_ARGS ctx, grid, g, d, y, x_new, x_old, S, st, kxprev_zero, check, partials, y_out
+  switch (cap) {
+    case 1: ident_launch<1>(PB_ARGS); break;
+    case 2: ident_launch<2>(PB_ARGS); break;
+    case 4: ident_launch<4>(PB_ARGS); break;
+    default: ident_launch<8>(PB_ARGS); break;
+  }
+#undef PB_ARGS
+  PB_CHECK_LAUNCH();
+  ctx->launches++;
+  return grid;
+}
+
+#endif
+
+}  // namespace pb

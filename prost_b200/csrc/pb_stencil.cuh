@@ -1,0 +1,523 @@
+// pb_stencil.cuh -- specialised fused PDHG passes for gradient operators in the planar layout.
+//
+// The generic fused kernel (pb_fused.cuh) interprets block/prox descriptors per element and
+// spends several hundred instructions per pixel doing so; on B200 that makes a 44 B/pixel
+// iteration instruction-bound (ncu: profiles/r1_generic_fused.md).  The kernels here fix the
+// operator structure at compile time:
+//
+//   K = [ BlockGradient2D | BlockGradient3D ]  at row 0 / col 0, label_first = false
+//       (+ optionally one identity block  f * I  below it, as in the lifted multilabel energy)
+//
+// and map threads to the image instead of to descriptor indices:
+//   * a thread owns VEC (1 or 4) consecutive y of one column, read with 128-bit loads;
+//   * (x, y, l) come from two multiply-high divisions per THREAD, not per element;
+//   * the y-neighbour comes from the thread's own vector (+ one scalar load), the x- and
+//     label-neighbours from aligned vector loads that hit L1/L2 (they are some other thread's
+//     primary loads), so every array still crosses HBM exactly once per pass;
+//   * the prox kind is a template parameter, the group lives in registers.
+//
+// Arithmetic (operation order, boundary handling, residual formulas) is identical to the generic
+// fused pass and therefore to the reference:
+//   forward  block_gradient2d.cu:25-78, block_gradient3d.cu:25-81 (Neumann in x, y; Dirichlet in l)
+//   adjoint  block_gradient2d.cu:80-139, block_gradient3d.cu:83-150
+//   primal / dual arguments and residuals  backend_pdhg.cu:38-120
+#pragma once
+
+#include "pb_backend.cuh"
+#include "pb_fused.cuh"
+#include "pb_prox.cuh"
+#include "pb_reduce.cuh"
+
+namespace pb {
+
+struct GradGeom {
+  uint32_t nx = 0, ny = 0, L = 0, nxny = 0, plane = 0;
+  uint32_t q = 0;                 // ny / VEC
+  FastDiv div_q, div_nx;
+  int has_id = 0;                 // identity block  id_factor * I  at rows [id_row, id_row + plane)
+  uint32_t id_row = 0;
+  float id_factor = 1.f;
+};
+
+constexpr int kStencilBlock = 128;
+
+#ifdef __CUDACC__
+
+template <int VEC> struct VecIO;
+template <> struct VecIO<1> {
+  static __device__ __forceinline__ void ld(const float* __restrict__ p, float (&o)[1]) { o[0] = *p; }
+  static __device__ __forceinline__ void st(float* __restrict__ p, const float (&v)[1]) { *p = v[0]; }
+};
+template <> struct VecIO<4> {
+  static __device__ __forceinline__ void ld(const float* __restrict__ p, float (&o)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+  }
+  static __device__ __forceinline__ void st(float* __restrict__ p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+
+template <int VEC>
+__device__ __forceinline__ void load_scale(const ScaleRef& s, uint32_t e, float (&o)[VEC]) {
+  if (s.ptr) {
+    VecIO<VEC>::ld(s.ptr + e, o);
+  } else {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) o[j] = s.val;
+  }
+}
+
+// forward differences of u at idx .. idx+VEC-1 (same column x, label l)
+template <int VEC, bool THREE_D>
+__device__ __forceinline__ void grad_fwd(const GradGeom& g, const float* __restrict__ u, uint32_t idx,
+                                         uint32_t x, uint32_t y0, uint32_t l, float (&gx)[VEC],
+                                         float (&gy)[VEC], float (&gl)[VEC]) {
+  float c[VEC], n[VEC];
+  VecIO<VEC>::ld(u + idx, c);
+  if (x < g.nx - 1) {
+    VecIO<VEC>::ld(u + idx + g.ny, n);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) gx[j] = n[j] - c[j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) gx[j] = 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j + 1 < VEC; ++j) gy[j] = c[j + 1] - c[j];
+  gy[VEC - 1] = (y0 + VEC < g.ny) ? u[idx + VEC] - c[VEC - 1] : 0.f;
+  if (THREE_D) {
+    if (l < g.L - 1) {
+      VecIO<VEC>::ld(u + idx + g.nxny, n);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) gl[j] = n[j] - c[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) gl[j] = -c[j];
+    }
+  }
+}
+
+// (K^T p) at idx .. idx+VEC-1 : minus divergence (+ identity rows)
+template <int VEC, bool THREE_D, bool HAS_ID>
+__device__ __forceinline__ void grad_adj(const GradGeom& g, const float* __restrict__ p, uint32_t idx,
+                                         uint32_t x, uint32_t y0, uint32_t l, float (&out)[VEC]) {
+  const float* __restrict__ p1 = p;
+  const float* __restrict__ p2 = p + g.plane;
+  float a[VEC], divx[VEC], divy[VEC], o[VEC];
+  if (x < g.nx - 1) {
+    VecIO<VEC>::ld(p1 + idx, divx);
+  } else {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) divx[j] = 0.f;
+  }
+  if (x > 0) {
+    VecIO<VEC>::ld(p1 + idx - g.ny, a);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) divx[j] -= a[j];
+  }
+  VecIO<VEC>::ld(p2 + idx, o);
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) divy[j] = o[j];
+  if (y0 + VEC == g.ny) divy[VEC - 1] = 0.f;              // y = ny-1
+#pragma unroll
+  for (int j = 1; j < VEC; ++j) divy[j] -= o[j - 1];
+  if (y0 > 0) divy[0] -= p2[idx - 1];
+  if (THREE_D) {
+    const float* __restrict__ p3 = p + 2u * (size_t)g.plane;
+    float d[VEC];
+    VecIO<VEC>::ld(p3 + idx, d);
+    if (l > 0) {
+      VecIO<VEC>::ld(p3 + idx - g.nxny, a);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) d[j] -= a[j];
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) out[j] = -(divx[j] + divy[j] + d[j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) out[j] = -(divx[j] + divy[j]);
+  }
+  if (HAS_ID) {
+    VecIO<VEC>::ld(p + g.id_row + idx, a);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) out[j] = __fadd_rn(out[j], __fmul_rn(a[j], g.id_factor));
+  }
+}
+
+// true when every coefficient except b (index 1) is a scalar: the common "data term" shape
+// c*f(a x - b) with a per-pixel b (the image) and scalar weights
+__device__ __forceinline__ bool coeffs_scalar_except_b(const CoeffRef& c) {
+  return !c.ptr[0] && !c.ptr[2] && !c.ptr[3] && !c.ptr[4] && !c.ptr[5] && !c.ptr[6];
+}
+
+// ---- primal pass:  x+ = prox_g( x - tau T K^T y ) ----------------------------------------------------
+//  CAPL == 1 : thread = (y-vector, x, l); the prox group is one element (Elem1D / Zero), p.count = plane
+//  CAPL  > 1 : thread = (y-vector, x);    the prox group spans the L <= CAPL labels of a pixel, planar,
+//              p.count = nx*ny, p.dim = L  (simplex over labels)
+//  TUNI: the preconditioner T is one scalar (always true for pure gradient operators), which lets
+//  the compiler hoist every step-size expression out of the per-lane code.
+template <int VEC, int CAPL, int KIND, int FN, bool THREE_D, bool HAS_ID, bool CHECK, bool TUNI>
+__device__ __forceinline__ void grad_primal_body(
+    const GradGeom& g, const ProxDesc& p, const float* __restrict__ x, const float* __restrict__ y,
+    const float* __restrict__ y_prev, const ScaleRef& T, const float tau, const int kty_zero,
+    const int ktyprev_zero, float* __restrict__ x_out, const uint32_t t, double& acc0, double& acc1) {
+  uint32_t xl, yv, l0 = 0, xx;
+  g.div_q.divmod(t, xl, yv);
+  if (CAPL == 1) g.div_nx.divmod(xl, l0, xx); else xx = xl;
+  const uint32_t y0 = yv * VEC;
+  const uint32_t pix = y0 + xx * g.ny;
+  const uint32_t nl = CAPL == 1 ? 1u : g.L;
+
+  float arg[CAPL][VEC], td[CAPL][VEC];
+#pragma unroll
+  for (int li = 0; li < CAPL; ++li) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) { arg[li][j] = 0.f; td[li][j] = TUNI ? T.val : 1.f; }
+    if (li < (int)nl) {
+      const uint32_t l = l0 + li;
+      const uint32_t idx = pix + l * g.nxny;
+      float xo[VEC], k[VEC];
+      VecIO<VEC>::ld(x + idx, xo);
+      if (kty_zero) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) k[j] = 0.f;
+      } else {
+        grad_adj<VEC, THREE_D, HAS_ID>(g, y, idx, xx, y0, l, k);
+      }
+      if (!TUNI) VecIO<VEC>::ld(T.ptr + idx, td[li]);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) arg[li][j] = xo[j] - tau * td[li][j] * k[j];
+    }
+  }
+  // prox, one lane (= one group) at a time
+  const uint32_t tx0 = CAPL == 1 ? pix + l0 * g.nxny : pix;
+  if (KIND == kProxElem1D && CAPL == 1 && TUNI && !p.moreau && coeffs_scalar_except_b(p.coeffs)) {
+    // scalar weights: everything but b is loop invariant across the lanes
+    Coeffs7 c;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) c.v[k] = p.coeffs.val[k];
+    float bv[VEC];
+    if (p.coeffs.ptr[1]) {
+      VecIO<VEC>::ld(p.coeffs.ptr[1] + tx0, bv);
+    } else {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) bv[j] = p.coeffs.val[1];
+    }
+    const int fn = FN >= 0 ? FN : p.fn;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      c.v[1] = bv[j];
+      arg[0][j] = elem1d_apply(fn, arg[0][j], tau, T.val, false, c);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      float v[CAPL], tdl[CAPL];
+#pragma unroll
+      for (int li = 0; li < CAPL; ++li) { v[li] = arg[li][j]; tdl[li] = td[li][j]; }
+      group_apply<CAPL, KIND, FN>(p, tx0 + j, v, tdl, tau, false);
+#pragma unroll
+      for (int li = 0; li < CAPL; ++li) arg[li][j] = v[li];
+    }
+  }
+#pragma unroll
+  for (int li = 0; li < CAPL; ++li) {
+    if (li < (int)nl) {
+      const uint32_t l = l0 + li;
+      const uint32_t idx = pix + l * g.nxny;
+      VecIO<VEC>::st(x_out + idx, arg[li]);
+      if (CHECK) {
+        // dual residual (backend_pdhg.cu:73-94); operands are re-read (L1/L2 resident) rather
+        // than kept live across the prox
+        float xo[VEC], k[VEC], kp[VEC];
+        VecIO<VEC>::ld(x + idx, xo);
+        if (kty_zero) {
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) k[j] = 0.f;
+        } else {
+          grad_adj<VEC, THREE_D, HAS_ID>(g, y, idx, xx, y0, l, k);
+        }
+        if (ktyprev_zero) {
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) kp[j] = 0.f;
+        } else {
+          grad_adj<VEC, THREE_D, HAS_ID>(g, y_prev, idx, xx, y0, l, kp);
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const float sq = sqrtf(td[li][j]);
+          const float w_hat = (xo[j] - arg[li][j]) / (tau * sq) - sq * kp[j];
+          const float diff = w_hat + sq * k[j];
+          acc0 += static_cast<double>(diff * diff);
+          acc1 += static_cast<double>(w_hat * w_hat);
+        }
+      }
+    }
+  }
+}
+
+template <int VEC, int CAPL, int KIND, int FN, bool THREE_D, bool HAS_ID, bool CHECK>
+__global__ void __launch_bounds__(kStencilBlock) grad_primal_kernel(
+    const GradGeom g, const ProxDesc p, const float* __restrict__ x, const float* __restrict__ y,
+    const float* __restrict__ y_prev, const ScaleRef T, const PdhgState* __restrict__ st,
+    const int kty_zero, const int ktyprev_zero, double* __restrict__ partials, float* __restrict__ x_out) {
+  const float tau = st->tau;
+  double acc0 = 0.0, acc1 = 0.0;
+  const uint32_t total = g.q * g.nx * (CAPL == 1 ? g.L : 1u);
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < total) {
+    if (T.ptr)
+      grad_primal_body<VEC, CAPL, KIND, FN, THREE_D, HAS_ID, CHECK, false>(
+          g, p, x, y, y_prev, T, tau, kty_zero, ktyprev_zero, x_out, t, acc0, acc1);
+    else
+      grad_primal_body<VEC, CAPL, KIND, FN, THREE_D, HAS_ID, CHECK, true>(
+          g, p, x, y, y_prev, T, tau, kty_zero, ktyprev_zero, x_out, t, acc0, acc1);
+  }
+  if (CHECK) {
+    block_sum2(acc0, acc1);
+    if (threadIdx.x == 0) { partials[2 * blockIdx.x] = acc0; partials[2 * blockIdx.x + 1] = acc1; }
+  }
+}
+
+// ---- dual pass on the gradient rows:  y+ = prox_f*( y + sigma S ((1+theta) K x+ - theta K x) ) -------
+//  prox = Norm2 family (optionally through Moreau), planar:
+//  CAPL == 1 : thread = (y-vector, x, l); group = the NCOMP components of one voxel,
+//              p.count = plane, p.dim = NCOMP
+//  CAPL  > 1 : thread = (y-vector, x);    group = NCOMP * L components of one pixel (L <= CAPL),
+//              p.count = nx*ny, p.dim = NCOMP * L, component i = c*L + l
+template <int VEC, int CAPL, int FN, bool THREE_D, bool CHECK, bool SUNI>
+__device__ __forceinline__ void grad_dual_body(
+    const GradGeom& g, const ProxDesc& p, const float* __restrict__ y, const float* __restrict__ xn,
+    const float* __restrict__ xo, const ScaleRef& S, const float sigma, const float theta,
+    const int kxprev_zero, float* __restrict__ y_out, const uint32_t t, double& acc0, double& acc1) {
+  constexpr int NCOMP = THREE_D ? 3 : 2;
+  constexpr int CAP = NCOMP * CAPL;
+  uint32_t xl, yv, l0 = 0, xx;
+  g.div_q.divmod(t, xl, yv);
+  if (CAPL == 1) g.div_nx.divmod(xl, l0, xx); else xx = xl;
+  const uint32_t y0 = yv * VEC;
+  const uint32_t pix = y0 + xx * g.ny;
+  const uint32_t nl = CAPL == 1 ? 1u : g.L;
+
+  // slot (c, li) -> c*CAPL + li ; unused label slots stay 0 (they do not change a 2-norm)
+  float arg[CAP][VEC], td[SUNI ? 1 : CAP][VEC];
+#pragma unroll
+  for (int s = 0; s < CAP; ++s) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      arg[s][j] = 0.f;
+      if (!SUNI) td[s][j] = 1.f;
+    }
+  }
+  if (SUNI) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) td[0][j] = S.val;
+  }
+#pragma unroll
+  for (int li = 0; li < CAPL; ++li) {
+    if (li < (int)nl) {
+      const uint32_t l = l0 + li;
+      const uint32_t idx = pix + l * g.nxny;
+      float k1[NCOMP][VEC], k0[NCOMP][VEC];
+      grad_fwd<VEC, THREE_D>(g, xn, idx, xx, y0, l, k1[0], k1[1], k1[NCOMP - 1]);
+      if (kxprev_zero) {
+#pragma unroll
+        for (int c = 0; c < NCOMP; ++c)
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) k0[c][j] = 0.f;
+      } else {
+        grad_fwd<VEC, THREE_D>(g, xo, idx, xx, y0, l, k0[0], k0[1], k0[NCOMP - 1]);
+      }
+#pragma unroll
+      for (int c = 0; c < NCOMP; ++c) {
+        const uint32_t e = c * g.plane + idx;
+        const int s = c * CAPL + li;
+        float yo[VEC];
+        VecIO<VEC>::ld(y + e, yo);
+        if (!SUNI) VecIO<VEC>::ld(S.ptr + e, td[s]);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const float ext = (1 + theta) * k1[c][j] - theta * k0[c][j];
+          arg[s][j] = yo[j] + sigma * td[SUNI ? 0 : s][j] * ext;
+        }
+      }
+    }
+  }
+  const uint32_t tx0 = CAPL == 1 ? pix + l0 * g.nxny : pix;
+  const int fn = FN >= 0 ? FN : p.fn;
+  bool scalar_coeffs = SUNI && !p.moreau;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) scalar_coeffs = scalar_coeffs && !p.coeffs.ptr[k];
+  if (scalar_coeffs) {
+    // all weights scalar: the step and every coefficient product are lane invariant
+    Coeffs7 c;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) c.v[k] = p.coeffs.val[k];
+    const float tau_eff = effective_tau(sigma, S.val, false);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      float sq = 0.f;
+#pragma unroll
+      for (int s = 0; s < CAP; ++s) sq += arg[s][j] * arg[s][j];
+      if (sq > 0.f) {
+        const float norm = sqrtf(sq);
+        const float r = scaled_fun_prox(fn, norm, tau_eff, c);
+#pragma unroll
+        for (int s = 0; s < CAP; ++s) arg[s][j] = r * arg[s][j] / norm;
+      } else {
+#pragma unroll
+        for (int s = 0; s < CAP; ++s) arg[s][j] = 0.f;
+      }
+    }
+  } else {
+    ProxDesc pd = p;
+    pd.dim = CAP;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      float v[CAP], tdl[CAP];
+#pragma unroll
+      for (int s = 0; s < CAP; ++s) { v[s] = arg[s][j]; tdl[s] = td[SUNI ? 0 : s][j]; }
+      group_apply<CAP, kProxNorm2, FN>(pd, tx0 + j, v, tdl, sigma, false);
+#pragma unroll
+      for (int s = 0; s < CAP; ++s) arg[s][j] = v[s];
+    }
+  }
+#pragma unroll
+  for (int li = 0; li < CAPL; ++li) {
+    if (li < (int)nl) {
+      const uint32_t l = l0 + li;
+      const uint32_t idx = pix + l * g.nxny;
+      float k1[NCOMP][VEC], k0[NCOMP][VEC];
+      if (CHECK) {
+        grad_fwd<VEC, THREE_D>(g, xn, idx, xx, y0, l, k1[0], k1[1], k1[NCOMP - 1]);
+        if (kxprev_zero) {
+#pragma unroll
+          for (int c = 0; c < NCOMP; ++c)
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) k0[c][j] = 0.f;
+        } else {
+          grad_fwd<VEC, THREE_D>(g, xo, idx, xx, y0, l, k0[0], k0[1], k0[NCOMP - 1]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < NCOMP; ++c) {
+        const uint32_t e = c * g.plane + idx;
+        const int s = c * CAPL + li;
+        VecIO<VEC>::st(y_out + e, arg[s]);
+        if (CHECK) {
+          // primal residual (backend_pdhg.cu:97-120)
+          float yo[VEC];
+          VecIO<VEC>::ld(y + e, yo);
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) {
+            const float ext = (1 + theta) * k1[c][j] - theta * k0[c][j];
+            const float sq = sqrtf(td[SUNI ? 0 : s][j]);
+            const float z_hat = (yo[j] - arg[s][j]) / (sigma * sq) + sq * ext;
+            const float diff = z_hat - sq * k1[c][j];
+            acc0 += static_cast<double>(diff * diff);
+            acc1 += static_cast<double>(z_hat * z_hat);
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int VEC, int CAPL, int FN, bool THREE_D, bool CHECK>
+__global__ void __launch_bounds__(kStencilBlock) grad_dual_norm2_kernel(
+    const GradGeom g, const ProxDesc p, const float* __restrict__ y, const float* __restrict__ xn,
+    const float* __restrict__ xo, const ScaleRef S, const PdhgState* __restrict__ st, const int kxprev_zero,
+    double* __restrict__ partials, float* __restrict__ y_out) {
+  const float sigma = st->sigma, theta = st->theta;
+  double acc0 = 0.0, acc1 = 0.0;
+  const uint32_t total = g.q * g.nx * (CAPL == 1 ? g.L : 1u);
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < total) {
+    if (S.ptr)
+      grad_dual_body<VEC, CAPL, FN, THREE_D, CHECK, false>(g, p, y, xn, xo, S, sigma, theta, kxprev_zero,
+                                                           y_out, t, acc0, acc1);
+    else
+      grad_dual_body<VEC, CAPL, FN, THREE_D, CHECK, true>(g, p, y, xn, xo, S, sigma, theta, kxprev_zero,
+                                                          y_out, t, acc0, acc1);
+  }
+  if (CHECK) {
+    block_sum2(acc0, acc1);
+    if (threadIdx.x == 0) { partials[2 * blockIdx.x] = acc0; partials[2 * blockIdx.x + 1] = acc1; }
+  }
+}
+
+// ---- dual pass on identity rows:  K x = f * x  (no stencil), any register-resident leaf prox ----------
+template <int CAP, bool CHECK>
+struct IdentityDualSource {
+  const float* __restrict__ y;
+  const float* __restrict__ x_new;    // already offset so that row e reads x[e - id_row]
+  const float* __restrict__ x_old;
+  ScaleRef S;
+  const PdhgState* __restrict__ st;
+  float factor;
+  uint32_t id_row;
+  int kxprev_zero;
+  double* __restrict__ partials;
+
+  struct Regs {
+    float sigma, theta;
+    float yo[CHECK ? CAP : 1], kx[CHECK ? CAP : 1], kxe[CHECK ? CAP : 1];
+    double acc0, acc1;
+  };
+  __device__ __forceinline__ float begin(Regs& r) const {
+    r.sigma = st->sigma;
+    r.theta = st->theta;
+    r.acc0 = r.acc1 = 0.0;
+    return r.sigma;
+  }
+  __device__ __forceinline__ float load(Regs& r, uint32_t e, int i) const {
+    const float yv = y[e];
+    const float k1 = __fmul_rn(x_new[e - id_row], factor);
+    const float k0 = kxprev_zero ? 0.f : __fmul_rn(x_old[e - id_row], factor);
+    const float ext = (1 + r.theta) * k1 - r.theta * k0;
+    if (CHECK) { r.yo[i] = yv; r.kx[i] = k1; r.kxe[i] = ext; }
+    return yv + r.sigma * S.at(e) * ext;
+  }
+  __device__ __forceinline__ void post(Regs& r, uint32_t e, int i, float yn) const {
+    if (CHECK) {
+      const float sq = sqrtf(S.at(e));
+      const float z_hat = (r.yo[i] - yn) / (r.sigma * sq) + sq * r.kxe[i];
+      const float diff = z_hat - sq * r.kx[i];
+      r.acc0 += static_cast<double>(diff * diff);
+      r.acc1 += static_cast<double>(z_hat * z_hat);
+    }
+  }
+  __device__ __forceinline__ void finish(Regs& r) const {
+    if (CHECK) {
+      block_sum2(r.acc0, r.acc1);
+      if (threadIdx.x == 0) { partials[2 * blockIdx.x] = r.acc0; partials[2 * blockIdx.x + 1] = r.acc1; }
+    }
+  }
+};
+
+#endif  // __CUDACC__
+
+// ---- host side: pattern matching + launch (pb_stencil.cu) -----------------------------------------
+
+struct StencilPlan {
+  bool ok = false;            // operator matches  [gradient (+ identity)]
+  bool three_d = false;
+  GradGeom geom;              // q / div_q filled per launch (depends on VEC)
+};
+
+// Recognises the operator structure; `blocks` are the problem's non-zero blocks.
+StencilPlan plan_stencil(const std::vector<std::shared_ptr<Block>>& blocks, size_t nrows, size_t ncols);
+
+// Each returns 0 when the (operator, prox) pair is not covered by a specialised kernel (the caller
+// then uses the generic fused kernel), otherwise the number of CTAs launched (= partial pairs written).
+unsigned stencil_primal_launch(Context* ctx, const StencilPlan& plan, const ProxDesc& d, const float* x,
+                               const float* y, const float* y_prev, ScaleRef T, const PdhgState* st,
+                               bool kty_zero, bool ktyprev_zero, bool check, double* partials, float* x_out,
+                               bool dry_run = false);
+unsigned stencil_dual_launch(Context* ctx, const StencilPlan& plan, const ProxDesc& d, const float* y,
+                             const float* x_new, const float* x_old, ScaleRef S, const PdhgState* st,
+                             bool kxprev_zero, bool check, double* partials, float* y_out,
+                             bool dry_run = false);
+
+}  // namespace pb

@@ -36,10 +36,11 @@ def test_linop_forward_adjoint(ctx, name):
     fwd, adj = op.Eval(x), op.EvalAdjoint(y)
     exact = not any(b[0] in ("dense", "sparse") for b in blocks)
     if exact:
-        # stencils and diagonals do the same float operations in the same order: bit-exact
-        # up to FMA contraction of the diagonal products
-        assert close(fwd, orc.linop(x, False), 1e-6) == 0
-        assert close(adj, orc.linop(y, True), 1e-6) == 0
+        # stencils and diagonals do the same float operations in the same order as the oracle;
+        # only FMA contraction of the diagonal products (29 terms per row) differs
+        tol = 1e-5 if any(b[0] == "diags" for b in blocks) else 1e-6
+        assert close(fwd, orc.linop(x, False), tol) == 0
+        assert close(adj, orc.linop(y, True), tol) == 0
     else:
         assert close(fwd, orc.linop(x, False), 1e-4) == 0
         assert close(adj, orc.linop(y, True), 1e-4) == 0
