@@ -145,6 +145,27 @@ __device__ __forceinline__ float scaled_fun_prox(int fn, float r, float tau, con
   return a == 1.f ? res : res / a;        // res / 1 == res exactly
 }
 
+// Same as scaled_fun_prox for a == 1, d == 0, e == 0 (the default weights of the reference's
+// function constructors): 1*(r - 0*tau) == r, c*1*1*tau == c*tau and x/1 == x hold exactly in
+// IEEE arithmetic, so dropping those operations does not change a single bit.
+__device__ __forceinline__ float scaled_fun_prox_simple(int fn, float r, float tau, float b, float cc,
+                                                        float alpha, float beta) {
+  return fun1d(fn, __fsub_rn(r, b), cc * tau, alpha, beta) + b;
+}
+
+__device__ __forceinline__ bool coeffs_simple(const Coeffs7& c) {
+  return c.v[0] == 1.f && c.v[3] == 0.f && c.v[4] == 0.f;
+}
+
+// p / n for several p sharing one divisor: rn = RN(1/n) is computed once with an IEEE division,
+// each quotient then costs one multiply and two FMAs (Markstein's correction step, which
+// reproduces the correctly rounded quotient of the full division).
+__device__ __forceinline__ float div_shared(float p, float n, float rn) {
+  const float q0 = __fmul_rn(p, rn);
+  const float rem = __fmaf_rn(-q0, n, p);
+  return __fmaf_rn(rem, rn, q0);
+}
+
 // ElemOperation1D::operator() on one element
 __device__ __forceinline__ float elem1d_apply(int fn, float arg, float tau_scal, float tau_diag,
                                               bool invert, const Coeffs7& c) {

@@ -205,10 +205,17 @@ __device__ __forceinline__ void grad_primal_body(
       for (int j = 0; j < VEC; ++j) bv[j] = p.coeffs.val[1];
     }
     const int fn = FN >= 0 ? FN : p.fn;
+    if (coeffs_simple(c) && c.v[2] != 0.f) {
+      const float tau_eff = effective_tau(tau, T.val, false);
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      c.v[1] = bv[j];
-      arg[0][j] = elem1d_apply(fn, arg[0][j], tau, T.val, false, c);
+      for (int j = 0; j < VEC; ++j)
+        arg[0][j] = scaled_fun_prox_simple(fn, arg[0][j], tau_eff, bv[j], c.v[2], c.v[5], c.v[6]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        c.v[1] = bv[j];
+        arg[0][j] = elem1d_apply(fn, arg[0][j], tau, T.val, false, c);
+      }
     }
   } else {
 #pragma unroll
@@ -277,6 +284,31 @@ __global__ void __launch_bounds__(kStencilBlock) grad_primal_kernel(
   if (CHECK) {
     block_sum2(acc0, acc1);
     if (threadIdx.x == 0) { partials[2 * blockIdx.x] = acc0; partials[2 * blockIdx.x + 1] = acc1; }
+  }
+}
+
+// Norm2 prox of VEC groups held in registers, scalar weights (elem_operation_norm2.hpp:39-88):
+// res_i = ((f_prox(a(|v| - d tau)/(1 + tau e) - b, .) + b)/a) * v_i / |v|.  The per-component
+// division by the shared norm uses div_shared.
+template <int VEC, int CAP, bool SIMPLE>
+__device__ __forceinline__ void norm2_lanes(const int fn, float (&arg)[CAP][VEC], const Coeffs7& c,
+                                            const float tau_eff) {
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    float sq = 0.f;
+#pragma unroll
+    for (int s = 0; s < CAP; ++s) sq += arg[s][j] * arg[s][j];
+    if (sq > 0.f) {
+      const float norm = sqrtf(sq);
+      const float r = SIMPLE ? scaled_fun_prox_simple(fn, norm, tau_eff, c.v[1], c.v[2], c.v[5], c.v[6])
+                             : scaled_fun_prox(fn, norm, tau_eff, c);
+      const float rn = 1.f / norm;
+#pragma unroll
+      for (int s = 0; s < CAP; ++s) arg[s][j] = div_shared(__fmul_rn(r, arg[s][j]), norm, rn);
+    } else {
+#pragma unroll
+      for (int s = 0; s < CAP; ++s) arg[s][j] = 0.f;
+    }
   }
 }
 
@@ -355,21 +387,10 @@ __device__ __forceinline__ void grad_dual_body(
 #pragma unroll
     for (int k = 0; k < 7; ++k) c.v[k] = p.coeffs.val[k];
     const float tau_eff = effective_tau(sigma, S.val, false);
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      float sq = 0.f;
-#pragma unroll
-      for (int s = 0; s < CAP; ++s) sq += arg[s][j] * arg[s][j];
-      if (sq > 0.f) {
-        const float norm = sqrtf(sq);
-        const float r = scaled_fun_prox(fn, norm, tau_eff, c);
-#pragma unroll
-        for (int s = 0; s < CAP; ++s) arg[s][j] = r * arg[s][j] / norm;
-      } else {
-#pragma unroll
-        for (int s = 0; s < CAP; ++s) arg[s][j] = 0.f;
-      }
-    }
+    if (coeffs_simple(c))
+      norm2_lanes<VEC, CAP, true>(fn, arg, c, tau_eff);
+    else
+      norm2_lanes<VEC, CAP, false>(fn, arg, c, tau_eff);
   } else {
     ProxDesc pd = p;
     pd.dim = CAP;
