@@ -83,7 +83,7 @@ struct PrimalSource {
       r.kty[i] = k;
       r.ktyp[i] = ktyprev_zero ? 0.f : gather_col(bl, e, y_prev);
     }
-    return xv - r.tau * T.at(e) * k;
+    return primal_prox_arg(xv, r.tau, T.at(e), k);
   }
   __device__ __forceinline__ void post(Regs& r, uint32_t e, int i, float xn) const {
     if (CHECK) {
@@ -129,13 +129,13 @@ struct DualSource {
     const float yv = y[e];
     const float k1 = gather_row(bl, e, x_new);
     const float k0 = kxprev_zero ? 0.f : gather_row(bl, e, x_old);
-    const float ext = (1 + r.theta) * k1 - r.theta * k0;
+    const float ext = dual_extrapolate(r.theta, k1, k0);
     if (CHECK) {
       r.yo[i] = yv;
       r.kx[i] = k1;
       r.kxe[i] = ext;
     }
-    return yv + r.sigma * S.at(e) * ext;
+    return dual_prox_arg(yv, r.sigma, S.at(e), ext);
   }
   __device__ __forceinline__ void post(Regs& r, uint32_t e, int i, float yn) const {
     if (CHECK) {

@@ -16,6 +16,21 @@
 
 namespace pb {
 
+// ---- PDHG prox arguments --------------------------------------------------------------------
+// The contraction pattern is pinned to what nvcc emits for the reference's thrust functors
+// (cuobjdump of backend_pdhg.cu: primal  FMUL t = tau*T; FFMA x - t*kty;  dual  FMUL u = theta*kx_prev;
+// FFMA ext = (1+theta)*kx - u; FMUL s = sigma*S; FFMA y + s*ext), so that every execution mode
+// rounds exactly like the reference instead of depending on per-kernel compiler choices.
+__device__ __forceinline__ float primal_prox_arg(float x, float tau, float T, float kty) {
+  return __fmaf_rn(-__fmul_rn(tau, T), kty, x);
+}
+__device__ __forceinline__ float dual_extrapolate(float theta, float kx, float kx_prev) {
+  return __fmaf_rn(1 + theta, kx, -__fmul_rn(theta, kx_prev));
+}
+__device__ __forceinline__ float dual_prox_arg(float y, float sigma, float S, float ext) {
+  return __fmaf_rn(__fmul_rn(sigma, S), ext, y);
+}
+
 // ---- Function1D: prox_{tau f}(x0) -------------------------------------------------------
 
 __device__ __forceinline__ float f1d_abs(float x0, float tau) {

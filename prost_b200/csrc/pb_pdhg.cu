@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(kBlock) primal_proxarg_kernel(float* __restric
                                                                 float tau) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
        i += (size_t)gridDim.x * blockDim.x)
-    temp[i] = x[i] - tau * T[i] * kty[i];
+    temp[i] = primal_prox_arg(x[i], tau, T[i], kty[i]);
 }
 
 // temp = y + sigma * S * ((1+theta) kx - theta kx_prev)   (dual_proxarg_functor, :54-70)
@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(kBlock) dual_proxarg_kernel(float* __restrict_
                                                               float sigma, float theta) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < m;
        i += (size_t)gridDim.x * blockDim.x)
-    temp[i] = y[i] + sigma * S[i] * ((1 + theta) * kx[i] - theta * kx_prev[i]);
+    temp[i] = dual_prox_arg(y[i], sigma, S[i], dual_extrapolate(theta, kx[i], kx_prev[i]));
 }
 
 // primal_residual_transform (:97-120): per-CTA partial (sum diff^2, sum z_hat^2)

@@ -187,7 +187,7 @@ __device__ __forceinline__ void grad_primal_body(
       }
       if (!TUNI) VecIO<VEC>::ld(T.ptr + idx, td[li]);
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) arg[li][j] = xo[j] - tau * td[li][j] * k[j];
+      for (int j = 0; j < VEC; ++j) arg[li][j] = primal_prox_arg(xo[j], tau, td[li][j], k[j]);
     }
   }
   // prox, one lane (= one group) at a time
@@ -370,8 +370,8 @@ __device__ __forceinline__ void grad_dual_body(
         if (!SUNI) VecIO<VEC>::ld(S.ptr + e, td[s]);
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
-          const float ext = (1 + theta) * k1[c][j] - theta * k0[c][j];
-          arg[s][j] = yo[j] + sigma * td[SUNI ? 0 : s][j] * ext;
+          const float ext = dual_extrapolate(theta, k1[c][j], k0[c][j]);
+          arg[s][j] = dual_prox_arg(yo[j], sigma, td[SUNI ? 0 : s][j], ext);
         }
       }
     }
@@ -432,7 +432,7 @@ __device__ __forceinline__ void grad_dual_body(
           VecIO<VEC>::ld(y + e, yo);
 #pragma unroll
           for (int j = 0; j < VEC; ++j) {
-            const float ext = (1 + theta) * k1[c][j] - theta * k0[c][j];
+            const float ext = dual_extrapolate(theta, k1[c][j], k0[c][j]);
             const float sq = sqrtf(td[SUNI ? 0 : s][j]);
             const float z_hat = (yo[j] - arg[s][j]) / (sigma * sq) + sq * ext;
             const float diff = z_hat - sq * k1[c][j];
@@ -496,9 +496,9 @@ struct IdentityDualSource {
     const float yv = y[e];
     const float k1 = __fmul_rn(x_new[e - id_row], factor);
     const float k0 = kxprev_zero ? 0.f : __fmul_rn(x_old[e - id_row], factor);
-    const float ext = (1 + r.theta) * k1 - r.theta * k0;
+    const float ext = dual_extrapolate(r.theta, k1, k0);
     if (CHECK) { r.yo[i] = yv; r.kx[i] = k1; r.kxe[i] = ext; }
-    return yv + r.sigma * S.at(e) * ext;
+    return dual_prox_arg(yv, r.sigma, S.at(e), ext);
   }
   __device__ __forceinline__ void post(Regs& r, uint32_t e, int i, float yn) const {
     if (CHECK) {

@@ -8,17 +8,29 @@ from oracle_binding import OracleProblem, OraclePDHG
 TOL = dict(tol_rel_primal=0.0, tol_rel_dual=0.0, tol_abs_primal=0.0, tol_abs_dual=0.0)
 
 
-def run_cuda(ctx, desc, iters, fuse=True, x0=None, y0=None, tol=None, **opts):
+def run_cuda(ctx, desc, iters, fuse=True, x0=None, y0=None, tol=None, use_solver=False, **opts):
+    """use_solver=False: exactly `iters` x PerformIteration.  use_solver=True: Solver::Solve with
+    max_iters=iters, which stops early on convergence like the reference's loop (solver.cu:141-196)."""
     prob = pb.create_problem(ctx, desc)
-    prob.Initialize()
     popts = pb.pdhg_options(scale_steps_operator=0, fuse=int(fuse), **opts)
-    sopts = pb.solver_options(verbose=0, max_iters=iters, **(tol or TOL))
+    sopts = pb.solver_options(verbose=0, max_iters=iters, num_cback_calls=0, **(tol or TOL))
     be = pb.BackendPDHG(ctx, prob, popts, sopts)
-    be.Initialize(x0, y0)
-    be.PerformIteration(iters)
-    x, z, y, w = be.current_solution()
+    if use_solver:
+        solver = pb.Solver(prob, be)
+        solver.SetOptions(sopts, x0=x0, y0=y0)
+        solver.Initialize()
+        solver.Solve()
+        x, z, y, w = (solver.cur_primal_sol, solver.cur_primal_constr_sol, solver.cur_dual_sol,
+                      solver.cur_dual_constr_sol)
+        done = solver.iterations
+    else:
+        prob.Initialize()
+        be.Initialize(x0, y0)
+        be.PerformIteration(iters)
+        x, z, y, w = be.current_solution()
+        done = iters
     return dict(x=x, z=z, y=y, w=w, res=be.residuals(), steps=be.stepsizes(), fused=be.is_fused, backend=be,
-                problem=prob)
+                problem=prob, iterations=done)
 
 
 def run_oracle(desc, iters, x0=None, y0=None, tol=None, **opts):
