@@ -1,0 +1,55 @@
+// prost/prox/prox_elem_operation.hpp -- ProxElemOperation<T, ELEM_OPERATION>
+// (reference: include/prost/prox/prox_elem_operation.hpp:33-102).
+#ifndef PROST_PROX_ELEM_OPERATION_HPP_
+#define PROST_PROX_ELEM_OPERATION_HPP_
+
+#include <array>
+
+#include "prost/prox/prox_separable_sum.hpp"
+
+namespace prost {
+
+template <typename T, class ELEM_OPERATION>
+class ProxElemOperation : public ProxSeparableSum<T> {
+ public:
+  /// Operations without coefficients (ElemOperationIndSimplex).
+  ProxElemOperation(size_t index, size_t count, size_t dim, bool interleaved, bool diagsteps)
+      : ProxSeparableSum<T>(index, count, ELEM_OPERATION::kDim <= 0 ? dim : ELEM_OPERATION::kDim, interleaved,
+                            diagsteps) {
+    static_assert(ELEM_OPERATION::kCoeffsCount == 0, "this element operation needs its coefficients");
+  }
+
+  /// Operations with coefficient arrays a,b,c,d,e,alpha,beta; each of length 1 or count.
+  ProxElemOperation(size_t index, size_t count, size_t dim, bool interleaved, bool diagsteps,
+                    std::array<std::vector<T>, ELEM_OPERATION::kCoeffsCount> coeffs)
+      : ProxSeparableSum<T>(index, count, ELEM_OPERATION::kDim <= 0 ? dim : ELEM_OPERATION::kDim, interleaved,
+                            diagsteps),
+        coeffs_(coeffs.begin(), coeffs.end()) {}
+
+ protected:
+  virtual pb_prox* create() {
+    pb_prox* h = nullptr;
+    pb_context* ctx = detail::context();
+    if (ELEM_OPERATION::kKind == detail::kElemOpIndSimplex) {
+      detail::check(pb_prox_create_ind_simplex(ctx, this->index_, this->count_, this->dim_, this->interleaved_,
+                                               this->diagsteps_, &h));
+      return h;
+    }
+    if (coeffs_.size() != 7) throw Exception("ProxElemOperation: expected 7 coefficient arrays.");
+    const float* ptrs[7];
+    size_t lens[7];
+    for (int k = 0; k < 7; ++k) { ptrs[k] = coeffs_[k].data(); lens[k] = coeffs_[k].size(); }
+    if (ELEM_OPERATION::kKind == detail::kElemOp1D)
+      detail::check(pb_prox_create_elem_1d(ctx, this->index_, this->count_, this->dim_, this->interleaved_,
+                                           this->diagsteps_, ELEM_OPERATION::kFunctionId, ptrs, lens, &h));
+    else
+      detail::check(pb_prox_create_elem_norm2(ctx, this->index_, this->count_, this->dim_, this->interleaved_,
+                                              this->diagsteps_, ELEM_OPERATION::kFunctionId, ptrs, lens, &h));
+    return h;
+  }
+  std::vector<std::vector<T> > coeffs_;
+};
+
+}  // namespace prost
+
+#endif

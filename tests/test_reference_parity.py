@@ -135,3 +135,29 @@ def test_warm_start_vs_reference(ctx):
         for fuse in (1, 2, 0):
             got = run_cuda(ctx, desc, iters, fuse=fuse, x0=x0, y0=y0, stepsize="alg1", residual_iter=1)
             assert_ref_parity(got, want, f"warm start iters={iters} fuse={fuse}")
+
+
+@pytest.mark.skipif(not ref_driver.available(ref_driver.OUR_DRIVER), reason="prost_b200_driver not built")
+@pytest.mark.parametrize("name", ["rof_boyd", "tvl1_color", "lifting_L8"])
+def test_cxx_api_drop_in(name):
+    """The SAME C++ program (oracle/driver/prost_driver.cu, prost's public API only) linked once
+    against the reference and once against include/prost/*.hpp + libprost_b200.so."""
+    desc_fn, iters, opts = PDHG_CASES[name]
+    desc = desc_fn()
+    want = ref_driver.run_solve(desc, iters, tol=TOL4, **opts)
+    got = ref_driver.run_solve(desc, iters, tol=TOL4, binary=ref_driver.OUR_DRIVER, **opts)
+    assert int(got["info"]["iterations"]) == int(want["info"]["iterations"])
+    assert_ref_parity(got, want, f"c++ drop-in {name}")
+    blocks = cases.linop_cases(small=True)["lifting_K"]
+    r = np.random.default_rng(1)
+    from oracle_binding import OracleProblem as _OP
+    m, n = _OP(blocks=blocks).linop_size()
+    x = r.random(n).astype(np.float32)
+    a = ref_driver.run_linop(blocks, x, False)
+    b = ref_driver.run_linop(blocks, x, False, binary=ref_driver.OUR_DRIVER)
+    assert np.array_equal(a["res"], b["res"]) and np.array_equal(a["rowsum"], b["rowsum"])
+    pdesc, pn = cases.prox_cases(small=True)["simplex_d5_il0"]
+    arg = (2 * r.standard_normal(pn)).astype(np.float32)
+    pa = ref_driver.run_prox(pdesc, arg, np.ones(pn), 1.0)
+    pbv = ref_driver.run_prox(pdesc, arg, np.ones(pn), 1.0, binary=ref_driver.OUR_DRIVER)
+    assert close_frac(pbv, pa, 1e-6) == 0
