@@ -48,6 +48,7 @@ typedef struct pb_linop pb_linop;
 typedef struct pb_prox pb_prox;
 typedef struct pb_problem pb_problem;
 typedef struct pb_backend pb_backend;
+typedef struct pb_comm pb_comm;
 
 /* ---- library / context -------------------------------------------------------------- */
 
@@ -272,6 +273,32 @@ unsigned long long pb_backend_launch_count(const pb_backend* b);
 int pb_backend_profile(pb_backend* b, int n_iters, float out_ms[3]);
 /* device pointers of the current iterates (x: ncols, y: nrows) for zero-copy callers */
 int pb_backend_device_iterates(pb_backend* b, float** d_x, float** d_y);
+
+/* ---- multi-GPU slab decomposition (no counterpart in the reference, which is single-GPU:
+ * SURVEY.md 2a / 8(e)) ----------------------------------------------------------------------
+ * One process per GPU.  Every rank builds the Problem of ITS block of image columns
+ * (BlockGradient2D/3D with the local nx, prox coefficient arrays sliced to those columns; ranks are
+ * ordered left to right along x) and attaches a communicator to the PDHG backend before
+ * pb_backend_initialize.  Stencil halos then travel peer-to-peer inside the fused passes (CUDA IPC
+ * mapped neighbour memory over NVLink; NCCL send/recv staging when PB_HALO=nccl or IPC is
+ * unavailable) and the four residual sums are all-reduced with NCCL at residual_iter boundaries.
+ * With a communicator attached, pb_backend_initialize / iterate / residuals / current_solution and
+ * pb_solver_solve are COLLECTIVE: every rank must make the same calls. */
+#define PB_COMM_ID_BYTES 128
+/* rank 0 creates the id (an ncclUniqueId); the host distributes the 128 bytes to all ranks
+ * (torch.distributed broadcast, MPI_Bcast, a file, ...) */
+int pb_comm_unique_id(void* h_id_out);
+int pb_comm_create(pb_context* ctx, int rank, int world, const void* h_id, pb_comm** out);
+void pb_comm_destroy(pb_comm* c);
+int pb_comm_rank(const pb_comm* c);
+int pb_comm_world(const pb_comm* c);
+/* 1: halos stored directly into the neighbour's memory by the kernels; 0: NCCL staging */
+int pb_comm_peer_to_peer(const pb_comm* c);
+int pb_comm_barrier(pb_comm* c);
+/* sum over ranks of n host doubles, in place (host-side reductions of callers, e.g. objectives) */
+int pb_comm_allreduce_sum(pb_comm* c, double* h_buf, size_t n);
+/* the backend's Problem is the slab of rank pb_comm_rank(c); the comm must outlive the backend */
+int pb_backend_set_slab(pb_backend* b, pb_comm* c);
 
 /* ---- Solver loop: Solver<T>::Solve, src/solver.cu:122-209 ------------------------------- */
 typedef int (*pb_stopping_cb)(void* user);    /* StoppingCallback, called every iteration */

@@ -163,6 +163,15 @@ SIGNATURES = {
     "pb_backend_is_fused": (C.c_int, [handle]),
     "pb_backend_launch_count": (C.c_ulonglong, [handle]),
     "pb_backend_device_iterates": (C.c_int, [handle, handle_p, handle_p]),
+    "pb_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "pb_comm_create": (C.c_int, [handle, C.c_int, C.c_int, C.c_void_p, handle_p]),
+    "pb_comm_destroy": (None, [handle]),
+    "pb_comm_rank": (C.c_int, [handle]),
+    "pb_comm_world": (C.c_int, [handle]),
+    "pb_comm_peer_to_peer": (C.c_int, [handle]),
+    "pb_comm_barrier": (C.c_int, [handle]),
+    "pb_comm_allreduce_sum": (C.c_int, [handle, c_double_p, C.c_size_t]),
+    "pb_backend_set_slab": (C.c_int, [handle, handle]),
     "pb_solver_solve": (C.c_int, [handle, C.POINTER(SolverOptions), STOPPING_CB, INTERM_CB, C.c_void_p,
                                   c_float_p, c_float_p, c_float_p, c_float_p, c_int_p, c_int_p]),
 }

@@ -53,6 +53,47 @@ class Context:
             self._h = None
 
 
+class Comm:
+    """pb_comm: one rank of the slab decomposition (one process per GPU).  ``unique_id`` is the 128
+    bytes rank 0 got from :func:`Comm.unique_id`, distributed by the caller (see
+    prost_b200.distributed.init_comm for the torch.distributed way)."""
+
+    ID_BYTES = 128
+
+    def __init__(self, ctx, rank, world, unique_id):
+        assert len(unique_id) == self.ID_BYTES
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        buf = C.create_string_buffer(bytes(unique_id), self.ID_BYTES)
+        check(lib.pb_comm_create(ctx._h, int(rank), int(world), buf, C.byref(self._h)))
+
+    @staticmethod
+    def unique_id():
+        buf = C.create_string_buffer(Comm.ID_BYTES)
+        check(lib.pb_comm_unique_id(buf))
+        return buf.raw
+
+    rank = property(lambda s: lib.pb_comm_rank(s._h))
+    world = property(lambda s: lib.pb_comm_world(s._h))
+    peer_to_peer = property(lambda s: bool(lib.pb_comm_peer_to_peer(s._h)))
+
+    def barrier(self):
+        check(lib.pb_comm_barrier(self._h))
+
+    def allreduce_sum(self, values):
+        a = np.ascontiguousarray(np.asarray(values, dtype=np.float64).ravel())
+        check(lib.pb_comm_allreduce_sum(self._h, a.ctypes.data_as(_capi.c_double_p), a.size))
+        return a
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.pb_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
 class _Handle:
     _destroy = None
 
@@ -432,12 +473,19 @@ class Backend(_Handle):
 
 
 class BackendPDHG(Backend):
-    def __init__(self, ctx, problem, opts=None, sopts=None):
+    def __init__(self, ctx, problem, opts=None, sopts=None, comm=None):
         super().__init__(ctx)
         self.problem = problem
         self.opts = opts or pdhg_options()
         self.sopts = sopts or solver_options()
         check(lib.pb_pdhg_create(ctx._h, problem._h, C.byref(self.opts), C.byref(self.sopts), C.byref(self._h)))
+        if comm is not None:
+            self.SetSlab(comm)
+
+    def SetSlab(self, comm):
+        """The problem is this rank's block of image columns (pb_backend_set_slab)."""
+        check(lib.pb_backend_set_slab(self._h, comm._h))
+        self.comm = comm
 
 
 class BackendADMM(Backend):

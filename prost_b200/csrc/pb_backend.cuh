@@ -103,6 +103,8 @@ class Backend {
   virtual void device_iterates(float** d_x, float** d_y) = 0;
   // iterations between two residual refreshes (for the solver loop's chunking)
   virtual int residual_iter() const = 0;
+  // slab decomposition (pb_comm.cuh); must be called before initialize()
+  virtual void set_slab(class Comm*) { fail(PB_ERR_UNSUPPORTED, "this backend has no slab decomposition"); }
 
   Context* ctx() const { return ctx_; }
   Problem* problem() const { return problem_.get(); }

@@ -8,6 +8,7 @@
 #include <new>
 
 #include "pb_backend.cuh"
+#include "pb_comm.cuh"
 #include "pb_problem.cuh"
 
 #ifndef PB_VERSION
@@ -20,6 +21,7 @@ struct pb_linop { pb::Context* ctx; std::shared_ptr<pb::LinearOperator> impl; bo
 struct pb_prox { pb::Context* ctx; std::shared_ptr<pb::Prox> impl; };
 struct pb_problem { std::shared_ptr<pb::Problem> impl; };
 struct pb_backend { std::shared_ptr<pb::Backend> impl; };
+struct pb_comm { std::unique_ptr<pb::Comm> impl; };
 
 namespace {
 
@@ -503,6 +505,33 @@ unsigned long long pb_backend_launch_count(const pb_backend* b) {
 }
 int pb_backend_device_iterates(pb_backend* b, float** d_x, float** d_y) {
   return guarded([&] { require(b && d_x && d_y, "NULL argument"); b->impl->device_iterates(d_x, d_y); });
+}
+
+// ---- slab decomposition --------------------------------------------------------------------------
+
+int pb_comm_unique_id(void* h_id_out) {
+  return guarded([&] { require(h_id_out != nullptr, "NULL argument"); pb::Comm::unique_id(h_id_out); });
+}
+int pb_comm_create(pb_context* c, int rank, int world, const void* h_id, pb_comm** out) {
+  return guarded([&] {
+    require(c && out, "pb_comm_create: NULL argument");
+    auto* h = new pb_comm();
+    try { h->impl.reset(new pb::Comm(&c->ctx, rank, world, h_id)); } catch (...) { delete h; throw; }
+    *out = h;
+  });
+}
+void pb_comm_destroy(pb_comm* c) { delete c; }
+int pb_comm_rank(const pb_comm* c) { return c ? c->impl->rank() : -1; }
+int pb_comm_world(const pb_comm* c) { return c ? c->impl->world() : 0; }
+int pb_comm_peer_to_peer(const pb_comm* c) { return c && c->impl->p2p() ? 1 : 0; }
+int pb_comm_barrier(pb_comm* c) {
+  return guarded([&] { require(c != nullptr, "NULL comm"); c->impl->barrier(); });
+}
+int pb_comm_allreduce_sum(pb_comm* c, double* h_buf, size_t n) {
+  return guarded([&] { require(c && h_buf, "NULL argument"); c->impl->allreduce_sum_host(h_buf, n); });
+}
+int pb_backend_set_slab(pb_backend* b, pb_comm* c) {
+  return guarded([&] { require(b && c, "NULL argument"); b->impl->set_slab(c->impl.get()); });
 }
 
 // ---- solver loop ---------------------------------------------------------------------------------

@@ -1,0 +1,253 @@
+// pb_comm.cu -- NCCL communicator + CUDA-IPC halo blocks for the slab decomposition (pb_comm.cuh).
+#include "pb_comm.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+namespace pb {
+
+namespace {
+
+// ---- lazily loaded NCCL entry points ---------------------------------------------------------------
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+  ncclResult_t (*CommDestroy)(ncclComm_t);
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*GroupStart)();
+  ncclResult_t (*GroupEnd)();
+  const char* (*GetErrorString)(ncclResult_t);
+};
+
+NcclApi& nccl() {
+  static NcclApi api;
+  static std::once_flag once;
+  static std::string err;
+  std::call_once(once, [] {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { err = std::string("cannot load libnccl.so.2: ") + dlerror(); return; }
+    auto sym = [&](const char* name) -> void* {
+      void* p = dlsym(h, name);
+      if (!p && err.empty()) err = std::string("libnccl is missing ") + name;
+      return p;
+    };
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+    api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
+    api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
+    api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
+    api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+    api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+  });
+  if (!err.empty()) fail(PB_ERR_UNSUPPORTED, "NCCL unavailable: " + err);
+  return api;
+}
+
+#define PB_NCCL(expr)                                                                       \
+  do {                                                                                      \
+    ncclResult_t pb_r__ = (expr);                                                           \
+    if (pb_r__ != ncclSuccess) {                                                            \
+      std::ostringstream pb_ss__;                                                           \
+      pb_ss__ << "NCCL error: " << nccl().GetErrorString(pb_r__) << " (" << #expr << " at " \
+              << __FILE__ << ":" << __LINE__ << ")";                                        \
+      ::pb::fail(PB_ERR_CUDA, pb_ss__.str());                                               \
+    }                                                                                       \
+  } while (0)
+
+inline ncclComm_t as_comm(void* p) { return static_cast<ncclComm_t>(p); }
+
+constexpr size_t kFlagBytes = 256;   // HaloFlags padded so that the float slots stay 16-byte aligned
+static_assert(sizeof(HaloFlags) <= kFlagBytes, "HaloFlags must fit its header");
+
+}  // namespace
+
+void Comm::unique_id(void* out128) {
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  PB_NCCL(nccl().GetUniqueId(&id));
+  std::memcpy(out128, &id, sizeof(id));
+}
+
+Comm::Comm(Context* ctx, int rank, int world, const void* id) : ctx_(ctx), rank_(rank), world_(world) {
+  if (world < 1 || rank < 0 || rank >= world) fail(PB_ERR_INVALID, "pb_comm_create: bad rank / world size");
+  if (!id) fail(PB_ERR_INVALID, "pb_comm_create: NULL unique id");
+  ctx_->bind();
+  ncclUniqueId uid;
+  std::memcpy(&uid, id, sizeof(uid));
+  ncclComm_t c = nullptr;
+  PB_NCCL(nccl().CommInitRank(&c, world, uid, rank));
+  nccl_ = c;
+  const char* mode = std::getenv("PB_HALO");
+  p2p_ = !(mode && std::strcmp(mode, "nccl") == 0);
+  scratch_.resize(16);
+}
+
+Comm::~Comm() {
+  cudaSetDevice(ctx_->device);
+  cudaStreamSynchronize(ctx_->stream);
+  release_halo();
+  if (nccl_) nccl().CommDestroy(as_comm(nccl_));
+}
+
+void Comm::release_halo() {
+  if (left_block_) cudaIpcCloseMemHandle(left_block_);
+  if (right_block_) cudaIpcCloseMemHandle(right_block_);
+  left_block_ = right_block_ = nullptr;
+  if (block_) cudaFree(block_);
+  block_ = nullptr;
+  flags_ = nullptr;
+  x_in_ = y_in_ = nullptr;
+  col_floats_ = 0;
+}
+
+void Comm::ensure_halo(size_t col_floats) {
+  ctx_->bind();
+  cudaStream_t s = ctx_->stream;
+  // every rank must agree on the size (and on p2p vs staging): checked with one all-reduce
+  // (zero variance: sum c = W c and sum c^2 = W c^2 hold on every rank only if all c are equal,
+  //  so either every rank throws or none does)
+  const double c = static_cast<double>(col_floats);
+  double chk[2] = {c, c * c};
+  allreduce_sum_host(chk, 2);
+  const double mean = chk[0] / world_;
+  if (chk[1] / world_ != mean * mean)
+    fail(PB_ERR_INVALID, "slab decomposition: ranks disagree on the halo column size (ny * L)");
+  if (col_floats == col_floats_ && block_) {
+    // same geometry as before: just reset the control words
+    PB_CUDA(cudaStreamSynchronize(s));
+    barrier();
+    PB_CUDA(cudaMemsetAsync(block_, 0, kFlagBytes, s));
+    PB_CUDA(cudaStreamSynchronize(s));
+    x_seq = y_seq = 0;
+    barrier();
+    return;
+  }
+  PB_CUDA(cudaStreamSynchronize(s));
+  barrier();                       // nobody still reads a block that is about to be unmapped
+  release_halo();
+  col_floats_ = col_floats;
+  x_seq = y_seq = 0;
+  const size_t bytes = kFlagBytes + 4 * col_floats * sizeof(float);
+  PB_CUDA(cudaMalloc(&block_, bytes));
+  PB_CUDA(cudaMemsetAsync(block_, 0, bytes, s));
+  flags_ = static_cast<HaloFlags*>(block_);
+  x_in_ = reinterpret_cast<float*>(static_cast<char*>(block_) + kFlagBytes);
+  y_in_ = x_in_ + 2 * col_floats;
+  stage_x_.resize(col_floats);
+  stage_y_.resize(col_floats);
+  stage_x_.zero(s);
+  stage_y_.zero(s);
+  PB_CUDA(cudaStreamSynchronize(s));
+
+  // exchange IPC handles (64 bytes per rank) with one all-gather, then map the two neighbours
+  int ok = 1;
+  if (p2p_ && world_ > 1) {
+    cudaIpcMemHandle_t mine;
+    std::memset(&mine, 0, sizeof(mine));
+    if (cudaIpcGetMemHandle(&mine, block_) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    DeviceBuffer<char> d_all(sizeof(mine) * world_), d_mine(sizeof(mine));
+    PB_CUDA(cudaMemcpyAsync(d_mine.data(), &mine, sizeof(mine), cudaMemcpyHostToDevice, s));
+    PB_NCCL(nccl().AllGather(d_mine.data(), d_all.data(), sizeof(mine), ncclChar, as_comm(nccl_), s));
+    std::vector<cudaIpcMemHandle_t> all(world_);
+    PB_CUDA(cudaMemcpyAsync(all.data(), d_all.data(), sizeof(mine) * world_, cudaMemcpyDeviceToHost, s));
+    PB_CUDA(cudaStreamSynchronize(s));
+    if (ok && has_left() &&
+        cudaIpcOpenMemHandle(&left_block_, all[rank_ - 1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError(); left_block_ = nullptr; ok = 0;
+    }
+    if (ok && has_right() &&
+        cudaIpcOpenMemHandle(&right_block_, all[rank_ + 1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError(); right_block_ = nullptr; ok = 0;
+    }
+  }
+  // p2p only if EVERY rank could map its neighbours; otherwise all ranks fall back to staging
+  double okd[1] = {ok ? 0.0 : 1.0};
+  allreduce_sum_host(okd, 1);
+  if (okd[0] != 0.0 || world_ == 1) {
+    if (p2p_ && world_ > 1 && rank_ == 0)
+      std::fprintf(stderr, "prost_b200: CUDA IPC halo mapping unavailable, using NCCL send/recv staging\n");
+    if (left_block_) cudaIpcCloseMemHandle(left_block_);
+    if (right_block_) cudaIpcCloseMemHandle(right_block_);
+    left_block_ = right_block_ = nullptr;
+    p2p_ = false;
+  }
+  barrier();
+}
+
+float* Comm::x_out(unsigned seq) const {
+  if (!has_left()) return nullptr;
+  if (!p2p_) return const_cast<float*>(stage_x_.data());
+  float* base = reinterpret_cast<float*>(static_cast<char*>(left_block_) + kFlagBytes);
+  return base + (seq & 1u) * col_floats_;
+}
+
+float* Comm::y_out(unsigned seq) const {
+  if (!has_right()) return nullptr;
+  if (!p2p_) return const_cast<float*>(stage_y_.data());
+  float* base = reinterpret_cast<float*>(static_cast<char*>(right_block_) + kFlagBytes);
+  return base + 2 * col_floats_ + (seq & 1u) * col_floats_;
+}
+
+unsigned* Comm::left_x_seq() const {
+  return (p2p_ && left_block_) ? &static_cast<HaloFlags*>(left_block_)->x_seq : nullptr;
+}
+unsigned* Comm::right_y_seq() const {
+  return (p2p_ && right_block_) ? &static_cast<HaloFlags*>(right_block_)->y_seq : nullptr;
+}
+
+void Comm::exchange_x(unsigned seq) {
+  if (p2p_ || world_ == 1) return;
+  PB_NCCL(nccl().GroupStart());
+  if (has_left()) PB_NCCL(nccl().Send(stage_x_.data(), col_floats_, ncclFloat, rank_ - 1, as_comm(nccl_), ctx_->stream));
+  if (has_right()) PB_NCCL(nccl().Recv(x_slot(seq), col_floats_, ncclFloat, rank_ + 1, as_comm(nccl_), ctx_->stream));
+  PB_NCCL(nccl().GroupEnd());
+}
+
+void Comm::exchange_y(unsigned seq) {
+  if (p2p_ || world_ == 1) return;
+  PB_NCCL(nccl().GroupStart());
+  if (has_right()) PB_NCCL(nccl().Send(stage_y_.data(), col_floats_, ncclFloat, rank_ + 1, as_comm(nccl_), ctx_->stream));
+  if (has_left()) PB_NCCL(nccl().Recv(y_slot(seq), col_floats_, ncclFloat, rank_ - 1, as_comm(nccl_), ctx_->stream));
+  PB_NCCL(nccl().GroupEnd());
+}
+
+void Comm::allreduce_sum(double* d_buf, size_t n) {
+  if (world_ == 1) return;
+  PB_NCCL(nccl().AllReduce(d_buf, d_buf, n, ncclDouble, ncclSum, as_comm(nccl_), ctx_->stream));
+}
+
+void Comm::allreduce_sum_host(double* h_buf, size_t n) {
+  if (world_ == 1) return;
+  ctx_->bind();
+  if (n > scratch_.size()) scratch_.resize(n);
+  scratch_.upload(h_buf, n, ctx_->stream);
+  allreduce_sum(scratch_.data(), n);
+  scratch_.download(h_buf, n, ctx_->stream);
+  PB_CUDA(cudaStreamSynchronize(ctx_->stream));
+}
+
+void Comm::barrier() {
+  double one[1] = {1.0};
+  allreduce_sum_host(one, 1);
+}
+
+void Comm::check_error() {
+  if (!flags_) return;
+  int e = 0;
+  PB_CUDA(cudaMemcpyAsync(&e, &flags_->error, sizeof(int), cudaMemcpyDeviceToHost, ctx_->stream));
+  PB_CUDA(cudaStreamSynchronize(ctx_->stream));
+  if (e) fail(PB_ERR_CUDA, "slab decomposition: timed out waiting for a neighbour's stencil halo");
+}
+
+}  // namespace pb

@@ -1,0 +1,96 @@
+// pb_comm.cuh -- one-process-per-GPU communicator for the slab decomposition.
+//
+// The reference is single-GPU (no NCCL/MPI/streams anywhere); this layer is what
+// lets the fused PDHG passes run on a column slab of a larger grid:
+//   * stencil halos travel peer-to-peer: every rank owns a small block of device memory (two
+//     ping-pong slots per direction + sequence flags) that its neighbours map through CUDA IPC,
+//     and the producing KERNEL stores its edge column straight into the neighbour's slot over
+//     NVLink, then publishes a sequence number; the consuming kernel's edge threads spin on that
+//     number, so the transfer overlaps the interior of both passes and no copy kernel, no
+//     NCCL call and no host synchronisation sits on the iteration path;
+//   * the four residual sums are combined with one ncclAllReduce (4 doubles) on the iteration
+//     stream at residual_iter boundaries only; every rank then runs the identical step-size
+//     state machine on identical bits.
+// If CUDA IPC is unavailable (e.g. PB_HALO=nccl, or the mapping fails) the same kernels write the
+// edge column to a local staging buffer and the halos move with ncclSend/ncclRecv between the passes.
+//
+// NCCL is loaded lazily (dlopen libnccl.so.2) so that single-GPU users carry no dependency and a
+// process that already loaded torch's bundled NCCL shares that copy.
+#pragma once
+
+#include "pb_common.cuh"
+
+namespace pb {
+
+// device-visible control words of one rank (lives at the start of the IPC block)
+struct HaloFlags {
+  unsigned x_seq;        // sequence number of the newest x halo written by the RIGHT neighbour
+  unsigned y_seq;        // sequence number of the newest y halo written by the LEFT neighbour
+  unsigned done_primal;  // local: edge CTAs of the running primal pass that finished
+  unsigned done_dual;    // local: same for the dual pass
+  int error;             // set by a kernel whose halo wait timed out
+  int pad[11];
+};
+
+class Comm {
+ public:
+  // collective over all ranks; `id` = 128 bytes from unique_id() on rank 0
+  Comm(Context* ctx, int rank, int world, const void* id);
+  ~Comm();
+  static void unique_id(void* out128);
+
+  int rank() const { return rank_; }
+  int world() const { return world_; }
+  bool p2p() const { return p2p_; }
+  bool has_left() const { return rank_ > 0; }
+  bool has_right() const { return rank_ + 1 < world_; }
+  Context* ctx() const { return ctx_; }
+
+  // collective: (re)allocates the halo block for edge columns of `col_floats` floats and maps the
+  // neighbours' blocks; resets the flags.  All ranks must pass the same size.
+  void ensure_halo(size_t col_floats);
+  size_t col_floats() const { return col_floats_; }
+
+  // in-stream sum over ranks of n doubles (device memory, in place)
+  void allreduce_sum(double* d_buf, size_t n);
+  // host-side conveniences (synchronise the stream)
+  void allreduce_sum_host(double* h_buf, size_t n);
+  void barrier();
+
+  // --- halo plumbing used by BackendPDHG (see pb_pdhg.cu: slab mode) -------------------------------
+  // local slots: what THIS rank reads
+  float* x_slot(unsigned seq) const { return x_in_ + (seq & 1u) * col_floats_; }   // from the right
+  float* y_slot(unsigned seq) const { return y_in_ + (seq & 1u) * col_floats_; }   // from the left
+  // where THIS rank writes its edge columns: the neighbour's slot (p2p) or the local staging buffer
+  float* x_out(unsigned seq) const;   // my column 0 of x      -> left neighbour's x slot
+  float* y_out(unsigned seq) const;   // my last column of y.gx -> right neighbour's y slot
+  HaloFlags* flags() const { return flags_; }
+  unsigned* left_x_seq() const;       // left neighbour's  flags->x_seq (p2p only, else null)
+  unsigned* right_y_seq() const;      // right neighbour's flags->y_seq (p2p only, else null)
+  // NCCL staging mode: move the staged edge column to the neighbour (no-ops in p2p mode)
+  void exchange_x(unsigned seq);
+  void exchange_y(unsigned seq);
+  // pass sequence numbers (identical on every rank: all ranks run the same passes)
+  unsigned x_seq = 0, y_seq = 0;
+  // throws if a kernel reported a halo timeout
+  void check_error();
+
+ private:
+  void release_halo();
+  Context* ctx_;
+  int rank_, world_;
+  void* nccl_ = nullptr;               // ncclComm_t
+  bool p2p_ = true;
+  size_t col_floats_ = 0;
+  // local IPC block: [HaloFlags | x_in[2][col] | y_in[2][col]]
+  void* block_ = nullptr;
+  HaloFlags* flags_ = nullptr;
+  float* x_in_ = nullptr;
+  float* y_in_ = nullptr;
+  void* left_block_ = nullptr;         // neighbours' blocks mapped into this process (p2p)
+  void* right_block_ = nullptr;
+  DeviceBuffer<float> stage_x_, stage_y_;   // staging mode
+  DeviceBuffer<double> scratch_;
+};
+
+}  // namespace pb

@@ -13,6 +13,7 @@
 #include <iostream>
 
 #include "pb_backend.cuh"
+#include "pb_comm.cuh"
 #include "pb_fused.cuh"
 #include "pb_reduce.cuh"
 #include "pb_stencil.cuh"
@@ -116,6 +117,55 @@ __global__ void __launch_bounds__(kBlock) pdhg_finalize_kernel(PdhgState* __rest
   }
 }
 
+// slab mode: the four sums were folded per rank and all-reduced; advance the state from them
+__global__ void pdhg_finalize_sums_kernel(PdhgState* __restrict__ st, PdhgParams prm,
+                                          const double* __restrict__ sums, unsigned long long iteration,
+                                          int check) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    PdhgState s = *st;
+    s.iteration = iteration;
+    pdhg_update(s, prm, sums, check != 0);
+    *st = s;
+  }
+}
+
+// slab mode, current_solution only: K u and K^T p over the local columns with the neighbours' halo
+// columns (same device functions, hence the same arithmetic, as the fused passes)
+template <bool THREE_D>
+__global__ void __launch_bounds__(kStencilBlock) slab_forward_kernel(const GradGeom g,
+                                                                    const float* __restrict__ u,
+                                                                    const float* __restrict__ u_halo,
+                                                                    float* __restrict__ kx) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= g.plane) return;
+  uint32_t xl, y, l, x;
+  g.div_q.divmod(t, xl, y);            // q = ny (VEC = 1)
+  g.div_nx.divmod(xl, l, x);
+  const uint32_t idx = y + x * g.ny + l * g.nxny;
+  float gx[1], gy[1], gl[1];
+  grad_fwd<1, THREE_D, true>(g, u, u_halo, idx, x, y, l, gx, gy, gl);
+  kx[idx] = gx[0];
+  kx[g.plane + idx] = gy[0];
+  if (THREE_D) kx[2u * (size_t)g.plane + idx] = gl[0];
+  if (g.has_id) kx[g.id_row + idx] = __fmul_rn(u[idx], g.id_factor);
+}
+
+template <bool THREE_D, bool HAS_ID>
+__global__ void __launch_bounds__(kStencilBlock) slab_adjoint_kernel(const GradGeom g,
+                                                                    const float* __restrict__ p,
+                                                                    const float* __restrict__ p_halo,
+                                                                    float* __restrict__ kty) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= g.plane) return;
+  uint32_t xl, y, l, x;
+  g.div_q.divmod(t, xl, y);
+  g.div_nx.divmod(xl, l, x);
+  const uint32_t idx = y + x * g.ny + l * g.nxny;
+  float out[1];
+  grad_adj<1, THREE_D, HAS_ID, true>(g, p, p_halo, idx, x, y, l, out);
+  kty[idx] = out[0];
+}
+
 // w = (x_prev - x) / (T tau) - kty_prev     (compute_w_variable_functor, :146-160)
 __global__ void __launch_bounds__(kBlock) w_variable_kernel(float* __restrict__ w,
                                                             const float* __restrict__ x_prev,
@@ -168,8 +218,14 @@ class BackendPDHG : public Backend {
   bool is_fused() const override { return fused_; }
   void device_iterates(float** d_x, float** d_y) override { *d_x = x_.data(); *d_y = y_.data(); }
   int residual_iter() const override { return opts_.residual_iter; }
+  void set_slab(Comm* comm) override { comm_ = comm; }
 
  private:
+  // slab mode (comm_ != nullptr): halo descriptors of the two passes, slab-aware K / K^T
+  void slab_primal_halo(unsigned xs);
+  void slab_dual_halo(unsigned xs, unsigned ys);
+  void slab_apply(float* d_res, const float* d_rhs, const float* d_halo, bool adjoint);
+  Comm* comm_ = nullptr;
   bool is_check_iteration() const {
     // size_t % int of the reference: a negative residual_iter wraps to a huge modulus, i.e.
     // "only at iteration 0" (Appendix B #4)
@@ -258,8 +314,15 @@ void BackendPDHG::initialize(const float* h_x0, size_t nx0, const float* h_y0, s
   params_.tol_abs_dual = sopts_.tol_abs_dual;
   params_.nrows = m;
   params_.ncols = n;
-  st.eps_primal = pdhg_eps(m, sopts_.tol_abs_primal, sopts_.tol_rel_primal, 0.f);
-  st.eps_dual = pdhg_eps(n, sopts_.tol_abs_dual, sopts_.tol_rel_dual, 0.f);
+  if (comm_) {
+    // eps_primal / eps_dual (backend.hpp:71-74) are functions of the GLOBAL problem size
+    double dims[2] = {static_cast<double>(m), static_cast<double>(n)};
+    comm_->allreduce_sum_host(dims, 2);
+    params_.nrows = static_cast<unsigned long long>(dims[0]);
+    params_.ncols = static_cast<unsigned long long>(dims[1]);
+  }
+  st.eps_primal = pdhg_eps(params_.nrows, sopts_.tol_abs_primal, sopts_.tol_rel_primal, 0.f);
+  st.eps_dual = pdhg_eps(params_.ncols, sopts_.tol_abs_dual, sopts_.tol_rel_dual, 0.f);
 
   // proxes, conjugated through Moreau where only the other form was given (:236-266)
   prox_g_.clear();
@@ -277,6 +340,9 @@ void BackendPDHG::initialize(const float* h_x0, size_t nx0, const float* h_y0, s
     prox_fstar_ = problem_->prox_fstar();
   }
 
+  if (opts_.scale_steps_operator && comm_)
+    fail(PB_ERR_UNSUPPORTED, "slab decomposition: scale_steps_operator (normest) is not distributed; "
+                             "set scale_steps_operator = false");
   if (opts_.scale_steps_operator) {                      // :274-286
     const float norm = problem_->normest(1e-6f, 100, opts_.normest_x0);
     if (std::abs(norm - 1) > 0.1) {
@@ -292,6 +358,30 @@ void BackendPDHG::initialize(const float* h_x0, size_t nx0, const float* h_y0, s
   if (ny0 > 0 && ny0 != m) fail(PB_ERR_INVALID, "Initial dual solution has wrong size.");
 
   fused_ = plan_fused();
+  if (comm_) {
+    // the halo protocol lives in the specialised stencil passes: one planar gradient operator
+    // (+ identity rows), one prox_g over all columns, Norm2 on the gradient rows
+    const ScaleRef Tr = problem_->right_ref(), Sr = problem_->left_ref();
+    bool ok = fused_ && stencil_.ok && g_descs_.size() == 1;
+    if (ok)
+      ok = stencil_primal_launch(ctx_, stencil_, g_descs_[0], nullptr, nullptr, nullptr, Tr, nullptr, false,
+                                 false, false, nullptr, nullptr, true) > 0;
+    int halo_passes = 0;
+    for (auto& d : f_descs_) {
+      if (!ok) break;
+      ok = stencil_dual_launch(ctx_, stencil_, d, nullptr, nullptr, nullptr, Sr, nullptr, false, false, nullptr,
+                               nullptr, true) > 0;
+      if (d.index == 0) ++halo_passes;
+    }
+    ok = ok && halo_passes == 1;
+    // every rank must come to the same verdict, otherwise the collective below would hang
+    double bad[1] = {ok ? 0.0 : 1.0};
+    comm_->allreduce_sum_host(bad, 1);
+    if (bad[0] != 0.0)
+      fail(PB_ERR_UNSUPPORTED, "slab decomposition needs the fused stencil passes: K = planar "
+                               "BlockGradient2D/3D (+ identity rows), one prox_g, Norm2 prox on the gradient rows");
+    comm_->ensure_halo((size_t)stencil_.geom.ny * stencil_.geom.L);
+  }
   try {
     x_.resize(n); x_prev_.resize(n); y_.resize(m); y_prev_.resize(m);
     if (!fused_) {
@@ -342,6 +432,8 @@ void BackendPDHG::iteration_fused() {
 
   // primal pass: x_prev_ <- prox_g(x_ - tau T K^T y_), then swap so that x_ is x^{k+1}
   unsigned off = 0;
+  unsigned xs = 0, ys = 0;
+  if (comm_) { xs = ++comm_->x_seq; slab_primal_halo(xs); }
   for (auto& d : g_descs_) {
     unsigned g = stencil_primal_launch(ctx_, stencil_, d, x_.data(), y_.data(), y_prev_.data(), T, st,
                                        iteration_ == 0, iteration_ <= 1, check,
@@ -353,6 +445,7 @@ void BackendPDHG::iteration_fused() {
   }
   const unsigned nd = off;
   x_.swap(x_prev_);
+  if (comm_) { comm_->exchange_x(xs); ys = ++comm_->y_seq; slab_dual_halo(xs, ys); }
   if (prof_ev_) PB_CUDA(cudaEventRecord(prof_ev_[1], ctx_->stream));
 
   // dual pass: y_prev_ <- prox_f*(y_ + sigma S K(2x^{k+1} - x^k)) (theta-extrapolated), then swap
@@ -367,15 +460,93 @@ void BackendPDHG::iteration_fused() {
   }
   const unsigned np = off;
   y_.swap(y_prev_);
+  if (comm_) { comm_->exchange_y(ys); stencil_.geom.halo = SlabHalo(); }
   if (prof_ev_) PB_CUDA(cudaEventRecord(prof_ev_[2], ctx_->stream));
 
-  if (check || opts_.stepsize_variant == PB_PDHG_ALG2) {
+  if (comm_ && comm_->world() > 1 && check) {
+    // per-rank fold -> one 4-double all-reduce -> identical state machine on every rank
+    fold_residuals_kernel<<<1, kBlock, 0, ctx_->stream>>>(part_p_.data(), np, part_d_.data(), nd,
+                                                          d_sums_.data());
+    PB_CHECK_LAUNCH();
+    comm_->allreduce_sum(d_sums_.data(), 4);
+    pdhg_finalize_sums_kernel<<<1, 32, 0, ctx_->stream>>>(d_state_.data(), params_, d_sums_.data(),
+                                                          iteration_, 1);
+    PB_CHECK_LAUNCH();
+    ctx_->launches += 2;
+  } else if (check || opts_.stepsize_variant == PB_PDHG_ALG2) {
     pdhg_finalize_kernel<<<1, kBlock, 0, ctx_->stream>>>(d_state_.data(), params_, part_p_.data(), np,
                                                          part_d_.data(), nd, iteration_, check ? 1 : 0);
     PB_CHECK_LAUNCH();
     ctx_->launches++;
   }
   iteration_++;
+}
+
+// Halo descriptor of the primal pass number `xs` (pb_comm.cuh): reads the y columns the left
+// neighbour's dual passes y_seq / y_seq-1 delivered, hands column 0 of the new x to the left.
+void BackendPDHG::slab_primal_halo(unsigned xs) {
+  SlabHalo h;
+  h.has_left = comm_->has_left();
+  h.has_right = comm_->has_right();
+  const unsigned ys = comm_->y_seq;                  // newest y halo
+  h.in_a = comm_->y_slot(ys);
+  h.in_b = comm_->y_slot(ys - 1);
+  h.out = comm_->x_out(xs);
+  if (comm_->p2p() && h.has_left) {
+    HaloFlags* f = comm_->flags();
+    h.wait_flag = &f->y_seq;
+    h.wait_seq = ys;
+    h.done_counter = &f->done_primal;
+    h.signal_flag = comm_->left_x_seq();
+    h.signal_seq = xs;
+    h.error = &f->error;
+  }
+  stencil_.geom.halo = h;
+}
+
+// Dual pass number `ys`: reads the x columns of the right neighbour's primal passes xs / xs-1,
+// hands the last column of the new x-component of y to the right.
+void BackendPDHG::slab_dual_halo(unsigned xs, unsigned ys) {
+  SlabHalo h;
+  h.has_left = comm_->has_left();
+  h.has_right = comm_->has_right();
+  h.in_a = comm_->x_slot(xs);
+  h.in_b = comm_->x_slot(xs - 1);
+  h.out = comm_->y_out(ys);
+  if (comm_->p2p() && h.has_right) {
+    HaloFlags* f = comm_->flags();
+    h.wait_flag = &f->x_seq;
+    h.wait_seq = xs;
+    h.done_counter = &f->done_dual;
+    h.signal_flag = comm_->right_y_seq();
+    h.signal_seq = ys;
+    h.error = &f->error;
+  }
+  stencil_.geom.halo = h;
+}
+
+// K u / K^T p on the local slab including the neighbours' columns (current_solution only)
+void BackendPDHG::slab_apply(float* d_res, const float* d_rhs, const float* d_halo, bool adjoint) {
+  GradGeom g = stencil_.geom;
+  g.q = g.ny;
+  g.div_q = FastDiv(g.ny);
+  g.div_nx = FastDiv(g.nx);
+  g.halo = SlabHalo();
+  g.halo.has_left = comm_->has_left();
+  g.halo.has_right = comm_->has_right();
+  const unsigned grid = (g.plane + kStencilBlock - 1) / kStencilBlock;
+  cudaStream_t s = ctx_->stream;
+  if (!adjoint) {
+    if (stencil_.three_d) slab_forward_kernel<true><<<grid, kStencilBlock, 0, s>>>(g, d_rhs, d_halo, d_res);
+    else slab_forward_kernel<false><<<grid, kStencilBlock, 0, s>>>(g, d_rhs, d_halo, d_res);
+  } else if (stencil_.three_d) {
+    if (g.has_id) slab_adjoint_kernel<true, true><<<grid, kStencilBlock, 0, s>>>(g, d_rhs, d_halo, d_res);
+    else slab_adjoint_kernel<true, false><<<grid, kStencilBlock, 0, s>>>(g, d_rhs, d_halo, d_res);
+  } else {
+    if (g.has_id) slab_adjoint_kernel<false, true><<<grid, kStencilBlock, 0, s>>>(g, d_rhs, d_halo, d_res);
+    else slab_adjoint_kernel<false, false><<<grid, kStencilBlock, 0, s>>>(g, d_rhs, d_halo, d_res);
+  }
+  PB_CHECK_LAUNCH();
 }
 
 void BackendPDHG::iteration_unfused() {
@@ -465,6 +636,7 @@ PdhgState BackendPDHG::fetch_state() {
 void BackendPDHG::residuals(float out[6]) {
   ctx_->bind();
   const PdhgState st = fetch_state();
+  if (comm_) comm_->check_error();
   out[0] = st.primal_residual;
   out[1] = st.dual_residual;
   out[2] = st.primal_var_norm;
@@ -497,6 +669,7 @@ void BackendPDHG::current_solution(float* h_x, float* h_z, float* h_y, float* h_
       if (h_w) {
         if (sol_a_.size() != n) { sol_a_.resize(n); sol_b_.resize(n); }
         if (iteration_ <= 1) sol_a_.zero(s);
+        else if (comm_) slab_apply(sol_a_.data(), y_prev_.data(), comm_->y_slot(comm_->y_seq - 1), true);
         else problem_->apply_K(sol_a_.data(), y_prev_.data(), true);
         w_variable_kernel<<<sgrid(n), kBlock, 0, s>>>(sol_b_.data(), x_prev_.data(), x_.data(), T,
                                                       sol_a_.data(), n, st.tau);
@@ -508,8 +681,10 @@ void BackendPDHG::current_solution(float* h_x, float* h_z, float* h_y, float* h_
         if (sol_a_.size() != m) { sol_a_.resize(m); sol_b_.resize(m); }
         if (sol_c_.size() != m) sol_c_.resize(m);
         if (iteration_ == 0) sol_a_.zero(s);
+        else if (comm_) slab_apply(sol_a_.data(), x_.data(), comm_->x_slot(comm_->x_seq), false);
         else problem_->apply_K(sol_a_.data(), x_.data(), false);
         if (iteration_ <= 1) sol_b_.zero(s);
+        else if (comm_) slab_apply(sol_b_.data(), x_prev_.data(), comm_->x_slot(comm_->x_seq - 1), false);
         else problem_->apply_K(sol_b_.data(), x_prev_.data(), false);
         z_variable_kernel<<<sgrid(m), kBlock, 0, s>>>(sol_c_.data(), y_prev_.data(), y_.data(), S,
                                                       sol_a_.data(), sol_b_.data(), m, st.sigma, st.theta);
@@ -532,6 +707,9 @@ void BackendPDHG::current_solution(float* h_x, float* h_z, float* h_y, float* h_
     }
   }
   PB_CUDA(cudaStreamSynchronize(s));
+  // slab mode: the halo slots read above are overwritten by the neighbours' next passes, so no rank
+  // may run ahead before every rank is done reading (current_solution is collective)
+  if (comm_) { comm_->check_error(); comm_->barrier(); }
 }
 
 std::shared_ptr<Backend> make_backend_pdhg(Context* ctx, std::shared_ptr<Problem> prob,

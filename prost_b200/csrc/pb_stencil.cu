@@ -4,6 +4,9 @@
 //   part 1  primal kernels with per-pixel label groups (simplex)
 //   part 2  dual Norm2 kernels on the gradient rows
 //   part 3  dual pass on identity rows (generic leaf prox, no stencil)
+// and, for parts 0..2, a second time with -DPB_STENCIL_SLAB=1: the same kernels with the halo
+// protocol of the slab decomposition compiled in (SLAB = true).  The single-GPU instantiations
+// carry none of it (no extra registers, branches or barriers).
 #include "pb_stencil.cuh"
 
 #include <algorithm>
@@ -11,18 +14,38 @@
 #ifndef PB_STENCIL_PART
 #error "compile with -DPB_STENCIL_PART=<0..3>"
 #endif
+#ifndef PB_STENCIL_SLAB
+#define PB_STENCIL_SLAB 0
+#endif
 
 namespace pb {
 
-// implemented in the other parts
-unsigned stencil_primal_simplex_launch(Context* ctx, const GradGeom& g, bool three_d, const ProxDesc& d,
-                                       const float* x, const float* y, const float* y_prev, ScaleRef T,
-                                       const PdhgState* st, bool kty_zero, bool ktyprev_zero, bool check,
-                                       double* partials, float* x_out, bool dry_run);
-unsigned stencil_dual_norm2_launch(Context* ctx, const GradGeom& g, bool three_d, const ProxDesc& d,
-                                   const float* y, const float* x_new, const float* x_old, ScaleRef S,
-                                   const PdhgState* st, bool kxprev_zero, bool check, double* partials,
-                                   float* y_out, bool dry_run);
+constexpr bool kSlab = PB_STENCIL_SLAB != 0;
+
+// Every launch function exists in two flavours with distinct names (plain functions, so that no TU
+// can implicitly instantiate the other flavour with its own kernels): <name>_single is compiled in
+// the PB_STENCIL_SLAB=0 objects, <name>_slab in the PB_STENCIL_SLAB=1 objects.
+#if PB_STENCIL_SLAB
+#define PB_FLAVOUR(name) name##_slab
+#else
+#define PB_FLAVOUR(name) name##_single
+#endif
+
+#define PB_DECLARE_PRIMAL(name)                                                                          \
+  unsigned name(Context* ctx, const GradGeom& g0, bool three_d, const ProxDesc& d, const float* x,        \
+                const float* y, const float* y_prev, ScaleRef T, const PdhgState* st, bool kty_zero,      \
+                bool ktyprev_zero, bool check, double* partials, float* x_out, bool dry_run)
+#define PB_DECLARE_DUAL(name)                                                                            \
+  unsigned name(Context* ctx, const GradGeom& g0, bool three_d, const ProxDesc& d, const float* y,        \
+                const float* x_new, const float* x_old, ScaleRef S, const PdhgState* st, bool kxprev_zero, \
+                bool check, double* partials, float* y_out, bool dry_run)
+PB_DECLARE_PRIMAL(stencil_primal1_launch_single);
+PB_DECLARE_PRIMAL(stencil_primal1_launch_slab);
+PB_DECLARE_PRIMAL(stencil_primal_simplex_launch_single);
+PB_DECLARE_PRIMAL(stencil_primal_simplex_launch_slab);
+PB_DECLARE_DUAL(stencil_dual_norm2_launch_single);
+PB_DECLARE_DUAL(stencil_dual_norm2_launch_slab);
+
 unsigned stencil_dual_identity_launch(Context* ctx, const GradGeom& g, const ProxDesc& d, const float* y,
                                       const float* x_new, const float* x_old, ScaleRef S, const PdhgState* st,
                                       bool kxprev_zero, bool check, double* partials, float* y_out,
@@ -32,6 +55,7 @@ static inline GradGeom with_vec(GradGeom g, int vec) {
   g.q = g.ny / vec;
   g.div_q = FastDiv(g.q);
   g.div_nx = FastDiv(g.nx);
+  g.div_L = FastDiv(g.L);
   return g;
 }
 
@@ -43,6 +67,7 @@ static inline unsigned grid_threads(size_t threads) {
 
 #if PB_STENCIL_PART == 0
 
+#if !PB_STENCIL_SLAB
 StencilPlan plan_stencil(const std::vector<std::shared_ptr<Block>>& blocks, size_t nrows, size_t ncols) {
   StencilPlan plan;
   const Block* grad = nullptr;
@@ -78,16 +103,17 @@ StencilPlan plan_stencil(const std::vector<std::shared_ptr<Block>>& blocks, size
   plan.ok = true;
   return plan;
 }
+#endif  // !PB_STENCIL_SLAB
 
 template <int VEC, int KIND, int FN, bool THREE_D, bool HAS_ID>
 static void primal1_launch(Context* ctx, unsigned grid, const GradGeom& g, const ProxDesc& d, const float* x,
                            const float* y, const float* y_prev, ScaleRef T, const PdhgState* st,
                            bool kty_zero, bool ktyprev_zero, bool check, double* partials, float* x_out) {
   if (check)
-    grad_primal_kernel<VEC, 1, KIND, FN, THREE_D, HAS_ID, true><<<grid, kStencilBlock, 0, ctx->stream>>>(
+    grad_primal_kernel<VEC, 1, KIND, FN, THREE_D, HAS_ID, true, kSlab><<<grid, kStencilBlock, 0, ctx->stream>>>(
         g, d, x, y, y_prev, T, st, kty_zero, ktyprev_zero, partials, x_out);
   else
-    grad_primal_kernel<VEC, 1, KIND, FN, THREE_D, HAS_ID, false><<<grid, kStencilBlock, 0, ctx->stream>>>(
+    grad_primal_kernel<VEC, 1, KIND, FN, THREE_D, HAS_ID, false, kSlab><<<grid, kStencilBlock, 0, ctx->stream>>>(
         g, d, x, y, y_prev, T, st, kty_zero, ktyprev_zero, partials, x_out);
 }
 
@@ -106,26 +132,36 @@ static void primal1_geom(Context* ctx, unsigned grid, const GradGeom& g, bool th
 #undef PB_ARGS
 }
 
+#if !PB_STENCIL_SLAB
 unsigned stencil_primal_launch(Context* ctx, const StencilPlan& plan, const ProxDesc& d, const float* x,
                                const float* y, const float* y_prev, ScaleRef T, const PdhgState* st,
                                bool kty_zero, bool ktyprev_zero, bool check, double* partials, float* x_out,
                                bool dry_run) {
   if (!plan.ok || d.index != 0) return 0;
   const GradGeom& g0 = plan.geom;
+  const bool slab = g0.halo.has_left || g0.halo.has_right;
+#define PB_ARGS ctx, g0, plan.three_d, d, x, y, y_prev, T, st, kty_zero, ktyprev_zero, check, partials, x_out, dry_run
   if (d.kind == kProxSimplex)
-    return stencil_primal_simplex_launch(ctx, g0, plan.three_d, d, x, y, y_prev, T, st, kty_zero,
-                                         ktyprev_zero, check, partials, x_out, dry_run);
+    return slab ? stencil_primal_simplex_launch_slab(PB_ARGS) : stencil_primal_simplex_launch_single(PB_ARGS);
   if (d.kind != kProxElem1D && d.kind != kProxZero) return 0;
+  return slab ? stencil_primal1_launch_slab(PB_ARGS) : stencil_primal1_launch_single(PB_ARGS);
+#undef PB_ARGS
+}
+#endif  // !PB_STENCIL_SLAB
+
+PB_DECLARE_PRIMAL(PB_FLAVOUR(stencil_primal1_launch)) {
   if (d.dim != 1 || d.count != g0.plane) return 0;
   bool vec4 = (g0.ny % 4 == 0) && aligned16(x) && aligned16(y) && aligned16(y_prev) && aligned16(x_out) &&
               (!T.ptr || aligned16(T.ptr)) && (!g0.has_id || g0.id_row % 4 == 0);
   for (int k = 0; k < 7; ++k)
     if (d.coeffs.ptr[k] && !aligned16(d.coeffs.ptr[k])) vec4 = false;
+  if (g0.halo.has_left && vec4 && !aligned16(g0.halo.out)) vec4 = false;
   const int vec = vec4 ? 4 : 1;
-  const GradGeom g = with_vec(g0, vec);
+  GradGeom g = with_vec(g0, vec);
+  g.halo.n_edge_ctas = count_edge_ctas(g.q, g.L);
   const unsigned grid = grid_threads((size_t)g.q * g.nx * g.L);
   if (dry_run || grid == 0) return grid;
-#define PB_ARGS ctx, grid, g, plan.three_d, d, x, y, y_prev, T, st, kty_zero, ktyprev_zero, check, partials, x_out
+#define PB_ARGS ctx, grid, g, three_d, d, x, y, y_prev, T, st, kty_zero, ktyprev_zero, check, partials, x_out
   // Function1D members with their own instantiation (the data terms of the reference's examples:
   // quadratic for ROF, abs for TV-L1); every other member dispatches at run time (FN = -1)
   if (d.kind == kProxElem1D) {
@@ -145,20 +181,26 @@ unsigned stencil_primal_launch(Context* ctx, const StencilPlan& plan, const Prox
   return grid;
 }
 
+#if !PB_STENCIL_SLAB
 unsigned stencil_dual_launch(Context* ctx, const StencilPlan& plan, const ProxDesc& d, const float* y,
                              const float* x_new, const float* x_old, ScaleRef S, const PdhgState* st,
                              bool kxprev_zero, bool check, double* partials, float* y_out, bool dry_run) {
   if (!plan.ok) return 0;
   const GradGeom& g = plan.geom;
   const uint32_t grad_rows = (plan.three_d ? 3u : 2u) * g.plane;
-  if (d.index == 0 && d.kind == kProxNorm2 && (size_t)d.count * d.dim == grad_rows)
-    return stencil_dual_norm2_launch(ctx, g, plan.three_d, d, y, x_new, x_old, S, st, kxprev_zero, check,
-                                     partials, y_out, dry_run);
+  if (d.index == 0 && d.kind == kProxNorm2 && (size_t)d.count * d.dim == grad_rows) {
+    if (g.halo.has_left || g.halo.has_right)
+      return stencil_dual_norm2_launch_slab(ctx, g, plan.three_d, d, y, x_new, x_old, S, st, kxprev_zero,
+                                            check, partials, y_out, dry_run);
+    return stencil_dual_norm2_launch_single(ctx, g, plan.three_d, d, y, x_new, x_old, S, st, kxprev_zero,
+                                            check, partials, y_out, dry_run);
+  }
   if (g.has_id && d.index == g.id_row && (size_t)d.count * d.dim == g.plane)
     return stencil_dual_identity_launch(ctx, g, d, y, x_new, x_old, S, st, kxprev_zero, check, partials,
                                         y_out, dry_run);
   return 0;
 }
+#endif  // !PB_STENCIL_SLAB
 
 #elif PB_STENCIL_PART == 1
 
@@ -167,21 +209,19 @@ static void simplex_launch(Context* ctx, unsigned grid, const GradGeom& g, const
                            const float* y, const float* y_prev, ScaleRef T, const PdhgState* st,
                            bool kty_zero, bool ktyprev_zero, bool check, double* partials, float* x_out) {
   if (check)
-    grad_primal_kernel<1, CAPL, kProxSimplex, -1, false, HAS_ID, true><<<grid, kStencilBlock, 0, ctx->stream>>>(
+    grad_primal_kernel<1, CAPL, kProxSimplex, -1, false, HAS_ID, true, kSlab><<<grid, kStencilBlock, 0, ctx->stream>>>(
         g, d, x, y, y_prev, T, st, kty_zero, ktyprev_zero, partials, x_out);
   else
-    grad_primal_kernel<1, CAPL, kProxSimplex, -1, false, HAS_ID, false><<<grid, kStencilBlock, 0, ctx->stream>>>(
+    grad_primal_kernel<1, CAPL, kProxSimplex, -1, false, HAS_ID, false, kSlab><<<grid, kStencilBlock, 0, ctx->stream>>>(
         g, d, x, y, y_prev, T, st, kty_zero, ktyprev_zero, partials, x_out);
 }
 
-unsigned stencil_primal_simplex_launch(Context* ctx, const GradGeom& g0, bool three_d, const ProxDesc& d,
-                                       const float* x, const float* y, const float* y_prev, ScaleRef T,
-                                       const PdhgState* st, bool kty_zero, bool ktyprev_zero, bool check,
-                                       double* partials, float* x_out, bool dry_run) {
+PB_DECLARE_PRIMAL(PB_FLAVOUR(stencil_primal_simplex_launch)) {
   // simplex over the labels of a pixel: planar, count = nx*ny, dim = L (2-D gradient only)
   if (three_d || d.interleaved || d.moreau || d.count != g0.nxny || d.dim != g0.L || g0.L < 2 || g0.L > 32)
     return 0;
-  const GradGeom g = with_vec(g0, 1);
+  GradGeom g = with_vec(g0, 1);
+  g.halo.n_edge_ctas = count_edge_ctas(g.q, 1);
   const unsigned grid = grid_threads((size_t)g.q * g.nx);
   if (dry_run || grid == 0) return grid;
   const int cap = g.L <= 4 ? 4 : g.L <= 8 ? 8 : g.L <= 16 ? 16 : 32;
@@ -203,10 +243,10 @@ static void dual_launch_fn(Context* ctx, unsigned grid, const GradGeom& g, const
                            const float* x_new, const float* x_old, ScaleRef S, const PdhgState* st,
                            bool kxprev_zero, bool check, double* partials, float* y_out) {
   if (check)
-    grad_dual_norm2_kernel<VEC, CAPL, FN, THREE_D, true><<<grid, kStencilBlock, 0, ctx->stream>>>(
+    grad_dual_norm2_kernel<VEC, CAPL, FN, THREE_D, true, kSlab><<<grid, kStencilBlock, 0, ctx->stream>>>(
         g, d, y, x_new, x_old, S, st, kxprev_zero, partials, y_out);
   else
-    grad_dual_norm2_kernel<VEC, CAPL, FN, THREE_D, false><<<grid, kStencilBlock, 0, ctx->stream>>>(
+    grad_dual_norm2_kernel<VEC, CAPL, FN, THREE_D, false, kSlab><<<grid, kStencilBlock, 0, ctx->stream>>>(
         g, d, y, x_new, x_old, S, st, kxprev_zero, partials, y_out);
 }
 
@@ -224,10 +264,7 @@ static void dual_launch(Context* ctx, unsigned grid, const GradGeom& g, const Pr
     dual_launch_fn<VEC, CAPL, -1, THREE_D>(ctx, grid, g, d, y, x_new, x_old, S, st, kxprev_zero, check, partials, y_out);
 }
 
-unsigned stencil_dual_norm2_launch(Context* ctx, const GradGeom& g0, bool three_d, const ProxDesc& d,
-                                   const float* y, const float* x_new, const float* x_old, ScaleRef S,
-                                   const PdhgState* st, bool kxprev_zero, bool check, double* partials,
-                                   float* y_out, bool dry_run) {
+PB_DECLARE_DUAL(PB_FLAVOUR(stencil_dual_norm2_launch)) {
   if (d.interleaved) return 0;
   const uint32_t ncomp = three_d ? 3u : 2u;
   const bool per_voxel = d.count == g0.plane && d.dim == ncomp;
@@ -238,8 +275,10 @@ unsigned stencil_dual_norm2_launch(Context* ctx, const GradGeom& g0, bool three_
   for (int k = 0; k < 7; ++k)
     if (d.coeffs.ptr[k] && !aligned16(d.coeffs.ptr[k])) vec4 = false;
   if (per_pixel && g0.L > 4) vec4 = false;             // keep the group within the register budget
+  if (g0.halo.has_right && vec4 && !aligned16(g0.halo.out)) vec4 = false;
   const int vec = vec4 ? 4 : 1;
-  const GradGeom g = with_vec(g0, vec);
+  GradGeom g = with_vec(g0, vec);
+  g.halo.n_edge_ctas = count_edge_ctas(g.q, per_voxel ? g.L : 1u);
   const unsigned grid = grid_threads((size_t)g.q * g.nx * (per_voxel ? g.L : 1u));
   if (dry_run || grid == 0) return grid;
 #define PB_ARGS ctx, grid, g, d, y, x_new, x_old, S, st, kxprev_zero, check, partials, y_out

@@ -30,16 +30,46 @@
 
 namespace pb {
 
+// Slab decomposition along x: the local grid is a block of columns of a wider
+// image.  The primal pass talks to the LEFT neighbour through its column x = 0 (it needs the
+// neighbour's last column of the x-component of y for the divergence and hands over its new
+// column 0 of x); the dual pass talks to the RIGHT neighbour through its column x = nx-1 (it needs
+// the neighbour's first column of x_new / x_old for the forward difference and hands over its new
+// last column of the x-component of y).  `in_a / in_b` are the received columns of the pass's two
+// stencil operands (primal: y, y_prev; dual: x_new, x_old), laid out  y + l*ny.  `out` is where the
+// outgoing column goes: the neighbour's slot mapped over NVLink (peer-to-peer mode) or a local
+// staging buffer (NCCL mode, all flag pointers null).  See pb_comm.cuh for the protocol.
+struct SlabHalo {
+  int has_left = 0, has_right = 0;
+  const float* in_a = nullptr;
+  const float* in_b = nullptr;
+  float* out = nullptr;
+  const unsigned* wait_flag = nullptr;   // local sequence word the neighbour publishes to
+  unsigned wait_seq = 0;                 // edge threads spin until *wait_flag >= wait_seq (0: no wait)
+  unsigned* done_counter = nullptr;      // local: counts finished edge CTAs of this launch
+  unsigned n_edge_ctas = 0;
+  unsigned* signal_flag = nullptr;       // neighbour's sequence word (peer memory)
+  unsigned signal_seq = 0;
+  int* error = nullptr;                  // set when a wait times out
+};
+
 struct GradGeom {
   uint32_t nx = 0, ny = 0, L = 0, nxny = 0, plane = 0;
   uint32_t q = 0;                 // ny / VEC
-  FastDiv div_q, div_nx;
+  FastDiv div_q, div_nx, div_L;
   int has_id = 0;                 // identity block  id_factor * I  at rows [id_row, id_row + plane)
   uint32_t id_row = 0;
   float id_factor = 1.f;
+  SlabHalo halo;                  // all zero on a single GPU
 };
 
 constexpr int kStencilBlock = 128;
+
+// Slab kernels map the edge column to threads [0, n_l * q) (n_l = L for per-voxel groups, 1 for
+// per-pixel groups): the number of CTAs the last edge CTA waits for before it publishes the halo.
+inline unsigned count_edge_ctas(uint32_t q, uint32_t n_l) {
+  return (unsigned)(((size_t)q * n_l + kStencilBlock - 1) / kStencilBlock);
+}
 
 #ifdef __CUDACC__
 
@@ -58,6 +88,46 @@ template <> struct VecIO<4> {
   }
 };
 
+// ---- halo protocol (device side) ---------------------------------------------------------------------
+// Edge threads spin (acquire, system scope) until the neighbour has published sequence `wait_seq`.
+// Bounded: after ~2 s the kernel gives up, raises the error word and carries on with stale data so
+// that a dead neighbour cannot hang the GPU.
+__device__ __forceinline__ void halo_wait(const SlabHalo& h) {
+  if (!h.wait_flag || h.wait_seq == 0) return;
+  if (h.error && *reinterpret_cast<volatile int*>(h.error)) return;   // sticky: one timeout poisons the solve
+  unsigned v;
+  unsigned long long t0 = 0;
+  for (unsigned spins = 0;; ++spins) {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(h.wait_flag) : "memory");
+    if ((int)(v - h.wait_seq) >= 0) break;
+    if ((spins & 1023u) == 1023u) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ull) { if (h.error) atomicExch(h.error, 1); break; }
+    }
+  }
+}
+
+// Called by every thread of the CTA at the end of a pass.  Edge threads fence their remote stores,
+// the CTA's thread 0 counts the CTA in, and the last edge CTA publishes the sequence number in the
+// neighbour's memory (release, system scope) -- by then every halo store AND every halo load of
+// this launch has been performed, which is what makes two ping-pong slots sufficient.
+__device__ __forceinline__ void halo_signal(const SlabHalo& h, bool edge_thread) {
+  if (!h.done_counter) return;                                 // uniform: single GPU or NCCL staging
+  if (edge_thread) __threadfence_system();
+  const int any = __syncthreads_or(edge_thread ? 1 : 0);
+  if (any && threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(h.done_counter, 1u);
+    if (prev + 1 == h.n_edge_ctas) {
+      atomicExch(h.done_counter, 0u);
+      __threadfence_system();
+      if (h.signal_flag)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(h.signal_flag), "r"(h.signal_seq) : "memory");
+    }
+  }
+}
+
 template <int VEC>
 __device__ __forceinline__ void load_scale(const ScaleRef& s, uint32_t e, float (&o)[VEC]) {
   if (s.ptr) {
@@ -69,14 +139,20 @@ __device__ __forceinline__ void load_scale(const ScaleRef& s, uint32_t e, float 
 }
 
 // forward differences of u at idx .. idx+VEC-1 (same column x, label l)
-template <int VEC, bool THREE_D>
-__device__ __forceinline__ void grad_fwd(const GradGeom& g, const float* __restrict__ u, uint32_t idx,
+template <int VEC, bool THREE_D, bool SLAB>
+__device__ __forceinline__ void grad_fwd(const GradGeom& g, const float* __restrict__ u,
+                                         const float* __restrict__ u_halo, uint32_t idx,
                                          uint32_t x, uint32_t y0, uint32_t l, float (&gx)[VEC],
                                          float (&gy)[VEC], float (&gl)[VEC]) {
   float c[VEC], n[VEC];
   VecIO<VEC>::ld(u + idx, c);
   if (x < g.nx - 1) {
     VecIO<VEC>::ld(u + idx + g.ny, n);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) gx[j] = n[j] - c[j];
+  } else if (SLAB && g.halo.has_right) {
+    // slab edge: column x+1 lives on the right neighbour
+    VecIO<VEC>::ld(u_halo + y0 + l * g.ny, n);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) gx[j] = n[j] - c[j];
   } else {
@@ -99,13 +175,14 @@ __device__ __forceinline__ void grad_fwd(const GradGeom& g, const float* __restr
 }
 
 // (K^T p) at idx .. idx+VEC-1 : minus divergence (+ identity rows)
-template <int VEC, bool THREE_D, bool HAS_ID>
-__device__ __forceinline__ void grad_adj(const GradGeom& g, const float* __restrict__ p, uint32_t idx,
+template <int VEC, bool THREE_D, bool HAS_ID, bool SLAB>
+__device__ __forceinline__ void grad_adj(const GradGeom& g, const float* __restrict__ p,
+                                         const float* __restrict__ p_halo, uint32_t idx,
                                          uint32_t x, uint32_t y0, uint32_t l, float (&out)[VEC]) {
   const float* __restrict__ p1 = p;
   const float* __restrict__ p2 = p + g.plane;
   float a[VEC], divx[VEC], divy[VEC], o[VEC];
-  if (x < g.nx - 1) {
+  if (x < g.nx - 1 || (SLAB && g.halo.has_right)) {
     VecIO<VEC>::ld(p1 + idx, divx);
   } else {
 #pragma unroll
@@ -113,6 +190,11 @@ __device__ __forceinline__ void grad_adj(const GradGeom& g, const float* __restr
   }
   if (x > 0) {
     VecIO<VEC>::ld(p1 + idx - g.ny, a);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) divx[j] -= a[j];
+  } else if (SLAB && g.halo.has_left) {
+    // slab edge: column x-1 of the x-component lives on the left neighbour
+    VecIO<VEC>::ld(p_halo + y0 + l * g.ny, a);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) divx[j] -= a[j];
   }
@@ -157,17 +239,22 @@ __device__ __forceinline__ bool coeffs_scalar_except_b(const CoeffRef& c) {
 //              p.count = nx*ny, p.dim = L  (simplex over labels)
 //  TUNI: the preconditioner T is one scalar (always true for pure gradient operators), which lets
 //  the compiler hoist every step-size expression out of the per-lane code.
-template <int VEC, int CAPL, int KIND, int FN, bool THREE_D, bool HAS_ID, bool CHECK, bool TUNI>
-__device__ __forceinline__ void grad_primal_body(
+template <int VEC, int CAPL, int KIND, int FN, bool THREE_D, bool HAS_ID, bool CHECK, bool TUNI, bool SLAB>
+__device__ __forceinline__ bool grad_primal_body(
     const GradGeom& g, const ProxDesc& p, const float* __restrict__ x, const float* __restrict__ y,
     const float* __restrict__ y_prev, const ScaleRef& T, const float tau, const int kty_zero,
     const int ktyprev_zero, float* __restrict__ x_out, const uint32_t t, double& acc0, double& acc1) {
   uint32_t xl, yv, l0 = 0, xx;
   g.div_q.divmod(t, xl, yv);
-  if (CAPL == 1) g.div_nx.divmod(xl, l0, xx); else xx = xl;
+  // slab kernels put x slowest so that the edge column (x = 0) is the FIRST q*L threads of the grid:
+  // its halo goes out, and the neighbour is signalled, at the start of the pass
+  if (CAPL == 1) { if (SLAB) g.div_L.divmod(xl, xx, l0); else g.div_nx.divmod(xl, l0, xx); } else xx = xl;
   const uint32_t y0 = yv * VEC;
   const uint32_t pix = y0 + xx * g.ny;
   const uint32_t nl = CAPL == 1 ? 1u : g.L;
+  // slab edge towards the left neighbour: its y halo must have arrived before K^T y is gathered
+  const bool edge = SLAB && g.halo.has_left && xx == 0;
+  if (SLAB && edge && !(kty_zero && (!CHECK || ktyprev_zero))) halo_wait(g.halo);
 
   float arg[CAPL][VEC], td[CAPL][VEC];
 #pragma unroll
@@ -183,7 +270,7 @@ __device__ __forceinline__ void grad_primal_body(
 #pragma unroll
         for (int j = 0; j < VEC; ++j) k[j] = 0.f;
       } else {
-        grad_adj<VEC, THREE_D, HAS_ID>(g, y, idx, xx, y0, l, k);
+        grad_adj<VEC, THREE_D, HAS_ID, SLAB>(g, y, g.halo.in_a, idx, xx, y0, l, k);
       }
       if (!TUNI) VecIO<VEC>::ld(T.ptr + idx, td[li]);
 #pragma unroll
@@ -234,6 +321,7 @@ __device__ __forceinline__ void grad_primal_body(
       const uint32_t l = l0 + li;
       const uint32_t idx = pix + l * g.nxny;
       VecIO<VEC>::st(x_out + idx, arg[li]);
+      if (SLAB && edge) VecIO<VEC>::st(g.halo.out + y0 + l * g.ny, arg[li]);   // new column 0 -> left neighbour
       if (CHECK) {
         // dual residual (backend_pdhg.cu:73-94); operands are re-read (L1/L2 resident) rather
         // than kept live across the prox
@@ -243,13 +331,13 @@ __device__ __forceinline__ void grad_primal_body(
 #pragma unroll
           for (int j = 0; j < VEC; ++j) k[j] = 0.f;
         } else {
-          grad_adj<VEC, THREE_D, HAS_ID>(g, y, idx, xx, y0, l, k);
+          grad_adj<VEC, THREE_D, HAS_ID, SLAB>(g, y, g.halo.in_a, idx, xx, y0, l, k);
         }
         if (ktyprev_zero) {
 #pragma unroll
           for (int j = 0; j < VEC; ++j) kp[j] = 0.f;
         } else {
-          grad_adj<VEC, THREE_D, HAS_ID>(g, y_prev, idx, xx, y0, l, kp);
+          grad_adj<VEC, THREE_D, HAS_ID, SLAB>(g, y_prev, g.halo.in_b, idx, xx, y0, l, kp);
         }
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
@@ -262,9 +350,10 @@ __device__ __forceinline__ void grad_primal_body(
       }
     }
   }
+  return edge;
 }
 
-template <int VEC, int CAPL, int KIND, int FN, bool THREE_D, bool HAS_ID, bool CHECK>
+template <int VEC, int CAPL, int KIND, int FN, bool THREE_D, bool HAS_ID, bool CHECK, bool SLAB>
 __global__ void __launch_bounds__(kStencilBlock) grad_primal_kernel(
     const GradGeom g, const ProxDesc p, const float* __restrict__ x, const float* __restrict__ y,
     const float* __restrict__ y_prev, const ScaleRef T, const PdhgState* __restrict__ st,
@@ -273,14 +362,16 @@ __global__ void __launch_bounds__(kStencilBlock) grad_primal_kernel(
   double acc0 = 0.0, acc1 = 0.0;
   const uint32_t total = g.q * g.nx * (CAPL == 1 ? g.L : 1u);
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  bool edge = false;
   if (t < total) {
     if (T.ptr)
-      grad_primal_body<VEC, CAPL, KIND, FN, THREE_D, HAS_ID, CHECK, false>(
+      edge = grad_primal_body<VEC, CAPL, KIND, FN, THREE_D, HAS_ID, CHECK, false, SLAB>(
           g, p, x, y, y_prev, T, tau, kty_zero, ktyprev_zero, x_out, t, acc0, acc1);
     else
-      grad_primal_body<VEC, CAPL, KIND, FN, THREE_D, HAS_ID, CHECK, true>(
+      edge = grad_primal_body<VEC, CAPL, KIND, FN, THREE_D, HAS_ID, CHECK, true, SLAB>(
           g, p, x, y, y_prev, T, tau, kty_zero, ktyprev_zero, x_out, t, acc0, acc1);
   }
+  if (SLAB) halo_signal(g.halo, edge);
   if (CHECK) {
     block_sum2(acc0, acc1);
     if (threadIdx.x == 0) { partials[2 * blockIdx.x] = acc0; partials[2 * blockIdx.x + 1] = acc1; }
@@ -318,8 +409,8 @@ __device__ __forceinline__ void norm2_lanes(const int fn, float (&arg)[CAP][VEC]
 //              p.count = plane, p.dim = NCOMP
 //  CAPL  > 1 : thread = (y-vector, x);    group = NCOMP * L components of one pixel (L <= CAPL),
 //              p.count = nx*ny, p.dim = NCOMP * L, component i = c*L + l
-template <int VEC, int CAPL, int FN, bool THREE_D, bool CHECK, bool SUNI>
-__device__ __forceinline__ void grad_dual_body(
+template <int VEC, int CAPL, int FN, bool THREE_D, bool CHECK, bool SUNI, bool SLAB>
+__device__ __forceinline__ bool grad_dual_body(
     const GradGeom& g, const ProxDesc& p, const float* __restrict__ y, const float* __restrict__ xn,
     const float* __restrict__ xo, const ScaleRef& S, const float sigma, const float theta,
     const int kxprev_zero, float* __restrict__ y_out, const uint32_t t, double& acc0, double& acc1) {
@@ -327,10 +418,15 @@ __device__ __forceinline__ void grad_dual_body(
   constexpr int CAP = NCOMP * CAPL;
   uint32_t xl, yv, l0 = 0, xx;
   g.div_q.divmod(t, xl, yv);
-  if (CAPL == 1) g.div_nx.divmod(xl, l0, xx); else xx = xl;
+  // slab kernels walk x from the right so that the edge column (x = nx-1) is the first q*L threads
+  if (CAPL == 1) { if (SLAB) g.div_L.divmod(xl, xx, l0); else g.div_nx.divmod(xl, l0, xx); } else xx = xl;
+  if (SLAB) xx = g.nx - 1 - xx;
   const uint32_t y0 = yv * VEC;
   const uint32_t pix = y0 + xx * g.ny;
   const uint32_t nl = CAPL == 1 ? 1u : g.L;
+  // slab edge towards the right neighbour: its x halo must have arrived before K x is gathered
+  const bool edge = SLAB && g.halo.has_right && xx == g.nx - 1;
+  if (SLAB && edge) halo_wait(g.halo);
 
   // slot (c, li) -> c*CAPL + li ; unused label slots stay 0 (they do not change a 2-norm)
   float arg[CAP][VEC], td[SUNI ? 1 : CAP][VEC];
@@ -352,14 +448,14 @@ __device__ __forceinline__ void grad_dual_body(
       const uint32_t l = l0 + li;
       const uint32_t idx = pix + l * g.nxny;
       float k1[NCOMP][VEC], k0[NCOMP][VEC];
-      grad_fwd<VEC, THREE_D>(g, xn, idx, xx, y0, l, k1[0], k1[1], k1[NCOMP - 1]);
+      grad_fwd<VEC, THREE_D, SLAB>(g, xn, g.halo.in_a, idx, xx, y0, l, k1[0], k1[1], k1[NCOMP - 1]);
       if (kxprev_zero) {
 #pragma unroll
         for (int c = 0; c < NCOMP; ++c)
 #pragma unroll
           for (int j = 0; j < VEC; ++j) k0[c][j] = 0.f;
       } else {
-        grad_fwd<VEC, THREE_D>(g, xo, idx, xx, y0, l, k0[0], k0[1], k0[NCOMP - 1]);
+        grad_fwd<VEC, THREE_D, SLAB>(g, xo, g.halo.in_b, idx, xx, y0, l, k0[0], k0[1], k0[NCOMP - 1]);
       }
 #pragma unroll
       for (int c = 0; c < NCOMP; ++c) {
@@ -411,14 +507,14 @@ __device__ __forceinline__ void grad_dual_body(
       const uint32_t idx = pix + l * g.nxny;
       float k1[NCOMP][VEC], k0[NCOMP][VEC];
       if (CHECK) {
-        grad_fwd<VEC, THREE_D>(g, xn, idx, xx, y0, l, k1[0], k1[1], k1[NCOMP - 1]);
+        grad_fwd<VEC, THREE_D, SLAB>(g, xn, g.halo.in_a, idx, xx, y0, l, k1[0], k1[1], k1[NCOMP - 1]);
         if (kxprev_zero) {
 #pragma unroll
           for (int c = 0; c < NCOMP; ++c)
 #pragma unroll
             for (int j = 0; j < VEC; ++j) k0[c][j] = 0.f;
         } else {
-          grad_fwd<VEC, THREE_D>(g, xo, idx, xx, y0, l, k0[0], k0[1], k0[NCOMP - 1]);
+          grad_fwd<VEC, THREE_D, SLAB>(g, xo, g.halo.in_b, idx, xx, y0, l, k0[0], k0[1], k0[NCOMP - 1]);
         }
       }
 #pragma unroll
@@ -426,6 +522,7 @@ __device__ __forceinline__ void grad_dual_body(
         const uint32_t e = c * g.plane + idx;
         const int s = c * CAPL + li;
         VecIO<VEC>::st(y_out + e, arg[s]);
+        if (SLAB && c == 0 && edge) VecIO<VEC>::st(g.halo.out + y0 + l * g.ny, arg[s]);  // last gx column -> right
         if (CHECK) {
           // primal residual (backend_pdhg.cu:97-120)
           float yo[VEC];
@@ -443,9 +540,10 @@ __device__ __forceinline__ void grad_dual_body(
       }
     }
   }
+  return edge;
 }
 
-template <int VEC, int CAPL, int FN, bool THREE_D, bool CHECK>
+template <int VEC, int CAPL, int FN, bool THREE_D, bool CHECK, bool SLAB>
 __global__ void __launch_bounds__(kStencilBlock) grad_dual_norm2_kernel(
     const GradGeom g, const ProxDesc p, const float* __restrict__ y, const float* __restrict__ xn,
     const float* __restrict__ xo, const ScaleRef S, const PdhgState* __restrict__ st, const int kxprev_zero,
@@ -454,14 +552,16 @@ __global__ void __launch_bounds__(kStencilBlock) grad_dual_norm2_kernel(
   double acc0 = 0.0, acc1 = 0.0;
   const uint32_t total = g.q * g.nx * (CAPL == 1 ? g.L : 1u);
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  bool edge = false;
   if (t < total) {
     if (S.ptr)
-      grad_dual_body<VEC, CAPL, FN, THREE_D, CHECK, false>(g, p, y, xn, xo, S, sigma, theta, kxprev_zero,
-                                                           y_out, t, acc0, acc1);
+      edge = grad_dual_body<VEC, CAPL, FN, THREE_D, CHECK, false, SLAB>(g, p, y, xn, xo, S, sigma, theta,
+                                                                        kxprev_zero, y_out, t, acc0, acc1);
     else
-      grad_dual_body<VEC, CAPL, FN, THREE_D, CHECK, true>(g, p, y, xn, xo, S, sigma, theta, kxprev_zero,
-                                                          y_out, t, acc0, acc1);
+      edge = grad_dual_body<VEC, CAPL, FN, THREE_D, CHECK, true, SLAB>(g, p, y, xn, xo, S, sigma, theta,
+                                                                       kxprev_zero, y_out, t, acc0, acc1);
   }
+  if (SLAB) halo_signal(g.halo, edge);
   if (CHECK) {
     block_sum2(acc0, acc1);
     if (threadIdx.x == 0) { partials[2 * blockIdx.x] = acc0; partials[2 * blockIdx.x + 1] = acc1; }
