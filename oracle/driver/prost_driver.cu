@@ -27,6 +27,8 @@
 //   scaling alpha <a> | identity | custom <left.f32> <right.f32>
 //   pdhg <tau0> <sigma0> <residual_iter> <scale_steps_operator> <alg2_gamma> <arg_alpha0> <arg_nu>
 //        <arg_delta> <arb_delta> <arb_tau> <variant 1..4>
+//   admm <rho0> <alpha> <cg_tol_pow> <cg_tol_min> <cg_tol_max> <cg_max_iter> <residual_iter> <arb_delta>
+//        <arb_tau> <arb_gamma>                                  (selects BackendADMM instead of BackendPDHG)
 //   solver <tol_rel_p> <tol_rel_d> <tol_abs_p> <tol_abs_d> <max_iters> <num_cback> <x0|-> <y0|-> <solve_dual>
 //   action solve | linop <in.f32> <transpose> | prox <arg.f32> <taudiag.f32> <tau>
 //   out <prefix>
@@ -42,6 +44,7 @@
 #include <string>
 #include <vector>
 
+#include "prost/backend/backend_admm.hpp"
 #include "prost/backend/backend_pdhg.hpp"
 #include "prost/exception.hpp"
 #include "prost/linop/block_dense.hpp"
@@ -230,6 +233,10 @@ int main(int argc, char** argv) {
     po.tau0 = 1; po.sigma0 = 1; po.residual_iter = 1; po.scale_steps_operator = false; po.alg2_gamma = 0;
     po.arg_alpha0 = 0.5f; po.arg_nu = 0.95f; po.arg_delta = 1.5f; po.arb_delta = 1.05f; po.arb_tau = 0.8f;
     po.stepsize_variant = BackendPDHG<real>::kPDHGStepsResidualBoyd;
+    BackendADMM<real>::Options ao;                        // matlab/+prost/+backend/admm.m:3-13
+    ao.rho0 = 1; ao.alpha = 1.7; ao.cg_tol_pow = 1.3; ao.cg_tol_min = 1e-5; ao.cg_tol_max = 1e-8; ao.cg_max_iter = 10;
+    ao.residual_iter = 1; ao.arb_delta = 1.05f; ao.arb_tau = 0.8f; ao.arb_gamma = 1.01f;
+    bool use_admm = false;
     Solver<real>::Options so;
     so.tol_rel_primal = so.tol_rel_dual = so.tol_abs_primal = so.tol_abs_dual = 1e-4f;
     so.max_iters = 100; so.num_cback_calls = 0; so.verbose = false; so.solve_dual_problem = false;
@@ -265,6 +272,11 @@ int main(int argc, char** argv) {
             po.arg_delta >> po.arb_delta >> po.arb_tau >> variant;
         po.scale_steps_operator = sso != 0;
         po.stepsize_variant = static_cast<BackendPDHG<real>::StepsizeVariant>(variant);
+      }
+      else if (key == "admm") {
+        in >> ao.rho0 >> ao.alpha >> ao.cg_tol_pow >> ao.cg_tol_min >> ao.cg_tol_max >> ao.cg_max_iter >>
+            ao.residual_iter >> ao.arb_delta >> ao.arb_tau >> ao.arb_gamma;
+        use_admm = true;
       }
       else if (key == "solver") {
         std::string fx, fy;
@@ -304,7 +316,9 @@ int main(int argc, char** argv) {
       write_file(out + "_res.f32", res);
       info << "n " << n << "\nms " << ms << "\n";
     } else {
-      std::shared_ptr<BackendPDHG<real>> backend(new BackendPDHG<real>(po));
+      std::shared_ptr<Backend<real>> backend;
+      if (use_admm) backend = std::shared_ptr<Backend<real>>(new BackendADMM<real>(ao));
+      else backend = std::shared_ptr<Backend<real>>(new BackendPDHG<real>(po));
       Solver<real> solver(problem, backend);
       solver.SetOptions(so);
       int iterations = 0;                // the stopping callback runs once per iteration (solver.cu:147)

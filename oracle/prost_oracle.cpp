@@ -1,6 +1,6 @@
 // oracle/prost_oracle.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 //
-// CPU restatement (C++/OpenMP) of the reference's PDHG hot path, used ONLY as the checker in
+// CPU restatement (C++/OpenMP) of the reference's PDHG / ADMM hot path, used ONLY as the checker in
 // tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.  The
 // product (prost_b200/) never links, imports or calls anything in this directory.
 //
@@ -16,6 +16,7 @@
 //               include/prost/prox/vector.hpp:42-48, prox_elem_operation.inl:32-94
 //   problem     src/problem.cu:92-158 (zero fill), :262-306 (scaling), :502-536 (averaging)
 //   PDHG        src/backend/backend_pdhg.cu:38-186, 199-309, 311-489, 513-563; backend.hpp:71-74
+//   ADMM        src/backend/backend_admm.cu:52-272, 285-665, 697-741; include/prost/cgls.hpp:222-371
 // Parity pinning: against outputs of the reference itself (oracle/_ref, run on the GPU box) stored
 // under tests/golden/, and against the closed forms of the reference's MATLAB tests
 // (matlab/+prost/+test/*.m) restated in numpy inside tests/.
@@ -26,6 +27,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <memory>
 #include <string>
 #include <tuple>
@@ -700,6 +702,203 @@ struct Pdhg {
   }
 };
 
+// ------------------------------------------------------------------------------------------------
+// ADMM (graph projection splitting) + CGLS: src/backend/backend_admm.cu:52-272, 285-665,
+// include/prost/cgls.hpp:222-371.  Statement by statement, same temporaries and aliases.
+// ------------------------------------------------------------------------------------------------
+struct Admm {
+  Problem* P;
+  // options (backend_admm.hpp:38-63)
+  double rho0, alpha, cg_tol_pow, cg_tol_min, cg_tol_max; int cg_max_iter, residual_iter;
+  float arb_delta, arb_tau, arb_gamma;
+  float tol_rel_p, tol_rel_d, tol_abs_p, tol_abs_d;
+  // state (backend_admm.hpp:83-99)
+  vec x_half, z_half, x_proj, z_proj, x_dual, z_dual, temp1, temp2, temp3;
+  float rho, delta; int arb_u, arb_l; size_t iteration;
+  float primal_residual = 0, dual_residual = 0, primal_var_norm = 0, dual_var_norm = 0;
+  std::vector<std::shared_ptr<Prox>> prox_g, prox_f;
+  int last_cg_iters = 0;
+  long total_cg_iters = 0;
+
+  float eps_primal() const { return std::sqrt(P->nrows) * tol_abs_p + tol_rel_p * primal_var_norm; }   // backend.hpp:71
+  float eps_dual() const { return std::sqrt(P->ncols) * tol_abs_d + tol_rel_d * dual_var_norm; }       // backend.hpp:74
+
+  int init() {                                              // Initialize :285-352
+    const size_t m = P->nrows, n = P->ncols;
+    x_half.assign(n, 0); x_proj.assign(n, 0); x_dual.assign(n, 0);
+    z_half.assign(m, 0); z_proj.assign(m, 0); z_dual.assign(m, 0);
+    temp1.assign(n, 0); temp2.assign(m, 0); temp3.assign(std::max(m, n), 0);
+    prox_g.clear(); prox_f.clear();
+    if (P->prox[0].empty()) { if (P->prox[2].empty()) { g_err = "Neither prox_g nor prox_gstar specified."; return -1; }
+      for (auto& p : P->prox[2]) prox_g.push_back(std::make_shared<ProxMoreau>(p)); } else prox_g = P->prox[0];
+    if (P->prox[1].empty()) { if (P->prox[3].empty()) { g_err = "Neither prox_f nor prox_fstar specified."; return -1; }
+      for (auto& p : P->prox[3]) prox_f.push_back(std::make_shared<ProxMoreau>(p)); } else prox_f = P->prox[1];
+    delta = arb_delta; rho = rho0; iteration = 0; arb_u = arb_l = 0;
+    return 0;
+  }
+
+  // linearoperator.cu:134-170 with a general beta
+  void linop(float* res, const float* rhs, float beta, bool transpose) const {
+    const size_t nout = transpose ? P->ncols : P->nrows;
+    if (beta == 0) std::fill(res, res + nout, 0.f);
+    else if (beta != 1) for (size_t i = 0; i < nout; ++i) res[i] = beta * res[i];
+    for (auto& b : P->blocks) {
+      if (transpose) b->eval_adj_add(res + b->col, rhs + b->row);
+      else b->eval_add(res + b->row, rhs + b->col);
+    }
+  }
+
+  // GemvPrecondK::operator() :198-272: y := alpha op(Sigma^{1/2} K Tau^{1/2}) x + beta y
+  void gemv(char op, float al, const vec& x, float be, vec& y) {
+    const size_t m = P->nrows, n = P->ncols;
+    const float* T = P->right.data();
+    const float* S = P->left.data();
+    if (op == 'n') {
+      for (size_t i = 0; i < n; ++i) temp3[i] = std::sqrt(T[i]) * x[i];                       // gemv_functor1
+      for (size_t i = 0; i < m; ++i) y[i] = (be / (al * std::sqrt(S[i]))) * y[i];             // gemv_functor2
+      linop(y.data(), temp3.data(), 1, false);
+      for (size_t i = 0; i < m; ++i) y[i] = al * std::sqrt(S[i]) * y[i];                      // gemv_functor3
+    } else {
+      for (size_t i = 0; i < m; ++i) temp3[i] = std::sqrt(S[i]) * x[i];
+      for (size_t i = 0; i < n; ++i) y[i] = (be / (al * std::sqrt(T[i]))) * y[i];
+      linop(y.data(), temp3.data(), 1, true);
+      for (size_t i = 0; i < n; ++i) y[i] = al * std::sqrt(T[i]) * y[i];
+    }
+  }
+
+  static double nrm2d(const vec& v, size_t n) {             // cgls.hpp:166-189 (double accumulation)
+    double s = 0;
+    for (size_t i = 0; i < n; ++i) s += static_cast<double>(v[i]) * static_cast<double>(v[i]);
+    return std::sqrt(s);
+  }
+  static float nrm2f(const vec& v, size_t n) {              // backend_admm.cu:46-50 (cublasSnrm2 -> float)
+    double s = 0;
+    for (size_t i = 0; i < n; ++i) s += static_cast<double>(v[i]) * static_cast<double>(v[i]);
+    return static_cast<float>(std::sqrt(s));
+  }
+
+  // cgls::Solve :222-371 with shift = 1 on the preconditioned operator
+  int cgls(const vec& b, vec& x, double shift, double tol, int maxit, vec& p, vec& q, vec& r, vec& s, int& iterations) {
+    const size_t m = P->nrows, n = P->ncols;
+    double gamma, normp, normq, norms, norms0, normx, xmax;
+    int k = 0, flag = 0, indefinite = 0;
+    const float kNegOne = -1.f, kZero = 0.f, kOne = 1.f, kNegShift = static_cast<float>(-shift);
+    const double kEps = std::numeric_limits<float>::epsilon();
+    std::copy(b.begin(), b.begin() + m, r.begin());
+    std::copy(x.begin(), x.begin() + n, s.begin());
+    normx = nrm2d(x, n);
+    if (normx > 0.) gemv('n', kNegOne, x, kOne, r);
+    gemv('t', kOne, r, kNegShift, s);
+    std::copy(s.begin(), s.begin() + n, p.begin());
+    norms = nrm2d(s, n);
+    norms0 = norms;
+    gamma = norms0 * norms0;
+    normx = nrm2d(x, n);
+    xmax = normx;
+    if (norms < kEps) flag = 1;
+    for (k = 0; k < maxit && !flag; ++k) {
+      gemv('n', kOne, p, kZero, q);
+      normp = nrm2d(p, n);
+      normq = nrm2d(q, m);
+      double delta_ = normq * normq + shift * normp * normp;
+      if (delta_ <= 0.) indefinite = 1;
+      if (delta_ == 0.) delta_ = kEps;
+      const float al = static_cast<float>(gamma / delta_);
+      const float neg_al = static_cast<float>(-gamma / delta_);
+      for (size_t i = 0; i < n; ++i) x[i] = al * p[i] + x[i];          // cublasSaxpy
+      for (size_t i = 0; i < m; ++i) r[i] = neg_al * q[i] + r[i];
+      std::copy(x.begin(), x.begin() + n, s.begin());
+      gemv('t', kOne, r, kNegShift, s);
+      norms = nrm2d(s, n);
+      const double gamma1 = gamma;
+      gamma = norms * norms;
+      const float be = static_cast<float>(gamma / gamma1);
+      for (size_t i = 0; i < n; ++i) s[i] = be * p[i] + s[i];
+      std::copy(s.begin(), s.begin() + n, p.begin());
+      normx = nrm2d(x, n);
+      xmax = std::max(xmax, normx);
+      const bool converged = (norms <= norms0 * tol) || (normx * tol >= 1.);
+      if (converged) break;
+    }
+    const double shrink = normx / xmax;
+    if (k == maxit) flag = 2;
+    else if (indefinite) flag = 3;
+    else if (shrink * shrink <= tol) flag = 4;
+    iterations = k;
+    return flag;
+  }
+
+  void iterate() {                                          // PerformIteration :354-665
+    const size_t m = P->nrows, n = P->ncols;
+    const float* T = P->right.data();
+    const float* S = P->left.data();
+    const float al = static_cast<float>(alpha);
+    for (size_t i = 0; i < n; ++i)                          // temp1_functor :52-66
+      temp1[i] = (al * x_half[i] + (1 - al) * x_proj[i] + x_dual[i]) / std::sqrt(T[i]);
+    for (size_t i = 0; i < m; ++i)                          // temp2_functor :68-79
+      temp2[i] = std::sqrt(S[i]) * (z_half[i] + z_dual[i]);
+    std::copy(temp2.begin(), temp2.end(), z_dual.begin());  // :394-395, tmp_proj_arg aliases z_dual
+    vec& tmp_proj_arg = z_dual;
+    std::copy(temp3.begin(), temp3.begin() + n, x_proj.begin());   // warm start :398
+    gemv('n', -1, temp1, 1, tmp_proj_arg);                  // :401
+    double cg_tol = cg_tol_min / std::pow(static_cast<float>(iteration + 1), cg_tol_pow);   // :403-405
+    cg_tol = std::max(cg_tol, cg_tol_max);
+    vec& tmp_p = x_half; vec& tmp_q = z_half; vec& tmp_r = z_proj; vec& tmp_s = x_dual;     // :411-414
+    cgls(tmp_proj_arg, x_proj, 1, cg_tol, cg_max_iter, tmp_p, tmp_q, tmp_r, tmp_s, last_cg_iters);
+    total_cg_iters += last_cg_iters;
+    std::copy(x_proj.begin(), x_proj.end(), temp3.begin()); // :439
+    for (size_t i = 0; i < n; ++i) x_proj[i] = std::sqrt(T[i]) * (x_proj[i] + temp1[i]);    // x_proj_functor
+    linop(z_proj.data(), x_proj.data(), 0, false);          // :456
+    for (size_t i = 0; i < n; ++i) x_dual[i] = temp1[i] * std::sqrt(T[i]) - x_proj[i];      // x_dual_functor
+    for (size_t i = 0; i < m; ++i) z_dual[i] = temp2[i] / std::sqrt(S[i]) - z_proj[i];      // z_dual_functor
+    for (size_t i = 0; i < n; ++i) temp1[i] = x_proj[i] - x_dual[i];
+    for (auto& p : prox_g) p->eval(x_half.data(), temp1.data(), T, 1 / rho, false);         // :505-506
+    for (size_t i = 0; i < m; ++i) temp2[i] = z_proj[i] - z_dual[i];
+    for (auto& p : prox_f) p->eval(z_half.data(), temp2.data(), S, rho, true);              // :522-523
+    iteration++;
+
+    if (iteration == 0 || (iteration % (size_t)(long long)residual_iter) == 0) {            // :529
+      std::copy(z_half.begin(), z_half.end(), temp2.begin());
+      linop(temp2.data(), x_half.data(), -1, false);        // temp2 = K x_half - z_half
+      for (size_t i = 0; i < m; ++i) temp2[i] = std::sqrt(S[i]) * temp2[i];
+      primal_residual = nrm2f(temp2, m);
+      for (size_t i = 0; i < m; ++i) temp2[i] = std::sqrt(S[i]) * z_half[i];
+      primal_var_norm = nrm2f(temp2, m);
+      for (size_t i = 0; i < n; ++i)                        // get_dual_functor(rho, -1) :184-196
+        temp1[i] = -rho * std::pow(T[i], -1.f) * (x_half[i] - x_proj[i] + x_dual[i]);
+      {
+        vec tw(n);                                          // the reference writes these n values into temp2_ (needs m >= n)
+        for (size_t i = 0; i < n; ++i) tw[i] = std::sqrt(T[i]) * temp1[i];
+        dual_var_norm = nrm2f(tw, n);
+      }
+      for (size_t i = 0; i < m; ++i)                        // get_dual_functor(rho, 1)
+        temp2[i] = -rho * std::pow(S[i], 1.f) * (z_half[i] - z_proj[i] + z_dual[i]);
+      linop(temp1.data(), temp2.data(), 1, true);           // w + K^T y
+      for (size_t i = 0; i < n; ++i) temp1[i] = std::sqrt(T[i]) * temp1[i];
+      dual_residual = nrm2f(temp1, n);
+      const float eps_p = eps_primal(), eps_d = eps_dual();
+      const float rho_prev = rho;
+      if ((dual_residual < eps_d) && (arb_tau * iteration > arb_l)) { rho *= delta; delta *= arb_gamma; arb_u = iteration; }
+      else if ((primal_residual < eps_p) && (arb_tau * iteration > arb_u)) { rho /= delta; delta *= arb_gamma; arb_l = iteration; }
+      if (std::abs(rho - rho_prev) > 1e-7) {                // :646-659
+        const float f = rho_prev / rho;
+        for (size_t i = 0; i < n; ++i) x_dual[i] = f * x_dual[i];
+        for (size_t i = 0; i < m; ++i) z_dual[i] = f * z_dual[i];
+      }
+    }
+  }
+
+  void solution(float* hx, float* hz, float* hy, float* hw) {   // current_solution :697-741
+    const size_t m = P->nrows, n = P->ncols;
+    const float* T = P->right.data();
+    const float* S = P->left.data();
+    if (hw) for (size_t i = 0; i < n; ++i) hw[i] = -rho * std::pow(T[i], -1.f) * (x_half[i] - x_proj[i] + x_dual[i]);
+    if (hy) for (size_t i = 0; i < m; ++i) hy[i] = -rho * std::pow(S[i], 1.f) * (z_half[i] - z_proj[i] + z_dual[i]);
+    if (hx) std::copy(x_half.begin(), x_half.end(), hx);
+    if (hz) std::copy(z_half.begin(), z_half.end(), hz);
+  }
+};
+
 }  // namespace orc
 
 // ------------------------------------------------------------------------------------------------
@@ -815,5 +1014,27 @@ void orc_pdhg_residuals(void* s, float* out) {
 }
 void orc_pdhg_stepsizes(void* s, double* out) { out[0] = SS->tau; out[1] = SS->sigma; out[2] = SS->theta; }
 void orc_pdhg_solution(void* s, float* x, float* z, float* y, float* w) { SS->solution(x, z, y, w); }
+
+void* orc_admm_new(void* p, double rho0, double alpha, double cg_tol_pow, double cg_tol_min, double cg_tol_max,
+                   int cg_max_iter, int residual_iter, float arb_delta, float arb_tau, float arb_gamma,
+                   float tol_rel_p, float tol_rel_d, float tol_abs_p, float tol_abs_d) {
+  Admm* s = new Admm();
+  s->P = PP;
+  s->rho0 = rho0; s->alpha = alpha; s->cg_tol_pow = cg_tol_pow; s->cg_tol_min = cg_tol_min; s->cg_tol_max = cg_tol_max;
+  s->cg_max_iter = cg_max_iter; s->residual_iter = residual_iter; s->arb_delta = arb_delta; s->arb_tau = arb_tau;
+  s->arb_gamma = arb_gamma;
+  s->tol_rel_p = tol_rel_p; s->tol_rel_d = tol_rel_d; s->tol_abs_p = tol_abs_p; s->tol_abs_d = tol_abs_d;
+  return s;
+}
+#define AA static_cast<Admm*>(s)
+void orc_admm_free(void* s) { delete AA; }
+int orc_admm_init(void* s) { return AA->init(); }
+void orc_admm_iterate(void* s, int n) { for (int i = 0; i < n; ++i) AA->iterate(); }
+void orc_admm_residuals(void* s, float* out) {
+  out[0] = AA->primal_residual; out[1] = AA->dual_residual; out[2] = AA->primal_var_norm; out[3] = AA->dual_var_norm;
+  out[4] = AA->eps_primal(); out[5] = AA->eps_dual();
+}
+void orc_admm_stepsizes(void* s, double* out) { out[0] = AA->rho; out[1] = AA->delta; out[2] = (double)AA->total_cg_iters; }
+void orc_admm_solution(void* s, float* x, float* z, float* y, float* w) { AA->solution(x, z, y, w); }
 
 }  // extern "C"

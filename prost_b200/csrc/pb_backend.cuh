@@ -103,6 +103,12 @@ class Backend {
   virtual void device_iterates(float** d_x, float** d_y) = 0;
   // iterations between two residual refreshes (for the solver loop's chunking)
   virtual int residual_iter() const = 0;
+  // does the iteration that starts with iteration() == it_before refresh the residuals?  PDHG checks
+  // before iteration_++ (backend_pdhg.cu:389, size_t % int), ADMM after it (backend_admm.cu:525-529).
+  virtual bool refreshes_on(size_t it_before) const {
+    const unsigned long long mod = static_cast<unsigned long long>(static_cast<long long>(residual_iter()));
+    return it_before == 0 || (it_before % mod) == 0;
+  }
   // slab decomposition (pb_comm.cuh); must be called before initialize()
   virtual void set_slab(class Comm*) { fail(PB_ERR_UNSUPPORTED, "this backend has no slab decomposition"); }
 

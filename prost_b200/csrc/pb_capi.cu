@@ -565,15 +565,13 @@ int pb_solver_solve(pb_backend* b, const pb_solver_options* so, pb_stopping_cb s
     int result = PB_STOPPED_MAX_ITERS;
     int iters = 0;
     float res[6] = {0, 0, 0, 0, 0, 0};
-    const unsigned long long mod =
-        static_cast<unsigned long long>(static_cast<long long>(be->residual_iter()));
     for (int i = 0; i < so->max_iters; ++i) {
       const size_t it_before = be->iteration();
       be->iterate(1);
       iters = i + 1;
       // residuals only change on refresh iterations; everything in between reuses the cached
       // values exactly like Solver::Solve does, without synchronising the stream
-      if (it_before == 0 || (it_before % mod) == 0) be->residuals(res);
+      if (be->refreshes_on(it_before)) be->residuals(res);
       const bool is_stopped = stop ? stop(user) != 0 : false;
       bool is_converged = (res[0] < res[4]) && (res[1] < res[5]);
 

@@ -47,6 +47,10 @@ struct Context {
   bool owns_stream = false;
   int num_sms = kNumSMs;
   unsigned long long launches = 0;    // kernels launched through this context
+  // Optional device flag observed by every operator-apply kernel: while *skip_flag != 0 the
+  // kernels return without touching memory.  Lets a device-resident loop (the CGLS projection of
+  // BackendADMM, pb_admm.cu) stop early without a host round trip per inner iteration.
+  const int* skip_flag = nullptr;
 
   void bind() const { PB_CUDA(cudaSetDevice(device)); }
 };

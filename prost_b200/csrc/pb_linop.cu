@@ -15,7 +15,8 @@ namespace pb {
 template <bool kTranspose>
 __global__ void __launch_bounds__(kBlock) block_apply_add_kernel(BlockDesc b, float* __restrict__ res,
                                                                   const float* __restrict__ rhs,
-                                                                  float sign) {
+                                                                  float sign, const int* __restrict__ skip) {
+  if (skip && *skip) return;
   const uint32_t n = kTranspose ? b.ncols : b.nrows;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float v = kTranspose ? block_col_dot(b, i, rhs) : block_row_dot(b, i, rhs);
@@ -23,7 +24,9 @@ __global__ void __launch_bounds__(kBlock) block_apply_add_kernel(BlockDesc b, fl
   }
 }
 
-__global__ void __launch_bounds__(kBlock) scale_kernel(float* __restrict__ v, size_t n, float beta) {
+__global__ void __launch_bounds__(kBlock) scale_kernel(float* __restrict__ v, size_t n, float beta,
+                                                       const int* __restrict__ skip) {
+  if (skip && *skip) return;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
        i += (size_t)gridDim.x * blockDim.x)
     v[i] = beta * v[i];
@@ -35,7 +38,9 @@ __global__ void __launch_bounds__(kBlock) csr_spmv_add_kernel(const int* __restr
                                                                const int* __restrict__ ind,
                                                                const float* __restrict__ val,
                                                                uint32_t nrows, float* __restrict__ res,
-                                                               const float* __restrict__ x, float sign) {
+                                                               const float* __restrict__ x, float sign,
+                                                               const int* __restrict__ skip) {
+  if (skip && *skip) return;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warps_per_grid = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < nrows; r += warps_per_grid) {
@@ -52,7 +57,9 @@ __global__ void __launch_bounds__(kBlock) csr_spmv_add_kernel(const int* __restr
 template <int kGroup>
 __global__ void __launch_bounds__(kBlock) csr_spmv_add_group_kernel(
     const int* __restrict__ ptr, const int* __restrict__ ind, const float* __restrict__ val,
-    uint32_t nrows, float* __restrict__ res, const float* __restrict__ x, float sign) {
+    uint32_t nrows, float* __restrict__ res, const float* __restrict__ x, float sign,
+    const int* __restrict__ skip) {
+  if (skip && *skip) return;
   const uint32_t sub = threadIdx.x % kGroup;
   const uint32_t groups_per_grid = (gridDim.x * blockDim.x) / kGroup;
   // all lanes of a warp iterate the same number of times so the shuffles stay converged
@@ -77,7 +84,9 @@ __global__ void __launch_bounds__(kBlock) csr_spmv_add_group_kernel(
 __global__ void __launch_bounds__(kBlock) dense_gemv_n_kernel(const float* __restrict__ A, uint32_t M,
                                                                uint32_t N, uint32_t cols_per_split,
                                                                const float* __restrict__ x,
-                                                               float* __restrict__ part) {
+                                                               float* __restrict__ part,
+                                                               const int* __restrict__ skip) {
+  if (skip && *skip) return;
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= M) return;
   const uint32_t c0 = blockIdx.y * cols_per_split;
@@ -96,7 +105,8 @@ __global__ void __launch_bounds__(kBlock) dense_gemv_n_kernel(const float* __res
 
 __global__ void __launch_bounds__(kBlock) dense_fold_kernel(const float* __restrict__ part, uint32_t M,
                                                              uint32_t splits, float* __restrict__ res,
-                                                             float sign) {
+                                                             float sign, const int* __restrict__ skip) {
+  if (skip && *skip) return;
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= M) return;
   float acc = 0.f;
@@ -107,7 +117,9 @@ __global__ void __launch_bounds__(kBlock) dense_fold_kernel(const float* __restr
 // Dense y += A^T x: one warp per column (contiguous in memory), shuffle-reduce.
 __global__ void __launch_bounds__(kBlock) dense_gemv_t_kernel(const float* __restrict__ A, uint32_t M,
                                                                uint32_t N, const float* __restrict__ x,
-                                                               float* __restrict__ res, float sign) {
+                                                               float* __restrict__ res, float sign,
+                                                               const int* __restrict__ skip) {
+  if (skip && *skip) return;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warps_per_grid = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < N; c += warps_per_grid) {
@@ -149,9 +161,9 @@ static void launch_generic_add(Context* ctx, const BlockDesc& d, bool transpose,
   if (n == 0) return;
   const unsigned grid = std::min<size_t>(grid_for(n), (size_t)ctx->num_sms * 32);
   if (transpose)
-    block_apply_add_kernel<true><<<grid, kBlock, 0, ctx->stream>>>(d, res, rhs, sign);
+    block_apply_add_kernel<true><<<grid, kBlock, 0, ctx->stream>>>(d, res, rhs, sign, ctx->skip_flag);
   else
-    block_apply_add_kernel<false><<<grid, kBlock, 0, ctx->stream>>>(d, res, rhs, sign);
+    block_apply_add_kernel<false><<<grid, kBlock, 0, ctx->stream>>>(d, res, rhs, sign, ctx->skip_flag);
   PB_CHECK_LAUNCH();
   ctx->launches++;
 }
@@ -331,15 +343,15 @@ class BlockSparse : public Block {
     if (avg <= 6.0) {
       const unsigned grid = std::min<size_t>(grid_for(rows * 4), cap);
       csr_spmv_add_group_kernel<4><<<grid, kBlock, 0, ctx_->stream>>>(ptr.data(), ind.data(), val.data(),
-                                                                      (uint32_t)rows, res, x, 1.f);
+                                                                      (uint32_t)rows, res, x, 1.f, ctx_->skip_flag);
     } else if (avg <= 24.0) {
       const unsigned grid = std::min<size_t>(grid_for(rows * 8), cap);
       csr_spmv_add_group_kernel<8><<<grid, kBlock, 0, ctx_->stream>>>(ptr.data(), ind.data(), val.data(),
-                                                                      (uint32_t)rows, res, x, 1.f);
+                                                                      (uint32_t)rows, res, x, 1.f, ctx_->skip_flag);
     } else {
       const unsigned grid = std::min<size_t>(grid_for(rows * 32), cap);
       csr_spmv_add_kernel<<<grid, kBlock, 0, ctx_->stream>>>(ptr.data(), ind.data(), val.data(),
-                                                             (uint32_t)rows, res, x, 1.f);
+                                                             (uint32_t)rows, res, x, 1.f, ctx_->skip_flag);
     }
     PB_CHECK_LAUNCH();
     ctx_->launches++;
@@ -399,10 +411,10 @@ class BlockDense : public Block {
     dim3 grid(grid_for(nrows_), splits_);
     dense_gemv_n_kernel<<<grid, kBlock, 0, ctx_->stream>>>(d_data_.data(), (uint32_t)nrows_,
                                                            (uint32_t)ncols_, cols_per_split_, rhs,
-                                                           d_part_.data());
+                                                           d_part_.data(), ctx_->skip_flag);
     PB_CHECK_LAUNCH();
     dense_fold_kernel<<<grid_for(nrows_), kBlock, 0, ctx_->stream>>>(d_part_.data(), (uint32_t)nrows_,
-                                                                     splits_, res, 1.f);
+                                                                     splits_, res, 1.f, ctx_->skip_flag);
     PB_CHECK_LAUNCH();
     ctx_->launches += 2;
   }
@@ -410,7 +422,7 @@ class BlockDense : public Block {
     if (nrows_ == 0 || ncols_ == 0) return;
     const unsigned grid = std::min<size_t>(grid_for(ncols_ * 32), (size_t)ctx_->num_sms * 16);
     dense_gemv_t_kernel<<<grid, kBlock, 0, ctx_->stream>>>(d_data_.data(), (uint32_t)nrows_,
-                                                           (uint32_t)ncols_, rhs, res, 1.f);
+                                                           (uint32_t)ncols_, rhs, res, 1.f, ctx_->skip_flag);
     PB_CHECK_LAUNCH();
     ctx_->launches++;
   }
@@ -492,7 +504,7 @@ void LinearOperator::eval(float* d_result, const float* d_rhs, float beta, bool 
     PB_CUDA(cudaMemsetAsync(d_result, 0, nout * sizeof(float), ctx_->stream));
   } else if (beta != 1.f) {
     const unsigned grid = std::min<size_t>(grid_for(nout), (size_t)ctx_->num_sms * 32);
-    scale_kernel<<<grid, kBlock, 0, ctx_->stream>>>(d_result, nout, beta);
+    scale_kernel<<<grid, kBlock, 0, ctx_->stream>>>(d_result, nout, beta, ctx_->skip_flag);
     PB_CHECK_LAUNCH();
     ctx_->launches++;
   }
@@ -508,7 +520,7 @@ void LinearOperator::eval(float* d_result, const float* d_rhs, float beta, bool 
     // as  result <- -( -beta*result + K^T rhs ).  Only used when solve_dual_problem is set.
     const unsigned grid = std::min<size_t>(grid_for(nout), (size_t)ctx_->num_sms * 32);
     if (beta != 0.f) {
-      scale_kernel<<<grid, kBlock, 0, ctx_->stream>>>(d_result, nout, -1.f);
+      scale_kernel<<<grid, kBlock, 0, ctx_->stream>>>(d_result, nout, -1.f, ctx_->skip_flag);
       PB_CHECK_LAUNCH();
       ctx_->launches++;
     }
@@ -518,7 +530,7 @@ void LinearOperator::eval(float* d_result, const float* d_rhs, float beta, bool 
       else
         b->eval_local_add(d_result + b->row(), d_rhs + b->col());
     }
-    scale_kernel<<<grid, kBlock, 0, ctx_->stream>>>(d_result, nout, -1.f);
+    scale_kernel<<<grid, kBlock, 0, ctx_->stream>>>(d_result, nout, -1.f, ctx_->skip_flag);
     PB_CHECK_LAUNCH();
     ctx_->launches++;
   }

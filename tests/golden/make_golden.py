@@ -17,6 +17,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+import admm_cases     # noqa: E402
 import cases          # noqa: E402
 import ref_driver     # noqa: E402
 from prost_b200 import synthetic as syn   # noqa: E402
@@ -34,9 +35,11 @@ PDHG_SMALL = {
 TOL4 = dict(tol_rel_primal=1e-4, tol_rel_dual=1e-4, tol_abs_primal=1e-4, tol_abs_dual=1e-4)
 
 
-def main(out):
+def main(out, only=""):
     os.makedirs(out, exist_ok=True)
     assert ref_driver.available(), "oracle/_ref/prost_ref_driver missing"
+    if only == "admm":
+        return main_admm(out)
     for name, blocks in cases.linop_cases(small=True).items():
         r = np.random.default_rng(zlib.crc32(name.encode()))
         from oracle_binding import OracleProblem
@@ -67,8 +70,19 @@ def main(out):
         np.savez_compressed(os.path.join(out, f"pdhg_{name}.npz"), x=w["x"], y=w["y"], z=w["z"], w=w["w"],
                             res=np.array([w["res"][k] for k in keys]), res_keys=np.array(keys),
                             iterations=np.int64(w["info"]["iterations"]), **extra)
+    main_admm(out)
     print("wrote", len(os.listdir(out)), "fixtures to", out)
 
 
+def main_admm(out):
+    for name, (fn, iters, opts, tol) in admm_cases.small().items():
+        desc = fn()
+        w = ref_driver.run_solve(desc, iters, tol=tol, admm=opts)
+        keys = sorted(w["res"])
+        np.savez_compressed(os.path.join(out, f"admm_{name}.npz"), x=w["x"], y=w["y"], z=w["z"], w=w["w"],
+                            res=np.array([w["res"][k] for k in keys]), res_keys=np.array(keys),
+                            iterations=np.int64(w["info"]["iterations"]))
+
+
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else HERE)
+    main(sys.argv[1] if len(sys.argv) > 1 else HERE, sys.argv[2] if len(sys.argv) > 2 else "")

@@ -67,6 +67,14 @@ lib.orc_pdhg_residuals.argtypes = [C.c_void_p, fp]
 lib.orc_pdhg_stepsizes.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
 lib.orc_pdhg_solution.argtypes = [C.c_void_p, fp, fp, fp, fp]
 lib.orc_set_num_threads.argtypes = [C.c_int]
+lib.orc_admm_new.restype = C.c_void_p
+lib.orc_admm_new.argtypes = [C.c_void_p] + [C.c_double] * 5 + [C.c_int, C.c_int] + [C.c_float] * 3 + [C.c_float] * 4
+lib.orc_admm_free.argtypes = [C.c_void_p]
+lib.orc_admm_init.argtypes = [C.c_void_p]
+lib.orc_admm_iterate.argtypes = [C.c_void_p, C.c_int]
+lib.orc_admm_residuals.argtypes = [C.c_void_p, fp]
+lib.orc_admm_stepsizes.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+lib.orc_admm_solution.argtypes = [C.c_void_p, fp, fp, fp, fp]
 
 
 def _f32(a):
@@ -263,6 +271,49 @@ class OraclePDHG:
         x, w = np.empty(n, np.float32), np.empty(n, np.float32)
         y, z = np.empty(m, np.float32), np.empty(m, np.float32)
         lib.orc_pdhg_solution(self.h, _p(x), _p(z), _p(y), _p(w))
+        return x, z, y, w
+
+
+class OracleADMM:
+    """Oracle twin of BackendADMM with the option names of +backend/admm.m."""
+
+    def __init__(self, prob, rho0=1.0, alpha=1.7, cg_tol_pow=1.3, cg_tol_min=1e-5, cg_tol_max=1e-8, cg_max_iter=10,
+                 residual_iter=1, arb_delta=1.05, arb_tau=0.8, arb_gamma=1.01,
+                 tol_rel_primal=1e-4, tol_rel_dual=1e-4, tol_abs_primal=1e-4, tol_abs_dual=1e-4):
+        self.prob = prob
+        self.h = C.c_void_p(lib.orc_admm_new(prob.h, rho0, alpha, cg_tol_pow, cg_tol_min, cg_tol_max, cg_max_iter,
+                                             residual_iter, arb_delta, arb_tau, arb_gamma,
+                                             tol_rel_primal, tol_rel_dual, tol_abs_primal, tol_abs_dual))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib.orc_admm_free(self.h)
+            self.h = None
+
+    def initialize(self):
+        if lib.orc_admm_init(self.h) != 0:
+            raise RuntimeError(lib.orc_last_error().decode())
+
+    def iterate(self, n=1):
+        lib.orc_admm_iterate(self.h, n)
+
+    def residuals(self):
+        out = (C.c_float * 6)()
+        lib.orc_admm_residuals(self.h, out)
+        keys = ["primal_residual", "dual_residual", "primal_var_norm", "dual_var_norm", "eps_primal", "eps_dual"]
+        return dict(zip(keys, [float(v) for v in out]))
+
+    def stepsizes(self):
+        """(rho, delta, total CG steps so far)"""
+        out = (C.c_double * 3)()
+        lib.orc_admm_stepsizes(self.h, out)
+        return float(out[0]), float(out[1]), float(out[2])
+
+    def solution(self):
+        n, m = self.prob.ncols, self.prob.nrows
+        x, w = np.empty(n, np.float32), np.empty(n, np.float32)
+        y, z = np.empty(m, np.float32), np.empty(m, np.float32)
+        lib.orc_admm_solution(self.h, _p(x), _p(z), _p(y), _p(w))
         return x, z, y, w
 
 

@@ -129,7 +129,9 @@ def run_prox(desc, arg, tau_diag, tau, binary=REF_DRIVER):
 
 def run_solve(desc, iters, x0=None, y0=None, tol=None, binary=REF_DRIVER, tau0=1.0, sigma0=1.0, residual_iter=1,
               alg2_gamma=0.0, arg_alpha0=0.5, arg_nu=0.95, arg_delta=1.5, arb_delta=1.05, arb_tau=0.8,
-              stepsize="boyd", scale_steps_operator=0, num_cback_calls=0, timeout=1200):
+              stepsize="boyd", scale_steps_operator=0, num_cback_calls=0, timeout=1200, admm=None):
+    """admm: None for BackendPDHG, or a dict of BackendADMM options (rho0, alpha, cg_tol_pow, cg_tol_min,
+    cg_tol_max, cg_max_iter, residual_iter, arb_delta, arb_tau, arb_gamma; defaults of +backend/admm.m)."""
     tol = tol or dict(tol_rel_primal=0.0, tol_rel_dual=0.0, tol_abs_primal=0.0, tol_abs_dual=0.0)
     with tempfile.TemporaryDirectory() as d:
         w = _Writer(d)
@@ -149,6 +151,13 @@ def run_solve(desc, iters, x0=None, y0=None, tol=None, binary=REF_DRIVER, tau0=1
             lines.append(f"scaling custom {fl} {fr}")
         lines.append(f"pdhg {tau0!r} {sigma0!r} {residual_iter} {int(scale_steps_operator)} {alg2_gamma!r} "
                      f"{arg_alpha0!r} {arg_nu!r} {arg_delta!r} {arb_delta!r} {arb_tau!r} {_STEPS[stepsize]}")
+        if admm is not None:
+            a = dict(rho0=1.0, alpha=1.7, cg_tol_pow=1.3, cg_tol_min=1e-5, cg_tol_max=1e-8, cg_max_iter=10,
+                     residual_iter=1, arb_delta=1.05, arb_tau=0.8, arb_gamma=1.01)
+            a.update(admm)
+            lines.append(f"admm {a['rho0']!r} {a['alpha']!r} {a['cg_tol_pow']!r} {a['cg_tol_min']!r} "
+                         f"{a['cg_tol_max']!r} {a['cg_max_iter']} {a['residual_iter']} {a['arb_delta']!r} "
+                         f"{a['arb_tau']!r} {a['arb_gamma']!r}")
         fx = w.arr(x0, np.float32)[0] if x0 is not None else "-"
         fy = w.arr(y0, np.float32)[0] if y0 is not None else "-"
         lines.append(f"solver {tol['tol_rel_primal']!r} {tol['tol_rel_dual']!r} {tol['tol_abs_primal']!r} "

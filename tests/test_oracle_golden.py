@@ -8,9 +8,10 @@ import zlib
 import numpy as np
 import pytest
 
+import admm_cases
 import cases
 from golden.make_golden import PDHG_SMALL, TOL4
-from oracle_binding import OraclePDHG, OracleProblem, oracle_prox_eval
+from oracle_binding import OracleADMM, OraclePDHG, OracleProblem, oracle_prox_eval
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 FILES = sorted(glob.glob(os.path.join(GOLDEN, "*.npz")))
@@ -78,3 +79,27 @@ def test_oracle_pdhg_matches_reference(path):
     res = o.residuals()
     for k, v in zip(g["res_keys"], g["res"]):
         assert abs(res[str(k)] - v) <= (5e-3 if loose else 1e-4) * max(abs(v), 1e-6) + 1e-7, k
+
+
+@pytest.mark.parametrize("path", [f for f in FILES if os.path.basename(f).startswith("admm_")],
+                         ids=lambda p: os.path.basename(p)[:-4])
+def test_oracle_admm_matches_reference(path):
+    """BackendADMM + cgls::Solve of the reference (cuSPARSE / cuBLAS inside) vs the CPU restatement."""
+    name = os.path.basename(path)[5:-4]
+    g = np.load(path)
+    fn, iters, opts, tol = admm_cases.small()[name]
+    o = OracleADMM(OracleProblem(fn()), **opts, **tol)
+    o.initialize()
+    o.iterate(int(g["iterations"]))
+    x, z, y, w = o.solution()
+    scale = lambda v: max(np.abs(v).max(), 1e-30)
+    assert np.abs(x - g["x"]).max() / scale(g["x"]) <= 1e-5
+    assert np.abs(z - g["z"]).max() / scale(g["z"]) <= 1e-5
+    assert np.abs(y - g["y"]).max() / scale(g["y"]) <= 2e-4
+    assert np.abs(w - g["w"]).max() / scale(g["w"]) <= 2e-4
+    res = dict(zip([str(k) for k in g["res_keys"]], g["res"]))
+    got = o.residuals()
+    for k in ("primal_var_norm", "dual_var_norm", "eps_primal", "eps_dual"):
+        assert abs(got[k] - res[k]) <= 1e-4 * max(abs(res[k]), 1e-6) + 1e-7, k
+    for k, sc in (("primal_residual", "primal_var_norm"), ("dual_residual", "dual_var_norm")):
+        assert abs(got[k] - res[k]) <= 1e-4 * abs(res[k]) + 1e-6 * max(res[sc], 1.0), (k, got[k], res[k])

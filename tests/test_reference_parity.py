@@ -11,11 +11,13 @@ import zlib
 import numpy as np
 import pytest
 
+import admm_cases
 import cases
 import prost_b200 as pb
 import ref_driver
 from oracle_binding import OracleProblem, oracle_prox_eval
-from pdhg_util import rel_err, rof_energy, run_cuda, run_oracle
+from pdhg_util import (assert_admm_parity, rel_err, rof_energy, run_cuda, run_cuda_admm, run_oracle,
+                       run_oracle_admm)
 from prost_b200 import synthetic as syn
 
 pytestmark = [pytest.mark.gpu,
@@ -135,6 +137,38 @@ def test_warm_start_vs_reference(ctx):
         for fuse in (1, 2, 0):
             got = run_cuda(ctx, desc, iters, fuse=fuse, x0=x0, y0=y0, stepsize="alg1", residual_iter=1)
             assert_ref_parity(got, want, f"warm start iters={iters} fuse={fuse}")
+
+
+ADMM_CASES = admm_cases.medium()
+
+
+@pytest.mark.parametrize("name", sorted(ADMM_CASES))
+def test_admm_vs_reference(ctx, name):
+    """BackendADMM against the reference's BackendADMM<float> + cgls::Solve (cuSPARSE SpMV, cuBLAS
+    gemv / axpy inside) through Solver::Solve on both sides; the same run pins the CPU oracle."""
+    fn, iters, opts, tol = ADMM_CASES[name]
+    desc = fn()
+    want = ref_driver.run_solve(desc, iters, tol=tol, admm=opts)
+    want["steps"] = None
+    got = run_cuda_admm(ctx, desc, iters, tol=tol, use_solver=True, **opts)
+    assert got["iterations"] == int(want["info"]["iterations"]), (got["iterations"], want["info"]["iterations"])
+    orc = run_oracle_admm(desc, got["iterations"], tol=tol, **opts)
+    for label, res in (("cuda", got), ("oracle", orc)):
+        res = dict(res, steps=(1.0,))
+        assert_admm_parity(res, dict(want, steps=(1.0,)), label=f"{label} {name}")
+
+
+def test_admm_cxx_api_drop_in():
+    """The driver written against prost's public C++ API with BackendADMM, linked against
+    include/prost/*.hpp + libprost_b200.so, vs the same program linked against the reference."""
+    if not ref_driver.available(ref_driver.OUR_DRIVER):
+        pytest.skip("prost_b200_driver not built")
+    fn, iters, opts, tol = ADMM_CASES["lasso_sparse_dense"]
+    desc = fn()
+    want = ref_driver.run_solve(desc, iters, tol=tol, admm=opts)
+    got = ref_driver.run_solve(desc, iters, tol=tol, admm=opts, binary=ref_driver.OUR_DRIVER)
+    assert int(got["info"]["iterations"]) == int(want["info"]["iterations"])
+    assert_admm_parity(dict(got, steps=(1.0,)), dict(want, steps=(1.0,)), label="c++ drop-in admm")
 
 
 @pytest.mark.skipif(not ref_driver.available(ref_driver.OUR_DRIVER), reason="prost_b200_driver not built")
