@@ -225,8 +225,10 @@ typedef struct pb_pdhg_options {
   /* extensions (not in the reference): */
   int fuse;                   /* 1 (default via pb_pdhg_default_options): fused passes where the
                                  planner can, specialised stencil kernels where the operator is a
-                                 planar gradient; 2: generic fused kernels only; 0: reference-shaped
-                                 unfused kernels */
+                                 planar gradient, and the whole iteration as ONE tiled pass where the
+                                 problem has the ROF shape (pb_tile.cu); 3: like 1 without the tiled
+                                 pass; 2: generic fused kernels only; 0: reference-shaped unfused
+                                 kernels */
   const float* normest_x0;    /* optional ncols-vector start for normest (parity runs) */
 } pb_pdhg_options;
 void pb_solver_default_options(pb_solver_options* o);   /* matlab/+prost/options.m:3-14 */
@@ -271,6 +273,10 @@ unsigned long long pb_backend_launch_count(const pb_backend* b);
  * (fused mode) or { primal half, dual half, residuals } (unfused).  Measurement aid for the
  * roofline figures in bench.py; advances the iteration like pb_backend_iterate. */
 int pb_backend_profile(pb_backend* b, int n_iters, float out_ms[3]);
+/* Same, split by kernel schedule (PDHG, fused mode): out = { primal pass ms, dual pass ms (averages over
+ * the iterations that ran as two passes), finalize ms (average over all), whole-iteration tiled kernel
+ * ms (average over the iterations that ran as ONE tiled pass), #two-pass iterations, #tiled iterations } */
+int pb_backend_profile_detail(pb_backend* b, int n_iters, float out[6]);
 /* device pointers of the current iterates (x: ncols, y: nrows) for zero-copy callers */
 int pb_backend_device_iterates(pb_backend* b, float** d_x, float** d_y);
 

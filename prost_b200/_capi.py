@@ -155,6 +155,7 @@ SIGNATURES = {
     "pb_backend_initialize": (C.c_int, [handle, c_float_p, C.c_size_t, c_float_p, C.c_size_t]),
     "pb_backend_iterate": (C.c_int, [handle, C.c_int]),
     "pb_backend_profile": (C.c_int, [handle, C.c_int, c_float_p]),
+    "pb_backend_profile_detail": (C.c_int, [handle, C.c_int, c_float_p]),
     "pb_backend_residuals": (C.c_int, [handle, c_float_p]),
     "pb_backend_stepsizes": (C.c_int, [handle, c_double_p]),
     "pb_backend_iteration": (C.c_size_t, [handle]),

@@ -440,6 +440,13 @@ class Backend(_Handle):
         check(lib.pb_backend_profile(self._h, n, out))
         return float(out[0]), float(out[1]), float(out[2])
 
+    def profile_detail(self, n=1):
+        """dict(primal_ms, dual_ms, finalize_ms, tile_ms, n_two_pass, n_tile): see pb_backend_profile_detail."""
+        out = (C.c_float * 6)()
+        check(lib.pb_backend_profile_detail(self._h, n, out))
+        keys = ["primal_ms", "dual_ms", "finalize_ms", "tile_ms", "n_two_pass", "n_tile"]
+        return dict(zip(keys, [float(v) for v in out]))
+
     def residuals(self):
         out = (C.c_float * 6)()
         check(lib.pb_backend_residuals(self._h, out))

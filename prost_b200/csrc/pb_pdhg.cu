@@ -206,6 +206,7 @@ class BackendPDHG : public Backend {
   void initialize(const float* h_x0, size_t nx0, const float* h_y0, size_t ny0) override;
   void iterate(int n_iters) override;
   void profile(int n_iters, float out_ms[3]) override;
+  void profile_detail(int n_iters, float out[6]) override;
   void residuals(float out[6]) override;
   void stepsizes(double out[3]) override;
   size_t iteration() const override { return iteration_; }
@@ -243,6 +244,8 @@ class BackendPDHG : public Backend {
   PdhgParams params_;
   ProxList prox_g_, prox_fstar_;
   bool fused_ = false;
+  bool tile_ok_ = false;               // non-check iterations run as one tiled pass (pb_tile.cu)
+  unsigned long long tile_iterations_ = 0;
   unsigned long long iteration_ = 0;
 
   // iterates: x_/y_ current, x_prev_/y_prev_ previous (ping-pong in fused mode)
@@ -284,7 +287,7 @@ bool BackendPDHG::plan_fused() {
     return true;
   };
   if (!(collect(prox_g_, g_descs_) && collect(prox_fstar_, f_descs_))) return false;
-  stencil_ = opts_.fuse >= 2 ? StencilPlan() : plan_stencil(K->blocks(), problem_->nrows(), problem_->ncols());
+  stencil_ = opts_.fuse == 2 ? StencilPlan() : plan_stencil(K->blocks(), problem_->nrows(), problem_->ncols());
   return true;
 }
 
@@ -358,6 +361,9 @@ void BackendPDHG::initialize(const float* h_x0, size_t nx0, const float* h_y0, s
   if (ny0 > 0 && ny0 != m) fail(PB_ERR_INVALID, "Initial dual solution has wrong size.");
 
   fused_ = plan_fused();
+  tile_ok_ = fused_ && !comm_ && opts_.fuse == 1 &&
+             tile_iteration_supported(stencil_, g_descs_, f_descs_, problem_->right_ref(), problem_->left_ref());
+  tile_iterations_ = 0;
   if (comm_) {
     // the halo protocol lives in the specialised stencil passes: one planar gradient operator
     // (+ identity rows), one prox_g over all columns, Norm2 on the gradient rows
@@ -430,39 +436,53 @@ void BackendPDHG::iteration_fused() {
   const ScaleRef T = problem_->right_ref(), S = problem_->left_ref();
   const PdhgState* st = d_state_.data();
 
-  // primal pass: x_prev_ <- prox_g(x_ - tau T K^T y_), then swap so that x_ is x^{k+1}
-  unsigned off = 0;
-  unsigned xs = 0, ys = 0;
-  if (comm_) { xs = ++comm_->x_seq; slab_primal_halo(xs); }
-  for (auto& d : g_descs_) {
-    unsigned g = stencil_primal_launch(ctx_, stencil_, d, x_.data(), y_.data(), y_prev_.data(), T, st,
-                                       iteration_ == 0, iteration_ <= 1, check,
-                                       part_d_.data() + 2 * (size_t)off, x_prev_.data());
-    if (g == 0)
-      g = fused_primal_launch(ctx_, d, blocks_, x_.data(), y_.data(), y_prev_.data(), T, st, iteration_ == 0,
-                              iteration_ <= 1, check, part_d_.data() + 2 * (size_t)off, x_prev_.data());
-    off += g;
-  }
-  const unsigned nd = off;
-  x_.swap(x_prev_);
-  if (comm_) { comm_->exchange_x(xs); ys = ++comm_->y_seq; slab_dual_halo(xs, ys); }
-  if (prof_ev_) PB_CUDA(cudaEventRecord(prof_ev_[1], ctx_->stream));
+  unsigned nd = 0, np = 0;
+  if (tile_ok_ && !check && iteration_ > 0) {
+    // whole iteration in one pass over HBM (pb_tile.cu): x_prev_ <- x^{k+1}, y_prev_ <- y^{k+1}
+    tile_iteration_launch(ctx_, stencil_, g_descs_[0], f_descs_[0], x_.data(), y_.data(), T, S, st,
+                          x_prev_.data(), y_prev_.data());
+    x_.swap(x_prev_);
+    y_.swap(y_prev_);
+    tile_iterations_++;
+    if (prof_ev_) {
+      PB_CUDA(cudaEventRecord(prof_ev_[1], ctx_->stream));
+      PB_CUDA(cudaEventRecord(prof_ev_[2], ctx_->stream));
+    }
+  } else {
+    // primal pass: x_prev_ <- prox_g(x_ - tau T K^T y_), then swap so that x_ is x^{k+1}
+    unsigned off = 0;
+    unsigned xs = 0, ys = 0;
+    if (comm_) { xs = ++comm_->x_seq; slab_primal_halo(xs); }
+    for (auto& d : g_descs_) {
+      unsigned g = stencil_primal_launch(ctx_, stencil_, d, x_.data(), y_.data(), y_prev_.data(), T, st,
+                                         iteration_ == 0, iteration_ <= 1, check,
+                                         part_d_.data() + 2 * (size_t)off, x_prev_.data());
+      if (g == 0)
+        g = fused_primal_launch(ctx_, d, blocks_, x_.data(), y_.data(), y_prev_.data(), T, st, iteration_ == 0,
+                                iteration_ <= 1, check, part_d_.data() + 2 * (size_t)off, x_prev_.data());
+      off += g;
+    }
+    nd = off;
+    x_.swap(x_prev_);
+    if (comm_) { comm_->exchange_x(xs); ys = ++comm_->y_seq; slab_dual_halo(xs, ys); }
+    if (prof_ev_) PB_CUDA(cudaEventRecord(prof_ev_[1], ctx_->stream));
 
-  // dual pass: y_prev_ <- prox_f*(y_ + sigma S K(2x^{k+1} - x^k)) (theta-extrapolated), then swap
-  off = 0;
-  for (auto& d : f_descs_) {
-    unsigned g = stencil_dual_launch(ctx_, stencil_, d, y_.data(), x_.data(), x_prev_.data(), S, st,
-                                     iteration_ == 0, check, part_p_.data() + 2 * (size_t)off, y_prev_.data());
-    if (g == 0)
-      g = fused_dual_launch(ctx_, d, blocks_, y_.data(), x_.data(), x_prev_.data(), S, st, iteration_ == 0,
-                            check, part_p_.data() + 2 * (size_t)off, y_prev_.data());
-    off += g;
-  }
-  const unsigned np = off;
-  y_.swap(y_prev_);
-  if (comm_) { comm_->exchange_y(ys); stencil_.geom.halo = SlabHalo(); }
-  if (prof_ev_) PB_CUDA(cudaEventRecord(prof_ev_[2], ctx_->stream));
+    // dual pass: y_prev_ <- prox_f*(y_ + sigma S K(2x^{k+1} - x^k)) (theta-extrapolated), then swap
+    off = 0;
+    for (auto& d : f_descs_) {
+      unsigned g = stencil_dual_launch(ctx_, stencil_, d, y_.data(), x_.data(), x_prev_.data(), S, st,
+                                       iteration_ == 0, check, part_p_.data() + 2 * (size_t)off, y_prev_.data());
+      if (g == 0)
+        g = fused_dual_launch(ctx_, d, blocks_, y_.data(), x_.data(), x_prev_.data(), S, st, iteration_ == 0,
+                              check, part_p_.data() + 2 * (size_t)off, y_prev_.data());
+      off += g;
+    }
+    np = off;
+    y_.swap(y_prev_);
+    if (comm_) { comm_->exchange_y(ys); stencil_.geom.halo = SlabHalo(); }
+    if (prof_ev_) PB_CUDA(cudaEventRecord(prof_ev_[2], ctx_->stream));
 
+  }
   if (comm_ && comm_->world() > 1 && check) {
     // per-rank fold -> one 4-double all-reduce -> identical state machine on every rank
     fold_residuals_kernel<<<1, kBlock, 0, ctx_->stream>>>(part_p_.data(), np, part_d_.data(), nd,
@@ -594,27 +614,47 @@ void BackendPDHG::iteration_unfused() {
 }
 
 void BackendPDHG::profile(int n_iters, float out_ms[3]) {
+  float d[6];
+  profile_detail(n_iters, d);
+  // averages over ALL profiled iterations (tiled iterations count as "primal pass" time)
+  const float n2 = d[4], nt = d[5], n = n2 + nt;
+  out_ms[0] = n > 0 ? (d[0] * n2 + d[3] * nt) / n : 0.f;
+  out_ms[1] = n > 0 ? d[1] * n2 / n : 0.f;
+  out_ms[2] = n > 0 ? d[2] : 0.f;
+}
+
+// out = { primal pass ms, dual pass ms (both averaged over the two-pass iterations), finalize ms
+// (averaged over all), tiled whole-iteration kernel ms (averaged over the tiled iterations),
+// number of two-pass iterations, number of tiled iterations }
+void BackendPDHG::profile_detail(int n_iters, float out[6]) {
   ctx_->bind();
-  out_ms[0] = out_ms[1] = out_ms[2] = 0.f;
+  for (int k = 0; k < 6; ++k) out[k] = 0.f;
   if (!fused_ || n_iters <= 0) { iterate(n_iters); return; }
   cudaEvent_t ev[4];
   for (auto& e : ev) PB_CUDA(cudaEventCreate(&e));
   prof_ev_ = ev;
-  double acc[3] = {0, 0, 0};
+  double acc[4] = {0, 0, 0, 0};
+  int n_two = 0, n_tile = 0;
   for (int i = 0; i < n_iters; ++i) {
+    const unsigned long long tiles_before = tile_iterations_;
     PB_CUDA(cudaEventRecord(ev[0], ctx_->stream));
     iteration_fused();
     PB_CUDA(cudaEventRecord(ev[3], ctx_->stream));
     PB_CUDA(cudaEventSynchronize(ev[3]));
-    for (int k = 0; k < 3; ++k) {
-      float ms = 0.f;
-      PB_CUDA(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
-      acc[k] += ms;
-    }
+    float ms[3];
+    for (int k = 0; k < 3; ++k) PB_CUDA(cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]));
+    if (tile_iterations_ != tiles_before) { acc[3] += ms[0]; ++n_tile; }
+    else { acc[0] += ms[0]; acc[1] += ms[1]; ++n_two; }
+    acc[2] += ms[2];
   }
   prof_ev_ = nullptr;
   for (auto& e : ev) cudaEventDestroy(e);
-  for (int k = 0; k < 3; ++k) out_ms[k] = static_cast<float>(acc[k] / n_iters);
+  out[0] = n_two ? static_cast<float>(acc[0] / n_two) : 0.f;
+  out[1] = n_two ? static_cast<float>(acc[1] / n_two) : 0.f;
+  out[2] = static_cast<float>(acc[2] / n_iters);
+  out[3] = n_tile ? static_cast<float>(acc[3] / n_tile) : 0.f;
+  out[4] = static_cast<float>(n_two);
+  out[5] = static_cast<float>(n_tile);
 }
 
 void BackendPDHG::iterate(int n_iters) {

@@ -641,4 +641,11 @@ unsigned stencil_dual_launch(Context* ctx, const StencilPlan& plan, const ProxDe
                              bool kxprev_zero, bool check, double* partials, float* y_out,
                              bool dry_run = false);
 
+// ---- whole iteration as one tiled pass (pb_tile.cu) ---------------------------------------------
+bool tile_iteration_supported(const StencilPlan& plan, const std::vector<ProxDesc>& gd,
+                              const std::vector<ProxDesc>& fd, ScaleRef T, ScaleRef S);
+void tile_iteration_launch(Context* ctx, const StencilPlan& plan, const ProxDesc& pg, const ProxDesc& pf,
+                           const float* x, const float* y, ScaleRef T, ScaleRef S, const PdhgState* st,
+                           float* x_out, float* y_out);
+
 }  // namespace pb
