@@ -338,8 +338,10 @@ def main():
     prob = build_problem(pb, syn, ctx, f)
     prob.Initialize()
     popts = pb.pdhg_options(scale_steps_operator=0, stepsize="alg1", residual_iter=RESIDUAL_ITER)
+    # num_cback_calls = 0: no intermediate callbacks, i.e. the solution is copied back once at the end
+    # (each intermediate callback of Solver::Solve is a full D2H copy of x, z, y, w: solver.cu:152-167)
     sopts = pb.solver_options(verbose=0, max_iters=args.steps, tol_rel_primal=0, tol_rel_dual=0,
-                              tol_abs_primal=0, tol_abs_dual=0)
+                              tol_abs_primal=0, tol_abs_dual=0, num_cback_calls=0)
     be = pb.BackendPDHG(ctx, prob, popts, sopts)
     be.Initialize()
     assert be.is_fused, "fused PDHG path not selected"
@@ -424,7 +426,8 @@ def main():
     e2e = {"value": args.steps / t_e2e, "unit": "iter/s", "h2d_bytes_per_step": h2d / args.steps,
            "d2h_bytes_per_step": d2h / args.steps, "seconds_total": t_e2e,
            "seconds": {"problem_build_h2d": t1 - t0, "solver_initialize": t2 - t1, "solve_and_d2h": t3 - t2},
-           "what": "Problem build + Solver.Initialize + Solver.Solve(max_iters=K) + solution copy-back"}
+           "what": "Problem build + Solver.Initialize + Solver.Solve(max_iters=K, num_cback_calls=0) + solution "
+                   "copy-back of x, z, y, w"}
     del be2, solver
 
     # ---------------- CPU baseline (oracle port, bounded sample) ------------------------------------

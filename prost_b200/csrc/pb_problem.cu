@@ -5,6 +5,8 @@
 #include "pb_problem.cuh"
 
 #include <algorithm>
+
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <iostream>
@@ -215,6 +217,22 @@ void Problem::average_preconditioners(std::vector<float>& precond, const ProxLis
   std::vector<std::tuple<size_t, size_t, size_t>> groups;
   for (auto& p : prox) {
     if (p->diagsteps()) continue;
+    // constant preconditioner over the prox' range and equally sized groups (gradient operators):
+    // every group averages the same `cnt` copies of one value -- evaluate that float running sum
+    // once instead of enumerating millions of groups
+    const size_t cnt_u = p->uniform_group_size();
+    if (cnt_u > 0 && p->size() > 0 && p->index() + p->size() <= precond.size()) {
+      const float* v = precond.data() + p->index();
+      bool uniform = true;
+      for (size_t i = 1; i < p->size() && uniform; ++i) uniform = v[i] == v[0];
+      if (uniform) {
+        float avg = 0;
+        for (size_t c = 0; c < cnt_u; ++c) avg += v[0];
+        avg /= static_cast<float>(cnt_u);
+        if (avg != v[0]) std::fill(precond.begin() + p->index(), precond.begin() + p->index() + p->size(), avg);
+        continue;
+      }
+    }
     groups.clear();
     p->get_separable_structure(groups);
     for (auto& g : groups) {

@@ -186,6 +186,7 @@ class ProxLeaf : public Prox {
     if (index + count * dim >= (1ull << 31)) fail(PB_ERR_UNSUPPORTED, "prox range exceeds 2^31-1");
   }
   int kind() const override { return kind_; }
+  size_t uniform_group_size() const override { return kind_ == kProxZero ? size_ : dim_; }
   void get_separable_structure(std::vector<std::tuple<size_t, size_t, size_t>>& sep) const override {
     if (kind_ == kProxZero) { sep.emplace_back(index_, size_, 1); return; }
     // ProxSeparableSum (prox_separable_sum.hpp:65-77)
@@ -312,6 +313,7 @@ class ProxMoreau : public Prox {
     const bool folded = inner_->leaf_desc(d, 0) && !d.moreau;
     return (folded ? 0 : size_ * sizeof(float)) + inner_->gpu_mem_amount();
   }
+  size_t uniform_group_size() const override { return inner_->uniform_group_size(); }
   void get_separable_structure(std::vector<std::tuple<size_t, size_t, size_t>>& sep) const override {
     inner_->get_separable_structure(sep);
   }
@@ -363,6 +365,7 @@ class ProxPermute : public Prox {
   size_t gpu_mem_amount() const override {
     return size_ * (sizeof(float) + sizeof(int)) + inner_->gpu_mem_amount();
   }
+  size_t uniform_group_size() const override { return inner_->uniform_group_size(); }
   void get_separable_structure(std::vector<std::tuple<size_t, size_t, size_t>>& sep) const override {
     inner_->get_separable_structure(sep);
   }

@@ -327,6 +327,10 @@ class Prox {
     sep.emplace_back(index_, size_, 1);
   }
 
+  // Common size of ALL groups of get_separable_structure(), or 0 when they differ / are unknown.
+  // Lets Problem::initialize average a constant preconditioner without enumerating the groups.
+  virtual size_t uniform_group_size() const { return size_; }
+
   // Prox::Eval (prox.cu:26-43): full-length device vectors; slices by index.
   void eval(float* d_result, const float* d_arg, const float* d_tau_diag, float tau, bool invert) {
     eval_local(d_result + index_, d_arg + index_, d_tau_diag + index_, tau, invert);

@@ -19,14 +19,22 @@
 // (K^T y := 0, K x_prev := 0); those run the two-pass kernels on the same ping-pong buffers.
 #include "pb_stencil.cuh"
 
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <map>
+#include <mutex>
+#include <tuple>
+
 namespace pb {
 
 namespace {
 
-constexpr int kTX = 32;             // tile columns
-constexpr int kTY = 128;            // tile rows (y is the contiguous direction): one warp = one column
-constexpr int kTileThreads = 256;   // 8 warps -> 4 column sweeps per tile
-constexpr int kSRow = kTY + 4;      // shared row pitch in floats: tile + halo row, 16-byte aligned
+constexpr int kTileThreads = 256;
+// Tile shape: TX columns x TY rows (y is the contiguous direction).  TY/4 threads cover one column
+// with 128-bit accesses, the CTA sweeps kTileThreads/(TY/4) columns at a time.  Shared row pitch
+// TY + 4 floats: tile + halo row, 16-byte aligned.
 
 // prox_g on VEC lanes: ProxElemOperation<ElemOperation1D<FN>> with scalar weights and an optional
 // per-pixel b (same code path as grad_primal_body's scalar-weight branch)
@@ -73,11 +81,16 @@ __device__ __forceinline__ void primal_point(const GradGeom& g, const ProxDesc& 
   elem1d_lanes<VEC, FN>(pg, cg, simple, tau, Tval, idx, xn);
 }
 
-template <int FN_G, int FN_F>
+template <int kTX, int kTY, int FN_G, int FN_F>
 __global__ void __launch_bounds__(kTileThreads, 3) grad2d_iteration_tile_kernel(
     const GradGeom g, const ProxDesc pg, const ProxDesc pf, const float* __restrict__ x,
     const float* __restrict__ y, const float Tval, const float Sval, const PdhgState* __restrict__ st,
     const uint32_t tiles_y, float* __restrict__ x_out, float* __restrict__ y_out) {
+  constexpr int kSRow = kTY + 4;
+  constexpr int kLanesY = kTY / 4;                    // threads per column
+  constexpr int kColsPerSweep = kTileThreads / kLanesY;
+  constexpr int kSweeps = kTX / kColsPerSweep;
+  static_assert(kTX % kColsPerSweep == 0 && kTX <= 32 && kLanesY <= kTileThreads - 32, "tile shape");
   __shared__ __align__(16) float sxn[kTX + 1][kSRow];
   __shared__ __align__(16) float sxo[kTX + 1][kSRow];
 
@@ -86,8 +99,9 @@ __global__ void __launch_bounds__(kTileThreads, 3) grad2d_iteration_tile_kernel(
   const uint32_t tx = tile / tiles_y, ty = tile - tx * tiles_y;
   const uint32_t cx = tx * kTX, cy = ty * kTY;
   const uint32_t l = blockIdx.y;
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t ly = lane * 4, gy = cy + ly;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t tcol = threadIdx.x / kLanesY;        // column of this thread within a sweep
+  const uint32_t ly = (threadIdx.x % kLanesY) * 4, gy = cy + ly;
 
   Coeffs7 cg, cf;
 #pragma unroll
@@ -96,8 +110,8 @@ __global__ void __launch_bounds__(kTileThreads, 3) grad2d_iteration_tile_kernel(
 
   // ---- phase A: x+ on the extended tile ---------------------------------------------------------
 #pragma unroll
-  for (int s = 0; s < kTX / 8; ++s) {
-    const uint32_t col = warp + 8 * s, gx = cx + col;
+  for (int s = 0; s < kSweeps; ++s) {
+    const uint32_t col = tcol + kColsPerSweep * s, gx = cx + col;
     if (gx < g.nx && gy < g.ny) {
       float xo[4], xn[4];
       primal_point<4, FN_G>(g, pg, cg, g_simple, x, y, tau, Tval, gx, gy, l, xo, xn);
@@ -106,7 +120,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) grad2d_iteration_tile_kernel(
       VecIO<4>::st(&sxo[col][ly], xo);
     }
   }
-  if (warp == 0) {                       // halo column x = cx + TX (owned by the tile to the right)
+  if (threadIdx.x < kLanesY) {           // halo column x = cx + TX (owned by the tile to the right)
     const uint32_t gx = cx + kTX;
     if (gx < g.nx && gy < g.ny) {
       float xo[4], xn[4];
@@ -114,9 +128,9 @@ __global__ void __launch_bounds__(kTileThreads, 3) grad2d_iteration_tile_kernel(
       VecIO<4>::st(&sxn[kTX][ly], xn);
       VecIO<4>::st(&sxo[kTX][ly], xo);
     }
-  } else if (warp == 1) {                // halo row y = cy + TY (owned by the tile below)
+  } else if (threadIdx.x >= kTileThreads - 32) {   // halo row y = cy + TY (owned by the tile below)
     const uint32_t gx = cx + lane, hy = cy + kTY;
-    if (gx < g.nx && hy < g.ny) {
+    if (lane < kTX && gx < g.nx && hy < g.ny) {
       float xo[1], xn[1];
       primal_point<1, FN_G>(g, pg, cg, g_simple, x, y, tau, Tval, gx, hy, l, xo, xn);
       sxn[lane][kTY] = xn[0];
@@ -130,8 +144,8 @@ __global__ void __launch_bounds__(kTileThreads, 3) grad2d_iteration_tile_kernel(
   const float tau_f = effective_tau(sigma, Sval, false);
   const bool f_simple = coeffs_simple(cf);
 #pragma unroll
-  for (int s = 0; s < kTX / 8; ++s) {
-    const uint32_t col = warp + 8 * s, gx = cx + col;
+  for (int s = 0; s < kSweeps; ++s) {
+    const uint32_t col = tcol + kColsPerSweep * s, gx = cx + col;
     if (gx < g.nx && gy < g.ny) {
       const uint32_t idx = gy + gx * g.ny + l * g.nxny;
       float arg[2][4];
@@ -173,16 +187,535 @@ __global__ void __launch_bounds__(kTileThreads, 3) grad2d_iteration_tile_kernel(
   }
 }
 
-template <int FN_G>
-void tile_launch_f(Context* ctx, dim3 grid, const GradGeom& g, const ProxDesc& pg, const ProxDesc& pf,
-                   const float* x, const float* y, float Tval, float Sval, const PdhgState* st,
-                   uint32_t tiles_y, float* x_out, float* y_out) {
+template <int TX, int TY, int FN_G>
+void tile_launch_f(Context* ctx, const GradGeom& g, const ProxDesc& pg, const ProxDesc& pf, const float* x,
+                   const float* y, float Tval, float Sval, const PdhgState* st, float* x_out, float* y_out) {
+  const uint32_t tiles_x = (g.nx + TX - 1) / TX, tiles_y = (g.ny + TY - 1) / TY;
+  const dim3 grid(tiles_x * tiles_y, g.L, 1);
   if (pf.fn == PB_FUN_IND_LEQ0)
-    grad2d_iteration_tile_kernel<FN_G, PB_FUN_IND_LEQ0><<<grid, kTileThreads, 0, ctx->stream>>>(
+    grad2d_iteration_tile_kernel<TX, TY, FN_G, PB_FUN_IND_LEQ0><<<grid, kTileThreads, 0, ctx->stream>>>(
         g, pg, pf, x, y, Tval, Sval, st, tiles_y, x_out, y_out);
   else
-    grad2d_iteration_tile_kernel<FN_G, -1><<<grid, kTileThreads, 0, ctx->stream>>>(
+    grad2d_iteration_tile_kernel<TX, TY, FN_G, -1><<<grid, kTileThreads, 0, ctx->stream>>>(
         g, pg, pf, x, y, Tval, Sval, st, tiles_y, x_out, y_out);
+}
+
+template <int TX, int TY>
+void tile_launch_g(Context* ctx, const GradGeom& g, const ProxDesc& pg, const ProxDesc& pf, const float* x,
+                   const float* y, float Tval, float Sval, const PdhgState* st, float* x_out, float* y_out) {
+  if (pg.fn == PB_FUN_SQUARE) tile_launch_f<TX, TY, PB_FUN_SQUARE>(ctx, g, pg, pf, x, y, Tval, Sval, st, x_out, y_out);
+  else if (pg.fn == PB_FUN_ABS) tile_launch_f<TX, TY, PB_FUN_ABS>(ctx, g, pg, pf, x, y, Tval, Sval, st, x_out, y_out);
+  else tile_launch_f<TX, TY, -1>(ctx, g, pg, pf, x, y, Tval, Sval, st, x_out, y_out);
+}
+
+
+// ---- TMA variant ------------------------------------------------------------------------------------
+// Same arithmetic, but every operand tile (with its halos) is brought into shared memory by four
+// cp.async.bulk.tensor (TMA) loads issued by one thread; the SM issues no global-load instructions at
+// all and the whole tile's bytes are in flight at once (the plain variant above is latency bound:
+// ncu long-scoreboard stalls, profiles/r01_tile.md).  Image borders come for free: out-of-range box
+// elements are zero-filled, which is exactly the K^T boundary rule for x = -1 and y = -1; the
+// x = nx-1 / y = ny-1 rules are applied in registers like in grad_adj / grad_fwd.
+//   box   origin (row, col)       extent (cols x rows)   used for
+//   p1    (cy,   cx-1)            (TX+2) x (TY+4)        gx component of y incl. left neighbour column
+//   p2    (cy-4, cx)              (TX+1) x (TY+8)        gy component of y incl. row cy-1 (16 B aligned)
+//   x, f  (cy,   cx)              (TX+1) x (TY+4)        primal iterate and data term incl. halo col / row
+constexpr int kTmaTX = 32, kTmaTY = 128;
+constexpr int kTmaR = kTmaTY + 4;          // rows per column in the p1 / x / f / x+ tiles
+constexpr int kTmaR2 = kTmaTY + 8;         // rows per column in the p2 tile (starts 4 rows early)
+constexpr int kTmaP1Bytes = (kTmaTX + 2) * kTmaR * 4;
+constexpr int kTmaP2Bytes = (kTmaTX + 1) * kTmaR2 * 4;
+constexpr int kTmaXBytes = (kTmaTX + 1) * kTmaR * 4;
+constexpr int align128(int v) { return (v + 127) / 128 * 128; }
+constexpr int kTmaOffP1 = 0;
+constexpr int kTmaOffP2 = kTmaOffP1 + align128(kTmaP1Bytes);
+constexpr int kTmaOffX = kTmaOffP2 + align128(kTmaP2Bytes);
+constexpr int kTmaOffF = kTmaOffX + align128(kTmaXBytes);
+constexpr int kTmaOffXn = kTmaOffF + align128(kTmaXBytes);
+constexpr int kTmaOffBar = kTmaOffXn + align128(kTmaXBytes);
+constexpr int kTmaSmemBytes = kTmaOffBar + 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, void* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+template <int FN_G, int FN_F>
+__global__ void __launch_bounds__(kTileThreads, 2) grad2d_iteration_tma_kernel(
+    const __grid_constant__ CUtensorMap map_p1, const __grid_constant__ CUtensorMap map_p2,
+    const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_f, const GradGeom g,
+    const ProxDesc pg, const ProxDesc pf, const float Tval, const float Sval,
+    const PdhgState* __restrict__ st, const uint32_t tiles_y, float* __restrict__ x_out,
+    float* __restrict__ y_out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  float (*s_p1)[kTmaR] = reinterpret_cast<float (*)[kTmaR]>(smem + kTmaOffP1);
+  float (*s_p2)[kTmaR2] = reinterpret_cast<float (*)[kTmaR2]>(smem + kTmaOffP2);
+  float (*s_x)[kTmaR] = reinterpret_cast<float (*)[kTmaR]>(smem + kTmaOffX);
+  float (*s_f)[kTmaR] = reinterpret_cast<float (*)[kTmaR]>(smem + kTmaOffF);
+  float (*s_xn)[kTmaR] = reinterpret_cast<float (*)[kTmaR]>(smem + kTmaOffXn);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kTmaOffBar);
+
+  const uint32_t tile = blockIdx.x;
+  const uint32_t tx = tile / tiles_y, ty = tile - tx * tiles_y;
+  const int cx = tx * kTmaTX, cy = ty * kTmaTY;
+  const int l = blockIdx.y;
+  const bool f_vec = pg.coeffs.ptr[1] != nullptr;
+
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t bytes = kTmaP1Bytes + kTmaP2Bytes + kTmaXBytes + (f_vec ? kTmaXBytes : 0);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    tma_load_3d(s_p1, &map_p1, bar, cy, cx - 1, l);
+    tma_load_3d(s_p2, &map_p2, bar, cy - 4, cx, (int)g.L + l);
+    tma_load_3d(s_x, &map_x, bar, cy, cx, l);
+    if (f_vec) tma_load_3d(s_f, &map_f, bar, cy, cx, l);
+  }
+
+  const float tau = st->tau, sigma = st->sigma, theta = st->theta;
+  Coeffs7 cg, cf;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) { cg.v[k] = pg.coeffs.val[k]; cf.v[k] = pf.coeffs.val[k]; }
+  const bool g_simple = coeffs_simple(cg) && cg.v[2] != 0.f;
+  const int fn_g = FN_G >= 0 ? FN_G : pg.fn;
+  const float tau_g = effective_tau(tau, Tval, false);
+
+  {  // wait for the four boxes (phase 0 of the one-shot barrier)
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+          : "=r"(done) : "r"(smem_u32(bar)), "r"(0u) : "memory");
+    }
+  }
+
+  // ---- phase A: x+ on (TX+1) columns x (TY+4) rows ---------------------------------------------------
+  constexpr int kVecA = kTmaR / 4;                       // 33 row vectors per column
+  for (int it = threadIdx.x; it < (kTmaTX + 1) * kVecA; it += kTileThreads) {
+    const int col = it / kVecA, v = it - col * kVecA;
+    const int r0 = 4 * v;
+    const uint32_t gx = cx + col, gy = cy + r0;
+    if (gx >= g.nx) continue;
+    float xo[4], divx[4], o[4], a[4], xn[4];
+    VecIO<4>::ld(&s_x[col][r0], xo);
+    if (gx < g.nx - 1) {
+      VecIO<4>::ld(&s_p1[col + 1][r0], divx);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) divx[j] = 0.f;
+    }
+    if (gx > 0) {
+      VecIO<4>::ld(&s_p1[col][r0], a);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) divx[j] -= a[j];
+    }
+    VecIO<4>::ld(&s_p2[col][4 + r0], o);
+    float divy[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) divy[j] = (gy + j == g.ny - 1) ? 0.f : o[j];
+#pragma unroll
+    for (int j = 1; j < 4; ++j) divy[j] -= o[j - 1];
+    if (gy > 0) divy[0] -= s_p2[col][4 + r0 - 1];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) xn[j] = primal_prox_arg(xo[j], tau, Tval, -(divx[j] + divy[j]));
+    float bv[4];
+    if (f_vec) {
+      VecIO<4>::ld(&s_f[col][r0], bv);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = cg.v[1];
+    }
+    if (g_simple) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) xn[j] = scaled_fun_prox_simple(fn_g, xn[j], tau_g, bv[j], cg.v[2], cg.v[5], cg.v[6]);
+    } else {
+      Coeffs7 c = cg;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        c.v[1] = bv[j];
+        xn[j] = elem1d_apply(fn_g, xn[j], tau, Tval, false, c);
+      }
+    }
+    VecIO<4>::st(&s_xn[col][r0], xn);
+    if (col < kTmaTX && v < kTmaTY / 4 && gy < g.ny)
+      VecIO<4>::st(x_out + gy + gx * g.ny + (uint32_t)l * g.nxny, xn);
+  }
+  __syncthreads();
+
+  // ---- phase B: y+ on the TX x TY tile -----------------------------------------------------------------
+  const int fn_f = FN_F >= 0 ? FN_F : pf.fn;
+  const float tau_f = effective_tau(sigma, Sval, false);
+  const bool f_simple = coeffs_simple(cf);
+  constexpr int kVecB = kTmaTY / 4;
+#pragma unroll
+  for (int s = 0; s < kTmaTX * kVecB / kTileThreads; ++s) {
+    const int it = threadIdx.x + s * kTileThreads;
+    const int col = it / kVecB, v = it - col * kVecB;
+    const int r0 = 4 * v;
+    const uint32_t gx = cx + col, gy = cy + r0;
+    if (gx < g.nx && gy < g.ny) {
+      const uint32_t idx = gy + gx * g.ny + (uint32_t)l * g.nxny;
+      float arg[2][4];
+      float cn[4], co[4], rn[4], ro[4];
+      VecIO<4>::ld(&s_xn[col][r0], cn);
+      VecIO<4>::ld(&s_x[col][r0], co);
+      float k1x[4], k0x[4], k1y[4], k0y[4];
+      if (gx < g.nx - 1) {
+        VecIO<4>::ld(&s_xn[col + 1][r0], rn);
+        VecIO<4>::ld(&s_x[col + 1][r0], ro);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { k1x[j] = rn[j] - cn[j]; k0x[j] = ro[j] - co[j]; }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { k1x[j] = 0.f; k0x[j] = 0.f; }
+      }
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { k1y[j] = cn[j + 1] - cn[j]; k0y[j] = co[j + 1] - co[j]; }
+      if (gy + 4 < g.ny) {
+        k1y[3] = s_xn[col][r0 + 4] - cn[3];
+        k0y[3] = s_x[col][r0 + 4] - co[3];
+      } else {
+        k1y[3] = 0.f;
+        k0y[3] = 0.f;
+      }
+      float y1[4], y2[4];
+      VecIO<4>::ld(&s_p1[col + 1][r0], y1);
+      VecIO<4>::ld(&s_p2[col][4 + r0], y2);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        arg[0][j] = dual_prox_arg(y1[j], sigma, Sval, dual_extrapolate(theta, k1x[j], k0x[j]));
+        arg[1][j] = dual_prox_arg(y2[j], sigma, Sval, dual_extrapolate(theta, k1y[j], k0y[j]));
+      }
+      if (f_simple) norm2_lanes<4, 2, true>(fn_f, arg, cf, tau_f);
+      else norm2_lanes<4, 2, false>(fn_f, arg, cf, tau_f);
+      VecIO<4>::st(y_out + idx, arg[0]);
+      VecIO<4>::st(y_out + g.plane + idx, arg[1]);
+    }
+  }
+}
+
+// ---- tensor maps (host) ------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    cudaGetLastError();
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// 3-D map over a planar float array [planes][nx][ny] (ny contiguous) with a (rows x cols x 1) box
+bool tensor_map_for(const float* base, uint32_t ny, uint32_t nx, uint32_t planes, uint32_t box_rows,
+                    uint32_t box_cols, CUtensorMap& out) {
+  typedef std::tuple<const void*, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t> Key;
+  static std::map<Key, CUtensorMap> cache;
+  static std::mutex mu;
+  const Key key(base, ny, nx, planes, box_rows, box_cols);
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) { out = it->second; return true; }
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return false;
+  const cuuint64_t dims[3] = {ny, nx, planes};
+  const cuuint64_t strides[2] = {(cuuint64_t)ny * 4, (cuuint64_t)ny * nx * 4};
+  const cuuint32_t box[3] = {box_rows, box_cols, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMap m;
+  const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  if (cache.size() > 256) cache.clear();
+  cache[key] = m;
+  out = m;
+  return true;
+}
+
+template <int FN_G, int FN_F>
+bool tma_launch_fn(Context* ctx, const CUtensorMap& mp1, const CUtensorMap& mp2, const CUtensorMap& mx,
+                   const CUtensorMap& mf, const GradGeom& g, const ProxDesc& pg, const ProxDesc& pf, float Tval,
+                   float Sval, const PdhgState* st, float* x_out, float* y_out) {
+  auto kernel = grad2d_iteration_tma_kernel<FN_G, FN_F>;
+  static bool configured = false, ok = false;
+  if (!configured) {
+    configured = true;
+    ok = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes) == cudaSuccess;
+    cudaGetLastError();
+  }
+  if (!ok) return false;
+  const uint32_t tiles_x = (g.nx + kTmaTX - 1) / kTmaTX, tiles_y = (g.ny + kTmaTY - 1) / kTmaTY;
+  const dim3 grid(tiles_x * tiles_y, g.L, 1);
+  kernel<<<grid, kTileThreads, kTmaSmemBytes, ctx->stream>>>(mp1, mp2, mx, mf, g, pg, pf, Tval, Sval, st, tiles_y,
+                                                             x_out, y_out);
+  return true;
+}
+
+bool tma_launch(Context* ctx, const GradGeom& g, const ProxDesc& pg, const ProxDesc& pf, const float* x,
+                const float* y, float Tval, float Sval, const PdhgState* st, float* x_out, float* y_out) {
+  CUtensorMap mp1, mp2, mx, mf;
+  if (!tensor_map_for(y, g.ny, g.nx, 2 * g.L, kTmaR, kTmaTX + 2, mp1)) return false;
+  if (!tensor_map_for(y, g.ny, g.nx, 2 * g.L, kTmaR2, kTmaTX + 1, mp2)) return false;
+  if (!tensor_map_for(x, g.ny, g.nx, g.L, kTmaR, kTmaTX + 1, mx)) return false;
+  const float* f = pg.coeffs.ptr[1] ? pg.coeffs.ptr[1] : x;      // unused when b is a scalar
+  if (!tensor_map_for(f, g.ny, g.nx, g.L, kTmaR, kTmaTX + 1, mf)) return false;
+#define PB_ARGS ctx, mp1, mp2, mx, mf, g, pg, pf, Tval, Sval, st, x_out, y_out
+  const bool leq0 = pf.fn == PB_FUN_IND_LEQ0;
+  if (pg.fn == PB_FUN_SQUARE) return leq0 ? tma_launch_fn<PB_FUN_SQUARE, PB_FUN_IND_LEQ0>(PB_ARGS) : tma_launch_fn<PB_FUN_SQUARE, -1>(PB_ARGS);
+  if (pg.fn == PB_FUN_ABS) return leq0 ? tma_launch_fn<PB_FUN_ABS, PB_FUN_IND_LEQ0>(PB_ARGS) : tma_launch_fn<PB_FUN_ABS, -1>(PB_ARGS);
+  return leq0 ? tma_launch_fn<-1, PB_FUN_IND_LEQ0>(PB_ARGS) : tma_launch_fn<-1, -1>(PB_ARGS);
+#undef PB_ARGS
+}
+
+
+// ---- persistent TMA ring ------------------------------------------------------------------------------
+// The one-shot kernels above alternate between waiting for memory and computing: ncu shows DRAM
+// ~50 % busy and the issue slots ~50 % busy, i.e. the two phases serialise (profiles/r01_tile.md).
+// Here ONE CTA of 1024 threads stays resident per SM and walks over tiles; the operand boxes of the
+// next two tiles are always in flight (two shared-memory stages filled by TMA, completion signalled on
+// mbarriers), so HBM streams continuously while the 32 warps compute the current tile.
+//   computed x+ region 32 columns x 128 rows = 1024 row vectors = exactly one per thread;
+//   owned tile         31 columns x 124 rows (the last column / 4 rows are the halo of the neighbours).
+constexpr int kRingThreads = 1024;
+constexpr int kRingCols = 32, kRingRows = 128;          // computed region
+constexpr int kRingTX = kRingCols - 1, kRingTY = kRingRows - 4;   // owned tile
+constexpr int kRingR2 = kRingRows + 4;                  // p2 box rows (starts 4 rows early)
+constexpr int kRingP1Bytes = (kRingCols + 1) * kRingRows * 4;
+constexpr int kRingP2Bytes = kRingCols * kRingR2 * 4;
+constexpr int kRingXBytes = kRingCols * kRingRows * 4;
+constexpr int kRingStageBytes = kRingP1Bytes + kRingP2Bytes + 2 * kRingXBytes;
+constexpr int kRingStages = 2;
+constexpr int kRingOffXn = kRingStages * kRingStageBytes;
+constexpr int kRingOffBar = kRingOffXn + kRingXBytes;
+constexpr int kRingSmemBytes = kRingOffBar + 128;
+static_assert(kRingP1Bytes % 128 == 0 && kRingP2Bytes % 128 == 0 && kRingXBytes % 128 == 0, "TMA alignment");
+
+template <int FN_G, int FN_F>
+__global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
+    const __grid_constant__ CUtensorMap map_p1, const __grid_constant__ CUtensorMap map_p2,
+    const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_f, const GradGeom g,
+    const ProxDesc pg, const ProxDesc pf, const float Tval, const float Sval,
+    const PdhgState* __restrict__ st, const uint32_t tiles_x, const uint32_t tiles_y, const uint32_t n_tiles,
+    float* __restrict__ x_out, float* __restrict__ y_out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  float (*s_xn)[kRingRows] = reinterpret_cast<float (*)[kRingRows]>(smem + kRingOffXn);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kRingOffBar);
+
+  const bool f_vec = pg.coeffs.ptr[1] != nullptr;
+  const uint32_t stage_tx = kRingP1Bytes + kRingP2Bytes + kRingXBytes + (f_vec ? kRingXBytes : 0);
+  const uint32_t per_plane = tiles_x * tiles_y;
+
+  auto issue = [&](uint32_t tile, int s) {           // thread 0 only
+    const uint32_t l = tile / per_plane, rem = tile - l * per_plane;
+    const uint32_t tx = rem / tiles_y, ty = rem - tx * tiles_y;
+    const int cx = tx * kRingTX, cy = ty * kRingTY;
+    unsigned char* base = smem + s * kRingStageBytes;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full[s])), "r"(stage_tx)
+                 : "memory");
+    tma_load_3d(base, &map_p1, &full[s], cy, cx - 1, (int)l);
+    tma_load_3d(base + kRingP1Bytes, &map_p2, &full[s], cy - 4, cx, (int)(g.L + l));
+    tma_load_3d(base + kRingP1Bytes + kRingP2Bytes, &map_x, &full[s], cy, cx, (int)l);
+    if (f_vec) tma_load_3d(base + kRingP1Bytes + kRingP2Bytes + kRingXBytes, &map_f, &full[s], cy, cx, (int)l);
+  };
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kRingStages; ++s)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[s])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kRingStages; ++s) {
+      const uint32_t t = blockIdx.x + s * gridDim.x;
+      if (t < n_tiles) issue(t, s);
+    }
+  }
+
+  const float tau = st->tau, sigma = st->sigma, theta = st->theta;
+  Coeffs7 cg, cf;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) { cg.v[k] = pg.coeffs.val[k]; cf.v[k] = pf.coeffs.val[k]; }
+  const bool g_simple = coeffs_simple(cg) && cg.v[2] != 0.f;
+  const int fn_g = FN_G >= 0 ? FN_G : pg.fn;
+  const float tau_g = effective_tau(tau, Tval, false);
+  const int fn_f = FN_F >= 0 ? FN_F : pf.fn;
+  const float tau_f = effective_tau(sigma, Sval, false);
+  const bool f_simple = coeffs_simple(cf);
+
+  const int col = threadIdx.x >> 5;          // warp = column of the computed region
+  const int r0 = (threadIdx.x & 31) * 4;     // lane = row vector
+
+  uint32_t k = 0;
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
+    const int s = k % kRingStages;
+    const uint32_t parity = (k / kRingStages) & 1u;
+    const uint32_t l = tile / per_plane, rem = tile - l * per_plane;
+    const uint32_t tx = rem / tiles_y, ty = rem - tx * tiles_y;
+    const int cx = tx * kRingTX, cy = ty * kRingTY;
+    unsigned char* base = smem + s * kRingStageBytes;
+    float (*s_p1)[kRingRows] = reinterpret_cast<float (*)[kRingRows]>(base);
+    float (*s_p2)[kRingR2] = reinterpret_cast<float (*)[kRingR2]>(base + kRingP1Bytes);
+    float (*s_x)[kRingRows] = reinterpret_cast<float (*)[kRingRows]>(base + kRingP1Bytes + kRingP2Bytes);
+    float (*s_f)[kRingRows] = reinterpret_cast<float (*)[kRingRows]>(base + kRingP1Bytes + kRingP2Bytes + kRingXBytes);
+
+    {
+      uint32_t done = 0;
+      while (!done) {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done) : "r"(smem_u32(&full[s])), "r"(parity) : "memory");
+      }
+    }
+
+    const uint32_t gx = cx + col, gy = cy + r0;
+    const uint32_t plane_off = l * g.nxny;
+    // ---- phase A: x+ at (col, r0..r0+3) of the computed region ------------------------------------------
+    if (gx < g.nx) {
+      float xo[4], divx[4], o[4], a[4], xn[4];
+      VecIO<4>::ld(&s_x[col][r0], xo);
+      if (gx < g.nx - 1) {
+        VecIO<4>::ld(&s_p1[col + 1][r0], divx);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) divx[j] = 0.f;
+      }
+      if (gx > 0) {
+        VecIO<4>::ld(&s_p1[col][r0], a);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) divx[j] -= a[j];
+      }
+      VecIO<4>::ld(&s_p2[col][4 + r0], o);
+      float divy[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) divy[j] = (gy + j == g.ny - 1) ? 0.f : o[j];
+#pragma unroll
+      for (int j = 1; j < 4; ++j) divy[j] -= o[j - 1];
+      if (gy > 0) divy[0] -= s_p2[col][4 + r0 - 1];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) xn[j] = primal_prox_arg(xo[j], tau, Tval, -(divx[j] + divy[j]));
+      float bv[4];
+      if (f_vec) {
+        VecIO<4>::ld(&s_f[col][r0], bv);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bv[j] = cg.v[1];
+      }
+      if (g_simple) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          xn[j] = scaled_fun_prox_simple(fn_g, xn[j], tau_g, bv[j], cg.v[2], cg.v[5], cg.v[6]);
+      } else {
+        Coeffs7 c = cg;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          c.v[1] = bv[j];
+          xn[j] = elem1d_apply(fn_g, xn[j], tau, Tval, false, c);
+        }
+      }
+      VecIO<4>::st(&s_xn[col][r0], xn);
+      if (col < kRingTX && r0 < kRingTY && gy < g.ny) VecIO<4>::st(x_out + gy + gx * g.ny + plane_off, xn);
+    }
+    __syncthreads();
+
+    // ---- phase B: y+ at the owned point (col, r0..r0+3) ---------------------------------------------------
+    if (col < kRingTX && r0 < kRingTY && gx < g.nx && gy < g.ny) {
+      const uint32_t idx = gy + gx * g.ny + plane_off;
+      float arg[2][4];
+      float cn[4], co[4], rn[4], ro[4];
+      VecIO<4>::ld(&s_xn[col][r0], cn);
+      VecIO<4>::ld(&s_x[col][r0], co);
+      float k1x[4], k0x[4], k1y[4], k0y[4];
+      if (gx < g.nx - 1) {
+        VecIO<4>::ld(&s_xn[col + 1][r0], rn);
+        VecIO<4>::ld(&s_x[col + 1][r0], ro);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { k1x[j] = rn[j] - cn[j]; k0x[j] = ro[j] - co[j]; }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { k1x[j] = 0.f; k0x[j] = 0.f; }
+      }
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { k1y[j] = cn[j + 1] - cn[j]; k0y[j] = co[j + 1] - co[j]; }
+      if (gy + 4 < g.ny) {
+        k1y[3] = s_xn[col][r0 + 4] - cn[3];
+        k0y[3] = s_x[col][r0 + 4] - co[3];
+      } else {
+        k1y[3] = 0.f;
+        k0y[3] = 0.f;
+      }
+      float y1[4], y2[4];
+      VecIO<4>::ld(&s_p1[col + 1][r0], y1);
+      VecIO<4>::ld(&s_p2[col][4 + r0], y2);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        arg[0][j] = dual_prox_arg(y1[j], sigma, Sval, dual_extrapolate(theta, k1x[j], k0x[j]));
+        arg[1][j] = dual_prox_arg(y2[j], sigma, Sval, dual_extrapolate(theta, k1y[j], k0y[j]));
+      }
+      if (f_simple) norm2_lanes<4, 2, true>(fn_f, arg, cf, tau_f);
+      else norm2_lanes<4, 2, false>(fn_f, arg, cf, tau_f);
+      VecIO<4>::st(y_out + idx, arg[0]);
+      VecIO<4>::st(y_out + (size_t)g.L * g.nxny + idx, arg[1]);
+    }
+    __syncthreads();          // every thread is done with stage s and with s_xn
+    if (threadIdx.x == 0) {
+      const uint32_t next = tile + kRingStages * gridDim.x;
+      if (next < n_tiles) issue(next, s);
+    }
+  }
+}
+
+template <int FN_G, int FN_F>
+bool ring_launch_fn(Context* ctx, const CUtensorMap& mp1, const CUtensorMap& mp2, const CUtensorMap& mx,
+                    const CUtensorMap& mf, const GradGeom& g, const ProxDesc& pg, const ProxDesc& pf, float Tval,
+                    float Sval, const PdhgState* st, float* x_out, float* y_out) {
+  auto kernel = grad2d_iteration_ring_kernel<FN_G, FN_F>;
+  static bool configured = false, ok = false;
+  if (!configured) {
+    configured = true;
+    ok = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingSmemBytes) == cudaSuccess;
+    cudaGetLastError();
+  }
+  if (!ok) return false;
+  const uint32_t tiles_x = (g.nx + kRingTX - 1) / kRingTX, tiles_y = (g.ny + kRingTY - 1) / kRingTY;
+  const uint64_t n_tiles = (uint64_t)tiles_x * tiles_y * g.L;
+  if (n_tiles >= (1ull << 31)) return false;
+  const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)ctx->num_sms);
+  kernel<<<grid, kRingThreads, kRingSmemBytes, ctx->stream>>>(mp1, mp2, mx, mf, g, pg, pf, Tval, Sval, st, tiles_x,
+                                                              tiles_y, (uint32_t)n_tiles, x_out, y_out);
+  return true;
+}
+
+bool ring_launch(Context* ctx, const GradGeom& g, const ProxDesc& pg, const ProxDesc& pf, const float* x,
+                 const float* y, float Tval, float Sval, const PdhgState* st, float* x_out, float* y_out) {
+  CUtensorMap mp1, mp2, mx, mf;
+  if (!tensor_map_for(y, g.ny, g.nx, 2 * g.L, kRingRows, kRingCols + 1, mp1)) return false;
+  if (!tensor_map_for(y, g.ny, g.nx, 2 * g.L, kRingR2, kRingCols, mp2)) return false;
+  if (!tensor_map_for(x, g.ny, g.nx, g.L, kRingRows, kRingCols, mx)) return false;
+  const float* f = pg.coeffs.ptr[1] ? pg.coeffs.ptr[1] : x;      // unused when b is a scalar
+  if (!tensor_map_for(f, g.ny, g.nx, g.L, kRingRows, kRingCols, mf)) return false;
+#define PB_ARGS ctx, mp1, mp2, mx, mf, g, pg, pf, Tval, Sval, st, x_out, y_out
+  const bool leq0 = pf.fn == PB_FUN_IND_LEQ0;
+  if (pg.fn == PB_FUN_SQUARE) return leq0 ? ring_launch_fn<PB_FUN_SQUARE, PB_FUN_IND_LEQ0>(PB_ARGS) : ring_launch_fn<PB_FUN_SQUARE, -1>(PB_ARGS);
+  if (pg.fn == PB_FUN_ABS) return leq0 ? ring_launch_fn<PB_FUN_ABS, PB_FUN_IND_LEQ0>(PB_ARGS) : ring_launch_fn<PB_FUN_ABS, -1>(PB_ARGS);
+  return leq0 ? ring_launch_fn<-1, PB_FUN_IND_LEQ0>(PB_ARGS) : ring_launch_fn<-1, -1>(PB_ARGS);
+#undef PB_ARGS
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -218,14 +751,29 @@ void tile_iteration_launch(Context* ctx, const StencilPlan& plan, const ProxDesc
                            const float* x, const float* y, ScaleRef T, ScaleRef S, const PdhgState* st,
                            float* x_out, float* y_out) {
   const GradGeom& g = plan.geom;
-  const uint32_t tiles_x = (g.nx + kTX - 1) / kTX, tiles_y = (g.ny + kTY - 1) / kTY;
-  const dim3 grid(tiles_x * tiles_y, g.L, 1);
-  if (pg.fn == PB_FUN_SQUARE)
-    tile_launch_f<PB_FUN_SQUARE>(ctx, grid, g, pg, pf, x, y, T.val, S.val, st, tiles_y, x_out, y_out);
-  else if (pg.fn == PB_FUN_ABS)
-    tile_launch_f<PB_FUN_ABS>(ctx, grid, g, pg, pf, x, y, T.val, S.val, st, tiles_y, x_out, y_out);
-  else
-    tile_launch_f<-1>(ctx, grid, g, pg, pf, x, y, T.val, S.val, st, tiles_y, x_out, y_out);
+  // tile shape: long columns segments keep DRAM pages busy, wide tiles keep the halo share low;
+  // PB_TILE_SHAPE (0..3) overrides the default for experiments
+  static const int shape = [] { const char* e = getenv("PB_TILE_SHAPE"); return e ? atoi(e) : 0; }();
+  // PB_TILE_MODE: 2 (default) persistent TMA ring, 1 one-shot TMA tiles, 0 plain loads (A/B experiments)
+  static const int mode = [] { const char* e = getenv("PB_TILE_MODE"); return e ? atoi(e) : 2; }();
+  if (mode == 2 && ring_launch(ctx, g, pg, pf, x, y, T.val, S.val, st, x_out, y_out)) {
+    PB_CHECK_LAUNCH();
+    ctx->launches++;
+    return;
+  }
+  if (mode >= 1 && tma_launch(ctx, g, pg, pf, x, y, T.val, S.val, st, x_out, y_out)) {
+    PB_CHECK_LAUNCH();
+    ctx->launches++;
+    return;
+  }
+#define PB_ARGS ctx, g, pg, pf, x, y, T.val, S.val, st, x_out, y_out
+  switch (shape) {
+    case 1: tile_launch_g<16, 256>(PB_ARGS); break;
+    case 2: tile_launch_g<8, 512>(PB_ARGS); break;
+    case 3: tile_launch_g<16, 128>(PB_ARGS); break;
+    default: tile_launch_g<32, 128>(PB_ARGS); break;
+  }
+#undef PB_ARGS
   PB_CHECK_LAUNCH();
   ctx->launches++;
 }

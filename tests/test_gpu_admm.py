@@ -21,8 +21,10 @@ CASES = admm_cases.medium()
 def test_admm_vs_oracle(ctx, name):
     fn, iters, opts, tol = CASES[name]
     desc = fn()
-    got = run_cuda_admm(ctx, desc, iters, tol=tol, **opts)
-    want = run_oracle_admm(desc, iters, tol=tol, **opts)
+    # with non-zero tolerances compare where Solver::Solve stops: past convergence the residual
+    # balancing keeps flipping rho on borderline float comparisons and trajectories decorrelate
+    got = run_cuda_admm(ctx, desc, iters, tol=tol, use_solver=tol is not admm_cases.TOL0, **opts)
+    want = run_oracle_admm(desc, got["iterations"], tol=tol, **opts)
     # the CG exit test |s| <= tol |s0| is a float comparison on sums whose order differs between the
     # SpMV implementations: an occasional borderline step more or less is legitimate
     assert abs(got["steps"][2] - want["steps"][2]) <= max(2, 0.01 * want["steps"][2]), \
