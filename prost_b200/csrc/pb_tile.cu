@@ -491,6 +491,10 @@ bool tma_launch(Context* ctx, const GradGeom& g, const ProxDesc& pg, const ProxD
 // mbarriers), so HBM streams continuously while the 32 warps compute the current tile.
 //   computed x+ region 32 columns x 128 rows = 1024 row vectors = exactly one per thread;
 //   owned tile         31 columns x 124 rows (the last column / 4 rows are the halo of the neighbours).
+// There is no CTA-wide barrier in the loop: warp w computes column w; its dual step only needs the
+// x+ of columns w and w+1, so it waits on column w+1's mbarrier; a stage is recycled when all 32
+// warps have arrived on its `empty` barrier, which warp 31 (it owns the halo column and has no dual
+// work) observes before it issues the next TMA loads.
 constexpr int kRingThreads = 1024;
 constexpr int kRingCols = 32, kRingRows = 128;          // computed region
 constexpr int kRingTX = kRingCols - 1, kRingTY = kRingRows - 4;   // owned tile
@@ -500,10 +504,25 @@ constexpr int kRingP2Bytes = kRingCols * kRingR2 * 4;
 constexpr int kRingXBytes = kRingCols * kRingRows * 4;
 constexpr int kRingStageBytes = kRingP1Bytes + kRingP2Bytes + 2 * kRingXBytes;
 constexpr int kRingStages = 2;
-constexpr int kRingOffXn = kRingStages * kRingStageBytes;
-constexpr int kRingOffBar = kRingOffXn + kRingXBytes;
-constexpr int kRingSmemBytes = kRingOffBar + 128;
+constexpr int kRingOffXn = kRingStages * kRingStageBytes;            // x+ tiles, one per stage
+constexpr int kRingOffBar = kRingOffXn + kRingStages * kRingXBytes;
+// mbarriers: full[stage] (TMA bytes landed), empty[stage] (all 32 warps done with the stage),
+// col_ready[stage][column] (that column's x+ is in shared memory).  Every barrier belongs to one stage, so
+// it can never run more than one phase ahead of a waiter (a stage is only refilled after ALL warps left it).
+constexpr int kRingSmemBytes = kRingOffBar + (2 * kRingStages + kRingStages * kRingCols) * 8 + 64;
 static_assert(kRingP1Bytes % 128 == 0 && kRingP2Bytes % 128 == 0 && kRingXBytes % 128 == 0, "TMA alignment");
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
 template <int FN_G, int FN_F>
 __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
@@ -513,8 +532,9 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
     const PdhgState* __restrict__ st, const uint32_t tiles_x, const uint32_t tiles_y, const uint32_t n_tiles,
     float* __restrict__ x_out, float* __restrict__ y_out) {
   extern __shared__ __align__(128) unsigned char smem[];
-  float (*s_xn)[kRingRows] = reinterpret_cast<float (*)[kRingRows]>(smem + kRingOffXn);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kRingOffBar);
+  uint64_t* empty = full + kRingStages;
+  uint64_t* col_ready = empty + kRingStages;
 
   const bool f_vec = pg.coeffs.ptr[1] != nullptr;
   const uint32_t stage_tx = kRingP1Bytes + kRingP2Bytes + kRingXBytes + (f_vec ? kRingXBytes : 0);
@@ -533,14 +553,19 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
     if (f_vec) tma_load_3d(base + kRingP1Bytes + kRingP2Bytes + kRingXBytes, &map_f, &full[s], cy, cx, (int)l);
   };
 
-  if (threadIdx.x == 0) {
+  const bool producer = threadIdx.x == kRingThreads - 32;     // lane 0 of warp 31
+  if (producer) {
 #pragma unroll
-    for (int s = 0; s < kRingStages; ++s)
+    for (int s = 0; s < kRingStages; ++s) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[s])));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 32;" ::"r"(smem_u32(&empty[s])));
+    }
+    for (int c = 0; c < kRingStages * kRingCols; ++c)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&col_ready[c])));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (producer) {
 #pragma unroll
     for (int s = 0; s < kRingStages; ++s) {
       const uint32_t t = blockIdx.x + s * gridDim.x;
@@ -574,15 +599,9 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
     float (*s_p2)[kRingR2] = reinterpret_cast<float (*)[kRingR2]>(base + kRingP1Bytes);
     float (*s_x)[kRingRows] = reinterpret_cast<float (*)[kRingRows]>(base + kRingP1Bytes + kRingP2Bytes);
     float (*s_f)[kRingRows] = reinterpret_cast<float (*)[kRingRows]>(base + kRingP1Bytes + kRingP2Bytes + kRingXBytes);
+    float (*s_xn)[kRingRows] = reinterpret_cast<float (*)[kRingRows]>(smem + kRingOffXn + s * kRingXBytes);
 
-    {
-      uint32_t done = 0;
-      while (!done) {
-        asm volatile(
-            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-            : "=r"(done) : "r"(smem_u32(&full[s])), "r"(parity) : "memory");
-      }
-    }
+    mbar_wait(&full[s], parity);
 
     const uint32_t gx = cx + col, gy = cy + r0;
     const uint32_t plane_off = l * g.nxny;
@@ -632,7 +651,10 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
       VecIO<4>::st(&s_xn[col][r0], xn);
       if (col < kRingTX && r0 < kRingTY && gy < g.ny) VecIO<4>::st(x_out + gy + gx * g.ny + plane_off, xn);
     }
-    __syncthreads();
+    // publish this column's x+ (one arrival per warp), then wait for the right neighbour's
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&col_ready[s * kRingCols + col]);
+    if (col < kRingTX) mbar_wait(&col_ready[s * kRingCols + col + 1], parity);
 
     // ---- phase B: y+ at the owned point (col, r0..r0+3) ---------------------------------------------------
     if (col < kRingTX && r0 < kRingTY && gx < g.nx && gy < g.ny) {
@@ -673,10 +695,15 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
       VecIO<4>::st(y_out + idx, arg[0]);
       VecIO<4>::st(y_out + (size_t)g.L * g.nxny + idx, arg[1]);
     }
-    __syncthreads();          // every thread is done with stage s and with s_xn
-    if (threadIdx.x == 0) {
+    // this warp is done with stage s (operand boxes and x+ tile)
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[s]);
+    if (col == kRingCols - 1) {       // warp 31 refills the stage once every warp has left it
       const uint32_t next = tile + kRingStages * gridDim.x;
-      if (next < n_tiles) issue(next, s);
+      if (next < n_tiles) {
+        mbar_wait(&empty[s], parity);
+        if (producer) issue(next, s);
+      }
     }
   }
 }
