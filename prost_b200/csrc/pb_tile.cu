@@ -513,11 +513,13 @@ constexpr int kRingSmemBytes = kRingOffBar + (2 * kRingStages + kRingStages * kR
 static_assert(kRingP1Bytes % 128 == 0 && kRingP2Bytes % 128 == 0 && kRingXBytes % 128 == 0, "TMA alignment");
 
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  // try_wait suspends the warp in hardware until the phase completes or the time hint (ns) expires,
+  // so a waiting warp costs (almost) no issue slots; the loop only covers the time-out case
   uint32_t done = 0;
   while (!done) {
     asm volatile(
-        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u) : "memory");
   }
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -529,8 +531,8 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
     const __grid_constant__ CUtensorMap map_p1, const __grid_constant__ CUtensorMap map_p2,
     const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_f, const GradGeom g,
     const ProxDesc pg, const ProxDesc pf, const float Tval, const float Sval,
-    const PdhgState* __restrict__ st, const uint32_t tiles_x, const uint32_t tiles_y, const uint32_t n_tiles,
-    float* __restrict__ x_out, float* __restrict__ y_out) {
+    const PdhgState* __restrict__ st, const FastDiv div_per_plane, const FastDiv div_tiles_y,
+    const uint32_t n_tiles, float* __restrict__ x_out, float* __restrict__ y_out) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kRingOffBar);
   uint64_t* empty = full + kRingStages;
@@ -538,11 +540,11 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
 
   const bool f_vec = pg.coeffs.ptr[1] != nullptr;
   const uint32_t stage_tx = kRingP1Bytes + kRingP2Bytes + kRingXBytes + (f_vec ? kRingXBytes : 0);
-  const uint32_t per_plane = tiles_x * tiles_y;
 
-  auto issue = [&](uint32_t tile, int s) {           // thread 0 only
-    const uint32_t l = tile / per_plane, rem = tile - l * per_plane;
-    const uint32_t tx = rem / tiles_y, ty = rem - tx * tiles_y;
+  auto issue = [&](uint32_t tile, int s) {           // producer lane only
+    uint32_t l, rem, tx, ty;
+    div_per_plane.divmod(tile, l, rem);
+    div_tiles_y.divmod(rem, tx, ty);
     const int cx = tx * kRingTX, cy = ty * kRingTY;
     unsigned char* base = smem + s * kRingStageBytes;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full[s])), "r"(stage_tx)
@@ -591,8 +593,9 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
     const int s = k % kRingStages;
     const uint32_t parity = (k / kRingStages) & 1u;
-    const uint32_t l = tile / per_plane, rem = tile - l * per_plane;
-    const uint32_t tx = rem / tiles_y, ty = rem - tx * tiles_y;
+    uint32_t l, rem, tx, ty;
+    div_per_plane.divmod(tile, l, rem);
+    div_tiles_y.divmod(rem, tx, ty);
     const int cx = tx * kRingTX, cy = ty * kRingTY;
     unsigned char* base = smem + s * kRingStageBytes;
     float (*s_p1)[kRingRows] = reinterpret_cast<float (*)[kRingRows]>(base);
@@ -608,25 +611,23 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
     // ---- phase A: x+ at (col, r0..r0+3) of the computed region ------------------------------------------
     if (gx < g.nx) {
       float xo[4], divx[4], o[4], a[4], xn[4];
+      // boundary rules as selects on always-valid shared-memory reads (no divergent regions):
+      // out-of-image box elements are TMA zero fill == the rule for x = -1 / y = -1 (x - 0 == x exactly)
       VecIO<4>::ld(&s_x[col][r0], xo);
-      if (gx < g.nx - 1) {
-        VecIO<4>::ld(&s_p1[col + 1][r0], divx);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) divx[j] = 0.f;
-      }
-      if (gx > 0) {
-        VecIO<4>::ld(&s_p1[col][r0], a);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) divx[j] -= a[j];
-      }
+      VecIO<4>::ld(&s_p1[col + 1][r0], divx);
+      VecIO<4>::ld(&s_p1[col][r0], a);
       VecIO<4>::ld(&s_p2[col][4 + r0], o);
+      const float up = s_p2[col][4 + r0 - 1];
+      const bool last_col = gx == g.nx - 1;
       float divy[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) divy[j] = (gy + j == g.ny - 1) ? 0.f : o[j];
+      for (int j = 0; j < 4; ++j) {
+        divx[j] = (last_col ? 0.f : divx[j]) - a[j];
+        divy[j] = (gy + j == g.ny - 1) ? 0.f : o[j];
+      }
+      divy[0] -= up;
 #pragma unroll
       for (int j = 1; j < 4; ++j) divy[j] -= o[j - 1];
-      if (gy > 0) divy[0] -= s_p2[col][4 + r0 - 1];
 #pragma unroll
       for (int j = 0; j < 4; ++j) xn[j] = primal_prox_arg(xo[j], tau, Tval, -(divx[j] + divy[j]));
       float bv[4];
@@ -663,25 +664,20 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
       float cn[4], co[4], rn[4], ro[4];
       VecIO<4>::ld(&s_xn[col][r0], cn);
       VecIO<4>::ld(&s_x[col][r0], co);
+      VecIO<4>::ld(&s_xn[col + 1][r0], rn);
+      VecIO<4>::ld(&s_x[col + 1][r0], ro);
+      const float dn = s_xn[col][r0 + 4], dold = s_x[col][r0 + 4];
+      const bool last_col = gx == g.nx - 1, last_row = gy + 4 >= g.ny;
       float k1x[4], k0x[4], k1y[4], k0y[4];
-      if (gx < g.nx - 1) {
-        VecIO<4>::ld(&s_xn[col + 1][r0], rn);
-        VecIO<4>::ld(&s_x[col + 1][r0], ro);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { k1x[j] = rn[j] - cn[j]; k0x[j] = ro[j] - co[j]; }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { k1x[j] = 0.f; k0x[j] = 0.f; }
+      for (int j = 0; j < 4; ++j) {          // grad_fwd: 0 on the last column
+        k1x[j] = last_col ? 0.f : rn[j] - cn[j];
+        k0x[j] = last_col ? 0.f : ro[j] - co[j];
       }
 #pragma unroll
       for (int j = 0; j < 3; ++j) { k1y[j] = cn[j + 1] - cn[j]; k0y[j] = co[j + 1] - co[j]; }
-      if (gy + 4 < g.ny) {
-        k1y[3] = s_xn[col][r0 + 4] - cn[3];
-        k0y[3] = s_x[col][r0 + 4] - co[3];
-      } else {
-        k1y[3] = 0.f;
-        k0y[3] = 0.f;
-      }
+      k1y[3] = last_row ? 0.f : dn - cn[3];   // 0 on the last row
+      k0y[3] = last_row ? 0.f : dold - co[3];
       float y1[4], y2[4];
       VecIO<4>::ld(&s_p1[col + 1][r0], y1);
       VecIO<4>::ld(&s_p2[col][4 + r0], y2);
@@ -724,8 +720,9 @@ bool ring_launch_fn(Context* ctx, const CUtensorMap& mp1, const CUtensorMap& mp2
   const uint64_t n_tiles = (uint64_t)tiles_x * tiles_y * g.L;
   if (n_tiles >= (1ull << 31)) return false;
   const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)ctx->num_sms);
-  kernel<<<grid, kRingThreads, kRingSmemBytes, ctx->stream>>>(mp1, mp2, mx, mf, g, pg, pf, Tval, Sval, st, tiles_x,
-                                                              tiles_y, (uint32_t)n_tiles, x_out, y_out);
+  kernel<<<grid, kRingThreads, kRingSmemBytes, ctx->stream>>>(mp1, mp2, mx, mf, g, pg, pf, Tval, Sval, st,
+                                                              FastDiv((uint64_t)tiles_x * tiles_y), FastDiv(tiles_y),
+                                                              (uint32_t)n_tiles, x_out, y_out);
   return true;
 }
 
