@@ -39,6 +39,8 @@ BYTES_PER_PX_PRIMAL = 20
 BYTES_PER_PX_DUAL = 24
 # one-pass tiled iteration (pb_tile.cu): read y (2N), x (N), f (N); write x+ (N), y+ (2N) = 7 floats
 BYTES_PER_PX_TILE = 28
+# the same pass on residual-refresh iterations also reads the previous dual iterate (2N): 9 floats
+BYTES_PER_PX_TILE_CHECK = 36
 
 
 def measured_peak():
@@ -373,26 +375,34 @@ def main():
     if tiled:
         kernel_bytes = BYTES_PER_PX_TILE * n
         kernel_ms = d["tile_ms"]
-        kernel_name = "grad2d_iteration_tile_kernel<SQUARE, IND_LEQ0> (whole PDHG iteration, one pass)"
+        kernel_name = ("grad2d_iteration_ring_kernel<SQUARE, IND_LEQ0, CHECK=false> (whole PDHG iteration in one "
+                       "pass, persistent TMA ring)")
     else:
         kernel_bytes = BYTES_PER_PX_DUAL * n
         kernel_ms = d["dual_ms"]
         kernel_name = "grad_dual_norm2_kernel (fused dual pass)"
     achieved = kernel_bytes / (kernel_ms * 1e-3) / 1e9
-    frac_tile = d["n_tile"] / max(d["n_tile"] + d["n_two_pass"], 1.0)
-    iter_bytes = (frac_tile * BYTES_PER_PX_TILE + (1 - frac_tile) * BYTES_PER_PX_ITER) * n
+    n_all = max(d["n_tile"] + d["n_two_pass"] + d["n_tile_check"], 1.0)
+    frac_tile, frac_chk, frac_two = d["n_tile"] / n_all, d["n_tile_check"] / n_all, d["n_two_pass"] / n_all
+    iter_bytes = (frac_tile * BYTES_PER_PX_TILE + frac_chk * BYTES_PER_PX_TILE_CHECK + frac_two * BYTES_PER_PX_ITER) * n
     achieved_iter = iter_bytes * value / 1e9
     roofline = {
         "bound": "hbm", "kernel": kernel_name,
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": None, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": kernel_bytes, "ms_per_launch": kernel_ms,
-        "launch_share": frac_tile if tiled else 1 - frac_tile,
+        "launch_share": frac_tile if tiled else frac_two,
+        "residual_refresh_iterations": {
+            "share": frac_chk, "kernel": "grad2d_iteration_ring_kernel<..., CHECK=true>",
+            "ms_per_launch": d["tile_check_ms"], "algorithmic_bytes_per_launch": BYTES_PER_PX_TILE_CHECK * n,
+            "achieved": (BYTES_PER_PX_TILE_CHECK * n / (d["tile_check_ms"] * 1e-3) / 1e9) if d["tile_check_ms"] else None,
+            "note": "1 in residual_iter iterations: the same pass also reads the previous dual iterate and "
+                    "accumulates the four residual sums; included in value"},
         "two_pass_iterations": {
-            "share": 1 - frac_tile,
+            "share": frac_two,
             "primal_pass": {"ms_per_launch": d["primal_ms"], "algorithmic_bytes_per_launch": BYTES_PER_PX_PRIMAL * n},
             "dual_pass": {"ms_per_launch": d["dual_ms"], "algorithmic_bytes_per_launch": BYTES_PER_PX_DUAL * n},
-            "note": "residual-refresh iterations (they also read the previous dual iterate); included in value"},
+            "note": "iteration 0 only (K^T y := 0, K x_prev := 0 special cases)"},
         "whole_iteration": {"algorithmic_bytes": iter_bytes, "achieved": achieved_iter, "frac": achieved_iter / peak,
                             "frac_of_8TBs_nominal": achieved_iter / 8000.0},
         # the same iterations/s expressed against SURVEY.md 8(d)'s two-pass minimum of 44 B/px

@@ -275,8 +275,9 @@ unsigned long long pb_backend_launch_count(const pb_backend* b);
 int pb_backend_profile(pb_backend* b, int n_iters, float out_ms[3]);
 /* Same, split by kernel schedule (PDHG, fused mode): out = { primal pass ms, dual pass ms (averages over
  * the iterations that ran as two passes), finalize ms (average over all), whole-iteration tiled kernel
- * ms (average over the iterations that ran as ONE tiled pass), #two-pass iterations, #tiled iterations } */
-int pb_backend_profile_detail(pb_backend* b, int n_iters, float out[6]);
+ * ms (average over the tiled iterations that do not refresh the residuals), #two-pass iterations, #such
+ * tiled iterations, tiled residual-refresh kernel ms, #tiled residual-refresh iterations } */
+int pb_backend_profile_detail(pb_backend* b, int n_iters, float out[8]);
 /* device pointers of the current iterates (x: ncols, y: nrows) for zero-copy callers */
 int pb_backend_device_iterates(pb_backend* b, float** d_x, float** d_y);
 

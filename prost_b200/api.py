@@ -441,10 +441,12 @@ class Backend(_Handle):
         return float(out[0]), float(out[1]), float(out[2])
 
     def profile_detail(self, n=1):
-        """dict(primal_ms, dual_ms, finalize_ms, tile_ms, n_two_pass, n_tile): see pb_backend_profile_detail."""
-        out = (C.c_float * 6)()
+        """dict(primal_ms, dual_ms, finalize_ms, tile_ms, n_two_pass, n_tile, tile_check_ms, n_tile_check):
+        see pb_backend_profile_detail."""
+        out = (C.c_float * 8)()
         check(lib.pb_backend_profile_detail(self._h, n, out))
-        keys = ["primal_ms", "dual_ms", "finalize_ms", "tile_ms", "n_two_pass", "n_tile"]
+        keys = ["primal_ms", "dual_ms", "finalize_ms", "tile_ms", "n_two_pass", "n_tile", "tile_check_ms",
+                "n_tile_check"]
         return dict(zip(keys, [float(v) for v in out]))
 
     def residuals(self):

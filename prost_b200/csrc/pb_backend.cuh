@@ -93,9 +93,9 @@ class Backend {
   virtual void initialize(const float* h_x0, size_t nx0, const float* h_y0, size_t ny0) = 0;
   virtual void iterate(int n_iters) = 0;
   virtual void profile(int n_iters, float out_ms[3]) { iterate(n_iters); out_ms[0] = out_ms[1] = out_ms[2] = 0.f; }
-  virtual void profile_detail(int n_iters, float out[6]) {
+  virtual void profile_detail(int n_iters, float out[8]) {
     profile(n_iters, out);
-    out[3] = 0.f; out[4] = static_cast<float>(n_iters); out[5] = 0.f;
+    out[3] = 0.f; out[4] = static_cast<float>(n_iters); out[5] = out[6] = out[7] = 0.f;
   }
   // primal_residual, dual_residual, primal_var_norm, dual_var_norm, eps_primal, eps_dual
   virtual void residuals(float out[6]) = 0;

@@ -488,7 +488,7 @@ int pb_backend_iterate(pb_backend* b, int n_iters) {
 int pb_backend_profile(pb_backend* b, int n_iters, float out_ms[3]) {
   return guarded([&] { require(b && out_ms, "NULL argument"); b->impl->profile(n_iters, out_ms); });
 }
-int pb_backend_profile_detail(pb_backend* b, int n_iters, float out[6]) {
+int pb_backend_profile_detail(pb_backend* b, int n_iters, float out[8]) {
   return guarded([&] { require(b && out, "NULL argument"); b->impl->profile_detail(n_iters, out); });
 }
 int pb_backend_residuals(pb_backend* b, float out[6]) {

@@ -206,14 +206,14 @@ class BackendPDHG : public Backend {
   void initialize(const float* h_x0, size_t nx0, const float* h_y0, size_t ny0) override;
   void iterate(int n_iters) override;
   void profile(int n_iters, float out_ms[3]) override;
-  void profile_detail(int n_iters, float out[6]) override;
+  void profile_detail(int n_iters, float out[8]) override;
   void residuals(float out[6]) override;
   void stepsizes(double out[3]) override;
   size_t iteration() const override { return iteration_; }
   void current_solution(float* h_x, float* h_z, float* h_y, float* h_w) override;
   size_t gpu_mem_amount() const override {
     const size_t m = problem_->nrows(), n = problem_->ncols();
-    if (fused_) return 2 * (n + m) * sizeof(float);
+    if (fused_) return (2 * (n + m) + (tile_ok_ ? m : 0)) * sizeof(float);
     return (4 * (n + m) + std::max(n, m)) * sizeof(float);     // backend_pdhg.cu:503-511
   }
   bool is_fused() const override { return fused_; }
@@ -245,11 +245,17 @@ class BackendPDHG : public Backend {
   ProxList prox_g_, prox_fstar_;
   bool fused_ = false;
   bool tile_ok_ = false;               // non-check iterations run as one tiled pass (pb_tile.cu)
-  unsigned long long tile_iterations_ = 0;
+  unsigned long long tile_iterations_ = 0, tile_check_iterations_ = 0;
   unsigned long long iteration_ = 0;
 
   // iterates: x_/y_ current, x_prev_/y_prev_ previous (ping-pong in fused mode)
   DeviceBuffer<float> x_, x_prev_, y_, y_prev_;
+  // third dual buffer for tiled residual-refresh iterations (they read y^k AND y^{k-1} while writing y^{k+1})
+  DeviceBuffer<float> y_stage_;
+  float* y_prev_staging() {
+    if (y_stage_.size() != y_.size()) y_stage_.resize(y_.size());
+    return y_stage_.data();
+  }
   // unfused only
   DeviceBuffer<float> temp_, kx_, kx_prev_, kty_, kty_prev_;
   // fused plan
@@ -390,6 +396,7 @@ void BackendPDHG::initialize(const float* h_x0, size_t nx0, const float* h_y0, s
   }
   try {
     x_.resize(n); x_prev_.resize(n); y_.resize(m); y_prev_.resize(m);
+    if (tile_ok_) y_stage_.resize(m);
     if (!fused_) {
       temp_.resize(std::max(m, n));
       kx_.resize(m); kx_prev_.resize(m); kty_.resize(n); kty_prev_.resize(n);
@@ -437,7 +444,25 @@ void BackendPDHG::iteration_fused() {
   const PdhgState* st = d_state_.data();
 
   unsigned nd = 0, np = 0;
-  if (tile_ok_ && !check && iteration_ > 0) {
+  unsigned tiled_check = 0;
+  if (tile_ok_ && check && iteration_ > 0)
+    tiled_check = tile_check_iteration_launch(ctx_, stencil_, g_descs_[0], f_descs_[0], x_.data(), y_.data(),
+                                              y_prev_.data(), T, S, st, iteration_ <= 1, part_d_.data(),
+                                              part_p_.data(), x_prev_.data(), y_prev_staging());
+  if (tiled_check) {
+    // residual-refresh iteration in one pass: x_prev_ <- x^{k+1}; y^{k+1} cannot overwrite y_prev_ (the
+    // pass reads y^{k-1} from it), so it goes to a third buffer that then takes y_prev_'s place
+    nd = np = tiled_check;
+    tile_check_iterations_++;
+    x_.swap(x_prev_);
+    y_prev_.swap(y_stage_);      // y_prev_ now holds y^{k+1}, y_stage_ the dead y^{k-1}
+    y_.swap(y_prev_);            // y_ = y^{k+1}, y_prev_ = y^k
+    tile_iterations_++;
+    if (prof_ev_) {
+      PB_CUDA(cudaEventRecord(prof_ev_[1], ctx_->stream));
+      PB_CUDA(cudaEventRecord(prof_ev_[2], ctx_->stream));
+    }
+  } else if (tile_ok_ && !check && iteration_ > 0) {
     // whole iteration in one pass over HBM (pb_tile.cu): x_prev_ <- x^{k+1}, y_prev_ <- y^{k+1}
     tile_iteration_launch(ctx_, stencil_, g_descs_[0], f_descs_[0], x_.data(), y_.data(), T, S, st,
                           x_prev_.data(), y_prev_.data());
@@ -614,36 +639,38 @@ void BackendPDHG::iteration_unfused() {
 }
 
 void BackendPDHG::profile(int n_iters, float out_ms[3]) {
-  float d[6];
+  float d[8];
   profile_detail(n_iters, d);
   // averages over ALL profiled iterations (tiled iterations count as "primal pass" time)
-  const float n2 = d[4], nt = d[5], n = n2 + nt;
-  out_ms[0] = n > 0 ? (d[0] * n2 + d[3] * nt) / n : 0.f;
+  const float n2 = d[4], nt = d[5], nc = d[7], n = n2 + nt + nc;
+  out_ms[0] = n > 0 ? (d[0] * n2 + d[3] * nt + d[6] * nc) / n : 0.f;
   out_ms[1] = n > 0 ? d[1] * n2 / n : 0.f;
   out_ms[2] = n > 0 ? d[2] : 0.f;
 }
 
 // out = { primal pass ms, dual pass ms (both averaged over the two-pass iterations), finalize ms
-// (averaged over all), tiled whole-iteration kernel ms (averaged over the tiled iterations),
-// number of two-pass iterations, number of tiled iterations }
-void BackendPDHG::profile_detail(int n_iters, float out[6]) {
+// (averaged over all), tiled whole-iteration kernel ms (averaged over the tiled iterations that do not
+// refresh the residuals), number of two-pass iterations, number of such tiled iterations, tiled
+// residual-refresh kernel ms, number of tiled residual-refresh iterations }
+void BackendPDHG::profile_detail(int n_iters, float out[8]) {
   ctx_->bind();
-  for (int k = 0; k < 6; ++k) out[k] = 0.f;
+  for (int k = 0; k < 8; ++k) out[k] = 0.f;
   if (!fused_ || n_iters <= 0) { iterate(n_iters); return; }
   cudaEvent_t ev[4];
   for (auto& e : ev) PB_CUDA(cudaEventCreate(&e));
   prof_ev_ = ev;
-  double acc[4] = {0, 0, 0, 0};
-  int n_two = 0, n_tile = 0;
+  double acc[5] = {0, 0, 0, 0, 0};
+  int n_two = 0, n_tile = 0, n_chk = 0;
   for (int i = 0; i < n_iters; ++i) {
-    const unsigned long long tiles_before = tile_iterations_;
+    const unsigned long long tiles_before = tile_iterations_, chk_before = tile_check_iterations_;
     PB_CUDA(cudaEventRecord(ev[0], ctx_->stream));
     iteration_fused();
     PB_CUDA(cudaEventRecord(ev[3], ctx_->stream));
     PB_CUDA(cudaEventSynchronize(ev[3]));
     float ms[3];
     for (int k = 0; k < 3; ++k) PB_CUDA(cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]));
-    if (tile_iterations_ != tiles_before) { acc[3] += ms[0]; ++n_tile; }
+    if (tile_check_iterations_ != chk_before) { acc[4] += ms[0]; ++n_chk; }
+    else if (tile_iterations_ != tiles_before) { acc[3] += ms[0]; ++n_tile; }
     else { acc[0] += ms[0]; acc[1] += ms[1]; ++n_two; }
     acc[2] += ms[2];
   }
@@ -655,6 +682,8 @@ void BackendPDHG::profile_detail(int n_iters, float out[6]) {
   out[3] = n_tile ? static_cast<float>(acc[3] / n_tile) : 0.f;
   out[4] = static_cast<float>(n_two);
   out[5] = static_cast<float>(n_tile);
+  out[6] = n_chk ? static_cast<float>(acc[4] / n_chk) : 0.f;
+  out[7] = static_cast<float>(n_chk);
 }
 
 void BackendPDHG::iterate(int n_iters) {

@@ -647,5 +647,11 @@ bool tile_iteration_supported(const StencilPlan& plan, const std::vector<ProxDes
 void tile_iteration_launch(Context* ctx, const StencilPlan& plan, const ProxDesc& pg, const ProxDesc& pf,
                            const float* x, const float* y, ScaleRef T, ScaleRef S, const PdhgState* st,
                            float* x_out, float* y_out);
+// residual-refresh iteration as one tiled pass; returns the number of (a, b) partial pairs written to each of
+// part_d (dual residual sums) and part_p (primal residual sums), 0 if the two-pass kernels have to run
+unsigned tile_check_iteration_launch(Context* ctx, const StencilPlan& plan, const ProxDesc& pg, const ProxDesc& pf,
+                                     const float* x, const float* y, const float* y_prev, ScaleRef T, ScaleRef S,
+                                     const PdhgState* st, bool ktyprev_zero, double* part_d, double* part_p,
+                                     float* x_out, float* y_out, bool dry_run = false);
 
 }  // namespace pb

@@ -502,7 +502,9 @@ constexpr int kRingR2 = kRingRows + 4;                  // p2 box rows (starts 4
 constexpr int kRingP1Bytes = (kRingCols + 1) * kRingRows * 4;
 constexpr int kRingP2Bytes = kRingCols * kRingR2 * 4;
 constexpr int kRingXBytes = kRingCols * kRingRows * 4;
-constexpr int kRingStageBytes = kRingP1Bytes + kRingP2Bytes + 2 * kRingXBytes;
+// stage contents: [p1][p2][x][f]; residual-refresh launches (CHECK) stage the previous dual iterate's
+// boxes [q1][q2] instead of f (which they read from global memory) so that two stages still fit
+constexpr int kRingStageBytes = 2 * (kRingP1Bytes + kRingP2Bytes) + kRingXBytes;
 constexpr int kRingStages = 2;
 constexpr int kRingOffXn = kRingStages * kRingStageBytes;            // x+ tiles, one per stage
 constexpr int kRingOffBar = kRingOffXn + kRingStages * kRingXBytes;
@@ -526,20 +528,27 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int FN_G, int FN_F>
+// CHECK: this iteration refreshes the residuals (backend_pdhg.cu:73-120, 383-436): the same pass also
+// gathers K^T y_prev from the previous dual iterate (map_q1 / map_q2) and accumulates the four residual
+// sums in double, one (a, b) pair per CTA for each of the two residuals.
+template <int FN_G, int FN_F, bool CHECK>
 __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
     const __grid_constant__ CUtensorMap map_p1, const __grid_constant__ CUtensorMap map_p2,
-    const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_f, const GradGeom g,
+    const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_f,
+    const __grid_constant__ CUtensorMap map_q1, const __grid_constant__ CUtensorMap map_q2, const GradGeom g,
     const ProxDesc pg, const ProxDesc pf, const float Tval, const float Sval,
     const PdhgState* __restrict__ st, const FastDiv div_per_plane, const FastDiv div_tiles_y,
-    const uint32_t n_tiles, float* __restrict__ x_out, float* __restrict__ y_out) {
+    const uint32_t n_tiles, const int ktyprev_zero, double* __restrict__ part_d, double* __restrict__ part_p,
+    float* __restrict__ x_out, float* __restrict__ y_out) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kRingOffBar);
   uint64_t* empty = full + kRingStages;
   uint64_t* col_ready = empty + kRingStages;
 
   const bool f_vec = pg.coeffs.ptr[1] != nullptr;
-  const uint32_t stage_tx = kRingP1Bytes + kRingP2Bytes + kRingXBytes + (f_vec ? kRingXBytes : 0);
+  const bool q_boxes = CHECK && !ktyprev_zero;
+  const uint32_t stage_tx = kRingP1Bytes + kRingP2Bytes + kRingXBytes +
+                            (CHECK ? (q_boxes ? kRingP1Bytes + kRingP2Bytes : 0) : (f_vec ? kRingXBytes : 0));
 
   auto issue = [&](uint32_t tile, int s) {           // producer lane only
     uint32_t l, rem, tx, ty;
@@ -552,7 +561,15 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
     tma_load_3d(base, &map_p1, &full[s], cy, cx - 1, (int)l);
     tma_load_3d(base + kRingP1Bytes, &map_p2, &full[s], cy - 4, cx, (int)(g.L + l));
     tma_load_3d(base + kRingP1Bytes + kRingP2Bytes, &map_x, &full[s], cy, cx, (int)l);
-    if (f_vec) tma_load_3d(base + kRingP1Bytes + kRingP2Bytes + kRingXBytes, &map_f, &full[s], cy, cx, (int)l);
+    if (CHECK) {
+      if (q_boxes) {
+        tma_load_3d(base + kRingP1Bytes + kRingP2Bytes + kRingXBytes, &map_q1, &full[s], cy, cx - 1, (int)l);
+        tma_load_3d(base + 2 * kRingP1Bytes + kRingP2Bytes + kRingXBytes, &map_q2, &full[s], cy - 4, cx,
+                    (int)(g.L + l));
+      }
+    } else if (f_vec) {
+      tma_load_3d(base + kRingP1Bytes + kRingP2Bytes + kRingXBytes, &map_f, &full[s], cy, cx, (int)l);
+    }
   };
 
   const bool producer = threadIdx.x == kRingThreads - 32;     // lane 0 of warp 31
@@ -588,6 +605,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
 
   const int col = threadIdx.x >> 5;          // warp = column of the computed region
   const int r0 = (threadIdx.x & 31) * 4;     // lane = row vector
+  double acc_d0 = 0.0, acc_d1 = 0.0, acc_p0 = 0.0, acc_p1 = 0.0;
 
   uint32_t k = 0;
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
@@ -602,6 +620,8 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
     float (*s_p2)[kRingR2] = reinterpret_cast<float (*)[kRingR2]>(base + kRingP1Bytes);
     float (*s_x)[kRingRows] = reinterpret_cast<float (*)[kRingRows]>(base + kRingP1Bytes + kRingP2Bytes);
     float (*s_f)[kRingRows] = reinterpret_cast<float (*)[kRingRows]>(base + kRingP1Bytes + kRingP2Bytes + kRingXBytes);
+    float (*s_q1)[kRingRows] = reinterpret_cast<float (*)[kRingRows]>(base + kRingP1Bytes + kRingP2Bytes + kRingXBytes);
+    float (*s_q2)[kRingR2] = reinterpret_cast<float (*)[kRingR2]>(base + 2 * kRingP1Bytes + kRingP2Bytes + kRingXBytes);
     float (*s_xn)[kRingRows] = reinterpret_cast<float (*)[kRingRows]>(smem + kRingOffXn + s * kRingXBytes);
 
     mbar_wait(&full[s], parity);
@@ -632,7 +652,13 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
       for (int j = 0; j < 4; ++j) xn[j] = primal_prox_arg(xo[j], tau, Tval, -(divx[j] + divy[j]));
       float bv[4];
       if (f_vec) {
-        VecIO<4>::ld(&s_f[col][r0], bv);
+        if (CHECK) {
+          // rows beyond the image are never used; clamp the address instead of predicating the load
+          const uint32_t gyc = gy < g.ny ? gy : 0u;
+          VecIO<4>::ld(pg.coeffs.ptr[1] + gyc + gx * g.ny + plane_off, bv);
+        } else {
+          VecIO<4>::ld(&s_f[col][r0], bv);
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j) bv[j] = cg.v[1];
@@ -650,7 +676,44 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
         }
       }
       VecIO<4>::st(&s_xn[col][r0], xn);
-      if (col < kRingTX && r0 < kRingTY && gy < g.ny) VecIO<4>::st(x_out + gy + gx * g.ny + plane_off, xn);
+      if (col < kRingTX && r0 < kRingTY && gy < g.ny) {
+        VecIO<4>::st(x_out + gy + gx * g.ny + plane_off, xn);
+        if (CHECK) {
+          // dual residual on the owned pixels: w^ = (x - x+)/(tau sqrt T) - sqrt T K^T y_prev,
+          // diff = w^ + sqrt T K^T y
+          float kp[4];
+          if (q_boxes) {
+            float qx[4], qa[4], qo[4];
+            VecIO<4>::ld(&s_q1[col + 1][r0], qx);
+            VecIO<4>::ld(&s_q1[col][r0], qa);
+            VecIO<4>::ld(&s_q2[col][4 + r0], qo);
+            const float qup = s_q2[col][4 + r0 - 1];
+            float qy[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              qx[j] = (last_col ? 0.f : qx[j]) - qa[j];
+              qy[j] = (gy + j == g.ny - 1) ? 0.f : qo[j];
+            }
+            qy[0] -= qup;
+#pragma unroll
+            for (int j = 1; j < 4; ++j) qy[j] -= qo[j - 1];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) kp[j] = -(qx[j] + qy[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) kp[j] = 0.f;
+          }
+          const float sq = sqrtf(Tval);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float kk = -(divx[j] + divy[j]);
+            const float w_hat = (xo[j] - xn[j]) / (tau * sq) - sq * kp[j];
+            const float diff = w_hat + sq * kk;
+            acc_d0 += static_cast<double>(diff * diff);
+            acc_d1 += static_cast<double>(w_hat * w_hat);
+          }
+        }
+      }
     }
     // publish this column's x+ (one arrival per warp), then wait for the right neighbour's
     __syncwarp();
@@ -690,6 +753,22 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
       else norm2_lanes<4, 2, false>(fn_f, arg, cf, tau_f);
       VecIO<4>::st(y_out + idx, arg[0]);
       VecIO<4>::st(y_out + (size_t)g.L * g.nxny + idx, arg[1]);
+      if (CHECK) {
+        // primal residual: z^ = (y - y+)/(sigma sqrt S) + sqrt S ((1+theta) K x+ - theta K x),
+        // diff = z^ - sqrt S K x+
+        const float sq = sqrtf(Sval);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float ex = dual_extrapolate(theta, k1x[j], k0x[j]);
+          const float zx = (y1[j] - arg[0][j]) / (sigma * sq) + sq * ex;
+          const float dx = zx - sq * k1x[j];
+          const float ey = dual_extrapolate(theta, k1y[j], k0y[j]);
+          const float zy = (y2[j] - arg[1][j]) / (sigma * sq) + sq * ey;
+          const float dy = zy - sq * k1y[j];
+          acc_p0 += static_cast<double>(dx * dx) + static_cast<double>(dy * dy);
+          acc_p1 += static_cast<double>(zx * zx) + static_cast<double>(zy * zy);
+        }
+      }
     }
     // this warp is done with stage s (operand boxes and x+ tile)
     __syncwarp();
@@ -702,39 +781,75 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
       }
     }
   }
+  if (CHECK) {
+    block_sum2(acc_d0, acc_d1);
+    block_sum2(acc_p0, acc_p1);
+    if (threadIdx.x == 0) {
+      part_d[2 * blockIdx.x] = acc_d0; part_d[2 * blockIdx.x + 1] = acc_d1;
+      part_p[2 * blockIdx.x] = acc_p0; part_p[2 * blockIdx.x + 1] = acc_p1;
+    }
+  }
 }
 
-template <int FN_G, int FN_F>
-bool ring_launch_fn(Context* ctx, const CUtensorMap& mp1, const CUtensorMap& mp2, const CUtensorMap& mx,
-                    const CUtensorMap& mf, const GradGeom& g, const ProxDesc& pg, const ProxDesc& pf, float Tval,
-                    float Sval, const PdhgState* st, float* x_out, float* y_out) {
-  auto kernel = grad2d_iteration_ring_kernel<FN_G, FN_F>;
+struct RingArgs {
+  CUtensorMap mp1, mp2, mx, mf, mq1, mq2;
+  bool check = false;
+  int ktyprev_zero = 1;
+  double* part_d = nullptr;
+  double* part_p = nullptr;
+};
+
+template <int FN_G, int FN_F, bool CHECK>
+unsigned ring_launch_k(Context* ctx, const RingArgs& a, const GradGeom& g, const ProxDesc& pg, const ProxDesc& pf,
+                       float Tval, float Sval, const PdhgState* st, float* x_out, float* y_out, bool dry_run) {
+  auto kernel = grad2d_iteration_ring_kernel<FN_G, FN_F, CHECK>;
   static bool configured = false, ok = false;
   if (!configured) {
     configured = true;
     ok = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingSmemBytes) == cudaSuccess;
     cudaGetLastError();
   }
-  if (!ok) return false;
+  if (!ok) return 0;
   const uint32_t tiles_x = (g.nx + kRingTX - 1) / kRingTX, tiles_y = (g.ny + kRingTY - 1) / kRingTY;
   const uint64_t n_tiles = (uint64_t)tiles_x * tiles_y * g.L;
-  if (n_tiles >= (1ull << 31)) return false;
+  if (n_tiles == 0 || n_tiles >= (1ull << 31)) return 0;
   const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)ctx->num_sms);
-  kernel<<<grid, kRingThreads, kRingSmemBytes, ctx->stream>>>(mp1, mp2, mx, mf, g, pg, pf, Tval, Sval, st,
-                                                              FastDiv((uint64_t)tiles_x * tiles_y), FastDiv(tiles_y),
-                                                              (uint32_t)n_tiles, x_out, y_out);
-  return true;
+  if (dry_run) return grid;
+  kernel<<<grid, kRingThreads, kRingSmemBytes, ctx->stream>>>(
+      a.mp1, a.mp2, a.mx, a.mf, a.mq1, a.mq2, g, pg, pf, Tval, Sval, st, FastDiv((uint64_t)tiles_x * tiles_y),
+      FastDiv(tiles_y), (uint32_t)n_tiles, a.ktyprev_zero, a.part_d, a.part_p, x_out, y_out);
+  return grid;
 }
 
-bool ring_launch(Context* ctx, const GradGeom& g, const ProxDesc& pg, const ProxDesc& pf, const float* x,
-                 const float* y, float Tval, float Sval, const PdhgState* st, float* x_out, float* y_out) {
-  CUtensorMap mp1, mp2, mx, mf;
-  if (!tensor_map_for(y, g.ny, g.nx, 2 * g.L, kRingRows, kRingCols + 1, mp1)) return false;
-  if (!tensor_map_for(y, g.ny, g.nx, 2 * g.L, kRingR2, kRingCols, mp2)) return false;
-  if (!tensor_map_for(x, g.ny, g.nx, g.L, kRingRows, kRingCols, mx)) return false;
-  const float* f = pg.coeffs.ptr[1] ? pg.coeffs.ptr[1] : x;      // unused when b is a scalar
-  if (!tensor_map_for(f, g.ny, g.nx, g.L, kRingRows, kRingCols, mf)) return false;
-#define PB_ARGS ctx, mp1, mp2, mx, mf, g, pg, pf, Tval, Sval, st, x_out, y_out
+template <int FN_G, int FN_F>
+unsigned ring_launch_fn(Context* ctx, const RingArgs& a, const GradGeom& g, const ProxDesc& pg, const ProxDesc& pf,
+                        float Tval, float Sval, const PdhgState* st, float* x_out, float* y_out, bool dry_run) {
+  if (a.check) return ring_launch_k<FN_G, FN_F, true>(ctx, a, g, pg, pf, Tval, Sval, st, x_out, y_out, dry_run);
+  return ring_launch_k<FN_G, FN_F, false>(ctx, a, g, pg, pf, Tval, Sval, st, x_out, y_out, dry_run);
+}
+
+// returns the number of CTAs (= residual partial pairs per residual when check), 0 if not launched
+unsigned ring_launch(Context* ctx, const GradGeom& g, const ProxDesc& pg, const ProxDesc& pf, const float* x,
+                     const float* y, const float* y_prev, float Tval, float Sval, const PdhgState* st, bool check,
+                     bool ktyprev_zero, double* part_d, double* part_p, float* x_out, float* y_out, bool dry_run) {
+  RingArgs a;
+  a.check = check;
+  a.ktyprev_zero = ktyprev_zero ? 1 : 0;
+  a.part_d = part_d;
+  a.part_p = part_p;
+  if (!dry_run) {
+    if (!tensor_map_for(y, g.ny, g.nx, 2 * g.L, kRingRows, kRingCols + 1, a.mp1)) return 0;
+    if (!tensor_map_for(y, g.ny, g.nx, 2 * g.L, kRingR2, kRingCols, a.mp2)) return 0;
+    if (!tensor_map_for(x, g.ny, g.nx, g.L, kRingRows, kRingCols, a.mx)) return 0;
+    const float* f = pg.coeffs.ptr[1] ? pg.coeffs.ptr[1] : x;      // unused when b is a scalar
+    if (!tensor_map_for(f, g.ny, g.nx, g.L, kRingRows, kRingCols, a.mf)) return 0;
+    const float* q = (check && !ktyprev_zero) ? y_prev : y;         // unused otherwise
+    if (!tensor_map_for(q, g.ny, g.nx, 2 * g.L, kRingRows, kRingCols + 1, a.mq1)) return 0;
+    if (!tensor_map_for(q, g.ny, g.nx, 2 * g.L, kRingR2, kRingCols, a.mq2)) return 0;
+  } else if (!encode_tiled_fn()) {
+    return 0;
+  }
+#define PB_ARGS ctx, a, g, pg, pf, Tval, Sval, st, x_out, y_out, dry_run
   const bool leq0 = pf.fn == PB_FUN_IND_LEQ0;
   if (pg.fn == PB_FUN_SQUARE) return leq0 ? ring_launch_fn<PB_FUN_SQUARE, PB_FUN_IND_LEQ0>(PB_ARGS) : ring_launch_fn<PB_FUN_SQUARE, -1>(PB_ARGS);
   if (pg.fn == PB_FUN_ABS) return leq0 ? ring_launch_fn<PB_FUN_ABS, PB_FUN_IND_LEQ0>(PB_ARGS) : ring_launch_fn<PB_FUN_ABS, -1>(PB_ARGS);
@@ -771,6 +886,28 @@ bool tile_iteration_supported(const StencilPlan& plan, const std::vector<ProxDes
   return true;
 }
 
+static int tile_mode() {
+  // PB_TILE_MODE: 2 (default) persistent TMA ring, 1 one-shot TMA tiles, 0 plain loads (A/B experiments)
+  static const int mode = [] { const char* e = getenv("PB_TILE_MODE"); return e ? atoi(e) : 2; }();
+  return mode;
+}
+
+// Residual-refresh iteration as one tiled pass (persistent ring only).  Returns the number of partial
+// pairs written to EACH of part_d / part_p, or 0 when the caller has to run the two-pass kernels.
+unsigned tile_check_iteration_launch(Context* ctx, const StencilPlan& plan, const ProxDesc& pg, const ProxDesc& pf,
+                                     const float* x, const float* y, const float* y_prev, ScaleRef T, ScaleRef S,
+                                     const PdhgState* st, bool ktyprev_zero, double* part_d, double* part_p,
+                                     float* x_out, float* y_out, bool dry_run) {
+  if (tile_mode() != 2) return 0;
+  const unsigned n = ring_launch(ctx, plan.geom, pg, pf, x, y, y_prev, T.val, S.val, st, true, ktyprev_zero, part_d,
+                                 part_p, x_out, y_out, dry_run);
+  if (n && !dry_run) {
+    PB_CHECK_LAUNCH();
+    ctx->launches++;
+  }
+  return n;
+}
+
 void tile_iteration_launch(Context* ctx, const StencilPlan& plan, const ProxDesc& pg, const ProxDesc& pf,
                            const float* x, const float* y, ScaleRef T, ScaleRef S, const PdhgState* st,
                            float* x_out, float* y_out) {
@@ -778,9 +915,9 @@ void tile_iteration_launch(Context* ctx, const StencilPlan& plan, const ProxDesc
   // tile shape: long columns segments keep DRAM pages busy, wide tiles keep the halo share low;
   // PB_TILE_SHAPE (0..3) overrides the default for experiments
   static const int shape = [] { const char* e = getenv("PB_TILE_SHAPE"); return e ? atoi(e) : 0; }();
-  // PB_TILE_MODE: 2 (default) persistent TMA ring, 1 one-shot TMA tiles, 0 plain loads (A/B experiments)
-  static const int mode = [] { const char* e = getenv("PB_TILE_MODE"); return e ? atoi(e) : 2; }();
-  if (mode == 2 && ring_launch(ctx, g, pg, pf, x, y, T.val, S.val, st, x_out, y_out)) {
+  const int mode = tile_mode();
+  if (mode == 2 && ring_launch(ctx, g, pg, pf, x, y, nullptr, T.val, S.val, st, false, true, nullptr, nullptr, x_out,
+                               y_out, false)) {
     PB_CHECK_LAUNCH();
     ctx->launches++;
     return;

@@ -1,16 +1,16 @@
-# scaling experiments (run under gpurun --gpus N): single-GPU baseline, strong scaling over N GPUs
+# multi-GPU check (run under gpurun --gpus N): slab tests, then strong scaling of the metric config over N GPUs
 set -x
 N=${1:-2}
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
 mkdir -p gpurun_out
-timeout 150 python -m pytest tests/test_gpu_slab.py -x -q 2>&1 | tail -5
-timeout 200 python bench.py --steps 1000 --warmup 20 --no-cpu-baseline > gpurun_out/e_n1.json 2> gpurun_out/e_n1.err
+timeout 300 python -m pytest tests/test_gpu_slab.py -q 2>&1 | tail -5
 for n in 2 4 8; do
   if [ $n -le $N ]; then
-    timeout 100 $TR --nproc-per-node $n --master-port $((29560+n)) bench.py --gpus $n --steps 2000 --warmup 20 > gpurun_out/e_n${n}_p2p.json 2> gpurun_out/e_n${n}.err
+    timeout 150 $TR --nproc-per-node $n --master-port $((29560+n)) bench.py --gpus $n --steps 2000 --warmup 20 > gpurun_out/s_n${n}.json 2> gpurun_out/s_n${n}.err
+    tail -2 gpurun_out/s_n${n}.err
   fi
 done
-for f in gpurun_out/e_n*.json; do echo $f; python - "$f" <<'PY'
+for f in gpurun_out/s_n*.json; do echo $f; python - "$f" <<'PY'
 import json,sys
 try:
     d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])

@@ -15,6 +15,12 @@ from prost_b200 import synthetic as syn
 
 pytestmark = pytest.mark.gpu
 
+
+def same_residuals(a, b):
+    """The tiled residual-refresh pass folds its double partial sums in a different order than the two-pass
+    kernels: the float residuals may differ in the last digit."""
+    return all(abs(a["res"][k] - b["res"][k]) <= 2e-6 * max(abs(b["res"][k]), 1e-30) for k in b["res"])
+
 TOL4 = dict(tol_rel_primal=1e-4, tol_rel_dual=1e-4, tol_abs_primal=1e-4, tol_abs_dual=1e-4)
 
 
@@ -24,7 +30,8 @@ def tiled_iterations(ctx, desc, **opts):
                         pb.solver_options(verbose=0, max_iters=10, **TOL))
     prob.Initialize()
     be.Initialize()
-    return be.profile_detail(10)["n_tile"]
+    d = be.profile_detail(10)
+    return d["n_tile"] + d["n_tile_check"]
 
 
 def with_g(desc, fn, **coeff):
@@ -69,7 +76,7 @@ def test_tile_bit_identical_to_two_pass(ctx, shape):
     b = run_cuda(ctx, desc, 37, fuse=3, **opts)
     for k in ("x", "y", "z", "w"):
         assert np.array_equal(a[k], b[k]), k
-    assert a["res"] == b["res"] and a["steps"] == b["steps"]
+    assert same_residuals(a, b) and a["steps"] == b["steps"]
 
 
 @pytest.mark.parametrize("stepsize", ["alg1", "alg2", "goldstein", "boyd"])
@@ -80,7 +87,7 @@ def test_tile_all_stepsizes(ctx, stepsize):
     b = run_cuda(ctx, desc, 150, fuse=3, tol=TOL4, **opts)
     for k in ("x", "y", "z", "w"):
         assert np.array_equal(a[k], b[k]), k
-    assert a["res"] == b["res"] and a["steps"] == b["steps"]
+    assert same_residuals(a, b) and a["steps"] == b["steps"]
     want = run_oracle(desc, 150, tol=TOL4, **opts)
     loose = stepsize == "alg2"
     assert_parity(a, want, iter_tol=5e-5 if loose else 1e-5, res_tol=5e-3 if loose else 1e-4, label=stepsize)
@@ -109,11 +116,11 @@ def test_tile_variants(ctx, variant):
         x0 = r.random(desc["ncols"]).astype(np.float32)
         y0 = (0.3 * r.standard_normal(desc["nrows"])).astype(np.float32)
     elif variant == "residual_iter_1":
-        opts["residual_iter"] = 1          # every iteration refreshes: the tiled kernel never runs
+        opts["residual_iter"] = 1          # every iteration refreshes: only the CHECK variant of the tiled kernel runs
     elif variant == "residual_never":
         opts["residual_iter"] = -1         # only iteration 0 refreshes (size_t % int wrap)
     n_tile = tiled_iterations(ctx, desc, **opts)
-    assert (n_tile == 0) if variant == "residual_iter_1" else (n_tile > 0)
+    assert n_tile > 0
     a = run_cuda(ctx, desc, 60, fuse=1, x0=x0, y0=y0, **opts)
     b = run_cuda(ctx, desc, 60, fuse=3, x0=x0, y0=y0, **opts)
     for k in ("x", "y", "z", "w"):
@@ -139,4 +146,4 @@ def test_tile_metric_config_row_checksums(ctx):
         va, vb = a[k].view(np.uint32).astype(np.uint64), b[k].view(np.uint32).astype(np.uint64)
         assert int(va.sum()) == int(vb.sum()) and int((va * np.arange(1, va.size + 1, dtype=np.uint64)).sum()) == \
             int((vb * np.arange(1, vb.size + 1, dtype=np.uint64)).sum()), k
-    assert a["res"] == b["res"]
+    assert same_residuals(a, b)
