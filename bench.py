@@ -169,7 +169,8 @@ def workload_config(n_gpus, scaling="strong"):
                          "FITS the 126 MB L2: the strong-scaling slabs run L2-resident by construction "
                          "(that is the workload, not a cached repeat: every iteration reads the previous "
                          "iteration's output)")),
-            "parallelism": (f"slab{n_gpus}: column slabs, peer-to-peer halo stores inside the fused passes, "
+            "parallelism": (f"slab{n_gpus}: column slabs, one-pass ring kernel per slab with peer-to-peer halo "
+                            f"stores over NVLink from its edge tiles, "
                             f"NCCL all-reduce of 4 residual sums every {RESIDUAL_ITER} iterations")
             if n_gpus > 1 else "single"}
 
@@ -232,25 +233,52 @@ def run_slab_arm(args, rank, local_rank, world):
     value = args.steps / (ms * 1e-3) * norm
 
     prof_iters = min(200, max(20, args.steps // 10))
-    t_primal, t_dual, t_fin = be.profile(prof_iters)
-    t_primal, t_dual = max_over_ranks(t_primal), max_over_ranks(t_dual)
+    d = be.profile_detail(prof_iters)
     peak, peak_src = measured_peak()
     wmax = max(part.width(r) for r in range(world))
-    dual_bytes = BYTES_PER_PX_DUAL * wmax * NY
-    primal_bytes = BYTES_PER_PX_PRIMAL * wmax * NY
-    ach_dual = dual_bytes / (t_dual * 1e-3) / 1e9
-    ach_primal = primal_bytes / (t_primal * 1e-3) / 1e9
-    ach_iter = BYTES_PER_PX_ITER * wmax * NY * (args.steps / (ms * 1e-3)) / 1e9
-    roofline = {
-        "bound": "hbm", "kernel": "grad_dual_norm2_kernel (fused dual pass), per GPU on its slab",
-        "achieved": ach_dual, "peak": peak, "unit": "GB/s", "frac": ach_dual / peak, "traffic": None,
-        "peak_source": peak_src, "algorithmic_bytes_per_launch": dual_bytes, "ms_per_launch": t_dual,
-        "primal_pass": {"achieved": ach_primal, "frac": ach_primal / peak,
-                        "algorithmic_bytes_per_launch": primal_bytes, "ms_per_launch": t_primal},
-        "whole_iteration_per_gpu": {"achieved": ach_iter, "frac": ach_iter / peak},
-        "note": ("per-GPU slab state fits the 126 MB L2 at this N, so the algorithmic GB/s can exceed the "
-                 "HBM copy peak" if 28 * wmax * NY / 1e6 < 126 else "slab exceeds L2"),
-    }
+    one_pass = d["n_tile"] > 0
+    fits_l2 = 28 * wmax * NY / 1e6 < 126
+    l2_note = ("per-GPU slab state fits the 126 MB L2 at this N, so the algorithmic GB/s can exceed the "
+               "HBM copy peak" if fits_l2 else "slab exceeds L2")
+    if one_pass:
+        # every iteration but the first is ONE launch of the ring kernel on the slab (pb_tile.cu, SLAB):
+        # the left-/right-edge tiles store their edge columns into the neighbours' memory over NVLink
+        t_tile, t_chk = max_over_ranks(d["tile_ms"]), max_over_ranks(d["tile_check_ms"])
+        tile_bytes = BYTES_PER_PX_TILE * wmax * NY
+        n_all = max(d["n_tile"] + d["n_two_pass"] + d["n_tile_check"], 1.0)
+        avg_px = (d["n_tile"] * BYTES_PER_PX_TILE + d["n_tile_check"] * BYTES_PER_PX_TILE_CHECK +
+                  d["n_two_pass"] * BYTES_PER_PX_ITER) / n_all
+        ach = tile_bytes / (t_tile * 1e-3) / 1e9
+        ach_iter = avg_px * wmax * NY * (args.steps / (ms * 1e-3)) / 1e9
+        roofline = {
+            "bound": "hbm", "kernel": "grad2d_iteration_ring_kernel<SQUARE, IND_LEQ0, CHECK=false, SLAB=true> (whole "
+                                      "PDHG iteration in one pass, per GPU on its slab)",
+            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "peak_source": peak_src, "algorithmic_bytes_per_launch": tile_bytes, "ms_per_launch": t_tile,
+            "launch_share": d["n_tile"] / n_all,
+            "residual_refresh_iterations": {"share": d["n_tile_check"] / n_all, "ms_per_launch": t_chk,
+                                            "algorithmic_bytes_per_launch": BYTES_PER_PX_TILE_CHECK * wmax * NY},
+            "whole_iteration_per_gpu": {"achieved": ach_iter, "frac": ach_iter / peak},
+            "note": l2_note + "; ms_per_launch is measured with a host synchronisation after every iteration "
+                              "(max over ranks), so it includes the launch skew between ranks that the "
+                              "back-to-back timed region hides",
+        }
+    else:
+        t_primal, t_dual = max_over_ranks(d["primal_ms"]), max_over_ranks(d["dual_ms"])
+        dual_bytes = BYTES_PER_PX_DUAL * wmax * NY
+        primal_bytes = BYTES_PER_PX_PRIMAL * wmax * NY
+        ach_dual = dual_bytes / (t_dual * 1e-3) / 1e9
+        ach_primal = primal_bytes / (t_primal * 1e-3) / 1e9
+        ach_iter = BYTES_PER_PX_ITER * wmax * NY * (args.steps / (ms * 1e-3)) / 1e9
+        roofline = {
+            "bound": "hbm", "kernel": "grad_dual_norm2_kernel (fused dual pass), per GPU on its slab",
+            "achieved": ach_dual, "peak": peak, "unit": "GB/s", "frac": ach_dual / peak, "traffic": None,
+            "peak_source": peak_src, "algorithmic_bytes_per_launch": dual_bytes, "ms_per_launch": t_dual,
+            "primal_pass": {"achieved": ach_primal, "frac": ach_primal / peak,
+                            "algorithmic_bytes_per_launch": primal_bytes, "ms_per_launch": t_primal},
+            "whole_iteration_per_gpu": {"achieved": ach_iter, "frac": ach_iter / peak},
+            "note": l2_note,
+        }
     res = be.residuals()
     p2p = comm.peer_to_peer
     del be
@@ -285,6 +313,7 @@ def run_slab_arm(args, rank, local_rank, world):
             "data": "synthetic", "config": workload_config(world, args.scaling), "clocks": clocks, "e2e": e2e,
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": None,
             "halo_mode": "peer-to-peer stores over NVLink (CUDA IPC)" if p2p else "NCCL send/recv staging",
+            "one_pass_iterations": bool(one_pass),
             "residuals_after_run": res,
         }
         print(json.dumps(line), flush=True)

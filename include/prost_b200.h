@@ -266,6 +266,8 @@ int pb_backend_current_solution(pb_backend* b, float* h_x, float* h_z, float* h_
 size_t pb_backend_gpu_mem_amount(const pb_backend* b);
 /* 1 if the fused-pass planner accepted the problem, 0 if the unfused kernels run */
 int pb_backend_is_fused(const pb_backend* b);
+/* PDHG: iterations that ran as ONE tiled pass over HBM (pb_tile.cu) since Initialize; 0 for other schedules */
+unsigned long long pb_backend_one_pass_iterations(const pb_backend* b);
 /* kernels launched by this backend since creation (bench.py "gpu_launches") */
 unsigned long long pb_backend_launch_count(const pb_backend* b);
 /* Runs n_iters further iterations with CUDA events around every phase and returns the average

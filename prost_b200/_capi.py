@@ -163,6 +163,7 @@ SIGNATURES = {
     "pb_backend_gpu_mem_amount": (C.c_size_t, [handle]),
     "pb_backend_is_fused": (C.c_int, [handle]),
     "pb_backend_launch_count": (C.c_ulonglong, [handle]),
+    "pb_backend_one_pass_iterations": (C.c_ulonglong, [handle]),
     "pb_backend_device_iterates": (C.c_int, [handle, handle_p, handle_p]),
     "pb_comm_unique_id": (C.c_int, [C.c_void_p]),
     "pb_comm_create": (C.c_int, [handle, C.c_int, C.c_int, C.c_void_p, handle_p]),

@@ -463,6 +463,7 @@ class Backend(_Handle):
     iteration = property(lambda s: lib.pb_backend_iteration(s._h))
     is_fused = property(lambda s: bool(lib.pb_backend_is_fused(s._h)))
     launch_count = property(lambda s: lib.pb_backend_launch_count(s._h))
+    one_pass_iterations = property(lambda s: lib.pb_backend_one_pass_iterations(s._h))
     gpu_mem_amount = property(lambda s: lib.pb_backend_gpu_mem_amount(s._h))
 
     def current_solution(self, with_constraints=True):

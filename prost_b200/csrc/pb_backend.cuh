@@ -104,6 +104,7 @@ class Backend {
   virtual void current_solution(float* h_x, float* h_z, float* h_y, float* h_w) = 0;
   virtual size_t gpu_mem_amount() const = 0;
   virtual bool is_fused() const { return false; }
+  virtual unsigned long long one_pass_iterations() const { return 0; }
   virtual void device_iterates(float** d_x, float** d_y) = 0;
   // iterations between two residual refreshes (for the solver loop's chunking)
   virtual int residual_iter() const = 0;

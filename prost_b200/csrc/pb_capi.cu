@@ -503,6 +503,7 @@ int pb_backend_current_solution(pb_backend* b, float* h_x, float* h_z, float* h_
 }
 size_t pb_backend_gpu_mem_amount(const pb_backend* b) { return b->impl->gpu_mem_amount(); }
 int pb_backend_is_fused(const pb_backend* b) { return b->impl->is_fused() ? 1 : 0; }
+unsigned long long pb_backend_one_pass_iterations(const pb_backend* b) { return b->impl->one_pass_iterations(); }
 unsigned long long pb_backend_launch_count(const pb_backend* b) {
   return b->impl->ctx()->launches - b->impl->launch_base;
 }

@@ -217,6 +217,7 @@ class BackendPDHG : public Backend {
     return (4 * (n + m) + std::max(n, m)) * sizeof(float);     // backend_pdhg.cu:503-511
   }
   bool is_fused() const override { return fused_; }
+  unsigned long long one_pass_iterations() const override { return tile_iterations_; }
   void device_iterates(float** d_x, float** d_y) override { *d_x = x_.data(); *d_y = y_.data(); }
   int residual_iter() const override { return opts_.residual_iter; }
   void set_slab(Comm* comm) override { comm_ = comm; }
@@ -225,6 +226,7 @@ class BackendPDHG : public Backend {
   // slab mode (comm_ != nullptr): halo descriptors of the two passes, slab-aware K / K^T
   void slab_primal_halo(unsigned xs);
   void slab_dual_halo(unsigned xs, unsigned ys);
+  RingHalo slab_ring_halo();           // advances x_seq / y_seq: one-pass iteration on a slab
   void slab_apply(float* d_res, const float* d_rhs, const float* d_halo, bool adjoint);
   Comm* comm_ = nullptr;
   bool is_check_iteration() const {
@@ -367,8 +369,14 @@ void BackendPDHG::initialize(const float* h_x0, size_t nx0, const float* h_y0, s
   if (ny0 > 0 && ny0 != m) fail(PB_ERR_INVALID, "Initial dual solution has wrong size.");
 
   fused_ = plan_fused();
-  tile_ok_ = fused_ && !comm_ && opts_.fuse == 1 &&
+  tile_ok_ = fused_ && opts_.fuse == 1 &&
              tile_iteration_supported(stencil_, g_descs_, f_descs_, problem_->right_ref(), problem_->left_ref());
+  // slabs: the one-pass kernel stores its edge columns straight into the neighbours' memory, so it
+  // needs the peer-to-peer halo blocks and the persistent-ring variant (PB_SLAB_TILE=0: two passes)
+  if (comm_) {
+    static const bool slab_tile = [] { const char* e = getenv("PB_SLAB_TILE"); return !e || atoi(e) != 0; }();
+    tile_ok_ = tile_ok_ && slab_tile && tile_ring_available() && stencil_.geom.nx >= 2;
+  }
   tile_iterations_ = 0;
   if (comm_) {
     // the halo protocol lives in the specialised stencil passes: one planar gradient operator
@@ -393,6 +401,11 @@ void BackendPDHG::initialize(const float* h_x0, size_t nx0, const float* h_y0, s
       fail(PB_ERR_UNSUPPORTED, "slab decomposition needs the fused stencil passes: K = planar "
                                "BlockGradient2D/3D (+ identity rows), one prox_g, Norm2 prox on the gradient rows");
     comm_->ensure_halo((size_t)stencil_.geom.ny * stencil_.geom.L);
+    // all ranks run the same kind of iteration: one pass only if every slab qualifies (p2p() is only
+    // known once the halo blocks are mapped)
+    double no_tile[1] = {(tile_ok_ && (comm_->p2p() || comm_->world() == 1)) ? 0.0 : 1.0};
+    comm_->allreduce_sum_host(no_tile, 1);
+    tile_ok_ = no_tile[0] == 0.0;
   }
   try {
     x_.resize(n); x_prev_.resize(n); y_.resize(m); y_prev_.resize(m);
@@ -445,10 +458,17 @@ void BackendPDHG::iteration_fused() {
 
   unsigned nd = 0, np = 0;
   unsigned tiled_check = 0;
-  if (tile_ok_ && check && iteration_ > 0)
+  RingHalo ring_halo;
+  const bool tiled = tile_ok_ && iteration_ > 0;
+  if (tiled && comm_) ring_halo = slab_ring_halo();
+  const RingHalo* rh = (tiled && comm_) ? &ring_halo : nullptr;
+  if (tiled && check) {
     tiled_check = tile_check_iteration_launch(ctx_, stencil_, g_descs_[0], f_descs_[0], x_.data(), y_.data(),
                                               y_prev_.data(), T, S, st, iteration_ <= 1, part_d_.data(),
-                                              part_p_.data(), x_prev_.data(), y_prev_staging());
+                                              part_p_.data(), x_prev_.data(), y_prev_staging(), false, rh);
+    if (!tiled_check && comm_)
+      fail(PB_ERR_CUDA, "slab decomposition: the one-pass ring kernel could not be launched");
+  }
   if (tiled_check) {
     // residual-refresh iteration in one pass: x_prev_ <- x^{k+1}; y^{k+1} cannot overwrite y_prev_ (the
     // pass reads y^{k-1} from it), so it goes to a third buffer that then takes y_prev_'s place
@@ -465,7 +485,7 @@ void BackendPDHG::iteration_fused() {
   } else if (tile_ok_ && !check && iteration_ > 0) {
     // whole iteration in one pass over HBM (pb_tile.cu): x_prev_ <- x^{k+1}, y_prev_ <- y^{k+1}
     tile_iteration_launch(ctx_, stencil_, g_descs_[0], f_descs_[0], x_.data(), y_.data(), T, S, st,
-                          x_prev_.data(), y_prev_.data());
+                          x_prev_.data(), y_prev_.data(), rh);
     x_.swap(x_prev_);
     y_.swap(y_prev_);
     tile_iterations_++;
@@ -547,6 +567,39 @@ void BackendPDHG::slab_primal_halo(unsigned xs) {
     h.error = &f->error;
   }
   stencil_.geom.halo = h;
+}
+
+// One-pass iteration (pb_tile.cu ring kernel) = primal pass `xs` and dual pass `ys` in one launch: the
+// left-edge tiles play the primal pass's part of the protocol, the right-edge tiles the dual pass's.
+RingHalo BackendPDHG::slab_ring_halo() {
+  RingHalo h;
+  h.has_left = comm_->has_left();
+  h.has_right = comm_->has_right();
+  const unsigned ys_in = comm_->y_seq;               // newest y halo (left neighbour's previous iteration)
+  const unsigned xs = ++comm_->x_seq, ys = ++comm_->y_seq;
+  HaloFlags* f = comm_->flags();
+  h.error = &f->error;
+  if (h.has_left) {
+    h.yl_a = comm_->y_slot(ys_in);
+    h.yl_b = comm_->y_slot(ys_in - 1);
+    h.x_out = comm_->x_out(xs);
+    h.y_wait_flag = &f->y_seq;
+    h.y_wait_seq = ys_in;
+    h.x_done = &f->done_primal;
+    h.x_signal = comm_->left_x_seq();
+    h.x_signal_seq = xs;
+  }
+  if (h.has_right) {
+    h.xr_n = comm_->x_slot(xs);
+    h.xr_o = comm_->x_slot(xs - 1);
+    h.y_out = comm_->y_out(ys);
+    h.x_wait_flag = &f->x_seq;
+    h.x_wait_seq = xs;
+    h.y_done = &f->done_dual;
+    h.y_signal = comm_->right_y_seq();
+    h.y_signal_seq = ys;
+  }
+  return h;
 }
 
 // Dual pass number `ys`: reads the x columns of the right neighbour's primal passes xs / xs-1,

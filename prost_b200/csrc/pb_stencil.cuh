@@ -53,6 +53,39 @@ struct SlabHalo {
   int* error = nullptr;                  // set when a wait times out
 };
 
+// Halo descriptor of the one-pass ring kernel (pb_tile.cu) on a slab: ONE launch does the primal and the
+// dual step, so it talks to both neighbours.  Same slots, sequence numbers and flags as the two-pass
+// protocol above (the two kinds of iteration interleave freely):
+//   left edge  (tiles with tx = 0, image column 0): waits for the left neighbour's newest y.gx column
+//              (yl_a; yl_b = the one before, residual refresh only), stores its new x column 0 into the
+//              left neighbour's x slot and publishes x_signal_seq once all left-edge tiles are done;
+//   right edge (tiles owning column nx-1): waits for the right neighbour's new x column 0 of THIS
+//              iteration (xr_n; xr_o = previous iterate), stores its new y.gx column nx-1 into the right
+//              neighbour's y slot and publishes y_signal_seq once all right-edge tiles are done.
+// Both edge tile groups are walked first (see the tile order in the kernel), so in steady state the
+// columns arrive long before they are needed.
+struct RingHalo {
+  int has_left = 0, has_right = 0;
+  const float* yl_a = nullptr;
+  const float* yl_b = nullptr;
+  float* x_out = nullptr;
+  const unsigned* y_wait_flag = nullptr;
+  unsigned y_wait_seq = 0;
+  unsigned* x_done = nullptr;
+  unsigned* x_signal = nullptr;
+  unsigned x_signal_seq = 0;
+  const float* xr_n = nullptr;
+  const float* xr_o = nullptr;
+  float* y_out = nullptr;
+  const unsigned* x_wait_flag = nullptr;
+  unsigned x_wait_seq = 0;
+  unsigned* y_done = nullptr;
+  unsigned* y_signal = nullptr;
+  unsigned y_signal_seq = 0;
+  unsigned n_edge_tiles = 0;             // tiles per edge = tiles_y * L (filled by the launcher)
+  int* error = nullptr;
+};
+
 struct GradGeom {
   uint32_t nx = 0, ny = 0, L = 0, nxny = 0, plane = 0;
   uint32_t q = 0;                 // ny / VEC
@@ -646,12 +679,15 @@ bool tile_iteration_supported(const StencilPlan& plan, const std::vector<ProxDes
                               const std::vector<ProxDesc>& fd, ScaleRef T, ScaleRef S);
 void tile_iteration_launch(Context* ctx, const StencilPlan& plan, const ProxDesc& pg, const ProxDesc& pf,
                            const float* x, const float* y, ScaleRef T, ScaleRef S, const PdhgState* st,
-                           float* x_out, float* y_out);
+                           float* x_out, float* y_out, const RingHalo* halo = nullptr);
+// slab mode: is the persistent ring (the only one-pass variant that speaks the halo protocol) available?
+bool tile_ring_available();
 // residual-refresh iteration as one tiled pass; returns the number of (a, b) partial pairs written to each of
 // part_d (dual residual sums) and part_p (primal residual sums), 0 if the two-pass kernels have to run
 unsigned tile_check_iteration_launch(Context* ctx, const StencilPlan& plan, const ProxDesc& pg, const ProxDesc& pf,
                                      const float* x, const float* y, const float* y_prev, ScaleRef T, ScaleRef S,
                                      const PdhgState* st, bool ktyprev_zero, double* part_d, double* part_p,
-                                     float* x_out, float* y_out, bool dry_run = false);
+                                     float* x_out, float* y_out, bool dry_run = false,
+                                     const RingHalo* halo = nullptr);
 
 }  // namespace pb

@@ -528,10 +528,48 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---- slab edges (SLAB instantiation only; protocol in pb_stencil.cuh: RingHalo, pb_comm.cuh) ---------------
+__device__ __forceinline__ void ring_flag_wait(const unsigned* flag, unsigned seq, int* error) {
+  if (!flag || seq == 0) return;
+  if (error && *reinterpret_cast<volatile int*>(error)) return;   // sticky: one timeout poisons the solve
+  unsigned v;
+  unsigned long long t0 = 0;
+  for (unsigned spins = 0;; ++spins) {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if ((int)(v - seq) >= 0) break;
+    if ((spins & 1023u) == 1023u) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ull) { if (error) atomicExch(error, 1); break; }
+    }
+  }
+}
+// whole warp: every lane has issued its halo loads and its remote stores; count the tile in and let the
+// last edge tile of the launch publish the sequence number in the neighbour's memory
+__device__ __forceinline__ void ring_edge_done(unsigned* counter, unsigned n_tiles, unsigned* signal, unsigned seq) {
+  __threadfence_system();
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0 && counter) {
+    const unsigned prev = atomicAdd(counter, 1u);
+    if (prev + 1 == n_tiles) {
+      atomicExch(counter, 0u);
+      __threadfence_system();
+      if (signal) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(signal), "r"(seq) : "memory");
+    }
+  }
+}
+// halo columns live in this GPU's memory but are written by the neighbour over NVLink: bypass L1
+__device__ __forceinline__ void ld_halo4(const float* p, float (&o)[4]) {
+  const float4 t = __ldcg(reinterpret_cast<const float4*>(p));
+  o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+}
+
 // CHECK: this iteration refreshes the residuals (backend_pdhg.cu:73-120, 383-436): the same pass also
 // gathers K^T y_prev from the previous dual iterate (map_q1 / map_q2) and accumulates the four residual
 // sums in double, one (a, b) pair per CTA for each of the two residuals.
-template <int FN_G, int FN_F, bool CHECK>
+// SLAB: the image is a block of columns of a wider one (has_left / has_right neighbours, RingHalo).
+template <int FN_G, int FN_F, bool CHECK, bool SLAB>
 __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
     const __grid_constant__ CUtensorMap map_p1, const __grid_constant__ CUtensorMap map_p2,
     const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_f,
@@ -539,8 +577,16 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
     const ProxDesc pg, const ProxDesc pf, const float Tval, const float Sval,
     const PdhgState* __restrict__ st, const FastDiv div_per_plane, const FastDiv div_tiles_y,
     const uint32_t n_tiles, const int ktyprev_zero, double* __restrict__ part_d, double* __restrict__ part_p,
-    float* __restrict__ x_out, float* __restrict__ y_out) {
+    float* __restrict__ x_out, float* __restrict__ y_out, const uint32_t tiles_x, const RingHalo h) {
   extern __shared__ __align__(128) unsigned char smem[];
+  // tile -> (label plane, tile column, tile row).  On a slab the two edge tile columns come first
+  // (tile column order 0, tiles_x-1, 1, 2, ...) so that the halos leave at the start of the launch.
+  auto decode = [&](uint32_t tile, uint32_t& l, uint32_t& tx, uint32_t& ty) {
+    uint32_t rem;
+    div_per_plane.divmod(tile, l, rem);
+    div_tiles_y.divmod(rem, tx, ty);
+    if (SLAB) tx = tx == 0 ? 0u : (tx == 1 ? tiles_x - 1 : tx - 1);
+  };
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kRingOffBar);
   uint64_t* empty = full + kRingStages;
   uint64_t* col_ready = empty + kRingStages;
@@ -551,9 +597,8 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
                             (CHECK ? (q_boxes ? kRingP1Bytes + kRingP2Bytes : 0) : (f_vec ? kRingXBytes : 0));
 
   auto issue = [&](uint32_t tile, int s) {           // producer lane only
-    uint32_t l, rem, tx, ty;
-    div_per_plane.divmod(tile, l, rem);
-    div_tiles_y.divmod(rem, tx, ty);
+    uint32_t l, tx, ty;
+    decode(tile, l, tx, ty);
     const int cx = tx * kRingTX, cy = ty * kRingTY;
     unsigned char* base = smem + s * kRingStageBytes;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full[s])), "r"(stage_tx)
@@ -611,9 +656,8 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
     const int s = k % kRingStages;
     const uint32_t parity = (k / kRingStages) & 1u;
-    uint32_t l, rem, tx, ty;
-    div_per_plane.divmod(tile, l, rem);
-    div_tiles_y.divmod(rem, tx, ty);
+    uint32_t l, tx, ty;
+    decode(tile, l, tx, ty);
     const int cx = tx * kRingTX, cy = ty * kRingTY;
     unsigned char* base = smem + s * kRingStageBytes;
     float (*s_p1)[kRingRows] = reinterpret_cast<float (*)[kRingRows]>(base);
@@ -628,6 +672,11 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
 
     const uint32_t gx = cx + col, gy = cy + r0;
     const uint32_t plane_off = l * g.nxny;
+    // slab edges (warp-uniform): column 0 takes y.gx of column -1 from the left neighbour's halo; the
+    // owner of column nx-1 takes x+ / x of column nx from the right neighbour's halo
+    const bool left_edge = SLAB && h.has_left && gx == 0;
+    const bool right_edge = SLAB && h.has_right && gx == g.nx - 1 && col < kRingTX;
+    const uint32_t halo_off = (gy < g.ny ? gy : 0u) + l * g.ny;
     // ---- phase A: x+ at (col, r0..r0+3) of the computed region ------------------------------------------
     if (gx < g.nx) {
       float xo[4], divx[4], o[4], a[4], xn[4];
@@ -636,9 +685,13 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
       VecIO<4>::ld(&s_x[col][r0], xo);
       VecIO<4>::ld(&s_p1[col + 1][r0], divx);
       VecIO<4>::ld(&s_p1[col][r0], a);
+      if (left_edge) {
+        ring_flag_wait(h.y_wait_flag, h.y_wait_seq, h.error);
+        ld_halo4(h.yl_a + halo_off, a);
+      }
       VecIO<4>::ld(&s_p2[col][4 + r0], o);
       const float up = s_p2[col][4 + r0 - 1];
-      const bool last_col = gx == g.nx - 1;
+      const bool last_col = gx == g.nx - 1 && !(SLAB && h.has_right);
       float divy[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -678,6 +731,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
       VecIO<4>::st(&s_xn[col][r0], xn);
       if (col < kRingTX && r0 < kRingTY && gy < g.ny) {
         VecIO<4>::st(x_out + gy + gx * g.ny + plane_off, xn);
+        if (left_edge) VecIO<4>::st(h.x_out + halo_off, xn);      // new column 0 -> left neighbour (NVLink)
         if (CHECK) {
           // dual residual on the owned pixels: w^ = (x - x+)/(tau sqrt T) - sqrt T K^T y_prev,
           // diff = w^ + sqrt T K^T y
@@ -686,6 +740,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
             float qx[4], qa[4], qo[4];
             VecIO<4>::ld(&s_q1[col + 1][r0], qx);
             VecIO<4>::ld(&s_q1[col][r0], qa);
+            if (left_edge) ld_halo4(h.yl_b + halo_off, qa);
             VecIO<4>::ld(&s_q2[col][4 + r0], qo);
             const float qup = s_q2[col][4 + r0 - 1];
             float qy[4];
@@ -715,6 +770,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
         }
       }
     }
+    if (left_edge) ring_edge_done(h.x_done, h.n_edge_tiles, h.x_signal, h.x_signal_seq);
     // publish this column's x+ (one arrival per warp), then wait for the right neighbour's
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(&col_ready[s * kRingCols + col]);
@@ -727,10 +783,16 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
       float cn[4], co[4], rn[4], ro[4];
       VecIO<4>::ld(&s_xn[col][r0], cn);
       VecIO<4>::ld(&s_x[col][r0], co);
-      VecIO<4>::ld(&s_xn[col + 1][r0], rn);
-      VecIO<4>::ld(&s_x[col + 1][r0], ro);
+      if (right_edge) {
+        ring_flag_wait(h.x_wait_flag, h.x_wait_seq, h.error);
+        ld_halo4(h.xr_n + halo_off, rn);
+        ld_halo4(h.xr_o + halo_off, ro);
+      } else {
+        VecIO<4>::ld(&s_xn[col + 1][r0], rn);
+        VecIO<4>::ld(&s_x[col + 1][r0], ro);
+      }
       const float dn = s_xn[col][r0 + 4], dold = s_x[col][r0 + 4];
-      const bool last_col = gx == g.nx - 1, last_row = gy + 4 >= g.ny;
+      const bool last_col = gx == g.nx - 1 && !(SLAB && h.has_right), last_row = gy + 4 >= g.ny;
       float k1x[4], k0x[4], k1y[4], k0y[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {          // grad_fwd: 0 on the last column
@@ -753,6 +815,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
       else norm2_lanes<4, 2, false>(fn_f, arg, cf, tau_f);
       VecIO<4>::st(y_out + idx, arg[0]);
       VecIO<4>::st(y_out + (size_t)g.L * g.nxny + idx, arg[1]);
+      if (right_edge) VecIO<4>::st(h.y_out + halo_off, arg[0]);     // new y.gx column nx-1 -> right neighbour
       if (CHECK) {
         // primal residual: z^ = (y - y+)/(sigma sqrt S) + sqrt S ((1+theta) K x+ - theta K x),
         // diff = z^ - sqrt S K x+
@@ -770,6 +833,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
         }
       }
     }
+    if (right_edge) ring_edge_done(h.y_done, h.n_edge_tiles, h.y_signal, h.y_signal_seq);
     // this warp is done with stage s (operand boxes and x+ tile)
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[s]);
@@ -797,12 +861,13 @@ struct RingArgs {
   int ktyprev_zero = 1;
   double* part_d = nullptr;
   double* part_p = nullptr;
+  const RingHalo* halo = nullptr;      // slab mode
 };
 
-template <int FN_G, int FN_F, bool CHECK>
+template <int FN_G, int FN_F, bool CHECK, bool SLAB>
 unsigned ring_launch_k(Context* ctx, const RingArgs& a, const GradGeom& g, const ProxDesc& pg, const ProxDesc& pf,
                        float Tval, float Sval, const PdhgState* st, float* x_out, float* y_out, bool dry_run) {
-  auto kernel = grad2d_iteration_ring_kernel<FN_G, FN_F, CHECK>;
+  auto kernel = grad2d_iteration_ring_kernel<FN_G, FN_F, CHECK, SLAB>;
   static bool configured = false, ok = false;
   if (!configured) {
     configured = true;
@@ -815,24 +880,35 @@ unsigned ring_launch_k(Context* ctx, const RingArgs& a, const GradGeom& g, const
   if (n_tiles == 0 || n_tiles >= (1ull << 31)) return 0;
   const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)ctx->num_sms);
   if (dry_run) return grid;
+  RingHalo h;
+  if (SLAB) {
+    h = *a.halo;
+    h.n_edge_tiles = tiles_y * g.L;
+  }
   kernel<<<grid, kRingThreads, kRingSmemBytes, ctx->stream>>>(
       a.mp1, a.mp2, a.mx, a.mf, a.mq1, a.mq2, g, pg, pf, Tval, Sval, st, FastDiv((uint64_t)tiles_x * tiles_y),
-      FastDiv(tiles_y), (uint32_t)n_tiles, a.ktyprev_zero, a.part_d, a.part_p, x_out, y_out);
+      FastDiv(tiles_y), (uint32_t)n_tiles, a.ktyprev_zero, a.part_d, a.part_p, x_out, y_out, tiles_x, h);
   return grid;
 }
 
 template <int FN_G, int FN_F>
 unsigned ring_launch_fn(Context* ctx, const RingArgs& a, const GradGeom& g, const ProxDesc& pg, const ProxDesc& pf,
                         float Tval, float Sval, const PdhgState* st, float* x_out, float* y_out, bool dry_run) {
-  if (a.check) return ring_launch_k<FN_G, FN_F, true>(ctx, a, g, pg, pf, Tval, Sval, st, x_out, y_out, dry_run);
-  return ring_launch_k<FN_G, FN_F, false>(ctx, a, g, pg, pf, Tval, Sval, st, x_out, y_out, dry_run);
+  if (a.halo) {
+    if (a.check) return ring_launch_k<FN_G, FN_F, true, true>(ctx, a, g, pg, pf, Tval, Sval, st, x_out, y_out, dry_run);
+    return ring_launch_k<FN_G, FN_F, false, true>(ctx, a, g, pg, pf, Tval, Sval, st, x_out, y_out, dry_run);
+  }
+  if (a.check) return ring_launch_k<FN_G, FN_F, true, false>(ctx, a, g, pg, pf, Tval, Sval, st, x_out, y_out, dry_run);
+  return ring_launch_k<FN_G, FN_F, false, false>(ctx, a, g, pg, pf, Tval, Sval, st, x_out, y_out, dry_run);
 }
 
 // returns the number of CTAs (= residual partial pairs per residual when check), 0 if not launched
 unsigned ring_launch(Context* ctx, const GradGeom& g, const ProxDesc& pg, const ProxDesc& pf, const float* x,
                      const float* y, const float* y_prev, float Tval, float Sval, const PdhgState* st, bool check,
-                     bool ktyprev_zero, double* part_d, double* part_p, float* x_out, float* y_out, bool dry_run) {
+                     bool ktyprev_zero, double* part_d, double* part_p, float* x_out, float* y_out, bool dry_run,
+                     const RingHalo* halo) {
   RingArgs a;
+  a.halo = halo;
   a.check = check;
   a.ktyprev_zero = ktyprev_zero ? 1 : 0;
   a.part_d = part_d;
@@ -868,7 +944,7 @@ bool tile_iteration_supported(const StencilPlan& plan, const std::vector<ProxDes
                               const std::vector<ProxDesc>& fd, ScaleRef T, ScaleRef S) {
   if (!plan.ok || plan.three_d) return false;
   const GradGeom& g = plan.geom;
-  if (g.has_id || g.halo.has_left || g.halo.has_right) return false;
+  if (g.has_id) return false;
   if (g.ny % 4 != 0 || g.plane % 4 != 0 || g.L > 65535u) return false;
   if (T.ptr || S.ptr) return false;
   if (gd.size() != 1 || fd.size() != 1) return false;
@@ -886,6 +962,9 @@ bool tile_iteration_supported(const StencilPlan& plan, const std::vector<ProxDes
   return true;
 }
 
+static int tile_mode();
+bool tile_ring_available() { return tile_mode() == 2 && encode_tiled_fn() != nullptr; }
+
 static int tile_mode() {
   // PB_TILE_MODE: 2 (default) persistent TMA ring, 1 one-shot TMA tiles, 0 plain loads (A/B experiments)
   static const int mode = [] { const char* e = getenv("PB_TILE_MODE"); return e ? atoi(e) : 2; }();
@@ -897,10 +976,10 @@ static int tile_mode() {
 unsigned tile_check_iteration_launch(Context* ctx, const StencilPlan& plan, const ProxDesc& pg, const ProxDesc& pf,
                                      const float* x, const float* y, const float* y_prev, ScaleRef T, ScaleRef S,
                                      const PdhgState* st, bool ktyprev_zero, double* part_d, double* part_p,
-                                     float* x_out, float* y_out, bool dry_run) {
+                                     float* x_out, float* y_out, bool dry_run, const RingHalo* halo) {
   if (tile_mode() != 2) return 0;
   const unsigned n = ring_launch(ctx, plan.geom, pg, pf, x, y, y_prev, T.val, S.val, st, true, ktyprev_zero, part_d,
-                                 part_p, x_out, y_out, dry_run);
+                                 part_p, x_out, y_out, dry_run, halo);
   if (n && !dry_run) {
     PB_CHECK_LAUNCH();
     ctx->launches++;
@@ -910,14 +989,23 @@ unsigned tile_check_iteration_launch(Context* ctx, const StencilPlan& plan, cons
 
 void tile_iteration_launch(Context* ctx, const StencilPlan& plan, const ProxDesc& pg, const ProxDesc& pf,
                            const float* x, const float* y, ScaleRef T, ScaleRef S, const PdhgState* st,
-                           float* x_out, float* y_out) {
+                           float* x_out, float* y_out, const RingHalo* halo) {
   const GradGeom& g = plan.geom;
+  if (halo) {
+    // slab mode: only the ring kernel speaks the halo protocol (tile_ring_available() was checked at Initialize)
+    if (!ring_launch(ctx, g, pg, pf, x, y, nullptr, T.val, S.val, st, false, true, nullptr, nullptr, x_out, y_out,
+                     false, halo))
+      fail(PB_ERR_CUDA, "slab decomposition: the one-pass ring kernel could not be launched");
+    PB_CHECK_LAUNCH();
+    ctx->launches++;
+    return;
+  }
   // tile shape: long columns segments keep DRAM pages busy, wide tiles keep the halo share low;
   // PB_TILE_SHAPE (0..3) overrides the default for experiments
   static const int shape = [] { const char* e = getenv("PB_TILE_SHAPE"); return e ? atoi(e) : 0; }();
   const int mode = tile_mode();
   if (mode == 2 && ring_launch(ctx, g, pg, pf, x, y, nullptr, T.val, S.val, st, false, true, nullptr, nullptr, x_out,
-                               y_out, false)) {
+                               y_out, false, nullptr)) {
     PB_CHECK_LAUNCH();
     ctx->launches++;
     return;

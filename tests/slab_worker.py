@@ -24,6 +24,11 @@ def cases():
         "tv3d": (lambda: syn.tv3d(14, 16, 6), dict(stepsize="alg1", residual_iter=5), 40),
         "lifting": (lambda: syn.lifting(18, 12, 6), dict(stepsize="boyd", residual_iter=5), 40),
         "rof_big": (lambda: syn.rof(1024, 512), dict(stepsize="alg1", residual_iter=10), 200),
+        # one-pass ring kernel on slabs (pb_tile.cu, SLAB): several tile columns / rows per slab; slab width 63
+        # puts the right edge column in a one-column tile (62 = 2 * 31), width 65 in the middle of one
+        "rof_tiles65": (lambda: syn.rof(130, 252), dict(stepsize="boyd", residual_iter=4), 60),
+        "rof_tiles63": (lambda: syn.rof(126, 128), dict(stepsize="goldstein", residual_iter=3), 60),
+        "rof_tiles_alg2": (lambda: syn.rof(200, 380), dict(stepsize="alg2", residual_iter=7, alg2_gamma=0.5), 45),
     }
 
 
@@ -66,7 +71,8 @@ def main():
             be.current_solution()
             be.PerformIteration(iters - iters // 2)
             x, z, y, w = be.current_solution()
-            return dict(x=x, z=z, y=y, w=w, res=be.residuals(), steps=be.stepsizes(), fused=be.is_fused)
+            return dict(x=x, z=z, y=y, w=w, res=be.residuals(), steps=be.stepsizes(), fused=be.is_fused,
+                        one_pass=int(be.one_pass_iterations))
 
         mine = run(local_desc, comm)
         gathered = [None] * world
@@ -74,7 +80,8 @@ def main():
         if rank == 0:
             ref = run(desc, None)
             out = {"res": mine["res"], "res_single": ref["res"], "steps": mine["steps"],
-                   "steps_single": ref["steps"], "err": {}}
+                   "steps_single": ref["steps"], "err": {}, "iters": iters,
+                   "one_pass": mine["one_pass"], "one_pass_single": ref["one_pass"]}
             for k in ("x", "z", "y", "w"):
                 glob = pbd.gather_planar([g[k] for g in gathered], part, ny)
                 denom = max(float(np.abs(ref[k]).max()), 1e-30)

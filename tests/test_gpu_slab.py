@@ -46,13 +46,21 @@ def _check(rep, expect_p2p):
             assert abs(v - ref) <= 1e-5 * max(abs(ref), 1e-6), f"{name}: {k} {v} vs {ref}"
         for a, b in zip(c["steps"], c["steps_single"]):
             assert abs(a - b) <= 1e-6 * max(abs(b), 1e-12), f"{name}: step sizes"
+        # ROF-shaped problems run every iteration but the first as ONE pass (pb_tile.cu ring kernel); on
+        # slabs that needs the peer-to-peer halo blocks (or a world of one rank)
+        if name.startswith("rof") and name != "rof_scalar":
+            assert c["one_pass_single"] == c["iters"] - 1, f"{name}: single-GPU run did not use the ring kernel"
+            if rep["p2p"] or rep["world"] == 1:
+                assert c["one_pass"] == c["iters"] - 1, f"{name}: slabs did not use the one-pass ring kernel"
+            else:
+                assert c["one_pass"] == 0
 
 
 def test_world1_communicator():
     """A communicator of one rank: no neighbours, all-reduce is the identity."""
     if _gpus() < 1:
         pytest.skip("no GPU")
-    _check(_run(1, "p2p", "rof_vec4,lifting"), None)
+    _check(_run(1, "p2p", "rof_vec4,lifting,rof_tiles65,rof_tiles_alg2"), None)
 
 
 @pytest.mark.parametrize("halo", ["p2p", "nccl"])
