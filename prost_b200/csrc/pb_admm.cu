@@ -717,10 +717,10 @@ void BackendADMM::current_solution(float* h_x, float* h_z, float* h_y, float* h_
     PB_CHECK_LAUNCH();
     ctx_->launches++;
   }
-  if (h_w) temp1_.download(h_w, n, st);
-  if (h_y) temp2_.download(h_y, m, st);
-  if (h_x) x_half_.download(h_x, n, st);
-  if (h_z) z_half_.download(h_z, m, st);
+  if (h_w) download_to_host(ctx_, h_w, temp1_.data(), n);
+  if (h_y) download_to_host(ctx_, h_y, temp2_.data(), m);
+  if (h_x) download_to_host(ctx_, h_x, x_half_.data(), n);
+  if (h_z) download_to_host(ctx_, h_z, z_half_.data(), m);
   PB_CUDA(cudaStreamSynchronize(st));
 }
 

@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstring>
 #include <deque>
+#include <thread>
 #include <iomanip>
 #include <iostream>
 #include <new>
@@ -95,6 +96,7 @@ int pb_context_create(int device, void* stream, pb_context** out) {
 void pb_context_destroy(pb_context* c) {
   if (!c) return;
   cudaSetDevice(c->ctx.device);
+  pb::release_host_staging(&c->ctx);
   if (c->ctx.owns_stream && c->ctx.stream) cudaStreamDestroy(c->ctx.stream);
   delete c;
 }
@@ -554,6 +556,19 @@ int pb_solver_solve(pb_backend* b, const pb_solver_options* so, pb_stopping_cb s
     if (!pz) { z.resize(m); pz = z.data(); }
     if (!pw) { w.resize(n); pw = w.data(); }
 
+    // Fault the (pageable) result buffers in on a helper thread while the GPU iterates: the final
+    // read-back of x, z, y, w then lands in resident pages (pb_hostio.cu).  Joined before the first copy.
+    std::thread prefault([=] {
+      pb::prefault_host_range(px, n * sizeof(float));
+      pb::prefault_host_range(py, m * sizeof(float));
+      pb::prefault_host_range(pz, m * sizeof(float));
+      pb::prefault_host_range(pw, n * sizeof(float));
+    });
+    struct Joiner {
+      std::thread& t;
+      ~Joiner() { if (t.joinable()) t.join(); }
+    } joiner{prefault};
+
     // callback schedule: linspace(0, max_iters-1, num_cback_calls) plus the end point
     // (solver.cu:130-135, common.cu:32-46)
     std::deque<double> cb_iters;
@@ -581,6 +596,7 @@ int pb_solver_solve(pb_backend* b, const pb_solver_options* so, pb_stopping_cb s
 
       const double front = cb_iters.empty() ? 1e300 : cb_iters.front();
       if (i >= front || is_converged || is_stopped || i == so->max_iters - 1) {
+        if (prefault.joinable()) prefault.join();
         be->current_solution(px, pz, py, pw);
         if (so->num_cback_calls >= 1) {
           if (so->verbose) {
@@ -612,6 +628,7 @@ int pb_solver_solve(pb_backend* b, const pb_solver_options* so, pb_stopping_cb s
     }
     if (so->verbose && result == PB_STOPPED_MAX_ITERS)
       std::cout << "Reached maximum of " << so->max_iters << " iterations." << std::endl;
+    if (prefault.joinable()) prefault.join();
     if (so->max_iters <= 0) be->current_solution(px, pz, py, pw);
     if (result_out) *result_out = result;
     if (iters_out) *iters_out = iters;

@@ -3,8 +3,10 @@
 
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <memory>
 #include <sstream>
 #include <stdexcept>
@@ -51,9 +53,50 @@ struct Context {
   // kernels return without touching memory.  Lets a device-resident loop (the CGLS projection of
   // BackendADMM, pb_admm.cu) stop early without a host round trip per inner iteration.
   const int* skip_flag = nullptr;
+  // two pinned staging buffers for copies to / from pageable host memory (pb_hostio.cu), allocated on
+  // first use and released by pb_context_destroy
+  void* stage[2] = {nullptr, nullptr};
+  cudaEvent_t stage_ev[2] = {nullptr, nullptr};
 
   void bind() const { PB_CUDA(cudaSetDevice(device)); }
 };
+
+// ---- host <-> device copies (pb_hostio.cu) ----------------------------------------------------------
+// Blocking copy of n floats from device memory into host memory.  Pinned / registered destinations are
+// written by one DMA; pageable ones through the context's pinned staging ring with a multi-threaded
+// copy-out, which is several times faster than cudaMemcpy into cold pageable memory (the final
+// x, z, y, w read of Solver::Solve, solver.cu:152-167, is 400 MB for a 4096^2 image).
+void download_to_host(Context* ctx, float* h, const float* d, size_t n);
+// Blocking copy of n floats from host memory into device memory (same split; the source is only read).
+void upload_from_host(Context* ctx, float* d, const float* h, size_t n);
+// Touches every page of a pageable host range (content preserved) so that a later copy into it does not
+// pay the first-touch page faults; no-op for pinned memory.  Safe to run on a helper thread.
+void prefault_host_range(void* p, size_t bytes);
+void release_host_staging(Context* ctx);
+
+// PB_TRACE=1: wall-clock of the host-side phases (Problem::Initialize, Backend::Initialize, solution
+// read-back ...) on stderr; the device is synchronised at both ends of a scope so that asynchronous work
+// is attributed to the phase that enqueued it.  Off by default (no synchronisation, no output).
+inline bool trace_enabled() {
+  static const bool on = [] { const char* e = getenv("PB_TRACE"); return e && atoi(e) != 0; }();
+  return on;
+}
+struct TraceScope {
+  const char* name;
+  std::chrono::steady_clock::time_point t0;
+  explicit TraceScope(const char* n) : name(n) {
+    if (trace_enabled()) { cudaDeviceSynchronize(); t0 = std::chrono::steady_clock::now(); }
+  }
+  ~TraceScope() {
+    if (!trace_enabled()) return;
+    cudaDeviceSynchronize();
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    std::fprintf(stderr, "[pb trace] %-44s %9.3f ms\n", name, ms);
+  }
+};
+#define PB_TRACE_CAT2(a, b) a##b
+#define PB_TRACE_CAT(a, b) PB_TRACE_CAT2(a, b)
+#define PB_TRACE_SCOPE(name) ::pb::TraceScope PB_TRACE_CAT(pb_trace_scope_, __LINE__)(name)
 
 // RAII device allocation (replaces thrust::device_vector members of the reference).
 template <typename T>

@@ -170,25 +170,25 @@ __global__ void __launch_bounds__(kStencilBlock) slab_adjoint_kernel(const GradG
 __global__ void __launch_bounds__(kBlock) w_variable_kernel(float* __restrict__ w,
                                                             const float* __restrict__ x_prev,
                                                             const float* __restrict__ x,
-                                                            const float* __restrict__ T,
+                                                            const ScaleRef T,
                                                             const float* __restrict__ kty_prev, size_t n,
                                                             float tau) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
        i += (size_t)gridDim.x * blockDim.x)
-    w[i] = (x_prev[i] - x[i]) / (T[i] * tau) - kty_prev[i];
+    w[i] = (x_prev[i] - x[i]) / ((T.ptr ? T.ptr[i] : T.val) * tau) - kty_prev[i];
 }
 
 // z = (y_prev - y) / (sigma S) + (1+theta) kx - theta kx_prev   (compute_z_variable_functor, :170-186)
 __global__ void __launch_bounds__(kBlock) z_variable_kernel(float* __restrict__ z,
                                                             const float* __restrict__ y_prev,
                                                             const float* __restrict__ y,
-                                                            const float* __restrict__ S,
+                                                            const ScaleRef S,
                                                             const float* __restrict__ kx,
                                                             const float* __restrict__ kx_prev, size_t m,
                                                             float sigma, float theta) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < m;
        i += (size_t)gridDim.x * blockDim.x)
-    z[i] = (y_prev[i] - y[i]) / (sigma * S[i]) + (1 + theta) * kx[i] - theta * kx_prev[i];
+    z[i] = (y_prev[i] - y[i]) / (sigma * (S.ptr ? S.ptr[i] : S.val)) + (1 + theta) * kx[i] - theta * kx_prev[i];
 }
 
 // ---- backend -------------------------------------------------------------------------------------
@@ -302,6 +302,7 @@ bool BackendPDHG::plan_fused() {
 void BackendPDHG::initialize(const float* h_x0, size_t nx0, const float* h_y0, size_t ny0) {
   ctx_->bind();
   if (!problem_->initialized()) fail(PB_ERR_INVALID, "Problem has not been initialized.");
+  PB_TRACE_SCOPE("BackendPDHG::initialize");
   const size_t m = problem_->nrows(), n = problem_->ncols();
   cudaStream_t s = ctx_->stream;
 
@@ -368,7 +369,7 @@ void BackendPDHG::initialize(const float* h_x0, size_t nx0, const float* h_y0, s
   if (nx0 > 0 && nx0 != n) fail(PB_ERR_INVALID, "Initial primal solution has wrong size.");
   if (ny0 > 0 && ny0 != m) fail(PB_ERR_INVALID, "Initial dual solution has wrong size.");
 
-  fused_ = plan_fused();
+  { PB_TRACE_SCOPE("  plan_fused"); fused_ = plan_fused(); }
   tile_ok_ = fused_ && opts_.fuse == 1 &&
              tile_iteration_supported(stencil_, g_descs_, f_descs_, problem_->right_ref(), problem_->left_ref());
   // slabs: the one-pass kernel stores its edge columns straight into the neighbours' memory, so it
@@ -408,6 +409,7 @@ void BackendPDHG::initialize(const float* h_x0, size_t nx0, const float* h_y0, s
     tile_ok_ = no_tile[0] == 0.0;
   }
   try {
+    PB_TRACE_SCOPE("  allocate iterates");
     x_.resize(n); x_prev_.resize(n); y_.resize(m); y_prev_.resize(m);
     if (tile_ok_) y_stage_.resize(m);
     if (!fused_) {
@@ -420,10 +422,21 @@ void BackendPDHG::initialize(const float* h_x0, size_t nx0, const float* h_y0, s
     if (e.status == PB_ERR_OOM) fail(PB_ERR_OOM, std::string("Out of memory: ") + e.what());
     throw;
   }
-  x_.zero(s); x_prev_.zero(s); y_.zero(s); y_prev_.zero(s);
   if (!fused_) { temp_.zero(s); kx_.zero(s); kx_prev_.zero(s); kty_.zero(s); kty_prev_.zero(s); }
-  if (nx0 > 0) { x_.upload(h_x0, n, s); x_prev_.upload(h_x0, n, s); }   // :288-308
-  if (ny0 > 0) { y_.upload(h_y0, m, s); y_prev_.upload(h_y0, m, s); }
+  // x0 / y0 (:288-308): one host -> device copy each, the previous iterate is a device copy
+  PB_TRACE_SCOPE("  x0 / y0 upload, partial buffers, state");
+  if (nx0 > 0) {
+    upload_from_host(ctx_, x_.data(), h_x0, n);
+    PB_CUDA(cudaMemcpyAsync(x_prev_.data(), x_.data(), n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  } else {
+    x_.zero(s); x_prev_.zero(s);
+  }
+  if (ny0 > 0) {
+    upload_from_host(ctx_, y_.data(), h_y0, m);
+    PB_CUDA(cudaMemcpyAsync(y_prev_.data(), y_.data(), m * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  } else {
+    y_.zero(s); y_prev_.zero(s);
+  }
 
   // partial-sum buffers: one (a, b) pair per CTA of every launch of a pass
   if (fused_) {
@@ -780,51 +793,52 @@ void BackendPDHG::current_solution(float* h_x, float* h_z, float* h_y, float* h_
   const size_t m = problem_->nrows(), n = problem_->ncols();
   cudaStream_t s = ctx_->stream;
   const PdhgState st = fetch_state();
-  if (h_x) x_.download(h_x, n, s);
-  if (h_y) y_.download(h_y, m, s);
+  PB_TRACE_SCOPE("BackendPDHG::current_solution");
+  if (h_x) download_to_host(ctx_, h_x, x_.data(), n);
+  if (h_y) download_to_host(ctx_, h_y, y_.data(), m);
   if (h_w || h_z) {
-    const float* T = problem_->scaling_right();
-    const float* S = problem_->scaling_left();
+    const ScaleRef T = problem_->right_ref(), S = problem_->left_ref();
     if (fused_) {
       // K x, K x_prev and K^T y_prev are not stored in fused mode: rebuild them with the
       // unfused operator, honouring the zero-initialised history of the reference
       if (h_w) {
-        if (sol_a_.size() != n) { sol_a_.resize(n); sol_b_.resize(n); }
-        if (iteration_ <= 1) sol_a_.zero(s);
+        const size_t cap = std::max(n, m);       // one allocation serves w (n) and z (m)
+        if (sol_a_.size() != cap) { sol_a_.resize(cap); sol_b_.resize(cap); }
+        if (iteration_ <= 1) PB_CUDA(cudaMemsetAsync(sol_a_.data(), 0, n * sizeof(float), s));
         else if (comm_) slab_apply(sol_a_.data(), y_prev_.data(), comm_->y_slot(comm_->y_seq - 1), true);
         else problem_->apply_K(sol_a_.data(), y_prev_.data(), true);
         w_variable_kernel<<<sgrid(n), kBlock, 0, s>>>(sol_b_.data(), x_prev_.data(), x_.data(), T,
                                                       sol_a_.data(), n, st.tau);
         PB_CHECK_LAUNCH();
-        sol_b_.download(h_w, n, s);
-        PB_CUDA(cudaStreamSynchronize(s));
+        download_to_host(ctx_, h_w, sol_b_.data(), n);
       }
       if (h_z) {
-        if (sol_a_.size() != m) { sol_a_.resize(m); sol_b_.resize(m); }
+        const size_t cap = std::max(n, m);
+        if (sol_a_.size() != cap) { sol_a_.resize(cap); sol_b_.resize(cap); }
         if (sol_c_.size() != m) sol_c_.resize(m);
-        if (iteration_ == 0) sol_a_.zero(s);
+        if (iteration_ == 0) PB_CUDA(cudaMemsetAsync(sol_a_.data(), 0, m * sizeof(float), s));
         else if (comm_) slab_apply(sol_a_.data(), x_.data(), comm_->x_slot(comm_->x_seq), false);
         else problem_->apply_K(sol_a_.data(), x_.data(), false);
-        if (iteration_ <= 1) sol_b_.zero(s);
+        if (iteration_ <= 1) PB_CUDA(cudaMemsetAsync(sol_b_.data(), 0, m * sizeof(float), s));
         else if (comm_) slab_apply(sol_b_.data(), x_prev_.data(), comm_->x_slot(comm_->x_seq - 1), false);
         else problem_->apply_K(sol_b_.data(), x_prev_.data(), false);
         z_variable_kernel<<<sgrid(m), kBlock, 0, s>>>(sol_c_.data(), y_prev_.data(), y_.data(), S,
                                                       sol_a_.data(), sol_b_.data(), m, st.sigma, st.theta);
         PB_CHECK_LAUNCH();
-        sol_c_.download(h_z, m, s);
+        download_to_host(ctx_, h_z, sol_c_.data(), m);
       }
     } else {
       if (h_w) {
         w_variable_kernel<<<sgrid(n), kBlock, 0, s>>>(temp_.data(), x_prev_.data(), x_.data(), T,
                                                       kty_prev_.data(), n, st.tau);
         PB_CHECK_LAUNCH();
-        temp_.download(h_w, n, s);
+        download_to_host(ctx_, h_w, temp_.data(), n);
       }
       if (h_z) {
         z_variable_kernel<<<sgrid(m), kBlock, 0, s>>>(temp_.data(), y_prev_.data(), y_.data(), S,
                                                       kx_.data(), kx_prev_.data(), m, st.sigma, st.theta);
         PB_CHECK_LAUNCH();
-        temp_.download(h_z, m, s);
+        download_to_host(ctx_, h_z, temp_.data(), m);
       }
     }
   }

@@ -127,10 +127,144 @@ static void check_domain_prox(const ProxList& proxs, size_t n, const std::string
 void Problem::set_scaling_custom(const float* left, size_t nl, const float* right, size_t nr) {
   scaling_type_ = kScalingCustom;
   // the reference stores the SQUARES of the user vectors (problem.cu:344-364)
-  left_host_.resize(nl);
-  right_host_.resize(nr);
-  for (size_t i = 0; i < nl; ++i) left_host_[i] = left[i] * left[i];
-  for (size_t i = 0; i < nr; ++i) right_host_[i] = right[i] * right[i];
+  custom_left_.resize(nl);
+  custom_right_.resize(nr);
+  for (size_t i = 0; i < nl; ++i) custom_left_[i] = left[i] * left[i];
+  for (size_t i = 0; i < nr; ++i) custom_right_[i] = right[i] * right[i];
+}
+
+// ---- ScaleVec ---------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(kBlock) fill_range_kernel(float* __restrict__ v, size_t n, float value) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    v[i] = value;
+}
+
+void ScaleVec::set_segments(size_t n, std::vector<ScaleSeg> segs) {
+  n_ = n;
+  segs_.clear();
+  for (auto& s : segs) {                       // merge neighbours with equal values
+    if (s.begin >= s.end) continue;
+    if (!segs_.empty() && segs_.back().end == s.begin && segs_.back().value == s.value) segs_.back().end = s.end;
+    else segs_.push_back(s);
+  }
+  uniform_ = n == 0 || (segs_.size() == 1 && segs_[0].begin == 0 && segs_[0].end == n);
+  value_ = segs_.empty() ? 1.f : segs_[0].value;
+  host_.clear(); host_.shrink_to_fit();
+  host_valid_ = dev_valid_ = false;
+  dev_.release();
+}
+
+void ScaleVec::set_host(std::vector<float> v) {
+  n_ = v.size();
+  segs_.clear();
+  host_ = std::move(v);
+  host_valid_ = true;
+  dev_valid_ = false;
+  dev_.release();
+  uniform_ = true;
+  for (size_t i = 1; i < n_ && uniform_; ++i) uniform_ = host_[i] == host_[0];
+  value_ = n_ ? host_[0] : 1.f;
+}
+
+const std::vector<float>& ScaleVec::host() const {
+  if (!host_valid_) {
+    host_.resize(n_);
+    for (auto& s : segs_) std::fill(host_.begin() + s.begin, host_.begin() + s.end, s.value);
+    host_valid_ = true;
+  }
+  return host_;
+}
+
+const float* ScaleVec::device(Context* ctx) const {
+  if (!dev_valid_) {
+    dev_.resize(n_);
+    if (!segs_.empty()) {
+      for (auto& s : segs_) {
+        const size_t len = s.end - s.begin;
+        const unsigned grid = (unsigned)std::min<size_t>(grid_for(len), (size_t)ctx->num_sms * 16);
+        fill_range_kernel<<<grid, kBlock, 0, ctx->stream>>>(dev_.data() + s.begin, len, s.value);
+        PB_CHECK_LAUNCH();
+      }
+    } else if (n_) {
+      upload_from_host(ctx, dev_.data(), host_.data(), n_);
+    }
+    dev_valid_ = true;
+  }
+  return dev_.data();
+}
+
+void ScaleVec::swap(ScaleVec& o) {
+  std::swap(n_, o.n_);
+  std::swap(uniform_, o.uniform_);
+  std::swap(value_, o.value_);
+  segs_.swap(o.segs_);
+  host_.swap(o.host_);
+  std::swap(host_valid_, o.host_valid_);
+  dev_.swap(o.dev_);
+  std::swap(dev_valid_, o.dev_valid_);
+}
+
+// Pock-Chambolle preconditioners in segment form: possible when every block has index-independent
+// row / column sums (gradient and zero blocks).  Same arithmetic as the element-wise loop in
+// Problem::initialize: float sum over the blocks in list order, 1. / s in double, empty rows / columns
+// carry the previous value, and the carry runs from the last row into the first column.
+bool Problem::scaling_segments(std::vector<ScaleSeg>& left, std::vector<ScaleSeg>& right) const {
+  const auto& blocks = linop_->blocks();
+  if (blocks.size() > 64) return false;
+  for (auto& b : blocks)
+    if (!b->uniform_sums()) return false;
+  float value = 1;
+  auto build = [&](bool rows, size_t n, float alpha, std::vector<ScaleSeg>& out) {
+    std::vector<size_t> cuts = {0, n};
+    for (auto& b : blocks) {
+      const size_t lo = rows ? b->row() : b->col(), hi = lo + (rows ? b->nrows() : b->ncols());
+      cuts.push_back(std::min(lo, n));
+      cuts.push_back(std::min(hi, n));
+    }
+    std::sort(cuts.begin(), cuts.end());
+    cuts.erase(std::unique(cuts.begin(), cuts.end()), cuts.end());
+    for (size_t k = 0; k + 1 < cuts.size(); ++k) {
+      float sum = 0.f;
+      for (auto& b : blocks) {
+        const size_t lo = rows ? b->row() : b->col(), len = rows ? b->nrows() : b->ncols();
+        if (len && cuts[k] >= lo && cuts[k] < lo + len) sum += rows ? b->row_sum(0, alpha) : b->col_sum(0, alpha);
+      }
+      if (sum > 0) value = static_cast<float>(1. / sum);
+      out.push_back({cuts[k], cuts[k + 1], value});
+    }
+  };
+  build(true, nrows_, scaling_alpha_, left);
+  build(false, ncols_, static_cast<float>(2. - scaling_alpha_), right);
+  return true;
+}
+
+// AveragePreconditioners on segments: a prox without diagsteps whose range lies inside ONE segment
+// averages `cnt` copies of the same value in every group (float running sum, then divide -- the
+// rounding of that sum is reproduced); anything else needs the element-wise path.
+bool Problem::average_segments(std::vector<ScaleSeg>& segs, const ProxList& prox) {
+  for (auto& p : prox) {
+    if (p->diagsteps() || p->size() == 0) continue;
+    const size_t cnt = p->uniform_group_size();
+    if (cnt == 0) return false;
+    const size_t lo = p->index(), hi = lo + p->size();
+    size_t k = 0;
+    while (k < segs.size() && !(segs[k].begin <= lo && lo < segs[k].end)) ++k;
+    if (k == segs.size() || hi > segs[k].end) return false;
+    const float v = segs[k].value;
+    float avg = 0;
+    for (size_t c = 0; c < cnt; ++c) avg += v;
+    avg /= static_cast<float>(cnt);
+    if (avg == v) continue;
+    const ScaleSeg old = segs[k];
+    std::vector<ScaleSeg> repl;
+    if (old.begin < lo) repl.push_back({old.begin, lo, v});
+    repl.push_back({lo, hi, avg});
+    if (hi < old.end) repl.push_back({hi, old.end, v});
+    segs.erase(segs.begin() + k);
+    segs.insert(segs.begin() + k, repl.begin(), repl.end());
+  }
+  return true;
 }
 
 static bool is_uniform(const std::vector<float>& v) {
@@ -141,6 +275,7 @@ static bool is_uniform(const std::vector<float>& v) {
 
 void Problem::initialize() {
   ctx_->bind();
+  PB_TRACE_SCOPE("Problem::initialize");
   linop_->initialize();
   if (!dims_set_) {
     nrows_ = linop_->nrows();
@@ -172,42 +307,66 @@ void Problem::initialize() {
   check_domain_prox(prox_gstar_, ncols_, "prox_gstar");
   check_domain_prox(prox_fstar_, nrows_, "prox_fstar");
 
-  if (scaling_type_ == kScalingAlpha) {
-    // Pock-Chambolle: Sigma_r = 1 / sum_c |K_rc|^alpha, T_c = 1 / sum_r |K_rc|^(2-alpha).
-    // An empty row/column reuses the previous value, and the carry runs from the last row
-    // into the first column because the reference uses one variable (problem.cu:262-287).
-    std::vector<float> rs, cs;
-    linop_->row_sums(scaling_alpha_, rs);
-    linop_->col_sums(static_cast<float>(2. - scaling_alpha_), cs);
-    left_host_.assign(nrows_, 0.f);
-    right_host_.assign(ncols_, 0.f);
-    float value = 1;
-    for (size_t r = 0; r < nrows_; ++r) {
-      const float s = r < rs.size() ? rs[r] : 0.f;
-      if (s > 0) value = static_cast<float>(1. / s);
-      left_host_[r] = value;
+  const ProxList& avg_right = prox_g_.empty() ? prox_gstar_ : prox_g_;
+  const ProxList& avg_left = prox_f_.empty() ? prox_fstar_ : prox_f_;
+  bool done = false;
+  {
+    // piecewise-constant preconditioners (gradient / zero blocks, identity scaling): a handful of
+    // segments instead of nrows + ncols element-wise evaluations, nothing to upload when uniform
+    PB_TRACE_SCOPE("Problem::initialize scaling (segments)");
+    std::vector<ScaleSeg> ls, rs;
+    bool ok = false;
+    if (scaling_type_ == kScalingIdentity) {
+      ls.push_back({0, nrows_, 1.f});
+      rs.push_back({0, ncols_, 1.f});
+      ok = true;
+    } else if (scaling_type_ == kScalingAlpha) {
+      ok = scaling_segments(ls, rs);
     }
-    for (size_t c = 0; c < ncols_; ++c) {
-      const float s = c < cs.size() ? cs[c] : 0.f;
-      if (s > 0) value = static_cast<float>(1. / s);
-      right_host_[c] = value;
+    if (ok && average_segments(rs, avg_right) && average_segments(ls, avg_left)) {
+      left_.set_segments(nrows_, std::move(ls));
+      right_.set_segments(ncols_, std::move(rs));
+      done = true;
     }
-  } else if (scaling_type_ == kScalingIdentity) {
-    left_host_.assign(nrows_, 1.f);
-    right_host_.assign(ncols_, 1.f);
-  } else {
-    if (left_host_.size() != nrows_ || right_host_.size() != ncols_)
-      fail(PB_ERR_INVALID,
-           "Preconditioners/diagonal scaling vectors do not fit the size of linear operator.");
   }
-
-  average_preconditioners(right_host_, prox_g_.empty() ? prox_gstar_ : prox_g_);
-  average_preconditioners(left_host_, prox_f_.empty() ? prox_fstar_ : prox_f_);
-
-  left_uniform_ = is_uniform(left_host_);
-  right_uniform_ = is_uniform(right_host_);
-  d_left_.assign(left_host_, ctx_->stream);
-  d_right_.assign(right_host_, ctx_->stream);
+  if (!done) {
+    PB_TRACE_SCOPE("Problem::initialize scaling (element-wise)");
+    std::vector<float> left_host, right_host;
+    if (scaling_type_ == kScalingAlpha) {
+      // Pock-Chambolle: Sigma_r = 1 / sum_c |K_rc|^alpha, T_c = 1 / sum_r |K_rc|^(2-alpha).
+      // An empty row/column reuses the previous value, and the carry runs from the last row
+      // into the first column because the reference uses one variable (problem.cu:262-287).
+      std::vector<float> rs, cs;
+      linop_->row_sums(scaling_alpha_, rs);
+      linop_->col_sums(static_cast<float>(2. - scaling_alpha_), cs);
+      left_host.assign(nrows_, 0.f);
+      right_host.assign(ncols_, 0.f);
+      float value = 1;
+      for (size_t r = 0; r < nrows_; ++r) {
+        const float s = r < rs.size() ? rs[r] : 0.f;
+        if (s > 0) value = static_cast<float>(1. / s);
+        left_host[r] = value;
+      }
+      for (size_t c = 0; c < ncols_; ++c) {
+        const float s = c < cs.size() ? cs[c] : 0.f;
+        if (s > 0) value = static_cast<float>(1. / s);
+        right_host[c] = value;
+      }
+    } else if (scaling_type_ == kScalingIdentity) {
+      left_host.assign(nrows_, 1.f);
+      right_host.assign(ncols_, 1.f);
+    } else {
+      if (custom_left_.size() != nrows_ || custom_right_.size() != ncols_)
+        fail(PB_ERR_INVALID,
+             "Preconditioners/diagonal scaling vectors do not fit the size of linear operator.");
+      left_host = custom_left_;
+      right_host = custom_right_;
+    }
+    average_preconditioners(right_host, avg_right);
+    average_preconditioners(left_host, avg_left);
+    left_.set_host(std::move(left_host));
+    right_.set_host(std::move(right_host));
+  }
   dualized_ = false;
   initialized_ = true;
 }
@@ -249,9 +408,7 @@ void Problem::dualize() {
   prox_g_.swap(prox_fstar_);
   prox_gstar_.swap(prox_f_);
   std::swap(nrows_, ncols_);
-  d_left_.swap(d_right_);
-  std::swap(left_host_, right_host_);
-  std::swap(left_uniform_, right_uniform_);
+  left_.swap(right_);
   dualized_ = !dualized_;
 }
 
@@ -297,13 +454,13 @@ float Problem::normest(float tol, int max_iters, const float* h_x0) {
   float norm = 0, norm_prev;
   for (int i = 0; i < max_iters; ++i) {
     norm_prev = norm;
-    mul_sqrt_kernel<<<sgrid(n), kBlock, 0, ctx_->stream>>>(x_temp.data(), d_right_.data(), x.data(), n);
+    mul_sqrt_kernel<<<sgrid(n), kBlock, 0, ctx_->stream>>>(x_temp.data(), scaling_right(), x.data(), n);
     apply_K(Ax_temp.data(), x_temp.data(), false);
-    mul_sqrt_kernel<<<sgrid(m), kBlock, 0, ctx_->stream>>>(Ax.data(), d_left_.data(), Ax_temp.data(), m);
+    mul_sqrt_kernel<<<sgrid(m), kBlock, 0, ctx_->stream>>>(Ax.data(), scaling_left(), Ax_temp.data(), m);
     const float norm_Ax = std::sqrt(static_cast<float>(device_sumsq(ctx_, Ax.data(), m, scratch)));
-    mul_sqrt_kernel<<<sgrid(m), kBlock, 0, ctx_->stream>>>(Ax_temp.data(), d_left_.data(), Ax.data(), m);
+    mul_sqrt_kernel<<<sgrid(m), kBlock, 0, ctx_->stream>>>(Ax_temp.data(), scaling_left(), Ax.data(), m);
     apply_K(x_temp.data(), Ax_temp.data(), true);
-    mul_sqrt_kernel<<<sgrid(n), kBlock, 0, ctx_->stream>>>(x.data(), d_right_.data(), x_temp.data(), n);
+    mul_sqrt_kernel<<<sgrid(n), kBlock, 0, ctx_->stream>>>(x.data(), scaling_right(), x_temp.data(), n);
     PB_CHECK_LAUNCH();
     ctx_->launches += 4;
     const float norm_x = std::sqrt(static_cast<float>(device_sumsq(ctx_, x.data(), n, scratch)));

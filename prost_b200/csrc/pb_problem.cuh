@@ -13,6 +13,36 @@ namespace pb {
 
 typedef std::vector<std::shared_ptr<Prox>> ProxList;
 
+// One diagonal preconditioner (Sigma or T).  Gradient-type operators give piecewise-constant -- for a
+// single block constant -- preconditioners, so the vector is kept as a few (begin, end, value) segments
+// and only materialised (host vector / device vector) for the consumers that index it per element.
+// The reference builds both vectors element by element through two virtual calls per row and column
+// (problem.cu:262-287) and uploads them; at 4096^2 that was 0.3 s of a 0.9 s solve here.
+struct ScaleSeg { size_t begin, end; float value; };
+class ScaleVec {
+ public:
+  void set_segments(size_t n, std::vector<ScaleSeg> segs);
+  void set_host(std::vector<float> v);
+  size_t size() const { return n_; }
+  bool uniform() const { return uniform_; }
+  float value() const { return value_; }                 // meaningful when uniform()
+  bool has_segments() const { return !segs_.empty() || n_ == 0; }
+  const std::vector<ScaleSeg>& segments() const { return segs_; }
+  const std::vector<float>& host() const;                // materialises on first use
+  const float* device(Context* ctx) const;               // materialises on first use
+  void swap(ScaleVec& o);
+
+ private:
+  size_t n_ = 0;
+  bool uniform_ = false;
+  float value_ = 1.f;
+  std::vector<ScaleSeg> segs_;                           // empty: only the host vector is authoritative
+  mutable std::vector<float> host_;
+  mutable bool host_valid_ = false;
+  mutable DeviceBuffer<float> dev_;
+  mutable bool dev_valid_ = false;
+};
+
 class Problem {
  public:
   enum Scaling { kScalingIdentity, kScalingAlpha, kScalingCustom };
@@ -49,16 +79,18 @@ class Problem {
   const ProxList& prox_fstar() const { return prox_fstar_; }
 
   // Sigma (left, nrows) and T (right, ncols)
-  const float* scaling_left() const { return d_left_.data(); }
-  const float* scaling_right() const { return d_right_.data(); }
-  const std::vector<float>& scaling_left_host() const { return left_host_; }
-  const std::vector<float>& scaling_right_host() const { return right_host_; }
-  ScaleRef left_ref() const { return left_uniform_ ? ScaleRef{nullptr, left_host_.empty() ? 1.f : left_host_[0]} : ScaleRef{d_left_.data(), 1.f}; }
-  ScaleRef right_ref() const { return right_uniform_ ? ScaleRef{nullptr, right_host_.empty() ? 1.f : right_host_[0]} : ScaleRef{d_right_.data(), 1.f}; }
+  const float* scaling_left() const { return left_.device(ctx_); }
+  const float* scaling_right() const { return right_.device(ctx_); }
+  const std::vector<float>& scaling_left_host() const { return left_.host(); }
+  const std::vector<float>& scaling_right_host() const { return right_.host(); }
+  ScaleRef left_ref() const { return left_.uniform() ? ScaleRef{nullptr, left_.value()} : ScaleRef{left_.device(ctx_), 1.f}; }
+  ScaleRef right_ref() const { return right_.uniform() ? ScaleRef{nullptr, right_.value()} : ScaleRef{right_.device(ctx_), 1.f}; }
   Context* ctx() const { return ctx_; }
 
  private:
   void average_preconditioners(std::vector<float>& precond, const ProxList& prox);
+  bool scaling_segments(std::vector<ScaleSeg>& left, std::vector<ScaleSeg>& right) const;
+  static bool average_segments(std::vector<ScaleSeg>& segs, const ProxList& prox);
 
   Context* ctx_;
   std::shared_ptr<LinearOperator> linop_;
@@ -69,9 +101,8 @@ class Problem {
   // sets alpha = 1 (matlab/+prost/problem.m:10), which is the default here (Appendix B #19)
   Scaling scaling_type_ = kScalingAlpha;
   float scaling_alpha_ = 1.f;
-  std::vector<float> left_host_, right_host_;
-  DeviceBuffer<float> d_left_, d_right_;
-  bool left_uniform_ = false, right_uniform_ = false;
+  std::vector<float> custom_left_, custom_right_;       // SetScalingCustom (squares of the user vectors)
+  ScaleVec left_, right_;
   bool dualized_ = false;
   bool initialized_ = false;
 };

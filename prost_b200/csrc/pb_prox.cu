@@ -234,7 +234,9 @@ class ProxElem : public ProxLeaf {
         // reference: coeffs_[i].size() > 1 => device vector indexed by the group id
         // (prox_elem_operation.inl:82-89,156-167)
         if (len < count) fail(PB_ERR_INVALID, "ProxElemOperation: coefficient array shorter than count");
-        d_coeffs_[k].assign(std::vector<float>(coeffs[k], coeffs[k] + len), ctx->stream);
+        // straight from the caller's buffer (one DMA when it is pinned), no intermediate host copy
+        d_coeffs_[k].resize(len);
+        upload_from_host(ctx, d_coeffs_[k].data(), coeffs[k], len);
         val_[k] = 0.f;
       } else {
         val_[k] = coeffs[k][0];

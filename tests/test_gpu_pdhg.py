@@ -217,3 +217,61 @@ def test_full_size_properties(ctx, size):
     assert abs(lhs - rhs) <= 1e-5 * abs(lhs)
     f = desc["data"]["f"]
     assert rof_energy(desc, a["x"]) < rof_energy(desc, f)
+
+
+def _scaling_cases():
+    N = 12 * 10
+    c1 = syn._coeffs(a=1, b=1, c=1)
+    two_grads = dict(            # two gradient blocks side by side + rows / columns beyond the operator
+        nrows=4 * N + 7, ncols=2 * N + 3,
+        blocks=[("gradient2d", 0, 0, [12, 10, 1, False]), ("gradient2d", 2 * N, N, [12, 10, 1, False])],
+        prox_g=[("elem_operation:1d:square", 0, 2 * N, True, [2 * N, 1, False, syn._coeffs(a=1, b=0.5, c=2)])],
+        prox_fstar=[("elem_operation:norm2:ind_leq0", 0, 2 * N, False, [N, 2, False, c1]),
+                    ("elem_operation:norm2:ind_leq0", 2 * N, 2 * N, False, [N, 2, False, c1])],
+        scaling=("alpha", 1.0))
+    stacked = dict(              # gradient2d on top of a zero block: empty rows carry the last value;
+        nrows=3 * N, ncols=N,    # groups of 3 average 1/2 with a rounded running sum
+        blocks=[("gradient2d", 0, 0, [12, 10, 1, False]), ("zero", 2 * N, 0, [N, N])],
+        prox_g=[("elem_operation:1d:abs", 0, N, False, [N, 1, False, c1])],
+        prox_fstar=[("elem_operation:norm2:ind_leq0", 0, 3 * N, False, [N, 3, False, c1])],
+        scaling=("alpha", 0.5))
+    straddle = dict(             # a prox group range that straddles two segments -> element-wise path
+        nrows=3 * N, ncols=N,
+        blocks=[("gradient2d", 0, 0, [12, 10, 1, False]), ("diags", 2 * N, 0, [N, N, [3.0], [0]])],
+        prox_g=[("elem_operation:1d:abs", 0, N, True, [N, 1, False, c1])],
+        prox_fstar=[("elem_operation:norm2:ind_leq0", 0, 3 * N, False, [N, 3, False, c1])],
+        scaling=("alpha", 1.0))
+    # 3-D gradient: T = 1/6; prox_g without diagsteps over groups of 7 -> the float running sum of seven
+    # copies divided by 7 is NOT 1/6 any more (0.16666666 vs 0.16666667); only part of the range is averaged
+    n3 = 7 * 8 * 6
+    tv3d_avg = dict(syn.tv3d(7, 8, 6))
+    tv3d_avg["prox_g"] = [("elem_operation:norm2:abs", 0, 7 * 16, False, [16, 7, False, c1]),
+                          ("elem_operation:1d:square", 7 * 16, n3 - 7 * 16, True,
+                           [n3 - 7 * 16, 1, False, syn._coeffs(a=1, b=0.25, c=3)])]
+    return {"rof": syn.rof(16, 12), "tvl1": syn.tvl1(12, 8, nc=3), "tv3d": syn.tv3d(6, 8, 5), "tv3d_avg": tv3d_avg,
+            "lifting": syn.lifting(6, 5, 4), "identity": dict(syn.rof(16, 12), scaling=("identity",)),
+            "two_grads": two_grads, "stacked_zero": stacked, "straddle": straddle}
+
+
+@pytest.mark.parametrize("name", sorted(_scaling_cases()))
+def test_scaling_matches_oracle_bitwise(ctx, name):
+    """Problem::Initialize preconditioners (problem.cu:262-306, 502-536): the segment representation
+    (pb_problem.cu: scaling_segments / average_segments) and the element-wise path give the oracle's
+    vectors bit for bit, including the carry over empty rows and the rounded group averages."""
+    from oracle_binding import OracleProblem
+    desc = _scaling_cases()[name]
+    prob = pb.create_problem(ctx, desc)
+    prob.Initialize()
+    left, right = prob.scaling()
+    ol, orr = OracleProblem(desc).scaling()
+    assert left.shape == ol.shape and right.shape == orr.shape
+    assert np.array_equal(left.view(np.uint32), np.asarray(ol, np.float32).view(np.uint32)), name
+    assert np.array_equal(right.view(np.uint32), np.asarray(orr, np.float32).view(np.uint32)), name
+    # a second Initialize (Solver::Initialize after a user call) must not average twice
+    prob.Initialize()
+    l2, r2 = prob.scaling()
+    assert np.array_equal(l2, left) and np.array_equal(r2, right)
+    # the solve that consumes them agrees with the oracle as well
+    got = run_cuda(ctx, desc, 30, stepsize="alg1", residual_iter=5)
+    want = run_oracle(desc, 30, stepsize="alg1", residual_iter=5)
+    assert_parity(got, want, label=f"scaling {name}")
