@@ -112,6 +112,32 @@ def build_problem(pb, syn, ctx, f):
     return prob
 
 
+def time_to_residual(pb, ctx, make_problem, comm=None, max_iters=20000):
+    """BASELINE metric, third part: wall time of Solver.Solve until r_p < eps_p and r_d < eps_d with all four
+    tolerances 1e-4 (backend.hpp:71-74), Alg2 with gamma = 0.05 lambda like the reference's ROF example
+    (matlab/examples/example_rof_primaldual.m:36-38).  Includes the copy-back of the solution."""
+    popts = pb.pdhg_options(scale_steps_operator=0, stepsize="alg2", alg2_gamma=0.05 * LAM,
+                            residual_iter=RESIDUAL_ITER)
+    sopts = pb.solver_options(verbose=0, max_iters=max_iters, tol_rel_primal=1e-4, tol_rel_dual=1e-4,
+                              tol_abs_primal=1e-4, tol_abs_dual=1e-4, num_cback_calls=0)
+    prob = make_problem()
+    be = pb.BackendPDHG(ctx, prob, popts, sopts, comm=comm) if comm else pb.BackendPDHG(ctx, prob, popts, sopts)
+    solver = pb.Solver(prob, be)
+    solver.SetOptions(sopts)
+    solver.Initialize()
+    ctx.synchronize()
+    t0 = time.perf_counter()
+    result = solver.Solve()
+    ctx.synchronize()
+    dt = time.perf_counter() - t0
+    res = be.residuals()
+    return {"seconds": dt, "iterations": int(solver.iterations), "converged": result == pb.Solver.CONVERGED,
+            "stepsize": "alg2, gamma = 0.05 lambda", "tolerances": 1e-4, "max_iters": max_iters,
+            "primal_residual": res["primal_residual"], "dual_residual": res["dual_residual"],
+            "eps_primal": res["eps_primal"], "eps_dual": res["eps_dual"],
+            "what": "Solver.Solve wall time (residual check every 10 iterations) incl. D2H of x, z, y, w"}
+
+
 def run_reference_arm(args, rank, world):
     """Reference arm for this tier: the CPU restatement of prost's PDHG iteration on host cores."""
     if rank != 0:
@@ -305,6 +331,7 @@ def run_slab_arm(args, rank, local_rank, world):
            "what": "per rank: Problem build + Solver.Initialize + Solver.Solve(max_iters=K) + solution copy-back; "
                    "max over ranks"}
     del be2, solver
+    ttr = time_to_residual(pb, ctx, lambda: pb.create_problem(ctx, syn.rof(w, NY, LAM, f=f_pin.numpy())), comm=comm)
     if rank == 0:
         line = {
             "metric": "pdhg_iterations_per_second", "value": value, "unit": "iter/s", "n_gpus": world,
@@ -313,7 +340,7 @@ def run_slab_arm(args, rank, local_rank, world):
             "data": "synthetic", "config": workload_config(world, args.scaling), "clocks": clocks, "e2e": e2e,
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": None,
             "halo_mode": "peer-to-peer stores over NVLink (CUDA IPC)" if p2p else "NCCL send/recv staging",
-            "one_pass_iterations": bool(one_pass),
+            "one_pass_iterations": bool(one_pass), "time_to_residual_1e-4": ttr,
             "residuals_after_run": res,
         }
         print(json.dumps(line), flush=True)
@@ -418,7 +445,10 @@ def main():
     roofline = {
         "bound": "hbm", "kernel": kernel_name,
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": None, "peak_source": peak_src,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel, ncu --set full capture
+        # committed as profiles/r01_tile_ring_full_raw.csv (268.5 + 160.5 MB: part of the previous
+        # iteration's output is still in the 126 MB L2, so less than the algorithmic 469.8 MB)
+        "traffic": 428923648 if tiled else None, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": kernel_bytes, "ms_per_launch": kernel_ms,
         "launch_share": frac_tile if tiled else frac_two,
         "residual_refresh_iterations": {
@@ -469,6 +499,9 @@ def main():
                    "copy-back of x, z, y, w"}
     del be2, solver
 
+    # ---------------- time to residual 1e-4 (third part of the BASELINE metric) ---------------------
+    ttr = time_to_residual(pb, ctx, lambda: build_problem(pb, syn, ctx, f_pin.numpy()))
+
     # ---------------- CPU baseline (oracle port, bounded sample) ------------------------------------
     cpu = None
     if not args.no_cpu_baseline:
@@ -495,7 +528,7 @@ def main():
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(1), "clocks": clocks, "e2e": e2e,
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-        "residuals_after_run": res,
+        "time_to_residual_1e-4": ttr, "residuals_after_run": res,
     }
     print(json.dumps(line), flush=True)
 

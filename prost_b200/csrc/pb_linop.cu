@@ -233,6 +233,14 @@ class BlockDiags : public Block {
     d_factors_.assign(factors_, ctx->stream);
   }
   int kind() const override { return kBlockDiags; }
+  // square block whose diagonals all sit at offset 0 (identity-type blocks, +block/identity.m:12-13):
+  // every row and every column sees every diagonal, so the sums do not depend on the index
+  bool uniform_sums() const override {
+    if (nrows_ != ncols_ || nrows_ == 0) return false;
+    for (long long o : offsets_)
+      if (o != 0) return false;
+    return true;
+  }
   float row_sum(size_t row, float alpha) const override {
     float sum = 0;
     for (size_t i = 0; i < offsets_.size(); ++i) {

@@ -264,6 +264,7 @@ class BackendPDHG : public Backend {
   StencilPlan stencil_;                // specialised gradient passes where the structure matches
   BlockList blocks_;
   std::vector<ProxDesc> g_descs_, f_descs_;
+  std::vector<ScaleRef> g_scale_, f_scale_;     // T / Sigma as seen by each prox (scalar when constant on its range)
   unsigned part_p_cap_ = 0, part_d_cap_ = 0;
   // state + reductions
   PdhgState h_state_;                  // master copy in unfused mode
@@ -284,17 +285,20 @@ bool BackendPDHG::plan_fused() {
     if (b->kind() == kBlockZero) continue;       // contributes nothing
     blocks_.b[blocks_.n++] = b->desc();
   }
-  auto collect = [](const ProxList& list, std::vector<ProxDesc>& out) {
+  auto collect = [&](const ProxList& list, std::vector<ProxDesc>& out, std::vector<ScaleRef>& scale, bool right) {
     out.clear();
+    scale.clear();
     for (auto& p : list) {
       ProxDesc d;
       if (!p->leaf_desc(d, 0)) return false;
       if (dim_cap(d.dim, d.kind) == 0) return false;
       out.push_back(d);
+      const size_t lo = p->index(), hi = p->index() + p->size();
+      scale.push_back(right ? problem_->right_ref(lo, hi) : problem_->left_ref(lo, hi));
     }
     return true;
   };
-  if (!(collect(prox_g_, g_descs_) && collect(prox_fstar_, f_descs_))) return false;
+  if (!(collect(prox_g_, g_descs_, g_scale_, true) && collect(prox_fstar_, f_descs_, f_scale_, false))) return false;
   stencil_ = opts_.fuse == 2 ? StencilPlan() : plan_stencil(K->blocks(), problem_->nrows(), problem_->ncols());
   return true;
 }
@@ -442,13 +446,16 @@ void BackendPDHG::initialize(const float* h_x0, size_t nx0, const float* h_y0, s
   if (fused_) {
     part_d_cap_ = part_p_cap_ = 0;
     const ScaleRef Tr = problem_->right_ref(), Sr = problem_->left_ref();
-    for (auto& d : g_descs_) {
-      const unsigned sg = stencil_primal_launch(ctx_, stencil_, d, x_.data(), y_.data(), y_prev_.data(), Tr,
+    (void)Tr; (void)Sr;
+    for (size_t i = 0; i < g_descs_.size(); ++i) {
+      const ProxDesc& d = g_descs_[i];
+      const unsigned sg = stencil_primal_launch(ctx_, stencil_, d, x_.data(), y_.data(), y_prev_.data(), g_scale_[i],
                                                 nullptr, false, false, true, nullptr, x_prev_.data(), true);
       part_d_cap_ += std::max(sg, fused_grid(ctx_, d));
     }
-    for (auto& d : f_descs_) {
-      const unsigned sg = stencil_dual_launch(ctx_, stencil_, d, y_.data(), x_.data(), x_prev_.data(), Sr,
+    for (size_t i = 0; i < f_descs_.size(); ++i) {
+      const ProxDesc& d = f_descs_[i];
+      const unsigned sg = stencil_dual_launch(ctx_, stencil_, d, y_.data(), x_.data(), x_prev_.data(), f_scale_[i],
                                               nullptr, false, true, nullptr, y_prev_.data(), true);
       part_p_cap_ += std::max(sg, fused_grid(ctx_, d));
     }
@@ -511,12 +518,14 @@ void BackendPDHG::iteration_fused() {
     unsigned off = 0;
     unsigned xs = 0, ys = 0;
     if (comm_) { xs = ++comm_->x_seq; slab_primal_halo(xs); }
-    for (auto& d : g_descs_) {
-      unsigned g = stencil_primal_launch(ctx_, stencil_, d, x_.data(), y_.data(), y_prev_.data(), T, st,
+    for (size_t i = 0; i < g_descs_.size(); ++i) {
+      const ProxDesc& d = g_descs_[i];
+      const ScaleRef Td = g_scale_[i];
+      unsigned g = stencil_primal_launch(ctx_, stencil_, d, x_.data(), y_.data(), y_prev_.data(), Td, st,
                                          iteration_ == 0, iteration_ <= 1, check,
                                          part_d_.data() + 2 * (size_t)off, x_prev_.data());
       if (g == 0)
-        g = fused_primal_launch(ctx_, d, blocks_, x_.data(), y_.data(), y_prev_.data(), T, st, iteration_ == 0,
+        g = fused_primal_launch(ctx_, d, blocks_, x_.data(), y_.data(), y_prev_.data(), Td, st, iteration_ == 0,
                                 iteration_ <= 1, check, part_d_.data() + 2 * (size_t)off, x_prev_.data());
       off += g;
     }
@@ -527,11 +536,13 @@ void BackendPDHG::iteration_fused() {
 
     // dual pass: y_prev_ <- prox_f*(y_ + sigma S K(2x^{k+1} - x^k)) (theta-extrapolated), then swap
     off = 0;
-    for (auto& d : f_descs_) {
-      unsigned g = stencil_dual_launch(ctx_, stencil_, d, y_.data(), x_.data(), x_prev_.data(), S, st,
+    for (size_t i = 0; i < f_descs_.size(); ++i) {
+      const ProxDesc& d = f_descs_[i];
+      const ScaleRef Sd = f_scale_[i];
+      unsigned g = stencil_dual_launch(ctx_, stencil_, d, y_.data(), x_.data(), x_prev_.data(), Sd, st,
                                        iteration_ == 0, check, part_p_.data() + 2 * (size_t)off, y_prev_.data());
       if (g == 0)
-        g = fused_dual_launch(ctx_, d, blocks_, y_.data(), x_.data(), x_prev_.data(), S, st, iteration_ == 0,
+        g = fused_dual_launch(ctx_, d, blocks_, y_.data(), x_.data(), x_prev_.data(), Sd, st, iteration_ == 0,
                               check, part_p_.data() + 2 * (size_t)off, y_prev_.data());
       off += g;
     }

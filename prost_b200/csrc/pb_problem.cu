@@ -194,6 +194,13 @@ const float* ScaleVec::device(Context* ctx) const {
   return dev_.data();
 }
 
+ScaleRef ScaleVec::ref(Context* ctx, size_t begin, size_t end) const {
+  if (uniform_) return ScaleRef{nullptr, value_};
+  for (auto& s : segs_)
+    if (s.begin <= begin && begin < s.end && end <= s.end) return ScaleRef{nullptr, s.value};
+  return ScaleRef{device(ctx), 1.f};
+}
+
 void ScaleVec::swap(ScaleVec& o) {
   std::swap(n_, o.n_);
   std::swap(uniform_, o.uniform_);

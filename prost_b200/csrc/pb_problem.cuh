@@ -30,6 +30,8 @@ class ScaleVec {
   const std::vector<ScaleSeg>& segments() const { return segs_; }
   const std::vector<float>& host() const;                // materialises on first use
   const float* device(Context* ctx) const;               // materialises on first use
+  // scalar when every entry of [begin, end) has the same value (one segment), else the device vector
+  ScaleRef ref(Context* ctx, size_t begin, size_t end) const;
   void swap(ScaleVec& o);
 
  private:
@@ -85,6 +87,10 @@ class Problem {
   const std::vector<float>& scaling_right_host() const { return right_.host(); }
   ScaleRef left_ref() const { return left_.uniform() ? ScaleRef{nullptr, left_.value()} : ScaleRef{left_.device(ctx_), 1.f}; }
   ScaleRef right_ref() const { return right_.uniform() ? ScaleRef{nullptr, right_.value()} : ScaleRef{right_.device(ctx_), 1.f}; }
+  // the same for the index range of one prox: gradient rows and identity rows of a stacked operator have
+  // different, but per range constant, preconditioners -- the fused passes then read no Sigma / T at all
+  ScaleRef left_ref(size_t begin, size_t end) const { return left_.ref(ctx_, begin, end); }
+  ScaleRef right_ref(size_t begin, size_t end) const { return right_.ref(ctx_, begin, end); }
   Context* ctx() const { return ctx_; }
 
  private:

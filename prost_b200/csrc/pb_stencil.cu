@@ -8,8 +8,10 @@
 // protocol of the slab decomposition compiled in (SLAB = true).  The single-GPU instantiations
 // carry none of it (no extra registers, branches or barriers).
 #include "pb_stencil.cuh"
+#include "pb_stencil_staged.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 #ifndef PB_STENCIL_PART
 #error "compile with -DPB_STENCIL_PART=<0..3>"
@@ -63,6 +65,21 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 
 static inline unsigned grid_threads(size_t threads) {
   return (unsigned)((threads + kStencilBlock - 1) / kStencilBlock);
+}
+
+// per-pixel label groups: operands staged through shared memory (pb_stencil_staged.cuh); PB_STAGED=0 selects
+// the plain register kernels (A/B experiments)
+static inline bool staged_enabled() {
+  static const bool on = [] { const char* e = getenv("PB_STAGED"); return !e || atoi(e) != 0; }();
+  return on;
+}
+static inline unsigned staged_grid(size_t threads) {
+  return (unsigned)((threads + kStagedBlock - 1) / kStagedBlock);
+}
+template <class Kernel>
+static bool staged_configure(Kernel kernel, size_t smem) {
+  // dynamic shared memory beyond 48 KB has to be opted into once per kernel
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
 }
 
 #if PB_STENCIL_PART == 0
@@ -216,15 +233,58 @@ static void simplex_launch(Context* ctx, unsigned grid, const GradGeom& g, const
         g, d, x, y, y_prev, T, st, kty_zero, ktyprev_zero, partials, x_out);
 }
 
+template <int CAPL, bool HAS_ID, bool CHECK>
+static bool simplex_staged_launch_k(Context* ctx, unsigned grid, const GradGeom& g, const ProxDesc& d, const float* x,
+                                    const float* y, const float* y_prev, float Tval, const PdhgState* st,
+                                    bool ktyprev_zero, double* partials, float* x_out) {
+  auto kernel = grad_primal_simplex_staged_kernel<CAPL, HAS_ID, CHECK, kSlab>;
+  const size_t smem = primal_staged_smem(CAPL, HAS_ID, CHECK);       // sized for the y_prev operands as well
+  static const bool ok = staged_configure(kernel, smem);
+  if (!ok) { cudaGetLastError(); return false; }
+  kernel<<<grid, kStagedBlock, smem, ctx->stream>>>(g, d, x, y, y_prev, Tval, st, ktyprev_zero ? 1 : 0, partials,
+                                                    x_out);
+  return true;
+}
+
+template <int CAPL>
+static bool simplex_staged_launch(Context* ctx, unsigned grid, const GradGeom& g, const ProxDesc& d, const float* x,
+                                  const float* y, const float* y_prev, float Tval, const PdhgState* st,
+                                  bool ktyprev_zero, bool check, double* partials, float* x_out) {
+#define PB_ARGS ctx, grid, g, d, x, y, y_prev, Tval, st, ktyprev_zero, partials, x_out
+  if (g.has_id) return check ? simplex_staged_launch_k<CAPL, true, true>(PB_ARGS) : simplex_staged_launch_k<CAPL, true, false>(PB_ARGS);
+  return check ? simplex_staged_launch_k<CAPL, false, true>(PB_ARGS) : simplex_staged_launch_k<CAPL, false, false>(PB_ARGS);
+#undef PB_ARGS
+}
+
 PB_DECLARE_PRIMAL(PB_FLAVOUR(stencil_primal_simplex_launch)) {
   // simplex over the labels of a pixel: planar, count = nx*ny, dim = L (2-D gradient only)
   if (three_d || d.interleaved || d.moreau || d.count != g0.nxny || d.dim != g0.L || g0.L < 2 || g0.L > 32)
     return 0;
   GradGeom g = with_vec(g0, 1);
+  const int cap = g.L <= 4 ? 4 : g.L <= 8 ? 8 : g.L <= 16 ? 16 : 32;
+  // operands staged through shared memory (every iteration but the first, uniform T)
+  if (!kty_zero && !T.ptr && staged_enabled()) {
+    const unsigned sgrid = staged_grid((size_t)g.q * g.nx);
+    if (dry_run || sgrid == 0) return sgrid;
+    g.halo.n_edge_ctas = staged_grid(g.q);
+    bool launched = false;
+#define PB_ARGS ctx, sgrid, g, d, x, y, y_prev, T.val, st, ktyprev_zero, check, partials, x_out
+    switch (cap) {
+      case 4: launched = simplex_staged_launch<4>(PB_ARGS); break;
+      case 8: launched = simplex_staged_launch<8>(PB_ARGS); break;
+      case 16: launched = simplex_staged_launch<16>(PB_ARGS); break;
+      default: launched = simplex_staged_launch<32>(PB_ARGS); break;
+    }
+#undef PB_ARGS
+    if (launched) {
+      PB_CHECK_LAUNCH();
+      ctx->launches++;
+      return sgrid;
+    }
+  }
   g.halo.n_edge_ctas = count_edge_ctas(g.q, 1);
   const unsigned grid = grid_threads((size_t)g.q * g.nx);
   if (dry_run || grid == 0) return grid;
-  const int cap = g.L <= 4 ? 4 : g.L <= 8 ? 8 : g.L <= 16 ? 16 : 32;
 #define PB_ARGS ctx, grid, g, d, x, y, y_prev, T, st, kty_zero, ktyprev_zero, check, partials, x_out
 #define PB_CASE(C) \
   case C: if (g.has_id) simplex_launch<C, true>(PB_ARGS); else simplex_launch<C, false>(PB_ARGS); break;
@@ -237,6 +297,30 @@ PB_DECLARE_PRIMAL(PB_FLAVOUR(stencil_primal_simplex_launch)) {
 }
 
 #elif PB_STENCIL_PART == 2
+
+template <int CAPL, int FN, bool CHECK>
+static bool dual_staged_launch_k(Context* ctx, unsigned grid, const GradGeom& g, const ProxDesc& d, const float* y,
+                                 const float* x_new, const float* x_old, float Sval, const PdhgState* st,
+                                 bool kxprev_zero, double* partials, float* y_out) {
+  auto kernel = grad_dual_norm2_staged_kernel<CAPL, FN, CHECK, kSlab>;
+  const size_t smem = dual_staged_smem(CAPL);
+  static const bool ok = staged_configure(kernel, smem);
+  if (!ok) { cudaGetLastError(); return false; }
+  kernel<<<grid, kStagedBlock, smem, ctx->stream>>>(g, d, y, x_new, x_old, Sval, st, kxprev_zero ? 1 : 0, partials,
+                                                    y_out);
+  return true;
+}
+
+template <int CAPL>
+static bool dual_staged_launch(Context* ctx, unsigned grid, const GradGeom& g, const ProxDesc& d, const float* y,
+                               const float* x_new, const float* x_old, float Sval, const PdhgState* st,
+                               bool kxprev_zero, bool check, double* partials, float* y_out) {
+#define PB_ARGS ctx, grid, g, d, y, x_new, x_old, Sval, st, kxprev_zero, partials, y_out
+  if (d.fn == PB_FUN_IND_LEQ0)
+    return check ? dual_staged_launch_k<CAPL, PB_FUN_IND_LEQ0, true>(PB_ARGS) : dual_staged_launch_k<CAPL, PB_FUN_IND_LEQ0, false>(PB_ARGS);
+  return check ? dual_staged_launch_k<CAPL, -1, true>(PB_ARGS) : dual_staged_launch_k<CAPL, -1, false>(PB_ARGS);
+#undef PB_ARGS
+}
 
 template <int VEC, int CAPL, int FN, bool THREE_D>
 static void dual_launch_fn(Context* ctx, unsigned grid, const GradGeom& g, const ProxDesc& d, const float* y,
@@ -276,6 +360,27 @@ PB_DECLARE_DUAL(PB_FLAVOUR(stencil_dual_norm2_launch)) {
     if (d.coeffs.ptr[k] && !aligned16(d.coeffs.ptr[k])) vec4 = false;
   if (per_pixel && g0.L > 4) vec4 = false;             // keep the group within the register budget
   if (g0.halo.has_right && vec4 && !aligned16(g0.halo.out)) vec4 = false;
+  // per-pixel groups over more than 4 labels, scalar weights, uniform Sigma on these rows: operands staged
+  // through shared memory (pb_stencil_staged.cuh)
+  bool scalar_coeffs = !d.moreau && !S.ptr;
+  for (int k = 0; k < 7; ++k) scalar_coeffs = scalar_coeffs && !d.coeffs.ptr[k];
+  if (per_pixel && g0.L > 4 && scalar_coeffs && staged_enabled()) {
+    GradGeom gs = with_vec(g0, 1);
+    const unsigned sgrid = staged_grid((size_t)gs.q * gs.nx);
+    if (dry_run || sgrid == 0) return sgrid;
+    gs.halo.n_edge_ctas = staged_grid(gs.q);
+    bool launched = false;
+#define PB_ARGS ctx, sgrid, gs, d, y, x_new, x_old, S.val, st, kxprev_zero, check, partials, y_out
+    if (gs.L <= 8) launched = dual_staged_launch<8>(PB_ARGS);
+    else if (gs.L <= 16) launched = dual_staged_launch<16>(PB_ARGS);
+    else launched = dual_staged_launch<32>(PB_ARGS);
+#undef PB_ARGS
+    if (launched) {
+      PB_CHECK_LAUNCH();
+      ctx->launches++;
+      return sgrid;
+    }
+  }
   const int vec = vec4 ? 4 : 1;
   GradGeom g = with_vec(g0, vec);
   g.halo.n_edge_ctas = count_edge_ctas(g.q, per_voxel ? g.L : 1u);

@@ -110,24 +110,35 @@ def tv3d(nx, ny, L, lam=10.0, f=None):
         scaling=("alpha", 1.0), data=dict(f=f))
 
 
-def lifting(nx, ny, L, lam=1.0):
+def lifting(nx, ny, L, lam=1.0, x0=0, x1=None):
     """C3: lifted multilabel stand-in built from in-tree operators only:
     K = [grad2d over L label planes ; identity], g = simplex over labels, f* = norm-ball on the
-    gradient rows + epigraph of a quadratic on the identity rows."""
-    N = nx * ny
-    NL = N * L
-    f = image(nx, ny)
+    gradient rows + epigraph of a quadratic on the identity rows.
+
+    ``x0, x1``: only the column slab [x0, x1) of the nx-column problem (what one rank of the slab
+    decomposition owns); every coefficient is a function of the GLOBAL pixel index, so the slab equals
+    ``distributed.shard_description`` of the global description without ever building that."""
+    x1 = nx if x1 is None else x1
+    w = x1 - x0
+    N, Nw = nx * ny, w * ny
+    NL = Nw * L
+    f = image(nx, ny, x0=x0, x1=x1)
     lab = (np.arange(L, dtype=np.float32) / L)[:, None]
     rho = ((lab - f[None, :]) ** 2).astype(np.float32).reshape(-1)          # unary cost, planar by label
-    b = (2.0 * uniform(30, np.arange(NL // 2, dtype=np.uint64)) - 1.0).astype(np.float32)
+    # pairs (x_i, y_i) = (r[i], r[NL/2 + i]): i runs over the first NL/2 entries of the label-planar vector,
+    # i.e. label planes 0 .. L/2-1 (and half of plane (L-1)/2 when L is odd); b_i is a hash of the GLOBAL index
+    pix = (np.arange(x0, x1, dtype=np.uint64)[:, None] * np.uint64(ny) + np.arange(ny, dtype=np.uint64)[None, :]).reshape(-1)
+    j = np.arange(NL // 2, dtype=np.uint64)
+    gidx = (j // np.uint64(Nw)) * np.uint64(N) + pix[(j % np.uint64(Nw)).astype(np.int64)]
+    b = (2.0 * uniform(30, gidx) - 1.0).astype(np.float32)
     c = -rho[: NL // 2]
     return dict(
         nrows=3 * NL, ncols=NL,
-        blocks=[("gradient2d", 0, 0, [nx, ny, L, False]),
+        blocks=[("gradient2d", 0, 0, [w, ny, L, False]),
                 ("diags", 2 * NL, 0, [NL, NL, [1.0], [0]])],
-        prox_g=[("elem_operation:ind_simplex", 0, NL, False, [N, L, False])],
+        prox_g=[("elem_operation:ind_simplex", 0, NL, False, [Nw, L, False])],
         prox_fstar=[("elem_operation:norm2:ind_leq0", 0, 2 * NL, False,
-                     [N, 2 * L, False, _coeffs(a=1.0 / lam, b=1, c=1)]),
+                     [Nw, 2 * L, False, _coeffs(a=1.0 / lam, b=1, c=1)]),
                     ("ind_epi_quad", 2 * NL, NL, False, [NL // 2, 2, False, [[1.0], b, c]])],
         scaling=("alpha", 1.0), data=dict(f=f))
 
