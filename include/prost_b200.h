@@ -63,6 +63,10 @@ int pb_device_count(void);                    /* reference: mex "list_gpus", pro
 int pb_context_create(int device, void* stream, pb_context** out);
 void pb_context_destroy(pb_context* ctx);
 int pb_context_synchronize(pb_context* ctx);
+/* Device buffers released by destroyed problems / backends are kept in a per-process cache for the next
+ * solve (the reference frees everything in its destructors and, from MATLAB, resets the device before every
+ * solve: prost.cpp:69-70).  This returns all cached blocks to the driver.  PB_POOL_MB=0 disables the cache. */
+void pb_release_cached_memory(void);
 void* pb_context_stream(pb_context* ctx);
 int pb_context_device(pb_context* ctx);
 

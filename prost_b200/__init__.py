@@ -19,3 +19,8 @@ def version():
 
 def device_count():
     return lib.pb_device_count()
+
+
+def release_cached_memory():
+    """Returns the device buffers cached from destroyed problems / backends to the driver."""
+    lib.pb_release_cached_memory()

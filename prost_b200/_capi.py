@@ -74,6 +74,7 @@ SIGNATURES = {
     "pb_context_create": (C.c_int, [C.c_int, C.c_void_p, handle_p]),
     "pb_context_destroy": (None, [handle]),
     "pb_context_synchronize": (C.c_int, [handle]),
+    "pb_release_cached_memory": (None, []),
     "pb_context_stream": (C.c_void_p, [handle]),
     "pb_context_device": (C.c_int, [handle]),
     "pb_malloc": (C.c_int, [handle, C.c_size_t, handle_p]),

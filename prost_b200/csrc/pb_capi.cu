@@ -101,6 +101,8 @@ void pb_context_destroy(pb_context* c) {
   delete c;
 }
 
+void pb_release_cached_memory(void) { pb::device_cache_release(); }
+
 int pb_context_synchronize(pb_context* c) {
   return guarded([&] {
     require(c != nullptr, "NULL context");

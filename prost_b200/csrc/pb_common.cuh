@@ -98,6 +98,18 @@ struct TraceScope {
 #define PB_TRACE_CAT(a, b) PB_TRACE_CAT2(a, b)
 #define PB_TRACE_SCOPE(name) ::pb::TraceScope PB_TRACE_CAT(pb_trace_scope_, __LINE__)(name)
 
+// ---- device memory (pb_hostio.cu) -----------------------------------------------------------------------
+// cudaMalloc / cudaFree with a per-process cache of released blocks (exact-size reuse): a solver that is
+// created, solved and destroyed repeatedly -- the reference's usage, one prost::Solver per solve -- asks for
+// the same few buffer sizes every time, and cudaMalloc right after cudaFree of gigabytes costs up to 100 ms
+// (measured: 3-97 ms for the first allocation of a solve), more than 500 fused PDHG iterations at 4096^2.
+// A block enters the cache only after the device is idle (cudaDeviceSynchronize, like the implicit
+// synchronisation of cudaFree), so it can be handed to any stream afterwards.  PB_POOL_MB caps the cached
+// bytes per process (default 32768, 0 disables); pb_release_cached_memory() returns everything to the driver.
+void* device_alloc(size_t bytes);                  // throws Error(PB_ERR_OOM / PB_ERR_CUDA)
+void device_free(void* p, size_t bytes, int device);
+void device_cache_release();
+
 // RAII device allocation (replaces thrust::device_vector members of the reference).
 template <typename T>
 class DeviceBuffer {
@@ -106,9 +118,9 @@ class DeviceBuffer {
   explicit DeviceBuffer(size_t n) { resize(n); }
   DeviceBuffer(const DeviceBuffer&) = delete;
   DeviceBuffer& operator=(const DeviceBuffer&) = delete;
-  DeviceBuffer(DeviceBuffer&& o) noexcept : ptr_(o.ptr_), n_(o.n_) { o.ptr_ = nullptr; o.n_ = 0; }
+  DeviceBuffer(DeviceBuffer&& o) noexcept : ptr_(o.ptr_), n_(o.n_), dev_(o.dev_) { o.ptr_ = nullptr; o.n_ = 0; }
   DeviceBuffer& operator=(DeviceBuffer&& o) noexcept {
-    if (this != &o) { release(); ptr_ = o.ptr_; n_ = o.n_; o.ptr_ = nullptr; o.n_ = 0; }
+    if (this != &o) { release(); ptr_ = o.ptr_; n_ = o.n_; dev_ = o.dev_; o.ptr_ = nullptr; o.n_ = 0; }
     return *this;
   }
   ~DeviceBuffer() { release(); }
@@ -116,20 +128,12 @@ class DeviceBuffer {
   void resize(size_t n) {
     release();
     if (n == 0) return;
-    void* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, n * sizeof(T));
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      std::ostringstream ss;
-      ss << "Out of memory: cudaMalloc of " << n * sizeof(T) << " bytes failed ("
-         << cudaGetErrorString(e) << ")";
-      fail(e == cudaErrorMemoryAllocation ? PB_ERR_OOM : PB_ERR_CUDA, ss.str());
-    }
-    ptr_ = static_cast<T*>(p);
+    ptr_ = static_cast<T*>(device_alloc(n * sizeof(T)));
+    cudaGetDevice(&dev_);
     n_ = n;
   }
   void release() {
-    if (ptr_) cudaFree(ptr_);
+    if (ptr_) device_free(ptr_, n_ * sizeof(T), dev_);
     ptr_ = nullptr;
     n_ = 0;
   }
@@ -150,11 +154,12 @@ class DeviceBuffer {
   T* data() { return ptr_; }
   const T* data() const { return ptr_; }
   size_t size() const { return n_; }
-  void swap(DeviceBuffer& o) { std::swap(ptr_, o.ptr_); std::swap(n_, o.n_); }
+  void swap(DeviceBuffer& o) { std::swap(ptr_, o.ptr_); std::swap(n_, o.n_); std::swap(dev_, o.dev_); }
 
  private:
   T* ptr_ = nullptr;
   size_t n_ = 0;
+  int dev_ = 0;
 };
 
 // grid size for a 1-thread-per-item streaming kernel

@@ -17,9 +17,113 @@
 
 #include <algorithm>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <thread>
 
 namespace pb {
+
+// ---- device memory cache (pb_common.cuh: device_alloc / device_free) ---------------------------------------
+namespace {
+
+struct DeviceCache {
+  std::mutex mu;
+  std::multimap<std::pair<int, size_t>, void*> blocks;    // (device, bytes) -> released block
+  size_t cached = 0;
+  size_t cap = [] {
+    const char* e = getenv("PB_POOL_MB");
+    return (e ? static_cast<size_t>(atoll(e)) : size_t(32768)) << 20;
+  }();
+};
+DeviceCache& device_cache() {
+  static DeviceCache* c = new DeviceCache();     // never destroyed: no CUDA calls during static teardown
+  return *c;
+}
+constexpr size_t kMinCachedBytes = 1u << 20;     // small blocks are cheap to allocate; keep the map short
+
+void release_blocks_of(int device) {              // device < 0: all devices
+  DeviceCache& c = device_cache();
+  std::vector<std::pair<int, void*>> victims;
+  {
+    std::lock_guard<std::mutex> lock(c.mu);
+    for (auto it = c.blocks.begin(); it != c.blocks.end();) {
+      if (device < 0 || it->first.first == device) {
+        victims.emplace_back(it->first.first, it->second);
+        c.cached -= it->first.second;
+        it = c.blocks.erase(it);
+      } else {
+        ++it;
+      }
+    }
+  }
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (auto& v : victims) {
+    cudaSetDevice(v.first);
+    cudaFree(v.second);
+  }
+  cudaSetDevice(cur);
+  cudaGetLastError();
+}
+
+}  // namespace
+
+void* device_alloc(size_t bytes) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  DeviceCache& c = device_cache();
+  if (bytes >= kMinCachedBytes) {
+    std::lock_guard<std::mutex> lock(c.mu);
+    auto it = c.blocks.find(std::make_pair(dev, bytes));
+    if (it != c.blocks.end()) {
+      void* p = it->second;
+      c.cached -= bytes;
+      c.blocks.erase(it);
+      return p;
+    }
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e == cudaErrorMemoryAllocation) {             // give the cached blocks back and try once more
+    cudaGetLastError();
+    release_blocks_of(dev);
+    e = cudaMalloc(&p, bytes);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    std::ostringstream ss;
+    ss << "Out of memory: cudaMalloc of " << bytes << " bytes failed (" << cudaGetErrorString(e) << ")";
+    fail(e == cudaErrorMemoryAllocation ? PB_ERR_OOM : PB_ERR_CUDA, ss.str());
+  }
+  return p;
+}
+
+void device_free(void* p, size_t bytes, int device) {
+  if (!p) return;
+  DeviceCache& c = device_cache();
+  if (bytes >= kMinCachedBytes && c.cap > 0) {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cur != device) cudaSetDevice(device);
+    // the block may still be in use by enqueued work: wait, exactly like cudaFree would
+    const cudaError_t e = cudaDeviceSynchronize();
+    if (cur != device) cudaSetDevice(cur);
+    if (e == cudaSuccess) {
+      std::lock_guard<std::mutex> lock(c.mu);
+      if (c.cached + bytes <= c.cap) {
+        c.blocks.emplace(std::make_pair(device, bytes), p);
+        c.cached += bytes;
+        return;
+      }
+    } else {
+      cudaGetLastError();
+    }
+  }
+  cudaFree(p);
+  cudaGetLastError();
+}
+
+void device_cache_release() { release_blocks_of(-1); }
 
 namespace {
 

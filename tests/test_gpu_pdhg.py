@@ -275,3 +275,22 @@ def test_scaling_matches_oracle_bitwise(ctx, name):
     got = run_cuda(ctx, desc, 30, stepsize="alg1", residual_iter=5)
     want = run_oracle(desc, 30, stepsize="alg1", residual_iter=5)
     assert_parity(got, want, label=f"scaling {name}")
+
+
+def test_device_buffer_cache_reuse_and_release(ctx):
+    """Released device buffers are cached for the next solve (pb_common.cuh: device_alloc); a second
+    solve on recycled blocks gives the same bits, and pb_release_cached_memory() empties the cache."""
+    import torch
+    desc = syn.rof(512, 512)                      # iterates of 1 and 2 MB: at / above the caching threshold
+    first = run_cuda(ctx, desc, 40, stepsize="alg1", residual_iter=5)
+    del first["backend"], first["problem"]
+    free_cached = torch.cuda.mem_get_info()[0]
+    second = run_cuda(ctx, desc, 40, stepsize="alg1", residual_iter=5)
+    for k in ("x", "y", "z", "w"):
+        assert np.array_equal(first[k], second[k]), k
+    del second["backend"], second["problem"]
+    pb.release_cached_memory()
+    free_released = torch.cuda.mem_get_info()[0]
+    assert free_released >= free_cached          # the cached blocks went back to the driver
+    third = run_cuda(ctx, desc, 40, stepsize="alg1", residual_iter=5)
+    assert np.array_equal(first["x"], third["x"])
