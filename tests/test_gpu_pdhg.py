@@ -291,6 +291,7 @@ def test_device_buffer_cache_reuse_and_release(ctx):
     del second["backend"], second["problem"]
     pb.release_cached_memory()
     free_released = torch.cuda.mem_get_info()[0]
-    assert free_released >= free_cached          # the cached blocks went back to the driver
+    # the cached blocks went back to the driver (slack: the driver's own heaps may have grown meanwhile)
+    assert free_released + (16 << 20) >= free_cached
     third = run_cuda(ctx, desc, 40, stepsize="alg1", residual_iter=5)
     assert np.array_equal(first["x"], third["x"])

@@ -96,3 +96,42 @@ def test_gloo_slab_iteration_matches_the_oracle(world):
     assert rep["err_x"] <= 1e-5 and rep["err_y"] <= 1e-5, rep
     for got, want in zip(rep["res"], rep["res_oracle"]):
         assert abs(got - want) <= 1e-4 * max(abs(want), 1e-6), rep
+
+
+def test_slab_lifting_generator_equals_sharded_global_description():
+    """synthetic.lifting(..., x0, x1) builds one rank's column slab directly (bench_lifting.py at 2048^2 x 32
+    never materialises the global problem); it must be exactly shard_description() of the global description,
+    and for x0 = 0, x1 = nx (odd label counts included) the global description itself."""
+    import numpy as np
+    from prost_b200 import distributed as pbd
+    from prost_b200 import synthetic as syn
+
+    def same(a, b):
+        assert a["nrows"] == b["nrows"] and a["ncols"] == b["ncols"]
+        for ba, bb in zip(a["blocks"], b["blocks"]):
+            assert ba[0] == bb[0] and int(ba[1]) == int(bb[1]) and int(ba[2]) == int(bb[2])
+            if ba[0] == "gradient2d":
+                assert [int(v) for v in ba[3][:3]] == [int(v) for v in bb[3][:3]]
+            else:
+                assert int(ba[3][0]) == int(bb[3][0]) and int(ba[3][1]) == int(bb[3][1])
+        for key in ("prox_g", "prox_fstar"):
+            assert len(a[key]) == len(b[key])
+            for pa, pb_ in zip(a[key], b[key]):
+                assert pa[0] == pb_[0] and [int(v) for v in pa[1:3]] == [int(v) for v in pb_[1:3]] and pa[3] == pb_[3]
+                assert [int(v) for v in pa[4][:2]] == [int(v) for v in pb_[4][:2]]
+                if pa[0] == "ind_epi_quad":
+                    for u, v in zip(pa[4][3], pb_[4][3]):
+                        assert np.array_equal(np.asarray(u, np.float32).ravel(), np.asarray(v, np.float32).ravel())
+
+    nx, ny, L = 12, 8, 6
+    glob = syn.lifting(nx, ny, L)
+    for world in (1, 2, 3):
+        part = pbd.SlabPartition(nx, world)
+        for r in range(world):
+            x0, x1 = part.range(r)
+            same(pbd.shard_description(glob, part, r), syn.lifting(nx, ny, L, x0=x0, x1=x1))
+    # odd L: the pair index runs over the first NL/2 entries of the label-planar vector
+    d = syn.lifting(12, 9, 5)
+    b = d["prox_fstar"][1][4][3][1]
+    ref = (2.0 * syn.uniform(30, np.arange(12 * 9 * 5 // 2, dtype=np.uint64)) - 1.0).astype(np.float32)
+    assert np.array_equal(b, ref)
