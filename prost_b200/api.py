@@ -559,7 +559,9 @@ class Solver:
             da = np.ctypeslib.as_array(d, shape=(nd,))
             return int(bool(self._interm(it, pa, da)))
 
-        scb, icb = _capi.STOPPING_CB(stop), _capi.INTERM_CB(interm)
+        # no user callback -> NULL (the C loop then knows that nothing can stop it between two events)
+        scb = _capi.STOPPING_CB(stop) if self._stop else _capi.STOPPING_CB()
+        icb = _capi.INTERM_CB(interm)
         result, iters = C.c_int(), C.c_int()
         check(lib.pb_solver_solve(self.backend._h, C.byref(self.opts), scb, icb, None, _fp(x), _fp(z), _fp(y),
                                   _fp(w), C.byref(result), C.byref(iters)))

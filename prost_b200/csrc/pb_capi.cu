@@ -1,6 +1,7 @@
 // pb_capi.cu -- extern "C" boundary (include/prost_b200.h) and the Solver loop
 // (Solver<T>::Solve, src/solver.cu:122-209).
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <thread>
@@ -586,9 +587,24 @@ int pb_solver_solve(pb_backend* b, const pb_solver_options* so, pb_stopping_cb s
     int result = PB_STOPPED_MAX_ITERS;
     int iters = 0;
     float res[6] = {0, 0, 0, 0, 0, 0};
+    // Experimental (PB_RING_ITERS > 1): without a stopping callback nothing observable happens between two
+    // "events" (residual refresh, intermediate callback, last iteration) -- the cached residuals the reference
+    // compares every iteration (solver.cu:141-150) do not change -- so such a stretch is enqueued with one
+    // iterate() call, which lets the backend put several iterations into one launch.
+    static const bool batch = [] { const char* e = getenv("PB_RING_ITERS"); return e && atoi(e) > 1; }();
     for (int i = 0; i < so->max_iters; ++i) {
-      const size_t it_before = be->iteration();
-      be->iterate(1);
+      size_t it_before = be->iteration();
+      int run = 1;
+      if (batch && !stop) {
+        const double front0 = cb_iters.empty() ? 1e300 : cb_iters.front();
+        auto quiet = [&](int idx, size_t itb) {
+          return !be->refreshes_on(itb) && !(idx >= front0) && idx != so->max_iters - 1;
+        };
+        while (i + run < so->max_iters && quiet(i + run - 1, it_before + run - 1)) ++run;
+      }
+      be->iterate(run);
+      i += run - 1;                     // the events of the stretch's last iteration are handled below
+      it_before += run - 1;
       iters = i + 1;
       // residuals only change on refresh iterations; everything in between reuses the cached
       // values exactly like Solver::Solve does, without synchronising the stream

@@ -227,6 +227,16 @@ class BackendPDHG : public Backend {
   void slab_primal_halo(unsigned xs);
   void slab_dual_halo(unsigned xs, unsigned ys);
   RingHalo slab_ring_halo();           // advances x_seq / y_seq: one-pass iteration on a slab
+  // experimental (PB_RING_ITERS > 1): up to ring_iters_ consecutive non-refresh iterations in one launch
+  bool is_check_at(unsigned long long it) const {
+    const unsigned long long mod = static_cast<unsigned long long>(static_cast<long long>(opts_.residual_iter));
+    return it == 0 || (it % mod) == 0;
+  }
+  bool multi_iteration_launch(int n_it);
+  int ring_iters_ = 0;
+  unsigned ring_base_ = 0;
+  DeviceBuffer<unsigned> ring_done_, ring_edge_counters_;
+  DeviceBuffer<int> ring_error_;
   void slab_apply(float* d_res, const float* d_rhs, const float* d_halo, bool adjoint);
   Comm* comm_ = nullptr;
   bool is_check_iteration() const {
@@ -383,6 +393,10 @@ void BackendPDHG::initialize(const float* h_x0, size_t nx0, const float* h_y0, s
     tile_ok_ = tile_ok_ && slab_tile && tile_ring_available() && stencil_.geom.nx >= 2;
   }
   tile_iterations_ = 0;
+  {
+    static const int ring_iters = [] { const char* e = getenv("PB_RING_ITERS"); return e ? atoi(e) : 0; }();
+    ring_iters_ = std::min(ring_iters, 32);
+  }
   if (comm_) {
     // the halo protocol lives in the specialised stencil passes: one planar gradient operator
     // (+ identity rows), one prox_g over all columns, Norm2 on the gradient rows
@@ -416,6 +430,16 @@ void BackendPDHG::initialize(const float* h_x0, size_t nx0, const float* h_y0, s
     PB_TRACE_SCOPE("  allocate iterates");
     x_.resize(n); x_prev_.resize(n); y_.resize(m); y_prev_.resize(m);
     if (tile_ok_) y_stage_.resize(m);
+    if (tile_ok_ && ring_iters_ > 1) {
+      const unsigned n_tiles = tile_ring_tile_count(stencil_);
+      ring_done_.resize(std::max(n_tiles, 1u));
+      ring_done_.zero(s);
+      ring_edge_counters_.resize(64);
+      ring_edge_counters_.zero(s);
+      ring_error_.resize(1);
+      ring_error_.zero(s);
+      ring_base_ = 0;
+    }
     if (!fused_) {
       temp_.resize(std::max(m, n));
       kx_.resize(m); kx_prev_.resize(m); kty_.resize(n); kty_prev_.resize(n);
@@ -765,16 +789,66 @@ void BackendPDHG::profile_detail(int n_iters, float out[8]) {
 
 void BackendPDHG::iterate(int n_iters) {
   ctx_->bind();
-  for (int i = 0; i < n_iters; ++i) {
+  for (int i = 0; i < n_iters;) {
+    if (fused_ && tile_ok_ && ring_iters_ > 1 && iteration_ > 0 && !prof_ev_ &&
+        opts_.stepsize_variant != PB_PDHG_ALG2) {
+      // stretch of iterations that neither refresh the residuals nor change the step sizes
+      int r = 0;
+      while (i + r < n_iters && r < ring_iters_ && !is_check_at(iteration_ + r)) ++r;
+      if (r >= 2 && multi_iteration_launch(r)) { i += r; continue; }
+    }
     if (fused_) iteration_fused();
     else iteration_unfused();
+    ++i;
   }
+}
+
+// n_it >= 2 non-refresh iterations in one launch of the persistent ring kernel (pb_tile.cu, RingMulti)
+bool BackendPDHG::multi_iteration_launch(int n_it) {
+  if (ring_done_.size() == 0) return false;
+  const ScaleRef T = problem_->right_ref(), S = problem_->left_ref();
+  RingMulti mi;
+  mi.n_it = n_it;
+  mi.base = ring_base_;
+  mi.done = ring_done_.data();
+  mi.error = ring_error_.data();
+  mi.x_io[0] = x_.data(); mi.x_io[1] = x_prev_.data();
+  mi.y_io[0] = y_.data(); mi.y_io[1] = y_prev_.data();
+  RingHalo h;
+  const unsigned xs0 = comm_ ? comm_->x_seq : 0, ys0 = comm_ ? comm_->y_seq : 0;
+  if (comm_) {
+    h = slab_ring_halo();                       // sequence numbers of the launch's first iteration
+    for (unsigned p = 0; p < 2; ++p) {
+      h.y_slot[p] = comm_->y_slot(p);
+      h.x_slot[p] = comm_->x_slot(p);
+      h.x_out_slot[p] = comm_->x_out(p);
+      h.y_out_slot[p] = comm_->y_out(p);
+    }
+    h.x_done_it = ring_edge_counters_.data();
+    h.y_done_it = ring_edge_counters_.data() + 32;
+  }
+  const unsigned grid = tile_multi_iteration_launch(ctx_, stencil_, g_descs_[0], f_descs_[0], x_.data(), y_.data(),
+                                                    x_prev_.data(), y_prev_.data(), T, S, d_state_.data(), mi,
+                                                    comm_ ? &h : nullptr);
+  if (!grid) {
+    if (comm_) { comm_->x_seq = xs0; comm_->y_seq = ys0; }     // nothing ran: take the sequence numbers back
+    return false;
+  }
+  if (comm_) { comm_->x_seq = xs0 + n_it; comm_->y_seq = ys0 + n_it; }
+  ring_base_ += static_cast<unsigned>(n_it);
+  if (n_it & 1) { x_.swap(x_prev_); y_.swap(y_prev_); }        // the newest iterate is in set (n_it & 1)
+  iteration_ += n_it;
+  tile_iterations_ += n_it;
+  return true;
 }
 
 PdhgState BackendPDHG::fetch_state() {
   if (fused_) {
     d_state_.download(&h_state_, 1, ctx_->stream);
+    int ring_err = 0;
+    if (ring_error_.size()) ring_error_.download(&ring_err, 1, ctx_->stream);
     PB_CUDA(cudaStreamSynchronize(ctx_->stream));
+    if (ring_err) fail(PB_ERR_CUDA, "multi-iteration ring kernel: a tile dependency wait timed out");
   }
   return h_state_;
 }

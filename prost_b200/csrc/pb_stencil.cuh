@@ -84,6 +84,29 @@ struct RingHalo {
   unsigned y_signal_seq = 0;
   unsigned n_edge_tiles = 0;             // tiles per edge = tiles_y * L (filled by the launcher)
   int* error = nullptr;
+  // multi-iteration launches (RingMulti): iteration `it` of the launch uses sequence numbers *_seq + it, the
+  // slots of that parity and its own pair of edge counters
+  const float* y_slot[2] = {nullptr, nullptr};     // local slots by (sequence number & 1)
+  const float* x_slot[2] = {nullptr, nullptr};
+  float* x_out_slot[2] = {nullptr, nullptr};       // the neighbours' slots
+  float* y_out_slot[2] = {nullptr, nullptr};
+  unsigned* x_done_it = nullptr;                   // [n_it] self-resetting edge counters
+  unsigned* y_done_it = nullptr;
+};
+
+// Several consecutive non-refresh iterations in ONE launch of the persistent ring kernel (experimental,
+// PB_RING_ITERS > 1): the CTAs stay resident and a tile of iteration it+1 starts as soon as its 3 x 3 tile
+// neighbourhood has finished iteration it (per-tile counters in global memory, release / acquire at gpu scope,
+// fence.proxy.async before the TMA loads), so the kernel boundary -- launch latency, pipeline prologue and
+// tail -- is paid once per launch instead of once per iteration.  Iterates ping-pong between the two buffer
+// sets io[0] (input of even iterations) and io[1].
+struct RingMulti {
+  int n_it = 1;
+  unsigned base = 0;                   // value of every done[] counter when the launch starts
+  unsigned* done = nullptr;            // per tile: iterations completed (monotonic across launches)
+  int* error = nullptr;                // set when a dependency wait times out
+  float* x_io[2] = {nullptr, nullptr};
+  float* y_io[2] = {nullptr, nullptr};
 };
 
 struct GradGeom {
@@ -682,6 +705,11 @@ void tile_iteration_launch(Context* ctx, const StencilPlan& plan, const ProxDesc
                            float* x_out, float* y_out, const RingHalo* halo = nullptr);
 // slab mode: is the persistent ring (the only one-pass variant that speaks the halo protocol) available?
 bool tile_ring_available();
+// several consecutive non-refresh iterations in one launch (RingMulti; experimental, PB_RING_ITERS > 1)
+unsigned tile_ring_tile_count(const StencilPlan& plan);
+unsigned tile_multi_iteration_launch(Context* ctx, const StencilPlan& plan, const ProxDesc& pg, const ProxDesc& pf,
+                                     float* x_a, float* y_a, float* x_b, float* y_b, ScaleRef T, ScaleRef S,
+                                     const PdhgState* st, const RingMulti& multi, const RingHalo* halo);
 // residual-refresh iteration as one tiled pass; returns the number of (a, b) partial pairs written to each of
 // part_d (dual residual sums) and part_p (primal residual sums), 0 if the two-pass kernels have to run
 unsigned tile_check_iteration_launch(Context* ctx, const StencilPlan& plan, const ProxDesc& pg, const ProxDesc& pf,

@@ -565,11 +565,32 @@ __device__ __forceinline__ void ld_halo4(const float* p, float (&o)[4]) {
   o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
 }
 
+// RingMulti: wait until a tile's iteration counter has reached `want` (acquire, gpu scope).  Non-blocking mode
+// returns false at once; blocking mode gives up after ~2 s and raises the error word (no GPU hang).
+__device__ __forceinline__ bool ring_count_wait(const unsigned* flag, unsigned want, bool blocking, int* error) {
+  unsigned v;
+  unsigned long long t0 = 0;
+  for (unsigned spins = 0;; ++spins) {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if ((int)(v - want) >= 0) return true;
+    if (!blocking) return false;
+    if (error && *reinterpret_cast<volatile int*>(error)) return true;
+    if ((spins & 1023u) == 1023u) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ull) { if (error) atomicExch(error, 1); return true; }
+    }
+  }
+}
+
 // CHECK: this iteration refreshes the residuals (backend_pdhg.cu:73-120, 383-436): the same pass also
 // gathers K^T y_prev from the previous dual iterate (map_q1 / map_q2) and accumulates the four residual
 // sums in double, one (a, b) pair per CTA for each of the two residuals.
 // SLAB: the image is a block of columns of a wider one (has_left / has_right neighbours, RingHalo).
-template <int FN_G, int FN_F, bool CHECK, bool SLAB>
+// MULTI: mi.n_it consecutive non-refresh iterations in one launch (RingMulti, pb_stencil.cuh); map_q1 / map_q2 /
+// map_xb are then the boxes over the second buffer set (odd iterations read it, even ones write it).
+template <int FN_G, int FN_F, bool CHECK, bool SLAB, bool MULTI = false>
 __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
     const __grid_constant__ CUtensorMap map_p1, const __grid_constant__ CUtensorMap map_p2,
     const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_f,
@@ -577,7 +598,9 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
     const ProxDesc pg, const ProxDesc pf, const float Tval, const float Sval,
     const PdhgState* __restrict__ st, const FastDiv div_per_plane, const FastDiv div_tiles_y,
     const uint32_t n_tiles, const int ktyprev_zero, double* __restrict__ part_d, double* __restrict__ part_p,
-    float* __restrict__ x_out, float* __restrict__ y_out, const uint32_t tiles_x, const RingHalo h) {
+    float* __restrict__ x_out, float* __restrict__ y_out, const uint32_t tiles_x, const RingHalo h,
+    const __grid_constant__ CUtensorMap map_xb, const RingMulti mi) {
+  static_assert(!(MULTI && CHECK), "residual-refresh iterations run one per launch");
   extern __shared__ __align__(128) unsigned char smem[];
   // tile -> (label plane, tile column, tile row).  On a slab the two edge tile columns come first
   // (tile column order 0, tiles_x-1, 1, 2, ...) so that the halos leave at the start of the launch.
@@ -596,16 +619,17 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
   const uint32_t stage_tx = kRingP1Bytes + kRingP2Bytes + kRingXBytes +
                             (CHECK ? (q_boxes ? kRingP1Bytes + kRingP2Bytes : 0) : (f_vec ? kRingXBytes : 0));
 
-  auto issue = [&](uint32_t tile, int s) {           // producer lane only
+  auto issue = [&](uint32_t tile, int s, uint32_t iter) {           // producer lane only
     uint32_t l, tx, ty;
     decode(tile, l, tx, ty);
     const int cx = tx * kRingTX, cy = ty * kRingTY;
     unsigned char* base = smem + s * kRingStageBytes;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full[s])), "r"(stage_tx)
                  : "memory");
-    tma_load_3d(base, &map_p1, &full[s], cy, cx - 1, (int)l);
-    tma_load_3d(base + kRingP1Bytes, &map_p2, &full[s], cy - 4, cx, (int)(g.L + l));
-    tma_load_3d(base + kRingP1Bytes + kRingP2Bytes, &map_x, &full[s], cy, cx, (int)l);
+    const bool odd = MULTI && (iter & 1u);       // odd iterations of a multi-iteration launch read buffer set 1
+    tma_load_3d(base, odd ? &map_q1 : &map_p1, &full[s], cy, cx - 1, (int)l);
+    tma_load_3d(base + kRingP1Bytes, odd ? &map_q2 : &map_p2, &full[s], cy - 4, cx, (int)(g.L + l));
+    tma_load_3d(base + kRingP1Bytes + kRingP2Bytes, odd ? &map_xb : &map_x, &full[s], cy, cx, (int)l);
     if (CHECK) {
       if (q_boxes) {
         tma_load_3d(base + kRingP1Bytes + kRingP2Bytes + kRingXBytes, &map_q1, &full[s], cy, cx - 1, (int)l);
@@ -629,11 +653,11 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (producer) {
+  if (producer && !MULTI) {
 #pragma unroll
     for (int s = 0; s < kRingStages; ++s) {
       const uint32_t t = blockIdx.x + s * gridDim.x;
-      if (t < n_tiles) issue(t, s);
+      if (t < n_tiles) issue(t, s, 0u);
     }
   }
 
@@ -652,12 +676,75 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
   const int r0 = (threadIdx.x & 31) * 4;     // lane = row vector
   double acc_d0 = 0.0, acc_d1 = 0.0, acc_p0 = 0.0, acc_p1 = 0.0;
 
-  uint32_t k = 0;
-  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
+  // ---- multi-iteration launches: work item k = (iteration, k-th tile of this CTA), issued by warp 31 -------------
+  const uint32_t n_work = MULTI ? ((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) * (uint32_t)mi.n_it : 0u;
+  uint32_t ki = 0, ki_it = 0, ki_tile = blockIdx.x;      // next work item to issue
+  // Whole warp 31.  The stage of work item ki must be free (bounded wait: the other warps need nothing from
+  // outside to leave it) and, from the second iteration on, the 3 x 3 tile neighbourhood must have finished the
+  // previous iteration: its outputs are this tile's TMA boxes, and it has read what this tile overwrites.
+  // Blocking mode is only used when this warp has nothing left to compute, so it cannot hold up a neighbour.
+  auto multi_issue = [&](bool blocking) -> bool {
+    if (!MULTI || ki >= n_work) return false;
+    const int si = ki % kRingStages;
+    if (ki >= (uint32_t)kRingStages) mbar_wait(&empty[si], ((ki - kRingStages) / kRingStages) & 1u);
+    if (ki_it > 0) {
+      uint32_t l, tx, ty;
+      decode(ki_tile, l, tx, ty);
+      const int lane = threadIdx.x & 31;
+      bool ready = true;
+      if (lane < 9 && lane != 4) {
+        const int ntx = (int)tx + lane % 3 - 1, nty = (int)ty + lane / 3 - 1;
+        if (ntx >= 0 && ntx < (int)tiles_x && nty >= 0 && nty < (int)div_tiles_y.d)
+          ready = ring_count_wait(mi.done + (l * div_per_plane.d + (uint32_t)ntx * div_tiles_y.d + (uint32_t)nty),
+                                  mi.base + ki_it, blocking, mi.error);
+      }
+      __syncwarp();
+      if (!__all_sync(0xffffffffu, ready)) return false;
+      asm volatile("fence.proxy.async;" ::: "memory");     // the neighbours' generic-proxy stores -> our TMA reads
+    }
+    if ((threadIdx.x & 31) == 0) issue(ki_tile, si, ki_it);
+    ++ki;
+    ki_tile += gridDim.x;
+    if (ki_tile >= n_tiles) { ki_tile = blockIdx.x; ++ki_it; }
+    return true;
+  };
+
+  uint32_t k = 0, it = 0;
+  for (uint32_t tile = blockIdx.x;; tile += gridDim.x, ++k) {
+    if (tile >= n_tiles) {
+      if (!MULTI || ++it >= (uint32_t)mi.n_it) break;
+      tile = blockIdx.x;
+    }
     const int s = k % kRingStages;
     const uint32_t parity = (k / kRingStages) & 1u;
     uint32_t l, tx, ty;
     decode(tile, l, tx, ty);
+    // where this iteration writes, and (slabs) which halo slots / sequence numbers / edge counters it uses
+    float* __restrict__ xo_ptr = MULTI ? mi.x_io[(it + 1) & 1u] : x_out;
+    float* __restrict__ yo_ptr = MULTI ? mi.y_io[(it + 1) & 1u] : y_out;
+    const float* yl_a = h.yl_a;
+    const float* xr_n = h.xr_n;
+    const float* xr_o = h.xr_o;
+    float* hx_out = h.x_out;
+    float* hy_out = h.y_out;
+    unsigned y_wait_seq = h.y_wait_seq, x_wait_seq = h.x_wait_seq;
+    unsigned x_signal_seq = h.x_signal_seq, y_signal_seq = h.y_signal_seq;
+    unsigned* x_done = h.x_done;
+    unsigned* y_done = h.y_done;
+    if (SLAB && MULTI) {
+      y_wait_seq += it; x_wait_seq += it; x_signal_seq += it; y_signal_seq += it;
+      yl_a = h.y_slot[y_wait_seq & 1u];
+      xr_n = h.x_slot[x_wait_seq & 1u];
+      xr_o = h.x_slot[(x_wait_seq - 1u) & 1u];
+      hx_out = h.x_out_slot[x_signal_seq & 1u];
+      hy_out = h.y_out_slot[y_signal_seq & 1u];
+      x_done = h.x_done_it + it;
+      y_done = h.y_done_it + it;
+    }
+    if (MULTI && col == kRingCols - 1) {
+      while (ki <= k) multi_issue(true);          // this work item must be on its way
+      if (ki == k + 1) multi_issue(false);        // prefetch the next one if its neighbourhood is ready
+    }
     const int cx = tx * kRingTX, cy = ty * kRingTY;
     unsigned char* base = smem + s * kRingStageBytes;
     float (*s_p1)[kRingRows] = reinterpret_cast<float (*)[kRingRows]>(base);
@@ -686,8 +773,8 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
       VecIO<4>::ld(&s_p1[col + 1][r0], divx);
       VecIO<4>::ld(&s_p1[col][r0], a);
       if (left_edge) {
-        ring_flag_wait(h.y_wait_flag, h.y_wait_seq, h.error);
-        ld_halo4(h.yl_a + halo_off, a);
+        ring_flag_wait(h.y_wait_flag, y_wait_seq, h.error);
+        ld_halo4(yl_a + halo_off, a);
       }
       VecIO<4>::ld(&s_p2[col][4 + r0], o);
       const float up = s_p2[col][4 + r0 - 1];
@@ -730,8 +817,8 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
       }
       VecIO<4>::st(&s_xn[col][r0], xn);
       if (col < kRingTX && r0 < kRingTY && gy < g.ny) {
-        VecIO<4>::st(x_out + gy + gx * g.ny + plane_off, xn);
-        if (left_edge) VecIO<4>::st(h.x_out + halo_off, xn);      // new column 0 -> left neighbour (NVLink)
+        VecIO<4>::st(xo_ptr + gy + gx * g.ny + plane_off, xn);
+        if (left_edge) VecIO<4>::st(hx_out + halo_off, xn);       // new column 0 -> left neighbour (NVLink)
         if (CHECK) {
           // dual residual on the owned pixels: w^ = (x - x+)/(tau sqrt T) - sqrt T K^T y_prev,
           // diff = w^ + sqrt T K^T y
@@ -770,7 +857,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
         }
       }
     }
-    if (left_edge) ring_edge_done(h.x_done, h.n_edge_tiles, h.x_signal, h.x_signal_seq);
+    if (left_edge) ring_edge_done(x_done, h.n_edge_tiles, h.x_signal, x_signal_seq);
     // publish this column's x+ (one arrival per warp), then wait for the right neighbour's
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(&col_ready[s * kRingCols + col]);
@@ -784,9 +871,9 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
       VecIO<4>::ld(&s_xn[col][r0], cn);
       VecIO<4>::ld(&s_x[col][r0], co);
       if (right_edge) {
-        ring_flag_wait(h.x_wait_flag, h.x_wait_seq, h.error);
-        ld_halo4(h.xr_n + halo_off, rn);
-        ld_halo4(h.xr_o + halo_off, ro);
+        ring_flag_wait(h.x_wait_flag, x_wait_seq, h.error);
+        ld_halo4(xr_n + halo_off, rn);
+        ld_halo4(xr_o + halo_off, ro);
       } else {
         VecIO<4>::ld(&s_xn[col + 1][r0], rn);
         VecIO<4>::ld(&s_x[col + 1][r0], ro);
@@ -813,9 +900,9 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
       }
       if (f_simple) norm2_lanes<4, 2, true>(fn_f, arg, cf, tau_f);
       else norm2_lanes<4, 2, false>(fn_f, arg, cf, tau_f);
-      VecIO<4>::st(y_out + idx, arg[0]);
-      VecIO<4>::st(y_out + (size_t)g.L * g.nxny + idx, arg[1]);
-      if (right_edge) VecIO<4>::st(h.y_out + halo_off, arg[0]);     // new y.gx column nx-1 -> right neighbour
+      VecIO<4>::st(yo_ptr + idx, arg[0]);
+      VecIO<4>::st(yo_ptr + (size_t)g.L * g.nxny + idx, arg[1]);
+      if (right_edge) VecIO<4>::st(hy_out + halo_off, arg[0]);      // new y.gx column nx-1 -> right neighbour
       if (CHECK) {
         // primal residual: z^ = (y - y+)/(sigma sqrt S) + sqrt S ((1+theta) K x+ - theta K x),
         // diff = z^ - sqrt S K x+
@@ -833,16 +920,28 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
         }
       }
     }
-    if (right_edge) ring_edge_done(h.y_done, h.n_edge_tiles, h.y_signal, h.y_signal_seq);
+    if (right_edge) ring_edge_done(y_done, h.n_edge_tiles, h.y_signal, y_signal_seq);
     // this warp is done with stage s (operand boxes and x+ tile)
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[s]);
-    if (col == kRingCols - 1) {       // warp 31 refills the stage once every warp has left it
+    if (!MULTI && col == kRingCols - 1) {       // warp 31 refills the stage once every warp has left it
       const uint32_t next = tile + kRingStages * gridDim.x;
       if (next < n_tiles) {
         mbar_wait(&empty[s], parity);
-        if (producer) issue(next, s);
+        if (producer) issue(next, s, 0u);
       }
+    }
+    if (MULTI && col == kRingCols - 1) {
+      // every warp has left work item k, i.e. issued its stores: publish the tile's iteration count (release at
+      // gpu scope; the other warps' stores are ordered before it through the `empty` mbarrier), then try to put
+      // the next work item into the freed stage
+      mbar_wait(&empty[s], parity);
+      if (producer) {
+        __threadfence();
+        unsigned* cnt = mi.done + (l * div_per_plane.d + tx * div_tiles_y.d + ty);
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(cnt), "r"(mi.base + it + 1u) : "memory");
+      }
+      multi_issue(false);
     }
   }
   if (CHECK) {
@@ -862,12 +961,14 @@ struct RingArgs {
   double* part_d = nullptr;
   double* part_p = nullptr;
   const RingHalo* halo = nullptr;      // slab mode
+  CUtensorMap mxb;                     // multi-iteration launches: x boxes over the second buffer set
+  const RingMulti* multi = nullptr;
 };
 
-template <int FN_G, int FN_F, bool CHECK, bool SLAB>
+template <int FN_G, int FN_F, bool CHECK, bool SLAB, bool MULTI = false>
 unsigned ring_launch_k(Context* ctx, const RingArgs& a, const GradGeom& g, const ProxDesc& pg, const ProxDesc& pf,
                        float Tval, float Sval, const PdhgState* st, float* x_out, float* y_out, bool dry_run) {
-  auto kernel = grad2d_iteration_ring_kernel<FN_G, FN_F, CHECK, SLAB>;
+  auto kernel = grad2d_iteration_ring_kernel<FN_G, FN_F, CHECK, SLAB, MULTI>;
   static bool configured = false, ok = false;
   if (!configured) {
     configured = true;
@@ -885,9 +986,29 @@ unsigned ring_launch_k(Context* ctx, const RingArgs& a, const GradGeom& g, const
     h = *a.halo;
     h.n_edge_tiles = tiles_y * g.L;
   }
+  if (MULTI) {
+    // the CTAs wait for each other's tiles: all of them have to be resident -> cooperative launch
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kRingThreads);
+    cfg.dynamicSmemBytes = kRingSmemBytes;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeCooperative;
+    attr.val.cooperative = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(
+        &cfg, kernel, a.mp1, a.mp2, a.mx, a.mf, a.mq1, a.mq2, g, pg, pf, Tval, Sval, st,
+        FastDiv((uint64_t)tiles_x * tiles_y), FastDiv(tiles_y), (uint32_t)n_tiles, a.ktyprev_zero, a.part_d, a.part_p,
+        x_out, y_out, tiles_x, h, a.mxb, *a.multi);
+    if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+    return grid;
+  }
   kernel<<<grid, kRingThreads, kRingSmemBytes, ctx->stream>>>(
       a.mp1, a.mp2, a.mx, a.mf, a.mq1, a.mq2, g, pg, pf, Tval, Sval, st, FastDiv((uint64_t)tiles_x * tiles_y),
-      FastDiv(tiles_y), (uint32_t)n_tiles, a.ktyprev_zero, a.part_d, a.part_p, x_out, y_out, tiles_x, h);
+      FastDiv(tiles_y), (uint32_t)n_tiles, a.ktyprev_zero, a.part_d, a.part_p, x_out, y_out, tiles_x, h, a.mx,
+      RingMulti());
   return grid;
 }
 
@@ -936,6 +1057,48 @@ unsigned ring_launch(Context* ctx, const GradGeom& g, const ProxDesc& pg, const 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace
+
+static int tile_mode();
+
+// ---- several non-refresh iterations in one launch (experimental, PB_RING_ITERS > 1) ----------------------------
+unsigned tile_ring_tile_count(const StencilPlan& plan) {
+  const GradGeom& g = plan.geom;
+  const uint64_t n = (uint64_t)((g.nx + kRingTX - 1) / kRingTX) * ((g.ny + kRingTY - 1) / kRingTY) * g.L;
+  return n < (1ull << 31) ? (unsigned)n : 0u;
+}
+
+// Iterations it = 0 .. n_it-1: even ones read (x_a, y_a) and write (x_b, y_b), odd ones the other way round.
+// Returns the number of CTAs, 0 if the launch was not possible (the caller then runs single iterations).
+unsigned tile_multi_iteration_launch(Context* ctx, const StencilPlan& plan, const ProxDesc& pg, const ProxDesc& pf,
+                                     float* x_a, float* y_a, float* x_b, float* y_b, ScaleRef T, ScaleRef S,
+                                     const PdhgState* st, const RingMulti& multi, const RingHalo* halo) {
+  if (tile_mode() != 2 || multi.n_it < 2 || !multi.done) return 0;
+  const GradGeom& g = plan.geom;
+  RingArgs a;
+  a.halo = halo;
+  a.multi = &multi;
+  if (!tensor_map_for(y_a, g.ny, g.nx, 2 * g.L, kRingRows, kRingCols + 1, a.mp1)) return 0;
+  if (!tensor_map_for(y_a, g.ny, g.nx, 2 * g.L, kRingR2, kRingCols, a.mp2)) return 0;
+  if (!tensor_map_for(x_a, g.ny, g.nx, g.L, kRingRows, kRingCols, a.mx)) return 0;
+  if (!tensor_map_for(y_b, g.ny, g.nx, 2 * g.L, kRingRows, kRingCols + 1, a.mq1)) return 0;
+  if (!tensor_map_for(y_b, g.ny, g.nx, 2 * g.L, kRingR2, kRingCols, a.mq2)) return 0;
+  if (!tensor_map_for(x_b, g.ny, g.nx, g.L, kRingRows, kRingCols, a.mxb)) return 0;
+  const float* f = pg.coeffs.ptr[1] ? pg.coeffs.ptr[1] : x_a;      // unused when b is a scalar
+  if (!tensor_map_for(f, g.ny, g.nx, g.L, kRingRows, kRingCols, a.mf)) return 0;
+#define PB_ARGS ctx, a, g, pg, pf, T.val, S.val, st, x_b, y_b, false
+  unsigned grid;
+  if (pg.fn == PB_FUN_SQUARE && pf.fn == PB_FUN_IND_LEQ0)
+    grid = halo ? ring_launch_k<PB_FUN_SQUARE, PB_FUN_IND_LEQ0, false, true, true>(PB_ARGS)
+                : ring_launch_k<PB_FUN_SQUARE, PB_FUN_IND_LEQ0, false, false, true>(PB_ARGS);
+  else
+    grid = halo ? ring_launch_k<-1, -1, false, true, true>(PB_ARGS) : ring_launch_k<-1, -1, false, false, true>(PB_ARGS);
+#undef PB_ARGS
+  if (grid) {
+    PB_CHECK_LAUNCH();
+    ctx->launches++;
+  }
+  return grid;
+}
 
 // Can the whole iteration run as one tiled pass?  K = one planar BlockGradient2D (no identity rows),
 // prox_g = one Elem1D over all columns with scalar weights (b may be per pixel), prox_f* = one
