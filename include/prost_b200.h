@@ -161,6 +161,11 @@ int pb_prox_create_ind_epi_quad(pb_context* ctx, size_t index, size_t count, siz
                                 int interleaved, int diagsteps, const float* h_a, size_t na,
                                 const float* h_b, size_t nb, const float* h_c, size_t nc,
                                 pb_prox** out);
+/* ProxTransform(shared_ptr<Prox> inner, a, b, c, d, e): prox of c f(a x - b) + <d, x> + (e/2)|x|^2 through the
+ * prox of f (prox_transform.hpp:38-44, prox_transform.cu:27-226); every coefficient has 1 or size elements,
+ * `a` must not contain zeros (same exception text as the reference) */
+int pb_prox_create_transform(pb_context* ctx, pb_prox* inner, const float* const coeffs[5],
+                             const size_t coeff_len[5], pb_prox** out);
 /* ProxMoreau(shared_ptr<Prox>): prox_moreau.hpp:37, prox_moreau.cu:98-134 */
 int pb_prox_create_moreau(pb_context* ctx, pb_prox* conjugate, pb_prox** out);
 /* ProxPermute(shared_ptr<Prox>, vector<int>): prox_permute.hpp:37, prox_permute.cu:101-145 */

@@ -23,6 +23,7 @@
 //           | simplex <idx> <count> <dim> <interleaved> <diagsteps>
 //           | epiquad <idx> <count> <dim> <interleaved> <diagsteps> <a> <b> <c>
 //           | moreau <PROX> | permute <perm.i32> <n> <PROX> | zero <idx> <size>
+//           | transform <a> <b> <c> <d> <e> <PROX>
 //     coefficient := s:<value> | f:<file>:<length>
 //   scaling alpha <a> | identity | custom <left.f32> <right.f32>
 //   pdhg <tau0> <sigma0> <residual_iter> <scale_steps_operator> <alg2_gamma> <arg_alpha0> <arg_nu>
@@ -62,6 +63,7 @@
 #include "prost/prox/prox_elem_operation.hpp"
 #include "prost/prox/prox_ind_epi_quad.hpp"
 #include "prost/prox/prox_moreau.hpp"
+#include "prost/prox/prox_transform.hpp"
 #include "prost/prox/prox_permute.hpp"
 #include "prost/prox/prox_zero.hpp"
 #include "prost/solver.hpp"
@@ -155,6 +157,12 @@ static std::shared_ptr<Prox<real>> parse_prox(std::istringstream& in) {
     return std::shared_ptr<Prox<real>>(new ProxIndEpiQuad<real>(idx, count, dim, il, ds, coeff(a), coeff(b), coeff(c)));
   }
   if (kind == "moreau") return std::shared_ptr<Prox<real>>(new ProxMoreau<real>(parse_prox(in)));
+  if (kind == "transform") {
+    std::string a, b, c, d, e;
+    in >> a >> b >> c >> d >> e;
+    const std::vector<real> va = coeff(a), vb = coeff(b), vc = coeff(c), vd = coeff(d), ve = coeff(e);
+    return std::shared_ptr<Prox<real>>(new ProxTransform<real>(parse_prox(in), va, vb, vc, vd, ve));
+  }
   if (kind == "permute") {
     std::string file;
     size_t n;

@@ -518,6 +518,30 @@ struct ProxMoreau : Prox {          // prox_moreau.cu:98-134
   }
 };
 
+struct ProxTransform : Prox {       // prox_transform.cu:27-226: prox of c f(a x - b) + <d, x> + (e/2)|x|^2
+  std::shared_ptr<Prox> inner;
+  vec co[5], scaled_arg, scaled_tau;   // a, b, c, d, e: one value or one per element
+  ProxTransform(std::shared_ptr<Prox> p, const float* const* coeffs, const size_t* len)
+      : Prox(p->index, p->size, p->diagsteps), inner(p), scaled_arg(p->size), scaled_tau(p->size) {
+    for (int k = 0; k < 5; ++k) co[k].assign(coeffs[k], coeffs[k] + len[k]);
+  }
+  void sep(std::vector<std::tuple<size_t, size_t, size_t>>& s) const override { inner->sep(s); }
+  float at(int k, size_t i) const { return co[k].size() > 1 ? co[k][i] : co[k][0]; }
+  void eval_local(float* res, const float* arg, const float* td, float tau, bool invert) override {
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < size; ++i) {
+      float tau2 = tau * td[i];                                      // :40-42
+      if (invert) tau2 = 1 / tau2;
+      const float a = at(0, i), b = at(1, i), c = at(2, i), d = at(3, i), e = at(4, i);
+      scaled_arg[i] = (a * (arg[i] - tau2 * d)) / (1 + tau2 * e) - b;  // :49
+      scaled_tau[i] = (a * a * c * tau2) / (1 + tau2 * e);             // :75
+    }
+    inner->eval_local(res, scaled_arg.data(), scaled_tau.data(), 1.f, false);   // :201-210
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < size; ++i) res[i] = (res[i] + at(1, i)) / at(0, i);  // :94
+  }
+};
+
 struct ProxPermute : Prox {         // prox_permute.cu:101-145
   std::shared_ptr<Prox> inner;
   std::vector<int> perm;
@@ -958,6 +982,9 @@ int orc_prox_epi_quad(void* p, size_t idx, size_t count, size_t dim, int il, int
 int orc_prox_moreau(void* p, int inner) { return push(PP, std::make_shared<ProxMoreau>(PP->pool[inner])); }
 int orc_prox_permute(void* p, int inner, const int* perm, size_t n) {
   return push(PP, std::make_shared<ProxPermute>(PP->pool[inner], perm, n));
+}
+int orc_prox_transform(void* p, int inner, const float* const* coeffs, const size_t* len) {
+  return push(PP, std::make_shared<ProxTransform>(PP->pool[inner], coeffs, len));
 }
 int orc_prox_zero(void* p, size_t idx, size_t size) { return push(PP, std::make_shared<ProxZero>(idx, size)); }
 void orc_set_prox(void* p, int which, int id) { PP->prox[which].push_back(PP->pool[id]); }

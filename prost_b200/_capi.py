@@ -118,6 +118,7 @@ SIGNATURES = {
     "pb_prox_create_ind_epi_quad": (C.c_int, [handle, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int,
                                               c_float_p, C.c_size_t, c_float_p, C.c_size_t, c_float_p,
                                               C.c_size_t, handle_p]),
+    "pb_prox_create_transform": (C.c_int, [handle, handle, C.POINTER(c_float_p), c_size_p, handle_p]),
     "pb_prox_create_moreau": (C.c_int, [handle, handle, handle_p]),
     "pb_prox_create_permute": (C.c_int, [handle, handle, c_int_p, C.c_size_t, handle_p]),
     "pb_prox_create_zero": (C.c_int, [handle, C.c_size_t, C.c_size_t, handle_p]),

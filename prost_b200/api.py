@@ -293,6 +293,19 @@ class ProxIndEpiQuad(Prox):
                                               C.byref(self._h)))
 
 
+class ProxTransform(Prox):
+    """ProxTransform<T>(inner, a, b, c, d, e): prox of c f(a x - b) + <d, x> + (e/2)|x|^2 through the prox of f
+    (prox_transform.hpp:38-44); every coefficient is a scalar or one value per element."""
+
+    def __init__(self, ctx, inner, a=1.0, b=0.0, c=1.0, d=0.0, e=0.0):
+        super().__init__(ctx)
+        self._inner = inner
+        keep = [_f32(np.atleast_1d(v)) for v in (a, b, c, d, e)]
+        ptrs = (_capi.c_float_p * 5)(*[_fp(v) for v in keep])
+        lens = (C.c_size_t * 5)(*[v.size for v in keep])
+        check(lib.pb_prox_create_transform(ctx._h, inner._h, ptrs, lens, C.byref(self._h)))
+
+
 class ProxMoreau(Prox):
     def __init__(self, ctx, conjugate):
         super().__init__(ctx)

@@ -317,6 +317,11 @@ int pb_prox_create_moreau(pb_context* c, pb_prox* conjugate, pb_prox** out) {
 int pb_prox_create_permute(pb_context* c, pb_prox* base, const int* perm, size_t n, pb_prox** out) {
   PB_MAKE_PROX((require(base != nullptr, "NULL prox"), pb::make_prox_permute(&c->ctx, base->impl, perm, n)));
 }
+int pb_prox_create_transform(pb_context* c, pb_prox* inner, const float* const coeffs[5], const size_t coeff_len[5],
+                             pb_prox** out) {
+  PB_MAKE_PROX((require(inner != nullptr && coeffs != nullptr && coeff_len != nullptr, "NULL argument"),
+                pb::make_prox_transform(&c->ctx, inner->impl, coeffs, coeff_len)));
+}
 int pb_prox_create_zero(pb_context* c, size_t index, size_t size, pb_prox** out) {
   PB_MAKE_PROX(pb::make_prox_zero(&c->ctx, index, size));
 }

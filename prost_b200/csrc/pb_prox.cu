@@ -349,6 +349,94 @@ class ProxMoreau : public Prox {
   DeviceBuffer<float> scaled_;
 };
 
+// ---- ProxTransform (prox_transform.cu:27-226): prox of  c f(a x - b) + <d, x> + (e/2)|x|^2  through the prox of f.
+// Same three element-wise steps around the inner prox as the reference, same float expressions.
+struct TransformCoeffs {
+  const float* ptr[5];      // a, b, c, d, e per element, or null
+  float val[5];
+  __device__ __forceinline__ float at(int k, size_t i) const { return ptr[k] ? ptr[k][i] : val[k]; }
+};
+
+__global__ void __launch_bounds__(kBlock) transform_prescale_kernel(float* __restrict__ scaled_arg,
+                                                                    float* __restrict__ scaled_tau,
+                                                                    const float* __restrict__ arg,
+                                                                    const float* __restrict__ td,
+                                                                    const TransformCoeffs co, size_t n, float tau,
+                                                                    bool invert) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float tau2 = tau * td[i];
+    if (invert) tau2 = 1 / tau2;
+    const float a = co.at(0, i), b = co.at(1, i), c = co.at(2, i), d = co.at(3, i), e = co.at(4, i);
+    scaled_arg[i] = (a * (arg[i] - tau2 * d)) / (1 + tau2 * e) - b;      // ProxTransformPrescaleArgument :49
+    scaled_tau[i] = (a * a * c * tau2) / (1 + tau2 * e);                 // ProxTransformPrescaleStepSize :75
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) transform_postscale_kernel(float* __restrict__ res,
+                                                                     const TransformCoeffs co, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    res[i] = (res[i] + co.at(1, i)) / co.at(0, i);                       // ProxTransformPostscale :94
+}
+
+class ProxTransform : public Prox {
+ public:
+  ProxTransform(Context* ctx, std::shared_ptr<Prox> inner, const float* const coeffs[5], const size_t len[5])
+      : Prox(ctx, inner->index(), inner->size(), inner->diagsteps()), inner_(std::move(inner)) {
+    static const char* names = "abcde";
+    for (int k = 0; k < 5; ++k) {
+      const size_t n = coeffs ? len[k] : 0;
+      if (n == 0 || !coeffs[k]) fail(PB_ERR_INVALID, "ProxTransform: empty coefficient array");
+      if (n > 1 && n < size_) {
+        std::ostringstream ss;
+        ss << "ProxTransform: coefficient '" << names[k] << "' has " << n << " elements, expected 1 or " << size_ << ".";
+        fail(PB_ERR_INVALID, ss.str());
+      }
+      if (k == 0)
+        for (size_t i = 0; i < n; ++i)
+          if (coeffs[0][i] == 0.f)
+            fail(PB_ERR_INVALID,
+                 "ProxTransform: Vector 'a' isn't allowed to contain zero element. (Division by zero)");
+      co_.ptr[k] = nullptr;
+      co_.val[k] = coeffs[k][0];
+      if (n > 1) {
+        d_co_[k].resize(size_);
+        upload_from_host(ctx, d_co_[k].data(), coeffs[k], size_);
+        co_.ptr[k] = d_co_[k].data();
+      }
+    }
+    scaled_arg_.resize(size_);
+    scaled_tau_.resize(size_);
+  }
+  int kind() const override { return kProxTransform; }
+  size_t gpu_mem_amount() const override {
+    size_t mem = 2 * size_ * sizeof(float) + inner_->gpu_mem_amount();
+    for (int k = 0; k < 5; ++k) mem += d_co_[k].size() * sizeof(float);
+    return mem;
+  }
+  size_t uniform_group_size() const override { return inner_->uniform_group_size(); }
+  void get_separable_structure(std::vector<std::tuple<size_t, size_t, size_t>>& sep) const override {
+    inner_->get_separable_structure(sep);
+  }
+  void eval_local(float* res, const float* arg, const float* td, float tau, bool invert) override {
+    ctx_->bind();
+    if (size_ == 0) return;
+    const unsigned grid = stream_grid(ctx_, size_);
+    transform_prescale_kernel<<<grid, kBlock, 0, ctx_->stream>>>(scaled_arg_.data(), scaled_tau_.data(), arg, td, co_,
+                                                                 size_, tau, invert);
+    PB_CHECK_LAUNCH();
+    // the inner prox sees the transformed step as its diagonal and tau = 1, never inverted (:201-210)
+    inner_->eval_local(res, scaled_arg_.data(), scaled_tau_.data(), 1.f, false);
+    transform_postscale_kernel<<<grid, kBlock, 0, ctx_->stream>>>(res, co_, size_);
+    PB_CHECK_LAUNCH();
+    ctx_->launches += 2;
+  }
+
+ private:
+  std::shared_ptr<Prox> inner_;
+  TransformCoeffs co_;
+  DeviceBuffer<float> d_co_[5], scaled_arg_, scaled_tau_;
+};
+
 class ProxPermute : public Prox {
  public:
   ProxPermute(Context* ctx, std::shared_ptr<Prox> inner, const int* perm, size_t n)
@@ -410,6 +498,10 @@ std::shared_ptr<Prox> make_prox_epi_quad(Context* ctx, size_t index, size_t coun
 }
 std::shared_ptr<Prox> make_prox_moreau(Context* ctx, std::shared_ptr<Prox> inner) {
   return std::make_shared<ProxMoreau>(ctx, std::move(inner));
+}
+std::shared_ptr<Prox> make_prox_transform(Context* ctx, std::shared_ptr<Prox> inner, const float* const coeffs[5],
+                                          const size_t coeff_len[5]) {
+  return std::make_shared<ProxTransform>(ctx, std::move(inner), coeffs, coeff_len);
 }
 std::shared_ptr<Prox> make_prox_permute(Context* ctx, std::shared_ptr<Prox> inner, const int* perm,
                                         size_t n) {

@@ -25,6 +25,7 @@ enum ProxKind : int {
   kProxEpiQuad = 4,
   kProxMoreau = 5,
   kProxPermute = 6,
+  kProxTransform = 7,
 };
 
 // per-element vector or scalar (ElemOpCoefficients: prox_elem_operation.hpp:104-109)
@@ -359,6 +360,9 @@ std::shared_ptr<Prox> make_prox_epi_quad(Context* ctx, size_t index, size_t coun
                                          bool interleaved, bool diagsteps, const float* a, size_t na,
                                          const float* b, size_t nb, const float* c, size_t nc);
 std::shared_ptr<Prox> make_prox_moreau(Context* ctx, std::shared_ptr<Prox> inner);
+// ProxTransform (prox_transform.hpp:38-44): a, b, c, d, e with one value or one value per element
+std::shared_ptr<Prox> make_prox_transform(Context* ctx, std::shared_ptr<Prox> inner, const float* const coeffs[5],
+                                          const size_t coeff_len[5]);
 std::shared_ptr<Prox> make_prox_permute(Context* ctx, std::shared_ptr<Prox> inner, const int* perm,
                                         size_t n);
 std::shared_ptr<Prox> make_prox_zero(Context* ctx, size_t index, size_t size);

@@ -11,6 +11,7 @@ reference's mex registry names and argument order (matlab/+prost/private/factory
   ind_epi_quad                                         : [count, dim, interleaved, [a, b, c]]
   moreau                                               : [child description]
   permute                                              : [child description, perm]
+  transform                                            : [a, b, c, d, e, child description]   (+function/transform.m)
   zero                                                 : []
   gradient2d / gradient3d : [nx, ny, L, label_first]     diags : [nrows, ncols, factors, offsets]
   dense : [A]     sparse : [A]     zero : [nrows, ncols]
@@ -36,6 +37,9 @@ def create_prox(ctx, desc):
         return api.ProxMoreau(ctx, create_prox(ctx, data[0]))
     if name == "permute":
         return api.ProxPermute(ctx, create_prox(ctx, data[0]), data[1])
+    if name == "transform":
+        a, b, c, d, e, child = data
+        return api.ProxTransform(ctx, create_prox(ctx, child), a, b, c, d, e)
     if name == "zero":
         return api.ProxZero(ctx, idx, size)
     raise api.ProstError(-4, f"Unknown prox '{name}'")

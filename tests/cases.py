@@ -163,3 +163,29 @@ def prox_cases(small=False):
     cases["offset_1d"] = (("elem_operation:1d:abs", 17, n, True, [n, 1, False, coeffs(c=0.5)]), n + 40)
     cases["zero"] = (("zero", 5, n, True, []), n + 9)
     return cases
+
+
+def prox_transform_cases(small=False):
+    """ProxTransform (prox_transform.cu:27-226; test_prox_transform.m uses N = 5000 and uniform random a..e):
+    per-element coefficients around a unit-coefficient 1-D prox, the conjugate of that, and scalar coefficients
+    around a Norm2 prox.  Kept apart from prox_cases() (added after the hot path)."""
+    r = rng(23)
+    nt = 5000 if not small else 211
+    a, b, c, d, e = (r.uniform(0.2, 1, nt), r.uniform(0, 1, nt), r.uniform(0.2, 1, nt), r.uniform(0, 1, nt),
+                     r.uniform(0, 1, nt))
+    cases = {}
+    for fun in ("abs", "square", "huber"):
+        unit = ("elem_operation:1d:" + fun, 0, nt, True, [nt, 1, False, coeffs(alpha=0.5)])
+        direct = ("elem_operation:1d:" + fun, 0, nt, True, [nt, 1, False, coeffs(a=a, b=b, c=c, d=d, e=e, alpha=0.5)])
+        cases[f"transform_{fun}_vec"] = (("transform", 0, nt, True, [a, b, c, d, e, unit]), nt, direct)
+        cases[f"moreau_transform_{fun}_vec"] = (
+            ("moreau", 0, nt, True, [("transform", 0, nt, True, [a, b, c, d, e, unit])]), nt,
+            ("moreau", 0, nt, True, [direct]))
+    n = 1200 if not small else 45
+    inner = ("elem_operation:norm2:abs", 0, n * 3, False, [n, 3, False, coeffs(c=0.8)])
+    cases["transform_norm2_scalar"] = (("transform", 0, n * 3, False, [[1.5], [0.2], [0.7], [0.1], [0.3], inner]),
+                                       n * 3, None)
+    cases["transform_offset"] = (("transform", 11, nt, True,
+                                  [a, [0.25], c, [0.0], e, ("elem_operation:1d:abs", 11, nt, True,
+                                                            [nt, 1, False, coeffs()])]), nt + 30, None)
+    return cases

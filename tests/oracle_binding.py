@@ -43,6 +43,7 @@ lib.orc_prox_simplex.argtypes = [C.c_void_p, sz, sz, sz, C.c_int, C.c_int]
 lib.orc_prox_epi_quad.argtypes = [C.c_void_p, sz, sz, sz, C.c_int, C.c_int, fp, sz, fp, sz, fp, sz]
 lib.orc_prox_moreau.argtypes = [C.c_void_p, C.c_int]
 lib.orc_prox_permute.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), sz]
+lib.orc_prox_transform.argtypes = [C.c_void_p, C.c_int, C.POINTER(fp), C.POINTER(sz)]
 lib.orc_prox_zero.argtypes = [C.c_void_p, sz, sz]
 lib.orc_set_prox.argtypes = [C.c_void_p, C.c_int, C.c_int]
 lib.orc_set_dims.argtypes = [C.c_void_p, sz, sz]
@@ -170,6 +171,11 @@ class OracleProblem:
             perm = np.ascontiguousarray(np.asarray(data[1], dtype=np.int32))
             return lib.orc_prox_permute(self.h, self.add_prox(data[0]), perm.ctypes.data_as(C.POINTER(C.c_int)),
                                         perm.size)
+        if name == "transform":
+            arrs = [_f32(np.atleast_1d(c)) for c in data[:5]]
+            ptrs = (fp * 5)(*[_p(a) for a in arrs])
+            lens = (sz * 5)(*[a.size for a in arrs])
+            return lib.orc_prox_transform(self.h, self.add_prox(data[5]), ptrs, lens)
         if name == "zero":
             return lib.orc_prox_zero(self.h, idx, size)
         raise ValueError(name)

@@ -84,6 +84,8 @@ class _Writer:
         if name == "permute":
             fp, n = self.arr(data[1], np.int32)
             return f"permute {fp} {n} " + self.prox(data[0])
+        if name == "transform":
+            return "transform " + " ".join(self.coeff(c) for c in data[:5]) + " " + self.prox(data[5])
         if name == "zero":
             return f"zero {idx} {size}"
         raise ValueError(name)

@@ -1,0 +1,76 @@
+"""GPU suite, SURVEY.md 8(f) row 2 (first widening step after the hot path): ProxTransform through the C ABI
+against the oracle, against the closed form of the reference's own test (test_prox_transform.m) and against
+the live reference build.  Runs last (file name) because it was added after the hot-path rows."""
+import zlib
+
+import numpy as np
+import pytest
+
+import cases
+import prost_b200 as pb
+import ref_driver
+from oracle_binding import oracle_prox_eval
+from pdhg_util import assert_parity, run_cuda, run_oracle
+
+pytestmark = pytest.mark.gpu
+
+CASES = cases.prox_transform_cases()
+
+
+def _inputs(name, n):
+    r = np.random.default_rng(zlib.crc32(name.encode()))
+    return (2 * r.standard_normal(n)).astype(np.float32), r.uniform(0.5, 1.5, n).astype(np.float32), 0.7
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("invert", [False, True])
+def test_transform_matches_oracle_and_closed_form(ctx, name, invert):
+    desc, n, direct = CASES[name]
+    arg, tau_diag, tau = _inputs(name, n)
+    got = pb.create_prox(ctx, desc).Eval(arg, tau_diag, tau, invert)
+    want = oracle_prox_eval(desc, arg, tau_diag, tau, invert)
+    lo, hi = desc[1], desc[1] + desc[2]
+    assert np.abs(got[lo:hi] - want[lo:hi]).max() <= 2e-5 * max(1.0, float(np.abs(want[lo:hi]).max())), name
+    if direct is not None:      # test_prox_transform.m: same function written with direct coefficients
+        ref = pb.create_prox(ctx, direct).Eval(arg, tau_diag, tau, invert)
+        assert np.abs(got[lo:hi] - ref[lo:hi]).max() < 2e-4 * max(1.0, float(np.abs(ref[lo:hi]).max())), name
+
+
+@pytest.mark.skipif(not ref_driver.available(), reason="oracle/_ref (compiled reference) not built")
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_transform_vs_reference(ctx, name):
+    desc, n, _ = CASES[name]
+    arg, tau_diag, tau = _inputs(name, n)
+    want = ref_driver.run_prox(desc, arg, tau_diag, tau)
+    got = pb.create_prox(ctx, desc).Eval(arg, tau_diag, tau)
+    lo, hi = desc[1], desc[1] + desc[2]
+    assert np.abs(got[lo:hi] - want[lo:hi]).max() <= 1e-5 * max(1.0, float(np.abs(want[lo:hi]).max())), name
+
+
+def test_transform_errors(ctx):
+    inner = pb.ProxElemOperation1D(ctx, "abs", 0, 10, 1, False, True, cases.coeffs())
+    with pytest.raises(pb.ProstError) as e:
+        pb.ProxTransform(ctx, inner, a=np.array([1, 0, 1, 1, 1, 1, 1, 1, 1, 1], np.float32))
+    assert "isn't allowed to contain zero" in str(e.value)
+    with pytest.raises(pb.ProstError):
+        pb.ProxTransform(ctx, inner, b=np.zeros(3, np.float32))      # neither 1 nor size elements
+
+
+def test_rof_written_with_transform_solves_like_direct(ctx):
+    """+function/transform.m: sum_1d('square', 1, f, lmb) == transform(sum_1d('square'), 1, f, lmb).  The
+    transformed prox is not a fusable leaf, so PDHG takes the unfused schedule; iterates agree with the oracle
+    running the same description and with the fused direct formulation."""
+    from prost_b200 import synthetic as syn
+    nx, ny = 24, 20
+    N = nx * ny
+    desc = syn.rof(nx, ny)
+    f = desc["data"]["f"]
+    tdesc = dict(desc)
+    tdesc["prox_g"] = [("transform", 0, N, True, [[1.0], f, [10.0], [0.0], [0.0],
+                                                   ("elem_operation:1d:square", 0, N, True, [N, 1, False, cases.coeffs()])])]
+    got = run_cuda(ctx, tdesc, 60, stepsize="alg1", residual_iter=5)
+    assert not got["fused"]
+    want = run_oracle(tdesc, 60, stepsize="alg1", residual_iter=5)
+    assert_parity(got, want, label="ROF via transform")
+    direct = run_cuda(ctx, desc, 60, stepsize="alg1", residual_iter=5)
+    assert np.abs(got["x"] - direct["x"]).max() < 1e-4
