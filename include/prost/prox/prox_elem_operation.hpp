@@ -12,7 +12,7 @@ namespace prost {
 template <typename T, class ELEM_OPERATION>
 class ProxElemOperation : public ProxSeparableSum<T> {
  public:
-  /// Operations without coefficients (ElemOperationIndSimplex).
+  /// Operations without coefficients (ElemOperationIndSimplex, ElemOperationIndSum).
   ProxElemOperation(size_t index, size_t count, size_t dim, bool interleaved, bool diagsteps)
       : ProxSeparableSum<T>(index, count, ELEM_OPERATION::kDim <= 0 ? dim : ELEM_OPERATION::kDim, interleaved,
                             diagsteps) {
@@ -33,6 +33,11 @@ class ProxElemOperation : public ProxSeparableSum<T> {
     if (ELEM_OPERATION::kKind == detail::kElemOpIndSimplex) {
       detail::check(pb_prox_create_ind_simplex(ctx, this->index_, this->count_, this->dim_, this->interleaved_,
                                                this->diagsteps_, &h));
+      return h;
+    }
+    if (ELEM_OPERATION::kKind == detail::kElemOpIndSum) {
+      detail::check(pb_prox_create_ind_sum(ctx, this->index_, this->count_, this->dim_, this->interleaved_,
+                                           this->diagsteps_, &h));
       return h;
     }
     if (coeffs_.size() != 7) throw Exception("ProxElemOperation: expected 7 coefficient arrays.");

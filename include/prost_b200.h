@@ -156,6 +156,10 @@ int pb_prox_create_elem_norm2(pb_context* ctx, size_t index, size_t count, size_
 /* ProxElemOperation<T,ElemOperationIndSimplex<T>>: elem_operation_ind_simplex.hpp:47-115 */
 int pb_prox_create_ind_simplex(pb_context* ctx, size_t index, size_t count, size_t dim,
                                int interleaved, int diagsteps, pb_prox** out);
+/* ProxElemOperation<T,ElemOperationIndSum<T>>: projection of every group onto sum_i x_i = 1
+ * (elem_operation_ind_sum.hpp:38-58; mex name "elem_operation:ind_sum", +function/sum_ind_sum.m) */
+int pb_prox_create_ind_sum(pb_context* ctx, size_t index, size_t count, size_t dim, int interleaved,
+                           int diagsteps, pb_prox** out);
 /* ProxIndEpiQuad(index,count,dim,interleaved,diagsteps,a,b,c): prox_ind_epi_quad.hpp:42-51 */
 int pb_prox_create_ind_epi_quad(pb_context* ctx, size_t index, size_t count, size_t dim,
                                 int interleaved, int diagsteps, const float* h_a, size_t na,

@@ -21,6 +21,7 @@
 //   prox g|f|gstar|fstar|eval <PROX>
 //     PROX := elem1d|norm2 <fun> <idx> <count> <dim> <interleaved> <diagsteps> <c0> .. <c6>
 //           | simplex <idx> <count> <dim> <interleaved> <diagsteps>
+//           | indsum <idx> <count> <dim> <interleaved> <diagsteps>
 //           | epiquad <idx> <count> <dim> <interleaved> <diagsteps> <a> <b> <c>
 //           | moreau <PROX> | permute <perm.i32> <n> <PROX> | zero <idx> <size>
 //           | transform <a> <b> <c> <d> <e> <PROX>
@@ -58,6 +59,7 @@
 #include "prost/problem.hpp"
 #include "prost/prox/elemop/elem_operation_1d.hpp"
 #include "prost/prox/elemop/elem_operation_ind_simplex.hpp"
+#include "prost/prox/elemop/elem_operation_ind_sum.hpp"
 #include "prost/prox/elemop/elem_operation_norm2.hpp"
 #include "prost/prox/elemop/function_1d.hpp"
 #include "prost/prox/prox_elem_operation.hpp"
@@ -148,6 +150,12 @@ static std::shared_ptr<Prox<real>> parse_prox(std::istringstream& in) {
     in >> idx >> count >> dim >> il >> ds;
     return std::shared_ptr<Prox<real>>(
         new ProxElemOperation<real, ElemOperationIndSimplex<real>>(idx, count, dim, il, ds));
+  }
+  if (kind == "indsum") {
+    size_t idx, count, dim;
+    int il, ds;
+    in >> idx >> count >> dim >> il >> ds;
+    return std::shared_ptr<Prox<real>>(new ProxElemOperation<real, ElemOperationIndSum<real>>(idx, count, dim, il, ds));
   }
   if (kind == "epiquad") {
     size_t idx, count, dim;

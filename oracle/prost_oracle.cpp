@@ -474,6 +474,19 @@ static void project_epi_quad_nd(float* xbase, size_t stride, size_t dim, float y
   y = alpha * sq_norm_x;
 }
 
+struct ProxIndSum : ProxSeparable {    // elem_operation_ind_sum.hpp:38-58: projection onto { sum_i x_i = 1 } per group
+  ProxIndSum(size_t i, size_t c, size_t d, bool il, bool ds) : ProxSeparable(i, c, d, il, ds) {}
+  void eval_local(float* res, const float* arg, const float*, float, bool) override {
+#pragma omp parallel for schedule(static)
+    for (size_t tx = 0; tx < count; ++tx) {
+      float tl = 0;
+      for (size_t k = 0; k < dim; ++k) tl += arg[at(tx, k)];
+      tl = static_cast<float>((tl - 1.) / static_cast<float>(dim));    // `1.` promotes to double (:50)
+      for (size_t k = 0; k < dim; ++k) res[at(tx, k)] = arg[at(tx, k)] - tl;
+    }
+  }
+};
+
 struct ProxEpiQuad : ProxSeparable {   // prox_ind_epi_quad.cu:42-79 (always planar)
   vec a, b, c;
   ProxEpiQuad(size_t i, size_t cnt, size_t d, bool il, bool ds, const float* a_, size_t na, const float* b_,
@@ -974,6 +987,9 @@ int orc_prox_elem(void* p, int norm2, size_t idx, size_t count, size_t dim, int 
 }
 int orc_prox_simplex(void* p, size_t idx, size_t count, size_t dim, int il, int ds) {
   return push(PP, std::make_shared<ProxSimplex>(idx, count, dim, il != 0, ds != 0));
+}
+int orc_prox_ind_sum(void* p, size_t idx, size_t count, size_t dim, int il, int ds) {
+  return push(PP, std::make_shared<ProxIndSum>(idx, count, dim, il != 0, ds != 0));
 }
 int orc_prox_epi_quad(void* p, size_t idx, size_t count, size_t dim, int il, int ds, const float* a, size_t na,
                       const float* b, size_t nb, const float* c, size_t nc) {

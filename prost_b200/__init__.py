@@ -7,6 +7,7 @@ sm_100a in prost_b200/csrc.  There is no CPU fallback.
 from .api import (ADMMOptions, Backend, Comm, BackendADMM, BackendPDHG, Block, BlockDense, BlockDiags,
                   BlockGradient2D, BlockGradient3D, BlockSparse, BlockZero, Context, LinearOperator,
                   PDHGOptions, Problem, ProstError, Prox, ProxElemOperation1D, ProxElemOperationIndSimplex,
+                  ProxElemOperationIndSum,
                   ProxElemOperationNorm2, ProxIndEpiQuad, ProxMoreau, ProxPermute, ProxTransform, ProxZero, Solver,
                   SolverOptions, admm_options, pdhg_options, solver_options)
 from .factory import create_block, create_linop, create_problem, create_prox

@@ -115,6 +115,7 @@ SIGNATURES = {
                                             C.c_int, C.POINTER(c_float_p), c_size_p, handle_p]),
     "pb_prox_create_ind_simplex": (C.c_int, [handle, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int,
                                              handle_p]),
+    "pb_prox_create_ind_sum": (C.c_int, [handle, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int, handle_p]),
     "pb_prox_create_ind_epi_quad": (C.c_int, [handle, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int,
                                               c_float_p, C.c_size_t, c_float_p, C.c_size_t, c_float_p,
                                               C.c_size_t, handle_p]),

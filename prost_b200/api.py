@@ -293,6 +293,15 @@ class ProxIndEpiQuad(Prox):
                                               C.byref(self._h)))
 
 
+class ProxElemOperationIndSum(Prox):
+    """ProxElemOperation<T, ElemOperationIndSum<T>>: per-group projection onto sum_i x_i = 1."""
+
+    def __init__(self, ctx, index, count, dim, interleaved, diagsteps):
+        super().__init__(ctx)
+        check(lib.pb_prox_create_ind_sum(ctx._h, index, count, dim, int(interleaved), int(diagsteps),
+                                         C.byref(self._h)))
+
+
 class ProxTransform(Prox):
     """ProxTransform<T>(inner, a, b, c, d, e): prox of c f(a x - b) + <d, x> + (e/2)|x|^2 through the prox of f
     (prox_transform.hpp:38-44); every coefficient is a scalar or one value per element."""

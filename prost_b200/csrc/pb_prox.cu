@@ -349,6 +349,47 @@ class ProxMoreau : public Prox {
   DeviceBuffer<float> scaled_;
 };
 
+// ---- ElemOperationIndSum (elem_operation_ind_sum.hpp:38-58): projection of every group onto { sum_i x_i = 1 }.
+// One thread per group, the group is read twice (second time from L1 / L2); tau is ignored like in the reference.
+__global__ void __launch_bounds__(kBlock) ind_sum_kernel(float* __restrict__ res, const float* __restrict__ arg,
+                                                         size_t count, size_t dim, bool interleaved) {
+  for (size_t tx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; tx < count; tx += (size_t)gridDim.x * blockDim.x) {
+    const size_t first = interleaved ? tx * dim : tx, stride = interleaved ? 1 : count;   // vector.hpp:42-48
+    float tl = 0;
+    for (size_t i = 0; i < dim; ++i) tl += arg[first + i * stride];
+    tl = static_cast<float>((tl - 1.) / static_cast<float>(dim));      // `1.` promotes to double (:50)
+    for (size_t i = 0; i < dim; ++i) res[first + i * stride] = arg[first + i * stride] - tl;
+  }
+}
+
+class ProxIndSum : public Prox {
+ public:
+  ProxIndSum(Context* ctx, size_t index, size_t count, size_t dim, bool interleaved, bool diagsteps)
+      : Prox(ctx, index, count * dim, diagsteps), count_(count), dim_(dim), interleaved_(interleaved) {
+    if (dim == 0) fail(PB_ERR_INVALID, "elem_operation:ind_sum needs dim >= 1");
+    if (index + count * dim >= (1ull << 31)) fail(PB_ERR_UNSUPPORTED, "prox range exceeds 2^31-1");
+  }
+  int kind() const override { return kProxIndSum; }
+  size_t uniform_group_size() const override { return dim_; }
+  void get_separable_structure(std::vector<std::tuple<size_t, size_t, size_t>>& sep) const override {
+    for (size_t i = 0; i < count_; ++i) {                 // ProxSeparableSum (prox_separable_sum.hpp:65-77)
+      if (interleaved_) sep.emplace_back(index_ + i * dim_, dim_, 1);
+      else sep.emplace_back(index_ + i, dim_, count_);
+    }
+  }
+  void eval_local(float* res, const float* arg, const float*, float, bool) override {
+    ctx_->bind();
+    if (count_ == 0) return;
+    ind_sum_kernel<<<stream_grid(ctx_, count_), kBlock, 0, ctx_->stream>>>(res, arg, count_, dim_, interleaved_);
+    PB_CHECK_LAUNCH();
+    ctx_->launches++;
+  }
+
+ private:
+  size_t count_, dim_;
+  bool interleaved_;
+};
+
 // ---- ProxTransform (prox_transform.cu:27-226): prox of  c f(a x - b) + <d, x> + (e/2)|x|^2  through the prox of f.
 // Same three element-wise steps around the inner prox as the reference, same float expressions.
 struct TransformCoeffs {
@@ -498,6 +539,10 @@ std::shared_ptr<Prox> make_prox_epi_quad(Context* ctx, size_t index, size_t coun
 }
 std::shared_ptr<Prox> make_prox_moreau(Context* ctx, std::shared_ptr<Prox> inner) {
   return std::make_shared<ProxMoreau>(ctx, std::move(inner));
+}
+std::shared_ptr<Prox> make_prox_ind_sum(Context* ctx, size_t index, size_t count, size_t dim, bool interleaved,
+                                        bool diagsteps) {
+  return std::make_shared<ProxIndSum>(ctx, index, count, dim, interleaved, diagsteps);
 }
 std::shared_ptr<Prox> make_prox_transform(Context* ctx, std::shared_ptr<Prox> inner, const float* const coeffs[5],
                                           const size_t coeff_len[5]) {

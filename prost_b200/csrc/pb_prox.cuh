@@ -26,6 +26,7 @@ enum ProxKind : int {
   kProxMoreau = 5,
   kProxPermute = 6,
   kProxTransform = 7,
+  kProxIndSum = 8,
 };
 
 // per-element vector or scalar (ElemOpCoefficients: prox_elem_operation.hpp:104-109)
@@ -360,6 +361,9 @@ std::shared_ptr<Prox> make_prox_epi_quad(Context* ctx, size_t index, size_t coun
                                          bool interleaved, bool diagsteps, const float* a, size_t na,
                                          const float* b, size_t nb, const float* c, size_t nc);
 std::shared_ptr<Prox> make_prox_moreau(Context* ctx, std::shared_ptr<Prox> inner);
+// ProxElemOperation<T, ElemOperationIndSum<T>> (elem_operation_ind_sum.hpp:38-58): sum-to-one projection per group
+std::shared_ptr<Prox> make_prox_ind_sum(Context* ctx, size_t index, size_t count, size_t dim, bool interleaved,
+                                        bool diagsteps);
 // ProxTransform (prox_transform.hpp:38-44): a, b, c, d, e with one value or one value per element
 std::shared_ptr<Prox> make_prox_transform(Context* ctx, std::shared_ptr<Prox> inner, const float* const coeffs[5],
                                           const size_t coeff_len[5]);

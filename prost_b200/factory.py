@@ -7,7 +7,7 @@ reference's mex registry names and argument order (matlab/+prost/private/factory
 
 ``data`` per name (same order as the cell arrays the MATLAB front end sends):
   elem_operation:1d:<fun>, elem_operation:norm2:<fun> : [count, dim, interleaved, [a,b,c,d,e,alpha,beta]]
-  elem_operation:ind_simplex                           : [count, dim, interleaved]
+  elem_operation:ind_simplex, elem_operation:ind_sum   : [count, dim, interleaved]
   ind_epi_quad                                         : [count, dim, interleaved, [a, b, c]]
   moreau                                               : [child description]
   permute                                              : [child description, perm]
@@ -30,6 +30,9 @@ def create_prox(ctx, desc):
     if name == "elem_operation:ind_simplex":
         count, dim, interleaved = data[:3]
         return api.ProxElemOperationIndSimplex(ctx, idx, count, dim, interleaved, diagsteps)
+    if name == "elem_operation:ind_sum":
+        count, dim, interleaved = data[:3]
+        return api.ProxElemOperationIndSum(ctx, idx, count, dim, interleaved, diagsteps)
     if name == "ind_epi_quad":
         count, dim, interleaved, (a, b, c) = data
         return api.ProxIndEpiQuad(ctx, idx, count, dim, interleaved, diagsteps, a, b, c)

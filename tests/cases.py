@@ -189,3 +189,16 @@ def prox_transform_cases(small=False):
                                   [a, [0.25], c, [0.0], e, ("elem_operation:1d:abs", 11, nt, True,
                                                             [nt, 1, False, coeffs()])]), nt + 30, None)
     return cases
+
+
+def prox_ind_sum_cases(small=False):
+    """elem_operation:ind_sum (elem_operation_ind_sum.hpp:38-58; test_prox_sum_ind_sum.m uses N = 21, d = 3)."""
+    cases = {}
+    for d in (1, 3, 7, 32, 100):
+        for il in (False, True):
+            n = 900 if not small else 37
+            cases[f"ind_sum_d{d}_il{int(il)}"] = (("elem_operation:ind_sum", 0, n * d, False, [n, d, il]), n * d)
+    cases["ind_sum_offset"] = (("elem_operation:ind_sum", 13, 40 * 5, False, [40, 5, False]), 40 * 5 + 21)
+    cases["moreau_ind_sum"] = (("moreau", 0, 50 * 4, False, [("elem_operation:ind_sum", 0, 50 * 4, False, [50, 4, True])]),
+                               50 * 4)
+    return cases

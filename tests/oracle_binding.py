@@ -40,6 +40,7 @@ lib.orc_add_zero.argtypes = [C.c_void_p, sz, sz, sz, sz]
 lib.orc_prox_elem.argtypes = [C.c_void_p, C.c_int, sz, sz, sz, C.c_int, C.c_int, C.c_int, C.POINTER(fp),
                               C.POINTER(sz)]
 lib.orc_prox_simplex.argtypes = [C.c_void_p, sz, sz, sz, C.c_int, C.c_int]
+lib.orc_prox_ind_sum.argtypes = [C.c_void_p, sz, sz, sz, C.c_int, C.c_int]
 lib.orc_prox_epi_quad.argtypes = [C.c_void_p, sz, sz, sz, C.c_int, C.c_int, fp, sz, fp, sz, fp, sz]
 lib.orc_prox_moreau.argtypes = [C.c_void_p, C.c_int]
 lib.orc_prox_permute.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), sz]
@@ -160,6 +161,9 @@ class OracleProblem:
         if name == "elem_operation:ind_simplex":
             count, dim, il = data[:3]
             return lib.orc_prox_simplex(self.h, idx, count, dim, int(il), int(diagsteps))
+        if name == "elem_operation:ind_sum":
+            count, dim, il = data[:3]
+            return lib.orc_prox_ind_sum(self.h, idx, count, dim, int(il), int(diagsteps))
         if name == "ind_epi_quad":
             count, dim, il, (a, b, c) = data
             a, b, c = _f32(a), _f32(b), _f32(c)

@@ -76,6 +76,9 @@ class _Writer:
         if name == "elem_operation:ind_simplex":
             count, dim, il = data[:3]
             return f"simplex {idx} {count} {dim} {int(il)} {int(ds)}"
+        if name == "elem_operation:ind_sum":
+            count, dim, il = data[:3]
+            return f"indsum {idx} {count} {dim} {int(il)} {int(ds)}"
         if name == "ind_epi_quad":
             count, dim, il, (a, b, c) = data
             return f"epiquad {idx} {count} {dim} {int(il)} {int(ds)} {self.coeff(a)} {self.coeff(b)} {self.coeff(c)}"

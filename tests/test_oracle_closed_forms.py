@@ -189,3 +189,22 @@ def test_prox_transform_equals_direct_coefficients():
             # differences of the inner results; the reference test only evaluates the non-inverted form)
             tol = 1e-4 if invert else 1e-5
             assert np.abs(x1 - x2).max() < tol * scale, (name, invert, float(np.abs(x1 - x2).max()), scale)
+
+
+def test_prox_ind_sum_closed_form():
+    """test_prox_sum_ind_sum.m: every group of the result sums to one (inf-norm 1e-5); and it is THE Euclidean
+    projection: x = y - (sum(y) - 1)/d, independent of the step sizes."""
+    import cases
+    from oracle_binding import oracle_prox_eval
+    for name, (desc, n) in cases.prox_ind_sum_cases().items():
+        if desc[0] != "elem_operation:ind_sum":
+            continue
+        idx, (count, dim, il) = desc[1], desc[4]
+        r = np.random.default_rng(dim + 7 * il)
+        y = r.standard_normal(n).astype(np.float32)
+        x = oracle_prox_eval(desc, y, r.random(n).astype(np.float32) + 0.1, 0.37)
+        Y = y[idx:idx + count * dim].reshape(count, dim) if il else y[idx:idx + count * dim].reshape(dim, count).T
+        X = x[idx:idx + count * dim].reshape(count, dim) if il else x[idx:idx + count * dim].reshape(dim, count).T
+        assert np.abs(X.sum(axis=1) - 1).max() < 1e-5 * max(1, dim / 8), name
+        want = Y.astype(np.float64) - (Y.astype(np.float64).sum(axis=1, keepdims=True) - 1) / dim
+        assert np.abs(X - want).max() < 1e-5, name

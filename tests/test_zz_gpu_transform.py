@@ -74,3 +74,24 @@ def test_rof_written_with_transform_solves_like_direct(ctx):
     assert_parity(got, want, label="ROF via transform")
     direct = run_cuda(ctx, desc, 60, stepsize="alg1", residual_iter=5)
     assert np.abs(got["x"] - direct["x"]).max() < 1e-4
+
+
+# ---- elem_operation:ind_sum (second item) -----------------------------------------------------
+SUM_CASES = cases.prox_ind_sum_cases()
+
+
+@pytest.mark.parametrize("name", sorted(SUM_CASES))
+def test_ind_sum_matches_oracle_and_reference(ctx, name):
+    desc, n = SUM_CASES[name]
+    arg, tau_diag, tau = _inputs(name, n)
+    got = pb.create_prox(ctx, desc).Eval(arg, tau_diag, tau)
+    want = oracle_prox_eval(desc, arg, tau_diag, tau)
+    lo, hi = desc[1], desc[1] + desc[2]
+    assert np.abs(got[lo:hi] - want[lo:hi]).max() <= 1e-5, name
+    if desc[0] == "elem_operation:ind_sum":          # test_prox_sum_ind_sum.m: groups sum to one
+        count, dim, il = desc[4]
+        G = got[lo:hi].reshape(count, dim) if il else got[lo:hi].reshape(dim, count).T
+        assert np.abs(G.sum(axis=1) - 1).max() < 1e-5 * max(1, dim / 8), name
+    if ref_driver.available():
+        ref = ref_driver.run_prox(desc, arg, tau_diag, tau)
+        assert np.abs(got[lo:hi] - ref[lo:hi]).max() <= 1e-5, name
