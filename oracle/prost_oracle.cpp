@@ -487,6 +487,46 @@ struct ProxIndSum : ProxSeparable {    // elem_operation_ind_sum.hpp:38-58: proj
   }
 };
 
+// SURVEY.md 8(f) row 2, oracle side only so far (the CUDA kernels follow once these are pinned on a GPU run of the
+// reference): projections onto a halfspace and onto the second-order cone, always planar like the reference.
+struct ProxIndHalfspace : ProxSeparable {   // prox_ind_halfspace.cu:34-92: { x | <a, x> <= b } per group
+  vec a, b;
+  ProxIndHalfspace(size_t i, size_t c, size_t d, bool il, bool ds, const float* pa, size_t na, const float* pb, size_t nb)
+      : ProxSeparable(i, c, d, il, ds), a(pa, pa + na), b(pb, pb + nb) {}
+  void eval_local(float* res, const float* arg, const float*, float, bool) override {
+    const bool a_per_group = a.size() == count * dim;     // else one normal of `dim` entries for all groups (:79-88)
+#pragma omp parallel for schedule(static)
+    for (size_t tx = 0; tx < count; ++tx) {
+      const float t = b.size() == count ? b[tx] : b[0];
+      auto n = [&](size_t k) { return a_per_group ? a[tx + count * k] : a[k]; };
+      float sq_norm = 0, iprod = 0;
+      for (size_t k = 0; k < dim; ++k) { sq_norm += n(k) * n(k); iprod += n(k) * arg[tx + count * k]; }   // :42-47
+      for (size_t k = 0; k < dim; ++k)
+        res[tx + count * k] = arg[tx + count * k] - (std::max(0.f, iprod - t) / sq_norm) * n(k);           // :49-51
+    }
+  }
+};
+
+struct ProxIndSOC : ProxSeparable {         // prox_ind_soc.cu:33-77: { (x, y) | |x|_2 <= y }, alpha = 1 only
+  ProxIndSOC(size_t i, size_t c, size_t d, bool il, bool ds) : ProxSeparable(i, c, d, il, ds) {}
+  void eval_local(float* res, const float* arg, const float*, float, bool) override {
+#pragma omp parallel for schedule(static)
+    for (size_t tx = 0; tx < count; ++tx) {
+      const float y0 = arg[count * (dim - 1) + tx];
+      float norm_x0 = 0;
+      for (size_t k = 0; k + 1 < dim; ++k) norm_x0 += arg[tx + count * k] * arg[tx + count * k];
+      norm_x0 = std::sqrt(norm_x0);
+      float fac, y;
+      if (norm_x0 <= y0) { fac = 1; y = y0; }                                   // inside the cone
+      else if (norm_x0 <= -y0) { fac = 0; y = 0; }                              // inside the polar cone
+      else { fac = (y0 + norm_x0) / (2 * norm_x0); y = fac * norm_x0; }
+      for (size_t k = 0; k + 1 < dim; ++k)
+        res[tx + count * k] = (norm_x0 <= y0) ? arg[tx + count * k] : fac * arg[tx + count * k];
+      res[count * (dim - 1) + tx] = y;
+    }
+  }
+};
+
 struct ProxEpiQuad : ProxSeparable {   // prox_ind_epi_quad.cu:42-79 (always planar)
   vec a, b, c;
   ProxEpiQuad(size_t i, size_t cnt, size_t d, bool il, bool ds, const float* a_, size_t na, const float* b_,
@@ -990,6 +1030,13 @@ int orc_prox_simplex(void* p, size_t idx, size_t count, size_t dim, int il, int 
 }
 int orc_prox_ind_sum(void* p, size_t idx, size_t count, size_t dim, int il, int ds) {
   return push(PP, std::make_shared<ProxIndSum>(idx, count, dim, il != 0, ds != 0));
+}
+int orc_prox_ind_halfspace(void* p, size_t idx, size_t count, size_t dim, int il, int ds, const float* a, size_t na,
+                           const float* b, size_t nb) {
+  return push(PP, std::make_shared<ProxIndHalfspace>(idx, count, dim, il != 0, ds != 0, a, na, b, nb));
+}
+int orc_prox_ind_soc(void* p, size_t idx, size_t count, size_t dim, int il, int ds) {
+  return push(PP, std::make_shared<ProxIndSOC>(idx, count, dim, il != 0, ds != 0));
 }
 int orc_prox_epi_quad(void* p, size_t idx, size_t count, size_t dim, int il, int ds, const float* a, size_t na,
                       const float* b, size_t nb, const float* c, size_t nc) {

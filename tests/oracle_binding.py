@@ -41,6 +41,8 @@ lib.orc_prox_elem.argtypes = [C.c_void_p, C.c_int, sz, sz, sz, C.c_int, C.c_int,
                               C.POINTER(sz)]
 lib.orc_prox_simplex.argtypes = [C.c_void_p, sz, sz, sz, C.c_int, C.c_int]
 lib.orc_prox_ind_sum.argtypes = [C.c_void_p, sz, sz, sz, C.c_int, C.c_int]
+lib.orc_prox_ind_halfspace.argtypes = [C.c_void_p, sz, sz, sz, C.c_int, C.c_int, fp, sz, fp, sz]
+lib.orc_prox_ind_soc.argtypes = [C.c_void_p, sz, sz, sz, C.c_int, C.c_int]
 lib.orc_prox_epi_quad.argtypes = [C.c_void_p, sz, sz, sz, C.c_int, C.c_int, fp, sz, fp, sz, fp, sz]
 lib.orc_prox_moreau.argtypes = [C.c_void_p, C.c_int]
 lib.orc_prox_permute.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), sz]
@@ -161,6 +163,14 @@ class OracleProblem:
         if name == "elem_operation:ind_simplex":
             count, dim, il = data[:3]
             return lib.orc_prox_simplex(self.h, idx, count, dim, int(il), int(diagsteps))
+        if name == "ind_halfspace":            # oracle only so far
+            count, dim, il, (a, b) = data
+            a, b = _f32(a), _f32(b)
+            return lib.orc_prox_ind_halfspace(self.h, idx, count, dim, int(il), int(diagsteps), _p(a), a.size,
+                                              _p(b), b.size)
+        if name == "ind_soc":
+            count, dim, il = data[:3]
+            return lib.orc_prox_ind_soc(self.h, idx, count, dim, int(il), int(diagsteps))
         if name == "elem_operation:ind_sum":
             count, dim, il = data[:3]
             return lib.orc_prox_ind_sum(self.h, idx, count, dim, int(il), int(diagsteps))

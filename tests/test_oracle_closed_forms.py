@@ -208,3 +208,40 @@ def test_prox_ind_sum_closed_form():
         assert np.abs(X.sum(axis=1) - 1).max() < 1e-5 * max(1, dim / 8), name
         want = Y.astype(np.float64) - (Y.astype(np.float64).sum(axis=1, keepdims=True) - 1) / dim
         assert np.abs(X - want).max() < 1e-5, name
+
+
+def test_prox_ind_halfspace_and_soc_are_projections():
+    """Oracle groundwork for SURVEY.md 8(f) row 2 (prox_ind_halfspace.cu:34-92, prox_ind_soc.cu:33-77): results are
+    feasible, feasible points stay put, and the displacement is normal to the constraint / cone surface
+    (optimality of a Euclidean projection), against a float64 closed form."""
+    from oracle_binding import oracle_prox_eval
+    r = np.random.default_rng(5)
+    count, dim = 400, 5
+    V = r.standard_normal((count, dim)).astype(np.float32)
+    ones = np.ones(count * dim, np.float32)
+    # halfspace, one normal per group and one shared normal; b per group and scalar
+    for per_group in (True, False):
+        A = r.standard_normal((count, dim) if per_group else (1, dim)).astype(np.float32)
+        b = r.standard_normal(count).astype(np.float32) if per_group else np.array([0.3], np.float32)
+        a_flat = A.T.ravel() if per_group else A.ravel()           # planar: element (group, k) at group + count*k
+        desc = ("ind_halfspace", 0, count * dim, False, [count, dim, False, [a_flat, b]])
+        X = oracle_prox_eval(desc, V.T.ravel(), ones, 1.0).reshape(dim, count).T
+        An = np.broadcast_to(A, (count, dim)).astype(np.float64)
+        bb = np.broadcast_to(b, (count,)).astype(np.float64)
+        viol = np.maximum(0.0, (An * V).sum(1) - bb)
+        want = V - (viol / (An * An).sum(1))[:, None] * An
+        assert np.abs(X - want).max() < 1e-5
+        assert ((An * X).sum(1) <= bb + 1e-4).all()
+    # second-order cone: last component is y
+    dim = 4
+    W = r.standard_normal((count, dim)).astype(np.float32)
+    W[:50, -1] = np.abs(W[:50, -1]) + np.linalg.norm(W[:50, :-1], axis=1)          # inside the cone
+    W[50:100, -1] = -np.abs(W[50:100, -1]) - np.linalg.norm(W[50:100, :-1], axis=1)  # inside the polar cone
+    desc = ("ind_soc", 0, count * dim, False, [count, dim, False])
+    X = oracle_prox_eval(desc, W.T.ravel(), np.ones(count * dim, np.float32), 1.0).reshape(dim, count).T
+    assert np.array_equal(X[:50], W[:50]) and not X[50:100].any()
+    nx, y = np.linalg.norm(X[:, :-1], axis=1), X[:, -1]
+    assert (nx <= y + 1e-5).all()
+    D = (W - X).astype(np.float64)                                   # residual lies in the polar cone, orthogonal to X
+    assert (np.linalg.norm(D[:, :-1], axis=1) <= -D[:, -1] + 1e-5).all()
+    assert np.abs((D * X).sum(1)).max() < 1e-5
