@@ -160,6 +160,15 @@ int pb_prox_create_ind_simplex(pb_context* ctx, size_t index, size_t count, size
  * (elem_operation_ind_sum.hpp:38-58; mex name "elem_operation:ind_sum", +function/sum_ind_sum.m) */
 int pb_prox_create_ind_sum(pb_context* ctx, size_t index, size_t count, size_t dim, int interleaved,
                            int diagsteps, pb_prox** out);
+/* ProxIndHalfspace(index,count,dim,interleaved,diagsteps,a,b): projection onto <a, x> <= b per group; a has
+ * count*dim (planar) or dim entries, b count or 1 (prox_ind_halfspace.hpp:41-52, prox_ind_halfspace.cu:34-137) */
+int pb_prox_create_ind_halfspace(pb_context* ctx, size_t index, size_t count, size_t dim, int interleaved,
+                                 int diagsteps, const float* h_a, size_t na, const float* h_b, size_t nb,
+                                 pb_prox** out);
+/* ProxIndSOC(index,count,dim,interleaved,diagsteps,alpha): projection onto |x|_2 <= y, y = last component;
+ * alpha must be 1 like in the reference (prox_ind_soc.hpp:39-48, prox_ind_soc.cu:33-120) */
+int pb_prox_create_ind_soc(pb_context* ctx, size_t index, size_t count, size_t dim, int interleaved,
+                           int diagsteps, float alpha, pb_prox** out);
 /* ProxIndEpiQuad(index,count,dim,interleaved,diagsteps,a,b,c): prox_ind_epi_quad.hpp:42-51 */
 int pb_prox_create_ind_epi_quad(pb_context* ctx, size_t index, size_t count, size_t dim,
                                 int interleaved, int diagsteps, const float* h_a, size_t na,

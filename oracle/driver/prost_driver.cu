@@ -22,6 +22,8 @@
 //     PROX := elem1d|norm2 <fun> <idx> <count> <dim> <interleaved> <diagsteps> <c0> .. <c6>
 //           | simplex <idx> <count> <dim> <interleaved> <diagsteps>
 //           | indsum <idx> <count> <dim> <interleaved> <diagsteps>
+//           | halfspace <idx> <count> <dim> <interleaved> <diagsteps> <a> <b>
+//           | soc <idx> <count> <dim> <interleaved> <diagsteps> <alpha>
 //           | epiquad <idx> <count> <dim> <interleaved> <diagsteps> <a> <b> <c>
 //           | moreau <PROX> | permute <perm.i32> <n> <PROX> | zero <idx> <size>
 //           | transform <a> <b> <c> <d> <e> <PROX>
@@ -65,6 +67,8 @@
 #include "prost/prox/prox_elem_operation.hpp"
 #include "prost/prox/prox_ind_epi_quad.hpp"
 #include "prost/prox/prox_moreau.hpp"
+#include "prost/prox/prox_ind_halfspace.hpp"
+#include "prost/prox/prox_ind_soc.hpp"
 #include "prost/prox/prox_transform.hpp"
 #include "prost/prox/prox_permute.hpp"
 #include "prost/prox/prox_zero.hpp"
@@ -150,6 +154,20 @@ static std::shared_ptr<Prox<real>> parse_prox(std::istringstream& in) {
     in >> idx >> count >> dim >> il >> ds;
     return std::shared_ptr<Prox<real>>(
         new ProxElemOperation<real, ElemOperationIndSimplex<real>>(idx, count, dim, il, ds));
+  }
+  if (kind == "halfspace") {
+    size_t idx, count, dim;
+    int il, ds;
+    std::string a, b;
+    in >> idx >> count >> dim >> il >> ds >> a >> b;
+    return std::shared_ptr<Prox<real>>(new ProxIndHalfspace<real>(idx, count, dim, il, ds, coeff(a), coeff(b)));
+  }
+  if (kind == "soc") {
+    size_t idx, count, dim;
+    int il, ds;
+    double alpha;
+    in >> idx >> count >> dim >> il >> ds >> alpha;
+    return std::shared_ptr<Prox<real>>(new ProxIndSOC<real>(idx, count, dim, il, ds, static_cast<real>(alpha)));
   }
   if (kind == "indsum") {
     size_t idx, count, dim;

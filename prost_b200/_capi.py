@@ -116,6 +116,10 @@ SIGNATURES = {
     "pb_prox_create_ind_simplex": (C.c_int, [handle, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int,
                                              handle_p]),
     "pb_prox_create_ind_sum": (C.c_int, [handle, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int, handle_p]),
+    "pb_prox_create_ind_halfspace": (C.c_int, [handle, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int,
+                                               c_float_p, C.c_size_t, c_float_p, C.c_size_t, handle_p]),
+    "pb_prox_create_ind_soc": (C.c_int, [handle, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_float,
+                                         handle_p]),
     "pb_prox_create_ind_epi_quad": (C.c_int, [handle, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int,
                                               c_float_p, C.c_size_t, c_float_p, C.c_size_t, c_float_p,
                                               C.c_size_t, handle_p]),

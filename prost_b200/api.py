@@ -302,6 +302,25 @@ class ProxElemOperationIndSum(Prox):
                                          C.byref(self._h)))
 
 
+class ProxIndHalfspace(Prox):
+    """ProxIndHalfspace<T>(index, count, dim, interleaved, diagsteps, a, b): projection onto <a, x> <= b."""
+
+    def __init__(self, ctx, index, count, dim, interleaved, diagsteps, a, b):
+        super().__init__(ctx)
+        a, b = _f32(a), _f32(b)
+        check(lib.pb_prox_create_ind_halfspace(ctx._h, index, count, dim, int(interleaved), int(diagsteps),
+                                               _fp(a), a.size, _fp(b), b.size, C.byref(self._h)))
+
+
+class ProxIndSOC(Prox):
+    """ProxIndSOC<T>(index, count, dim, interleaved, diagsteps, alpha): projection onto the second-order cone."""
+
+    def __init__(self, ctx, index, count, dim, interleaved, diagsteps, alpha=1.0):
+        super().__init__(ctx)
+        check(lib.pb_prox_create_ind_soc(ctx._h, index, count, dim, int(interleaved), int(diagsteps), float(alpha),
+                                         C.byref(self._h)))
+
+
 class ProxTransform(Prox):
     """ProxTransform<T>(inner, a, b, c, d, e): prox of c f(a x - b) + <d, x> + (e/2)|x|^2 through the prox of f
     (prox_transform.hpp:38-44); every coefficient is a scalar or one value per element."""

@@ -309,6 +309,14 @@ int pb_prox_create_ind_sum(pb_context* c, size_t index, size_t count, size_t dim
                            pb_prox** out) {
   PB_MAKE_PROX(pb::make_prox_ind_sum(&c->ctx, index, count, dim, interleaved != 0, diagsteps != 0));
 }
+int pb_prox_create_ind_halfspace(pb_context* c, size_t index, size_t count, size_t dim, int interleaved, int diagsteps,
+                                 const float* a, size_t na, const float* b, size_t nb, pb_prox** out) {
+  PB_MAKE_PROX(pb::make_prox_ind_halfspace(&c->ctx, index, count, dim, interleaved != 0, diagsteps != 0, a, na, b, nb));
+}
+int pb_prox_create_ind_soc(pb_context* c, size_t index, size_t count, size_t dim, int interleaved, int diagsteps,
+                           float alpha, pb_prox** out) {
+  PB_MAKE_PROX(pb::make_prox_ind_soc(&c->ctx, index, count, dim, interleaved != 0, diagsteps != 0, alpha));
+}
 int pb_prox_create_ind_epi_quad(pb_context* c, size_t index, size_t count, size_t dim, int interleaved,
                                 int diagsteps, const float* a, size_t na, const float* b, size_t nb,
                                 const float* cc, size_t nc, pb_prox** out) {

@@ -390,6 +390,120 @@ class ProxIndSum : public Prox {
   bool interleaved_;
 };
 
+// ---- ProxIndHalfspace (prox_ind_halfspace.cu:34-92): projection of every group onto { x | <a, x> <= b }; planar
+// groups (element k of group tx at tx + count*k); `a` holds one normal per group (count*dim, planar) or one normal
+// for all groups (dim); `b` one offset per group or one for all.  tau is ignored like in the reference.
+__global__ void __launch_bounds__(kBlock) ind_halfspace_kernel(float* __restrict__ res, const float* __restrict__ arg,
+                                                               size_t count, size_t dim, const float* __restrict__ a,
+                                                               const float* __restrict__ b, bool a_per_group,
+                                                               bool b_per_group) {
+  for (size_t tx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; tx < count; tx += (size_t)gridDim.x * blockDim.x) {
+    const float t = b_per_group ? b[tx] : b[0];
+    const float* n = a_per_group ? a + tx : a;
+    const size_t n_stride = a_per_group ? count : 1;
+    float sq_norm = 0, iprod = 0;
+    for (size_t k = 0; k < dim; ++k) {                                   // ProjectHalfspace :42-47
+      const float nk = n[k * n_stride];
+      sq_norm += nk * nk;
+      iprod += nk * arg[tx + count * k];
+    }
+    for (size_t k = 0; k < dim; ++k)                                     // :49-51
+      res[tx + count * k] = arg[tx + count * k] - (fmaxf(0.f, iprod - t) / sq_norm) * n[k * n_stride];
+  }
+}
+
+// ---- ProxIndSOC (prox_ind_soc.cu:33-77): projection onto { (x, y) | |x|_2 <= y }; x = components 0..dim-2 (planar),
+// y = component dim-1; alpha = 1 only, like the reference (ProxIndSOC::Initialize).
+__global__ void __launch_bounds__(kBlock) ind_soc_kernel(float* __restrict__ res, const float* __restrict__ arg,
+                                                         size_t count, size_t dim) {
+  for (size_t tx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; tx < count; tx += (size_t)gridDim.x * blockDim.x) {
+    const float y0 = arg[count * (dim - 1) + tx];
+    float norm_x0 = 0;
+    for (size_t k = 0; k + 1 < dim; ++k) norm_x0 += arg[tx + count * k] * arg[tx + count * k];
+    norm_x0 = sqrtf(norm_x0);
+    if (norm_x0 <= y0) {
+      for (size_t k = 0; k + 1 < dim; ++k) res[tx + count * k] = arg[tx + count * k];
+      res[count * (dim - 1) + tx] = y0;
+    } else if (norm_x0 <= -y0) {
+      for (size_t k = 0; k + 1 < dim; ++k) res[tx + count * k] = 0;
+      res[count * (dim - 1) + tx] = 0;
+    } else {
+      const float fac = (y0 + norm_x0) / (2 * norm_x0);
+      for (size_t k = 0; k + 1 < dim; ++k) res[tx + count * k] = fac * arg[tx + count * k];
+      res[count * (dim - 1) + tx] = fac * norm_x0;
+    }
+  }
+}
+
+// common part of the planar-group projections that live outside the fused machinery
+class ProxGroupProjection : public Prox {
+ public:
+  ProxGroupProjection(Context* ctx, size_t index, size_t count, size_t dim, bool interleaved, bool diagsteps)
+      : Prox(ctx, index, count * dim, diagsteps), count_(count), dim_(dim), interleaved_(interleaved) {
+    if (index + count * dim >= (1ull << 31)) fail(PB_ERR_UNSUPPORTED, "prox range exceeds 2^31-1");
+  }
+  size_t uniform_group_size() const override { return dim_; }
+  void get_separable_structure(std::vector<std::tuple<size_t, size_t, size_t>>& sep) const override {
+    for (size_t i = 0; i < count_; ++i) {                 // ProxSeparableSum (prox_separable_sum.hpp:65-77)
+      if (interleaved_) sep.emplace_back(index_ + i * dim_, dim_, 1);
+      else sep.emplace_back(index_ + i, dim_, count_);
+    }
+  }
+
+ protected:
+  size_t count_, dim_;
+  bool interleaved_;
+};
+
+class ProxIndHalfspace : public ProxGroupProjection {
+ public:
+  ProxIndHalfspace(Context* ctx, size_t index, size_t count, size_t dim, bool interleaved, bool diagsteps,
+                   const float* a, size_t na, const float* b, size_t nb)
+      : ProxGroupProjection(ctx, index, count, dim, interleaved, diagsteps) {
+    // checks and messages of ProxIndHalfspace::Initialize (prox_ind_halfspace.cu:132-137)
+    if (!a || !b || (na != count * dim && na != dim))
+      fail(PB_ERR_INVALID, "Wrong input: Coefficient a has to have dimension count*dim or dim!");
+    if (nb != count && nb != 1) fail(PB_ERR_INVALID, "Wrong input: Coefficient b has to have dimension count or 1!");
+    a_per_group_ = na == count * dim;          // (count == 1: both readings address the same elements)
+    b_per_group_ = nb == count;
+    d_a_.resize(na);
+    d_b_.resize(nb);
+    upload_from_host(ctx, d_a_.data(), a, na);
+    upload_from_host(ctx, d_b_.data(), b, nb);
+  }
+  int kind() const override { return kProxIndHalfspace; }
+  size_t gpu_mem_amount() const override { return (d_a_.size() + d_b_.size()) * sizeof(float); }
+  void eval_local(float* res, const float* arg, const float*, float, bool) override {
+    ctx_->bind();
+    if (count_ == 0) return;
+    ind_halfspace_kernel<<<stream_grid(ctx_, count_), kBlock, 0, ctx_->stream>>>(
+        res, arg, count_, dim_, d_a_.data(), d_b_.data(), a_per_group_, b_per_group_);
+    PB_CHECK_LAUNCH();
+    ctx_->launches++;
+  }
+
+ private:
+  DeviceBuffer<float> d_a_, d_b_;
+  bool a_per_group_ = false, b_per_group_ = false;
+};
+
+class ProxIndSOC : public ProxGroupProjection {
+ public:
+  ProxIndSOC(Context* ctx, size_t index, size_t count, size_t dim, bool interleaved, bool diagsteps, float alpha)
+      : ProxGroupProjection(ctx, index, count, dim, interleaved, diagsteps) {
+    if (alpha != 1) fail(PB_ERR_INVALID, "ProxIndSOC: Only alpha = 1 implemented right now.");   // prox_ind_soc.cu:117-119
+    if (dim < 1) fail(PB_ERR_INVALID, "ProxIndSOC needs dim >= 1");
+  }
+  int kind() const override { return kProxIndSOC; }
+  void eval_local(float* res, const float* arg, const float*, float, bool) override {
+    ctx_->bind();
+    if (count_ == 0) return;
+    ind_soc_kernel<<<stream_grid(ctx_, count_), kBlock, 0, ctx_->stream>>>(res, arg, count_, dim_);
+    PB_CHECK_LAUNCH();
+    ctx_->launches++;
+  }
+};
+
 // ---- ProxTransform (prox_transform.cu:27-226): prox of  c f(a x - b) + <d, x> + (e/2)|x|^2  through the prox of f.
 // Same three element-wise steps around the inner prox as the reference, same float expressions.
 struct TransformCoeffs {
@@ -543,6 +657,14 @@ std::shared_ptr<Prox> make_prox_moreau(Context* ctx, std::shared_ptr<Prox> inner
 std::shared_ptr<Prox> make_prox_ind_sum(Context* ctx, size_t index, size_t count, size_t dim, bool interleaved,
                                         bool diagsteps) {
   return std::make_shared<ProxIndSum>(ctx, index, count, dim, interleaved, diagsteps);
+}
+std::shared_ptr<Prox> make_prox_ind_halfspace(Context* ctx, size_t index, size_t count, size_t dim, bool interleaved,
+                                              bool diagsteps, const float* a, size_t na, const float* b, size_t nb) {
+  return std::make_shared<ProxIndHalfspace>(ctx, index, count, dim, interleaved, diagsteps, a, na, b, nb);
+}
+std::shared_ptr<Prox> make_prox_ind_soc(Context* ctx, size_t index, size_t count, size_t dim, bool interleaved,
+                                        bool diagsteps, float alpha) {
+  return std::make_shared<ProxIndSOC>(ctx, index, count, dim, interleaved, diagsteps, alpha);
 }
 std::shared_ptr<Prox> make_prox_transform(Context* ctx, std::shared_ptr<Prox> inner, const float* const coeffs[5],
                                           const size_t coeff_len[5]) {

@@ -27,6 +27,8 @@ enum ProxKind : int {
   kProxPermute = 6,
   kProxTransform = 7,
   kProxIndSum = 8,
+  kProxIndHalfspace = 9,
+  kProxIndSOC = 10,
 };
 
 // per-element vector or scalar (ElemOpCoefficients: prox_elem_operation.hpp:104-109)
@@ -364,6 +366,12 @@ std::shared_ptr<Prox> make_prox_moreau(Context* ctx, std::shared_ptr<Prox> inner
 // ProxElemOperation<T, ElemOperationIndSum<T>> (elem_operation_ind_sum.hpp:38-58): sum-to-one projection per group
 std::shared_ptr<Prox> make_prox_ind_sum(Context* ctx, size_t index, size_t count, size_t dim, bool interleaved,
                                         bool diagsteps);
+// ProxIndHalfspace(index,count,dim,interleaved,diagsteps,a,b) (prox_ind_halfspace.hpp:41-52), ProxIndSOC(..., alpha)
+// (prox_ind_soc.hpp:39-48); both address planar groups regardless of `interleaved`, like the reference kernels
+std::shared_ptr<Prox> make_prox_ind_halfspace(Context* ctx, size_t index, size_t count, size_t dim, bool interleaved,
+                                              bool diagsteps, const float* a, size_t na, const float* b, size_t nb);
+std::shared_ptr<Prox> make_prox_ind_soc(Context* ctx, size_t index, size_t count, size_t dim, bool interleaved,
+                                        bool diagsteps, float alpha);
 // ProxTransform (prox_transform.hpp:38-44): a, b, c, d, e with one value or one value per element
 std::shared_ptr<Prox> make_prox_transform(Context* ctx, std::shared_ptr<Prox> inner, const float* const coeffs[5],
                                           const size_t coeff_len[5]);

@@ -9,6 +9,8 @@ reference's mex registry names and argument order (matlab/+prost/private/factory
   elem_operation:1d:<fun>, elem_operation:norm2:<fun> : [count, dim, interleaved, [a,b,c,d,e,alpha,beta]]
   elem_operation:ind_simplex, elem_operation:ind_sum   : [count, dim, interleaved]
   ind_epi_quad                                         : [count, dim, interleaved, [a, b, c]]
+  ind_halfspace                                        : [count, dim, interleaved, [a, b]]
+  ind_soc                                              : [count, dim, interleaved, alpha]
   moreau                                               : [child description]
   permute                                              : [child description, perm]
   transform                                            : [a, b, c, d, e, child description]   (+function/transform.m)
@@ -33,6 +35,12 @@ def create_prox(ctx, desc):
     if name == "elem_operation:ind_sum":
         count, dim, interleaved = data[:3]
         return api.ProxElemOperationIndSum(ctx, idx, count, dim, interleaved, diagsteps)
+    if name == "ind_halfspace":
+        count, dim, interleaved, (a, b) = data
+        return api.ProxIndHalfspace(ctx, idx, count, dim, interleaved, diagsteps, a, b)
+    if name == "ind_soc":
+        count, dim, interleaved = data[:3]
+        return api.ProxIndSOC(ctx, idx, count, dim, interleaved, diagsteps, data[3] if len(data) > 3 else 1.0)
     if name == "ind_epi_quad":
         count, dim, interleaved, (a, b, c) = data
         return api.ProxIndEpiQuad(ctx, idx, count, dim, interleaved, diagsteps, a, b, c)

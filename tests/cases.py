@@ -202,3 +202,21 @@ def prox_ind_sum_cases(small=False):
     cases["moreau_ind_sum"] = (("moreau", 0, 50 * 4, False, [("elem_operation:ind_sum", 0, 50 * 4, False, [50, 4, True])]),
                                50 * 4)
     return cases
+
+
+def prox_projection_cases(small=False):
+    """ind_halfspace (prox_ind_halfspace.cu) and ind_soc (prox_ind_soc.cu): planar groups."""
+    r = rng(31)
+    cases = {}
+    n = 700 if not small else 29
+    for d in (1, 2, 5, 17):
+        a_g = r.standard_normal(n * d).astype(np.float32) + 0.1
+        cases[f"halfspace_d{d}_group"] = (("ind_halfspace", 0, n * d, False,
+                                           [n, d, False, [a_g, r.standard_normal(n).astype(np.float32)]]), n * d)
+        cases[f"halfspace_d{d}_shared"] = (("ind_halfspace", 0, n * d, False,
+                                            [n, d, False, [r.standard_normal(d).astype(np.float32) + 0.1, [0.3]]]), n * d)
+    for d in (2, 3, 9):
+        cases[f"soc_d{d}"] = (("ind_soc", 0, n * d, False, [n, d, False, 1.0]), n * d)
+    cases["soc_offset"] = (("ind_soc", 9, n * 4, False, [n, 4, False, 1.0]), n * 4 + 15)
+    cases["moreau_soc"] = (("moreau", 0, n * 3, False, [("ind_soc", 0, n * 3, False, [n, 3, False, 1.0])]), n * 3)
+    return cases

@@ -76,6 +76,12 @@ class _Writer:
         if name == "elem_operation:ind_simplex":
             count, dim, il = data[:3]
             return f"simplex {idx} {count} {dim} {int(il)} {int(ds)}"
+        if name == "ind_halfspace":
+            count, dim, il, (a, b) = data
+            return f"halfspace {idx} {count} {dim} {int(il)} {int(ds)} {self.coeff(a)} {self.coeff(b)}"
+        if name == "ind_soc":
+            count, dim, il = data[:3]
+            return f"soc {idx} {count} {dim} {int(il)} {int(ds)} {float(data[3]) if len(data) > 3 else 1.0!r}"
         if name == "elem_operation:ind_sum":
             count, dim, il = data[:3]
             return f"indsum {idx} {count} {dim} {int(il)} {int(ds)}"

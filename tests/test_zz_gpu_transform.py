@@ -95,3 +95,30 @@ def test_ind_sum_matches_oracle_and_reference(ctx, name):
     if ref_driver.available():
         ref = ref_driver.run_prox(desc, arg, tau_diag, tau)
         assert np.abs(got[lo:hi] - ref[lo:hi]).max() <= 1e-5, name
+
+
+# ---- ind_halfspace, ind_soc -------------------------------------------------------------
+PROJ_CASES = cases.prox_projection_cases()
+
+
+@pytest.mark.parametrize("name", sorted(PROJ_CASES))
+def test_projection_prox_matches_oracle_and_reference(ctx, name):
+    desc, n = PROJ_CASES[name]
+    arg, tau_diag, tau = _inputs(name, n)
+    got = pb.create_prox(ctx, desc).Eval(arg, tau_diag, tau)
+    want = oracle_prox_eval(desc, arg, tau_diag, tau)
+    lo, hi = desc[1], desc[1] + desc[2]
+    scale = max(1.0, float(np.abs(want[lo:hi]).max()))
+    assert np.abs(got[lo:hi] - want[lo:hi]).max() <= 2e-5 * scale, name
+    if ref_driver.available():
+        ref = ref_driver.run_prox(desc, arg, tau_diag, tau)
+        assert np.abs(got[lo:hi] - ref[lo:hi]).max() <= 1e-5 * scale, name
+
+
+def test_projection_prox_errors(ctx):
+    with pytest.raises(pb.ProstError) as e:
+        pb.ProxIndSOC(ctx, 0, 10, 3, False, False, alpha=2.0)
+    assert "Only alpha = 1" in str(e.value)
+    with pytest.raises(pb.ProstError) as e:
+        pb.ProxIndHalfspace(ctx, 0, 10, 3, False, False, np.ones(7, np.float32), np.ones(1, np.float32))
+    assert "Coefficient a has to have dimension count*dim or dim" in str(e.value)
