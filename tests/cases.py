@@ -220,3 +220,13 @@ def prox_projection_cases(small=False):
     cases["soc_offset"] = (("ind_soc", 9, n * 4, False, [n, 4, False, 1.0]), n * 4 + 15)
     cases["moreau_soc"] = (("moreau", 0, n * 3, False, [("ind_soc", 0, n * 3, False, [n, 3, False, 1.0])]), n * 3)
     return cases
+
+
+def all_prox_cases(small=False):
+    """prox_cases() plus the SURVEY.md 8(f) row-2 proxes, as name -> (description, vector length): what
+    tests/golden/make_golden.py records from the reference and test_oracle_golden.py replays on the CPU."""
+    out = dict(prox_cases(small))
+    out.update({k: (v[0], v[1]) for k, v in prox_transform_cases(small).items()})
+    out.update(prox_ind_sum_cases(small))
+    out.update(prox_projection_cases(small))
+    return out

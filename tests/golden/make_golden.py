@@ -51,7 +51,7 @@ def main(out, only=""):
         a = ref_driver.run_linop(blocks, y, True)
         np.savez_compressed(os.path.join(out, f"linop_{name}.npz"), x=x, y=y, fwd=f["res"], adj=a["res"],
                             rowsum=f["rowsum"], colsum=f["colsum"])
-    for name, (desc, n) in cases.prox_cases(small=True).items():
+    for name, (desc, n) in cases.all_prox_cases(small=True).items():
         r = np.random.default_rng(zlib.crc32(name.encode()))
         arg = (2 * r.standard_normal(n)).astype(np.float32)
         td = r.uniform(0.5, 1.5, n).astype(np.float32)

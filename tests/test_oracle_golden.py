@@ -47,7 +47,7 @@ def test_oracle_linop_matches_reference(path):
 def test_oracle_prox_matches_reference(path):
     name = os.path.basename(path)[5:-4]
     g = np.load(path)
-    desc, n = cases.prox_cases(small=True)[name]
+    desc, n = cases.all_prox_cases(small=True)[name]
     res = oracle_prox_eval(desc, g["arg"], g["tau_diag"], float(g["tau"]))
     lo, hi = desc[1], desc[1] + desc[2]
     jumpy = any(k in name for k in ("l0", "truncquad", "trunclin", "lq"))
