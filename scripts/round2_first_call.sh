@@ -29,3 +29,7 @@ except Exception as e:
     print("source page summary failed:", e)
 PY
 rm -f gpurun_out/r2_lifting_check.ncu-rep gpurun_out/r2_lifting_check_source.csv
+#  4. golden fixtures of the 8(f) row-2 proxes (ProxTransform, ind_sum, ind_halfspace, ind_soc) from the live reference;
+#     copy gpurun_out/golden_new/*.npz into tests/golden/ afterwards
+timeout 300 python tests/golden/make_golden.py gpurun_out/golden_new new_prox > gpurun_out/r2_golden.log 2>&1
+ls gpurun_out/golden_new | wc -l

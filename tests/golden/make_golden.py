@@ -40,6 +40,17 @@ def main(out, only=""):
     assert ref_driver.available(), "oracle/_ref/prost_ref_driver missing"
     if only == "admm":
         return main_admm(out)
+    if only == "new_prox":        # only the prox cases that have no fixture yet (small files, quick)
+        for name, (desc, n) in cases.all_prox_cases(small=True).items():
+            if os.path.exists(os.path.join(HERE, f"prox_{name}.npz")):
+                continue
+            r = np.random.default_rng(zlib.crc32(name.encode()))
+            arg = (2 * r.standard_normal(n)).astype(np.float32)
+            td = r.uniform(0.5, 1.5, n).astype(np.float32)
+            res = ref_driver.run_prox(desc, arg, td, 0.7)
+            np.savez_compressed(os.path.join(out, f"prox_{name}.npz"), arg=arg, tau_diag=td, tau=np.float32(0.7),
+                                res=res)
+        return
     for name, blocks in cases.linop_cases(small=True).items():
         r = np.random.default_rng(zlib.crc32(name.encode()))
         from oracle_binding import OracleProblem
