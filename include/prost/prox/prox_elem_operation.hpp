@@ -5,6 +5,7 @@
 
 #include <array>
 
+#include "prost/prox/elemop/elem_operation.hpp"
 #include "prost/prox/prox_separable_sum.hpp"
 
 namespace prost {

@@ -62,3 +62,23 @@ def test_no_cpu_fallback_without_gpu():
     with pytest.raises(pb.ProstError) as e:
         pb.Context(0)
     assert "no CPU fallback" in str(e.value)
+
+
+def test_public_headers_compile_standalone():
+    """include/prost_b200.h is plain C (the drop-in boundary binds from C, cgo-style FFI and ctypes alike) and
+    every include/prost/**/*.hpp shim compiles on its own with a host C++14 compiler (no nvcc, no thrust)."""
+    import glob
+    import shutil
+    import subprocess
+    inc = os.path.join(ROOT, "include")
+    gcc, gxx = shutil.which("gcc"), shutil.which("g++")
+    if not gcc or not gxx:
+        pytest.skip("no host compiler")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c",
+                        os.path.join(inc, "prost_b200.h")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for hpp in sorted(glob.glob(os.path.join(inc, "prost", "**", "*.hpp"), recursive=True)):
+        rel = os.path.relpath(hpp, inc)
+        r = subprocess.run([gxx, "-std=c++14", "-fsyntax-only", "-x", "c++", "-I", inc, "-"],
+                           input=f'#include "{rel}"\nint main() {{ return 0; }}\n', capture_output=True, text=True)
+        assert r.returncode == 0, f"{rel}:\n{r.stderr[:2000]}"
