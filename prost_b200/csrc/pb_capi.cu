@@ -578,11 +578,14 @@ int pb_solver_solve(pb_backend* b, const pb_solver_options* so, pb_stopping_cb s
 
     // Fault the (pageable) result buffers in on a helper thread while the GPU iterates: the final
     // read-back of x, z, y, w then lands in resident pages (pb_hostio.cu).  Joined before the first copy.
-    std::thread prefault([=] {
+    std::thread prefault([=] {      // one thread per buffer: short solves must not wait for 400 MB of page faults
+      std::thread ty([=] { pb::prefault_host_range(py, m * sizeof(float)); });
+      std::thread tz([=] { pb::prefault_host_range(pz, m * sizeof(float)); });
+      std::thread tw([=] { pb::prefault_host_range(pw, n * sizeof(float)); });
       pb::prefault_host_range(px, n * sizeof(float));
-      pb::prefault_host_range(py, m * sizeof(float));
-      pb::prefault_host_range(pz, m * sizeof(float));
-      pb::prefault_host_range(pw, n * sizeof(float));
+      ty.join();
+      tz.join();
+      tw.join();
     });
     struct Joiner {
       std::thread& t;

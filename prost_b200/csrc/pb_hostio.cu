@@ -129,7 +129,7 @@ namespace {
 
 constexpr size_t kStageBytes = 32u << 20;
 constexpr size_t kDirectBytes = 1u << 20;       // small copies: plain cudaMemcpyAsync
-constexpr int kCopyThreads = 4;
+constexpr int kCopyThreads = 8;
 
 bool host_pinned(const void* p) {
   cudaPointerAttributes a;
