@@ -290,6 +290,58 @@ struct BlockSparse : Block {        // block_sparse.cu (CSC in, CSR of K and of 
   }
 };
 
+// SURVEY.md 8(f) row 3, oracle side only so far: Kronecker products of a small matrix K (mr x mc, column-major) with
+// an identity of size d.  id_first = false: kron(K, I_d) (block_dense_kron_id.cu:28-64, block_sparse_kron_id.cu),
+// id_first = true: kron(I_d, K) (block_id_kron_dense.cu:28-64, block_id_kron_sparse.cu).  The sparse variants are
+// the same operators with K given in CSC; the oracle stores K densely (zeros add exactly 0 to the float sums).
+struct BlockKron : Block {
+  vec k;
+  size_t mr, mc, d;
+  bool id_first;
+  BlockKron(size_t r, size_t c, size_t mr_, size_t mc_, size_t d_, bool idf, const float* data)
+      : Block(r, c, mr_ * d_, mc_ * d_), k(data, data + mr_ * mc_), mr(mr_), mc(mc_), d(d_), id_first(idf) {}
+  void eval_add(float* res, const float* rhs) const override {
+#pragma omp parallel for schedule(static)
+    for (size_t tx = 0; tx < d * mr; ++tx) {
+      float sum = 0;
+      if (!id_first) {
+        const size_t row = tx / d, ofs = tx % d;
+        for (size_t i = 0; i < mc; ++i) sum += k[i * mr + row] * rhs[i * d + ofs];
+      } else {
+        const size_t row = tx % mr, ofs = (tx / mr) * mc;
+        for (size_t i = 0; i < mc; ++i) sum += k[i * mr + row] * rhs[ofs + i];
+      }
+      res[tx] += sum;
+    }
+  }
+  void eval_adj_add(float* res, const float* rhs) const override {
+#pragma omp parallel for schedule(static)
+    for (size_t tx = 0; tx < d * mc; ++tx) {
+      float sum = 0;
+      if (!id_first) {
+        const size_t colm = tx / d, ofs = tx % d;
+        for (size_t i = 0; i < mr; ++i) sum += k[i + colm * mr] * rhs[i * d + ofs];
+      } else {
+        const size_t colm = tx % mc, ofs = (tx / mc) * mr;
+        for (size_t i = 0; i < mr; ++i) sum += k[i + colm * mr] * rhs[ofs + i];
+      }
+      res[tx] += sum;
+    }
+  }
+  float row_sum(size_t r, float alpha) const override {                 // block_dense_kron_id.cu:100-109, id_kron_*: row % mr
+    const size_t row = id_first ? r % mr : r / d;
+    float s = 0;
+    for (size_t i = 0; i < mc; ++i) s += std::pow(std::abs(k[i * mr + row]), alpha);
+    return s;
+  }
+  float col_sum(size_t c, float alpha) const override {
+    const size_t colm = id_first ? c % mc : c / d;
+    float s = 0;
+    for (size_t i = 0; i < mr; ++i) s += std::pow(std::abs(k[i + colm * mr]), alpha);
+    return s;
+  }
+};
+
 struct BlockDense : Block {         // block_dense.cu (column-major, gemv N / T)
   vec a;
   BlockDense(size_t r, size_t c, size_t nr, size_t nc, const float* d) : Block(r, c, nr, nc), a(d, d + nr * nc) {}
@@ -1015,6 +1067,9 @@ void orc_add_sparse_csc(void* p, size_t row, size_t col, int m, int n, int nnz, 
 }
 void orc_add_dense(void* p, size_t row, size_t col, size_t nr, size_t nc, const float* d) {
   PP->blocks.push_back(std::make_shared<BlockDense>(row, col, nr, nc, d));
+}
+void orc_add_kron(void* p, size_t row, size_t col, size_t mr, size_t mc, size_t d, int id_first, const float* data) {
+  PP->blocks.push_back(std::make_shared<BlockKron>(row, col, mr, mc, d, id_first != 0, data));
 }
 void orc_add_zero(void* p, size_t row, size_t col, size_t nr, size_t nc) {
   PP->blocks.push_back(std::make_shared<BlockZero>(row, col, nr, nc));

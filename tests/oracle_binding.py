@@ -36,6 +36,7 @@ lib.orc_add_diags.argtypes = [C.c_void_p, sz, sz, sz, sz, sz, C.POINTER(C.c_int6
 lib.orc_add_sparse_csc.argtypes = [C.c_void_p, sz, sz, C.c_int, C.c_int, C.c_int, fp,
                                    C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
 lib.orc_add_dense.argtypes = [C.c_void_p, sz, sz, sz, sz, fp]
+lib.orc_add_kron.argtypes = [C.c_void_p, sz, sz, sz, sz, sz, C.c_int, fp]
 lib.orc_add_zero.argtypes = [C.c_void_p, sz, sz, sz, sz]
 lib.orc_prox_elem.argtypes = [C.c_void_p, C.c_int, sz, sz, sz, C.c_int, C.c_int, C.c_int, C.POINTER(fp),
                               C.POINTER(sz)]
@@ -145,6 +146,12 @@ class OracleProblem:
             A = np.asarray(data[0], dtype=np.float32)
             d = np.ascontiguousarray(A.T).ravel()
             lib.orc_add_dense(self.h, row, col, A.shape[0], A.shape[1], _p(d))
+        elif name in ("dense_kron_id", "id_kron_dense", "sparse_kron_id", "id_kron_sparse"):
+            # oracle only so far: data = [K, diaglength]
+            K = data[0].toarray() if hasattr(data[0], "toarray") else np.asarray(data[0])
+            K = np.asarray(K, dtype=np.float32)
+            d = np.ascontiguousarray(K.T).ravel()
+            lib.orc_add_kron(self.h, row, col, K.shape[0], K.shape[1], int(data[1]), int(name.startswith("id_")), _p(d))
         elif name == "zero":
             lib.orc_add_zero(self.h, row, col, data[0], data[1])
         else:

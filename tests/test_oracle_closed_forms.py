@@ -245,3 +245,27 @@ def test_prox_ind_halfspace_and_soc_are_projections():
     D = (W - X).astype(np.float64)                                   # residual lies in the polar cone, orthogonal to X
     assert (np.linalg.norm(D[:, :-1], axis=1) <= -D[:, -1] + 1e-5).all()
     assert np.abs((D * X).sum(1)).max() < 1e-5
+
+
+def test_kronecker_blocks_match_numpy_kron():
+    """test_linop_dense_kron_id.m / test_linop_id_kron_dense.m / test_linop_sparse_kron_id.m /
+    test_linop_id_kron_sparse.m restated: four copies of the block in a 2 x 2 arrangement against
+    kron(K, I) resp. kron(I, K), forward and adjoint (the reference tests use 1e-3 on float), plus the row and
+    column sums that feed the preconditioners."""
+    import scipy.sparse as sp
+    r = np.random.default_rng(9)
+    d, mr, mc = 122, 13, 14
+    Kd = r.standard_normal((mr, mc)).astype(np.float32)
+    Ks = sp.random(mr, mc, density=0.3, random_state=3, format="csc", dtype=np.float32)
+    for name, K in (("dense_kron_id", Kd), ("id_kron_dense", Kd), ("sparse_kron_id", Ks), ("id_kron_sparse", Ks)):
+        Kf = (K.toarray() if hasattr(K, "toarray") else K).astype(np.float64)
+        full = np.kron(np.eye(d), Kf) if name.startswith("id_") else np.kron(Kf, np.eye(d))
+        M = np.block([[full, full], [full, full]])
+        blocks = [(name, rr * mr * d, cc * mc * d, [K, d]) for rr in (0, 1) for cc in (0, 1)]
+        P = OracleProblem(blocks=blocks)
+        x = r.standard_normal(2 * mc * d).astype(np.float32)
+        y = r.standard_normal(2 * mr * d).astype(np.float32)
+        assert np.abs(P.linop(x, False) - M @ x).max() < 1e-3, name
+        assert np.abs(P.linop(y, True) - M.T @ y).max() < 1e-3, name
+        assert np.allclose(P.row_sums(1.0), np.abs(M).sum(1), rtol=1e-5, atol=1e-6), name
+        assert np.allclose(P.col_sums(1.0), np.abs(M).sum(0), rtol=1e-5, atol=1e-6), name
