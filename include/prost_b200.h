@@ -99,6 +99,14 @@ int pb_block_create_sparse_csc(pb_context* ctx, size_t row, size_t col, int m, i
 /* BlockDense::CreateFromColFirstData(row,col,nrows,ncols,data): include/prost/linop/block_dense.hpp:42-43 */
 int pb_block_create_dense(pb_context* ctx, size_t row, size_t col, size_t nrows, size_t ncols,
                           const float* h_data_colmajor, pb_block** out);
+/* BlockDenseKronId::CreateFromColFirstData(diaglength,row,col,nrows,ncols,data): kron(K, I_diaglength), K is
+ * nrows x ncols column-major, the block is (nrows*diaglength) x (ncols*diaglength)
+ * (include/prost/linop/block_dense_kron_id.hpp:40-46, src/linop/block_dense_kron_id.cu) */
+int pb_block_create_dense_kron_id(pb_context* ctx, size_t diaglength, size_t row, size_t col, size_t nrows,
+                                  size_t ncols, const float* h_data_colmajor, pb_block** out);
+/* BlockIdKronDense::CreateFromColFirstData(...): kron(I_diaglength, K) (block_id_kron_dense.hpp:42-48) */
+int pb_block_create_id_kron_dense(pb_context* ctx, size_t diaglength, size_t row, size_t col, size_t nrows,
+                                  size_t ncols, const float* h_data_colmajor, pb_block** out);
 /* BlockZero(row,col,nrows,ncols): include/prost/linop/block_zero.hpp */
 int pb_block_create_zero(pb_context* ctx, size_t row, size_t col, size_t nrows, size_t ncols,
                          pb_block** out);

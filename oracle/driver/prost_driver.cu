@@ -17,6 +17,7 @@
 //   block diags <row> <col> <nrows> <ncols> <ndiags> <offsets.i64> <factors.f32>
 //   block sparse <row> <col> <m> <n> <nnz> <val.f32> <ptr.i32> <ind.i32>        (CSC)
 //   block dense <row> <col> <nrows> <ncols> <data.f32>                           (column-major)
+//   block dense_kron_id|id_kron_dense <row> <col> <mat_nrows> <mat_ncols> <diaglength> <data.f32 column-major>
 //   block zero <row> <col> <nrows> <ncols>
 //   prox g|f|gstar|fstar|eval <PROX>
 //     PROX := elem1d|norm2 <fun> <idx> <count> <dim> <interleaved> <diagsteps> <c0> .. <c6>
@@ -52,6 +53,8 @@
 #include "prost/backend/backend_pdhg.hpp"
 #include "prost/exception.hpp"
 #include "prost/linop/block_dense.hpp"
+#include "prost/linop/block_dense_kron_id.hpp"
+#include "prost/linop/block_id_kron_dense.hpp"
 #include "prost/linop/block_diags.hpp"
 #include "prost/linop/block_gradient2d.hpp"
 #include "prost/linop/block_gradient3d.hpp"
@@ -238,6 +241,17 @@ static std::shared_ptr<Block<real>> parse_block(std::istringstream& in) {
     in >> nrows >> ncols >> fd;
     return std::shared_ptr<Block<real>>(
         BlockDense<real>::CreateFromColFirstData(row, col, nrows, ncols, read_real(fd, nrows * ncols)));
+  }
+  if (kind == "dense_kron_id" || kind == "id_kron_dense") {
+    size_t nrows, ncols, diaglength;
+    std::string fd;
+    in >> nrows >> ncols >> diaglength >> fd;
+    const std::vector<real> data = read_real(fd, nrows * ncols);
+    if (kind == "dense_kron_id")
+      return std::shared_ptr<Block<real>>(
+          BlockDenseKronId<real>::CreateFromColFirstData(diaglength, row, col, nrows, ncols, data));
+    return std::shared_ptr<Block<real>>(
+        BlockIdKronDense<real>::CreateFromColFirstData(diaglength, row, col, nrows, ncols, data));
   }
   if (kind == "zero") {
     size_t nrows, ncols;

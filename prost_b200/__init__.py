@@ -4,7 +4,8 @@ The package is a thin ctypes mirror of the C ABI in include/prost_b200.h; the ho
 PDHG passes, operator applies, separable proxes, residual reductions) is hand-written CUDA for
 sm_100a in prost_b200/csrc.  There is no CPU fallback.
 """
-from .api import (ADMMOptions, Backend, Comm, BackendADMM, BackendPDHG, Block, BlockDense, BlockDiags,
+from .api import (ADMMOptions, Backend, Comm, BackendADMM, BackendPDHG, Block, BlockDense, BlockDenseKronId,
+                  BlockIdKronDense, BlockDiags,
                   BlockGradient2D, BlockGradient3D, BlockSparse, BlockZero, Context, LinearOperator,
                   PDHGOptions, Problem, ProstError, Prox, ProxElemOperation1D, ProxElemOperationIndSimplex,
                   ProxElemOperationIndSum,

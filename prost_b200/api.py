@@ -173,6 +173,28 @@ class BlockDense(Block):
         check(lib.pb_block_create_dense(ctx._h, row, col, A.shape[0], A.shape[1], _fp(data), C.byref(self._h)))
 
 
+class BlockDenseKronId(Block):
+    """BlockDenseKronId::CreateFromColFirstData: kron(K, I_diaglength); ``K`` is a small 2-D array."""
+
+    def __init__(self, ctx, row, col, K, diaglength):
+        super().__init__(ctx)
+        K = np.asarray(K, dtype=np.float32)
+        data = np.ascontiguousarray(K.T).ravel()          # column-major
+        check(lib.pb_block_create_dense_kron_id(ctx._h, int(diaglength), row, col, K.shape[0], K.shape[1], _fp(data),
+                                                C.byref(self._h)))
+
+
+class BlockIdKronDense(Block):
+    """BlockIdKronDense::CreateFromColFirstData: kron(I_diaglength, K)."""
+
+    def __init__(self, ctx, row, col, K, diaglength):
+        super().__init__(ctx)
+        K = np.asarray(K, dtype=np.float32)
+        data = np.ascontiguousarray(K.T).ravel()
+        check(lib.pb_block_create_id_kron_dense(ctx._h, int(diaglength), row, col, K.shape[0], K.shape[1], _fp(data),
+                                                C.byref(self._h)))
+
+
 class BlockZero(Block):
     def __init__(self, ctx, row, col, nrows, ncols):
         super().__init__(ctx)

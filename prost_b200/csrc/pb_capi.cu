@@ -176,6 +176,14 @@ int pb_block_create_dense(pb_context* c, size_t row, size_t col, size_t nrows, s
                           const float* data, pb_block** out) {
   PB_MAKE_BLOCK(pb::make_block_dense(&c->ctx, row, col, nrows, ncols, data));
 }
+int pb_block_create_dense_kron_id(pb_context* c, size_t diaglength, size_t row, size_t col, size_t nrows,
+                                  size_t ncols, const float* data, pb_block** out) {
+  PB_MAKE_BLOCK(pb::make_block_dense_kron(&c->ctx, false, diaglength, row, col, nrows, ncols, data));
+}
+int pb_block_create_id_kron_dense(pb_context* c, size_t diaglength, size_t row, size_t col, size_t nrows,
+                                  size_t ncols, const float* data, pb_block** out) {
+  PB_MAKE_BLOCK(pb::make_block_dense_kron(&c->ctx, true, diaglength, row, col, nrows, ncols, data));
+}
 int pb_block_create_zero(pb_context* c, size_t row, size_t col, size_t nrows, size_t ncols,
                          pb_block** out) {
   PB_MAKE_BLOCK(pb::make_block_zero(&c->ctx, row, col, nrows, ncols));

@@ -441,6 +441,108 @@ class BlockDense : public Block {
   uint32_t splits_ = 1, cols_per_split_ = 0;
 };
 
+// ---- Kronecker products with an identity (block_dense_kron_id.cu, block_id_kron_dense.cu) --------------
+// K is a small n_out x n_in matrix read through strides (so, si) so that one kernel serves K and K^T.
+//
+// kron(K, I_d):  res[o*d + k] += sum_i K(o, i) rhs[i*d + k].  This is the GEMM  Res (n_out x d) += K X (n_in x d)
+// with d in the millions and n_in, n_out in the tens: every thread owns one column k (coalesced across threads)
+// and kRowTile output rows in registers, K is read as warp-wide broadcasts, X once per row tile.  Same
+// summation order as the reference (i ascending, sum first, then += into the result).
+constexpr int kKronRowTile = 8;
+
+__global__ void __launch_bounds__(kBlock) kron_k_id_kernel(float* __restrict__ res, const float* __restrict__ rhs,
+                                                           const float* __restrict__ K, uint32_t n_out, uint32_t n_in,
+                                                           size_t d, uint32_t so, uint32_t si,
+                                                           const int* __restrict__ skip) {
+  if (skip && *skip) return;
+  const size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const uint32_t o0 = blockIdx.y * kKronRowTile;
+  if (k >= d) return;
+  float acc[kKronRowTile];
+#pragma unroll
+  for (int r = 0; r < kKronRowTile; ++r) acc[r] = 0.f;
+  for (uint32_t i = 0; i < n_in; ++i) {
+    const float x = rhs[(size_t)i * d + k];
+#pragma unroll
+    for (int r = 0; r < kKronRowTile; ++r)
+      if (o0 + r < n_out) acc[r] += __ldg(K + (size_t)(o0 + r) * so + (size_t)i * si) * x;
+  }
+#pragma unroll
+  for (int r = 0; r < kKronRowTile; ++r)
+    if (o0 + r < n_out) res[(size_t)(o0 + r) * d + k] += acc[r];
+}
+
+// kron(I_d, K):  res[b*n_out + o] += sum_i K(o, i) rhs[b*n_in + i]  -- d independent small products
+__global__ void __launch_bounds__(kBlock) kron_id_k_kernel(float* __restrict__ res, const float* __restrict__ rhs,
+                                                           const float* __restrict__ K, uint32_t n_out, uint32_t n_in,
+                                                           size_t d, uint32_t so, uint32_t si,
+                                                           const int* __restrict__ skip) {
+  if (skip && *skip) return;
+  const size_t total = d * n_out;
+  for (size_t tx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; tx < total; tx += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = tx / n_out;
+    const uint32_t o = (uint32_t)(tx - b * n_out);
+    const float* x = rhs + b * n_in;
+    float sum = 0.f;
+    for (uint32_t i = 0; i < n_in; ++i) sum += __ldg(K + (size_t)o * so + (size_t)i * si) * x[i];
+    res[tx] += sum;
+  }
+}
+
+class BlockDenseKron : public Block {
+ public:
+  BlockDenseKron(Context* ctx, bool id_first, size_t diaglength, size_t row, size_t col, size_t mr, size_t mc,
+                 const float* data)
+      : Block(ctx, row, col, mr * diaglength, mc * diaglength), id_first_(id_first), d_(diaglength), mr_(mr), mc_(mc),
+        host_(data, data + mr * mc) {
+    checked_u32(mr, "Kronecker factor rows");
+    checked_u32(mc, "Kronecker factor columns");
+    if (diaglength == 0) fail(PB_ERR_INVALID, "Kronecker block: diaglength must be positive");
+    d_data_.assign(host_, ctx->stream);
+  }
+  int kind() const override { return id_first_ ? kBlockIdKronDense : kBlockDenseKronId; }
+  // block_dense_kron_id.cu:100-121 (row / diaglength), block_id_kron_dense.cu (row % mat_nrows)
+  float row_sum(size_t row, float alpha) const override {
+    const size_t r = id_first_ ? row % mr_ : row / d_;
+    float sum = 0;
+    for (size_t i = 0; i < mc_; ++i) sum += std::pow(std::abs(host_[i * mr_ + r]), alpha);
+    return sum;
+  }
+  float col_sum(size_t col, float alpha) const override {
+    const size_t c = id_first_ ? col % mc_ : col / d_;
+    float sum = 0;
+    for (size_t i = 0; i < mr_; ++i) sum += std::pow(std::abs(host_[i + c * mr_]), alpha);
+    return sum;
+  }
+  size_t gpu_mem_amount() const override { return host_.size() * sizeof(float); }
+  void eval_local_add(float* res, const float* rhs) override { apply(res, rhs, false); }
+  void eval_adjoint_local_add(float* res, const float* rhs) override { apply(res, rhs, true); }
+
+ private:
+  void apply(float* res, const float* rhs, bool transpose) {
+    if (mr_ == 0 || mc_ == 0) return;
+    // K(o, i): column-major K[i*mr + o]; transposed K^T(o, i) = K[o*mr + i]
+    const uint32_t n_out = (uint32_t)(transpose ? mc_ : mr_), n_in = (uint32_t)(transpose ? mr_ : mc_);
+    const uint32_t so = transpose ? (uint32_t)mr_ : 1u, si = transpose ? 1u : (uint32_t)mr_;
+    if (!id_first_) {
+      const dim3 grid(grid_for(d_), (n_out + kKronRowTile - 1) / kKronRowTile);
+      if (grid.y > 65535u) fail(PB_ERR_UNSUPPORTED, "Kronecker block: factor too large for this kernel");
+      kron_k_id_kernel<<<grid, kBlock, 0, ctx_->stream>>>(res, rhs, d_data_.data(), n_out, n_in, d_, so, si,
+                                                          ctx_->skip_flag);
+    } else {
+      const unsigned grid = (unsigned)std::min<size_t>(grid_for(d_ * n_out), (size_t)ctx_->num_sms * 32);
+      kron_id_k_kernel<<<grid, kBlock, 0, ctx_->stream>>>(res, rhs, d_data_.data(), n_out, n_in, d_, so, si,
+                                                          ctx_->skip_flag);
+    }
+    PB_CHECK_LAUNCH();
+    ctx_->launches++;
+  }
+  bool id_first_;
+  size_t d_, mr_, mc_;
+  std::vector<float> host_;
+  DeviceBuffer<float> d_data_;
+};
+
 // ---- zero -----------------------------------------------------------------------------------------
 
 class BlockZero : public Block {
@@ -473,6 +575,10 @@ std::shared_ptr<Block> make_block_sparse_csc(Context* ctx, size_t row, size_t co
 std::shared_ptr<Block> make_block_dense(Context* ctx, size_t row, size_t col, size_t nrows,
                                         size_t ncols, const float* data) {
   return std::make_shared<BlockDense>(ctx, row, col, nrows, ncols, data);
+}
+std::shared_ptr<Block> make_block_dense_kron(Context* ctx, bool id_first, size_t diaglength, size_t row, size_t col,
+                                             size_t mat_nrows, size_t mat_ncols, const float* data) {
+  return std::make_shared<BlockDenseKron>(ctx, id_first, diaglength, row, col, mat_nrows, mat_ncols, data);
 }
 std::shared_ptr<Block> make_block_zero(Context* ctx, size_t row, size_t col, size_t nrows,
                                        size_t ncols) {

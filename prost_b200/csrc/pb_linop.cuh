@@ -23,6 +23,8 @@ enum BlockKind : int {
   kBlockDiags = 3,
   kBlockSparse = 4,
   kBlockDense = 5,
+  kBlockDenseKronId = 6,
+  kBlockIdKronDense = 7,
 };
 
 // POD view of one block, passed by value to kernels.
@@ -195,6 +197,9 @@ std::shared_ptr<Block> make_block_sparse_csc(Context* ctx, size_t row, size_t co
                                              const int32_t* ind);
 std::shared_ptr<Block> make_block_dense(Context* ctx, size_t row, size_t col, size_t nrows,
                                         size_t ncols, const float* data);
+// kron(K, I_d) (BlockDenseKronId) and kron(I_d, K) (BlockIdKronDense); K is mat_nrows x mat_ncols, column-major
+std::shared_ptr<Block> make_block_dense_kron(Context* ctx, bool id_first, size_t diaglength, size_t row, size_t col,
+                                             size_t mat_nrows, size_t mat_ncols, const float* data);
 std::shared_ptr<Block> make_block_zero(Context* ctx, size_t row, size_t col, size_t nrows,
                                        size_t ncols);
 

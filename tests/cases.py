@@ -230,3 +230,16 @@ def all_prox_cases(small=False):
     out.update(prox_ind_sum_cases(small))
     out.update(prox_projection_cases(small))
     return out
+
+
+def linop_kron_cases(small=False):
+    """test_linop_dense_kron_id.m / test_linop_id_kron_dense.m: K 13 x 14, diaglength 122, four copies in a 2 x 2
+    arrangement; plus a tall factor (more rows than one register tile) and a single block."""
+    r = rng(41)
+    cases = {}
+    d, mr, mc = (122, 13, 14) if not small else (7, 3, 4)
+    K = r.standard_normal((mr, mc)).astype(np.float32)
+    for name in ("dense_kron_id", "id_kron_dense"):
+        cases[f"{name}_2x2"] = [(name, rr * mr * d, cc * mc * d, [K, d]) for rr in (0, 1) for cc in (0, 1)]
+        cases[f"{name}_tall"] = [(name, 0, 0, [r.standard_normal((21, 5)).astype(np.float32), 1031 if not small else 9])]
+    return cases

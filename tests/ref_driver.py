@@ -62,6 +62,10 @@ class _Writer:
             A = np.asarray(data[0], dtype=np.float32)
             fd, _ = self.arr(np.ascontiguousarray(A.T), np.float32)
             return f"block dense {row} {col} {A.shape[0]} {A.shape[1]} {fd}"
+        if name in ("dense_kron_id", "id_kron_dense"):
+            K = np.asarray(data[0], dtype=np.float32)
+            fd, _ = self.arr(np.ascontiguousarray(K.T), np.float32)
+            return f"block {name} {row} {col} {K.shape[0]} {K.shape[1]} {int(data[1])} {fd}"
         if name == "zero":
             return f"block zero {row} {col} {data[0]} {data[1]}"
         raise ValueError(name)

@@ -122,3 +122,35 @@ def test_projection_prox_errors(ctx):
     with pytest.raises(pb.ProstError) as e:
         pb.ProxIndHalfspace(ctx, 0, 10, 3, False, False, np.ones(7, np.float32), np.ones(1, np.float32))
     assert "Coefficient a has to have dimension count*dim or dim" in str(e.value)
+
+
+# ---- Kronecker blocks dense_kron_id / id_kron_dense ------------------------------------------
+KRON_CASES = cases.linop_kron_cases()
+
+
+@pytest.mark.parametrize("name", sorted(KRON_CASES))
+def test_kron_blocks_forward_adjoint(ctx, name):
+    from oracle_binding import OracleProblem
+    blocks = KRON_CASES[name]
+    op = pb.create_linop(ctx, blocks)
+    m, n = op.nrows, op.ncols
+    r = np.random.default_rng(zlib.crc32(name.encode()))
+    x, y = r.standard_normal(n).astype(np.float32), r.standard_normal(m).astype(np.float32)
+    orc = OracleProblem(blocks=blocks)
+    fwd, adj = op.Eval(x), op.EvalAdjoint(y)
+    assert np.abs(fwd - orc.linop(x, False)).max() <= 1e-5 * max(1.0, float(np.abs(fwd).max())), name
+    assert np.abs(adj - orc.linop(y, True)).max() <= 1e-5 * max(1.0, float(np.abs(adj).max())), name
+    # the reference tests compare with kron() at 1e-3
+    M = np.zeros((m, n))
+    for (bname, row, col, (K, d)) in blocks:
+        full = np.kron(np.eye(d), K) if bname.startswith("id_") else np.kron(K, np.eye(d))
+        M[row:row + full.shape[0], col:col + full.shape[1]] += full
+    assert np.abs(fwd - M @ x).max() < 1e-3 and np.abs(adj - M.T @ y).max() < 1e-3, name
+    assert abs(float(y @ fwd) - float(adj @ x)) <= 1e-3 * max(1.0, abs(float(y @ fwd))), name      # <Kx, y> = <x, K^T y>
+    assert np.allclose(op.row_sums(1.0), np.abs(M).sum(1), rtol=1e-5, atol=1e-6)
+    assert np.allclose(op.col_sums(1.0), np.abs(M).sum(0), rtol=1e-5, atol=1e-6)
+    if ref_driver.available():
+        ref_f = ref_driver.run_linop(blocks, x, False)["res"]
+        ref_a = ref_driver.run_linop(blocks, y, True)["res"]
+        assert np.abs(fwd - ref_f).max() <= 1e-5 * max(1.0, float(np.abs(ref_f).max())), name
+        assert np.abs(adj - ref_a).max() <= 1e-5 * max(1.0, float(np.abs(ref_a).max())), name
