@@ -241,5 +241,5 @@ def linop_kron_cases(small=False):
     K = r.standard_normal((mr, mc)).astype(np.float32)
     for name in ("dense_kron_id", "id_kron_dense"):
         cases[f"{name}_2x2"] = [(name, rr * mr * d, cc * mc * d, [K, d]) for rr in (0, 1) for cc in (0, 1)]
-        cases[f"{name}_tall"] = [(name, 0, 0, [r.standard_normal((21, 5)).astype(np.float32), 1031 if not small else 9])]
+        cases[f"{name}_tall"] = [(name, 0, 0, [r.standard_normal((21, 5)).astype(np.float32), 257 if not small else 9])]
     return cases
