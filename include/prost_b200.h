@@ -107,6 +107,13 @@ int pb_block_create_dense_kron_id(pb_context* ctx, size_t diaglength, size_t row
 /* BlockIdKronDense::CreateFromColFirstData(...): kron(I_diaglength, K) (block_id_kron_dense.hpp:42-48) */
 int pb_block_create_id_kron_dense(pb_context* ctx, size_t diaglength, size_t row, size_t col, size_t nrows,
                                   size_t ncols, const float* h_data_colmajor, pb_block** out);
+/* BlockSparseKronId::CreateFromCSC(row,col,diaglength,m,n,nnz,val,ptr,ind): kron(K, I_diaglength) for a sparse m x n
+ * factor in CSC with int32 indices (block_sparse_kron_id.hpp:39-48, src/linop/block_sparse_kron_id.cu) */
+int pb_block_create_sparse_kron_id(pb_context* ctx, size_t row, size_t col, size_t diaglength, int m, int n, int nnz,
+                                   const float* h_val, const int32_t* h_ptr, const int32_t* h_ind, pb_block** out);
+/* BlockIdKronSparse::CreateFromCSC(...): kron(I_diaglength, K) (block_id_kron_sparse.hpp:39-48) */
+int pb_block_create_id_kron_sparse(pb_context* ctx, size_t row, size_t col, size_t diaglength, int m, int n, int nnz,
+                                   const float* h_val, const int32_t* h_ptr, const int32_t* h_ind, pb_block** out);
 /* BlockZero(row,col,nrows,ncols): include/prost/linop/block_zero.hpp */
 int pb_block_create_zero(pb_context* ctx, size_t row, size_t col, size_t nrows, size_t ncols,
                          pb_block** out);

@@ -18,6 +18,7 @@
 //   block sparse <row> <col> <m> <n> <nnz> <val.f32> <ptr.i32> <ind.i32>        (CSC)
 //   block dense <row> <col> <nrows> <ncols> <data.f32>                           (column-major)
 //   block dense_kron_id|id_kron_dense <row> <col> <mat_nrows> <mat_ncols> <diaglength> <data.f32 column-major>
+//   block sparse_kron_id|id_kron_sparse <row> <col> <diaglength> <m> <n> <nnz> <val.f32> <ptr.i32> <ind.i32>   (CSC)
 //   block zero <row> <col> <nrows> <ncols>
 //   prox g|f|gstar|fstar|eval <PROX>
 //     PROX := elem1d|norm2 <fun> <idx> <count> <dim> <interleaved> <diagsteps> <c0> .. <c6>
@@ -55,6 +56,8 @@
 #include "prost/linop/block_dense.hpp"
 #include "prost/linop/block_dense_kron_id.hpp"
 #include "prost/linop/block_id_kron_dense.hpp"
+#include "prost/linop/block_id_kron_sparse.hpp"
+#include "prost/linop/block_sparse_kron_id.hpp"
 #include "prost/linop/block_diags.hpp"
 #include "prost/linop/block_gradient2d.hpp"
 #include "prost/linop/block_gradient3d.hpp"
@@ -241,6 +244,17 @@ static std::shared_ptr<Block<real>> parse_block(std::istringstream& in) {
     in >> nrows >> ncols >> fd;
     return std::shared_ptr<Block<real>>(
         BlockDense<real>::CreateFromColFirstData(row, col, nrows, ncols, read_real(fd, nrows * ncols)));
+  }
+  if (kind == "sparse_kron_id" || kind == "id_kron_sparse") {
+    size_t diaglength;
+    int m, n, nnz;
+    std::string fv, fp, fi;
+    in >> diaglength >> m >> n >> nnz >> fv >> fp >> fi;
+    const std::vector<real> val = read_real(fv, nnz);
+    const std::vector<int32_t> ptr = read_file<int32_t>(fp, n + 1), ind = read_file<int32_t>(fi, nnz);
+    if (kind == "sparse_kron_id")
+      return std::shared_ptr<Block<real>>(BlockSparseKronId<real>::CreateFromCSC(row, col, diaglength, m, n, nnz, val, ptr, ind));
+    return std::shared_ptr<Block<real>>(BlockIdKronSparse<real>::CreateFromCSC(row, col, diaglength, m, n, nnz, val, ptr, ind));
   }
   if (kind == "dense_kron_id" || kind == "id_kron_dense") {
     size_t nrows, ncols, diaglength;

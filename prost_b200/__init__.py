@@ -5,7 +5,7 @@ PDHG passes, operator applies, separable proxes, residual reductions) is hand-wr
 sm_100a in prost_b200/csrc.  There is no CPU fallback.
 """
 from .api import (ADMMOptions, Backend, Comm, BackendADMM, BackendPDHG, Block, BlockDense, BlockDenseKronId,
-                  BlockIdKronDense, BlockDiags,
+                  BlockIdKronDense, BlockIdKronSparse, BlockSparseKronId, BlockDiags,
                   BlockGradient2D, BlockGradient3D, BlockSparse, BlockZero, Context, LinearOperator,
                   PDHGOptions, Problem, ProstError, Prox, ProxElemOperation1D, ProxElemOperationIndSimplex,
                   ProxElemOperationIndSum,

@@ -87,6 +87,10 @@ SIGNATURES = {
     "pb_block_create_sparse_csc": (C.c_int, [handle, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int,
                                              c_float_p, c_i32_p, c_i32_p, handle_p]),
     "pb_block_create_dense": (C.c_int, [handle] + [C.c_size_t] * 4 + [c_float_p, handle_p]),
+    "pb_block_create_sparse_kron_id": (C.c_int, [handle, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                                 c_float_p, c_i32_p, c_i32_p, handle_p]),
+    "pb_block_create_id_kron_sparse": (C.c_int, [handle, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                                 c_float_p, c_i32_p, c_i32_p, handle_p]),
     "pb_block_create_dense_kron_id": (C.c_int, [handle] + [C.c_size_t] * 5 + [c_float_p, handle_p]),
     "pb_block_create_id_kron_dense": (C.c_int, [handle] + [C.c_size_t] * 5 + [c_float_p, handle_p]),
     "pb_block_create_zero": (C.c_int, [handle] + [C.c_size_t] * 4 + [handle_p]),

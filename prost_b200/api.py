@@ -195,6 +195,32 @@ class BlockIdKronDense(Block):
                                                 C.byref(self._h)))
 
 
+class _BlockSparseKron(Block):
+    _create = None
+
+    def __init__(self, ctx, row, col, K, diaglength):
+        import scipy.sparse as sp
+        super().__init__(ctx)
+        K = sp.csc_matrix(K)
+        K.sort_indices()
+        val = _f32(K.data)
+        ptr = np.ascontiguousarray(K.indptr.astype(np.int32))
+        ind = np.ascontiguousarray(K.indices.astype(np.int32))
+        check(getattr(lib, self._create)(ctx._h, row, col, int(diaglength), K.shape[0], K.shape[1], K.nnz, _fp(val),
+                                         ptr.ctypes.data_as(_capi.c_i32_p), ind.ctypes.data_as(_capi.c_i32_p),
+                                         C.byref(self._h)))
+
+
+class BlockSparseKronId(_BlockSparseKron):
+    """BlockSparseKronId::CreateFromCSC: kron(K, I_diaglength) for a sparse factor."""
+    _create = "pb_block_create_sparse_kron_id"
+
+
+class BlockIdKronSparse(_BlockSparseKron):
+    """BlockIdKronSparse::CreateFromCSC: kron(I_diaglength, K) for a sparse factor."""
+    _create = "pb_block_create_id_kron_sparse"
+
+
 class BlockZero(Block):
     def __init__(self, ctx, row, col, nrows, ncols):
         super().__init__(ctx)

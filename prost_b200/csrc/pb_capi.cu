@@ -184,6 +184,16 @@ int pb_block_create_id_kron_dense(pb_context* c, size_t diaglength, size_t row, 
                                   size_t ncols, const float* data, pb_block** out) {
   PB_MAKE_BLOCK(pb::make_block_dense_kron(&c->ctx, true, diaglength, row, col, nrows, ncols, data));
 }
+int pb_block_create_sparse_kron_id(pb_context* c, size_t row, size_t col, size_t diaglength, int m, int n, int nnz,
+                                   const float* val, const int32_t* ptr, const int32_t* ind, pb_block** out) {
+  PB_MAKE_BLOCK((require(val && ptr && ind, "NULL argument"),
+                 pb::make_block_sparse_kron(&c->ctx, false, diaglength, row, col, m, n, nnz, val, ptr, ind)));
+}
+int pb_block_create_id_kron_sparse(pb_context* c, size_t row, size_t col, size_t diaglength, int m, int n, int nnz,
+                                   const float* val, const int32_t* ptr, const int32_t* ind, pb_block** out) {
+  PB_MAKE_BLOCK((require(val && ptr && ind, "NULL argument"),
+                 pb::make_block_sparse_kron(&c->ctx, true, diaglength, row, col, m, n, nnz, val, ptr, ind)));
+}
 int pb_block_create_zero(pb_context* c, size_t row, size_t col, size_t nrows, size_t ncols,
                          pb_block** out) {
   PB_MAKE_BLOCK(pb::make_block_zero(&c->ctx, row, col, nrows, ncols));

@@ -543,6 +543,122 @@ class BlockDenseKron : public Block {
   DeviceBuffer<float> d_data_;
 };
 
+// ---- the same products for a sparse factor (block_sparse_kron_id.cu:28-52, block_id_kron_sparse.cu) -------
+// CSR of the factor (or of its transpose for the adjoint); entries of a row in ascending column order, so the sums
+// run in the reference's order.
+// kron(K, I_d):  res[o*d + k] += sum_{j in row o} val[j] rhs[ind[j]*d + k]     (k fastest: coalesced)
+__global__ void __launch_bounds__(kBlock) kron_sparse_id_kernel(float* __restrict__ res, const float* __restrict__ rhs,
+                                                                const int* __restrict__ ptr, const int* __restrict__ ind,
+                                                                const float* __restrict__ val, uint32_t n_out, size_t d,
+                                                                const int* __restrict__ skip) {
+  if (skip && *skip) return;
+  const size_t total = d * n_out;
+  for (size_t tx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; tx < total; tx += (size_t)gridDim.x * blockDim.x) {
+    const size_t o = tx / d, k = tx - o * d;
+    float sum = 0.f;
+    const int stop = ptr[o + 1];
+    for (int j = ptr[o]; j < stop; ++j) sum += val[j] * rhs[(size_t)ind[j] * d + k];
+    res[tx] += sum;
+  }
+}
+
+// kron(I_d, K):  res[b*n_out + o] += sum_{j in row o} val[j] rhs[b*n_in + ind[j]]
+__global__ void __launch_bounds__(kBlock) kron_id_sparse_kernel(float* __restrict__ res, const float* __restrict__ rhs,
+                                                                const int* __restrict__ ptr, const int* __restrict__ ind,
+                                                                const float* __restrict__ val, uint32_t n_out,
+                                                                uint32_t n_in, size_t d, const int* __restrict__ skip) {
+  if (skip && *skip) return;
+  const size_t total = d * n_out;
+  for (size_t tx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; tx < total; tx += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = tx / n_out, o = tx - b * n_out;
+    const float* x = rhs + b * n_in;
+    float sum = 0.f;
+    const int stop = ptr[o + 1];
+    for (int j = ptr[o]; j < stop; ++j) sum += val[j] * x[ind[j]];
+    res[tx] += sum;
+  }
+}
+
+class BlockSparseKron : public Block {
+ public:
+  BlockSparseKron(Context* ctx, bool id_first, size_t diaglength, size_t row, size_t col, int m, int n, int nnz,
+                  const float* val, const int32_t* ptr, const int32_t* ind)
+      : Block(ctx, row, col, (size_t)std::max(m, 0) * diaglength, (size_t)std::max(n, 0) * diaglength),
+        id_first_(id_first), d_(diaglength), m_(m), n_(n) {
+    if (m < 0 || n < 0 || nnz < 0) fail(PB_ERR_INVALID, "Kronecker block: negative size");
+    if (diaglength == 0) fail(PB_ERR_INVALID, "Kronecker block: diaglength must be positive");
+    if (ptr[0] != 0 || ptr[n] != nnz) fail(PB_ERR_INVALID, "Kronecker block: inconsistent CSC column pointer");
+    for (int k = 0; k < nnz; ++k)
+      if (ind[k] < 0 || ind[k] >= m) fail(PB_ERR_INVALID, "Kronecker block: row index out of range");
+    // CSC of K == CSR of K^T; CSR of K by a counting-sort transpose (ascending columns within a row, like the
+    // reference's host csr2csc, common.cu:54-82)
+    ptr_t_.assign(ptr, ptr + n + 1);
+    ind_t_.assign(ind, ind + nnz);
+    val_t_.assign(val, val + nnz);
+    ptr_.assign(m + 1, 0);
+    for (int k = 0; k < nnz; ++k) ptr_[ind[k] + 1]++;
+    for (int r = 0; r < m; ++r) ptr_[r + 1] += ptr_[r];
+    ind_.resize(nnz);
+    val_.resize(nnz);
+    std::vector<int> fill(ptr_.begin(), ptr_.end() - 1);
+    for (int c = 0; c < n; ++c)
+      for (int k = ptr[c]; k < ptr[c + 1]; ++k) {
+        const int dst = fill[ind[k]]++;
+        ind_[dst] = c;
+        val_[dst] = val[k];
+      }
+    d_ptr_.assign(ptr_, ctx->stream);
+    d_ind_.assign(ind_, ctx->stream);
+    d_val_.assign(val_, ctx->stream);
+    d_ptr_t_.assign(ptr_t_, ctx->stream);
+    d_ind_t_.assign(ind_t_, ctx->stream);
+    d_val_t_.assign(val_t_, ctx->stream);
+  }
+  int kind() const override { return id_first_ ? kBlockIdKronSparse : kBlockSparseKronId; }
+  // block_sparse_kron_id.cu (row / diaglength), block_id_kron_sparse.cu:127-150 (row % mat_nrows)
+  float row_sum(size_t row, float alpha) const override {
+    const size_t r = id_first_ ? row % (size_t)m_ : row / d_;
+    float sum = 0;
+    for (int k = ptr_[r]; k < ptr_[r + 1]; ++k) sum += std::pow(std::abs(val_[k]), alpha);
+    return sum;
+  }
+  float col_sum(size_t col, float alpha) const override {
+    const size_t c = id_first_ ? col % (size_t)n_ : col / d_;
+    float sum = 0;
+    for (int k = ptr_t_[c]; k < ptr_t_[c + 1]; ++k) sum += std::pow(std::abs(val_t_[k]), alpha);
+    return sum;
+  }
+  size_t gpu_mem_amount() const override {
+    return 2 * val_.size() * (sizeof(int32_t) + sizeof(float)) + (size_t)(m_ + n_ + 2) * sizeof(int32_t);
+  }
+  void eval_local_add(float* res, const float* rhs) override { apply(res, rhs, d_ptr_, d_ind_, d_val_, m_, n_); }
+  void eval_adjoint_local_add(float* res, const float* rhs) override {
+    apply(res, rhs, d_ptr_t_, d_ind_t_, d_val_t_, n_, m_);
+  }
+
+ private:
+  void apply(float* res, const float* rhs, const DeviceBuffer<int>& ptr, const DeviceBuffer<int>& ind,
+             const DeviceBuffer<float>& val, int n_out, int n_in) {
+    if (n_out == 0 || n_in == 0 || val.size() == 0) return;
+    const unsigned grid = (unsigned)std::min<size_t>(grid_for(d_ * (size_t)n_out), (size_t)ctx_->num_sms * 32);
+    if (!id_first_)
+      kron_sparse_id_kernel<<<grid, kBlock, 0, ctx_->stream>>>(res, rhs, ptr.data(), ind.data(), val.data(),
+                                                               (uint32_t)n_out, d_, ctx_->skip_flag);
+    else
+      kron_id_sparse_kernel<<<grid, kBlock, 0, ctx_->stream>>>(res, rhs, ptr.data(), ind.data(), val.data(),
+                                                               (uint32_t)n_out, (uint32_t)n_in, d_, ctx_->skip_flag);
+    PB_CHECK_LAUNCH();
+    ctx_->launches++;
+  }
+  bool id_first_;
+  size_t d_;
+  int m_, n_;
+  std::vector<int> ptr_, ind_, ptr_t_, ind_t_;
+  std::vector<float> val_, val_t_;
+  DeviceBuffer<int> d_ptr_, d_ind_, d_ptr_t_, d_ind_t_;
+  DeviceBuffer<float> d_val_, d_val_t_;
+};
+
 // ---- zero -----------------------------------------------------------------------------------------
 
 class BlockZero : public Block {
@@ -579,6 +695,11 @@ std::shared_ptr<Block> make_block_dense(Context* ctx, size_t row, size_t col, si
 std::shared_ptr<Block> make_block_dense_kron(Context* ctx, bool id_first, size_t diaglength, size_t row, size_t col,
                                              size_t mat_nrows, size_t mat_ncols, const float* data) {
   return std::make_shared<BlockDenseKron>(ctx, id_first, diaglength, row, col, mat_nrows, mat_ncols, data);
+}
+std::shared_ptr<Block> make_block_sparse_kron(Context* ctx, bool id_first, size_t diaglength, size_t row, size_t col,
+                                              int m, int n, int nnz, const float* val, const int32_t* ptr,
+                                              const int32_t* ind) {
+  return std::make_shared<BlockSparseKron>(ctx, id_first, diaglength, row, col, m, n, nnz, val, ptr, ind);
 }
 std::shared_ptr<Block> make_block_zero(Context* ctx, size_t row, size_t col, size_t nrows,
                                        size_t ncols) {

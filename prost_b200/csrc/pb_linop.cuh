@@ -25,6 +25,8 @@ enum BlockKind : int {
   kBlockDense = 5,
   kBlockDenseKronId = 6,
   kBlockIdKronDense = 7,
+  kBlockSparseKronId = 8,
+  kBlockIdKronSparse = 9,
 };
 
 // POD view of one block, passed by value to kernels.
@@ -200,6 +202,10 @@ std::shared_ptr<Block> make_block_dense(Context* ctx, size_t row, size_t col, si
 // kron(K, I_d) (BlockDenseKronId) and kron(I_d, K) (BlockIdKronDense); K is mat_nrows x mat_ncols, column-major
 std::shared_ptr<Block> make_block_dense_kron(Context* ctx, bool id_first, size_t diaglength, size_t row, size_t col,
                                              size_t mat_nrows, size_t mat_ncols, const float* data);
+// the same two products for a sparse factor given in CSC (BlockSparseKronId / BlockIdKronSparse::CreateFromCSC)
+std::shared_ptr<Block> make_block_sparse_kron(Context* ctx, bool id_first, size_t diaglength, size_t row, size_t col,
+                                              int m, int n, int nnz, const float* val, const int32_t* ptr,
+                                              const int32_t* ind);
 std::shared_ptr<Block> make_block_zero(Context* ctx, size_t row, size_t col, size_t nrows,
                                        size_t ncols);
 

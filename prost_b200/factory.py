@@ -16,7 +16,7 @@ reference's mex registry names and argument order (matlab/+prost/private/factory
   transform                                            : [a, b, c, d, e, child description]   (+function/transform.m)
   zero                                                 : []
   gradient2d / gradient3d : [nx, ny, L, label_first]     diags : [nrows, ncols, factors, offsets]
-  dense : [A]     sparse : [A]     zero : [nrows, ncols]     dense_kron_id / id_kron_dense : [K, diaglength]
+  dense : [A]     sparse : [A]     zero : [nrows, ncols]     dense_kron_id / id_kron_dense / sparse_kron_id / id_kron_sparse : [K, diaglength]
 """
 from . import api
 
@@ -71,6 +71,10 @@ def create_block(ctx, desc):
         return api.BlockDenseKronId(ctx, row, col, data[0], data[1])
     if name == "id_kron_dense":
         return api.BlockIdKronDense(ctx, row, col, data[0], data[1])
+    if name == "sparse_kron_id":
+        return api.BlockSparseKronId(ctx, row, col, data[0], data[1])
+    if name == "id_kron_sparse":
+        return api.BlockIdKronSparse(ctx, row, col, data[0], data[1])
     if name == "sparse":
         return api.BlockSparse(ctx, row, col, data[0])
     if name == "zero":

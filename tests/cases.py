@@ -242,4 +242,10 @@ def linop_kron_cases(small=False):
     for name in ("dense_kron_id", "id_kron_dense"):
         cases[f"{name}_2x2"] = [(name, rr * mr * d, cc * mc * d, [K, d]) for rr in (0, 1) for cc in (0, 1)]
         cases[f"{name}_tall"] = [(name, 0, 0, [r.standard_normal((21, 5)).astype(np.float32), 257 if not small else 9])]
+    # test_linop_sparse_kron_id.m / test_linop_id_kron_sparse.m: sparse factor, same 2 x 2 arrangement
+    Ks = sp.random(mr, mc, density=0.3, random_state=5, format="csc", dtype=np.float32)
+    for name in ("sparse_kron_id", "id_kron_sparse"):
+        cases[f"{name}_2x2"] = [(name, rr * mr * d, cc * mc * d, [Ks, d]) for rr in (0, 1) for cc in (0, 1)]
+        cases[f"{name}_empty_rows"] = [(name, 0, 0, [sp.csc_matrix(np.array([[0, 2.0, 0], [0, 0, 0], [1.5, 0, -1.0]],
+                                                                             dtype=np.float32)), 33 if not small else 5])]
     return cases

@@ -62,6 +62,14 @@ class _Writer:
             A = np.asarray(data[0], dtype=np.float32)
             fd, _ = self.arr(np.ascontiguousarray(A.T), np.float32)
             return f"block dense {row} {col} {A.shape[0]} {A.shape[1]} {fd}"
+        if name in ("sparse_kron_id", "id_kron_sparse"):
+            import scipy.sparse as sp
+            A = sp.csc_matrix(data[0])
+            A.sort_indices()
+            fv, _ = self.arr(A.data, np.float32)
+            fp, _ = self.arr(A.indptr, np.int32)
+            fi, _ = self.arr(A.indices, np.int32)
+            return f"block {name} {row} {col} {int(data[1])} {A.shape[0]} {A.shape[1]} {A.nnz} {fv} {fp} {fi}"
         if name in ("dense_kron_id", "id_kron_dense"):
             K = np.asarray(data[0], dtype=np.float32)
             fd, _ = self.arr(np.ascontiguousarray(K.T), np.float32)

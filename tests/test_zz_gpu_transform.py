@@ -124,7 +124,7 @@ def test_projection_prox_errors(ctx):
     assert "Coefficient a has to have dimension count*dim or dim" in str(e.value)
 
 
-# ---- Kronecker blocks dense_kron_id / id_kron_dense ------------------------------------------
+# ---- Kronecker blocks dense_kron_id / id_kron_dense / sparse_kron_id / id_kron_sparse ------------------------------------------
 KRON_CASES = cases.linop_kron_cases()
 
 
@@ -143,6 +143,7 @@ def test_kron_blocks_forward_adjoint(ctx, name):
     # the reference tests compare with kron() at 1e-3
     M = np.zeros((m, n))
     for (bname, row, col, (K, d)) in blocks:
+        K = K.toarray() if hasattr(K, "toarray") else K
         full = np.kron(np.eye(d), K) if bname.startswith("id_") else np.kron(K, np.eye(d))
         M[row:row + full.shape[0], col:col + full.shape[1]] += full
     assert np.abs(fwd - M @ x).max() < 1e-3 and np.abs(adj - M.T @ y).max() < 1e-3, name
