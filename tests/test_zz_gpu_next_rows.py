@@ -1,6 +1,9 @@
-"""GPU suite, SURVEY.md 8(f) row 2 (first widening step after the hot path): ProxTransform through the C ABI
-against the oracle, against the closed form of the reference's own test (test_prox_transform.m) and against
-the live reference build.  Runs last (file name) because it was added after the hot-path rows."""
+"""GPU suite, SURVEY.md 8(f) "next" rows (the widening steps after the hot path), all through the C ABI against
+the oracle, the closed forms of the reference's own MATLAB tests and the live reference build:
+  row 2: ProxTransform, elem_operation:ind_sum, ProxIndHalfspace, ProxIndSOC
+  row 3: Kronecker blocks dense_kron_id, id_kron_dense, sparse_kron_id, id_kron_sparse
+Runs last (file name): these were written after round 1's GPU budget was spent, so the round-end suite is their
+first run."""
 import zlib
 
 import numpy as np
