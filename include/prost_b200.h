@@ -287,6 +287,9 @@ int pb_pdhg_create(pb_context* ctx, pb_problem* prob, const pb_pdhg_options* opt
 int pb_admm_create(pb_context* ctx, pb_problem* prob, const pb_admm_options* opts,
                    const pb_solver_options* sopts, pb_backend** out);
 void pb_backend_destroy(pb_backend* b);
+/* Backend::SetOptions(Solver::Options) as called by Solver::Initialize (solver.cu:88-90): the solver's
+ * tolerances govern eps_primal / eps_dual and hence the stopping test.  Before pb_backend_initialize. */
+int pb_backend_set_solver_options(pb_backend* b, const pb_solver_options* sopts);
 /* Backend::Initialize with Solver::Options::x0/y0 (NULL or length 0 => zeros) */
 int pb_backend_initialize(pb_backend* b, const float* h_x0, size_t nx0, const float* h_y0,
                           size_t ny0);

@@ -165,6 +165,7 @@ SIGNATURES = {
     "pb_pdhg_create": (C.c_int, [handle, handle, C.POINTER(PDHGOptions), C.POINTER(SolverOptions), handle_p]),
     "pb_admm_create": (C.c_int, [handle, handle, C.POINTER(ADMMOptions), C.POINTER(SolverOptions), handle_p]),
     "pb_backend_destroy": (None, [handle]),
+    "pb_backend_set_solver_options": (C.c_int, [handle, C.POINTER(SolverOptions)]),
     "pb_backend_initialize": (C.c_int, [handle, c_float_p, C.c_size_t, c_float_p, C.c_size_t]),
     "pb_backend_iterate": (C.c_int, [handle, C.c_int]),
     "pb_backend_profile": (C.c_int, [handle, C.c_int, c_float_p]),

@@ -629,6 +629,10 @@ class Solver:
             self.problem.Dualize()
             x0, y0 = y0, x0
         try:
+            # Solver::Initialize pushes its options into the backend (solver.cu:88-90): the solver's
+            # tolerances govern the stopping test even if the backend was constructed with others
+            check(lib.pb_backend_set_solver_options(self.backend._h, C.byref(self.opts)))
+            self.backend.sopts = self.opts
             self.backend.Initialize(x0, y0)
         except ProstError as e:
             raise ProstError(e.status, f"Failed to initialize the backend. Reason: {e}") from None

@@ -120,6 +120,8 @@ class Backend {
   Context* ctx() const { return ctx_; }
   Problem* problem() const { return problem_.get(); }
   const pb_solver_options& solver_options() const { return sopts_; }
+  // Solver::Initialize pushes its options into the backend (solver.cu:88-90); takes effect at initialize()
+  void set_solver_options(const pb_solver_options& o) { sopts_ = o; }
   unsigned long long launch_base = 0;
 
  protected:

@@ -519,6 +519,9 @@ int pb_admm_create(pb_context* c, pb_problem* prob, const pb_admm_options* opts,
   });
 }
 void pb_backend_destroy(pb_backend* b) { delete b; }
+int pb_backend_set_solver_options(pb_backend* b, const pb_solver_options* sopts) {
+  return guarded([&] { require(b && sopts, "NULL argument"); b->impl->set_solver_options(*sopts); });
+}
 int pb_backend_initialize(pb_backend* b, const float* h_x0, size_t nx0, const float* h_y0, size_t ny0) {
   return guarded([&] { require(b != nullptr, "NULL backend"); b->impl->initialize(h_x0, nx0, h_y0, ny0); });
 }

@@ -380,8 +380,20 @@ void BackendPDHG::initialize(const float* h_x0, size_t nx0, const float* h_y0, s
     }
   }
 
-  if (nx0 > 0 && nx0 != n) fail(PB_ERR_INVALID, "Initial primal solution has wrong size.");
-  if (ny0 > 0 && ny0 != m) fail(PB_ERR_INVALID, "Initial dual solution has wrong size.");
+  // Slabs: a rank-local failure must not leave the peers blocked in the next collective, so every rank-local
+  // verdict between two collectives is voted on (sum of failure flags) before any rank throws.
+  auto vote = [&](bool ok_local, int status, const std::string& msg) {
+    if (comm_) {
+      double bad[1] = {ok_local ? 0.0 : 1.0};
+      comm_->allreduce_sum_host(bad, 1);
+      if (bad[0] != 0.0)
+        fail(status, ok_local ? "slab decomposition: another rank failed to initialize (" + msg + ")" : msg);
+    } else if (!ok_local) {
+      fail(status, msg);
+    }
+  };
+  vote(!(nx0 > 0 && nx0 != n), PB_ERR_INVALID, "Initial primal solution has wrong size.");
+  vote(!(ny0 > 0 && ny0 != m), PB_ERR_INVALID, "Initial dual solution has wrong size.");
 
   { PB_TRACE_SCOPE("  plan_fused"); fused_ = plan_fused(); }
   tile_ok_ = fused_ && opts_.fuse == 1 &&
@@ -426,29 +438,34 @@ void BackendPDHG::initialize(const float* h_x0, size_t nx0, const float* h_y0, s
     comm_->allreduce_sum_host(no_tile, 1);
     tile_ok_ = no_tile[0] == 0.0;
   }
-  try {
+  {
     PB_TRACE_SCOPE("  allocate iterates");
-    x_.resize(n); x_prev_.resize(n); y_.resize(m); y_prev_.resize(m);
-    if (tile_ok_) y_stage_.resize(m);
-    if (tile_ok_ && ring_iters_ > 1) {
-      const unsigned n_tiles = tile_ring_tile_count(stencil_);
-      ring_done_.resize(std::max(n_tiles, 1u));
-      ring_done_.zero(s);
-      ring_edge_counters_.resize(64);
-      ring_edge_counters_.zero(s);
-      ring_error_.resize(1);
-      ring_error_.zero(s);
-      ring_base_ = 0;
+    std::string alloc_error;
+    int alloc_status = PB_OK;
+    try {
+      x_.resize(n); x_prev_.resize(n); y_.resize(m); y_prev_.resize(m);
+      if (tile_ok_) y_stage_.resize(m);
+      if (tile_ok_ && ring_iters_ > 1) {
+        const unsigned n_tiles = tile_ring_tile_count(stencil_);
+        ring_done_.resize(std::max(n_tiles, 1u));
+        ring_done_.zero(s);
+        ring_edge_counters_.resize(64);
+        ring_edge_counters_.zero(s);
+        ring_error_.resize(1);
+        ring_error_.zero(s);
+        ring_base_ = 0;
+      }
+      if (!fused_) {
+        temp_.resize(std::max(m, n));
+        kx_.resize(m); kx_prev_.resize(m); kty_.resize(n); kty_prev_.resize(n);
+      }
+      d_state_.resize(1);
+      d_sums_.resize(4);
+    } catch (Error& e) {
+      alloc_status = e.status;
+      alloc_error = e.status == PB_ERR_OOM ? std::string("Out of memory: ") + e.what() : std::string(e.what());
     }
-    if (!fused_) {
-      temp_.resize(std::max(m, n));
-      kx_.resize(m); kx_prev_.resize(m); kty_.resize(n); kty_prev_.resize(n);
-    }
-    d_state_.resize(1);
-    d_sums_.resize(4);
-  } catch (Error& e) {
-    if (e.status == PB_ERR_OOM) fail(PB_ERR_OOM, std::string("Out of memory: ") + e.what());
-    throw;
+    vote(alloc_status == PB_OK, alloc_status == PB_OK ? PB_ERR_OOM : alloc_status, alloc_error.empty() ? "allocation" : alloc_error);
   }
   if (!fused_) { temp_.zero(s); kx_.zero(s); kx_prev_.zero(s); kty_.zero(s); kty_prev_.zero(s); }
   // x0 / y0 (:288-308): one host -> device copy each, the previous iterate is a device copy
@@ -757,25 +774,31 @@ void BackendPDHG::profile_detail(int n_iters, float out[8]) {
   ctx_->bind();
   for (int k = 0; k < 8; ++k) out[k] = 0.f;
   if (!fused_ || n_iters <= 0) { iterate(n_iters); return; }
-  cudaEvent_t ev[4];
+  // four events per iteration, all recorded back to back and read after ONE synchronisation at the end: the
+  // iterations run exactly as in iterate() (no host round trip between them, so on slabs no rank skew either)
+  std::vector<cudaEvent_t> ev(4 * (size_t)n_iters);
   for (auto& e : ev) PB_CUDA(cudaEventCreate(&e));
-  prof_ev_ = ev;
+  std::vector<unsigned char> kind(n_iters);          // 0 two-pass, 1 one-pass, 2 one-pass with residual refresh
+  for (int i = 0; i < n_iters; ++i) {
+    const unsigned long long tiles_before = tile_iterations_, chk_before = tile_check_iterations_;
+    prof_ev_ = &ev[4 * (size_t)i];
+    PB_CUDA(cudaEventRecord(prof_ev_[0], ctx_->stream));
+    iteration_fused();
+    PB_CUDA(cudaEventRecord(prof_ev_[3], ctx_->stream));
+    kind[i] = tile_check_iterations_ != chk_before ? 2 : (tile_iterations_ != tiles_before ? 1 : 0);
+  }
+  prof_ev_ = nullptr;
+  PB_CUDA(cudaStreamSynchronize(ctx_->stream));
   double acc[5] = {0, 0, 0, 0, 0};
   int n_two = 0, n_tile = 0, n_chk = 0;
   for (int i = 0; i < n_iters; ++i) {
-    const unsigned long long tiles_before = tile_iterations_, chk_before = tile_check_iterations_;
-    PB_CUDA(cudaEventRecord(ev[0], ctx_->stream));
-    iteration_fused();
-    PB_CUDA(cudaEventRecord(ev[3], ctx_->stream));
-    PB_CUDA(cudaEventSynchronize(ev[3]));
     float ms[3];
-    for (int k = 0; k < 3; ++k) PB_CUDA(cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]));
-    if (tile_check_iterations_ != chk_before) { acc[4] += ms[0]; ++n_chk; }
-    else if (tile_iterations_ != tiles_before) { acc[3] += ms[0]; ++n_tile; }
+    for (int k = 0; k < 3; ++k) PB_CUDA(cudaEventElapsedTime(&ms[k], ev[4 * (size_t)i + k], ev[4 * (size_t)i + k + 1]));
+    if (kind[i] == 2) { acc[4] += ms[0]; ++n_chk; }
+    else if (kind[i] == 1) { acc[3] += ms[0]; ++n_tile; }
     else { acc[0] += ms[0]; acc[1] += ms[1]; ++n_two; }
     acc[2] += ms[2];
   }
-  prof_ev_ = nullptr;
   for (auto& e : ev) cudaEventDestroy(e);
   out[0] = n_two ? static_cast<float>(acc[0] / n_two) : 0.f;
   out[1] = n_two ? static_cast<float>(acc[1] / n_two) : 0.f;

@@ -8,14 +8,16 @@ from oracle_binding import OracleProblem, OraclePDHG
 TOL = dict(tol_rel_primal=0.0, tol_rel_dual=0.0, tol_abs_primal=0.0, tol_abs_dual=0.0)
 
 
-def run_cuda(ctx, desc, iters, fuse=True, x0=None, y0=None, tol=None, use_solver=False, **opts):
+def run_cuda(ctx, desc, iters, fuse=True, x0=None, y0=None, tol=None, use_solver=False, solve_dual_problem=False,
+             **opts):
     """use_solver=False: exactly `iters` x PerformIteration.  use_solver=True: Solver::Solve with
     max_iters=iters, which stops early on convergence like the reference's loop (solver.cu:141-196)."""
     prob = pb.create_problem(ctx, desc)
     popts = pb.pdhg_options(scale_steps_operator=0, fuse=int(fuse), **opts)
-    sopts = pb.solver_options(verbose=0, max_iters=iters, num_cback_calls=0, **(tol or TOL))
+    sopts = pb.solver_options(verbose=0, max_iters=iters, num_cback_calls=0,
+                              solve_dual_problem=int(bool(solve_dual_problem)), **(tol or TOL))
     be = pb.BackendPDHG(ctx, prob, popts, sopts)
-    if use_solver:
+    if use_solver or solve_dual_problem:
         solver = pb.Solver(prob, be)
         solver.SetOptions(sopts, x0=x0, y0=y0)
         solver.Initialize()

@@ -152,7 +152,8 @@ def run_prox(desc, arg, tau_diag, tau, binary=REF_DRIVER):
 
 def run_solve(desc, iters, x0=None, y0=None, tol=None, binary=REF_DRIVER, tau0=1.0, sigma0=1.0, residual_iter=1,
               alg2_gamma=0.0, arg_alpha0=0.5, arg_nu=0.95, arg_delta=1.5, arb_delta=1.05, arb_tau=0.8,
-              stepsize="boyd", scale_steps_operator=0, num_cback_calls=0, timeout=1200, admm=None):
+              stepsize="boyd", scale_steps_operator=0, num_cback_calls=0, timeout=1200, admm=None,
+              solve_dual_problem=False):
     """admm: None for BackendPDHG, or a dict of BackendADMM options (rho0, alpha, cg_tol_pow, cg_tol_min,
     cg_tol_max, cg_max_iter, residual_iter, arb_delta, arb_tau, arb_gamma; defaults of +backend/admm.m)."""
     tol = tol or dict(tol_rel_primal=0.0, tol_rel_dual=0.0, tol_abs_primal=0.0, tol_abs_dual=0.0)
@@ -184,7 +185,7 @@ def run_solve(desc, iters, x0=None, y0=None, tol=None, binary=REF_DRIVER, tau0=1
         fx = w.arr(x0, np.float32)[0] if x0 is not None else "-"
         fy = w.arr(y0, np.float32)[0] if y0 is not None else "-"
         lines.append(f"solver {tol['tol_rel_primal']!r} {tol['tol_rel_dual']!r} {tol['tol_abs_primal']!r} "
-                     f"{tol['tol_abs_dual']!r} {iters} {num_cback_calls} {fx} {fy} 0")
+                     f"{tol['tol_abs_dual']!r} {iters} {num_cback_calls} {fx} {fy} {int(bool(solve_dual_problem))}")
         lines += ["action solve - - -", f"out {d}/out"]
         info = _run(binary, d, lines, timeout=timeout)
         out = {k: np.fromfile(f"{d}/out_{k}.f32", np.float32) for k in ("x", "y", "z", "w")}

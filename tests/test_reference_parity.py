@@ -115,6 +115,26 @@ def test_pdhg_vs_reference(ctx, name, fuse):
                           res_tol=5e-3 if loose else 1e-4)
 
 
+@pytest.mark.parametrize("name", ["rof_alg1", "rof_boyd", "tvl1_color", "lifting_L8"])
+def test_pdhg_dual_problem_vs_reference(ctx, name):
+    """Solver::Options::solve_dual_problem (solver.cu:80-84, 199-203; dual_linearoperator.cu:38-80): PDHG on the
+    dualised problem (prox_g <-> prox_fstar, K -> -K^T, x0 <-> y0, swapped scalings), solutions swapped back by
+    cur_primal_sol() & co.  Same iteration count and iterates as the live reference; warm start included."""
+    desc_fn, iters, opts = PDHG_CASES[name]
+    desc = desc_fn()
+    r = np.random.default_rng(5)
+    x0 = r.random(desc["ncols"]).astype(np.float32)
+    y0 = (0.1 * r.standard_normal(desc["nrows"])).astype(np.float32)
+    want = ref_driver.run_solve(desc, iters, tol=TOL4, x0=x0, y0=y0, solve_dual_problem=True, **opts)
+    for fuse in (1, 0):
+        got = run_cuda(ctx, desc, iters, fuse=fuse, tol=TOL4, x0=x0, y0=y0, solve_dual_problem=True, **opts)
+        assert got["iterations"] == int(want["info"]["iterations"]), (got["iterations"], want["info"]["iterations"])
+        assert_ref_parity(got, want, f"dual problem {name} fuse={fuse}")
+    # and it is a different trajectory from the primal run (the test would be vacuous otherwise)
+    primal = run_cuda(ctx, desc, iters, fuse=1, tol=TOL4, x0=x0, y0=y0, use_solver=True, **opts)
+    assert rel_err(primal["x"], got["x"]) > 1e-4
+
+
 def test_c1_rof_512_1000_iterations_vs_reference(ctx):
     """BASELINE config 1 against the reference's CUDA solver: ROF 512x512, 1000 PDHG iterations."""
     desc = syn.rof(512, 512)
