@@ -5,20 +5,32 @@
 
 A *step* is one PDHG iteration (BackendPDHG::PerformIteration, backend_pdhg.cu:311-381) on the
 metric config of SURVEY.md section 8(d): ROF 4096 x 4096 gray, BlockGradient2D + 1d:square +
-norm2:ind_leq0, alpha = 1 preconditioning, Alg1 steps, residuals every 10 iterations.
+norm2:ind_leq0, alpha = 1 preconditioning, Alg1 steps, residuals every 10 iterations.  With N > 1 (one
+process per GPU under torch.distributed.run) the same image is split into N column slabs (strong scaling).
 Rank 0 prints ONE JSON line (contract in the task statement):
 
-  value      iterations/s with all inputs resident in HBM, CUDA-event timed over K iterations
-  e2e        iterations/s of a whole solve through the public Solver API with pinned HOST
-             buffers: problem upload (H2D), K iterations, solution download (D2H)
-  roofline   dominant kernel (fused dual pass): algorithmic bytes / event-timed duration vs the
-             measured HBM copy bandwidth in MEASURED_PEAKS.json
-  cpu_baseline  the OpenMP oracle port of the same iteration on the host cores (bounded sample)
+  value      iterations/s with all inputs resident in HBM, CUDA-event timed over K iterations, max over ranks
+  e2e        iterations/s of a whole solve through the public Solver API with pinned HOST buffers:
+             problem upload (H2D), K iterations, solution download (D2H)
+  roofline   dominant kernel (one-pass ring kernel, pb_tile.cu): algorithmic bytes per launch / CUDA-event
+             duration of the launch vs the measured HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline   the OpenMP oracle port of the same iteration on the host cores (bounded sample)
+  reference_cuda the UNMODIFIED reference CUDA solver (oracle/_ref, compiled for sm_100) on the same GPU and
+             the same 4096^2 input through the same C++ driver program, with the max relative difference of
+             the iterates (N = 1 only; part of the baseline leg)
+  workloads  BASELINE configs 2-4 at full size on the same N GPUs: TV-L1 4096^2 x 3 (boyd), lifting
+             2048^2 x 32 (boyd), 3-D TV 512^3 -- iterations/s and fraction of the HBM roofline each
+
+Algorithmic bytes: the one-pass kernel reads y (2 floats), x, f and writes x+, y+ (2):
+7 floats = 28 B per pixel and iteration (36 B on residual-refresh iterations, which also read the previous
+dual iterate).  SURVEY.md 8(d)'s 44 B/pixel is the minimum of a TWO-pass schedule; it is reported once, as
+`roofline.two_pass_equivalent`, and used for nothing else.
 
 --impl reference times the reference algorithm's CPU restatement (prost has no CPU path of its
 own; oracle/prost_oracle.cpp, kind "port") on all host threads.
 """
 import argparse
+import importlib.util
 import json
 import os
 import subprocess
@@ -32,15 +44,11 @@ sys.path.insert(0, ROOT)
 NX = NY = 4096
 LAM = 10.0
 RESIDUAL_ITER = 10
-# primal pass reads y (2N) + x (N) + f (N), writes x+ (N); dual pass reads x+, x (2N),
-# y (2N), writes y+ (2N): 11 floats = 44 B per pixel per iteration, 20 B primal + 24 B dual.
-BYTES_PER_PX_ITER = 44
+BYTES_PER_PX_TILE = 28          # one-pass iteration: read y (2N), x (N), f (N); write x+ (N), y+ (2N)
+BYTES_PER_PX_TILE_CHECK = 36    # + the previous dual iterate (2N) on residual-refresh iterations
+BYTES_PER_PX_TWO_PASS = 44      # 20 B primal pass + 24 B dual pass (iteration 0 only here)
 BYTES_PER_PX_PRIMAL = 20
 BYTES_PER_PX_DUAL = 24
-# one-pass tiled iteration (pb_tile.cu): read y (2N), x (N), f (N); write x+ (N), y+ (2N) = 7 floats
-BYTES_PER_PX_TILE = 28
-# the same pass on residual-refresh iterations also reads the previous dual iterate (2N): 9 floats
-BYTES_PER_PX_TILE_CHECK = 36
 
 
 def measured_peak():
@@ -51,6 +59,33 @@ def measured_peak():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def measured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the ncu --set full
+    capture that scripts/capture_ring_traffic.sh wrote (profiles/ring_traffic.json); None if there is none."""
+    path = os.path.join(ROOT, "profiles", "ring_traffic.json")
+    try:
+        d = json.load(open(path))
+        return float(d["dram_bytes_per_launch"]), d.get("source")
+    except Exception:
+        return None, None
+
+
+def load_synthetic():
+    """prost_b200/synthetic.py as a stand-alone module (numpy only): the reference arm must not import the
+    package, which would dlopen libprost_b200.so into a process that is supposed to run none of it."""
+    spec = importlib.util.spec_from_file_location("pb_synthetic", os.path.join(ROOT, "prost_b200", "synthetic.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
 class ClockSampler:
@@ -106,52 +141,40 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def build_problem(pb, syn, ctx, f):
-    desc = syn.rof(NX, NY, LAM, f=f)
-    prob = pb.create_problem(ctx, desc)
-    return prob
-
-
-def time_to_residual(pb, ctx, make_problem, comm=None, max_iters=20000):
-    """BASELINE metric, third part: wall time of Solver.Solve until r_p < eps_p and r_d < eps_d with all four
-    tolerances 1e-4 (backend.hpp:71-74), Alg2 with gamma = 0.05 lambda like the reference's ROF example
-    (matlab/examples/example_rof_primaldual.m:36-38).  Includes the copy-back of the solution."""
-    popts = pb.pdhg_options(scale_steps_operator=0, stepsize="alg2", alg2_gamma=0.05 * LAM,
-                            residual_iter=RESIDUAL_ITER)
-    sopts = pb.solver_options(verbose=0, max_iters=max_iters, tol_rel_primal=1e-4, tol_rel_dual=1e-4,
-                              tol_abs_primal=1e-4, tol_abs_dual=1e-4, num_cback_calls=0)
-    prob = make_problem()
-    be = pb.BackendPDHG(ctx, prob, popts, sopts, comm=comm) if comm else pb.BackendPDHG(ctx, prob, popts, sopts)
-    solver = pb.Solver(prob, be)
-    solver.SetOptions(sopts)
-    solver.Initialize()
-    ctx.synchronize()
+def oracle_rate(syn, cols, seconds, threads):
+    """iterations/s of the FULL 4096-column image from the OpenMP oracle on a `cols`-column slab (the
+    iteration is bandwidth-bound on the host, so the rate scales with 1/columns)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as ob
+    ob.lib.orc_set_num_threads(int(threads))
+    o = ob.OraclePDHG(ob.OracleProblem(syn.rof(cols, NY, LAM)), stepsize="alg1", residual_iter=RESIDUAL_ITER,
+                      tol_rel_primal=0, tol_rel_dual=0, tol_abs_primal=0, tol_abs_dual=0)
+    o.initialize()
+    o.iterate(2)
     t0 = time.perf_counter()
-    result = solver.Solve()
-    ctx.synchronize()
+    its = 0
+    while time.perf_counter() - t0 < seconds:
+        o.iterate(5)
+        its += 5
     dt = time.perf_counter() - t0
-    res = be.residuals()
-    return {"seconds": dt, "iterations": int(solver.iterations), "converged": result == pb.Solver.CONVERGED,
-            "stepsize": "alg2, gamma = 0.05 lambda", "tolerances": 1e-4, "max_iters": max_iters,
-            "primal_residual": res["primal_residual"], "dual_residual": res["dual_residual"],
-            "eps_primal": res["eps_primal"], "eps_dual": res["eps_dual"],
-            "what": "Solver.Solve wall time (residual check every 10 iterations) incl. D2H of x, z, y, w"}
+    return its / dt * cols / NX, its, ob.num_threads()
 
 
 def run_reference_arm(args, rank, world):
-    """Reference arm for this tier: the CPU restatement of prost's PDHG iteration on host cores."""
+    """Reference arm for this tier: the CPU restatement of prost's PDHG iteration on ALL host cores (under
+    torch.distributed.run OMP_NUM_THREADS is 1, so the thread count is set explicitly)."""
     if rank != 0:
         return
+    syn = load_synthetic()
+    threads = host_cores()
+    os.environ["OMP_NUM_THREADS"] = str(threads)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from oracle_binding import OracleProblem, OraclePDHG, num_threads
-    from prost_b200 import synthetic as syn
-    threads = num_threads()
-    # bounded sample: a slab of columns sized so that K+W iterations take about two minutes;
-    # the iteration is bandwidth-bound on the host, so iterations/s scales with 1/columns.
+    import oracle_binding as ob
+    ob.lib.orc_set_num_threads(threads)
+    # bounded sample: a slab of columns sized so that K+W iterations take about two minutes
     probe_cols = 256
-    desc = syn.rof(probe_cols, NY, LAM)
-    o = OraclePDHG(OracleProblem(desc), stepsize="alg1", residual_iter=RESIDUAL_ITER,
-                   tol_rel_primal=0, tol_rel_dual=0, tol_abs_primal=0, tol_abs_dual=0)
+    o = ob.OraclePDHG(ob.OracleProblem(syn.rof(probe_cols, NY, LAM)), stepsize="alg1", residual_iter=RESIDUAL_ITER,
+                      tol_rel_primal=0, tol_rel_dual=0, tol_abs_primal=0, tol_abs_dual=0)
     o.initialize()
     o.iterate(2)
     t0 = time.perf_counter()
@@ -161,9 +184,8 @@ def run_reference_arm(args, rank, world):
     cols = int(min(NX, max(64, probe_cols * budget / max(t_iter_probe * (args.steps + args.warmup), 1e-9))))
     cols = max(64, (cols // 64) * 64)
     if cols != probe_cols:
-        desc = syn.rof(cols, NY, LAM)
-        o = OraclePDHG(OracleProblem(desc), stepsize="alg1", residual_iter=RESIDUAL_ITER,
-                       tol_rel_primal=0, tol_rel_dual=0, tol_abs_primal=0, tol_abs_dual=0)
+        o = ob.OraclePDHG(ob.OracleProblem(syn.rof(cols, NY, LAM)), stepsize="alg1", residual_iter=RESIDUAL_ITER,
+                          tol_rel_primal=0, tol_rel_dual=0, tol_abs_primal=0, tol_abs_dual=0)
         o.initialize()
     o.iterate(args.warmup)
     t0 = time.perf_counter()
@@ -178,174 +200,423 @@ def run_reference_arm(args, rank, world):
         "ms_per_step": dt / args.steps / frac * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": "iter/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "iter/s", "cores": ob.num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n_gpus, scaling="strong"):
-    cols = NX * n_gpus if scaling == "weak" else NX
-    per_gpu_mb = 28 * (cols // n_gpus) * NY / 1e6
-    return {"workload": f"ROF-TV {cols}x{NY} gray, PDHG Alg1, BlockGradient2D + 1d:square(lambda={LAM:g}) + "
+def workload_config(n_gpus):
+    per_gpu_mb = BYTES_PER_PX_TILE * (NX // n_gpus) * NY / 1e6
+    return {"workload": f"ROF-TV {NX}x{NY} gray, PDHG Alg1, BlockGradient2D + 1d:square(lambda={LAM:g}) + "
                         f"norm2:ind_leq0, alpha=1 preconditioning, residual_iter={RESIDUAL_ITER}",
-            "n_pixels": cols * NY, "bytes_per_iteration_algorithmic": BYTES_PER_PX_ITER * cols * NY,
+            "n_pixels": NX * NY,
+            "bytes_per_iteration_algorithmic": BYTES_PER_PX_TILE * NX * NY,
+            "bytes_per_pixel": {"one_pass_iteration": BYTES_PER_PX_TILE, "residual_refresh_iteration": BYTES_PER_PX_TILE_CHECK,
+                                "two_pass_schedule_SURVEY_8d": BYTES_PER_PX_TWO_PASS},
             "cache": (f"per-GPU state (x,x_prev,y,y_prev,f) = {per_gpu_mb:.0f} MB; "
                       + ("exceeds the 126 MB L2, no flush needed" if per_gpu_mb > 126 else
                          "FITS the 126 MB L2: the strong-scaling slabs run L2-resident by construction "
                          "(that is the workload, not a cached repeat: every iteration reads the previous "
                          "iteration's output)")),
-            "parallelism": (f"slab{n_gpus}: column slabs, one-pass ring kernel per slab with peer-to-peer halo "
-                            f"stores over NVLink from its edge tiles, "
-                            f"NCCL all-reduce of 4 residual sums every {RESIDUAL_ITER} iterations")
+            "parallelism": (f"slab{n_gpus}: column slabs, persistent one-pass ring kernel per slab (up to 16 iterations "
+                            f"per launch) with peer-to-peer halo stores over NVLink from its edge tiles; residual sums "
+                            f"combined through peer-mapped slots inside the residual-refresh launch every "
+                            f"{RESIDUAL_ITER} iterations")
             if n_gpus > 1 else "single"}
 
 
-def run_slab_arm(args, rank, local_rank, world):
-    """N > 1: one process per GPU, each owning a block of image columns."""
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-    import prost_b200 as pb
-    from prost_b200 import synthetic as syn
-    from prost_b200 import distributed as pbd
+class Env:
+    """Rank plumbing shared by all legs of the `ours` arm."""
 
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    stream = torch.cuda.Stream()
-    torch.cuda.set_stream(stream)
-    ctx = pb.Context(local_rank, stream.cuda_stream)
-    comm = pbd.init_comm(ctx)
+    def __init__(self, args):
+        import torch
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        torch.cuda.set_device(self.local)
+        import prost_b200 as pb
+        from prost_b200 import distributed as pbd
+        self.pb, self.pbd = pb, pbd
+        from prost_b200 import synthetic
+        self.syn = synthetic
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist = dist
+        # a dedicated (non-default) stream: the context launches on it and the CUDA events are recorded on
+        # it, so the events bracket exactly the kernels of the timed region
+        self.stream = torch.cuda.Stream()
+        torch.cuda.set_stream(self.stream)
+        assert self.stream.cuda_stream != 0
+        self.ctx = pb.Context(self.local, self.stream.cuda_stream)
+        self.comm = pbd.init_comm(self.ctx) if self.world > 1 else None
 
-    weak = args.scaling == "weak"
-    cols_total = NX * world if weak else NX
-    part = pbd.SlabPartition(cols_total, world, align=4)
-    x0, x1 = part.range(rank)
-    w = x1 - x0
-    f = syn.image(cols_total, NY, x0=x0, x1=x1)        # this rank's columns only (counter-based RNG)
-    n, m = w * NY, 2 * w * NY
-    norm = cols_total / NX                               # iterations of a 4096^2 image per iteration
-
-    def max_over_ranks(v):
-        t = torch.tensor([float(v)], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    def max_over_ranks(self, v):
+        if self.world == 1:
+            return float(v)
+        t = self.torch.tensor([float(v)], device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
+    def barrier(self):
+        if self.dist:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed_iterations(self, be, steps):
+        """EXACTLY `steps` iterations between two events on the launching stream, barrier + synchronize on both
+        sides, max over ranks; returns ms."""
+        torch = self.torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record(self.stream)
+        be.PerformIteration(steps)
+        e1.record(self.stream)
+        self.barrier()
+        return self.max_over_ranks(e0.elapsed_time(e1))
+
+    def backend(self, prob, popts, sopts):
+        pb = self.pb
+        return pb.BackendPDHG(self.ctx, prob, popts, sopts, comm=self.comm) if self.comm else \
+            pb.BackendPDHG(self.ctx, prob, popts, sopts)
+
+    def close(self):
+        if self.comm:
+            self.comm.close()
+            self.dist.destroy_process_group()
+
+
+def time_to_residual(env, make_problem, max_iters=20000):
+    """BASELINE metric, third part: wall time of Solver.Solve until r_p < eps_p and r_d < eps_d with all four
+    tolerances 1e-4 (backend.hpp:71-74), Alg2 with gamma = 0.05 lambda like the reference's ROF example
+    (matlab/examples/example_rof_primaldual.m:36-38).  Includes the copy-back of the solution."""
+    pb = env.pb
+    popts = pb.pdhg_options(scale_steps_operator=0, stepsize="alg2", alg2_gamma=0.05 * LAM,
+                            residual_iter=RESIDUAL_ITER)
+    sopts = pb.solver_options(verbose=0, max_iters=max_iters, tol_rel_primal=1e-4, tol_rel_dual=1e-4,
+                              tol_abs_primal=1e-4, tol_abs_dual=1e-4, num_cback_calls=0)
+    prob = make_problem()
+    be = env.backend(prob, popts, sopts)
+    solver = pb.Solver(prob, be)
+    solver.SetOptions(sopts)
+    solver.Initialize()
+    env.barrier()
+    t0 = time.perf_counter()
+    result = solver.Solve()
+    env.ctx.synchronize()
+    dt = env.max_over_ranks(time.perf_counter() - t0)
+    res = be.residuals()
+    return {"seconds": dt, "iterations": int(solver.iterations), "converged": result == pb.Solver.CONVERGED,
+            "stepsize": "alg2, gamma = 0.05 lambda", "tolerances": 1e-4, "max_iters": max_iters,
+            "primal_residual": res["primal_residual"], "dual_residual": res["dual_residual"],
+            "eps_primal": res["eps_primal"], "eps_dual": res["eps_dual"],
+            "what": "Solver.Solve wall time (residual check every 10 iterations) incl. D2H of x, z, y, w"}
+
+
+def iterate_hash(env, be, part, n_planes_x, n_planes_y):
+    """Order-independent checksum of the device iterates after the timed run: sum over elements of
+    bits(v) * (global index + 1) mod 2^64, summed over ranks.  The N-rank value must equal the 1-rank value
+    (slab iterates are bit-identical to the single-GPU ones), which makes the scaling run carry slab parity."""
+    import numpy as np
+    x, _z, y, _w = be.current_solution(with_constraints=False)
+    x0, x1 = part.range(env.rank)
+    w = x1 - x0
+
+    def h(arr, planes):
+        a = arr.view(np.uint32).astype(np.uint64).reshape(planes, w, NY)
+        p = np.arange(planes, dtype=np.uint64)[:, None, None] * np.uint64(NX * NY)
+        c = (np.arange(x0, x1, dtype=np.uint64) * np.uint64(NY))[None, :, None]
+        r = np.arange(NY, dtype=np.uint64)[None, None, :]
+        with np.errstate(over="ignore"):
+            return int((a * (p + c + r + np.uint64(1))).sum(dtype=np.uint64))
+
+    hx, hy = h(x, n_planes_x), h(y, n_planes_y)
+    if env.world > 1:
+        vals = [None] * env.world
+        env.dist.all_gather_object(vals, (hx, hy))
+        hx = sum(v[0] for v in vals) % (1 << 64)
+        hy = sum(v[1] for v in vals) % (1 << 64)
+    return {"x": f"{hx:016x}", "y": f"{hy:016x}"}
+
+
+def aux_workload(env, name, steps, warmup):
+    """BASELINE configs 2-4 at full size on the same GPUs: iterations/s (device-timed, max over ranks) and the
+    fraction of the HBM roofline on the algorithmic bytes of SURVEY.md 8(d)."""
+    pb, syn, pbd = env.pb, env.syn, env.pbd
+    t0 = time.perf_counter()
+    if name == "tvl1_4096x4096x3":
+        nx, ny, planes, bytes_per_unit, unit = 4096, 4096, 3, 132, "pixel"
+        part = pbd.SlabPartition(nx, env.world, align=4)
+        x0, x1 = part.range(env.rank)
+        f = syn.salt_and_pepper(syn.image(nx, ny, 3, x0=x0, x1=x1), nx=nx, ny=ny, x0=x0, x1=x1)
+        desc = syn.tvl1(x1 - x0, ny, nc=3, lam=1.0, f=f)
+        step = "boyd"
+        units = nx * ny
+    elif name == "lifting_2048x2048x32":
+        nx, ny, planes, bytes_per_unit, unit = 2048, 2048, 32, 56, "pixel-label"
+        part = pbd.SlabPartition(nx, env.world, align=4)
+        x0, x1 = part.range(env.rank)
+        desc = syn.lifting(nx, ny, 32, x0=x0, x1=x1)
+        step = "boyd"
+        units = nx * ny * 32
+    elif name == "tv3d_512x512x512":
+        nx, ny, planes, bytes_per_unit, unit = 512, 512, 512, 56, "voxel"
+        part = pbd.SlabPartition(nx, env.world, align=4)
+        x0, x1 = part.range(env.rank)
+        desc = syn.tv3d(x1 - x0, ny, 512, f=syn.image(nx, ny, 512, x0=x0, x1=x1))
+        step = "alg1"
+        units = nx * ny * 512
+    else:
+        raise ValueError(name)
+    t_gen = time.perf_counter() - t0
+    prob = pb.create_problem(env.ctx, desc)
+    prob.Initialize()
+    popts = pb.pdhg_options(scale_steps_operator=0, stepsize=step, residual_iter=RESIDUAL_ITER)
+    sopts = pb.solver_options(verbose=0, max_iters=steps, tol_rel_primal=0, tol_rel_dual=0, tol_abs_primal=0,
+                              tol_abs_dual=0, num_cback_calls=0)
+    be = env.backend(prob, popts, sopts)
+    be.Initialize()
+    assert be.is_fused, f"{name}: fused PDHG path not selected"
+    be.PerformIteration(warmup)
+    launches0 = be.launch_count
+    ms = env.timed_iterations(be, steps)
+    launches = be.launch_count - launches0
+    one_pass = int(be.one_pass_iterations)
+    res = be.residuals()
+    value = steps / (ms * 1e-3)
+    peak, _ = measured_peak()
+    wmax = max(part.width(r) for r in range(env.world))
+    per_gpu_bytes = bytes_per_unit * wmax * ny * (planes if name != "tvl1_4096x4096x3" else 1)
+    ach = per_gpu_bytes * value / 1e9
+    del be, prob
+    return {"value": value, "unit": "iter/s", "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
+            "stepsize": step, "residual_iter": RESIDUAL_ITER, "n_units": units, "unit_name": unit,
+            "bytes_per_unit_algorithmic": bytes_per_unit,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "what": "whole iteration per GPU on SURVEY.md 8(d)'s algorithmic bytes"},
+            "gpu_launches": int(launches), "one_pass_iterations_total": one_pass,
+            "host_seconds_generate": t_gen, "residuals_after_run": res}
+
+
+def reference_cuda_line(syn, f, iters=(50, 350)):
+    """BASELINE.md line A and the full-size parity check in one: the UNMODIFIED reference CUDA solver
+    (oracle/_ref/prost_ref_driver, tum-vision/prost compiled for sm_100) and this library through the SAME C++
+    driver program on the metric config's 4096^2 input.  Two runs per library (iters[0] and iters[1] iterations,
+    the program's own clock around Solver::Solve(), which includes the final copy-back of x, z, y, w into pageable
+    std::vectors): the difference of the two isolates the iteration rate from that fixed cost.  Parity: max
+    relative difference of x, y, z, w after iters[1] iterations."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ref_driver
+    if not (ref_driver.available(ref_driver.REF_DRIVER) and ref_driver.available(ref_driver.OUR_DRIVER)):
+        return {"unavailable": "oracle/_ref/prost_ref_driver or prost_b200/lib/prost_b200_driver not built"}
+    desc = syn.rof(NX, NY, LAM, f=f)
+    opts = dict(stepsize="alg1", residual_iter=RESIDUAL_ITER, timeout=900)
+    out = {"workload": f"ROF-TV {NX}x{NY}, PDHG Alg1, residual_iter={RESIDUAL_ITER}, {iters[0]} and {iters[1]} iterations, the "
+                       f"same C++ driver program (oracle/driver/prost_driver.cu) linked against each library; "
+                       f"solve_ms = Solver::Solve() incl. the final copy-back of x, z, y, w"}
+    last = {}
+    for tag, binary in (("reference_sm100", ref_driver.REF_DRIVER), ("prost_b200", ref_driver.OUR_DRIVER)):
+        ms = []
+        for k in iters:
+            r = ref_driver.run_solve(desc, k, binary=binary, **opts)
+            ms.append(float(r["info"]["solve_ms"]))
+        last[tag] = r
+        out[tag] = {"solve_ms": dict(zip(map(str, iters), ms)),
+                    "iter_per_s_incl_copy_back": iters[1] / (ms[1] * 1e-3),
+                    "iter_per_s": (iters[1] - iters[0]) / max((ms[1] - ms[0]) * 1e-3, 1e-9),
+                    "residuals": r["res"]}
+    a, b = last["reference_sm100"], last["prost_b200"]
+    out["max_rel_diff"] = {k: float(np.abs(a[k] - b[k]).max() / max(float(np.abs(a[k]).max()), 1e-30))
+                           for k in ("x", "y", "z", "w")}
+    out["parity_ok"] = bool(max(out["max_rel_diff"][k] for k in ("x", "y")) <= 1e-5)
+    out["speedup_iterations"] = out["prost_b200"]["iter_per_s"] / out["reference_sm100"]["iter_per_s"]
+    return out
+
+
+def run_ours(args):
+    import numpy as np
+    env = Env(args)
+    pb, syn, pbd, torch = env.pb, env.syn, env.pbd, env.torch
+    rank, world = env.rank, env.world
+
+    part = pbd.SlabPartition(NX, world, align=4)
+    x0c, x1c = part.range(rank)
+    w = x1c - x0c
+    f = syn.image(NX, NY, x0=x0c, x1=x1c)              # this rank's columns only (counter-based RNG)
+    n, m = w * NY, 2 * w * NY
+    wmax = max(part.width(r) for r in range(world))
+
+    # ---------------- device-resident throughput (value) ----------------------------------------
     popts = pb.pdhg_options(scale_steps_operator=0, stepsize="alg1", residual_iter=RESIDUAL_ITER)
+    # num_cback_calls = 0: no intermediate callbacks, i.e. the solution is copied back once at the end
+    # (each intermediate callback of Solver::Solve is a full D2H copy of x, z, y, w: solver.cu:152-167)
     sopts = pb.solver_options(verbose=0, max_iters=args.steps, tol_rel_primal=0, tol_rel_dual=0,
                               tol_abs_primal=0, tol_abs_dual=0, num_cback_calls=0)
-    prob = pb.create_problem(ctx, syn.rof(w, NY, LAM, f=f))
+    prob = pb.create_problem(env.ctx, syn.rof(w, NY, LAM, f=f))
     prob.Initialize()
-    be = pb.BackendPDHG(ctx, prob, popts, sopts, comm=comm)
+    be = env.backend(prob, popts, sopts)
     be.Initialize()
-    assert be.is_fused
+    assert be.is_fused, "fused PDHG path not selected"
     be.PerformIteration(args.warmup)
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(env.local)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
     launches0 = be.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    dist.barrier()
-    torch.cuda.synchronize()
-    e0.record(stream)
-    be.PerformIteration(args.steps)
-    e1.record(stream)
-    torch.cuda.synchronize()
-    dist.barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1))
+    ms = env.timed_iterations(be, args.steps)
     launches = be.launch_count - launches0
     clocks = sampler.stop() if rank == 0 else None
-    value = args.steps / (ms * 1e-3) * norm
+    value = args.steps / (ms * 1e-3)
+    # slab parity carried by the run itself: checksum of the iterates after W + K iterations
+    hashes = iterate_hash(env, be, part, 1, 2)
 
-    prof_iters = min(200, max(20, args.steps // 10))
+    # ---------------- per-kernel timing for the roofline --------------------------------------------
+    # CUDA events around every launch, recorded back to back and read after ONE synchronisation at the end
+    # (pb_backend_profile_detail), single launches per iteration so that every launch has its own pair.
+    prof_iters = min(400, max(40, args.steps // 5))
     d = be.profile_detail(prof_iters)
     peak, peak_src = measured_peak()
-    wmax = max(part.width(r) for r in range(world))
+    t_tile = env.max_over_ranks(d["tile_ms"])
+    t_chk = env.max_over_ranks(d["tile_check_ms"])
+    t_primal, t_dual = env.max_over_ranks(d["primal_ms"]), env.max_over_ranks(d["dual_ms"])
     one_pass = d["n_tile"] > 0
-    fits_l2 = 28 * wmax * NY / 1e6 < 126
-    l2_note = ("per-GPU slab state fits the 126 MB L2 at this N, so the algorithmic GB/s can exceed the "
-               "HBM copy peak" if fits_l2 else "slab exceeds L2")
+    n_all = max(d["n_tile"] + d["n_two_pass"] + d["n_tile_check"], 1.0)
+    frac_tile, frac_chk, frac_two = d["n_tile"] / n_all, d["n_tile_check"] / n_all, d["n_two_pass"] / n_all
+    px_gpu = wmax * NY
     if one_pass:
-        # every iteration but the first is ONE launch of the ring kernel on the slab (pb_tile.cu, SLAB):
-        # the left-/right-edge tiles store their edge columns into the neighbours' memory over NVLink
-        t_tile, t_chk = max_over_ranks(d["tile_ms"]), max_over_ranks(d["tile_check_ms"])
-        tile_bytes = BYTES_PER_PX_TILE * wmax * NY
-        n_all = max(d["n_tile"] + d["n_two_pass"] + d["n_tile_check"], 1.0)
-        avg_px = (d["n_tile"] * BYTES_PER_PX_TILE + d["n_tile_check"] * BYTES_PER_PX_TILE_CHECK +
-                  d["n_two_pass"] * BYTES_PER_PX_ITER) / n_all
-        ach = tile_bytes / (t_tile * 1e-3) / 1e9
-        ach_iter = avg_px * wmax * NY * (args.steps / (ms * 1e-3)) / 1e9
-        roofline = {
-            "bound": "hbm", "kernel": "grad2d_iteration_ring_kernel<SQUARE, IND_LEQ0, CHECK=false, SLAB=true> (whole "
-                                      "PDHG iteration in one pass, per GPU on its slab)",
-            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-            "peak_source": peak_src, "algorithmic_bytes_per_launch": tile_bytes, "ms_per_launch": t_tile,
-            "launch_share": d["n_tile"] / n_all,
-            "residual_refresh_iterations": {"share": d["n_tile_check"] / n_all, "ms_per_launch": t_chk,
-                                            "algorithmic_bytes_per_launch": BYTES_PER_PX_TILE_CHECK * wmax * NY},
-            "whole_iteration_per_gpu": {"achieved": ach_iter, "frac": ach_iter / peak},
-            "note": l2_note + "; ms_per_launch is measured with a host synchronisation after every iteration "
-                              "(max over ranks), so it includes the launch skew between ranks that the "
-                              "back-to-back timed region hides",
-        }
+        kernel_bytes, kernel_ms = BYTES_PER_PX_TILE * px_gpu, t_tile
+        kernel_name = ("grad2d_iteration_ring_kernel<SQUARE, IND_LEQ0, CHECK=false%s> (whole PDHG iteration in one "
+                       "pass, persistent TMA ring%s)" % (", SLAB=true" if world > 1 else "",
+                                                         ", per GPU on its slab" if world > 1 else ""))
     else:
-        t_primal, t_dual = max_over_ranks(d["primal_ms"]), max_over_ranks(d["dual_ms"])
-        dual_bytes = BYTES_PER_PX_DUAL * wmax * NY
-        primal_bytes = BYTES_PER_PX_PRIMAL * wmax * NY
-        ach_dual = dual_bytes / (t_dual * 1e-3) / 1e9
-        ach_primal = primal_bytes / (t_primal * 1e-3) / 1e9
-        ach_iter = BYTES_PER_PX_ITER * wmax * NY * (args.steps / (ms * 1e-3)) / 1e9
-        roofline = {
-            "bound": "hbm", "kernel": "grad_dual_norm2_kernel (fused dual pass), per GPU on its slab",
-            "achieved": ach_dual, "peak": peak, "unit": "GB/s", "frac": ach_dual / peak, "traffic": None,
-            "peak_source": peak_src, "algorithmic_bytes_per_launch": dual_bytes, "ms_per_launch": t_dual,
-            "primal_pass": {"achieved": ach_primal, "frac": ach_primal / peak,
-                            "algorithmic_bytes_per_launch": primal_bytes, "ms_per_launch": t_primal},
-            "whole_iteration_per_gpu": {"achieved": ach_iter, "frac": ach_iter / peak},
-            "note": l2_note,
-        }
+        kernel_bytes, kernel_ms = BYTES_PER_PX_DUAL * px_gpu, t_dual
+        kernel_name = "grad_dual_norm2_kernel (fused dual pass)"
+    achieved = kernel_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms else 0.0
+    # the timed region: one residual-refresh iteration in RESIDUAL_ITER, the rest plain one-pass iterations
+    px_avg = ((RESIDUAL_ITER - 1) * BYTES_PER_PX_TILE + BYTES_PER_PX_TILE_CHECK) / RESIDUAL_ITER if one_pass \
+        else BYTES_PER_PX_TWO_PASS
+    achieved_iter = px_avg * px_gpu * value / 1e9
+    traffic, traffic_src = measured_traffic() if (one_pass and world == 1) else (None, None)
+    fits_l2 = BYTES_PER_PX_TILE * px_gpu / 1e6 < 126
+    roofline = {
+        "bound": "hbm", "kernel": kernel_name,
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": kernel_bytes, "ms_per_launch": kernel_ms,
+        "launch_share": frac_tile if one_pass else frac_two,
+        "timing": "CUDA events on the launching stream around every launch of %d profiled iterations (one launch per "
+                  "iteration), read after one synchronisation at the end; max over ranks of the per-rank means" % prof_iters,
+        "residual_refresh_iterations": {
+            "share": frac_chk, "kernel": "grad2d_iteration_ring_kernel<..., CHECK=true> (also folds the residual sums, "
+                                         "combines them across ranks and runs the step-size state machine)",
+            "ms_per_launch": t_chk, "algorithmic_bytes_per_launch": BYTES_PER_PX_TILE_CHECK * px_gpu,
+            "achieved": (BYTES_PER_PX_TILE_CHECK * px_gpu / (t_chk * 1e-3) / 1e9) if t_chk else None,
+            "frac": (BYTES_PER_PX_TILE_CHECK * px_gpu / (t_chk * 1e-3) / 1e9 / peak) if t_chk else None},
+        "two_pass_iterations": {
+            "share": frac_two,
+            "primal_pass": {"ms_per_launch": t_primal, "algorithmic_bytes_per_launch": BYTES_PER_PX_PRIMAL * px_gpu},
+            "dual_pass": {"ms_per_launch": t_dual, "algorithmic_bytes_per_launch": BYTES_PER_PX_DUAL * px_gpu},
+            "note": "iteration 0 only (K^T y := 0, K x_prev := 0 special cases)"},
+        "whole_iteration_per_gpu": {"algorithmic_bytes": px_avg * px_gpu, "achieved": achieved_iter,
+                                    "frac": achieved_iter / peak, "frac_of_8TBs_nominal": achieved_iter / 8000.0},
+        "two_pass_equivalent": {"bytes_per_pixel": BYTES_PER_PX_TWO_PASS,
+                                "achieved": BYTES_PER_PX_TWO_PASS * px_gpu * value / 1e9,
+                                "frac": BYTES_PER_PX_TWO_PASS * px_gpu * value / 1e9 / peak,
+                                "note": "the same iterations/s expressed in SURVEY.md 8(d)'s two-pass minimum; the "
+                                        "one-pass kernel does not move these bytes"},
+        "note": ("per-GPU slab state fits the 126 MB L2 at this N, so the algorithmic GB/s can exceed the HBM copy peak"
+                 if fits_l2 else "per-GPU state exceeds L2"),
+    }
     res = be.residuals()
-    p2p = comm.peer_to_peer
-    del be
+    p2p = env.comm.peer_to_peer if env.comm else None
+    del be, prob
 
-    # end to end through the public Solver API with pinned host buffers, collectively on all ranks
+    # ---------------- end to end through the public API with host buffers (e2e) --------------------
     f_pin = torch.from_numpy(f).pin_memory()
     x0_pin = torch.zeros(n, dtype=torch.float32).pin_memory()
     y0_pin = torch.zeros(m, dtype=torch.float32).pin_memory()
-    dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    prob2 = pb.create_problem(ctx, syn.rof(w, NY, LAM, f=f_pin.numpy()))
-    be2 = pb.BackendPDHG(ctx, prob2, popts, sopts, comm=comm)
-    solver = pb.Solver(prob2, be2)
-    solver.SetOptions(sopts, x0=x0_pin.numpy(), y0=y0_pin.numpy())
-    solver.Initialize()
-    solver.Solve()
-    ctx.synchronize()
-    t_e2e = max_over_ranks(time.perf_counter() - t0)
-    h2d = 4 * (n + n + m) + 4 * (n + m)
-    d2h = 4 * (2 * n + 2 * m)
-    e2e = {"value": args.steps / t_e2e * norm, "unit": "iter/s", "h2d_bytes_per_step": h2d * world / args.steps,
+    def e2e_solve(max_iters):
+        so = pb.solver_options(verbose=0, max_iters=max_iters, tol_rel_primal=0, tol_rel_dual=0,
+                               tol_abs_primal=0, tol_abs_dual=0, num_cback_calls=0)
+        env.barrier()
+        ta = time.perf_counter()
+        prob2 = pb.create_problem(env.ctx, syn.rof(w, NY, LAM, f=f_pin.numpy()))      # H2D: f (prox coefficient b)
+        be2 = env.backend(prob2, popts, so)
+        solver = pb.Solver(prob2, be2)
+        solver.SetOptions(so, x0=x0_pin.numpy(), y0=y0_pin.numpy())
+        tb = time.perf_counter()
+        solver.Initialize()                                      # x0 / y0 H2D (the scaling is built on the device)
+        env.ctx.synchronize()
+        tc = time.perf_counter()
+        solver.Solve()                                           # K iterations + D2H of x, z, y, w
+        env.ctx.synchronize()
+        td = time.perf_counter()
+        return ta, tb, tc, td
+
+    # one untimed solve of the same size first: the device-buffer cache and the pinned result pool are then warm,
+    # as they are for every solve of a process but its first
+    e2e_solve(3)
+    t0, t1, t2, t3 = e2e_solve(args.steps)
+    t_e2e = env.max_over_ranks(t3 - t0)
+    h2d = 4 * (n + n + m)                        # f, x0, y0
+    d2h = 4 * (2 * n + 2 * m)                    # x, w, y, z
+    e2e = {"value": args.steps / t_e2e, "unit": "iter/s", "h2d_bytes_per_step": h2d * world / args.steps,
            "d2h_bytes_per_step": d2h * world / args.steps, "seconds_total": t_e2e,
-           "what": "per rank: Problem build + Solver.Initialize + Solver.Solve(max_iters=K) + solution copy-back; "
-                   "max over ranks"}
-    del be2, solver
-    ttr = time_to_residual(pb, ctx, lambda: pb.create_problem(ctx, syn.rof(w, NY, LAM, f=f_pin.numpy())), comm=comm)
+           "seconds": {"problem_build_h2d": t1 - t0, "solver_initialize": t2 - t1, "solve_and_d2h": t3 - t2},
+           "what": "per rank: Problem build + Solver.Initialize + Solver.Solve(max_iters=K, num_cback_calls=0) + "
+                   "solution copy-back of x, z, y, w into pinned result vectors (library pool); max over ranks; one "
+                   "untimed 3-iteration solve of the same size ran before it (warm buffer pools)"}
+
+    # ---------------- time to residual 1e-4 (third part of the BASELINE metric) ---------------------
+    ttr = time_to_residual(env, lambda: pb.create_problem(env.ctx, syn.rof(w, NY, LAM, f=f_pin.numpy())))
+    del f_pin, x0_pin, y0_pin
+
+    # ---------------- BASELINE configs 2-4 at full size ---------------------------------------------
+    workloads = {}
+    if not args.no_workloads:
+        for name, steps, warm in (("tvl1_4096x4096x3", 100, 5), ("lifting_2048x2048x32", 60, 5),
+                                  ("tv3d_512x512x512", 60, 5)):
+            try:
+                workloads[name] = aux_workload(env, name, steps, warm)
+            except Exception as e:                                   # must not cost the metric line
+                workloads[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            pb.release_cached_memory()
+
+    # ---------------- baselines: CPU port, reference CUDA solver (rank 0) ----------------------------
+    cpu = ref_cuda = None
+    if rank == 0 and not args.no_cpu_baseline:
+        threads = host_cores()
+        rate, its, used = oracle_rate(syn, 1024, 12.0, threads)
+        cpu = {"value": rate, "unit": "iter/s", "cores": used, "kind": "port",
+               "sample": f"{its} iterations of the OpenMP oracle on a 1024x{NY} slab (1/{NX // 1024} of the image), "
+                         f"scaled by area"}
+        if world == 1:
+            try:
+                ref_cuda = reference_cuda_line(syn, f)
+            except Exception as e:
+                ref_cuda = {"error": f"{type(e).__name__}: {e}"[:300]}
+    env.barrier()
+
     if rank == 0:
         line = {
             "metric": "pdhg_iterations_per_second", "value": value, "unit": "iter/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": workload_config(world, args.scaling), "clocks": clocks, "e2e": e2e,
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": None,
-            "halo_mode": "peer-to-peer stores over NVLink (CUDA IPC)" if p2p else "NCCL send/recv staging",
-            "one_pass_iterations": bool(one_pass), "time_to_residual_1e-4": ttr,
-            "residuals_after_run": res,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(world), "clocks": clocks, "e2e": e2e,
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "reference_cuda": ref_cuda,
+            "halo_mode": (None if world == 1 else
+                          "peer-to-peer stores over NVLink (CUDA IPC)" if p2p else "NCCL send/recv staging"),
+            "one_pass_iterations": bool(one_pass), "iterate_hash": hashes,
+            "time_to_residual_1e-4": ttr, "residuals_after_run": res, "workloads": workloads,
         }
         print(json.dumps(line), flush=True)
-    comm.close()
-    dist.destroy_process_group()
+    env.close()
 
 
 def main():
@@ -355,182 +626,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
-                    help="N>1: strong = the 4096^2 image split into N column slabs (the BASELINE metric); "
-                         "weak = 4096 columns per GPU (a 4096N x 4096 image), value normalised to 4096^2 iterations")
-    ap.add_argument("--nx", type=int, default=NX, help="image columns (default 4096 = the BASELINE metric config; "
-                                                       "other values are for scaling experiments only)")
+    ap.add_argument("--no-workloads", action="store_true", help="skip BASELINE configs 2-4")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    globals()["NX"] = args.nx
-
     rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
         return
-
-    import numpy as np
-    import torch
-    import prost_b200 as pb
-    from prost_b200 import synthetic as syn
-
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        run_slab_arm(args, rank, local_rank, world)
-        return
-
-    # a dedicated (non-default) stream: the context launches on it and the CUDA events below are
-    # recorded on it, so the events bracket exactly the kernels of the timed region
-    stream = torch.cuda.Stream()
-    torch.cuda.set_stream(stream)
-    assert stream.cuda_stream != 0
-    ctx = pb.Context(local_rank, stream.cuda_stream)
-
-    f = syn.image(NX, NY)
-    n, m = NX * NY, 2 * NX * NY
-
-    # ---------------- device-resident throughput (value) ----------------------------------------
-    prob = build_problem(pb, syn, ctx, f)
-    prob.Initialize()
-    popts = pb.pdhg_options(scale_steps_operator=0, stepsize="alg1", residual_iter=RESIDUAL_ITER)
-    # num_cback_calls = 0: no intermediate callbacks, i.e. the solution is copied back once at the end
-    # (each intermediate callback of Solver::Solve is a full D2H copy of x, z, y, w: solver.cu:152-167)
-    sopts = pb.solver_options(verbose=0, max_iters=args.steps, tol_rel_primal=0, tol_rel_dual=0,
-                              tol_abs_primal=0, tol_abs_dual=0, num_cback_calls=0)
-    be = pb.BackendPDHG(ctx, prob, popts, sopts)
-    be.Initialize()
-    assert be.is_fused, "fused PDHG path not selected"
-    be.PerformIteration(args.warmup)
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.3)
-    launches0 = be.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record(stream)
-    be.PerformIteration(args.steps)
-    e1.record(stream)
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    launches = be.launch_count - launches0
-    clocks = sampler.stop()
-    value = args.steps / (ms * 1e-3)
-
-    # ---------------- per-kernel timing for the roofline (events around each kernel) ----------------
-    # Iterations that refresh the residuals (1 in RESIDUAL_ITER) run as two passes (44 B/px + the
-    # previous dual iterate), all others as ONE tiled kernel that moves 28 B/px (pb_tile.cu): read
-    # y (2 floats), x, f; write x+, y+ (2 floats).  The dominant kernel is the tiled one.
-    prof_iters = min(400, max(40, args.steps // 5))
-    d = be.profile_detail(prof_iters)
-    peak, peak_src = measured_peak()
-    tiled = d["n_tile"] > 0
-    if tiled:
-        kernel_bytes = BYTES_PER_PX_TILE * n
-        kernel_ms = d["tile_ms"]
-        kernel_name = ("grad2d_iteration_ring_kernel<SQUARE, IND_LEQ0, CHECK=false> (whole PDHG iteration in one "
-                       "pass, persistent TMA ring)")
-    else:
-        kernel_bytes = BYTES_PER_PX_DUAL * n
-        kernel_ms = d["dual_ms"]
-        kernel_name = "grad_dual_norm2_kernel (fused dual pass)"
-    achieved = kernel_bytes / (kernel_ms * 1e-3) / 1e9
-    n_all = max(d["n_tile"] + d["n_two_pass"] + d["n_tile_check"], 1.0)
-    frac_tile, frac_chk, frac_two = d["n_tile"] / n_all, d["n_tile_check"] / n_all, d["n_two_pass"] / n_all
-    iter_bytes = (frac_tile * BYTES_PER_PX_TILE + frac_chk * BYTES_PER_PX_TILE_CHECK + frac_two * BYTES_PER_PX_ITER) * n
-    achieved_iter = iter_bytes * value / 1e9
-    roofline = {
-        "bound": "hbm", "kernel": kernel_name,
-        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel, ncu --set full capture
-        # committed as profiles/r01_tile_ring_full_raw.csv (268.5 + 160.5 MB: part of the previous
-        # iteration's output is still in the 126 MB L2, so less than the algorithmic 469.8 MB)
-        "traffic": 428923648 if tiled else None, "peak_source": peak_src,
-        "algorithmic_bytes_per_launch": kernel_bytes, "ms_per_launch": kernel_ms,
-        "launch_share": frac_tile if tiled else frac_two,
-        "residual_refresh_iterations": {
-            "share": frac_chk, "kernel": "grad2d_iteration_ring_kernel<..., CHECK=true>",
-            "ms_per_launch": d["tile_check_ms"], "algorithmic_bytes_per_launch": BYTES_PER_PX_TILE_CHECK * n,
-            "achieved": (BYTES_PER_PX_TILE_CHECK * n / (d["tile_check_ms"] * 1e-3) / 1e9) if d["tile_check_ms"] else None,
-            "note": "1 in residual_iter iterations: the same pass also reads the previous dual iterate and "
-                    "accumulates the four residual sums; included in value"},
-        "two_pass_iterations": {
-            "share": frac_two,
-            "primal_pass": {"ms_per_launch": d["primal_ms"], "algorithmic_bytes_per_launch": BYTES_PER_PX_PRIMAL * n},
-            "dual_pass": {"ms_per_launch": d["dual_ms"], "algorithmic_bytes_per_launch": BYTES_PER_PX_DUAL * n},
-            "note": "iteration 0 only (K^T y := 0, K x_prev := 0 special cases)"},
-        "whole_iteration": {"algorithmic_bytes": iter_bytes, "achieved": achieved_iter, "frac": achieved_iter / peak,
-                            "frac_of_8TBs_nominal": achieved_iter / 8000.0},
-        # the same iterations/s expressed against SURVEY.md 8(d)'s two-pass minimum of 44 B/px
-        "equivalent_at_44B_per_px": {"achieved": BYTES_PER_PX_ITER * n * value / 1e9,
-                                     "frac": BYTES_PER_PX_ITER * n * value / 1e9 / peak},
-        "finalize_ms": d["finalize_ms"],
-    }
-    res = be.residuals()
-    del be
-
-    # ---------------- end to end through the public API with host buffers (e2e) --------------------
-    f_pin = torch.from_numpy(f).pin_memory()
-    x0_pin = torch.zeros(n, dtype=torch.float32).pin_memory()
-    y0_pin = torch.zeros(m, dtype=torch.float32).pin_memory()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    prob2 = build_problem(pb, syn, ctx, f_pin.numpy())           # H2D: f (prox coefficient b)
-    be2 = pb.BackendPDHG(ctx, prob2, popts, sopts)
-    solver = pb.Solver(prob2, be2)
-    solver.SetOptions(sopts, x0=x0_pin.numpy(), y0=y0_pin.numpy())
-    t1 = time.perf_counter()
-    solver.Initialize()                                          # scaling upload, x0 / y0 H2D
-    ctx.synchronize()
-    t2 = time.perf_counter()
-    solver.Solve()                                               # K iterations + D2H of x, z, y, w
-    ctx.synchronize()
-    t3 = time.perf_counter()
-    t_e2e = t3 - t0
-    h2d = 4 * (n + n + m) + 4 * (n + m)          # f, x0 (x2 buffers share one upload each), y0, scaling
-    d2h = 4 * (2 * n + 2 * m)                    # x, w, y, z
-    e2e = {"value": args.steps / t_e2e, "unit": "iter/s", "h2d_bytes_per_step": h2d / args.steps,
-           "d2h_bytes_per_step": d2h / args.steps, "seconds_total": t_e2e,
-           "seconds": {"problem_build_h2d": t1 - t0, "solver_initialize": t2 - t1, "solve_and_d2h": t3 - t2},
-           "what": "Problem build + Solver.Initialize + Solver.Solve(max_iters=K, num_cback_calls=0) + solution "
-                   "copy-back of x, z, y, w"}
-    del be2, solver
-
-    # ---------------- time to residual 1e-4 (third part of the BASELINE metric) ---------------------
-    ttr = time_to_residual(pb, ctx, lambda: build_problem(pb, syn, ctx, f_pin.numpy()))
-
-    # ---------------- CPU baseline (oracle port, bounded sample) ------------------------------------
-    cpu = None
-    if not args.no_cpu_baseline:
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        from oracle_binding import OracleProblem, OraclePDHG, num_threads
-        cols = 1024
-        o = OraclePDHG(OracleProblem(syn.rof(cols, NY, LAM)), stepsize="alg1", residual_iter=RESIDUAL_ITER,
-                       tol_rel_primal=0, tol_rel_dual=0, tol_abs_primal=0, tol_abs_dual=0)
-        o.initialize()
-        o.iterate(2)
-        t0 = time.perf_counter()
-        its = 0
-        while time.perf_counter() - t0 < 12.0:
-            o.iterate(5)
-            its += 5
-        dt = time.perf_counter() - t0
-        cpu = {"value": its / dt * cols / NX, "unit": "iter/s", "cores": num_threads(), "kind": "port",
-               "sample": f"{its} iterations of the OpenMP oracle on a {cols}x{NY} slab (1/{NX // cols} of the "
-                         f"image), scaled by area"}
-
-    line = {
-        "metric": "pdhg_iterations_per_second", "value": value, "unit": "iter/s", "n_gpus": 1,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload_config(1), "clocks": clocks, "e2e": e2e,
-        "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-        "time_to_residual_1e-4": ttr, "residuals_after_run": res,
-    }
-    print(json.dumps(line), flush=True)
+    run_ours(args)
 
 
 if __name__ == "__main__":

@@ -72,6 +72,11 @@ int pb_context_device(pb_context* ctx);
 
 /* device memory helpers for callers that hold device vectors (reference: thrust::device_vector) */
 int pb_malloc(pb_context* ctx, size_t bytes, void** d_out);
+/* Pinned (page-locked) host memory for iterates and results: buffers from here are read / written by ONE DMA, where
+ * the reference's std::vector results (solver.cu:152-167) are pageable.  Freed blocks are kept for exact-size
+ * reuse (PB_HOST_POOL_MB, default 4096) until pb_release_cached_memory(). */
+int pb_host_alloc(size_t bytes, void** h_out);
+void pb_host_free(void* h_ptr);
 int pb_free(pb_context* ctx, void* d_ptr);
 int pb_memcpy_h2d(pb_context* ctx, void* d_dst, const void* h_src, size_t bytes);
 int pb_memcpy_d2h(pb_context* ctx, void* h_dst, const void* d_src, size_t bytes);
@@ -175,6 +180,13 @@ int pb_prox_create_ind_simplex(pb_context* ctx, size_t index, size_t count, size
  * (elem_operation_ind_sum.hpp:38-58; mex name "elem_operation:ind_sum", +function/sum_ind_sum.m) */
 int pb_prox_create_ind_sum(pb_context* ctx, size_t index, size_t count, size_t dim, int interleaved,
                            int diagsteps, pb_prox** out);
+/* ProxIndSum(index,size,count,dim,inds,sum[,count2,dim2,inds2,sum2]) (prox_ind_sum.hpp:37-62, prox_ind_sum.cu:33-145;
+ * mex name "ind_sum", +function/sum_ind_sum2.m): groups given as index lists (count*dim entries relative to `index`,
+ * group-major) are projected onto sum = `sum` in the metric of the step sizes; all other elements are copied.
+ * h_inds2 == NULL: one list.  diagsteps is always true. */
+int pb_prox_create_ind_sum_indexed(pb_context* ctx, size_t index, size_t size, size_t count, size_t dim,
+                                   const unsigned long long* h_inds, float sum, size_t count2, size_t dim2,
+                                   const unsigned long long* h_inds2, float sum2, pb_prox** out);
 /* ProxIndHalfspace(index,count,dim,interleaved,diagsteps,a,b): projection onto <a, x> <= b per group; a has
  * count*dim (planar) or dim entries, b count or 1 (prox_ind_halfspace.hpp:41-52, prox_ind_halfspace.cu:34-137) */
 int pb_prox_create_ind_halfspace(pb_context* ctx, size_t index, size_t count, size_t dim, int interleaved,

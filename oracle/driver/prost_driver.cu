@@ -25,6 +25,7 @@
 //           | simplex <idx> <count> <dim> <interleaved> <diagsteps>
 //           | indsum <idx> <count> <dim> <interleaved> <diagsteps>
 //           | halfspace <idx> <count> <dim> <interleaved> <diagsteps> <a> <b>
+//           | indsumidx <idx> <size> <n_lists: 1|2> { <dim> <inds file (u64)> <n_inds> <sum> } x n_lists
 //           | soc <idx> <count> <dim> <interleaved> <diagsteps> <alpha>
 //           | epiquad <idx> <count> <dim> <interleaved> <diagsteps> <a> <b> <c>
 //           | moreau <PROX> | permute <perm.i32> <n> <PROX> | zero <idx> <size>
@@ -74,6 +75,7 @@
 #include "prost/prox/prox_ind_epi_quad.hpp"
 #include "prost/prox/prox_moreau.hpp"
 #include "prost/prox/prox_ind_halfspace.hpp"
+#include "prost/prox/prox_ind_sum.hpp"
 #include "prost/prox/prox_ind_soc.hpp"
 #include "prost/prox/prox_transform.hpp"
 #include "prost/prox/prox_permute.hpp"
@@ -160,6 +162,26 @@ static std::shared_ptr<Prox<real>> parse_prox(std::istringstream& in) {
     in >> idx >> count >> dim >> il >> ds;
     return std::shared_ptr<Prox<real>>(
         new ProxElemOperation<real, ElemOperationIndSimplex<real>>(idx, count, dim, il, ds));
+  }
+  if (kind == "indsumidx") {
+    size_t idx, size;
+    int lists;
+    in >> idx >> size >> lists;
+    size_t dim[2] = {0, 0}, n[2] = {0, 0};
+    double total[2] = {0, 0};
+    std::vector<size_t> inds[2];
+    for (int l = 0; l < lists && l < 2; ++l) {
+      std::string file;
+      in >> dim[l] >> file >> n[l] >> total[l];
+      const std::vector<unsigned long long> raw = read_file<unsigned long long>(file, n[l]);
+      inds[l].assign(raw.begin(), raw.end());
+    }
+    if (lists == 1)
+      return std::shared_ptr<Prox<real>>(
+          new ProxIndSum<real>(idx, size, n[0] / dim[0], dim[0], inds[0], static_cast<real>(total[0])));
+    return std::shared_ptr<Prox<real>>(new ProxIndSum<real>(idx, size, n[0] / dim[0], dim[0], inds[0],
+                                                            static_cast<real>(total[0]), n[1] / dim[1], dim[1], inds[1],
+                                                            static_cast<real>(total[1])));
   }
   if (kind == "halfspace") {
     size_t idx, count, dim;

@@ -559,6 +559,45 @@ struct ProxIndHalfspace : ProxSeparable {   // prox_ind_halfspace.cu:34-92: { x 
   }
 };
 
+// ProxIndSum (prox_ind_sum.cu:33-145, prox_ind_sum.hpp:37-62): index-list groups; the zero prox elsewhere; the
+// second list's launch is sized by the FIRST list's group count (:135), so only its first
+// ceil(count / 256) * 256 groups are ever projected.
+struct ProxIndSumIndexed : Prox {
+  size_t count[2], dim[2];
+  std::vector<size_t> inds[2];
+  float total[2];
+  bool two;
+  ProxIndSumIndexed(size_t i, size_t s, size_t c, size_t d, const unsigned long long* in, float t, size_t c2, size_t d2,
+                    const unsigned long long* in2, float t2)
+      : Prox(i, s, true), two(in2 != nullptr) {
+    count[0] = c; dim[0] = d; total[0] = t; inds[0].assign(in, in + c * d);
+    count[1] = c2; dim[1] = d2; total[1] = t2;
+    if (two) inds[1].assign(in2, in2 + c2 * d2);
+  }
+  void eval_local(float* res, const float* arg, const float* td, float tau, bool invert) override {
+    std::copy(arg, arg + size, res);                                             // :113-115
+    for (int l = 0; l < (two ? 2 : 1); ++l) {
+      const size_t n_run = l == 0 ? count[0] : std::min(count[1], (count[0] + 255) / 256 * 256);
+      const std::vector<size_t>& ix = inds[l];
+      const size_t d = dim[l];
+      for (size_t tx = 0; tx < n_run; ++tx) {                                    // ProxIndSumKernel :47-67
+        float sum_arg = 0, sum_tau = 0;
+        for (size_t k = 0; k < d; ++k) {
+          float mytau = td[ix[tx * d + k]] * tau;
+          if (invert) mytau = static_cast<float>(1. / mytau);
+          sum_arg += arg[ix[tx * d + k]];
+          sum_tau += mytau;
+        }
+        for (size_t k = 0; k < d; ++k) {
+          float mytau = td[ix[tx * d + k]] * tau;
+          if (invert) mytau = static_cast<float>(1. / mytau);
+          res[ix[tx * d + k]] = arg[ix[tx * d + k]] - mytau * (sum_arg - total[l]) / sum_tau;
+        }
+      }
+    }
+  }
+};
+
 struct ProxIndSOC : ProxSeparable {         // prox_ind_soc.cu:33-77: { (x, y) | |x|_2 <= y }, alpha = 1 only
   ProxIndSOC(size_t i, size_t c, size_t d, bool il, bool ds) : ProxSeparable(i, c, d, il, ds) {}
   void eval_local(float* res, const float* arg, const float*, float, bool) override {
@@ -1089,6 +1128,10 @@ int orc_prox_ind_sum(void* p, size_t idx, size_t count, size_t dim, int il, int 
 int orc_prox_ind_halfspace(void* p, size_t idx, size_t count, size_t dim, int il, int ds, const float* a, size_t na,
                            const float* b, size_t nb) {
   return push(PP, std::make_shared<ProxIndHalfspace>(idx, count, dim, il != 0, ds != 0, a, na, b, nb));
+}
+int orc_prox_ind_sum_indexed(void* p, size_t idx, size_t size, size_t count, size_t dim, const unsigned long long* inds,
+                             float total, size_t count2, size_t dim2, const unsigned long long* inds2, float total2) {
+  return push(PP, std::make_shared<ProxIndSumIndexed>(idx, size, count, dim, inds, total, count2, dim2, inds2, total2));
 }
 int orc_prox_ind_soc(void* p, size_t idx, size_t count, size_t dim, int il, int ds) {
   return push(PP, std::make_shared<ProxIndSOC>(idx, count, dim, il != 0, ds != 0));

@@ -77,6 +77,8 @@ SIGNATURES = {
     "pb_release_cached_memory": (None, []),
     "pb_context_stream": (C.c_void_p, [handle]),
     "pb_context_device": (C.c_int, [handle]),
+    "pb_host_alloc": (C.c_int, [C.c_size_t, handle_p]),
+    "pb_host_free": (None, [handle]),
     "pb_malloc": (C.c_int, [handle, C.c_size_t, handle_p]),
     "pb_free": (C.c_int, [handle, C.c_void_p]),
     "pb_memcpy_h2d": (C.c_int, [handle, C.c_void_p, C.c_void_p, C.c_size_t]),
@@ -122,6 +124,9 @@ SIGNATURES = {
     "pb_prox_create_ind_simplex": (C.c_int, [handle, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int,
                                              handle_p]),
     "pb_prox_create_ind_sum": (C.c_int, [handle, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int, handle_p]),
+    "pb_prox_create_ind_sum_indexed": (C.c_int, [handle, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t,
+                                                 C.POINTER(C.c_ulonglong), C.c_float, C.c_size_t, C.c_size_t,
+                                                 C.POINTER(C.c_ulonglong), C.c_float, handle_p]),
     "pb_prox_create_ind_halfspace": (C.c_int, [handle, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int,
                                                c_float_p, C.c_size_t, c_float_p, C.c_size_t, handle_p]),
     "pb_prox_create_ind_soc": (C.c_int, [handle, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_float,

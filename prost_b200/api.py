@@ -6,6 +6,7 @@ Initialize``, ``Solver.Initialize / Solve``, ``LinearOperator.Eval / EvalAdjoint
 This module is plumbing only: all arithmetic happens in ``libprost_b200.so`` on the GPU.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -22,6 +23,28 @@ def _f32(a):
 
 def _fp(a):
     return a.ctypes.data_as(_capi.c_float_p)
+
+
+class _PinnedBlock:
+    """One block of the library's pinned-host pool (pb_host_alloc); goes back to the pool when collected."""
+
+    def __init__(self, nbytes):
+        self.ptr = C.c_void_p()
+        check(lib.pb_host_alloc(int(nbytes), C.byref(self.ptr)))
+
+    def __del__(self):
+        if getattr(self, "ptr", None) and self.ptr.value and lib is not None:
+            lib.pb_host_free(self.ptr)
+            self.ptr = C.c_void_p()
+
+
+def pinned_empty(n, dtype=np.float32):
+    """float32 vector of n elements in pinned host memory; the array keeps its block alive."""
+    dt = np.dtype(dtype)
+    blk = _PinnedBlock(max(int(n), 1) * dt.itemsize)
+    raw = (C.c_char * (max(int(n), 1) * dt.itemsize)).from_address(blk.ptr.value)
+    raw._owner = blk
+    return np.frombuffer(raw, dtype=dt, count=int(n))
 
 
 def function_id(name):
@@ -350,6 +373,24 @@ class ProxElemOperationIndSum(Prox):
                                          C.byref(self._h)))
 
 
+class ProxIndSum(Prox):
+    """ProxIndSum<T>(index, size, count, dim, inds, sum[, count2, dim2, inds2, sum2]) (prox_ind_sum.hpp:37-62):
+    index-list groups projected onto sum = ``sum`` in the metric of the step sizes; count = len(inds) / dim like in
+    the mex factory (factory.cpp:459-481)."""
+
+    def __init__(self, ctx, index, size, dim, inds, total, dim2=None, inds2=None, total2=0.0):
+        super().__init__(ctx)
+        u64p = C.POINTER(C.c_ulonglong)
+        a = np.ascontiguousarray(np.asarray(inds, dtype=np.uint64).ravel())
+        two = inds2 is not None
+        b = np.ascontiguousarray(np.asarray(inds2 if two else [], dtype=np.uint64).ravel())
+        d2 = int(dim2) if two else 0
+        check(lib.pb_prox_create_ind_sum_indexed(
+            ctx._h, index, size, a.size // int(dim), int(dim), a.ctypes.data_as(u64p), float(total),
+            (b.size // d2) if two and d2 else 0, d2, b.ctypes.data_as(u64p) if two else None, float(total2),
+            C.byref(self._h)))
+
+
 class ProxIndHalfspace(Prox):
     """ProxIndHalfspace<T>(index, count, dim, interleaved, diagsteps, a, b): projection onto <a, x> <= b."""
 
@@ -639,8 +680,11 @@ class Solver:
 
     def Solve(self):
         n, m = self.problem.ncols, self.problem.nrows
-        x, w = np.empty(n, np.float32), np.empty(n, np.float32)
-        y, z = np.empty(m, np.float32), np.empty(m, np.float32)
+        # result vectors in pinned memory (pool with exact-size reuse): one DMA each instead of a staged copy
+        # into cold pageable pages; PB_PINNED_RESULTS=0 gives plain numpy arrays like the reference's std::vector
+        alloc = np.empty if os.environ.get("PB_PINNED_RESULTS", "1") == "0" else pinned_empty
+        x, w = alloc(n, np.float32), alloc(n, np.float32)
+        y, z = alloc(m, np.float32), alloc(m, np.float32)
 
         def stop(_user):
             return int(bool(self._stop())) if self._stop else 0

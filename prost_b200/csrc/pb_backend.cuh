@@ -114,6 +114,9 @@ class Backend {
     const unsigned long long mod = static_cast<unsigned long long>(static_cast<long long>(residual_iter()));
     return it_before == 0 || (it_before % mod) == 0;
   }
+  // may iterate(n) put several iterations into one launch?  (the solver loop then enqueues whole stretches
+  // between two observable events with one call)
+  virtual bool batches_iterations() const { return false; }
   // slab decomposition (pb_comm.cuh); must be called before initialize()
   virtual void set_slab(class Comm*) { fail(PB_ERR_UNSUPPORTED, "this backend has no slab decomposition"); }
 

@@ -114,6 +114,10 @@ int pb_context_synchronize(pb_context* c) {
 void* pb_context_stream(pb_context* c) { return c ? static_cast<void*>(c->ctx.stream) : nullptr; }
 int pb_context_device(pb_context* c) { return c ? c->ctx.device : -1; }
 
+int pb_host_alloc(size_t bytes, void** h_out) {
+  return guarded([&] { require(h_out != nullptr, "pb_host_alloc: NULL argument"); *h_out = pb::host_pool_alloc(bytes); });
+}
+void pb_host_free(void* p) { pb::host_pool_free(p); }
 int pb_malloc(pb_context* c, size_t bytes, void** d_out) {
   return guarded([&] {
     require(c && d_out, "pb_malloc: NULL argument");
@@ -326,6 +330,11 @@ int pb_prox_create_ind_simplex(pb_context* c, size_t index, size_t count, size_t
 int pb_prox_create_ind_sum(pb_context* c, size_t index, size_t count, size_t dim, int interleaved, int diagsteps,
                            pb_prox** out) {
   PB_MAKE_PROX(pb::make_prox_ind_sum(&c->ctx, index, count, dim, interleaved != 0, diagsteps != 0));
+}
+int pb_prox_create_ind_sum_indexed(pb_context* c, size_t index, size_t size, size_t count, size_t dim,
+                                   const unsigned long long* inds, float sum, size_t count2, size_t dim2,
+                                   const unsigned long long* inds2, float sum2, pb_prox** out) {
+  PB_MAKE_PROX(pb::make_prox_ind_sum_indexed(&c->ctx, index, size, count, dim, inds, sum, count2, dim2, inds2, sum2));
 }
 int pb_prox_create_ind_halfspace(pb_context* c, size_t index, size_t count, size_t dim, int interleaved, int diagsteps,
                                  const float* a, size_t na, const float* b, size_t nb, pb_prox** out) {
@@ -628,11 +637,11 @@ int pb_solver_solve(pb_backend* b, const pb_solver_options* so, pb_stopping_cb s
     int result = PB_STOPPED_MAX_ITERS;
     int iters = 0;
     float res[6] = {0, 0, 0, 0, 0, 0};
-    // Experimental (PB_RING_ITERS > 1): without a stopping callback nothing observable happens between two
-    // "events" (residual refresh, intermediate callback, last iteration) -- the cached residuals the reference
-    // compares every iteration (solver.cu:141-150) do not change -- so such a stretch is enqueued with one
-    // iterate() call, which lets the backend put several iterations into one launch.
-    static const bool batch = [] { const char* e = getenv("PB_RING_ITERS"); return e && atoi(e) > 1; }();
+    // Without a stopping callback nothing observable happens between two "events" (residual refresh,
+    // intermediate callback, last iteration) -- the cached residuals the reference compares every iteration
+    // (solver.cu:141-150) do not change -- so such a stretch is enqueued with one iterate() call, which lets the
+    // backend put several iterations into one launch (persistent ring, pb_tile.cu RingMulti).
+    const bool batch = be->batches_iterations();
     for (int i = 0; i < so->max_iters; ++i) {
       size_t it_before = be->iteration();
       int run = 1;

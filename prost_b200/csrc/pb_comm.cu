@@ -67,8 +67,14 @@ NcclApi& nccl() {
 
 inline ncclComm_t as_comm(void* p) { return static_cast<ncclComm_t>(p); }
 
-constexpr size_t kFlagBytes = 256;   // HaloFlags padded so that the float slots stay 16-byte aligned
-static_assert(sizeof(HaloFlags) <= kFlagBytes, "HaloFlags must fit its header");
+// header of the IPC block: HaloFlags | reduce sequence words (offset 256) | reduce slots (offset 512);
+// padded so that the float slots behind it stay 16-byte aligned
+constexpr size_t kFlagBytes = 2048;
+constexpr size_t kRedFlagOff = 256, kRedSlotOff = 512;
+constexpr int kRedRanks = 8;         // == kMaxReduceRanks (pb_stencil.cuh)
+static_assert(sizeof(HaloFlags) <= kRedFlagOff, "HaloFlags must fit its header");
+static_assert(kRedFlagOff + kRedRanks * sizeof(unsigned) <= kRedSlotOff, "reduce flags");
+static_assert(kRedSlotOff + 2 * kRedRanks * 4 * sizeof(double) <= kFlagBytes, "reduce slots");
 
 }  // namespace
 
@@ -101,8 +107,9 @@ Comm::~Comm() {
 }
 
 void Comm::release_halo() {
-  if (left_block_) cudaIpcCloseMemHandle(left_block_);
-  if (right_block_) cudaIpcCloseMemHandle(right_block_);
+  for (int r = 0; r < (int)peer_blocks_.size(); ++r)
+    if (r != rank_ && peer_blocks_[r]) cudaIpcCloseMemHandle(peer_blocks_[r]);
+  peer_blocks_.clear();
   left_block_ = right_block_ = nullptr;
   if (block_) cudaFree(block_);
   block_ = nullptr;
@@ -129,7 +136,7 @@ void Comm::ensure_halo(size_t col_floats) {
     barrier();
     PB_CUDA(cudaMemsetAsync(block_, 0, kFlagBytes, s));
     PB_CUDA(cudaStreamSynchronize(s));
-    x_seq = y_seq = 0;
+    x_seq = y_seq = red_seq = 0;
     barrier();
     return;
   }
@@ -137,7 +144,7 @@ void Comm::ensure_halo(size_t col_floats) {
   barrier();                       // nobody still reads a block that is about to be unmapped
   release_halo();
   col_floats_ = col_floats;
-  x_seq = y_seq = 0;
+  x_seq = y_seq = red_seq = 0;
   const size_t bytes = kFlagBytes + 4 * col_floats * sizeof(float);
   PB_CUDA(cudaMalloc(&block_, bytes));
   PB_CUDA(cudaMemsetAsync(block_, 0, bytes, s));
@@ -162,14 +169,17 @@ void Comm::ensure_halo(size_t col_floats) {
     std::vector<cudaIpcMemHandle_t> all(world_);
     PB_CUDA(cudaMemcpyAsync(all.data(), d_all.data(), sizeof(mine) * world_, cudaMemcpyDeviceToHost, s));
     PB_CUDA(cudaStreamSynchronize(s));
-    if (ok && has_left() &&
-        cudaIpcOpenMemHandle(&left_block_, all[rank_ - 1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-      cudaGetLastError(); left_block_ = nullptr; ok = 0;
+    // every rank's block: the neighbours' carry the stencil halos, all of them the residual-sum slots
+    peer_blocks_.assign(world_, nullptr);
+    peer_blocks_[rank_] = block_;
+    for (int r = 0; ok && r < world_; ++r) {
+      if (r == rank_) continue;
+      if (cudaIpcOpenMemHandle(&peer_blocks_[r], all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError(); peer_blocks_[r] = nullptr; ok = 0;
+      }
     }
-    if (ok && has_right() &&
-        cudaIpcOpenMemHandle(&right_block_, all[rank_ + 1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-      cudaGetLastError(); right_block_ = nullptr; ok = 0;
-    }
+    if (ok && has_left()) left_block_ = peer_blocks_[rank_ - 1];
+    if (ok && has_right()) right_block_ = peer_blocks_[rank_ + 1];
   }
   // p2p only if EVERY rank could map its neighbours; otherwise all ranks fall back to staging
   double okd[1] = {ok ? 0.0 : 1.0};
@@ -177,8 +187,9 @@ void Comm::ensure_halo(size_t col_floats) {
   if (okd[0] != 0.0 || world_ == 1) {
     if (p2p_ && world_ > 1 && rank_ == 0)
       std::fprintf(stderr, "prost_b200: CUDA IPC halo mapping unavailable, using NCCL send/recv staging\n");
-    if (left_block_) cudaIpcCloseMemHandle(left_block_);
-    if (right_block_) cudaIpcCloseMemHandle(right_block_);
+    for (int r = 0; r < (int)peer_blocks_.size(); ++r)
+      if (r != rank_ && peer_blocks_[r]) cudaIpcCloseMemHandle(peer_blocks_[r]);
+    peer_blocks_.clear();
     left_block_ = right_block_ = nullptr;
     p2p_ = false;
   }
@@ -204,6 +215,22 @@ unsigned* Comm::left_x_seq() const {
 }
 unsigned* Comm::right_y_seq() const {
   return (p2p_ && right_block_) ? &static_cast<HaloFlags*>(right_block_)->y_seq : nullptr;
+}
+
+bool Comm::reduce_p2p() const {
+  return p2p_ && world_ > 1 && world_ <= kRedRanks && (int)peer_blocks_.size() == world_;
+}
+const double* Comm::red_in() const {
+  return reinterpret_cast<const double*>(static_cast<char*>(block_) + kRedSlotOff);
+}
+const unsigned* Comm::red_flag_in() const {
+  return reinterpret_cast<const unsigned*>(static_cast<char*>(block_) + kRedFlagOff);
+}
+double* Comm::red_out(int r) const {
+  return reinterpret_cast<double*>(static_cast<char*>(peer_blocks_[r]) + kRedSlotOff);
+}
+unsigned* Comm::red_flag_out(int r) const {
+  return reinterpret_cast<unsigned*>(static_cast<char*>(peer_blocks_[r]) + kRedFlagOff);
 }
 
 void Comm::exchange_x(unsigned seq) {

@@ -75,6 +75,15 @@ class Comm {
   // throws if a kernel reported a halo timeout
   void check_error();
 
+  // --- in-kernel sum over ranks (RingFinish, pb_stencil.cuh): every rank's block carries
+  // [2][kMaxReduceRanks][4] double slots + one sequence word per writer; all blocks are peer-mapped
+  bool reduce_p2p() const;                    // p2p mode, world <= kMaxReduceRanks, every block mapped
+  const double* red_in() const;               // local slots
+  const unsigned* red_flag_in() const;        // local sequence words
+  double* red_out(int r) const;               // rank r's slots (own block for r == rank)
+  unsigned* red_flag_out(int r) const;
+  unsigned red_seq = 0;                       // identical on every rank
+
  private:
   void release_halo();
   Context* ctx_;
@@ -89,6 +98,7 @@ class Comm {
   float* y_in_ = nullptr;
   void* left_block_ = nullptr;         // neighbours' blocks mapped into this process (p2p)
   void* right_block_ = nullptr;
+  std::vector<void*> peer_blocks_;     // every rank's block (own: block_), p2p only
   DeviceBuffer<float> stage_x_, stage_y_;   // staging mode
   DeviceBuffer<double> scratch_;
 };

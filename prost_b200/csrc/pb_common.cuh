@@ -109,6 +109,9 @@ struct TraceScope {
 void* device_alloc(size_t bytes);                  // throws Error(PB_ERR_OOM / PB_ERR_CUDA)
 void device_free(void* p, size_t bytes, int device);
 void device_cache_release();
+// pinned host blocks with exact-size reuse (pb_hostio.cu)
+void* host_pool_alloc(size_t bytes);
+void host_pool_free(void* p);
 
 // RAII device allocation (replaces thrust::device_vector members of the reference).
 template <typename T>

@@ -193,6 +193,9 @@ __global__ void __launch_bounds__(kBlock) z_variable_kernel(float* __restrict__ 
 
 // ---- backend -------------------------------------------------------------------------------------
 
+// default number of iterations per persistent-ring launch on ONE GPU (0: one launch per iteration)
+constexpr int kRingItersSingleGpu = 0;
+
 class BackendPDHG : public Backend {
  public:
   BackendPDHG(Context* ctx, std::shared_ptr<Problem> prob, const pb_pdhg_options& opts,
@@ -220,6 +223,7 @@ class BackendPDHG : public Backend {
   unsigned long long one_pass_iterations() const override { return tile_iterations_; }
   void device_iterates(float** d_x, float** d_y) override { *d_x = x_.data(); *d_y = y_.data(); }
   int residual_iter() const override { return opts_.residual_iter; }
+  bool batches_iterations() const override { return fused_ && tile_ok_ && ring_iters_ > 1; }
   void set_slab(Comm* comm) override { comm_ = comm; }
 
  private:
@@ -236,6 +240,8 @@ class BackendPDHG : public Backend {
   int ring_iters_ = 0;
   unsigned ring_base_ = 0;
   DeviceBuffer<unsigned> ring_done_, ring_edge_counters_;
+  DeviceBuffer<unsigned> fin_ticket_;        // RingFinish: CTAs of the running residual-refresh launch that are done
+  RingFinish ring_finish();                  // advances comm_->red_seq on slabs
   DeviceBuffer<int> ring_error_;
   void slab_apply(float* d_res, const float* d_rhs, const float* d_halo, bool adjoint);
   Comm* comm_ = nullptr;
@@ -406,8 +412,12 @@ void BackendPDHG::initialize(const float* h_x0, size_t nx0, const float* h_y0, s
   }
   tile_iterations_ = 0;
   {
-    static const int ring_iters = [] { const char* e = getenv("PB_RING_ITERS"); return e ? atoi(e) : 0; }();
-    ring_iters_ = std::min(ring_iters, 32);
+    // Iterations per launch of the persistent ring (RingMulti): on slabs the kernel boundary (launch latency,
+    // pipeline prologue / tail, rank skew) costs more than the slab's HBM time, so stretches of non-refresh
+    // iterations run as one launch by default; PB_RING_ITERS overrides (0 / 1: one launch per iteration).
+    static const int ring_iters = [] { const char* e = getenv("PB_RING_ITERS"); return e ? atoi(e) : -1; }();
+    const int dflt = (comm_ && comm_->world() > 1) ? 16 : kRingItersSingleGpu;
+    ring_iters_ = std::min(ring_iters >= 0 ? ring_iters : dflt, 32);
   }
   if (comm_) {
     // the halo protocol lives in the specialised stencil passes: one planar gradient operator
@@ -447,7 +457,7 @@ void BackendPDHG::initialize(const float* h_x0, size_t nx0, const float* h_y0, s
       if (tile_ok_) y_stage_.resize(m);
       if (tile_ok_ && ring_iters_ > 1) {
         const unsigned n_tiles = tile_ring_tile_count(stencil_);
-        ring_done_.resize(std::max(n_tiles, 1u));
+        ring_done_.resize(std::max(n_tiles, 1024u));
         ring_done_.zero(s);
         ring_edge_counters_.resize(64);
         ring_edge_counters_.zero(s);
@@ -461,6 +471,7 @@ void BackendPDHG::initialize(const float* h_x0, size_t nx0, const float* h_y0, s
       }
       d_state_.resize(1);
       d_sums_.resize(4);
+      if (tile_ok_) { fin_ticket_.resize(1); fin_ticket_.zero(s); }
     } catch (Error& e) {
       alloc_status = e.status;
       alloc_error = e.status == PB_ERR_OOM ? std::string("Out of memory: ") + e.what() : std::string(e.what());
@@ -523,12 +534,23 @@ void BackendPDHG::iteration_fused() {
   const bool tiled = tile_ok_ && iteration_ > 0;
   if (tiled && comm_) ring_halo = slab_ring_halo();
   const RingHalo* rh = (tiled && comm_) ? &ring_halo : nullptr;
+  // the residual-refresh launch folds the sums, combines them across ranks and advances the step-size state
+  // itself (RingFinish) unless the halos travel through NCCL staging buffers (no peer-mapped slots then)
+  bool finished_in_kernel = false;
   if (tiled && check) {
+    static const bool in_kernel = [] { const char* e = getenv("PB_RING_FINISH"); return !e || atoi(e) != 0; }();
+    const bool can_finish = in_kernel && (!comm_ || comm_->world() == 1 || comm_->reduce_p2p());
+    const unsigned red_seq0 = comm_ ? comm_->red_seq : 0;
+    RingFinish fin;
+    if (can_finish) fin = ring_finish();
     tiled_check = tile_check_iteration_launch(ctx_, stencil_, g_descs_[0], f_descs_[0], x_.data(), y_.data(),
                                               y_prev_.data(), T, S, st, iteration_ <= 1, part_d_.data(),
-                                              part_p_.data(), x_prev_.data(), y_prev_staging(), false, rh);
+                                              part_p_.data(), x_prev_.data(), y_prev_staging(), false, rh,
+                                              can_finish ? &fin : nullptr);
     if (!tiled_check && comm_)
       fail(PB_ERR_CUDA, "slab decomposition: the one-pass ring kernel could not be launched");
+    if (!tiled_check && comm_) comm_->red_seq = red_seq0;
+    finished_in_kernel = tiled_check && can_finish;
   }
   if (tiled_check) {
     // residual-refresh iteration in one pass: x_prev_ <- x^{k+1}; y^{k+1} cannot overwrite y_prev_ (the
@@ -593,7 +615,9 @@ void BackendPDHG::iteration_fused() {
     if (prof_ev_) PB_CUDA(cudaEventRecord(prof_ev_[2], ctx_->stream));
 
   }
-  if (comm_ && comm_->world() > 1 && check) {
+  if (finished_in_kernel) {
+    // nothing to launch: residual sums, cross-rank combination and pdhg_update happened in the ring kernel
+  } else if (comm_ && comm_->world() > 1 && check) {
     // per-rank fold -> one 4-double all-reduce -> identical state machine on every rank
     fold_residuals_kernel<<<1, kBlock, 0, ctx_->stream>>>(part_p_.data(), np, part_d_.data(), nd,
                                                           d_sums_.data());
@@ -610,6 +634,27 @@ void BackendPDHG::iteration_fused() {
     ctx_->launches++;
   }
   iteration_++;
+}
+
+RingFinish BackendPDHG::ring_finish() {
+  RingFinish f;
+  f.ticket = fin_ticket_.data();
+  f.state = d_state_.data();
+  f.prm = params_;
+  f.iteration = iteration_;
+  if (comm_ && comm_->world() > 1) {
+    f.world = comm_->world();
+    f.rank = comm_->rank();
+    f.seq = ++comm_->red_seq;
+    f.red_in = comm_->red_in();
+    f.red_flag_in = comm_->red_flag_in();
+    for (int r = 0; r < f.world; ++r) {
+      f.red_out[r] = comm_->red_out(r);
+      f.red_flag_out[r] = comm_->red_flag_out(r);
+    }
+    f.error = &comm_->flags()->error;
+  }
+  return f;
 }
 
 // Halo descriptor of the primal pass number `xs` (pb_comm.cuh): reads the y columns the left
@@ -835,6 +880,12 @@ bool BackendPDHG::multi_iteration_launch(int n_it) {
   mi.base = ring_base_;
   mi.done = ring_done_.data();
   mi.error = ring_error_.data();
+  {
+    static const int coarse = [] { const char* e = getenv("PB_RING_COARSE"); return e ? atoi(e) : 0; }();
+    static const int debug = [] { const char* e = getenv("PB_RING_DEBUG"); return e ? atoi(e) : 0; }();
+    mi.coarse = coarse;
+    mi.debug = debug;
+  }
   mi.x_io[0] = x_.data(); mi.x_io[1] = x_prev_.data();
   mi.y_io[0] = y_.data(); mi.y_io[1] = y_prev_.data();
   RingHalo h;
@@ -886,6 +937,13 @@ void BackendPDHG::residuals(float out[6]) {
   out[3] = st.dual_var_norm;
   out[4] = st.eps_primal;
   out[5] = st.eps_dual;
+  if (!comm_) {
+    // Backend::eps_primal() / eps_dual() are evaluated at call time with the problem's CURRENT dimensions
+    // (backend.hpp:71-74): once a dualised solve has been restored (solver.cu:199-203) those are the original
+    // ones again, which is what a caller reading them after Solver::Solve() gets from the reference
+    out[4] = pdhg_eps(problem_->nrows(), sopts_.tol_abs_primal, sopts_.tol_rel_primal, st.primal_var_norm);
+    out[5] = pdhg_eps(problem_->ncols(), sopts_.tol_abs_dual, sopts_.tol_rel_dual, st.dual_var_norm);
+  }
 }
 
 void BackendPDHG::stepsizes(double out[3]) {

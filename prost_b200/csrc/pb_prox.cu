@@ -504,6 +504,97 @@ class ProxIndSOC : public ProxGroupProjection {
   }
 };
 
+// ---- ProxIndSum (prox_ind_sum.cu:33-70, prox_ind_sum.hpp:37-62): projection, in the metric of the step sizes,
+// of index-list groups onto { sum_i x[inds[g*dim + i]] = total }: x_j - tau_j (sum_arg - total) / sum_tau.  Elements
+// that no list mentions are copied (the zero prox).  One thread per group like the reference (the members of a group
+// are scattered, so there is nothing to coalesce but the index list itself, which is stored member-major here:
+// entry i of group g at i*count + g).  Same float expressions in the same order as the reference kernel.
+__global__ void __launch_bounds__(kBlock) ind_sum_indexed_kernel(float* __restrict__ res, const float* __restrict__ arg,
+                                                                 const float* __restrict__ td,
+                                                                 const uint32_t* __restrict__ inds, size_t count,
+                                                                 size_t n_run, size_t dim, float total, float tau,
+                                                                 bool invert) {
+  for (size_t tx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; tx < n_run; tx += (size_t)gridDim.x * blockDim.x) {
+    float sum_arg = 0, sum_tau = 0;
+    for (size_t i = 0; i < dim; ++i) {
+      const uint32_t j = inds[i * count + tx];
+      float mytau = td[j] * tau;
+      if (invert) mytau = static_cast<float>(1. / mytau);
+      sum_arg += arg[j];
+      sum_tau += mytau;
+    }
+    for (size_t i = 0; i < dim; ++i) {
+      const uint32_t j = inds[i * count + tx];
+      float mytau = td[j] * tau;
+      if (invert) mytau = static_cast<float>(1. / mytau);
+      res[j] = arg[j] - mytau * (sum_arg - total) / sum_tau;
+    }
+  }
+}
+
+class ProxIndSumIndexed : public Prox {
+ public:
+  struct List {
+    size_t count = 0, dim = 0, n_run = 0;
+    float total = 0;
+    DeviceBuffer<uint32_t> inds;
+  };
+  // diagsteps is always true (prox_ind_sum.hpp:44: Prox<T>(index, size, true))
+  ProxIndSumIndexed(Context* ctx, size_t index, size_t size, size_t count, size_t dim, const unsigned long long* inds,
+                    float total, size_t count2, size_t dim2, const unsigned long long* inds2, float total2)
+      : Prox(ctx, index, size, true) {
+    if (index + size >= (1ull << 31)) fail(PB_ERR_UNSUPPORTED, "prox range exceeds 2^31-1");
+    fill(lists_[0], count, dim, inds, total);
+    two_ = inds2 != nullptr;
+    if (two_) {
+      fill(lists_[1], count2, dim2, inds2, total2);
+      // the reference sizes the second launch with the FIRST list's group count (prox_ind_sum.cu:135):
+      // groups of the second list beyond that many 256-thread blocks are never projected
+      const size_t covered = (count + 255) / 256 * 256;
+      lists_[1].n_run = std::min(count2, covered);
+    }
+  }
+  int kind() const override { return kProxIndSumIndexed; }
+  size_t uniform_group_size() const override { return size_; }
+  size_t gpu_mem_amount() const override {
+    return (lists_[0].inds.size() + lists_[1].inds.size()) * sizeof(size_t);       // prox_ind_sum.cu:88-90
+  }
+  void eval_local(float* res, const float* arg, const float* td, float tau, bool invert) override {
+    ctx_->bind();
+    if (size_ == 0) return;
+    // zero prox on the other indices (prox_ind_sum.cu:113-115)
+    if (res != arg) PB_CUDA(cudaMemcpyAsync(res, arg, size_ * sizeof(float), cudaMemcpyDeviceToDevice, ctx_->stream));
+    for (int k = 0; k < (two_ ? 2 : 1); ++k) {
+      const List& l = lists_[k];
+      if (l.n_run == 0) continue;
+      ind_sum_indexed_kernel<<<stream_grid(ctx_, l.n_run), kBlock, 0, ctx_->stream>>>(
+          res, arg, td, l.inds.data(), l.count, l.n_run, l.dim, l.total, tau, invert);
+      PB_CHECK_LAUNCH();
+      ctx_->launches++;
+    }
+  }
+
+ private:
+  void fill(List& l, size_t count, size_t dim, const unsigned long long* inds, float total) {
+    if (!inds && count * dim != 0) fail(PB_ERR_INVALID, "ProxIndSum: dimensions dont fit");   // prox_ind_sum.cu:74-75
+    l.count = l.n_run = count;
+    l.dim = dim;
+    l.total = total;
+    std::vector<uint32_t> t(count * dim);
+    for (size_t g = 0; g < count; ++g)
+      for (size_t i = 0; i < dim; ++i) {
+        const unsigned long long j = inds[g * dim + i];
+        if (j >= size_) fail(PB_ERR_INVALID, "ProxIndSum: index outside the prox range");
+        t[i * count + g] = static_cast<uint32_t>(j);
+      }
+    l.inds.resize(t.size());
+    if (!t.empty()) l.inds.upload(t.data(), t.size(), ctx_->stream);
+    PB_CUDA(cudaStreamSynchronize(ctx_->stream));
+  }
+  List lists_[2];
+  bool two_ = false;
+};
+
 // ---- ProxTransform (prox_transform.cu:27-226): prox of  c f(a x - b) + <d, x> + (e/2)|x|^2  through the prox of f.
 // Same three element-wise steps around the inner prox as the reference, same float expressions.
 struct TransformCoeffs {
@@ -658,6 +749,12 @@ std::shared_ptr<Prox> make_prox_ind_sum(Context* ctx, size_t index, size_t count
                                         bool diagsteps) {
   return std::make_shared<ProxIndSum>(ctx, index, count, dim, interleaved, diagsteps);
 }
+std::shared_ptr<Prox> make_prox_ind_sum_indexed(Context* ctx, size_t index, size_t size, size_t count, size_t dim,
+                                                const unsigned long long* inds, float total, size_t count2,
+                                                size_t dim2, const unsigned long long* inds2, float total2) {
+  return std::make_shared<ProxIndSumIndexed>(ctx, index, size, count, dim, inds, total, count2, dim2, inds2, total2);
+}
+
 std::shared_ptr<Prox> make_prox_ind_halfspace(Context* ctx, size_t index, size_t count, size_t dim, bool interleaved,
                                               bool diagsteps, const float* a, size_t na, const float* b, size_t nb) {
   return std::make_shared<ProxIndHalfspace>(ctx, index, count, dim, interleaved, diagsteps, a, na, b, nb);

@@ -29,6 +29,7 @@ enum ProxKind : int {
   kProxIndSum = 8,
   kProxIndHalfspace = 9,
   kProxIndSOC = 10,
+  kProxIndSumIndexed = 11,
 };
 
 // per-element vector or scalar (ElemOpCoefficients: prox_elem_operation.hpp:104-109)
@@ -366,6 +367,11 @@ std::shared_ptr<Prox> make_prox_moreau(Context* ctx, std::shared_ptr<Prox> inner
 // ProxElemOperation<T, ElemOperationIndSum<T>> (elem_operation_ind_sum.hpp:38-58): sum-to-one projection per group
 std::shared_ptr<Prox> make_prox_ind_sum(Context* ctx, size_t index, size_t count, size_t dim, bool interleaved,
                                         bool diagsteps);
+// ProxIndSum(index,size,count,dim,inds,sum[,count2,dim2,inds2,sum2]) (prox_ind_sum.hpp:37-62): index-list groups;
+// inds2 == nullptr: one list
+std::shared_ptr<Prox> make_prox_ind_sum_indexed(Context* ctx, size_t index, size_t size, size_t count, size_t dim,
+                                                const unsigned long long* inds, float total, size_t count2,
+                                                size_t dim2, const unsigned long long* inds2, float total2);
 // ProxIndHalfspace(index,count,dim,interleaved,diagsteps,a,b) (prox_ind_halfspace.hpp:41-52), ProxIndSOC(..., alpha)
 // (prox_ind_soc.hpp:39-48); both address planar groups regardless of `interleaved`, like the reference kernels
 std::shared_ptr<Prox> make_prox_ind_halfspace(Context* ctx, size_t index, size_t count, size_t dim, bool interleaved,

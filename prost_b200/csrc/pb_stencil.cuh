@@ -107,6 +107,31 @@ struct RingMulti {
   int* error = nullptr;                // set when a dependency wait times out
   float* x_io[2] = {nullptr, nullptr};
   float* y_io[2] = {nullptr, nullptr};
+  // dependency granularity: 0 = per tile (one release per tile, 3 x 3 tile neighbourhood probed per work item),
+  // 1 = per CTA and iteration (one release per CTA and iteration: done[cta] counts the iterations the CTA has
+  // finished; a work item waits for the CTAs that own its neighbour tiles)
+  int coarse = 0;
+  int debug = 0;                       // timing experiments only: bit 0 skips the release, bit 1 the probe
+};
+
+// Residual-refresh launches of the ring kernel finish the iteration themselves: the last CTA to arrive (ticket)
+// folds the per-CTA partial sums in index order, on slabs combines them across ranks through peer-mapped slots
+// (every rank stores its four sums into every rank's block over NVLink and sums the slots in rank order, so all
+// ranks get identical bits), and runs the step-size state machine (pdhg_update) -- no fold / all-reduce /
+// finalize launches on the iteration path.  ticket == nullptr: the caller finalizes (NCCL staging mode).
+constexpr int kMaxReduceRanks = 8;
+struct RingFinish {
+  unsigned* ticket = nullptr;
+  PdhgState* state = nullptr;
+  PdhgParams prm;
+  unsigned long long iteration = 0;
+  int world = 1, rank = 0;
+  unsigned seq = 0;                              // number of this reduction; slots / flags by (seq & 1)
+  const double* red_in = nullptr;                // local slots [2][kMaxReduceRanks][4]
+  const unsigned* red_flag_in = nullptr;         // local flags [kMaxReduceRanks]: newest seq written by rank r
+  double* red_out[kMaxReduceRanks] = {};         // every rank's slots (own included)
+  unsigned* red_flag_out[kMaxReduceRanks] = {};
+  int* error = nullptr;
 };
 
 struct GradGeom {
@@ -716,6 +741,6 @@ unsigned tile_check_iteration_launch(Context* ctx, const StencilPlan& plan, cons
                                      const float* x, const float* y, const float* y_prev, ScaleRef T, ScaleRef S,
                                      const PdhgState* st, bool ktyprev_zero, double* part_d, double* part_p,
                                      float* x_out, float* y_out, bool dry_run = false,
-                                     const RingHalo* halo = nullptr);
+                                     const RingHalo* halo = nullptr, const RingFinish* finish = nullptr);
 
 }  // namespace pb

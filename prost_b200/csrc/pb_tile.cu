@@ -599,7 +599,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
     const PdhgState* __restrict__ st, const FastDiv div_per_plane, const FastDiv div_tiles_y,
     const uint32_t n_tiles, const int ktyprev_zero, double* __restrict__ part_d, double* __restrict__ part_p,
     float* __restrict__ x_out, float* __restrict__ y_out, const uint32_t tiles_x, const RingHalo h,
-    const __grid_constant__ CUtensorMap map_xb, const RingMulti mi) {
+    const __grid_constant__ CUtensorMap map_xb, const RingMulti mi, const RingFinish fin) {
   static_assert(!(MULTI && CHECK), "residual-refresh iterations run one per launch");
   extern __shared__ __align__(128) unsigned char smem[];
   // tile -> (label plane, tile column, tile row).  On a slab the two edge tile columns come first
@@ -675,6 +675,12 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
   const int col = threadIdx.x >> 5;          // warp = column of the computed region
   const int r0 = (threadIdx.x & 31) * 4;     // lane = row vector
   double acc_d0 = 0.0, acc_d1 = 0.0, acc_p0 = 0.0, acc_p1 = 0.0;
+  // residual sums (CHECK): T, Sigma, tau, sigma are uniform here, so the divisions of backend_pdhg.cu:85-88,
+  // 109-113 become multiplications by two reciprocals computed once (1 ulp per term, far inside the 1e-4 bar
+  // on the residuals); the squares of a thread's four pixels are summed in float before they enter the double
+  // accumulators (one conversion per sum instead of one per pixel)
+  const float sq_T = sqrtf(Tval), sq_S = sqrtf(Sval);
+  const float inv_tau_sq = 1.f / (tau * sq_T), inv_sigma_sq = 1.f / (sigma * sq_S);
 
   // ---- multi-iteration launches: work item k = (iteration, k-th tile of this CTA), issued by warp 31 -------------
   const uint32_t n_work = MULTI ? ((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) * (uint32_t)mi.n_it : 0u;
@@ -686,22 +692,32 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
   auto multi_issue = [&](bool blocking) -> bool {
     if (!MULTI || ki >= n_work) return false;
     const int si = ki % kRingStages;
-    if (ki >= (uint32_t)kRingStages) mbar_wait(&empty[si], ((ki - kRingStages) / kRingStages) & 1u);
     if (ki_it > 0) {
+      // neighbourhood probe first: its loads overlap the wait for the stage below
       uint32_t l, tx, ty;
       decode(ki_tile, l, tx, ty);
       const int lane = threadIdx.x & 31;
       bool ready = true;
-      if (lane < 9 && lane != 4) {
+      if (lane < 9 && lane != 4 && !(mi.debug & 2)) {
         const int ntx = (int)tx + lane % 3 - 1, nty = (int)ty + lane / 3 - 1;
-        if (ntx >= 0 && ntx < (int)tiles_x && nty >= 0 && nty < (int)div_tiles_y.d)
-          ready = ring_count_wait(mi.done + (l * div_per_plane.d + (uint32_t)ntx * div_tiles_y.d + (uint32_t)nty),
-                                  mi.base + ki_it, blocking, mi.error);
+        if (ntx >= 0 && ntx < (int)tiles_x && nty >= 0 && nty < (int)div_tiles_y.d) {
+          uint32_t slot = l * div_per_plane.d + (uint32_t)ntx * div_tiles_y.d + (uint32_t)nty;
+          if (mi.coarse) {
+            // owner CTA of the neighbour tile: position in the walk order (slabs walk the edge columns first)
+            const uint32_t wx = SLAB ? ((uint32_t)ntx == 0u ? 0u : ((uint32_t)ntx == tiles_x - 1 ? 1u : (uint32_t)ntx + 1u))
+                                     : (uint32_t)ntx;
+            slot = (l * div_per_plane.d + wx * div_tiles_y.d + (uint32_t)nty) % gridDim.x;
+            if (slot == blockIdx.x) slot = 0xffffffffu;        // own tiles: program order
+          }
+          if (slot != 0xffffffffu) ready = ring_count_wait(mi.done + slot, mi.base + ki_it, blocking, mi.error);
+        }
       }
       __syncwarp();
       if (!__all_sync(0xffffffffu, ready)) return false;
-      asm volatile("fence.proxy.async;" ::: "memory");     // the neighbours' generic-proxy stores -> our TMA reads
     }
+    if (ki >= (uint32_t)kRingStages) mbar_wait(&empty[si], ((ki - kRingStages) / kRingStages) & 1u);
+    // the neighbours' (and this CTA's own) generic-proxy stores -> our TMA reads
+    asm volatile("fence.proxy.async;" ::: "memory");
     if ((threadIdx.x & 31) == 0) issue(ki_tile, si, ki_it);
     ++ki;
     ki_tile += gridDim.x;
@@ -845,15 +861,17 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
 #pragma unroll
             for (int j = 0; j < 4; ++j) kp[j] = 0.f;
           }
-          const float sq = sqrtf(Tval);
+          float s0 = 0.f, s1 = 0.f;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float kk = -(divx[j] + divy[j]);
-            const float w_hat = (xo[j] - xn[j]) / (tau * sq) - sq * kp[j];
-            const float diff = w_hat + sq * kk;
-            acc_d0 += static_cast<double>(diff * diff);
-            acc_d1 += static_cast<double>(w_hat * w_hat);
+            const float w_hat = (xo[j] - xn[j]) * inv_tau_sq - sq_T * kp[j];
+            const float diff = w_hat + sq_T * kk;
+            s0 += diff * diff;
+            s1 += w_hat * w_hat;
           }
+          acc_d0 += static_cast<double>(s0);
+          acc_d1 += static_cast<double>(s1);
         }
       }
     }
@@ -906,18 +924,20 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
       if (CHECK) {
         // primal residual: z^ = (y - y+)/(sigma sqrt S) + sqrt S ((1+theta) K x+ - theta K x),
         // diff = z^ - sqrt S K x+
-        const float sq = sqrtf(Sval);
+        float s0 = 0.f, s1 = 0.f;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float ex = dual_extrapolate(theta, k1x[j], k0x[j]);
-          const float zx = (y1[j] - arg[0][j]) / (sigma * sq) + sq * ex;
-          const float dx = zx - sq * k1x[j];
+          const float zx = (y1[j] - arg[0][j]) * inv_sigma_sq + sq_S * ex;
+          const float dx = zx - sq_S * k1x[j];
           const float ey = dual_extrapolate(theta, k1y[j], k0y[j]);
-          const float zy = (y2[j] - arg[1][j]) / (sigma * sq) + sq * ey;
-          const float dy = zy - sq * k1y[j];
-          acc_p0 += static_cast<double>(dx * dx) + static_cast<double>(dy * dy);
-          acc_p1 += static_cast<double>(zx * zx) + static_cast<double>(zy * zy);
+          const float zy = (y2[j] - arg[1][j]) * inv_sigma_sq + sq_S * ey;
+          const float dy = zy - sq_S * k1y[j];
+          s0 += dx * dx + dy * dy;
+          s1 += zx * zx + zy * zy;
         }
+        acc_p0 += static_cast<double>(s0);
+        acc_p1 += static_cast<double>(s1);
       }
     }
     if (right_edge) ring_edge_done(y_done, h.n_edge_tiles, h.y_signal, y_signal_seq);
@@ -932,24 +952,80 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
       }
     }
     if (MULTI && col == kRingCols - 1) {
-      // every warp has left work item k, i.e. issued its stores: publish the tile's iteration count (release at
-      // gpu scope; the other warps' stores are ordered before it through the `empty` mbarrier), then try to put
-      // the next work item into the freed stage
+      // First put the next work item into the stage that is being freed (its neighbourhood is probed while the
+      // other warps are still in phase B; multi_issue waits for the stage itself), THEN publish this tile's
+      // iteration count: the release at gpu scope is a full fence and must not sit in front of the TMA issue.
+      // Every warp has left work item k once `empty` completes, i.e. has issued its stores; they are ordered
+      // before the release through that mbarrier (cumulativity).
+      const bool issued = multi_issue(false);
       mbar_wait(&empty[s], parity);
-      if (producer) {
-        __threadfence();
-        unsigned* cnt = mi.done + (l * div_per_plane.d + tx * div_tiles_y.d + ty);
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(cnt), "r"(mi.base + it + 1u) : "memory");
+      if (producer && !(mi.debug & 1)) {
+        if (!mi.coarse) {
+          unsigned* cnt = mi.done + (l * div_per_plane.d + tx * div_tiles_y.d + ty);
+          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(cnt), "r"(mi.base + it + 1u) : "memory");
+        } else if (tile + gridDim.x >= n_tiles) {      // this CTA's last tile of the iteration
+          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(mi.done + blockIdx.x), "r"(mi.base + it + 1u)
+                       : "memory");
+        }
       }
-      multi_issue(false);
+      if (!issued) multi_issue(false);
     }
   }
   if (CHECK) {
     block_sum2(acc_d0, acc_d1);
     block_sum2(acc_p0, acc_p1);
+    __shared__ unsigned s_last;
     if (threadIdx.x == 0) {
       part_d[2 * blockIdx.x] = acc_d0; part_d[2 * blockIdx.x + 1] = acc_d1;
       part_p[2 * blockIdx.x] = acc_p0; part_p[2 * blockIdx.x + 1] = acc_p1;
+      unsigned last = 0;
+      if (fin.ticket) {
+        __threadfence();
+        last = atomicAdd(fin.ticket, 1u) + 1u == gridDim.x ? 1u : 0u;
+      }
+      s_last = last;
+    }
+    __syncthreads();
+    if (s_last) {
+      // last CTA of the launch: every partial pair is visible (ticket + fences); fold in index order
+      __threadfence();
+      double pa = 0.0, pb = 0.0, da = 0.0, db = 0.0;
+      for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
+        pa += __ldcg(part_p + 2 * i); pb += __ldcg(part_p + 2 * i + 1);
+        da += __ldcg(part_d + 2 * i); db += __ldcg(part_d + 2 * i + 1);
+      }
+      block_sum2(pa, pb);
+      block_sum2(da, db);
+      if (threadIdx.x == 0) {
+        double sums[4] = {pa, pb, da, db};
+        if (fin.world > 1) {
+          // slabs: my four sums into every rank's slot [seq & 1][my rank] (peer memory over NVLink), then the
+          // sequence number; wait for every rank's and add the slots in rank order (identical on all ranks)
+          const unsigned slot = (fin.seq & 1u) * kMaxReduceRanks;
+          for (int r = 0; r < fin.world; ++r) {
+            double* o = fin.red_out[r] + (size_t)(slot + fin.rank) * 4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) __stcg(o + j, sums[j]);
+          }
+          __threadfence_system();
+          for (int r = 0; r < fin.world; ++r)
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(fin.red_flag_out[r] + fin.rank), "r"(fin.seq)
+                         : "memory");
+#pragma unroll
+          for (int j = 0; j < 4; ++j) sums[j] = 0.0;
+          for (int r = 0; r < fin.world; ++r) {
+            ring_flag_wait(fin.red_flag_in + r, fin.seq, fin.error);
+            const double* in = fin.red_in + (size_t)(slot + r) * 4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sums[j] += __ldcg(in + j);
+          }
+        }
+        PdhgState ns = *fin.state;
+        ns.iteration = fin.iteration;
+        pdhg_update(ns, fin.prm, sums, true);
+        *fin.state = ns;
+        *fin.ticket = 0u;
+      }
     }
   }
 }
@@ -963,6 +1039,7 @@ struct RingArgs {
   const RingHalo* halo = nullptr;      // slab mode
   CUtensorMap mxb;                     // multi-iteration launches: x boxes over the second buffer set
   const RingMulti* multi = nullptr;
+  const RingFinish* finish = nullptr;  // residual-refresh launches that finalize the iteration in the kernel
 };
 
 template <int FN_G, int FN_F, bool CHECK, bool SLAB, bool MULTI = false>
@@ -1001,14 +1078,14 @@ unsigned ring_launch_k(Context* ctx, const RingArgs& a, const GradGeom& g, const
     const cudaError_t e = cudaLaunchKernelEx(
         &cfg, kernel, a.mp1, a.mp2, a.mx, a.mf, a.mq1, a.mq2, g, pg, pf, Tval, Sval, st,
         FastDiv((uint64_t)tiles_x * tiles_y), FastDiv(tiles_y), (uint32_t)n_tiles, a.ktyprev_zero, a.part_d, a.part_p,
-        x_out, y_out, tiles_x, h, a.mxb, *a.multi);
+        x_out, y_out, tiles_x, h, a.mxb, *a.multi, RingFinish());
     if (e != cudaSuccess) { cudaGetLastError(); return 0; }
     return grid;
   }
   kernel<<<grid, kRingThreads, kRingSmemBytes, ctx->stream>>>(
       a.mp1, a.mp2, a.mx, a.mf, a.mq1, a.mq2, g, pg, pf, Tval, Sval, st, FastDiv((uint64_t)tiles_x * tiles_y),
       FastDiv(tiles_y), (uint32_t)n_tiles, a.ktyprev_zero, a.part_d, a.part_p, x_out, y_out, tiles_x, h, a.mx,
-      RingMulti());
+      RingMulti(), (CHECK && a.finish) ? *a.finish : RingFinish());
   return grid;
 }
 
@@ -1027,9 +1104,10 @@ unsigned ring_launch_fn(Context* ctx, const RingArgs& a, const GradGeom& g, cons
 unsigned ring_launch(Context* ctx, const GradGeom& g, const ProxDesc& pg, const ProxDesc& pf, const float* x,
                      const float* y, const float* y_prev, float Tval, float Sval, const PdhgState* st, bool check,
                      bool ktyprev_zero, double* part_d, double* part_p, float* x_out, float* y_out, bool dry_run,
-                     const RingHalo* halo) {
+                     const RingHalo* halo, const RingFinish* finish = nullptr) {
   RingArgs a;
   a.halo = halo;
+  a.finish = finish;
   a.check = check;
   a.ktyprev_zero = ktyprev_zero ? 1 : 0;
   a.part_d = part_d;
@@ -1139,10 +1217,11 @@ static int tile_mode() {
 unsigned tile_check_iteration_launch(Context* ctx, const StencilPlan& plan, const ProxDesc& pg, const ProxDesc& pf,
                                      const float* x, const float* y, const float* y_prev, ScaleRef T, ScaleRef S,
                                      const PdhgState* st, bool ktyprev_zero, double* part_d, double* part_p,
-                                     float* x_out, float* y_out, bool dry_run, const RingHalo* halo) {
+                                     float* x_out, float* y_out, bool dry_run, const RingHalo* halo,
+                                     const RingFinish* finish) {
   if (tile_mode() != 2) return 0;
   const unsigned n = ring_launch(ctx, plan.geom, pg, pf, x, y, y_prev, T.val, S.val, st, true, ktyprev_zero, part_d,
-                                 part_p, x_out, y_out, dry_run, halo);
+                                 part_p, x_out, y_out, dry_run, halo, finish);
   if (n && !dry_run) {
     PB_CHECK_LAUNCH();
     ctx->launches++;

@@ -9,6 +9,7 @@ reference's mex registry names and argument order (matlab/+prost/private/factory
   elem_operation:1d:<fun>, elem_operation:norm2:<fun> : [count, dim, interleaved, [a,b,c,d,e,alpha,beta]]
   elem_operation:ind_simplex, elem_operation:ind_sum   : [count, dim, interleaved]
   ind_epi_quad                                         : [count, dim, interleaved, [a, b, c]]
+  ind_sum                                              : [dim, inds, sum(, dim2, inds2, sum2)]
   ind_halfspace                                        : [count, dim, interleaved, [a, b]]
   ind_soc                                              : [count, dim, interleaved, alpha]
   moreau                                               : [child description]
@@ -35,6 +36,10 @@ def create_prox(ctx, desc):
     if name == "elem_operation:ind_sum":
         count, dim, interleaved = data[:3]
         return api.ProxElemOperationIndSum(ctx, idx, count, dim, interleaved, diagsteps)
+    if name == "ind_sum":                  # +function/sum_ind_sum2.m: { dim, inds, s1 [, dim2, inds2, s2] }
+        if len(data) == 3:
+            return api.ProxIndSum(ctx, idx, size, data[0], data[1], data[2])
+        return api.ProxIndSum(ctx, idx, size, data[0], data[1], data[2], data[3], data[4], data[5])
     if name == "ind_halfspace":
         count, dim, interleaved, (a, b) = data
         return api.ProxIndHalfspace(ctx, idx, count, dim, interleaved, diagsteps, a, b)

@@ -55,9 +55,19 @@ def image(nx, ny, nc=1, sigma_n=0.1, stream=1, x0=0, x1=None):
     return out.reshape(-1)
 
 
-def salt_and_pepper(f, stream=20, frac=0.25):
-    """25 % salt-and-pepper noise as in example_tvl1.m:11-14."""
-    u = uniform(stream, np.arange(f.size, dtype=np.uint64))
+def salt_and_pepper(f, stream=20, frac=0.25, nx=None, ny=None, x0=0, x1=None):
+    """25 % salt-and-pepper noise as in example_tvl1.m:11-14.  With ``nx, ny, x0, x1`` the array is the column
+    slab [x0, x1) of a planar nx x ny x nc image and the hash counters are the GLOBAL element indices, so a slab
+    equals the slice of the whole noisy image."""
+    if nx is None:
+        idx = np.arange(f.size, dtype=np.uint64)
+    else:
+        x1 = nx if x1 is None else x1
+        w = x1 - x0
+        nc = f.size // (w * ny)
+        lin = (np.arange(x0, x1, dtype=np.uint64)[:, None] * np.uint64(ny) + np.arange(ny, dtype=np.uint64)[None, :])
+        idx = (np.arange(nc, dtype=np.uint64)[:, None, None] * np.uint64(nx * ny) + lin[None]).reshape(-1)
+    u = uniform(stream, idx)
     out = f.copy()
     out[u < frac / 2] = 1.0
     out[(u >= frac / 2) & (u < frac)] = 0.0

@@ -40,7 +40,7 @@ def worker():
         dist.init_process_group("gloo")
         comm = pbd.init_comm(ctx)
     out = {}
-    for name, (nx, ny), step, res_iter, iters in CASES:
+    for name, (nx, ny), step, res_iter, iters in ([] if os.environ.get("PB_RING_DEBUG") else CASES):
         part = pbd.SlabPartition(nx, world)
         x0, x1 = part.range(rank)
         desc = syn.rof(x1 - x0, ny, 10.0, f=syn.image(nx, ny, x0=x0, x1=x1))
@@ -54,7 +54,7 @@ def worker():
         be.PerformIteration(iters // 3)
         be.PerformIteration(iters - iters // 3)
         x, z, y, w = be.current_solution()
-        np.savez(os.path.join(os.environ["PB_CHECK_DIR"], f"{name}_r{rank}_{os.environ['PB_RING_ITERS']}.npz"),
+        np.savez(os.path.join(os.environ["PB_CHECK_DIR"], f"{name}_r{rank}_{os.environ['PB_CHECK_TAG']}.npz"),
                  x=x, y=y, z=z, w=w, res=np.array(list(be.residuals().values())))
         out[name] = int(be.one_pass_iterations)
         del be, prob
@@ -90,24 +90,33 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     tmp = os.environ.get("PB_CHECK_SHARED") or tempfile.mkdtemp(prefix="ring_multi_")
     reports = {}
-    for setting in ("1", "9"):
-        env = dict(os.environ, PB_RING_ITERS=setting, PB_CHECK_DIR=tmp)
+    # tag -> environment: single launches (the reference), 9 iterations per launch with per-tile and with per-CTA
+    # dependencies; the PB_RING_DEBUG variants skip synchronisation steps (timing experiments, results unusable)
+    settings = [("1", dict(PB_RING_ITERS="1")), ("9", dict(PB_RING_ITERS="9")),
+                ("9coarse", dict(PB_RING_ITERS="9", PB_RING_COARSE="1")),
+                ("16coarse", dict(PB_RING_ITERS="16", PB_RING_COARSE="1"))]
+    if os.environ.get("PB_CHECK_DEBUG_VARIANTS"):
+        settings += [("9_noprobe", dict(PB_RING_ITERS="9", PB_RING_DEBUG="2")),
+                     ("9_noprobe_norelease", dict(PB_RING_ITERS="9", PB_RING_DEBUG="3"))]
+    for k, (tag, extra) in enumerate(settings):
+        env = dict(os.environ, PB_CHECK_DIR=tmp, PB_CHECK_TAG=tag, **extra)
         if world > 1:
-            env["MASTER_PORT"] = str(int(os.environ.get("MASTER_PORT", "29500")) + 1 + int(setting))
+            env["MASTER_PORT"] = str(int(os.environ.get("MASTER_PORT", "29500")) + 1 + k)
         p = subprocess.run([sys.executable, os.path.abspath(__file__)], env=env, capture_output=True, text=True, timeout=900)
         lines = [ln for ln in p.stdout.splitlines() if ln.startswith("RING_MULTI ")]
         if p.returncode != 0:
-            print(p.stdout[-2000:], p.stderr[-2000:])
+            print(tag, p.stdout[-2000:], p.stderr[-2000:])
             sys.exit(1)
         if lines:
-            reports[setting] = json.loads(lines[-1][len("RING_MULTI "):])
+            reports[tag] = json.loads(lines[-1][len("RING_MULTI "):])
     ok = True
     for name, *_ in CASES:
         a = np.load(os.path.join(tmp, f"{name}_r{rank}_1.npz"))
-        b = np.load(os.path.join(tmp, f"{name}_r{rank}_9.npz"))
-        same = all(np.array_equal(a[k], b[k]) for k in ("x", "y", "z", "w", "res"))
-        ok &= same
-        print(f"rank {rank} {name}: {'bit-identical' if same else 'DIFFERENT'}")
+        for tag in ("9", "9coarse", "16coarse"):
+            b = np.load(os.path.join(tmp, f"{name}_r{rank}_{tag}.npz"))
+            same = all(np.array_equal(a[k], b[k]) for k in ("x", "y", "z", "w", "res"))
+            ok &= same
+            print(f"rank {rank} {name} [{tag}]: {'bit-identical' if same else 'DIFFERENT'}")
     if rank == 0:
         print(json.dumps(reports))
     sys.exit(0 if ok else 1)

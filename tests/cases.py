@@ -204,6 +204,30 @@ def prox_ind_sum_cases(small=False):
     return cases
 
 
+def prox_ind_sum_indexed_cases(small=False):
+    """ProxIndSum (prox_ind_sum.cu:33-145; mex name "ind_sum", +function/sum_ind_sum2.m): groups given as index
+    lists inside the prox range; one list, two lists (rows and columns of a matrix, as in the optimal-transport
+    use of sum_ind_sum2), an offset range, and a second list longer than the reference's launch covers."""
+    r = rng(53)
+    cases = {}
+    n1, n2 = (60, 45) if not small else (9, 7)
+    N = n1 * n2
+    rows = np.arange(N, dtype=np.uint64).reshape(n1, n2)              # group g = row g (dim n2)
+    cols = np.ascontiguousarray(rows.T)                               # group g = column g (dim n1)
+    cases["ind_sum_idx_rows"] = (("ind_sum", 0, N, True, [n2, rows.ravel(), 1.0]), N)
+    cases["ind_sum_idx_rows_cols"] = (("ind_sum", 0, N, True, [n2, rows.ravel(), 1.0, n1, cols.ravel(), 0.5]), N)
+    perm = r.permutation(N).astype(np.uint64)
+    k = (N // 5) * 5
+    cases["ind_sum_idx_scattered_offset"] = (("ind_sum", 17, N, True, [5, perm[:k], -2.0]), N + 40)
+    # 3 groups in the first list -> the reference launches ONE 256-thread block for the second list as well:
+    # only the first 256 of its 300 groups are projected (prox_ind_sum.cu:135)
+    M = 300 * 2 + 6
+    first = np.arange(6, dtype=np.uint64) + np.uint64(600)
+    second = np.arange(600, dtype=np.uint64)
+    cases["ind_sum_idx_second_list_truncated"] = (("ind_sum", 0, M, True, [2, first, 3.0, 2, second, 1.0]), M)
+    return cases
+
+
 def prox_projection_cases(small=False):
     """ind_halfspace (prox_ind_halfspace.cu) and ind_soc (prox_ind_soc.cu): planar groups."""
     r = rng(31)
@@ -228,6 +252,7 @@ def all_prox_cases(small=False):
     out = dict(prox_cases(small))
     out.update({k: (v[0], v[1]) for k, v in prox_transform_cases(small).items()})
     out.update(prox_ind_sum_cases(small))
+    out.update(prox_ind_sum_indexed_cases(small))
     out.update(prox_projection_cases(small))
     return out
 

@@ -42,6 +42,8 @@ lib.orc_prox_elem.argtypes = [C.c_void_p, C.c_int, sz, sz, sz, C.c_int, C.c_int,
                               C.POINTER(sz)]
 lib.orc_prox_simplex.argtypes = [C.c_void_p, sz, sz, sz, C.c_int, C.c_int]
 lib.orc_prox_ind_sum.argtypes = [C.c_void_p, sz, sz, sz, C.c_int, C.c_int]
+lib.orc_prox_ind_sum_indexed.argtypes = [C.c_void_p, sz, sz, sz, sz, C.POINTER(C.c_ulonglong), C.c_float, sz, sz,
+                                         C.POINTER(C.c_ulonglong), C.c_float]
 lib.orc_prox_ind_halfspace.argtypes = [C.c_void_p, sz, sz, sz, C.c_int, C.c_int, fp, sz, fp, sz]
 lib.orc_prox_ind_soc.argtypes = [C.c_void_p, sz, sz, sz, C.c_int, C.c_int]
 lib.orc_prox_epi_quad.argtypes = [C.c_void_p, sz, sz, sz, C.c_int, C.c_int, fp, sz, fp, sz, fp, sz]
@@ -175,6 +177,16 @@ class OracleProblem:
             a, b = _f32(a), _f32(b)
             return lib.orc_prox_ind_halfspace(self.h, idx, count, dim, int(il), int(diagsteps), _p(a), a.size,
                                               _p(b), b.size)
+        if name == "ind_sum":                  # ProxIndSum: [dim, inds, sum(, dim2, inds2, sum2)]
+            u64p = C.POINTER(C.c_ulonglong)
+            a = np.ascontiguousarray(np.asarray(data[1], dtype=np.uint64).ravel())
+            two = len(data) == 6
+            b = np.ascontiguousarray(np.asarray(data[4] if two else [], dtype=np.uint64).ravel())
+            d1, d2 = int(data[0]), int(data[3]) if two else 0
+            return lib.orc_prox_ind_sum_indexed(self.h, idx, size, a.size // d1, d1, a.ctypes.data_as(u64p),
+                                                float(data[2]), (b.size // d2) if two else 0, d2,
+                                                b.ctypes.data_as(u64p) if two else None,
+                                                float(data[5]) if two else 0.0)
         if name == "ind_soc":
             count, dim, il = data[:3]
             return lib.orc_prox_ind_soc(self.h, idx, count, dim, int(il), int(diagsteps))

@@ -94,6 +94,12 @@ class _Writer:
         if name == "ind_soc":
             count, dim, il = data[:3]
             return f"soc {idx} {count} {dim} {int(il)} {int(ds)} {float(data[3]) if len(data) > 3 else 1.0!r}"
+        if name == "ind_sum":
+            parts = [f"indsumidx {idx} {size} {len(data) // 3}"]
+            for k in range(0, len(data), 3):
+                fi, n = self.arr(data[k + 1], np.uint64)
+                parts.append(f"{int(data[k])} {fi} {n} {float(data[k + 2])!r}")
+            return " ".join(parts)
         if name == "elem_operation:ind_sum":
             count, dim, il = data[:3]
             return f"indsum {idx} {count} {dim} {int(il)} {int(ds)}"

@@ -269,3 +269,30 @@ def test_kronecker_blocks_match_numpy_kron():
         assert np.abs(P.linop(y, True) - M.T @ y).max() < 1e-3, name
         assert np.allclose(P.row_sums(1.0), np.abs(M).sum(1), rtol=1e-5, atol=1e-6), name
         assert np.allclose(P.col_sums(1.0), np.abs(M).sum(0), rtol=1e-5, atol=1e-6), name
+
+
+def test_prox_ind_sum_indexed_is_the_weighted_projection():
+    """Oracle pin for ProxIndSum (prox_ind_sum.cu:33-70): per index-list group g the result is the minimiser of
+    sum_j (x_j - arg_j)^2 / (2 tau_j) subject to sum_j x_j = s, i.e. x_j = arg_j - tau_j (sum arg - s) / sum tau
+    (double-precision closed form); elements outside every list are copied; two lists run one after the other on
+    the ORIGINAL argument; the second launch covers ceil(count_1 / 256) * 256 groups only (:135)."""
+    r = np.random.default_rng(11)
+    for name, (desc, n) in cases.prox_ind_sum_indexed_cases().items():
+        arg = (2 * r.standard_normal(n)).astype(np.float32)
+        td = r.uniform(0.5, 1.5, n).astype(np.float32)
+        for invert in (False, True):
+            res = oracle_prox_eval(desc, arg, td, 0.7, invert)
+            lo, hi = desc[1], desc[1] + desc[2]
+            a, t = arg[lo:hi].astype(np.float64), td[lo:hi].astype(np.float64) * 0.7
+            if invert:
+                t = 1.0 / t
+            want = a.copy()
+            data = desc[4]
+            for l, k in enumerate(range(0, len(data), 3)):
+                dim, inds, s = int(data[k]), np.asarray(data[k + 1], np.int64).reshape(-1, int(data[k])), float(data[k + 2])
+                if l == 1:
+                    first_count = np.asarray(data[1]).size // int(data[0])
+                    inds = inds[: (first_count + 255) // 256 * 256]
+                for g in inds:
+                    want[g] = a[g] - t[g] * (a[g].sum() - s) / t[g].sum()
+            assert np.abs(res[lo:hi] - want).max() <= 2e-5 * max(1.0, np.abs(want).max()), (name, invert)

@@ -100,6 +100,39 @@ def test_ind_sum_matches_oracle_and_reference(ctx, name):
         assert np.abs(got[lo:hi] - ref[lo:hi]).max() <= 1e-5, name
 
 
+# ---- ind_sum: ProxIndSum over index lists (last item) -------------------------------------
+IDX_CASES = cases.prox_ind_sum_indexed_cases()
+
+
+@pytest.mark.parametrize("name", sorted(IDX_CASES))
+@pytest.mark.parametrize("invert", [False, True])
+def test_ind_sum_indexed_matches_oracle_and_reference(ctx, name, invert):
+    desc, n = IDX_CASES[name]
+    arg, tau_diag, tau = _inputs(name, n)
+    got = pb.create_prox(ctx, desc).Eval(arg, tau_diag, tau, invert)
+    want = oracle_prox_eval(desc, arg, tau_diag, tau, invert)
+    lo, hi = desc[1], desc[1] + desc[2]
+    # same float expressions in the same order: identical bits
+    assert np.array_equal(got[lo:hi], want[lo:hi]), name
+    data = desc[4]
+    last = 3 if len(data) == 6 else 0              # the groups of the list that ran last sum to its constant
+    dim, inds, total = int(data[last]), np.asarray(data[last + 1], np.int64), float(data[last + 2])
+    if name != "ind_sum_idx_second_list_truncated":
+        sums = got[lo:hi][inds].reshape(-1, dim).sum(axis=1)
+        assert np.abs(sums - total).max() < 1e-4 * max(1.0, dim / 8), name
+    untouched = np.setdiff1d(np.arange(hi - lo), np.concatenate([np.asarray(data[k + 1], np.int64) for k in range(1, len(data), 3)] + [inds]))
+    assert np.array_equal(got[lo:hi][untouched], arg[lo:hi][untouched])
+    if ref_driver.available() and not invert:
+        ref = ref_driver.run_prox(desc, arg, tau_diag, tau)
+        assert np.array_equal(got[lo:hi], ref[lo:hi]), name
+
+
+def test_ind_sum_indexed_errors(ctx):
+    with pytest.raises(pb.ProstError) as e:
+        pb.ProxIndSum(ctx, 0, 10, 2, np.array([0, 1, 2, 10], np.uint64), 1.0)
+    assert "outside the prox range" in str(e.value)
+
+
 # ---- ind_halfspace, ind_soc -------------------------------------------------------------
 PROJ_CASES = cases.prox_projection_cases()
 
