@@ -333,6 +333,10 @@ int pb_backend_profile(pb_backend* b, int n_iters, float out_ms[3]);
  * tiled iterations, tiled residual-refresh kernel ms, #tiled residual-refresh iterations } */
 int pb_backend_profile_detail(pb_backend* b, int n_iters, float out[8]);
 /* device pointers of the current iterates (x: ncols, y: nrows) for zero-copy callers */
+/* PB_RING_TRACE=1 (scaling experiments): per launch of the one-pass ring kernel {first CTA start, last CTA end,
+ * longest left-edge halo wait, longest right-edge halo wait} in ns of the GPU's global timer; copies up to n
+ * launches (4 values each) and returns the number of launches traced so far. */
+unsigned pb_ring_trace_read(unsigned long long* h_out, unsigned n);
 int pb_backend_device_iterates(pb_backend* b, float** d_x, float** d_y);
 
 /* ---- multi-GPU slab decomposition (no counterpart in the reference, which is single-GPU:

@@ -193,6 +193,7 @@ SIGNATURES = {
     "pb_comm_barrier": (C.c_int, [handle]),
     "pb_comm_allreduce_sum": (C.c_int, [handle, c_double_p, C.c_size_t]),
     "pb_backend_set_slab": (C.c_int, [handle, handle]),
+    "pb_ring_trace_read": (C.c_uint, [C.POINTER(C.c_ulonglong), C.c_uint]),
     "pb_solver_solve": (C.c_int, [handle, C.POINTER(SolverOptions), STOPPING_CB, INTERM_CB, C.c_void_p,
                                   c_float_p, c_float_p, c_float_p, c_float_p, c_int_p, c_int_p]),
 }

@@ -10,6 +10,8 @@
 #include <new>
 
 #include "pb_backend.cuh"
+
+namespace pb { unsigned tile_ring_trace_read(unsigned long long* h_out, unsigned n); }   // pb_tile.cu
 #include "pb_comm.cuh"
 #include "pb_problem.cuh"
 
@@ -562,6 +564,8 @@ unsigned long long pb_backend_launch_count(const pb_backend* b) {
 int pb_backend_device_iterates(pb_backend* b, float** d_x, float** d_y) {
   return guarded([&] { require(b && d_x && d_y, "NULL argument"); b->impl->device_iterates(d_x, d_y); });
 }
+
+unsigned pb_ring_trace_read(unsigned long long* h_out, unsigned n) { return pb::tile_ring_trace_read(h_out, n); }
 
 // ---- slab decomposition --------------------------------------------------------------------------
 

@@ -115,6 +115,7 @@ void Comm::release_halo() {
   block_ = nullptr;
   flags_ = nullptr;
   x_in_ = y_in_ = nullptr;
+  x_ll_ = y_ll_ = nullptr;
   col_floats_ = 0;
 }
 
@@ -134,7 +135,7 @@ void Comm::ensure_halo(size_t col_floats) {
     // same geometry as before: just reset the control words
     PB_CUDA(cudaStreamSynchronize(s));
     barrier();
-    PB_CUDA(cudaMemsetAsync(block_, 0, kFlagBytes, s));
+    PB_CUDA(cudaMemsetAsync(block_, 0, kFlagBytes + 4 * col_floats_ * sizeof(float) + 5 * ll_lines() * sizeof(uint4), s));
     PB_CUDA(cudaStreamSynchronize(s));
     x_seq = y_seq = red_seq = 0;
     barrier();
@@ -145,12 +146,14 @@ void Comm::ensure_halo(size_t col_floats) {
   release_halo();
   col_floats_ = col_floats;
   x_seq = y_seq = red_seq = 0;
-  const size_t bytes = kFlagBytes + 4 * col_floats * sizeof(float);
+  const size_t bytes = kFlagBytes + 4 * col_floats * sizeof(float) + 5 * ll_lines() * sizeof(uint4);
   PB_CUDA(cudaMalloc(&block_, bytes));
   PB_CUDA(cudaMemsetAsync(block_, 0, bytes, s));
   flags_ = static_cast<HaloFlags*>(block_);
   x_in_ = reinterpret_cast<float*>(static_cast<char*>(block_) + kFlagBytes);
   y_in_ = x_in_ + 2 * col_floats;
+  x_ll_ = reinterpret_cast<uint4*>(y_in_ + 2 * col_floats);
+  y_ll_ = x_ll_ + 2 * ll_lines();
   stage_x_.resize(col_floats);
   stage_y_.resize(col_floats);
   stage_x_.zero(s);
@@ -208,6 +211,85 @@ float* Comm::y_out(unsigned seq) const {
   if (!p2p_) return const_cast<float*>(stage_y_.data());
   float* base = reinterpret_cast<float*>(static_cast<char*>(right_block_) + kFlagBytes);
   return base + 2 * col_floats_ + (seq & 1u) * col_floats_;
+}
+
+uint4* Comm::x_ll_out(unsigned seq) const {
+  if (!has_left() || !p2p_ || !left_block_) return nullptr;
+  char* base = static_cast<char*>(left_block_) + kFlagBytes + 4 * col_floats_ * sizeof(float);
+  return reinterpret_cast<uint4*>(base) + (seq & 1u) * ll_lines();
+}
+
+uint4* Comm::y_ll_out(unsigned seq) const {
+  if (!has_right() || !p2p_ || !right_block_) return nullptr;
+  char* base = static_cast<char*>(right_block_) + kFlagBytes + 4 * col_floats_ * sizeof(float);
+  return reinterpret_cast<uint4*>(base) + 2 * ll_lines() + (seq % 3u) * ll_lines();
+}
+
+namespace {
+
+// plain column (sequence word protocol of the two-pass kernels) -> flag-in-data lines, local memory only
+__global__ void halo_pack_ll_kernel(const float* __restrict__ plain, uint4* __restrict__ ll, unsigned seq,
+                                    const unsigned* wait_flag, unsigned groups, int* error) {
+  if (wait_flag) {
+    unsigned v;
+    unsigned long long t0 = 0;
+    for (unsigned spins = 0;; ++spins) {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(wait_flag) : "memory");
+      if ((int)(v - seq) >= 0) break;
+      if ((spins & 1023u) == 1023u) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 2000000000ull) { if (error) atomicExch(error, 1); break; }
+      }
+    }
+  }
+  for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < groups; q += gridDim.x * blockDim.x) {
+    const float4 v = __ldcg(reinterpret_cast<const float4*>(plain) + q);
+    ll[2 * q] = make_uint4(__float_as_uint(v.x), seq, __float_as_uint(v.y), seq);
+    ll[2 * q + 1] = make_uint4(__float_as_uint(v.z), seq, __float_as_uint(v.w), seq);
+  }
+}
+
+// flag-in-data lines of sequence number `seq` -> plain column (local; the lines are there: the iteration that
+// consumed them has completed on this stream)
+__global__ void halo_unpack_ll_kernel(const uint4* __restrict__ ll, float* __restrict__ plain, unsigned groups) {
+  for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < groups; q += gridDim.x * blockDim.x) {
+    const uint4 a = __ldcg(ll + 2 * q), b = __ldcg(ll + 2 * q + 1);
+    reinterpret_cast<float4*>(plain)[q] =
+        make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(b.x), __uint_as_float(b.z));
+  }
+}
+
+}  // namespace
+
+void Comm::pack_ll(unsigned xs, unsigned ys) {
+  if (!p2p_ || world_ == 1 || !block_) return;
+  const unsigned groups = static_cast<unsigned>(col_floats_ / 4);
+  const unsigned grid = std::max(1u, std::min(64u, (groups + 255u) / 256u));
+  if (has_right())
+    halo_pack_ll_kernel<<<grid, 256, 0, ctx_->stream>>>(x_slot(xs), const_cast<uint4*>(x_ll(xs)), xs, &flags_->x_seq,
+                                                        groups, &flags_->error);
+  if (has_left())
+    halo_pack_ll_kernel<<<grid, 256, 0, ctx_->stream>>>(y_slot(ys), const_cast<uint4*>(y_ll(ys)), ys, &flags_->y_seq,
+                                                        groups, &flags_->error);
+  PB_CHECK_LAUNCH();
+}
+
+void Comm::unpack_ll_x(unsigned seq) {
+  if (!p2p_ || world_ == 1 || !block_ || !has_right()) return;
+  const unsigned groups = static_cast<unsigned>(col_floats_ / 4);
+  halo_unpack_ll_kernel<<<std::max(1u, std::min(64u, (groups + 255u) / 256u)), 256, 0, ctx_->stream>>>(
+      x_ll(seq), x_slot(seq), groups);
+  PB_CHECK_LAUNCH();
+}
+
+void Comm::unpack_ll_y(unsigned seq) {
+  if (!p2p_ || world_ == 1 || !block_ || !has_left()) return;
+  const unsigned groups = static_cast<unsigned>(col_floats_ / 4);
+  halo_unpack_ll_kernel<<<std::max(1u, std::min(64u, (groups + 255u) / 256u)), 256, 0, ctx_->stream>>>(
+      y_ll(seq), y_slot(seq), groups);
+  PB_CHECK_LAUNCH();
 }
 
 unsigned* Comm::left_x_seq() const {

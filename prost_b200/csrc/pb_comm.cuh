@@ -72,6 +72,18 @@ class Comm {
   void exchange_y(unsigned seq);
   // pass sequence numbers (identical on every rank: all ranks run the same passes)
   unsigned x_seq = 0, y_seq = 0;
+  // --- flag-in-data slots of the one-pass ring kernel (RingHalo, pb_stencil.cuh): two 16-byte lines per four rows
+  const uint4* x_ll(unsigned seq) const { return x_ll_ + (seq & 1u) * ll_lines(); }      // local, from the right
+  const uint4* y_ll(unsigned seq) const { return y_ll_ + (seq % 3u) * ll_lines(); }      // local, from the left
+  uint4* x_ll_out(unsigned seq) const;         // the left neighbour's x slot (p2p only)
+  uint4* y_ll_out(unsigned seq) const;         // the right neighbour's y slot
+  size_t ll_lines() const { return (col_floats_ + 3) / 4 * 2; }        // 16-byte lines per slot
+  // after a two-pass iteration (plain slots + sequence words): repack the received columns x(xs), y(ys) into the
+  // local flag-in-data slots, so that a following one-pass iteration finds them there
+  void pack_ll(unsigned xs, unsigned ys);
+  // before the plain slots are read on the host side of current_solution: the reverse, for one sequence number
+  void unpack_ll_x(unsigned seq);
+  void unpack_ll_y(unsigned seq);
   // throws if a kernel reported a halo timeout
   void check_error();
 
@@ -91,11 +103,14 @@ class Comm {
   void* nccl_ = nullptr;               // ncclComm_t
   bool p2p_ = true;
   size_t col_floats_ = 0;
-  // local IPC block: [HaloFlags | x_in[2][col] | y_in[2][col]]
+  // local IPC block: [header: HaloFlags, reduce words and slots | x_in[2][col] | y_in[2][col] | x_ll[2][2 col] |
+  // y_ll[3][2 col]]
   void* block_ = nullptr;
   HaloFlags* flags_ = nullptr;
   float* x_in_ = nullptr;
   float* y_in_ = nullptr;
+  uint4* x_ll_ = nullptr;              // [2][ll_lines]
+  uint4* y_ll_ = nullptr;              // [3][ll_lines]
   void* left_block_ = nullptr;         // neighbours' blocks mapped into this process (p2p)
   void* right_block_ = nullptr;
   std::vector<void*> peer_blocks_;     // every rank's block (own: block_), p2p only

@@ -193,8 +193,10 @@ __global__ void __launch_bounds__(kBlock) z_variable_kernel(float* __restrict__ 
 
 // ---- backend -------------------------------------------------------------------------------------
 
-// default number of iterations per persistent-ring launch on ONE GPU (0: one launch per iteration)
-constexpr int kRingItersSingleGpu = 0;
+// default number of iterations per persistent-ring launch (0: one launch per iteration).  Multi-iteration
+// launches (RingMulti) are bit-identical but measured SLOWER on 1 and 2 GPUs (profiles/r02_scaling.md): the
+// per-tile release fences sit on the tile pipeline's critical path; PB_RING_ITERS=n enables them for experiments.
+constexpr int kRingItersDefault = 0;
 
 class BackendPDHG : public Backend {
  public:
@@ -245,6 +247,7 @@ class BackendPDHG : public Backend {
   DeviceBuffer<int> ring_error_;
   void slab_apply(float* d_res, const float* d_rhs, const float* d_halo, bool adjoint);
   Comm* comm_ = nullptr;
+  bool halo_in_ll_ = false;            // the newest halo columns live in the ring kernel's flag-in-data slots only
   bool is_check_iteration() const {
     // size_t % int of the reference: a negative residual_iter wraps to a huge modulus, i.e.
     // "only at iteration 0" (Appendix B #4)
@@ -327,6 +330,7 @@ void BackendPDHG::initialize(const float* h_x0, size_t nx0, const float* h_y0, s
   cudaStream_t s = ctx_->stream;
 
   iteration_ = 0;
+  halo_in_ll_ = false;
   PdhgState st{};
   st.tau = static_cast<float>(opts_.tau0);
   st.sigma = static_cast<float>(opts_.sigma0);
@@ -412,11 +416,9 @@ void BackendPDHG::initialize(const float* h_x0, size_t nx0, const float* h_y0, s
   }
   tile_iterations_ = 0;
   {
-    // Iterations per launch of the persistent ring (RingMulti): on slabs the kernel boundary (launch latency,
-    // pipeline prologue / tail, rank skew) costs more than the slab's HBM time, so stretches of non-refresh
-    // iterations run as one launch by default; PB_RING_ITERS overrides (0 / 1: one launch per iteration).
+    // Iterations per launch of the persistent ring (RingMulti); PB_RING_ITERS overrides the default.
     static const int ring_iters = [] { const char* e = getenv("PB_RING_ITERS"); return e ? atoi(e) : -1; }();
-    const int dflt = (comm_ && comm_->world() > 1) ? 16 : kRingItersSingleGpu;
+    const int dflt = kRingItersDefault;
     ring_iters_ = std::min(ring_iters >= 0 ? ring_iters : dflt, 32);
   }
   if (comm_) {
@@ -612,6 +614,9 @@ void BackendPDHG::iteration_fused() {
     np = off;
     y_.swap(y_prev_);
     if (comm_) { comm_->exchange_y(ys); stencil_.geom.halo = SlabHalo(); }
+    // the one-pass ring kernel reads its halo columns from flag-in-data slots: repack what this two-pass
+    // iteration received (iteration 0 of a ROF-shaped slab problem)
+    if (comm_ && tile_ok_) { comm_->pack_ll(xs, ys); halo_in_ll_ = false; }
     if (prof_ev_) PB_CUDA(cudaEventRecord(prof_ev_[2], ctx_->stream));
 
   }
@@ -687,28 +692,20 @@ RingHalo BackendPDHG::slab_ring_halo() {
   h.has_right = comm_->has_right();
   const unsigned ys_in = comm_->y_seq;               // newest y halo (left neighbour's previous iteration)
   const unsigned xs = ++comm_->x_seq, ys = ++comm_->y_seq;
-  HaloFlags* f = comm_->flags();
-  h.error = &f->error;
+  h.error = &comm_->flags()->error;
   if (h.has_left) {
-    h.yl_a = comm_->y_slot(ys_in);
-    h.yl_b = comm_->y_slot(ys_in - 1);
-    h.x_out = comm_->x_out(xs);
-    h.y_wait_flag = &f->y_seq;
+    for (unsigned p = 0; p < 3; ++p) h.yl_ll[p] = comm_->y_ll(p);
+    for (unsigned p = 0; p < 2; ++p) h.x_out_ll[p] = comm_->x_ll_out(p);
     h.y_wait_seq = ys_in;
-    h.x_done = &f->done_primal;
-    h.x_signal = comm_->left_x_seq();
     h.x_signal_seq = xs;
   }
   if (h.has_right) {
-    h.xr_n = comm_->x_slot(xs);
-    h.xr_o = comm_->x_slot(xs - 1);
-    h.y_out = comm_->y_out(ys);
-    h.x_wait_flag = &f->x_seq;
+    for (unsigned p = 0; p < 2; ++p) h.xr_ll[p] = comm_->x_ll(p);
+    for (unsigned p = 0; p < 3; ++p) h.y_out_ll[p] = comm_->y_ll_out(p);
     h.x_wait_seq = xs;
-    h.y_done = &f->done_dual;
-    h.y_signal = comm_->right_y_seq();
     h.y_signal_seq = ys;
   }
+  halo_in_ll_ = true;
   return h;
 }
 
@@ -892,14 +889,6 @@ bool BackendPDHG::multi_iteration_launch(int n_it) {
   const unsigned xs0 = comm_ ? comm_->x_seq : 0, ys0 = comm_ ? comm_->y_seq : 0;
   if (comm_) {
     h = slab_ring_halo();                       // sequence numbers of the launch's first iteration
-    for (unsigned p = 0; p < 2; ++p) {
-      h.y_slot[p] = comm_->y_slot(p);
-      h.x_slot[p] = comm_->x_slot(p);
-      h.x_out_slot[p] = comm_->x_out(p);
-      h.y_out_slot[p] = comm_->y_out(p);
-    }
-    h.x_done_it = ring_edge_counters_.data();
-    h.y_done_it = ring_edge_counters_.data() + 32;
   }
   const unsigned grid = tile_multi_iteration_launch(ctx_, stencil_, g_descs_[0], f_descs_[0], x_.data(), y_.data(),
                                                     x_prev_.data(), y_prev_.data(), T, S, d_state_.data(), mi,
@@ -964,6 +953,12 @@ void BackendPDHG::current_solution(float* h_x, float* h_z, float* h_y, float* h_
   if (h_y) download_to_host(ctx_, h_y, y_.data(), m);
   if (h_w || h_z) {
     const ScaleRef T = problem_->right_ref(), S = problem_->left_ref();
+    if (fused_ && comm_ && halo_in_ll_) {
+      // one-pass iterations keep the halo columns in flag-in-data slots; slab_apply reads plain columns
+      comm_->unpack_ll_x(comm_->x_seq);
+      comm_->unpack_ll_x(comm_->x_seq - 1);
+      comm_->unpack_ll_y(comm_->y_seq - 1);
+    }
     if (fused_) {
       // K x, K x_prev and K^T y_prev are not stored in fused mode: rebuild them with the
       // unfused operator, honouring the zero-initialised history of the reference

@@ -267,7 +267,8 @@ __device__ __forceinline__ void group_apply(const ProxDesc& p, uint32_t tx, floa
 //   float  load(r, e, i)            argument of global element e (component slot i)
 //   void   post(r, e, i, result)    called after the prox
 //   void   finish(r)                block-level epilogue (residual partials)
-template <int CAP, class Src>
+// KIND >= 0 fixes the prox kind at compile time (no run-time dispatch, no dead cases in the kernel).
+template <int CAP, class Src, int KIND = -1>
 __global__ void __launch_bounds__(kBlock) prox_pass_kernel(const ProxDesc p, const Src src,
                                                            float* __restrict__ out,
                                                            const ScaleRef tdiag, const bool invert) {
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(kBlock) prox_pass_kernel(const ProxDesc p, con
         v[i] = src.load(r, e, i);
       }
     }
-    group_apply<CAP>(p, tx, v, td, tau, invert);
+    group_apply<CAP, KIND>(p, tx, v, td, tau, invert);
 #pragma unroll
     for (int i = 0; i < CAP; ++i) {
       if (i < (int)p.dim) {

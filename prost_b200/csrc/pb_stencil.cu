@@ -237,8 +237,9 @@ template <int CAPL, bool HAS_ID, bool CHECK>
 static bool simplex_staged_launch_k(Context* ctx, unsigned grid, const GradGeom& g, const ProxDesc& d, const float* x,
                                     const float* y, const float* y_prev, float Tval, const PdhgState* st,
                                     bool ktyprev_zero, double* partials, float* x_out) {
-  auto kernel = grad_primal_simplex_staged_kernel<CAPL, HAS_ID, CHECK, kSlab>;
-  const size_t smem = primal_staged_smem(CAPL, HAS_ID, CHECK);       // sized for the y_prev operands as well
+  constexpr int LC = CAPL < kStagedChunk ? CAPL : kStagedChunk;
+  auto kernel = grad_primal_simplex_staged_kernel<CAPL, LC, HAS_ID, CHECK, kSlab>;
+  const size_t smem = primal_staged_smem(CAPL, LC, HAS_ID, CHECK);   // sized for the y_prev operands as well
   static const bool ok = staged_configure(kernel, smem);
   if (!ok) { cudaGetLastError(); return false; }
   kernel<<<grid, kStagedBlock, smem, ctx->stream>>>(g, d, x, y, y_prev, Tval, st, ktyprev_zero ? 1 : 0, partials,
@@ -302,8 +303,9 @@ template <int CAPL, int FN, bool CHECK>
 static bool dual_staged_launch_k(Context* ctx, unsigned grid, const GradGeom& g, const ProxDesc& d, const float* y,
                                  const float* x_new, const float* x_old, float Sval, const PdhgState* st,
                                  bool kxprev_zero, double* partials, float* y_out) {
-  auto kernel = grad_dual_norm2_staged_kernel<CAPL, FN, CHECK, kSlab>;
-  const size_t smem = dual_staged_smem(CAPL);
+  constexpr int LC = CAPL < kStagedChunk ? CAPL : kStagedChunk;
+  auto kernel = grad_dual_norm2_staged_kernel<CAPL, LC, FN, CHECK, kSlab>;
+  const size_t smem = dual_staged_smem(CAPL, LC, CHECK);
   static const bool ok = staged_configure(kernel, smem);
   if (!ok) { cudaGetLastError(); return false; }
   kernel<<<grid, kStagedBlock, smem, ctx->stream>>>(g, d, y, x_new, x_old, Sval, st, kxprev_zero ? 1 : 0, partials,
@@ -412,17 +414,29 @@ PB_DECLARE_DUAL(PB_FLAVOUR(stencil_dual_norm2_launch)) {
 
 #elif PB_STENCIL_PART == 3
 
+template <int CAP, int KIND = -1>
+static void ident_launch_k(Context* ctx, unsigned grid, const GradGeom& g, const ProxDesc& d, const float* y,
+                           const float* x_new, const float* x_old, ScaleRef S, const PdhgState* st,
+                           bool kxprev_zero, bool check, double* partials, float* y_out) {
+  if (check) {
+    IdentityDualSource<CAP, true> src{y, x_new, x_old, S, st, g.id_factor, g.id_row, kxprev_zero, partials};
+    prox_pass_kernel<CAP, IdentityDualSource<CAP, true>, KIND><<<grid, kBlock, 0, ctx->stream>>>(d, src, y_out, S, false);
+  } else {
+    IdentityDualSource<CAP, false> src{y, x_new, x_old, S, st, g.id_factor, g.id_row, kxprev_zero, partials};
+    prox_pass_kernel<CAP, IdentityDualSource<CAP, false>, KIND><<<grid, kBlock, 0, ctx->stream>>>(d, src, y_out, S, false);
+  }
+}
+
 template <int CAP>
 static void ident_launch(Context* ctx, unsigned grid, const GradGeom& g, const ProxDesc& d, const float* y,
                          const float* x_new, const float* x_old, ScaleRef S, const PdhgState* st,
                          bool kxprev_zero, bool check, double* partials, float* y_out) {
-  if (check) {
-    IdentityDualSource<CAP, true> src{y, x_new, x_old, S, st, g.id_factor, g.id_row, kxprev_zero, partials};
-    prox_pass_kernel<CAP, IdentityDualSource<CAP, true>><<<grid, kBlock, 0, ctx->stream>>>(d, src, y_out, S, false);
-  } else {
-    IdentityDualSource<CAP, false> src{y, x_new, x_old, S, st, g.id_factor, g.id_row, kxprev_zero, partials};
-    prox_pass_kernel<CAP, IdentityDualSource<CAP, false>><<<grid, kBlock, 0, ctx->stream>>>(d, src, y_out, S, false);
-  }
+  // the lifted multilabel energy's identity rows carry the epigraph projection on (x, y) pairs: compiled without
+  // the run-time prox dispatch (whose dead cases cost registers and local memory, profiles/r01_lifting.md)
+  if (CAP == 2 && d.kind == kProxEpiQuad)
+    ident_launch_k<CAP, kProxEpiQuad>(ctx, grid, g, d, y, x_new, x_old, S, st, kxprev_zero, check, partials, y_out);
+  else
+    ident_launch_k<CAP, -1>(ctx, grid, g, d, y, x_new, x_old, S, st, kxprev_zero, check, partials, y_out);
 }
 
 unsigned stencil_dual_identity_launch(Context* ctx, const GradGeom& g, const ProxDesc& d, const float* y,

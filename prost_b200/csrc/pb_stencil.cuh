@@ -53,45 +53,36 @@ struct SlabHalo {
   int* error = nullptr;                  // set when a wait times out
 };
 
-// Halo descriptor of the one-pass ring kernel (pb_tile.cu) on a slab: ONE launch does the primal and the
-// dual step, so it talks to both neighbours.  Same slots, sequence numbers and flags as the two-pass
-// protocol above (the two kinds of iteration interleave freely):
-//   left edge  (tiles with tx = 0, image column 0): waits for the left neighbour's newest y.gx column
-//              (yl_a; yl_b = the one before, residual refresh only), stores its new x column 0 into the
-//              left neighbour's x slot and publishes x_signal_seq once all left-edge tiles are done;
-//   right edge (tiles owning column nx-1): waits for the right neighbour's new x column 0 of THIS
-//              iteration (xr_n; xr_o = previous iterate), stores its new y.gx column nx-1 into the right
-//              neighbour's y slot and publishes y_signal_seq once all right-edge tiles are done.
-// Both edge tile groups are walked first (see the tile order in the kernel), so in steady state the
-// columns arrive long before they are needed.
+// Halo descriptor of the one-pass ring kernel (pb_tile.cu) on a slab: ONE launch does the primal and the dual
+// step, so it talks to both neighbours.  Its edge columns travel in a flag-in-data layout ("LL", as in NCCL's
+// low-latency protocol): every group of four rows is two 16-byte lines {v0, seq, v1, seq} {v2, seq, v3, seq},
+// each 8-byte half carrying the sequence number of the iteration that produced it.  The producer's edge warp
+// stores the lines straight into the neighbour's memory over NVLink (8-byte halves arrive atomically); the
+// consumer's edge warp polls the two lines of ITS rows until all four tags match -- no system-scope fence, no
+// edge-tile counter and no separate flag sit between the neighbour's store and this GPU's load (round 1 paid a
+// fence.sys on the compute path plus a counter and a flag hop per edge and iteration, profiles/r01_scaling.md).
+//   left edge  (tiles of column 0): waits for the left neighbour's newest y.gx column nx-1 (sequence
+//              y_wait_seq, produced by its PREVIOUS iteration) row group by row group, computes column 0 and
+//              stores its new x column 0 into the left neighbour's x slot tagged x_signal_seq;
+//   right edge (tiles owning column nx-1): waits for the right neighbour's new x column 0 of THIS iteration
+//              (x_wait_seq; the previous iterate's column is still in the other slot), stores its new y.gx
+//              column nx-1 into the right neighbour's y slot tagged y_signal_seq.
+// Slot reuse: x has two slots (sequence & 1), y three (sequence % 3: the residual-refresh launch also reads the
+// y column before the newest one).  A row group is overwritten only by a thread that has already consumed what
+// the overwritten data fed (x: the producer of x(s+2)[r] has seen y(s+1)[r], whose producer had read x(s)[r];
+// y(s+3)[r] needs x(s+3)[r], i.e. the neighbour has started launch s+3 and finished every read of launch s+2).
+// The left-edge tile column is walked first and the right-edge one in the second wave (pb_tile.cu: decode), so
+// in steady state the columns arrive before they are needed.
 struct RingHalo {
   int has_left = 0, has_right = 0;
-  const float* yl_a = nullptr;
-  const float* yl_b = nullptr;
-  float* x_out = nullptr;
-  const unsigned* y_wait_flag = nullptr;
-  unsigned y_wait_seq = 0;
-  unsigned* x_done = nullptr;
-  unsigned* x_signal = nullptr;
-  unsigned x_signal_seq = 0;
-  const float* xr_n = nullptr;
-  const float* xr_o = nullptr;
-  float* y_out = nullptr;
-  const unsigned* x_wait_flag = nullptr;
-  unsigned x_wait_seq = 0;
-  unsigned* y_done = nullptr;
-  unsigned* y_signal = nullptr;
-  unsigned y_signal_seq = 0;
-  unsigned n_edge_tiles = 0;             // tiles per edge = tiles_y * L (filled by the launcher)
-  int* error = nullptr;
-  // multi-iteration launches (RingMulti): iteration `it` of the launch uses sequence numbers *_seq + it, the
-  // slots of that parity and its own pair of edge counters
-  const float* y_slot[2] = {nullptr, nullptr};     // local slots by (sequence number & 1)
-  const float* x_slot[2] = {nullptr, nullptr};
-  float* x_out_slot[2] = {nullptr, nullptr};       // the neighbours' slots
-  float* y_out_slot[2] = {nullptr, nullptr};
-  unsigned* x_done_it = nullptr;                   // [n_it] self-resetting edge counters
-  unsigned* y_done_it = nullptr;
+  const uint4* yl_ll[3] = {nullptr, nullptr, nullptr};   // local y slots by (sequence % 3), written by the left rank
+  const uint4* xr_ll[2] = {nullptr, nullptr};            // local x slots by (sequence & 1), written by the right rank
+  uint4* x_out_ll[2] = {nullptr, nullptr};               // the left neighbour's x slots
+  uint4* y_out_ll[3] = {nullptr, nullptr, nullptr};      // the right neighbour's y slots
+  unsigned y_wait_seq = 0;             // newest y column from the left (0: none yet)
+  unsigned x_wait_seq = 0;             // x column of this iteration from the right
+  unsigned x_signal_seq = 0, y_signal_seq = 0;
+  int* error = nullptr;                // set when a wait times out
 };
 
 // Several consecutive non-refresh iterations in ONE launch of the persistent ring kernel (experimental,
@@ -112,6 +103,10 @@ struct RingMulti {
   // finished; a work item waits for the CTAs that own its neighbour tiles)
   int coarse = 0;
   int debug = 0;                       // timing experiments only: bit 0 skips the release, bit 1 the probe
+  // PB_RING_TRACE: per launch {first CTA start, last CTA end, longest left-edge halo wait, longest right-edge halo
+  // wait} in globaltimer ns (atomicMin / atomicMax), slot = launch number modulo the buffer length
+  unsigned long long* trace = nullptr;
+  unsigned trace_slot = 0;
 };
 
 // Residual-refresh launches of the ring kernel finish the iteration themselves: the last CTA to arrive (ticket)
@@ -730,6 +725,7 @@ void tile_iteration_launch(Context* ctx, const StencilPlan& plan, const ProxDesc
                            float* x_out, float* y_out, const RingHalo* halo = nullptr);
 // slab mode: is the persistent ring (the only one-pass variant that speaks the halo protocol) available?
 bool tile_ring_available();
+unsigned tile_ring_trace_read(unsigned long long* h_out, unsigned n);      // PB_RING_TRACE experiments
 // several consecutive non-refresh iterations in one launch (RingMulti; experimental, PB_RING_ITERS > 1)
 unsigned tile_ring_tile_count(const StencilPlan& plan);
 unsigned tile_multi_iteration_launch(Context* ctx, const StencilPlan& plan, const ProxDesc& pg, const ProxDesc& pf,

@@ -43,15 +43,28 @@ __device__ __forceinline__ float staged_adj(float a1, float a2, float a3, float 
   return out;
 }
 
+// Labels are staged in chunks of LC: chunk c+1 is in flight (its own cp.async group, second buffer) while chunk c
+// is turned into prox arguments that stay in registers, so a thread holds 2 * LC labels of operands in shared
+// memory instead of all CAPL.  Staging everything at once (round 1: 768 B per thread at 32 labels) left 6-8
+// resident warps per SM and 0.33 issued instructions per cycle and scheduler (profiles/r01_lifting.md); with
+// LC = 4 the footprint is 192-256 B per thread and the register file, not shared memory, bounds the occupancy.
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int kStagedChunk = 4;
+
 // ---- primal pass: x+ = proj_simplex( x - tau T K^T y ) over the L <= CAPL labels of a pixel -----------------
-// operands per label: x, p1, p1-left, p2, p2-up (+ identity rows) (+ the same five of y_prev when CHECK)
-template <int CAPL, bool HAS_ID, bool CHECK, bool SLAB>
-__global__ void __launch_bounds__(kStagedBlock) grad_primal_simplex_staged_kernel(
+// operands per label: x, p1, p1-left, p2, p2-up (+ identity rows) (+ the same dual operands of y_prev when CHECK)
+template <int CAPL, int LC, bool HAS_ID, bool CHECK, bool SLAB>
+__global__ void __launch_bounds__(kStagedBlock, CHECK ? 2 : 8) grad_primal_simplex_staged_kernel(
     const GradGeom g, const ProxDesc p, const float* __restrict__ x, const float* __restrict__ y,
     const float* __restrict__ y_prev, const float Tval, const PdhgState* __restrict__ st, const int ktyprev_zero,
     double* __restrict__ partials, float* __restrict__ x_out) {
   extern __shared__ __align__(16) float staged_smem[];
-  constexpr int NA = HAS_ID ? 6 : 5;                  // arrays of the current dual iterate (incl. x)
+  constexpr int NA = HAS_ID ? 6 : 5;                  // arrays of the current iterate (x + dual operands)
+  constexpr int NT = NA + (CHECK ? NA - 1 : 0);       // + the dual operands of y_prev
+  constexpr int NCH = (CAPL + LC - 1) / LC;
   constexpr int B = kStagedBlock;
   const float tau = st->tau;
   double acc0 = 0.0, acc1 = 0.0;
@@ -70,41 +83,68 @@ __global__ void __launch_bounds__(kStagedBlock) grad_primal_simplex_staged_kerne
     const bool has3 = y0 + 1 != g.ny, has4 = y0 > 0;
     const bool prev = CHECK && !ktyprev_zero;
     float* s = staged_smem + threadIdx.x;
-    auto stage_dual = [&](const float* __restrict__ q, const float* __restrict__ q_halo, int a0, int li,
-                          uint32_t idx) {
+    // chunk buffer b, array a, label slot j of the chunk; (CHECK) keep[k][label]: xo, K^T y, K^T y_prev
+    auto at = [&](int b, int a, int j) -> float* { return s + ((b * NT + a) * LC + j) * B; };
+    float* keep = s + 2 * NT * LC * B;
+    auto stage_dual = [&](const float* __restrict__ q, const float* __restrict__ q_halo, int b, int a0, int j,
+                          int li, uint32_t idx) {
       const float* q1 = q;
       const float* q2 = q + g.plane;
-      cp_async4(s + ((a0 + 0) * CAPL + li) * B, q1 + idx, has1);
-      cp_async4(s + ((a0 + 1) * CAPL + li) * B,
+      cp_async4(at(b, a0 + 0, j), q1 + idx, has1);
+      cp_async4(at(b, a0 + 1, j),
                 left_in ? q1 + idx - g.ny : (left_halo ? q_halo + y0 + li * g.ny : q1), left_in || left_halo);
-      cp_async4(s + ((a0 + 2) * CAPL + li) * B, q2 + idx, has3);
-      cp_async4(s + ((a0 + 3) * CAPL + li) * B, has4 ? q2 + idx - 1 : q2, has4);
-      if (HAS_ID) cp_async4(s + ((a0 + 4) * CAPL + li) * B, q + g.id_row + idx, true);
+      cp_async4(at(b, a0 + 2, j), q2 + idx, has3);
+      cp_async4(at(b, a0 + 3, j), has4 ? q2 + idx - 1 : q2, has4);
+      if (HAS_ID) cp_async4(at(b, a0 + 4, j), q + g.id_row + idx, true);
     };
+    auto stage_chunk = [&](int c) {
+      const int b = c & 1;
 #pragma unroll
-    for (int li = 0; li < CAPL; ++li) {
-      if (li < nl) {
-        const uint32_t idx = pix + li * g.nxny;
-        cp_async4(s + (0 * CAPL + li) * B, x + idx, true);
-        stage_dual(y, g.halo.in_a, 1, li, idx);
-        if (prev) stage_dual(y_prev, g.halo.in_b, NA, li, idx);
+      for (int j = 0; j < LC; ++j) {
+        const int li = c * LC + j;
+        if (li < CAPL && li < nl) {
+          const uint32_t idx = pix + li * g.nxny;
+          cp_async4(at(b, 0, j), x + idx, true);
+          stage_dual(y, g.halo.in_a, b, 1, j, li, idx);
+          if (prev) stage_dual(y_prev, g.halo.in_b, b, NA, j, li, idx);
+        }
       }
-    }
-    cp_async_wait_all();
-
+      cp_async_commit();
+    };
+    stage_chunk(0);
     float v[CAPL], tdl[CAPL];
 #pragma unroll
-    for (int li = 0; li < CAPL; ++li) {
-      v[li] = 0.f;
-      tdl[li] = Tval;
-      if (li < nl) {
-        const float k = staged_adj<HAS_ID>(s[(1 * CAPL + li) * B], s[(2 * CAPL + li) * B], s[(3 * CAPL + li) * B],
-                                           s[(4 * CAPL + li) * B], HAS_ID ? s[(5 * CAPL + li) * B] : 0.f,
-                                           g.id_factor);
-        v[li] = primal_prox_arg(s[(0 * CAPL + li) * B], tau, Tval, k);
+    for (int c = 0; c < NCH; ++c) {
+      if (c + 1 < NCH) stage_chunk(c + 1);
+      else cp_async_commit();                          // empty group: uniform accounting for wait_group 1
+      cp_async_wait_group<1>();
+      const int b = c & 1;
+#pragma unroll
+      for (int j = 0; j < LC; ++j) {
+        const int li = c * LC + j;
+        if (li < CAPL) {
+          v[li] = 0.f;
+          tdl[li] = Tval;
+          if (li < nl) {
+            const float k = staged_adj<HAS_ID>(*at(b, 1, j), *at(b, 2, j), *at(b, 3, j), *at(b, 4, j),
+                                               HAS_ID ? *at(b, 5, j) : 0.f, g.id_factor);
+            const float xo = *at(b, 0, j);
+            v[li] = primal_prox_arg(xo, tau, Tval, k);
+            if (CHECK) {
+              float kp = 0.f;
+              if (prev)
+                kp = staged_adj<HAS_ID>(*at(b, NA + 0, j), *at(b, NA + 1, j), *at(b, NA + 2, j), *at(b, NA + 3, j),
+                                        HAS_ID ? *at(b, NA + 4, j) : 0.f, g.id_factor);
+              keep[(0 * CAPL + li) * B] = xo;
+              keep[(1 * CAPL + li) * B] = k;
+              keep[(2 * CAPL + li) * B] = kp;
+            }
+          }
+        }
       }
     }
     group_apply<CAPL, kProxSimplex, -1>(p, pix, v, tdl, tau, false);
+    const float sq = sqrtf(Tval);
 #pragma unroll
     for (int li = 0; li < CAPL; ++li) {
       if (li < nl) {
@@ -113,16 +153,7 @@ __global__ void __launch_bounds__(kStagedBlock) grad_primal_simplex_staged_kerne
         if (SLAB && edge) g.halo.out[y0 + li * g.ny] = v[li];       // new column 0 -> left neighbour
         if (CHECK) {
           // dual residual (backend_pdhg.cu:73-94), same expressions as grad_primal_body
-          const float xo = s[(0 * CAPL + li) * B];
-          const float k = staged_adj<HAS_ID>(s[(1 * CAPL + li) * B], s[(2 * CAPL + li) * B],
-                                             s[(3 * CAPL + li) * B], s[(4 * CAPL + li) * B],
-                                             HAS_ID ? s[(5 * CAPL + li) * B] : 0.f, g.id_factor);
-          float kp = 0.f;
-          if (prev)
-            kp = staged_adj<HAS_ID>(s[((NA + 0) * CAPL + li) * B], s[((NA + 1) * CAPL + li) * B],
-                                    s[((NA + 2) * CAPL + li) * B], s[((NA + 3) * CAPL + li) * B],
-                                    HAS_ID ? s[((NA + 4) * CAPL + li) * B] : 0.f, g.id_factor);
-          const float sq = sqrtf(Tval);
+          const float xo = keep[(0 * CAPL + li) * B], k = keep[(1 * CAPL + li) * B], kp = keep[(2 * CAPL + li) * B];
           const float w_hat = (xo - v[li]) / (tau * sq) - sq * kp;
           const float diff = w_hat + sq * k;
           acc0 += static_cast<double>(diff * diff);
@@ -138,22 +169,25 @@ __global__ void __launch_bounds__(kStagedBlock) grad_primal_simplex_staged_kerne
   }
 }
 
-inline size_t primal_staged_smem(int capl, bool has_id, bool check_prev) {
+inline size_t primal_staged_smem(int capl, int lc, bool has_id, bool check) {
   const int na = has_id ? 6 : 5;
-  return static_cast<size_t>(na + (check_prev ? na - 1 : 0)) * capl * kStagedBlock * sizeof(float);
+  const int nt = na + (check ? na - 1 : 0);
+  return static_cast<size_t>(2 * nt * lc + (check ? 3 * capl : 0)) * kStagedBlock * sizeof(float);
 }
 
 // ---- dual pass on the gradient rows: y+ = prox_Norm2( y + sigma S ((1+theta) K x+ - theta K x) ) -----------
 // group = the 2L gradient components of a pixel (component c*L + l), scalar weights, uniform Sigma.
 // operands per label: x+ (centre, right, down), x (centre, right, down), y.gx, y.gy
-template <int CAPL, int FN, bool CHECK, bool SLAB>
-__global__ void __launch_bounds__(kStagedBlock) grad_dual_norm2_staged_kernel(
+template <int CAPL, int LC, int FN, bool CHECK, bool SLAB>
+__global__ void __launch_bounds__(kStagedBlock, CHECK ? 2 : 6) grad_dual_norm2_staged_kernel(
     const GradGeom g, const ProxDesc p, const float* __restrict__ y, const float* __restrict__ xn,
     const float* __restrict__ xo, const float Sval, const PdhgState* __restrict__ st, const int kxprev_zero,
     double* __restrict__ partials, float* __restrict__ y_out) {
   extern __shared__ __align__(16) float staged_smem[];
   constexpr int B = kStagedBlock;
   constexpr int CAP = 2 * CAPL;
+  constexpr int NT = 8;
+  constexpr int NCH = (CAPL + LC - 1) / LC;
   const float sigma = st->sigma, theta = st->theta;
   double acc0 = 0.0, acc1 = 0.0;
   const uint32_t total = g.q * g.nx;
@@ -170,42 +204,66 @@ __global__ void __launch_bounds__(kStagedBlock) grad_dual_norm2_staged_kernel(
     const bool right_in = xx < g.nx - 1, right_halo = SLAB && !right_in && g.halo.has_right;
     const bool has_r = right_in || right_halo, has_d = y0 + 1 < g.ny;
     float* s = staged_smem + threadIdx.x;
-    auto stage_primal = [&](const float* __restrict__ u, const float* __restrict__ u_halo, int a0, int li,
-                            uint32_t idx) {
-      cp_async4(s + ((a0 + 0) * CAPL + li) * B, u + idx, true);
-      cp_async4(s + ((a0 + 1) * CAPL + li) * B,
+    auto at = [&](int b, int a, int j) -> float* { return s + ((b * NT + a) * LC + j) * B; };
+    // (CHECK) keep[k][label]: y.gx, y.gy, extrapolated K x (x, y), K x+ (x, y)
+    float* keep = s + 2 * NT * LC * B;
+    auto stage_primal = [&](const float* __restrict__ u, const float* __restrict__ u_halo, int b, int a0, int j,
+                            int li, uint32_t idx) {
+      cp_async4(at(b, a0 + 0, j), u + idx, true);
+      cp_async4(at(b, a0 + 1, j),
                 right_in ? u + idx + g.ny : (right_halo ? u_halo + y0 + li * g.ny : u), has_r);
-      cp_async4(s + ((a0 + 2) * CAPL + li) * B, has_d ? u + idx + 1 : u, has_d);
+      cp_async4(at(b, a0 + 2, j), has_d ? u + idx + 1 : u, has_d);
     };
+    auto stage_chunk = [&](int c) {
+      const int b = c & 1;
 #pragma unroll
-    for (int li = 0; li < CAPL; ++li) {
-      if (li < nl) {
-        const uint32_t idx = pix + li * g.nxny;
-        stage_primal(xn, g.halo.in_a, 0, li, idx);
-        if (!kxprev_zero) stage_primal(xo, g.halo.in_b, 3, li, idx);
-        cp_async4(s + (6 * CAPL + li) * B, y + idx, true);
-        cp_async4(s + (7 * CAPL + li) * B, y + g.plane + idx, true);
+      for (int j = 0; j < LC; ++j) {
+        const int li = c * LC + j;
+        if (li < CAPL && li < nl) {
+          const uint32_t idx = pix + li * g.nxny;
+          stage_primal(xn, g.halo.in_a, b, 0, j, li, idx);
+          if (!kxprev_zero) stage_primal(xo, g.halo.in_b, b, 3, j, li, idx);
+          cp_async4(at(b, 6, j), y + idx, true);
+          cp_async4(at(b, 7, j), y + g.plane + idx, true);
+        }
       }
-    }
-    cp_async_wait_all();
-
-    // grad_fwd<1, false, .>: gx = right - centre (0 on the last column), gy = down - centre (0 on the last row)
-    auto k_of = [&](int a0, int li, float& kx, float& ky) {
-      const float c = s[((a0 + 0) * CAPL + li) * B];
-      kx = has_r ? s[((a0 + 1) * CAPL + li) * B] - c : 0.f;
-      ky = has_d ? s[((a0 + 2) * CAPL + li) * B] - c : 0.f;
+      cp_async_commit();
     };
+    // grad_fwd<1, false, .>: gx = right - centre (0 on the last column), gy = down - centre (0 on the last row)
+    auto k_of = [&](int b, int a0, int j, float& kx, float& ky) {
+      const float c = *at(b, a0 + 0, j);
+      kx = has_r ? *at(b, a0 + 1, j) - c : 0.f;
+      ky = has_d ? *at(b, a0 + 2, j) - c : 0.f;
+    };
+    stage_chunk(0);
     float arg[CAP][1];
 #pragma unroll
-    for (int i = 0; i < CAP; ++i) arg[i][0] = 0.f;       // unused label slots do not change a 2-norm
+    for (int c = 0; c < NCH; ++c) {
+      if (c + 1 < NCH) stage_chunk(c + 1);
+      else cp_async_commit();
+      cp_async_wait_group<1>();
+      const int b = c & 1;
 #pragma unroll
-    for (int li = 0; li < CAPL; ++li) {
-      if (li < nl) {
-        float k1x, k1y, k0x = 0.f, k0y = 0.f;
-        k_of(0, li, k1x, k1y);
-        if (!kxprev_zero) k_of(3, li, k0x, k0y);
-        arg[li][0] = dual_prox_arg(s[(6 * CAPL + li) * B], sigma, Sval, dual_extrapolate(theta, k1x, k0x));
-        arg[CAPL + li][0] = dual_prox_arg(s[(7 * CAPL + li) * B], sigma, Sval, dual_extrapolate(theta, k1y, k0y));
+      for (int j = 0; j < LC; ++j) {
+        const int li = c * LC + j;
+        if (li < CAPL) {
+          arg[li][0] = 0.f;                            // unused label slots do not change a 2-norm
+          arg[CAPL + li][0] = 0.f;
+          if (li < nl) {
+            float k1x, k1y, k0x = 0.f, k0y = 0.f;
+            k_of(b, 0, j, k1x, k1y);
+            if (!kxprev_zero) k_of(b, 3, j, k0x, k0y);
+            const float ex = dual_extrapolate(theta, k1x, k0x), ey = dual_extrapolate(theta, k1y, k0y);
+            const float ygx = *at(b, 6, j), ygy = *at(b, 7, j);
+            arg[li][0] = dual_prox_arg(ygx, sigma, Sval, ex);
+            arg[CAPL + li][0] = dual_prox_arg(ygy, sigma, Sval, ey);
+            if (CHECK) {
+              keep[(0 * CAPL + li) * B] = ygx; keep[(1 * CAPL + li) * B] = ygy;
+              keep[(2 * CAPL + li) * B] = ex;  keep[(3 * CAPL + li) * B] = ey;
+              keep[(4 * CAPL + li) * B] = k1x; keep[(5 * CAPL + li) * B] = k1y;
+            }
+          }
+        }
       }
     }
     Coeffs7 c;
@@ -215,6 +273,7 @@ __global__ void __launch_bounds__(kStagedBlock) grad_dual_norm2_staged_kernel(
     const float tau_eff = effective_tau(sigma, Sval, false);
     if (coeffs_simple(c)) norm2_lanes<1, CAP, true>(fn, arg, c, tau_eff);
     else norm2_lanes<1, CAP, false>(fn, arg, c, tau_eff);
+    const float sq = sqrtf(Sval);
 #pragma unroll
     for (int li = 0; li < CAPL; ++li) {
       if (li < nl) {
@@ -224,16 +283,13 @@ __global__ void __launch_bounds__(kStagedBlock) grad_dual_norm2_staged_kernel(
         if (SLAB && edge) g.halo.out[y0 + li * g.ny] = arg[li][0];   // last gx column -> right neighbour
         if (CHECK) {
           // primal residual (backend_pdhg.cu:97-120), same expressions as grad_dual_body
-          float k1[2], k0[2] = {0.f, 0.f};
-          k_of(0, li, k1[0], k1[1]);
-          if (!kxprev_zero) k_of(3, li, k0[0], k0[1]);
-          const float sq = sqrtf(Sval);
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
-            const float yo = s[((6 + cc) * CAPL + li) * B];
-            const float ext = dual_extrapolate(theta, k1[cc], k0[cc]);
+            const float yo = keep[((0 + cc) * CAPL + li) * B];
+            const float ext = keep[((2 + cc) * CAPL + li) * B];
+            const float k1 = keep[((4 + cc) * CAPL + li) * B];
             const float z_hat = (yo - arg[cc * CAPL + li][0]) / (sigma * sq) + sq * ext;
-            const float diff = z_hat - sq * k1[cc];
+            const float diff = z_hat - sq * k1;
             acc0 += static_cast<double>(diff * diff);
             acc1 += static_cast<double>(z_hat * z_hat);
           }
@@ -248,7 +304,9 @@ __global__ void __launch_bounds__(kStagedBlock) grad_dual_norm2_staged_kernel(
   }
 }
 
-inline size_t dual_staged_smem(int capl) { return static_cast<size_t>(8) * capl * kStagedBlock * sizeof(float); }
+inline size_t dual_staged_smem(int capl, int lc, bool check) {
+  return static_cast<size_t>(2 * 8 * lc + (check ? 6 * capl : 0)) * kStagedBlock * sizeof(float);
+}
 
 #endif  // __CUDACC__
 

@@ -545,24 +545,57 @@ __device__ __forceinline__ void ring_flag_wait(const unsigned* flag, unsigned se
     }
   }
 }
-// whole warp: every lane has issued its halo loads and its remote stores; count the tile in and let the
-// last edge tile of the launch publish the sequence number in the neighbour's memory
-__device__ __forceinline__ void ring_edge_done(unsigned* counter, unsigned n_tiles, unsigned* signal, unsigned seq) {
-  __threadfence_system();
-  __syncwarp();
-  if ((threadIdx.x & 31) == 0 && counter) {
-    const unsigned prev = atomicAdd(counter, 1u);
-    if (prev + 1 == n_tiles) {
-      atomicExch(counter, 0u);
-      __threadfence_system();
-      if (signal) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(signal), "r"(seq) : "memory");
+// ---- flag-in-data halo lines (RingHalo, pb_stencil.cuh) --------------------------------------------------------
+// four rows = two 16-byte lines {v0, seq, v1, seq} {v2, seq, v3, seq}; volatile accesses go to L2, the point of
+// coherence for the neighbour's NVLink stores
+__device__ __forceinline__ void ll_ld_line(const uint4* p, uint4& v) {
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+}
+// the four rows of sequence number `seq`: spins until all four tags match (gives up after ~2 s, no GPU hang)
+__device__ __forceinline__ void ll_wait_load4(const uint4* p, unsigned seq, float (&o)[4], int* error) {
+  uint4 a, b;
+  unsigned long long t0 = 0;
+  for (unsigned spins = 0;; ++spins) {
+    ll_ld_line(p, a);
+    ll_ld_line(p + 1, b);
+    if (a.y == seq && a.w == seq && b.y == seq && b.w == seq) break;
+    if ((spins & 255u) == 255u) {
+      if (error && *reinterpret_cast<volatile int*>(error)) break;      // sticky: one timeout poisons the solve
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ull) { if (error) atomicExch(error, 1); break; }
     }
   }
+  o[0] = __uint_as_float(a.x); o[1] = __uint_as_float(a.z); o[2] = __uint_as_float(b.x); o[3] = __uint_as_float(b.z);
 }
-// halo columns live in this GPU's memory but are written by the neighbour over NVLink: bypass L1
-__device__ __forceinline__ void ld_halo4(const float* p, float (&o)[4]) {
-  const float4 t = __ldcg(reinterpret_cast<const float4*>(p));
-  o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+// same, with the first poll already issued (lines a, b were loaded before the caller waited for something else)
+__device__ __forceinline__ void ll_finish_load4(const uint4* p, unsigned seq, uint4 a, uint4 b, float (&o)[4],
+                                                int* error) {
+  if (!(a.y == seq && a.w == seq && b.y == seq && b.w == seq)) {
+    ll_wait_load4(p, seq, o, error);
+    return;
+  }
+  o[0] = __uint_as_float(a.x); o[1] = __uint_as_float(a.z); o[2] = __uint_as_float(b.x); o[3] = __uint_as_float(b.z);
+}
+// slot selection without indexing the kernel-parameter arrays dynamically (that would copy them to local memory)
+template <class P>
+__device__ __forceinline__ P sel3(P const (&a)[3], unsigned k) { return k == 0u ? a[0] : (k == 1u ? a[1] : a[2]); }
+template <class P>
+__device__ __forceinline__ P sel2(P const (&a)[2], unsigned k) { return k == 0u ? a[0] : a[1]; }
+// rows that are known to be there (the slot of an earlier sequence number)
+__device__ __forceinline__ void ll_read4(const uint4* p, float (&o)[4]) {
+  uint4 a, b;
+  ll_ld_line(p, a);
+  ll_ld_line(p + 1, b);
+  o[0] = __uint_as_float(a.x); o[1] = __uint_as_float(a.z); o[2] = __uint_as_float(b.x); o[3] = __uint_as_float(b.z);
+}
+__device__ __forceinline__ void ll_store4(uint4* p, const float (&v)[4], unsigned seq) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(__float_as_uint(v[0])), "r"(seq),
+               "r"(__float_as_uint(v[1])), "r"(seq) : "memory");
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p + 1), "r"(__float_as_uint(v[2])), "r"(seq),
+               "r"(__float_as_uint(v[3])), "r"(seq) : "memory");
 }
 
 // RingMulti: wait until a tile's iteration counter has reached `want` (acquire, gpu scope).  Non-blocking mode
@@ -602,13 +635,15 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
     const __grid_constant__ CUtensorMap map_xb, const RingMulti mi, const RingFinish fin) {
   static_assert(!(MULTI && CHECK), "residual-refresh iterations run one per launch");
   extern __shared__ __align__(128) unsigned char smem[];
-  // tile -> (label plane, tile column, tile row).  On a slab the two edge tile columns come first
-  // (tile column order 0, tiles_x-1, 1, 2, ...) so that the halos leave at the start of the launch.
+  // tile -> (label plane, tile column, tile row).  On a slab the left-edge tile column is walked first (its new x
+  // column leaves at the start of the launch) and the right-edge one at the first position of the SECOND wave:
+  // its tiles need the right neighbour's x column of this very iteration, which that rank's first wave produces.
+  const uint32_t right_pos = min(tiles_x - 1u, (gridDim.x + div_tiles_y.d - 1u) / div_tiles_y.d);
   auto decode = [&](uint32_t tile, uint32_t& l, uint32_t& tx, uint32_t& ty) {
     uint32_t rem;
     div_per_plane.divmod(tile, l, rem);
     div_tiles_y.divmod(rem, tx, ty);
-    if (SLAB) tx = tx == 0 ? 0u : (tx == 1 ? tiles_x - 1 : tx - 1);
+    if (SLAB) tx = tx < right_pos ? tx : (tx == right_pos ? tiles_x - 1 : tx - 1);
   };
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kRingOffBar);
   uint64_t* empty = full + kRingStages;
@@ -651,6 +686,22 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
     for (int c = 0; c < kRingStages * kRingCols; ++c)
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&col_ready[c])));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // tensor maps into the descriptor cache while the previous launch drains
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_p1)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_p2)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_f)) : "memory");
+  }
+  // Programmatic dependent launch: iteration k+1 is launched while iteration k still runs (its CTAs become
+  // resident as SMs free up), so launch latency and this prologue overlap the previous launch's tail; from here
+  // on every thread may touch what that launch wrote (iterates, step-size state), hence the wait.  The next
+  // launch may be scheduled right away: it blocks at the same point until THIS grid has completed and flushed.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (mi.trace && threadIdx.x == 0) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    atomicMin(mi.trace + 4 * mi.trace_slot, now);
   }
   __syncthreads();
   if (producer && !MULTI) {
@@ -704,8 +755,9 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
           uint32_t slot = l * div_per_plane.d + (uint32_t)ntx * div_tiles_y.d + (uint32_t)nty;
           if (mi.coarse) {
             // owner CTA of the neighbour tile: position in the walk order (slabs walk the edge columns first)
-            const uint32_t wx = SLAB ? ((uint32_t)ntx == 0u ? 0u : ((uint32_t)ntx == tiles_x - 1 ? 1u : (uint32_t)ntx + 1u))
-                                     : (uint32_t)ntx;
+            const uint32_t wx = !SLAB ? (uint32_t)ntx
+                                : ((uint32_t)ntx == tiles_x - 1 ? right_pos
+                                                                : ((uint32_t)ntx < right_pos ? (uint32_t)ntx : (uint32_t)ntx + 1u));
             slot = (l * div_per_plane.d + wx * div_tiles_y.d + (uint32_t)nty) % gridDim.x;
             if (slot == blockIdx.x) slot = 0xffffffffu;        // own tiles: program order
           }
@@ -736,27 +788,11 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
     uint32_t l, tx, ty;
     decode(tile, l, tx, ty);
     // where this iteration writes, and (slabs) which halo slots / sequence numbers / edge counters it uses
-    float* __restrict__ xo_ptr = MULTI ? mi.x_io[(it + 1) & 1u] : x_out;
-    float* __restrict__ yo_ptr = MULTI ? mi.y_io[(it + 1) & 1u] : y_out;
-    const float* yl_a = h.yl_a;
-    const float* xr_n = h.xr_n;
-    const float* xr_o = h.xr_o;
-    float* hx_out = h.x_out;
-    float* hy_out = h.y_out;
+    float* __restrict__ xo_ptr = MULTI ? sel2(mi.x_io, (it + 1) & 1u) : x_out;
+    float* __restrict__ yo_ptr = MULTI ? sel2(mi.y_io, (it + 1) & 1u) : y_out;
     unsigned y_wait_seq = h.y_wait_seq, x_wait_seq = h.x_wait_seq;
     unsigned x_signal_seq = h.x_signal_seq, y_signal_seq = h.y_signal_seq;
-    unsigned* x_done = h.x_done;
-    unsigned* y_done = h.y_done;
-    if (SLAB && MULTI) {
-      y_wait_seq += it; x_wait_seq += it; x_signal_seq += it; y_signal_seq += it;
-      yl_a = h.y_slot[y_wait_seq & 1u];
-      xr_n = h.x_slot[x_wait_seq & 1u];
-      xr_o = h.x_slot[(x_wait_seq - 1u) & 1u];
-      hx_out = h.x_out_slot[x_signal_seq & 1u];
-      hy_out = h.y_out_slot[y_signal_seq & 1u];
-      x_done = h.x_done_it + it;
-      y_done = h.y_done_it + it;
-    }
+    if (SLAB && MULTI) { y_wait_seq += it; x_wait_seq += it; x_signal_seq += it; y_signal_seq += it; }
     if (MULTI && col == kRingCols - 1) {
       while (ki <= k) multi_issue(true);          // this work item must be on its way
       if (ki == k + 1) multi_issue(false);        // prefetch the next one if its neighbourhood is ready
@@ -771,15 +807,23 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
     float (*s_q2)[kRingR2] = reinterpret_cast<float (*)[kRingR2]>(base + 2 * kRingP1Bytes + kRingP2Bytes + kRingXBytes);
     float (*s_xn)[kRingRows] = reinterpret_cast<float (*)[kRingRows]>(smem + kRingOffXn + s * kRingXBytes);
 
-    mbar_wait(&full[s], parity);
-
     const uint32_t gx = cx + col, gy = cy + r0;
     const uint32_t plane_off = l * g.nxny;
     // slab edges (warp-uniform): column 0 takes y.gx of column -1 from the left neighbour's halo; the
     // owner of column nx-1 takes x+ / x of column nx from the right neighbour's halo
     const bool left_edge = SLAB && h.has_left && gx == 0;
     const bool right_edge = SLAB && h.has_right && gx == g.nx - 1 && col < kRingTX;
-    const uint32_t halo_off = (gy < g.ny ? gy : 0u) + l * g.ny;
+    const uint32_t halo_ll = (((gy < g.ny ? gy : 0u) + l * g.ny) >> 2) * 2u;      // two 16-byte lines per 4 rows
+    // first poll of this warp's halo lines before the wait for the operand boxes: a volatile load of lines the
+    // neighbour wrote over NVLink takes 1-2 us, which the TMA wait hides
+    uint4 pre_a = make_uint4(0u, 0u, 0u, 0u), pre_b = make_uint4(0u, 0u, 0u, 0u);
+    const uint4* pre_p = nullptr;
+    if (SLAB) {
+      if (left_edge && y_wait_seq) pre_p = sel3(h.yl_ll, y_wait_seq % 3u) + halo_ll;
+      else if (right_edge) pre_p = sel2(h.xr_ll, x_wait_seq & 1u) + halo_ll;
+      if (pre_p) { ll_ld_line(pre_p, pre_a); ll_ld_line(pre_p + 1, pre_b); }
+    }
+    mbar_wait(&full[s], parity);
     // ---- phase A: x+ at (col, r0..r0+3) of the computed region ------------------------------------------
     if (gx < g.nx) {
       float xo[4], divx[4], o[4], a[4], xn[4];
@@ -788,9 +832,19 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
       VecIO<4>::ld(&s_x[col][r0], xo);
       VecIO<4>::ld(&s_p1[col + 1][r0], divx);
       VecIO<4>::ld(&s_p1[col][r0], a);
+      float qa_halo[4] = {0.f, 0.f, 0.f, 0.f};
       if (left_edge) {
-        ring_flag_wait(h.y_wait_flag, y_wait_seq, h.error);
-        ld_halo4(yl_a + halo_off, a);
+        // y.gx of column -1: the left neighbour's previous iteration, row group by row group
+        unsigned long long tw0 = 0;
+        if (mi.trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tw0));
+        if (y_wait_seq) ll_finish_load4(pre_p, y_wait_seq, pre_a, pre_b, a, h.error);
+        if (mi.trace) {
+          unsigned long long tw1;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tw1));
+          atomicMax(mi.trace + 4 * mi.trace_slot + 2, tw1 - tw0);
+        }
+        // (refresh) the column before it, read BEFORE this thread's x store lets the neighbour move on
+        if (CHECK && q_boxes && y_wait_seq > 1u) ll_read4(sel3(h.yl_ll, (y_wait_seq - 1u) % 3u) + halo_ll, qa_halo);
       }
       VecIO<4>::ld(&s_p2[col][4 + r0], o);
       const float up = s_p2[col][4 + r0 - 1];
@@ -834,7 +888,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
       VecIO<4>::st(&s_xn[col][r0], xn);
       if (col < kRingTX && r0 < kRingTY && gy < g.ny) {
         VecIO<4>::st(xo_ptr + gy + gx * g.ny + plane_off, xn);
-        if (left_edge) VecIO<4>::st(hx_out + halo_off, xn);       // new column 0 -> left neighbour (NVLink)
+        if (left_edge) ll_store4(sel2(h.x_out_ll, x_signal_seq & 1u) + halo_ll, xn, x_signal_seq);   // -> left neighbour
         if (CHECK) {
           // dual residual on the owned pixels: w^ = (x - x+)/(tau sqrt T) - sqrt T K^T y_prev,
           // diff = w^ + sqrt T K^T y
@@ -843,7 +897,10 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
             float qx[4], qa[4], qo[4];
             VecIO<4>::ld(&s_q1[col + 1][r0], qx);
             VecIO<4>::ld(&s_q1[col][r0], qa);
-            if (left_edge) ld_halo4(h.yl_b + halo_off, qa);
+            if (left_edge) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) qa[j] = qa_halo[j];
+            }
             VecIO<4>::ld(&s_q2[col][4 + r0], qo);
             const float qup = s_q2[col][4 + r0 - 1];
             float qy[4];
@@ -875,7 +932,6 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
         }
       }
     }
-    if (left_edge) ring_edge_done(x_done, h.n_edge_tiles, h.x_signal, x_signal_seq);
     // publish this column's x+ (one arrival per warp), then wait for the right neighbour's
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(&col_ready[s * kRingCols + col]);
@@ -889,9 +945,16 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
       VecIO<4>::ld(&s_xn[col][r0], cn);
       VecIO<4>::ld(&s_x[col][r0], co);
       if (right_edge) {
-        ring_flag_wait(h.x_wait_flag, x_wait_seq, h.error);
-        ld_halo4(xr_n + halo_off, rn);
-        ld_halo4(xr_o + halo_off, ro);
+        // x+ / x of column nx: the right neighbour's column 0 of THIS iteration and of the previous one
+        unsigned long long tw0 = 0;
+        if (mi.trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tw0));
+        ll_finish_load4(pre_p, x_wait_seq, pre_a, pre_b, rn, h.error);
+        if (mi.trace) {
+          unsigned long long tw1;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tw1));
+          atomicMax(mi.trace + 4 * mi.trace_slot + 3, tw1 - tw0);
+        }
+        ll_read4(sel2(h.xr_ll, (x_wait_seq - 1u) & 1u) + halo_ll, ro);
       } else {
         VecIO<4>::ld(&s_xn[col + 1][r0], rn);
         VecIO<4>::ld(&s_x[col + 1][r0], ro);
@@ -920,7 +983,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
       else norm2_lanes<4, 2, false>(fn_f, arg, cf, tau_f);
       VecIO<4>::st(yo_ptr + idx, arg[0]);
       VecIO<4>::st(yo_ptr + (size_t)g.L * g.nxny + idx, arg[1]);
-      if (right_edge) VecIO<4>::st(hy_out + halo_off, arg[0]);      // new y.gx column nx-1 -> right neighbour
+      if (right_edge) ll_store4(sel3(h.y_out_ll, y_signal_seq % 3u) + halo_ll, arg[0], y_signal_seq);   // -> right neighbour
       if (CHECK) {
         // primal residual: z^ = (y - y+)/(sigma sqrt S) + sqrt S ((1+theta) K x+ - theta K x),
         // diff = z^ - sqrt S K x+
@@ -940,7 +1003,6 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
         acc_p1 += static_cast<double>(s1);
       }
     }
-    if (right_edge) ring_edge_done(y_done, h.n_edge_tiles, h.y_signal, y_signal_seq);
     // this warp is done with stage s (operand boxes and x+ tile)
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[s]);
@@ -970,6 +1032,11 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
       }
       if (!issued) multi_issue(false);
     }
+  }
+  if (mi.trace && threadIdx.x == 0) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    atomicMax(mi.trace + 4 * mi.trace_slot + 1, now);
   }
   if (CHECK) {
     block_sum2(acc_d0, acc_d1);
@@ -1030,6 +1097,32 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
   }
 }
 
+// ---- PB_RING_TRACE=1: launch timeline for scaling experiments (pb_ring_trace_read in the C ABI) ----------------
+constexpr unsigned kRingTraceSlots = 4096;
+struct RingTrace {
+  unsigned long long* buf = nullptr;
+  unsigned next = 0;
+};
+RingTrace& ring_trace() {
+  static RingTrace t;
+  return t;
+}
+RingMulti ring_trace_next() {
+  RingMulti m;
+  static const bool on = [] { const char* e = getenv("PB_RING_TRACE"); return e && atoi(e) != 0; }();
+  if (!on) return m;
+  RingTrace& t = ring_trace();
+  if (!t.buf) {
+    if (cudaMalloc(&t.buf, kRingTraceSlots * 4 * sizeof(unsigned long long)) != cudaSuccess) { cudaGetLastError(); return m; }
+    std::vector<unsigned long long> init(kRingTraceSlots * 4, 0ull);
+    for (unsigned i = 0; i < kRingTraceSlots; ++i) init[4 * i] = ~0ull;
+    cudaMemcpy(t.buf, init.data(), init.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice);
+  }
+  m.trace = t.buf;
+  m.trace_slot = t.next++ % kRingTraceSlots;
+  return m;
+}
+
 struct RingArgs {
   CUtensorMap mp1, mp2, mx, mf, mq1, mq2;
   bool check = false;
@@ -1059,10 +1152,7 @@ unsigned ring_launch_k(Context* ctx, const RingArgs& a, const GradGeom& g, const
   const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)ctx->num_sms);
   if (dry_run) return grid;
   RingHalo h;
-  if (SLAB) {
-    h = *a.halo;
-    h.n_edge_tiles = tiles_y * g.L;
-  }
+  if (SLAB) h = *a.halo;
   if (MULTI) {
     // the CTAs wait for each other's tiles: all of them have to be resident -> cooperative launch
     cudaLaunchConfig_t cfg = {};
@@ -1082,10 +1172,29 @@ unsigned ring_launch_k(Context* ctx, const RingArgs& a, const GradGeom& g, const
     if (e != cudaSuccess) { cudaGetLastError(); return 0; }
     return grid;
   }
-  kernel<<<grid, kRingThreads, kRingSmemBytes, ctx->stream>>>(
-      a.mp1, a.mp2, a.mx, a.mf, a.mq1, a.mq2, g, pg, pf, Tval, Sval, st, FastDiv((uint64_t)tiles_x * tiles_y),
-      FastDiv(tiles_y), (uint32_t)n_tiles, a.ktyprev_zero, a.part_d, a.part_p, x_out, y_out, tiles_x, h, a.mx,
-      RingMulti(), (CHECK && a.finish) ? *a.finish : RingFinish());
+  {
+    // programmatic stream serialization: see griddepcontrol in the kernel.  Measured (profiles/r02_scaling.md): the
+    // launch-to-launch gap drops from 3.8 to 1.8 us on one GPU, but on slabs the end-of-kernel flush of the
+    // NVLink halo stores dominates the gap and early-resident CTAs cost more than they hide (period 54.3 vs
+    // 52.9 us at 2 x 2048 columns), so slabs keep plain stream order.  PB_RING_PDL=0/1 overrides.
+    static const int pdl_env = [] { const char* e = getenv("PB_RING_PDL"); return e ? atoi(e) : -1; }();
+    const bool pdl = pdl_env >= 0 ? pdl_env != 0 : !SLAB;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kRingThreads);
+    cfg.dynamicSmemBytes = kRingSmemBytes;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    const cudaError_t e = cudaLaunchKernelEx(
+        &cfg, kernel, a.mp1, a.mp2, a.mx, a.mf, a.mq1, a.mq2, g, pg, pf, Tval, Sval, st,
+        FastDiv((uint64_t)tiles_x * tiles_y), FastDiv(tiles_y), (uint32_t)n_tiles, a.ktyprev_zero, a.part_d, a.part_p,
+        x_out, y_out, tiles_x, h, a.mx, ring_trace_next(), (CHECK && a.finish) ? *a.finish : RingFinish());
+    if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+  }
   return grid;
 }
 
@@ -1137,6 +1246,16 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 }  // namespace
 
 static int tile_mode();
+
+// copies the trace (up to n launches x 4 values) to the host; returns the number of launches recorded so far
+unsigned tile_ring_trace_read(unsigned long long* h_out, unsigned n) {
+  RingTrace& t = ring_trace();
+  if (!t.buf) return 0;
+  cudaDeviceSynchronize();
+  const unsigned k = std::min(std::min(n, t.next), kRingTraceSlots);
+  if (k) cudaMemcpy(h_out, t.buf, (size_t)k * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  return t.next;
+}
 
 // ---- several non-refresh iterations in one launch (experimental, PB_RING_ITERS > 1) ----------------------------
 unsigned tile_ring_tile_count(const StencilPlan& plan) {

@@ -1,5 +1,9 @@
-"""Model check (CPU, no GPU) of the peer-to-peer halo protocol the one-pass ring kernel runs on column slabs
-(prost_b200/csrc/pb_tile.cu SLAB, pb_stencil.cuh RingHalo, pb_pdhg.cu slab_ring_halo).
+"""Model checks (CPU, no GPU) of the peer-to-peer halo protocols on column slabs.
+
+Second half of this file: the flag-in-data ("LL") protocol the one-pass ring kernel runs since round 2
+(prost_b200/csrc/pb_tile.cu SLAB, pb_stencil.cuh RingHalo, pb_pdhg.cu slab_ring_halo).  First half: the
+sequence-word protocol with edge-tile counters (round 1's ring kernel; the two-pass slab kernels still publish a
+whole column with one sequence word after all their edge CTAs are done, pb_stencil.cuh SlabHalo):
 
 Per rank and iteration `it` (sequence numbers xs = ys = it, ys_in = it - 1) two groups of tiles run:
   left-edge tiles  : wait y_flag >= ys_in; read y slot ys_in (and, on residual-refresh iterations, slot
@@ -149,3 +153,78 @@ def _broken_model(world, n_iters, n_tiles, seed):
 def test_model_detects_a_broken_protocol():
     outcomes = {_broken_model(3, n_iters=7, n_tiles=3, seed=s) for s in range(200)}
     assert outcomes - {"ok"}, "the model never noticed that early publishing is unsafe"
+
+
+# ---- flag-in-data protocol of the ring kernel (round 2) ----------------------------------------------------------
+# Every segment of a column carries the tag (writer rank, iteration) itself; there is no separate flag and no
+# counter.  Left-edge tile j of iteration `it` waits until segments j and j+1 of y slot (it-1) % Y carry the tag
+# of the left neighbour's iteration it-1, reads (refresh iterations) the column before it from slot (it-2) % Y,
+# then stores x segment j into the left neighbour's slot it & 1.  Right-edge tile j waits for x segment j of slot
+# it & 1 (tag: right neighbour, iteration it), reads segment j of the other slot (iteration it-1) and stores y
+# segment j into the right neighbour's slot it % Y.  Y = 3 in the product; the model shows that Y = 2 is NOT
+# enough once refresh iterations read the column before the newest one.
+class LLRank:
+    def __init__(self, r, world, n_tiles, y_slots):
+        self.r, self.world = r, world
+        self.has_left, self.has_right = r > 0, r + 1 < world
+        self.x_slot = [[None] * n_tiles for _ in range(2)]
+        self.y_slot = [[None] * n_tiles for _ in range(y_slots)]
+        self.done = {"L": [0] * n_tiles, "R": [0] * n_tiles}
+
+
+def run_model_ll(world, n_iters, n_tiles, multi, check_every, seed, y_slots=3):
+    rng = random.Random(seed)
+    ranks = [LLRank(r, world, n_tiles, y_slots) for r in range(world)]
+    total = world * 2 * n_tiles * n_iters
+    completed = 0
+    while completed < total:
+        enabled = []
+        for rk in ranks:
+            for grp in ("L", "R"):
+                for j in range(n_tiles):
+                    it = rk.done[grp][j] + 1
+                    if it > n_iters:
+                        continue
+                    if multi:
+                        nb = [t for t in (j - 1, j, j + 1) if 0 <= t < n_tiles]
+                        if any(rk.done[g][t] < it - 1 for g in ("L", "R") for t in nb):
+                            continue
+                    elif any(rk.done[g][t] < it - 1 for g in ("L", "R") for t in range(n_tiles)):
+                        continue
+                    segs = [t for t in (j, j + 1) if t < n_tiles]
+                    # the waits: tags in the data (iteration 1 = the two-pass iteration 0 of the solver, no y halo)
+                    if grp == "L" and rk.has_left and it > 1 and \
+                            any(rk.y_slot[(it - 1) % y_slots][t] != (rk.r - 1, it - 1) for t in segs):
+                        continue
+                    if grp == "R" and rk.has_right and rk.x_slot[it & 1][j] != (rk.r + 1, it):
+                        continue
+                    enabled.append((rk, grp, j, it, segs))
+        if not enabled:
+            return "deadlock"
+        rk, grp, j, it, segs = rng.choice(enabled)
+        refresh = check_every and it % check_every == 0
+        if grp == "L" and rk.has_left:
+            if refresh and it > 2 and any(rk.y_slot[(it - 2) % y_slots][t] != (rk.r - 1, it - 2) for t in segs):
+                return "stale previous y halo"
+            ranks[rk.r - 1].x_slot[it & 1][j] = (rk.r, it)
+        if grp == "R" and rk.has_right:
+            if it > 1 and rk.x_slot[(it - 1) & 1][j] != (rk.r + 1, it - 1):
+                return "stale previous x halo"
+            ranks[rk.r + 1].y_slot[it % y_slots][j] = (rk.r, it)
+        rk.done[grp][j] = it
+        completed += 1
+    return "ok"
+
+
+@pytest.mark.parametrize("multi", [False, True])
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_flag_in_data_halo_protocol_is_safe_and_live(world, multi):
+    for seed in range(60):
+        assert run_model_ll(world, n_iters=8, n_tiles=3, multi=multi, check_every=3, seed=seed) == "ok"
+        assert run_model_ll(world, n_iters=8, n_tiles=4, multi=multi, check_every=1, seed=seed) == "ok"
+
+
+def test_flag_in_data_model_needs_the_third_y_slot():
+    outcomes = {run_model_ll(3, n_iters=8, n_tiles=3, multi=False, check_every=1, seed=s, y_slots=2) for s in range(300)}
+    assert "stale previous y halo" in outcomes, "two y slots should be caught as unsafe under refresh reads"
+    assert "deadlock" not in outcomes
