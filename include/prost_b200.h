@@ -362,7 +362,11 @@ int pb_comm_peer_to_peer(const pb_comm* c);
 int pb_comm_barrier(pb_comm* c);
 /* sum over ranks of n host doubles, in place (host-side reductions of callers, e.g. objectives) */
 int pb_comm_allreduce_sum(pb_comm* c, double* h_buf, size_t n);
-/* the backend's Problem is the slab of rank pb_comm_rank(c); the comm must outlive the backend */
+/* the backend's Problem is the shard of rank pb_comm_rank(c); the comm must outlive the backend.
+ * BackendPDHG: a slab of image COLUMNS (stencil halos travel peer to peer inside the kernels).
+ * BackendADMM: a block of ROWS of K and of the f-side proxes; columns and the n-side vectors are
+ *   replicated, K^T r is summed over the ranks with one ncclAllReduce of n floats per adjoint apply
+ *   (cgls.hpp:290-357, backend_admm.cu:198-272 on one GPU), sums over rows inside the reduction kernels. */
 int pb_backend_set_slab(pb_backend* b, pb_comm* c);
 
 /* ---- Solver loop: Solver<T>::Solve, src/solver.cu:122-209 ------------------------------- */

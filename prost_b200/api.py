@@ -629,12 +629,20 @@ class BackendPDHG(Backend):
 
 
 class BackendADMM(Backend):
-    def __init__(self, ctx, problem, opts=None, sopts=None):
+    def __init__(self, ctx, problem, opts=None, sopts=None, comm=None):
         super().__init__(ctx)
         self.problem = problem
         self.opts = opts or admm_options()
         self.sopts = sopts or solver_options()
         check(lib.pb_admm_create(ctx._h, problem._h, C.byref(self.opts), C.byref(self.sopts), C.byref(self._h)))
+        if comm is not None:
+            self.SetRowShards(comm)
+
+    def SetRowShards(self, comm):
+        """The problem is this rank's block of ROWS of K and of the f-side proxes (distributed.shard_rows); K^T r
+        is summed over the ranks with NCCL, sums over rows inside the reduction kernels (pb_backend_set_slab)."""
+        check(lib.pb_backend_set_slab(self._h, comm._h))
+        self.comm = comm
 
 
 class Solver:

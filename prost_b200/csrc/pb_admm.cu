@@ -28,6 +28,8 @@
 #include <limits>
 
 #include "pb_backend.cuh"
+#include "pb_comm.cuh"
+#include "pb_crosssum.cuh"
 #include "pb_reduce.cuh"
 
 namespace pb {
@@ -47,8 +49,10 @@ struct CgState {
 
 // CTA partial -> global partial; the last CTA to arrive folds all partials in index order.
 // Returns true in thread 0 of that CTA with (a, b) = totals.  All threads must call.
+// `cross` (row-sharded ADMM): sums over the m-side rows are partial per rank; the folding thread then combines them
+// through peer-mapped slots (pb_crosssum.cuh), so the scalar recurrences stay on the device and identical on all ranks.
 __device__ __forceinline__ bool reduce_last(double& a, double& b, double* __restrict__ partials,
-                                            unsigned* ticket) {
+                                            unsigned* ticket, const CrossSum* cross = nullptr) {
   __shared__ int s_last;
   block_sum2(a, b);
   if (threadIdx.x == 0) {
@@ -66,6 +70,12 @@ __device__ __forceinline__ bool reduce_last(double& a, double& b, double* __rest
     fb += __ldcg(partials + 2 * i + 1);
   }
   block_sum2(fa, fb);
+  if (threadIdx.x == 0 && cross) {
+    double v[4] = {fa, fb, 0.0, 0.0};
+    cross_rank_sum4(*cross, v);
+    fa = v[0];
+    fb = v[1];
+  }
   a = fa;
   b = fb;
   if (threadIdx.x == 0) *ticket = 0;
@@ -185,7 +195,7 @@ __global__ void __launch_bounds__(kBlock) cg_init_tail_kernel(size_t n, ScaleRef
 // CG step, after q <- K temp3: q = 1 sqrt(S) q (gemv_functor3), |q|; delta, alpha (:303-315)
 __global__ void __launch_bounds__(kBlock) cg_forward_tail_kernel(size_t m, ScaleRef S, float* __restrict__ q,
                                                                  CgState* cg, double* partials, double shift,
-                                                                 double k_eps) {
+                                                                 double k_eps, const CrossSum cross) {
   if (cg->done) return;
   double acc = 0.0, unused = 0.0;
   PB_GRID_STRIDE(i, m) {
@@ -193,7 +203,7 @@ __global__ void __launch_bounds__(kBlock) cg_forward_tail_kernel(size_t m, Scale
     q[i] = qv;
     acc += static_cast<double>(qv) * static_cast<double>(qv);
   }
-  if (reduce_last(acc, unused, partials, &cg->ticket)) {
+  if (reduce_last(acc, unused, partials, &cg->ticket, &cross)) {
     cg->normq = sqrt(acc);
     double delta = cg->normq * cg->normq + shift * cg->normp * cg->normp;
     if (delta <= 0.) cg->indefinite = 1;
@@ -316,7 +326,7 @@ __global__ void __launch_bounds__(kBlock) admm_primal_residual_kernel(size_t m, 
                                                                       const float* __restrict__ kxz,
                                                                       const float* __restrict__ z_half,
                                                                       double* partials, unsigned* ticket,
-                                                                      double* sums) {
+                                                                      double* sums, const CrossSum cross) {
   double a = 0.0, b = 0.0;
   PB_GRID_STRIDE(i, m) {
     const float ss = sqrtf(S.at((uint32_t)i));
@@ -325,7 +335,7 @@ __global__ void __launch_bounds__(kBlock) admm_primal_residual_kernel(size_t m, 
     a += static_cast<double>(v) * static_cast<double>(v);
     b += static_cast<double>(u) * static_cast<double>(u);
   }
-  if (reduce_last(a, b, partials, ticket)) { sums[0] = a; sums[1] = b; }
+  if (reduce_last(a, b, partials, ticket, &cross)) { sums[0] = a; sums[1] = b; }
 }
 
 // w = -rho T^-1 (x_half - x_proj + x_dual) -> temp1, sums[3] = |sqrt(T) w|^2;
@@ -384,6 +394,13 @@ __global__ void __launch_bounds__(kBlock) admm_scale_tail_kernel(float* __restri
   PB_GRID_STRIDE(i, n) v[i] = beta * v[i];
 }
 
+// row-sharded adjoint: res = beta res + (sum over ranks of the partial K^T rhs)
+__global__ void __launch_bounds__(kBlock) admm_axpby_kernel(float* __restrict__ res, const float* __restrict__ part,
+                                                            size_t n, float beta, const int* __restrict__ skip) {
+  if (skip && *skip) return;
+  PB_GRID_STRIDE(i, n) res[i] = beta == 0.f ? part[i] : beta * res[i] + part[i];
+}
+
 }  // namespace
 
 class BackendADMM : public Backend {
@@ -415,6 +432,11 @@ class BackendADMM : public Backend {
     if (d_y) *d_y = nullptr;        // the dual iterate is implicit: y = -rho S (z_half - z_proj + z_dual)
   }
   int residual_iter() const override { return opts_.residual_iter; }
+  // Row-sharded ADMM over the GPUs of one box: this rank's Problem holds a block of ROWS of K and
+  // of the f-side vectors; the n-side vectors are replicated.  K x is local; K^T r is summed over ranks with one
+  // ncclAllReduce of n floats per adjoint apply; the sums over rows (|q|^2, primal residual) are combined inside
+  // the reduction kernels (pb_crosssum.cuh); sums over columns are computed redundantly and identically.
+  void set_slab(Comm* comm) override { comm_ = comm; }
   // residuals refresh AFTER iteration_++ (backend_admm.cu:525-529)
   bool refreshes_on(size_t it_before) const override {
     const unsigned long long mod = static_cast<unsigned long long>(static_cast<long long>(opts_.residual_iter));
@@ -435,6 +457,11 @@ class BackendADMM : public Backend {
   long long cg_steps_total();
 
   pb_admm_options opts_;
+  Comm* comm_ = nullptr;
+  bool sharded() const { return comm_ && comm_->world() > 1; }
+  CrossSum cross() const { return sharded() ? comm_->cross_sum() : CrossSum(); }
+  unsigned long long global_rows_ = 0;
+  DeviceBuffer<float> kt_part_;        // row-sharded: this rank's partial K^T rhs
   DeviceBuffer<float> x_half_, z_half_, x_proj_, z_proj_, x_dual_, z_dual_, temp1_, temp2_, temp3_;
   DeviceBuffer<CgState> d_cg_;
   DeviceBuffer<double> d_part_, d_sums_;
@@ -476,7 +503,24 @@ void BackendADMM::initialize(const float*, size_t, const float*, size_t) {
   const size_t m = problem_->nrows(), n = problem_->ncols();
   if (std::max(m, n) >= (1ull << 31)) fail(PB_ERR_UNSUPPORTED, "BackendADMM: more than 2^31-1 variables");
   cudaStream_t s = ctx_->stream;
+  global_rows_ = m;
+  if (sharded()) {
+    // every rank must come to the same verdict before anybody throws (the next call is collective)
+    const bool ok_local = problem_->scaling_type() != Problem::kScalingAlpha;
+    double v[3] = {ok_local ? 0.0 : 1.0, static_cast<double>(m), static_cast<double>(n)};
+    comm_->allreduce_sum_host(v, 3);
+    if (v[0] != 0.0)
+      fail(PB_ERR_UNSUPPORTED, "row-sharded ADMM: the alpha preconditioners need column sums over all ranks' rows; "
+                               "use identity or custom scaling");
+    if (v[2] != static_cast<double>(n) * comm_->world())
+      fail(PB_ERR_INVALID, "row-sharded ADMM: ranks disagree on the number of columns");
+    global_rows_ = static_cast<unsigned long long>(v[1]);
+    comm_->ensure_halo(4);             // maps every rank's control block (reduction slots)
+    if (!comm_->reduce_p2p())
+      fail(PB_ERR_UNSUPPORTED, "row-sharded ADMM needs peer-to-peer access between the GPUs (CUDA IPC)");
+  }
   try {
+    if (sharded()) kt_part_.resize(n);
     x_half_.resize(n); x_proj_.resize(n); x_dual_.resize(n);
     z_half_.resize(m); z_proj_.resize(m); z_dual_.resize(m);
     temp1_.resize(n); temp2_.resize(m); temp3_.resize(std::max(m, n));
@@ -519,6 +563,19 @@ void BackendADMM::initialize(const float*, size_t, const float*, size_t) {
 void BackendADMM::apply(float* d_res, const float* d_rhs, float beta, bool transpose, const int* skip) {
   LinearOperator* K = problem_->linop();
   ctx_->skip_flag = skip;
+  if (transpose && sharded()) {
+    // partial K^T rhs of this rank's rows -> sum over ranks -> res = beta res + sum.  The all-reduce is a host-
+    // enqueued collective and runs even when the device-side skip flag is set (its result is then not used).
+    const size_t n = problem_->ncols();
+    K->eval(kt_part_.data(), d_rhs, 0.f, true);
+    if (n > K->ncols()) PB_CUDA(cudaMemsetAsync(kt_part_.data() + K->ncols(), 0, (n - K->ncols()) * sizeof(float), ctx_->stream));
+    comm_->allreduce_sum_f32(kt_part_.data(), n);
+    admm_axpby_kernel<<<egrid(n), kBlock, 0, ctx_->stream>>>(d_res, kt_part_.data(), n, beta, skip);
+    PB_CHECK_LAUNCH();
+    ctx_->launches++;
+    ctx_->skip_flag = nullptr;
+    return;
+  }
   K->eval(d_res, d_rhs, beta, transpose);
   const size_t covered = transpose ? K->ncols() : K->nrows();
   const size_t total = transpose ? problem_->ncols() : problem_->nrows();
@@ -572,7 +629,7 @@ void BackendADMM::project_onto_graph(double cg_tol) {
 
   for (int k = 0; k < opts_.cg_max_iter; ++k) {
     apply(q, temp3_.data(), 0.f, false, skip_done());                // q = K~ p
-    cg_forward_tail_kernel<<<egrid(m), kBlock, 0, st>>>(m, S, q, cg, part, shift, k_eps);
+    cg_forward_tail_kernel<<<egrid(m), kBlock, 0, st>>>(m, S, q, cg, part, shift, k_eps, cross());
     PB_CHECK_LAUNCH();
     cg_update_kernel<<<egrid(len), kBlock, 0, st>>>(n, m, T, S, neg_shift, x, p, r, q, s, temp3_.data(), cg, part);
     PB_CHECK_LAUNCH();
@@ -599,7 +656,7 @@ void BackendADMM::update_residuals() {                     // backend_admm.cu:52
   PB_CUDA(cudaMemcpyAsync(temp2_.data(), z_half_.data(), m * sizeof(float), cudaMemcpyDeviceToDevice, st));
   apply(temp2_.data(), x_half_.data(), -1.f, false, nullptr);        // K x_half - z_half
   admm_primal_residual_kernel<<<egrid(m), kBlock, 0, st>>>(m, S, temp2_.data(), z_half_.data(), part, ticket,
-                                                           d_sums_.data());
+                                                           d_sums_.data(), cross());
   PB_CHECK_LAUNCH();
   admm_dual_variables_kernel<<<egrid(len), kBlock, 0, st>>>(n, m, rho_, T, S, x_half_.data(), x_proj_.data(),
                                                             x_dual_.data(), z_half_.data(), z_proj_.data(),
@@ -619,7 +676,7 @@ void BackendADMM::update_residuals() {                     // backend_admm.cu:52
   dual_residual_ = static_cast<float>(std::sqrt(sums[2]));
   dual_var_norm_ = static_cast<float>(std::sqrt(sums[3]));
 
-  const float eps_p = pdhg_eps(m, sopts_.tol_abs_primal, sopts_.tol_rel_primal, primal_var_norm_);
+  const float eps_p = pdhg_eps(global_rows_, sopts_.tol_abs_primal, sopts_.tol_rel_primal, primal_var_norm_);
   const float eps_d = pdhg_eps(n, sopts_.tol_abs_dual, sopts_.tol_rel_dual, dual_var_norm_);
   const float rho_prev = rho_;
   const float t_it = opts_.arb_tau * static_cast<float>(iteration_);
@@ -700,7 +757,8 @@ void BackendADMM::residuals(float out[6]) {
   out[1] = dual_residual_;
   out[2] = primal_var_norm_;
   out[3] = dual_var_norm_;
-  out[4] = pdhg_eps(problem_->nrows(), sopts_.tol_abs_primal, sopts_.tol_rel_primal, primal_var_norm_);
+  out[4] = pdhg_eps(sharded() ? global_rows_ : problem_->nrows(), sopts_.tol_abs_primal, sopts_.tol_rel_primal,
+                    primal_var_norm_);
   out[5] = pdhg_eps(problem_->ncols(), sopts_.tol_abs_dual, sopts_.tol_rel_dual, dual_var_norm_);
 }
 

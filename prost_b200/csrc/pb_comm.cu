@@ -137,7 +137,7 @@ void Comm::ensure_halo(size_t col_floats) {
     barrier();
     PB_CUDA(cudaMemsetAsync(block_, 0, kFlagBytes + 4 * col_floats_ * sizeof(float) + 5 * ll_lines() * sizeof(uint4), s));
     PB_CUDA(cudaStreamSynchronize(s));
-    x_seq = y_seq = red_seq = 0;
+    x_seq = y_seq = 0;
     barrier();
     return;
   }
@@ -145,7 +145,7 @@ void Comm::ensure_halo(size_t col_floats) {
   barrier();                       // nobody still reads a block that is about to be unmapped
   release_halo();
   col_floats_ = col_floats;
-  x_seq = y_seq = red_seq = 0;
+  x_seq = y_seq = 0;
   const size_t bytes = kFlagBytes + 4 * col_floats * sizeof(float) + 5 * ll_lines() * sizeof(uint4);
   PB_CUDA(cudaMalloc(&block_, bytes));
   PB_CUDA(cudaMemsetAsync(block_, 0, bytes, s));
@@ -315,6 +315,24 @@ unsigned* Comm::red_flag_out(int r) const {
   return reinterpret_cast<unsigned*>(static_cast<char*>(peer_blocks_[r]) + kRedFlagOff);
 }
 
+unsigned* Comm::red_count() const { return flags_ ? &flags_->red_count : nullptr; }
+
+CrossSum Comm::cross_sum() const {
+  CrossSum c;
+  if (!reduce_p2p()) return c;
+  c.world = world_;
+  c.rank = rank_;
+  c.count = red_count();
+  c.red_in = red_in();
+  c.red_flag_in = red_flag_in();
+  for (int r = 0; r < world_; ++r) {
+    c.red_out[r] = red_out(r);
+    c.red_flag_out[r] = red_flag_out(r);
+  }
+  c.error = &flags_->error;
+  return c;
+}
+
 void Comm::exchange_x(unsigned seq) {
   if (p2p_ || world_ == 1) return;
   PB_NCCL(nccl().GroupStart());
@@ -334,6 +352,11 @@ void Comm::exchange_y(unsigned seq) {
 void Comm::allreduce_sum(double* d_buf, size_t n) {
   if (world_ == 1) return;
   PB_NCCL(nccl().AllReduce(d_buf, d_buf, n, ncclDouble, ncclSum, as_comm(nccl_), ctx_->stream));
+}
+
+void Comm::allreduce_sum_f32(float* d_buf, size_t n) {
+  if (world_ == 1) return;
+  PB_NCCL(nccl().AllReduce(d_buf, d_buf, n, ncclFloat, ncclSum, as_comm(nccl_), ctx_->stream));
 }
 
 void Comm::allreduce_sum_host(double* h_buf, size_t n) {

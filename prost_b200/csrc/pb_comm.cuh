@@ -19,6 +19,7 @@
 #pragma once
 
 #include "pb_common.cuh"
+#include "pb_crosssum.cuh"
 
 namespace pb {
 
@@ -29,7 +30,8 @@ struct HaloFlags {
   unsigned done_primal;  // local: edge CTAs of the running primal pass that finished
   unsigned done_dual;    // local: same for the dual pass
   int error;             // set by a kernel whose halo wait timed out
-  int pad[11];
+  unsigned red_count;    // local: reductions over ranks executed so far (pb_crosssum.cuh)
+  int pad[10];
 };
 
 class Comm {
@@ -53,6 +55,8 @@ class Comm {
 
   // in-stream sum over ranks of n doubles (device memory, in place)
   void allreduce_sum(double* d_buf, size_t n);
+  // in-stream sum over ranks of n floats: the partial K^T r vectors of the row-sharded ADMM
+  void allreduce_sum_f32(float* d_buf, size_t n);
   // host-side conveniences (synchronise the stream)
   void allreduce_sum_host(double* h_buf, size_t n);
   void barrier();
@@ -94,7 +98,9 @@ class Comm {
   const unsigned* red_flag_in() const;        // local sequence words
   double* red_out(int r) const;               // rank r's slots (own block for r == rank)
   unsigned* red_flag_out(int r) const;
-  unsigned red_seq = 0;                       // identical on every rank
+  unsigned* red_count() const;                // local device counter of executed reductions (pb_crosssum.cuh)
+  // descriptor for kernels that sum over ranks themselves (world 1: no-op descriptor)
+  struct CrossSum cross_sum() const;
 
  private:
   void release_halo();

@@ -243,7 +243,7 @@ class BackendPDHG : public Backend {
   unsigned ring_base_ = 0;
   DeviceBuffer<unsigned> ring_done_, ring_edge_counters_;
   DeviceBuffer<unsigned> fin_ticket_;        // RingFinish: CTAs of the running residual-refresh launch that are done
-  RingFinish ring_finish();                  // advances comm_->red_seq on slabs
+  RingFinish ring_finish();
   DeviceBuffer<int> ring_error_;
   void slab_apply(float* d_res, const float* d_rhs, const float* d_halo, bool adjoint);
   Comm* comm_ = nullptr;
@@ -542,7 +542,6 @@ void BackendPDHG::iteration_fused() {
   if (tiled && check) {
     static const bool in_kernel = [] { const char* e = getenv("PB_RING_FINISH"); return !e || atoi(e) != 0; }();
     const bool can_finish = in_kernel && (!comm_ || comm_->world() == 1 || comm_->reduce_p2p());
-    const unsigned red_seq0 = comm_ ? comm_->red_seq : 0;
     RingFinish fin;
     if (can_finish) fin = ring_finish();
     tiled_check = tile_check_iteration_launch(ctx_, stencil_, g_descs_[0], f_descs_[0], x_.data(), y_.data(),
@@ -551,7 +550,6 @@ void BackendPDHG::iteration_fused() {
                                               can_finish ? &fin : nullptr);
     if (!tiled_check && comm_)
       fail(PB_ERR_CUDA, "slab decomposition: the one-pass ring kernel could not be launched");
-    if (!tiled_check && comm_) comm_->red_seq = red_seq0;
     finished_in_kernel = tiled_check && can_finish;
   }
   if (tiled_check) {
@@ -647,18 +645,7 @@ RingFinish BackendPDHG::ring_finish() {
   f.state = d_state_.data();
   f.prm = params_;
   f.iteration = iteration_;
-  if (comm_ && comm_->world() > 1) {
-    f.world = comm_->world();
-    f.rank = comm_->rank();
-    f.seq = ++comm_->red_seq;
-    f.red_in = comm_->red_in();
-    f.red_flag_in = comm_->red_flag_in();
-    for (int r = 0; r < f.world; ++r) {
-      f.red_out[r] = comm_->red_out(r);
-      f.red_flag_out[r] = comm_->red_flag_out(r);
-    }
-    f.error = &comm_->flags()->error;
-  }
+  if (comm_ && comm_->world() > 1) f.cross = comm_->cross_sum();
   return f;
 }
 

@@ -59,6 +59,7 @@ class Problem {
   void set_dimensions(size_t nrows, size_t ncols) { nrows_ = nrows; ncols_ = ncols; dims_set_ = true; }
   void set_scaling_alpha(float alpha) { scaling_type_ = kScalingAlpha; scaling_alpha_ = alpha; }
   void set_scaling_identity() { scaling_type_ = kScalingIdentity; }
+  Scaling scaling_type() const { return scaling_type_; }
   void set_scaling_custom(const float* left, size_t nl, const float* right, size_t nr);
 
   void initialize();

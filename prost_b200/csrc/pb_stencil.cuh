@@ -24,6 +24,7 @@
 #pragma once
 
 #include "pb_backend.cuh"
+#include "pb_crosssum.cuh"
 #include "pb_fused.cuh"
 #include "pb_prox.cuh"
 #include "pb_reduce.cuh"
@@ -111,22 +112,15 @@ struct RingMulti {
 
 // Residual-refresh launches of the ring kernel finish the iteration themselves: the last CTA to arrive (ticket)
 // folds the per-CTA partial sums in index order, on slabs combines them across ranks through peer-mapped slots
-// (every rank stores its four sums into every rank's block over NVLink and sums the slots in rank order, so all
-// ranks get identical bits), and runs the step-size state machine (pdhg_update) -- no fold / all-reduce /
-// finalize launches on the iteration path.  ticket == nullptr: the caller finalizes (NCCL staging mode).
-constexpr int kMaxReduceRanks = 8;
+// (cross_rank_sum4, pb_crosssum.cuh: identical bits on all ranks), and runs the step-size state machine
+// (pdhg_update) -- no fold / all-reduce / finalize launches on the iteration path.  ticket == nullptr: the caller
+// finalizes (NCCL staging mode).
 struct RingFinish {
   unsigned* ticket = nullptr;
   PdhgState* state = nullptr;
   PdhgParams prm;
   unsigned long long iteration = 0;
-  int world = 1, rank = 0;
-  unsigned seq = 0;                              // number of this reduction; slots / flags by (seq & 1)
-  const double* red_in = nullptr;                // local slots [2][kMaxReduceRanks][4]
-  const unsigned* red_flag_in = nullptr;         // local flags [kMaxReduceRanks]: newest seq written by rank r
-  double* red_out[kMaxReduceRanks] = {};         // every rank's slots (own included)
-  unsigned* red_flag_out[kMaxReduceRanks] = {};
-  int* error = nullptr;
+  CrossSum cross;
 };
 
 struct GradGeom {

@@ -1065,28 +1065,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) grad2d_iteration_ring_kernel(
       block_sum2(da, db);
       if (threadIdx.x == 0) {
         double sums[4] = {pa, pb, da, db};
-        if (fin.world > 1) {
-          // slabs: my four sums into every rank's slot [seq & 1][my rank] (peer memory over NVLink), then the
-          // sequence number; wait for every rank's and add the slots in rank order (identical on all ranks)
-          const unsigned slot = (fin.seq & 1u) * kMaxReduceRanks;
-          for (int r = 0; r < fin.world; ++r) {
-            double* o = fin.red_out[r] + (size_t)(slot + fin.rank) * 4;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) __stcg(o + j, sums[j]);
-          }
-          __threadfence_system();
-          for (int r = 0; r < fin.world; ++r)
-            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(fin.red_flag_out[r] + fin.rank), "r"(fin.seq)
-                         : "memory");
-#pragma unroll
-          for (int j = 0; j < 4; ++j) sums[j] = 0.0;
-          for (int r = 0; r < fin.world; ++r) {
-            ring_flag_wait(fin.red_flag_in + r, fin.seq, fin.error);
-            const double* in = fin.red_in + (size_t)(slot + r) * 4;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) sums[j] += __ldcg(in + j);
-          }
-        }
+        cross_rank_sum4(fin.cross, sums);
         PdhgState ns = *fin.state;
         ns.iteration = fin.iteration;
         pdhg_update(ns, fin.prm, sums, true);

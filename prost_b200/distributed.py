@@ -131,6 +131,96 @@ def shard_description(desc, part, rank):
     return out
 
 
+class RowPartition:
+    """Rows [r0(k), r1(k)) of an m-row operator for each of ``world`` ranks (balanced, in order)."""
+
+    def __init__(self, nrows, world):
+        if world < 1 or nrows < world:
+            raise ValueError(f"cannot split {nrows} rows over {world} ranks")
+        base, extra = divmod(int(nrows), world)
+        widths = [base + (1 if r < extra else 0) for r in range(world)]
+        self.nrows, self.world = int(nrows), world
+        self.bounds = np.concatenate([[0], np.cumsum(widths)]).astype(np.int64)
+
+    def range(self, rank):
+        return int(self.bounds[rank]), int(self.bounds[rank + 1])
+
+
+def shard_rows(desc, part, rank):
+    """Row-sharded ADMM (BASELINE config 5): the description of rank ``rank``'s block of ROWS of the
+    stacked operator and of the f-side proxes; columns, prox_g and the n-side vectors stay whole (replicated).
+
+    Blocks are cut at the rank's row range (sparse / dense / zero blocks: a row slice of the matrix; diagonal
+    identity-pattern blocks become sparse slices).  f-side proxes must be element-wise (1d family, dim 1): their
+    index range and per-element coefficients are sliced.  Scaling: identity, or custom with the left vector sliced
+    (the alpha preconditioners need column sums over all ranks' rows and are rejected by the backend)."""
+    import scipy.sparse as sp
+    if part.nrows != int(desc["nrows"]):
+        raise ValueError("partition and description disagree on nrows")
+    r0, r1 = part.range(rank)
+
+    def block(b):
+        name, row, col, data = b
+        if name == "sparse":
+            A = sp.csr_matrix(data[0])
+        elif name == "dense":
+            A = np.asarray(data[0], dtype=np.float32)
+        elif name == "zero":
+            A = None
+            shape = (int(data[0]), int(data[1]))
+        elif name == "diags":
+            nr, nc, factors, offsets = data
+            A = sp.diags([np.full(min(nr, nc - max(o, 0)) if o >= 0 else min(nr + o, nc), f, np.float32)
+                          for f, o in zip(np.atleast_1d(factors), np.atleast_1d(offsets))],
+                         [int(o) for o in np.atleast_1d(offsets)], shape=(nr, nc), format="csr", dtype=np.float32)
+        else:
+            raise api.ProstError(-4, f"block '{name}' does not shard along rows")
+        nr = shape[0] if A is None else A.shape[0]
+        nc = shape[1] if A is None else A.shape[1]
+        lo, hi = max(r0, row), min(r1, row + nr)
+        if lo >= hi:
+            return None
+        if A is None:
+            return ("zero", lo - r0, col, [hi - lo, nc])
+        sl = A[lo - row:hi - row, :]
+        if name == "dense":
+            return ("dense", lo - r0, col, [np.ascontiguousarray(sl)])
+        return ("sparse", lo - r0, col, [sp.csc_matrix(sl)])
+
+    def prox(d):
+        name, idx, size, diagsteps, data = d
+        lo, hi = max(r0, idx), min(r1, idx + size)
+        if lo >= hi:
+            return None
+        if name == "zero":
+            return (name, lo - r0, hi - lo, diagsteps, [])
+        if not name.startswith("elem_operation:1d:"):
+            raise api.ProstError(-4, f"f-side prox '{name}' does not shard along rows (element-wise 1d proxes do)")
+        count, dim, interleaved, coeffs = data
+        if dim != 1:
+            raise api.ProstError(-4, "row-sharded ADMM needs dim = 1 on the f side")
+        cs = []
+        for c in coeffs:
+            c = np.asarray(c, dtype=np.float32).ravel()
+            cs.append(c if c.size == 1 else np.ascontiguousarray(c[lo - idx:hi - idx]))
+        return (name, lo - r0, hi - lo, diagsteps, [hi - lo, 1, interleaved, cs])
+
+    out = dict(nrows=r1 - r0, ncols=int(desc["ncols"]),
+               blocks=[b for b in (block(b) for b in desc["blocks"]) if b is not None])
+    for key in ("prox_g", "prox_gstar"):
+        if key in desc:
+            out[key] = list(desc[key])
+    for key in ("prox_f", "prox_fstar"):
+        if key in desc:
+            out[key] = [p for p in (prox(d) for d in desc[key]) if p is not None]
+    sc = desc.get("scaling", ("alpha", 1.0))
+    if sc[0] == "custom":
+        sc = ("custom", np.asarray(sc[1], np.float32)[r0:r1], np.asarray(sc[2], np.float32))
+    out["scaling"] = sc
+    out["rows"] = dict(r0=r0, r1=r1, rank=rank, world=part.world)
+    return out
+
+
 def init_comm(ctx, group=None):
     """Communicator over the ranks of an initialised ``torch.distributed`` process group: rank 0
     creates the NCCL unique id, torch broadcasts the 128 bytes (any backend: gloo or nccl)."""

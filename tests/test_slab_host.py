@@ -135,3 +135,36 @@ def test_slab_lifting_generator_equals_sharded_global_description():
     b = d["prox_fstar"][1][4][3][1]
     ref = (2.0 * syn.uniform(30, np.arange(12 * 9 * 5 // 2, dtype=np.uint64)) - 1.0).astype(np.float32)
     assert np.array_equal(b, ref)
+
+
+def test_shard_rows_partitions_the_stacked_operator():
+    """Host logic of the row-sharded ADMM (prost_b200.distributed.shard_rows): the ranks' row blocks of the sparse +
+    dense LASSO operator stack back to the global matrix, f-side coefficients are sliced with their rows, the
+    g side stays whole."""
+    import scipy.sparse as sp
+    from prost_b200 import distributed as pbd
+    from prost_b200 import synthetic as syn
+    import cases
+    desc = syn.lasso(500, 120, nnz_per_row=4, dense=40)
+    M = cases.linop_matrix(desc["blocks"]).toarray()
+    for world in (1, 2, 3, 7):
+        part = pbd.RowPartition(desc["nrows"], world)
+        rows, bvec = [], []
+        for r in range(world):
+            d = pbd.shard_rows(desc, part, r)
+            r0, r1 = part.range(r)
+            assert d["nrows"] == r1 - r0 and d["ncols"] == desc["ncols"]
+            Mr = np.zeros((d["nrows"], d["ncols"]))
+            for (name, row, col, data) in d["blocks"]:
+                A = data[0].toarray() if sp.issparse(data[0]) else np.asarray(data[0])
+                Mr[row:row + A.shape[0], col:col + A.shape[1]] += A
+            rows.append(Mr)
+            assert d["prox_g"] == desc["prox_g"]
+            covered = 0
+            for (name, idx, size, ds, (count, dim, il, coeffs)) in d["prox_f"]:
+                assert idx == covered and count == size and dim == 1
+                covered += size
+                bvec.append(coeffs[1])
+            assert covered == d["nrows"]
+        assert np.allclose(np.vstack(rows), M, rtol=0, atol=0)
+        assert np.array_equal(np.concatenate(bvec), desc["prox_f"][0][4][3][1])
