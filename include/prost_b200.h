@@ -187,6 +187,14 @@ int pb_prox_create_ind_sum(pb_context* ctx, size_t index, size_t count, size_t d
 int pb_prox_create_ind_sum_indexed(pb_context* ctx, size_t index, size_t size, size_t count, size_t dim,
                                    const unsigned long long* h_inds, float sum, size_t count2, size_t dim2,
                                    const unsigned long long* h_inds2, float sum2, pb_prox** out);
+/* ProxIndEpiConjQuad1D (north star: "ProxEpiConjQuadr"; mex name "ind_epi_conjquad_1d"): per (x, y) pair the
+ * projection onto the epigraph of the conjugate of rho(u) = a u^2 + b u + c on [alpha, beta], a >= 0.  PARITY
+ * UNPINNED: the reference only names the class (cmake/CustomSources.cmake.example:8-14, un-vendored repository
+ * preciserelaxation/src/cvpr2016/prost); built on helper.hpp:112-215 and validated against a double-precision
+ * brute-force projection.  coeffs = {a, b, c, alpha, beta}, each with 1 or count entries; pairs are planar
+ * (x at i, y at count + i) or interleaved. */
+int pb_prox_create_ind_epi_conjquad_1d(pb_context* ctx, size_t index, size_t count, int interleaved, int diagsteps,
+                                       const float* const h_coeffs[5], const size_t coeff_len[5], pb_prox** out);
 /* ProxIndHalfspace(index,count,dim,interleaved,diagsteps,a,b): projection onto <a, x> <= b per group; a has
  * count*dim (planar) or dim entries, b count or 1 (prox_ind_halfspace.hpp:41-52, prox_ind_halfspace.cu:34-137) */
 int pb_prox_create_ind_halfspace(pb_context* ctx, size_t index, size_t count, size_t dim, int interleaved,

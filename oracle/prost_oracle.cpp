@@ -598,6 +598,78 @@ struct ProxIndSumIndexed : Prox {
   }
 };
 
+// ProxIndEpiConjQuad1D ("ProxEpiConjQuadr" in the north star).  PARITY UNPINNED: the reference tree only names the
+// class (cmake/CustomSources.cmake.example:8-14: ../../preciserelaxation/src/cvpr2016/prost/prox_ind_epi_conjquad_1d.cu,
+// no version pinned, not vendored).  Restated from the published definition (Moellenhoff, Laude, Moeller, Lellmann,
+// Cremers: Sublabel-accurate relaxation of nonconvex energies, CVPR 2016, eq. (17)-(21): the dual constraint set of
+// a piecewise quadratic data term is the epigraph of the conjugate of every piece) on top of the in-tree helpers it
+// uses (helper.hpp:112-183 ProjectEpiQuad1d / ProjectEpiQuadGeneral1d, :185-215 halfspace projection).  Pinned only
+// by a double-precision brute-force projection (tests/test_oracle_closed_forms.py).
+static void project_epi_quad_1d(float x0, float y0, float alpha, float& x, float& y) {      // helper.hpp:112-157
+  if (y0 >= alpha * (x0 * x0)) { x = x0; y = y0; return; }
+  const float a = static_cast<float>(2. * alpha * std::abs(x0));
+  const float b = static_cast<float>(2. * (1. - 2. * alpha * y0) / 3.);
+  float d, v;
+  if (b < 0) {
+    const float sq = std::pow(-b, static_cast<float>(3. / 2.));
+    d = (a - sq) * (a + sq);
+  } else {
+    d = a * a + b * b * b;
+  }
+  if (d >= 0) {
+    const float c = std::pow(a + std::sqrt(d), static_cast<float>(1. / 3.));
+    v = c - b / c;
+  } else {
+    v = 2 * std::sqrt(-b) * std::cos(std::acos(a / std::pow(-b, static_cast<float>(3. / 2.))) / static_cast<float>(3.));
+  }
+  if (x0 > 0) x = static_cast<float>(v / (2. * alpha));
+  else if (x0 < 0) x = static_cast<float>(-v / (2. * alpha));
+  else x = 0;
+  y = alpha * x * x;
+}
+
+struct ProxIndEpiConjQuad1D : ProxSeparable {
+  vec co[5];                               // a, b, c, alpha, beta: 1 or count entries
+  ProxIndEpiConjQuad1D(size_t i, size_t cnt, bool il, bool ds, const float* const* c, const size_t* len)
+      : ProxSeparable(i, cnt, 2, il, ds) {
+    for (int k = 0; k < 5; ++k) co[k].assign(c[k], c[k] + len[k]);
+  }
+  void eval_local(float* res, const float* arg, const float*, float, bool) override {
+#pragma omp parallel for schedule(static)
+    for (size_t tx = 0; tx < count; ++tx) {
+      auto at = [&](int k) { return co[k].size() == 1 ? co[k][0] : co[k][tx]; };
+      const float a = at(0), b = at(1), c = at(2), alpha = at(3), beta = at(4);
+      const float x0 = arg[this->at(tx, 0)], y0 = arg[this->at(tx, 1)];
+      const float x1 = 2 * a * alpha + b, x2 = 2 * a * beta + b;
+      const float r1 = (a * alpha + b) * alpha + c, r2 = (a * beta + b) * beta + c;
+      const float y1 = alpha * x1 - r1, y2 = beta * x2 - r2;
+      const float s1 = (x0 - x1) + alpha * (y0 - y1), s2 = (x0 - x2) + beta * (y0 - y2);
+      float x, y;
+      if (s1 <= 0) {
+        const float viol = std::max(0.f, alpha * x0 - y0 - r1) / (alpha * alpha + 1.f);
+        x = x0 - viol * alpha;
+        y = y0 + viol;
+      } else if (s2 >= 0) {
+        const float viol = std::max(0.f, beta * x0 - y0 - r2) / (beta * beta + 1.f);
+        x = x0 - viol * beta;
+        y = y0 + viol;
+      } else if (a > 0) {
+        const float p = 1.f / (4 * a), q = -b / (2 * a), r = b * b / (4 * a) - c;
+        float tx_, ty_;                                                  // ProjectEpiQuadGeneral1d, helper.hpp:160-183
+        project_epi_quad_1d(static_cast<float>(x0 + q / (2. * p)), static_cast<float>(y0 + q * q / (4. * p) - r), p, tx_, ty_);
+        x = static_cast<float>(tx_ - q / (2. * p));
+        y = static_cast<float>(ty_ - q * q / (4. * p) + r);
+      } else {
+        const bool inside = y0 >= std::max(alpha * (x0 - b), beta * (x0 - b)) - c;
+        x = inside ? x0 : b;
+        y = inside ? y0 : -c;
+      }
+      res[this->at(tx, 0)] = x;
+      res[this->at(tx, 1)] = y;
+    }
+  }
+};
+
 struct ProxIndSOC : ProxSeparable {         // prox_ind_soc.cu:33-77: { (x, y) | |x|_2 <= y }, alpha = 1 only
   ProxIndSOC(size_t i, size_t c, size_t d, bool il, bool ds) : ProxSeparable(i, c, d, il, ds) {}
   void eval_local(float* res, const float* arg, const float*, float, bool) override {
@@ -1132,6 +1204,10 @@ int orc_prox_ind_halfspace(void* p, size_t idx, size_t count, size_t dim, int il
 int orc_prox_ind_sum_indexed(void* p, size_t idx, size_t size, size_t count, size_t dim, const unsigned long long* inds,
                              float total, size_t count2, size_t dim2, const unsigned long long* inds2, float total2) {
   return push(PP, std::make_shared<ProxIndSumIndexed>(idx, size, count, dim, inds, total, count2, dim2, inds2, total2));
+}
+int orc_prox_ind_epi_conjquad_1d(void* p, size_t idx, size_t count, int il, int ds, const float* const* coeffs,
+                                 const size_t* len) {
+  return push(PP, std::make_shared<ProxIndEpiConjQuad1D>(idx, count, il != 0, ds != 0, coeffs, len));
 }
 int orc_prox_ind_soc(void* p, size_t idx, size_t count, size_t dim, int il, int ds) {
   return push(PP, std::make_shared<ProxIndSOC>(idx, count, dim, il != 0, ds != 0));

@@ -391,6 +391,20 @@ class ProxIndSum(Prox):
             C.byref(self._h)))
 
 
+class ProxIndEpiConjQuad1D(Prox):
+    """ProxIndEpiConjQuad1D (the north star's "ProxEpiConjQuadr"; source external to the reference tree, parity
+    unpinned): per (x, y) pair the projection onto the epigraph of the conjugate of a u^2 + b u + c on
+    [alpha, beta].  Every coefficient is a scalar or one value per pair."""
+
+    def __init__(self, ctx, index, count, interleaved, diagsteps, a, b, c, alpha, beta):
+        super().__init__(ctx)
+        keep = [_f32(np.atleast_1d(v)) for v in (a, b, c, alpha, beta)]
+        ptrs = (_capi.c_float_p * 5)(*[_fp(v) for v in keep])
+        lens = (C.c_size_t * 5)(*[v.size for v in keep])
+        check(lib.pb_prox_create_ind_epi_conjquad_1d(ctx._h, index, count, int(interleaved), int(diagsteps), ptrs, lens,
+                                                     C.byref(self._h)))
+
+
 class ProxIndHalfspace(Prox):
     """ProxIndHalfspace<T>(index, count, dim, interleaved, diagsteps, a, b): projection onto <a, x> <= b."""
 

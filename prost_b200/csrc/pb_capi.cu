@@ -338,6 +338,11 @@ int pb_prox_create_ind_sum_indexed(pb_context* c, size_t index, size_t size, siz
                                    const unsigned long long* inds2, float sum2, pb_prox** out) {
   PB_MAKE_PROX(pb::make_prox_ind_sum_indexed(&c->ctx, index, size, count, dim, inds, sum, count2, dim2, inds2, sum2));
 }
+int pb_prox_create_ind_epi_conjquad_1d(pb_context* c, size_t index, size_t count, int interleaved, int diagsteps,
+                                       const float* const coeffs[5], const size_t coeff_len[5], pb_prox** out) {
+  PB_MAKE_PROX((require(coeffs && coeff_len, "NULL coefficients"),
+                pb::make_prox_ind_epi_conjquad_1d(&c->ctx, index, count, interleaved != 0, diagsteps != 0, coeffs, coeff_len)));
+}
 int pb_prox_create_ind_halfspace(pb_context* c, size_t index, size_t count, size_t dim, int interleaved, int diagsteps,
                                  const float* a, size_t na, const float* b, size_t nb, pb_prox** out) {
   PB_MAKE_PROX(pb::make_prox_ind_halfspace(&c->ctx, index, count, dim, interleaved != 0, diagsteps != 0, a, na, b, nb));

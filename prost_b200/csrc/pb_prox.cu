@@ -595,6 +595,130 @@ class ProxIndSumIndexed : public Prox {
   bool two_ = false;
 };
 
+// ---- ProxIndEpiConjQuad1D ("ProxEpiConjQuadr" of the sublabel-accurate lifting, Moellenhoff et al. CVPR 2016) ----------
+// PARITY UNPINNED: the reference names this prox only in cmake/CustomSources.cmake.example:8-14 (un-vendored repository
+// preciserelaxation/src/cvpr2016/prost/prox_ind_epi_conjquad_1d.cu); its source is not under /root/reference.  Built
+// from the published definition and the in-tree pieces it rests on (helper.hpp:112-183 ProjectEpiQuad1d /
+// ProjectEpiQuadGeneral1d, :185-215 ProjectHalfspace), validated against a double-precision brute-force projection
+// (tests/test_oracle_closed_forms.py, tests/test_zz_gpu_next_rows.py).
+//
+// Per group (x, y): Euclidean projection onto epi(rho*) with rho(u) = a u^2 + b u + c on [alpha, beta], a >= 0:
+//   rho*(x) = alpha x - rho(alpha)            x <= x1 = 2 a alpha + b      (ray of slope alpha)
+//           = (x - b)^2 / (4a) - c            x1 <= x <= x2 = 2 a beta + b (parabola arc; a = 0: the vertex (b, -c))
+//           = beta x - rho(beta)              x >= x2                      (ray of slope beta)
+// rho* is C^1, so the three boundary pieces own the strips between the normals at the two junctions: the sign of
+// the tangential coordinate (x0 - xj) + slope_j (y0 - yj) selects the piece.
+__device__ __forceinline__ void project_epi_quad_1d(float x0, float y0, float alpha, float& x, float& y) {
+  if (y0 >= alpha * (x0 * x0)) { x = x0; y = y0; return; }                  // helper.hpp:121-124
+  const float a = static_cast<float>(2. * static_cast<double>(alpha) * static_cast<double>(fabsf(x0)));
+  const float b = static_cast<float>(2. * (1. - 2. * static_cast<double>(alpha) * static_cast<double>(y0)) / 3.);
+  float d, v;
+  if (b < 0) {
+    const float sq = powf(-b, 1.5f);
+    d = (a - sq) * (a + sq);
+  } else {
+    d = a * a + b * b * b;
+  }
+  if (d >= 0) {
+    const float c = powf(a + sqrtf(d), static_cast<float>(1. / 3.));
+    v = c - b / c;
+  } else {
+    v = 2 * sqrtf(-b) * cosf(acosf(a / powf(-b, 1.5f)) / 3.f);
+  }
+  if (x0 > 0) x = static_cast<float>(static_cast<double>(v) / (2. * static_cast<double>(alpha)));
+  else if (x0 < 0) x = static_cast<float>(-static_cast<double>(v) / (2. * static_cast<double>(alpha)));
+  else x = 0;
+  y = alpha * x * x;
+}
+
+__device__ __forceinline__ void project_epi_conjquad_1d(float x0, float y0, float a, float b, float c, float alpha,
+                                                        float beta, float& x, float& y) {
+  const float x1 = 2 * a * alpha + b, x2 = 2 * a * beta + b;               // junction abscissae
+  const float r1 = (a * alpha + b) * alpha + c, r2 = (a * beta + b) * beta + c;   // rho(alpha), rho(beta)
+  const float y1 = alpha * x1 - r1, y2 = beta * x2 - r2;                   // rho*(x1), rho*(x2)
+  const float s1 = (x0 - x1) + alpha * (y0 - y1);                          // tangential coordinates at the junctions
+  const float s2 = (x0 - x2) + beta * (y0 - y2);
+  if (s1 <= 0) {                                                           // ray 1: halfspace alpha x - y <= rho(alpha)
+    const float viol = fmaxf(0.f, alpha * x0 - y0 - r1) / (alpha * alpha + 1.f);
+    x = x0 - viol * alpha;
+    y = y0 + viol;
+  } else if (s2 >= 0) {                                                    // ray 2
+    const float viol = fmaxf(0.f, beta * x0 - y0 - r2) / (beta * beta + 1.f);
+    x = x0 - viol * beta;
+    y = y0 + viol;
+  } else if (a > 0) {                                                      // parabola y >= p x^2 + q x + r
+    const float p = 1.f / (4 * a), q = -b / (2 * a), r = b * b / (4 * a) - c;
+    float tx, ty;                                                          // ProjectEpiQuadGeneral1d, helper.hpp:160-183
+    project_epi_quad_1d(static_cast<float>(x0 + q / (2. * p)), static_cast<float>(y0 + q * q / (4. * p) - r), p, tx, ty);
+    x = static_cast<float>(tx - q / (2. * p));
+    y = static_cast<float>(ty - q * q / (4. * p) + r);
+  } else {                                                                 // a = 0: normal cone of the vertex (b, -c)
+    const bool inside = y0 >= fmaxf(alpha * (x0 - b), beta * (x0 - b)) - c;
+    x = inside ? x0 : b;
+    y = inside ? y0 : -c;
+  }
+}
+
+struct ConjQuadCoeffs {
+  const float* ptr[5];      // a, b, c, alpha, beta per group, or null
+  float val[5];
+  __device__ __forceinline__ float at(int k, size_t i) const { return ptr[k] ? ptr[k][i] : val[k]; }
+};
+
+__global__ void __launch_bounds__(kBlock) ind_epi_conjquad_1d_kernel(float* __restrict__ res,
+                                                                     const float* __restrict__ arg, size_t count,
+                                                                     bool interleaved, const ConjQuadCoeffs co) {
+  for (size_t tx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; tx < count; tx += (size_t)gridDim.x * blockDim.x) {
+    const size_t ix = interleaved ? 2 * tx : tx, iy = interleaved ? 2 * tx + 1 : tx + count;
+    float x, y;
+    project_epi_conjquad_1d(arg[ix], arg[iy], co.at(0, tx), co.at(1, tx), co.at(2, tx), co.at(3, tx), co.at(4, tx), x, y);
+    res[ix] = x;
+    res[iy] = y;
+  }
+}
+
+class ProxIndEpiConjQuad1D : public ProxGroupProjection {
+ public:
+  ProxIndEpiConjQuad1D(Context* ctx, size_t index, size_t count, bool interleaved, bool diagsteps,
+                       const float* const coeffs[5], const size_t len[5])
+      : ProxGroupProjection(ctx, index, count, 2, interleaved, diagsteps) {
+    static const char* names[5] = {"a", "b", "c", "alpha", "beta"};
+    for (int k = 0; k < 5; ++k) {
+      if (!coeffs[k] || (len[k] != 1 && len[k] != count))
+        fail(PB_ERR_INVALID, std::string("ProxIndEpiConjQuad1D: coefficient ") + names[k] + " needs 1 or count entries");
+      co_.ptr[k] = nullptr;
+      co_.val[k] = coeffs[k][0];
+      if (len[k] > 1) {
+        d_[k].resize(len[k]);
+        upload_from_host(ctx, d_[k].data(), coeffs[k], len[k]);
+        co_.ptr[k] = d_[k].data();
+      }
+    }
+    for (size_t i = 0; i < std::max(len[0], std::max(len[3], len[4])); ++i) {
+      const float a = coeffs[0][len[0] > 1 ? i : 0], al = coeffs[3][len[3] > 1 ? i : 0], be = coeffs[4][len[4] > 1 ? i : 0];
+      if (!(a >= 0.f)) fail(PB_ERR_INVALID, "ProxIndEpiConjQuad1D: a must be >= 0 (convex pieces)");
+      if (!(al <= be)) fail(PB_ERR_INVALID, "ProxIndEpiConjQuad1D: needs alpha <= beta");
+    }
+  }
+  int kind() const override { return kProxIndEpiConjQuad1D; }
+  size_t gpu_mem_amount() const override {
+    size_t n = 0;
+    for (auto& d : d_) n += d.size();
+    return n * sizeof(float);
+  }
+  void eval_local(float* res, const float* arg, const float*, float, bool) override {
+    ctx_->bind();
+    if (count_ == 0) return;
+    ind_epi_conjquad_1d_kernel<<<stream_grid(ctx_, count_), kBlock, 0, ctx_->stream>>>(res, arg, count_, interleaved_, co_);
+    PB_CHECK_LAUNCH();
+    ctx_->launches++;
+  }
+
+ private:
+  ConjQuadCoeffs co_;
+  DeviceBuffer<float> d_[5];
+};
+
 // ---- ProxTransform (prox_transform.cu:27-226): prox of  c f(a x - b) + <d, x> + (e/2)|x|^2  through the prox of f.
 // Same three element-wise steps around the inner prox as the reference, same float expressions.
 struct TransformCoeffs {
@@ -753,6 +877,11 @@ std::shared_ptr<Prox> make_prox_ind_sum_indexed(Context* ctx, size_t index, size
                                                 const unsigned long long* inds, float total, size_t count2,
                                                 size_t dim2, const unsigned long long* inds2, float total2) {
   return std::make_shared<ProxIndSumIndexed>(ctx, index, size, count, dim, inds, total, count2, dim2, inds2, total2);
+}
+
+std::shared_ptr<Prox> make_prox_ind_epi_conjquad_1d(Context* ctx, size_t index, size_t count, bool interleaved,
+                                                    bool diagsteps, const float* const coeffs[5], const size_t len[5]) {
+  return std::make_shared<ProxIndEpiConjQuad1D>(ctx, index, count, interleaved, diagsteps, coeffs, len);
 }
 
 std::shared_ptr<Prox> make_prox_ind_halfspace(Context* ctx, size_t index, size_t count, size_t dim, bool interleaved,

@@ -30,6 +30,7 @@ enum ProxKind : int {
   kProxIndHalfspace = 9,
   kProxIndSOC = 10,
   kProxIndSumIndexed = 11,
+  kProxIndEpiConjQuad1D = 12,
 };
 
 // per-element vector or scalar (ElemOpCoefficients: prox_elem_operation.hpp:104-109)
@@ -373,6 +374,10 @@ std::shared_ptr<Prox> make_prox_ind_sum(Context* ctx, size_t index, size_t count
 std::shared_ptr<Prox> make_prox_ind_sum_indexed(Context* ctx, size_t index, size_t size, size_t count, size_t dim,
                                                 const unsigned long long* inds, float total, size_t count2,
                                                 size_t dim2, const unsigned long long* inds2, float total2);
+// ProxIndEpiConjQuad1D (external to the reference tree, cmake/CustomSources.cmake.example:8-14; parity unpinned):
+// projection of (x, y) pairs onto the epigraph of the conjugate of a u^2 + b u + c restricted to [alpha, beta]
+std::shared_ptr<Prox> make_prox_ind_epi_conjquad_1d(Context* ctx, size_t index, size_t count, bool interleaved,
+                                                    bool diagsteps, const float* const coeffs[5], const size_t len[5]);
 // ProxIndHalfspace(index,count,dim,interleaved,diagsteps,a,b) (prox_ind_halfspace.hpp:41-52), ProxIndSOC(..., alpha)
 // (prox_ind_soc.hpp:39-48); both address planar groups regardless of `interleaved`, like the reference kernels
 std::shared_ptr<Prox> make_prox_ind_halfspace(Context* ctx, size_t index, size_t count, size_t dim, bool interleaved,

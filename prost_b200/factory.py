@@ -10,6 +10,7 @@ reference's mex registry names and argument order (matlab/+prost/private/factory
   elem_operation:ind_simplex, elem_operation:ind_sum   : [count, dim, interleaved]
   ind_epi_quad                                         : [count, dim, interleaved, [a, b, c]]
   ind_sum                                              : [dim, inds, sum(, dim2, inds2, sum2)]
+  ind_epi_conjquad_1d                                  : [count, interleaved, [a, b, c, alpha, beta]]
   ind_halfspace                                        : [count, dim, interleaved, [a, b]]
   ind_soc                                              : [count, dim, interleaved, alpha]
   moreau                                               : [child description]
@@ -40,6 +41,9 @@ def create_prox(ctx, desc):
         if len(data) == 3:
             return api.ProxIndSum(ctx, idx, size, data[0], data[1], data[2])
         return api.ProxIndSum(ctx, idx, size, data[0], data[1], data[2], data[3], data[4], data[5])
+    if name == "ind_epi_conjquad_1d":      # [count, interleaved, [a, b, c, alpha, beta]]  (source external, see api)
+        count, interleaved, (a, b, c, alpha, beta) = data
+        return api.ProxIndEpiConjQuad1D(ctx, idx, count, interleaved, diagsteps, a, b, c, alpha, beta)
     if name == "ind_halfspace":
         count, dim, interleaved, (a, b) = data
         return api.ProxIndHalfspace(ctx, idx, count, dim, interleaved, diagsteps, a, b)

@@ -228,6 +228,26 @@ def prox_ind_sum_indexed_cases(small=False):
     return cases
 
 
+def prox_epi_conjquad_cases(small=False):
+    """ind_epi_conjquad_1d (the north star's ProxEpiConjQuadr; parity unpinned, see prost_b200/csrc/pb_prox.cu):
+    (x, y) pairs against the conjugate of a u^2 + b u + c on [alpha, beta]: per-pair and scalar coefficients, planar
+    and interleaved, and the degenerate linear pieces a = 0."""
+    r = rng(61)
+    cases = {}
+    n = 800 if not small else 41
+    a = r.uniform(0.2, 3.0, n).astype(np.float32)
+    b = r.uniform(-2, 2, n).astype(np.float32)
+    c = r.uniform(-1, 1, n).astype(np.float32)
+    lo = r.uniform(-1.5, 0.5, n).astype(np.float32)
+    hi = (lo + r.uniform(0.05, 2.0, n)).astype(np.float32)
+    for il in (False, True):
+        cases[f"epi_conjquad_vec_il{int(il)}"] = (("ind_epi_conjquad_1d", 0, 2 * n, False, [n, il, [a, b, c, lo, hi]]), 2 * n)
+    cases["epi_conjquad_scalar"] = (("ind_epi_conjquad_1d", 0, 2 * n, False, [n, False, [[0.7], [-0.3], [0.2], [-0.5], [1.25]]]), 2 * n)
+    cases["epi_conjquad_linear"] = (("ind_epi_conjquad_1d", 5, 2 * n, False, [n, False, [np.zeros(n, np.float32), b, c, lo, hi]]),
+                                    2 * n + 9)
+    return cases
+
+
 def prox_projection_cases(small=False):
     """ind_halfspace (prox_ind_halfspace.cu) and ind_soc (prox_ind_soc.cu): planar groups."""
     r = rng(31)

@@ -44,6 +44,7 @@ lib.orc_prox_simplex.argtypes = [C.c_void_p, sz, sz, sz, C.c_int, C.c_int]
 lib.orc_prox_ind_sum.argtypes = [C.c_void_p, sz, sz, sz, C.c_int, C.c_int]
 lib.orc_prox_ind_sum_indexed.argtypes = [C.c_void_p, sz, sz, sz, sz, C.POINTER(C.c_ulonglong), C.c_float, sz, sz,
                                          C.POINTER(C.c_ulonglong), C.c_float]
+lib.orc_prox_ind_epi_conjquad_1d.argtypes = [C.c_void_p, sz, sz, C.c_int, C.c_int, C.POINTER(fp), C.POINTER(sz)]
 lib.orc_prox_ind_halfspace.argtypes = [C.c_void_p, sz, sz, sz, C.c_int, C.c_int, fp, sz, fp, sz]
 lib.orc_prox_ind_soc.argtypes = [C.c_void_p, sz, sz, sz, C.c_int, C.c_int]
 lib.orc_prox_epi_quad.argtypes = [C.c_void_p, sz, sz, sz, C.c_int, C.c_int, fp, sz, fp, sz, fp, sz]
@@ -187,6 +188,12 @@ class OracleProblem:
                                                 float(data[2]), (b.size // d2) if two else 0, d2,
                                                 b.ctypes.data_as(u64p) if two else None,
                                                 float(data[5]) if two else 0.0)
+        if name == "ind_epi_conjquad_1d":
+            count, il, coeffs = data
+            arrs = [_f32(np.atleast_1d(c)) for c in coeffs]
+            ptrs = (fp * 5)(*[_p(a) for a in arrs])
+            lens = (sz * 5)(*[a.size for a in arrs])
+            return lib.orc_prox_ind_epi_conjquad_1d(self.h, idx, count, int(il), int(diagsteps), ptrs, lens)
         if name == "ind_soc":
             count, dim, il = data[:3]
             return lib.orc_prox_ind_soc(self.h, idx, count, dim, int(il), int(diagsteps))

@@ -125,3 +125,31 @@ def brute_force_epi_quad(x0, y0, a, iters=200):
     r = 0.5 * (lo + hi)
     x = x0 / n0 * r if n0 > 0 else np.zeros_like(x0)
     return x, a * r * r
+
+
+def project_epi_conjquad_1d_bruteforce(x0, y0, a, b, c, alpha, beta):
+    """Double-precision Euclidean projection of (x0, y0) onto epi(rho*), rho(u) = a u^2 + b u + c on [alpha, beta]:
+    rho*(x) = max_{u in [alpha, beta]} (u x - rho(u)).  Independent of the product's case analysis: the distance to
+    the boundary point (x, rho*(x)) is minimised over x by a bracketing grid followed by golden-section search."""
+    def conj(x):
+        if a > 0:
+            u = min(max((x - b) / (2 * a), alpha), beta)
+        else:
+            u = alpha if (x - b) < 0 else beta
+        return u * x - (a * u * u + b * u + c)
+    if y0 >= conj(x0):
+        return x0, y0
+    f = lambda x: (x - x0) ** 2 + (conj(x) - y0) ** 2
+    span = 10.0 + abs(x0) + abs(y0) + abs(b) + 2 * a * max(abs(alpha), abs(beta))
+    xs = np.linspace(x0 - span, x0 + span, 4001)
+    k = int(np.argmin([f(x) for x in xs]))
+    lo, hi = xs[max(k - 1, 0)], xs[min(k + 1, len(xs) - 1)]
+    g = (np.sqrt(5.0) - 1) / 2
+    for _ in range(200):
+        m1, m2 = hi - g * (hi - lo), lo + g * (hi - lo)
+        if f(m1) < f(m2):
+            hi = m2
+        else:
+            lo = m1
+    x = 0.5 * (lo + hi)
+    return x, conj(x)

@@ -296,3 +296,27 @@ def test_prox_ind_sum_indexed_is_the_weighted_projection():
                 for g in inds:
                     want[g] = a[g] - t[g] * (a[g].sum() - s) / t[g].sum()
             assert np.abs(res[lo:hi] - want).max() <= 2e-5 * max(1.0, np.abs(want).max()), (name, invert)
+
+
+def test_prox_ind_epi_conjquad_1d_is_the_projection_onto_the_conjugate_epigraph():
+    """ProxIndEpiConjQuad1D has no source in the reference tree (parity unpinned): the oracle is pinned on an
+    independent double-precision brute-force projection onto epi(rho*), rho(u) = a u^2 + b u + c on [alpha, beta],
+    covering both rays, the parabola arc, the a = 0 vertex and interior points; results are feasible and
+    idempotent."""
+    r = np.random.default_rng(17)
+    for name, (desc, n) in cases.prox_epi_conjquad_cases(small=True).items():
+        count, il, co = desc[4]
+        lo, hi = desc[1], desc[1] + desc[2]
+        arg = (3 * r.standard_normal(n)).astype(np.float32)
+        res = oracle_prox_eval(desc, arg, np.ones(n, np.float32), 1.0)
+        again = oracle_prox_eval(desc, res, np.ones(n, np.float32), 1.0)
+        A, R, R2 = arg[lo:hi], res[lo:hi], again[lo:hi]
+        xs, ys = (A[0::2], A[1::2]) if il else (A[:count], A[count:])
+        rx, ry = (R[0::2], R[1::2]) if il else (R[:count], R[count:])
+        assert np.abs(R2 - R).max() <= 2e-5 * max(1.0, np.abs(R).max()), name          # projection: idempotent
+        at = lambda k, i: float(np.atleast_1d(co[k])[i if np.atleast_1d(co[k]).size > 1 else 0])
+        for i in range(count):
+            wx, wy = refmath.project_epi_conjquad_1d_bruteforce(float(xs[i]), float(ys[i]), at(0, i), at(1, i), at(2, i),
+                                                                at(3, i), at(4, i))
+            scale = max(1.0, abs(wx), abs(wy))
+            assert abs(rx[i] - wx) <= 2e-4 * scale and abs(ry[i] - wy) <= 2e-4 * scale, (name, i, (rx[i], ry[i]), (wx, wy))

@@ -134,6 +134,55 @@ def test_ind_sum_indexed_errors(ctx):
     assert "outside the prox range" in str(e.value)
 
 
+# ---- ind_epi_conjquad_1d: the north star's ProxEpiConjQuadr (source external to the reference tree) -------------
+CONJ_CASES = cases.prox_epi_conjquad_cases()
+
+
+@pytest.mark.parametrize("name", sorted(CONJ_CASES))
+def test_epi_conjquad_matches_oracle_and_bruteforce(ctx, name):
+    """PARITY UNPINNED (no reference source): the CUDA kernel against the oracle restatement (same float
+    expressions) and, on a sample, against the independent double-precision brute-force projection."""
+    import refmath
+    desc, n = CONJ_CASES[name]
+    arg, tau_diag, tau = _inputs(name, n)
+    arg = (1.5 * arg).astype(np.float32)
+    got = pb.create_prox(ctx, desc).Eval(arg, tau_diag, tau)
+    want = oracle_prox_eval(desc, arg, tau_diag, tau)
+    lo, hi = desc[1], desc[1] + desc[2]
+    scale = max(1.0, float(np.abs(want[lo:hi]).max()))
+    assert np.abs(got[lo:hi] - want[lo:hi]).max() <= 2e-5 * scale, name
+    count, il, co = desc[4]
+    G, A = got[lo:hi], arg[lo:hi]
+    gx, gy = (G[0::2], G[1::2]) if il else (G[:count], G[count:])
+    ax, ay = (A[0::2], A[1::2]) if il else (A[:count], A[count:])
+    at = lambda k, i: float(np.atleast_1d(co[k])[i if np.atleast_1d(co[k]).size > 1 else 0])
+    for i in range(0, count, 7):
+        wx, wy = refmath.project_epi_conjquad_1d_bruteforce(float(ax[i]), float(ay[i]), at(0, i), at(1, i), at(2, i),
+                                                            at(3, i), at(4, i))
+        s = max(1.0, abs(wx), abs(wy))
+        assert abs(gx[i] - wx) <= 2e-4 * s and abs(gy[i] - wy) <= 2e-4 * s, (name, i)
+
+
+def test_epi_conjquad_in_a_pdhg_solve_matches_oracle(ctx):
+    """Sublabel-style dual constraint inside PDHG: K = identity block, f* = ind_epi_conjquad_1d on (x, y) pairs,
+    g = quadratic; the unfused schedule against the oracle running the same description."""
+    r = np.random.default_rng(3)
+    n = 600
+    a = r.uniform(0.3, 2.0, n // 2).astype(np.float32)
+    b = r.uniform(-1, 1, n // 2).astype(np.float32)
+    c = r.uniform(-0.5, 0.5, n // 2).astype(np.float32)
+    lo = r.uniform(-1, 0, n // 2).astype(np.float32)
+    hi = (lo + r.uniform(0.2, 1.5, n // 2)).astype(np.float32)
+    f = r.standard_normal(n).astype(np.float32)
+    desc = dict(nrows=n, ncols=n, blocks=[("diags", 0, 0, [n, n, [1.0], [0]])],
+                prox_g=[("elem_operation:1d:square", 0, n, True, [n, 1, False, cases.coeffs(a=1, b=f, c=2.0)])],
+                prox_fstar=[("ind_epi_conjquad_1d", 0, n, False, [n // 2, False, [a, b, c, lo, hi]])],
+                scaling=("alpha", 1.0))
+    got = run_cuda(ctx, desc, 80, stepsize="alg1", residual_iter=4)
+    want = run_oracle(desc, 80, stepsize="alg1", residual_iter=4)
+    assert_parity(got, want, iter_tol=5e-5, label="epi_conjquad in PDHG")
+
+
 # ---- ind_halfspace, ind_soc (SURVEY.md 8(f) row 2) -------------------------------------------------------------
 PROJ_CASES = cases.prox_projection_cases()
 
