@@ -8,7 +8,7 @@
 namespace prost {
 
 namespace detail {
-enum ElemOpKind { kElemOp1D, kElemOpNorm2, kElemOpIndSimplex, kElemOpIndSum };
+enum ElemOpKind { kElemOp1D, kElemOpNorm2, kElemOpIndSimplex, kElemOpIndSum, kElemOpSpectral };
 }
 
 /// DIM = 0 means "taken from the constructor"; COEFFS_COUNT = number of per-element coefficient arrays.

@@ -10,6 +10,14 @@
 
 namespace prost {
 
+namespace detail {
+// kSpectralKind / kFunction2D of the spectral tags, 0 for every other element operation (SFINAE on the member)
+template <class OP> int spectral_kind(decltype(OP::kSpectralKind)*) { return OP::kSpectralKind; }
+template <class OP> int spectral_kind(...) { return 0; }
+template <class OP> int function_2d(decltype(OP::kFunction2D)*) { return OP::kFunction2D; }
+template <class OP> int function_2d(...) { return 0; }
+}  // namespace detail
+
 template <typename T, class ELEM_OPERATION>
 class ProxElemOperation : public ProxSeparableSum<T> {
  public:
@@ -45,7 +53,12 @@ class ProxElemOperation : public ProxSeparableSum<T> {
     const float* ptrs[7];
     size_t lens[7];
     for (int k = 0; k < 7; ++k) { ptrs[k] = coeffs_[k].data(); lens[k] = coeffs_[k].size(); }
-    if (ELEM_OPERATION::kKind == detail::kElemOp1D)
+    if (ELEM_OPERATION::kKind == detail::kElemOpSpectral)
+      detail::check(pb_prox_create_spectral(ctx, detail::spectral_kind<ELEM_OPERATION>(0), this->index_, this->count_,
+                                            this->dim_, this->interleaved_, this->diagsteps_,
+                                            ELEM_OPERATION::kFunctionId, detail::function_2d<ELEM_OPERATION>(0), ptrs,
+                                            lens, &h));
+    else if (ELEM_OPERATION::kKind == detail::kElemOp1D)
       detail::check(pb_prox_create_elem_1d(ctx, this->index_, this->count_, this->dim_, this->interleaved_,
                                            this->diagsteps_, ELEM_OPERATION::kFunctionId, ptrs, lens, &h));
     else

@@ -187,6 +187,19 @@ int pb_prox_create_ind_sum(pb_context* ctx, size_t index, size_t count, size_t d
 int pb_prox_create_ind_sum_indexed(pb_context* ctx, size_t index, size_t size, size_t count, size_t dim,
                                    const unsigned long long* h_inds, float sum, size_t count2, size_t dim2,
                                    const unsigned long long* h_inds2, float sum2, pb_prox** out);
+/* Spectral element operations: ProxElemOperation<T, ElemOperationSingularNx2<T, FUN_2D>> (prox of
+ * h(sigma_1) + h(sigma_2) / a Function2D of the singular values of an N x 2 matrix, dim = 2N,
+ * elem_operation_singular_nx2.hpp:32-150, function_2d.hpp:28-101) and ElemOperationEigen2x2 / Eigen3x3 / EigenNxN
+ * (prox of sum_i h(lambda_i) of the symmetrised matrix, dim = 4 / 9 / n^2 with n <= 8 here;
+ * elem_operation_eigen_2x2.hpp:94-146, elem_operation_eigen_3x3.hpp:302-377, elem_operation_eigen_nxn.hpp).
+ * coeffs = a, b, c, d, e, alpha, beta of c h(a x - b) + d x + (e/2) x^2, 1 or count entries each.
+ * function_2d (singular_nx2 only): 0 = sum_1d:<function_1d>, 1 = ind_l1_ball, 2 = moreau:ind_l1_ball. */
+typedef enum pb_spectral_kind {
+  PB_SPECTRAL_SINGULAR_NX2 = 0, PB_SPECTRAL_EIGEN_2X2 = 1, PB_SPECTRAL_EIGEN_3X3 = 2, PB_SPECTRAL_EIGEN_NXN = 3
+} pb_spectral_kind;
+int pb_prox_create_spectral(pb_context* ctx, int kind, size_t index, size_t count, size_t dim, int interleaved,
+                            int diagsteps, int function_1d, int function_2d, const float* const h_coeffs[7],
+                            const size_t coeff_len[7], pb_prox** out);
 /* ProxIndEpiConjQuad1D (north star: "ProxEpiConjQuadr"; mex name "ind_epi_conjquad_1d"): per (x, y) pair the
  * projection onto the epigraph of the conjugate of rho(u) = a u^2 + b u + c on [alpha, beta], a >= 0.  PARITY
  * UNPINNED: the reference only names the class (cmake/CustomSources.cmake.example:8-14, un-vendored repository

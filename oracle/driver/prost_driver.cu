@@ -25,6 +25,7 @@
 //           | simplex <idx> <count> <dim> <interleaved> <diagsteps>
 //           | indsum <idx> <count> <dim> <interleaved> <diagsteps>
 //           | halfspace <idx> <count> <dim> <interleaved> <diagsteps> <a> <b>
+//           | spectral <singular_nx2|eigen_2x2|eigen_3x3|eigen_nxn> <fun> <idx> <count> <dim> <interleaved> <diagsteps> <7 coeffs>
 //           | indsumidx <idx> <size> <n_lists: 1|2> { <dim> <inds file (u64)> <n_inds> <sum> } x n_lists
 //           | soc <idx> <count> <dim> <interleaved> <diagsteps> <alpha>
 //           | epiquad <idx> <count> <dim> <interleaved> <diagsteps> <a> <b> <c>
@@ -76,6 +77,11 @@
 #include "prost/prox/prox_moreau.hpp"
 #include "prost/prox/prox_ind_halfspace.hpp"
 #include "prost/prox/prox_ind_sum.hpp"
+#include "prost/prox/elemop/elem_operation_singular_nx2.hpp"
+#include "prost/prox/elemop/elem_operation_eigen_2x2.hpp"
+#include "prost/prox/elemop/elem_operation_eigen_3x3.hpp"
+#include "prost/prox/elemop/elem_operation_eigen_nxn.hpp"
+#include "prost/prox/elemop/function_2d.hpp"
 #include "prost/prox/prox_ind_soc.hpp"
 #include "prost/prox/prox_transform.hpp"
 #include "prost/prox/prox_permute.hpp"
@@ -162,6 +168,44 @@ static std::shared_ptr<Prox<real>> parse_prox(std::istringstream& in) {
     in >> idx >> count >> dim >> il >> ds;
     return std::shared_ptr<Prox<real>>(
         new ProxElemOperation<real, ElemOperationIndSimplex<real>>(idx, count, dim, il, ds));
+  }
+  if (kind == "spectral") {
+    std::string op, fun;
+    size_t idx, count, dim;
+    int il, ds;
+    in >> op >> fun >> idx >> count >> dim >> il >> ds;
+    std::array<std::vector<real>, 7> c;
+    for (int k = 0; k < 7; ++k) { std::string tok; in >> tok; c[k] = coeff(tok); }
+    Prox<real>* p = nullptr;
+#define PB_SPEC_EIG(OPNAME, CLASS)                                                                                       \
+    if (op == OPNAME) {                                                                                                \
+      if (fun == "zero") p = new ProxElemOperation<real, CLASS<real, Function1DZero<real>>>(idx, count, dim, il, ds, c);          \
+      else if (fun == "abs") p = new ProxElemOperation<real, CLASS<real, Function1DAbs<real>>>(idx, count, dim, il, ds, c);       \
+      else if (fun == "square") p = new ProxElemOperation<real, CLASS<real, Function1DSquare<real>>>(idx, count, dim, il, ds, c); \
+      else if (fun == "ind_leq0") p = new ProxElemOperation<real, CLASS<real, Function1DIndLeq0<real>>>(idx, count, dim, il, ds, c); \
+      else if (fun == "ind_geq0") p = new ProxElemOperation<real, CLASS<real, Function1DIndGeq0<real>>>(idx, count, dim, il, ds, c); \
+      else if (fun == "ind_box01") p = new ProxElemOperation<real, CLASS<real, Function1DIndBox01<real>>>(idx, count, dim, il, ds, c); \
+      else if (fun == "huber") p = new ProxElemOperation<real, CLASS<real, Function1DHuber<real>>>(idx, count, dim, il, ds, c);   \
+    }
+    PB_SPEC_EIG("eigen_2x2", ElemOperationEigen2x2)
+    PB_SPEC_EIG("eigen_3x3", ElemOperationEigen3x3)
+    PB_SPEC_EIG("eigen_nxn", ElemOperationEigenNxN)
+#undef PB_SPEC_EIG
+    if (op == "singular_nx2") {
+#define PB_SPEC_SV(FUNNAME, ...) \
+      if (fun == FUNNAME) p = new ProxElemOperation<real, ElemOperationSingularNx2<real, __VA_ARGS__>>(idx, count, dim, il, ds, c);
+      PB_SPEC_SV("sum_1d:zero", Function2DSum1D<real, Function1DZero<real>>)
+      PB_SPEC_SV("sum_1d:abs", Function2DSum1D<real, Function1DAbs<real>>)
+      PB_SPEC_SV("sum_1d:square", Function2DSum1D<real, Function1DSquare<real>>)
+      PB_SPEC_SV("sum_1d:ind_leq0", Function2DSum1D<real, Function1DIndLeq0<real>>)
+      PB_SPEC_SV("sum_1d:ind_box01", Function2DSum1D<real, Function1DIndBox01<real>>)
+      PB_SPEC_SV("sum_1d:huber", Function2DSum1D<real, Function1DHuber<real>>)
+      PB_SPEC_SV("ind_l1_ball", Function2DIndL1Ball<real>)
+      PB_SPEC_SV("moreau:ind_l1_ball", Function2DMoreau<real, Function2DIndL1Ball<real>>)
+#undef PB_SPEC_SV
+    }
+    if (!p) { std::cerr << "unknown spectral operation " << op << " " << fun << std::endl; std::exit(2); }
+    return std::shared_ptr<Prox<real>>(p);
   }
   if (kind == "indsumidx") {
     size_t idx, size;

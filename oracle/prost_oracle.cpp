@@ -460,6 +460,179 @@ struct ProxElem7 : ProxSeparable {  // 1D and Norm2 families with 7 coefficients
   }
 };
 
+// ---- spectral element operations ---------------------------------------------------------
+// singular_nx2 and eigen_2x2 follow the reference statement by statement (elem_operation_singular_nx2.hpp:41-150,
+// function_2d.hpp:28-101; elem_operation_eigen_2x2.hpp:30-146 incl. its dlaev2-style rotation).  eigen_3x3 / eigen_nxn:
+// the reference diagonalises with Kopp's Cardano + cross-product routine (elem_operation_eigen_3x3.hpp:31-300) resp.
+// EISPACK tred2 / tql2 (elem_operation_eigen_nxn.hpp); a spectral function V f(Lambda) V^T does not depend on the
+// eigen-solver, so this restatement uses cyclic Jacobi rotations in double and is pinned on numpy's eigh (the
+// closed form of the reference's own test_prox_sum_eigen_3x3.m / _nxn.m) and on the live reference.
+static void oracle_ind_l1_ball(float y1, float y2, float& x1, float& x2, float alpha) {      // function_2d.hpp:43-82
+  float v1 = std::abs(y1), v2 = std::abs(y2);
+  if (v1 + v2 <= alpha) { x1 = y1; x2 = y2; return; }
+  float mu1, mu2;
+  if (v1 < v2) { mu1 = v2; mu2 = v1; } else { mu1 = v1; mu2 = v2; }
+  float l = 0.5 * (mu2 - mu1 + alpha);
+  char rho = 2;
+  if (l <= 0.) rho = 1;
+  float theta = (1. / rho) * (mu1 + (rho == 2 ? mu2 : 0.) - alpha);
+  mu1 = std::max(v1 - theta, 0.f);
+  mu2 = std::max(v2 - theta, 0.f);
+  x1 = ((0.f < y1) - (y1 < 0.f)) * mu1;
+  x2 = ((0.f < y2) - (y2 < 0.f)) * mu2;
+}
+
+static void jacobi_eig(std::vector<double>& A, std::vector<double>& V, int n) {     // A symmetric n x n, row-major
+  V.assign((size_t)n * n, 0.0);
+  for (int i = 0; i < n; ++i) V[i * n + i] = 1.0;
+  for (int sweep = 0; sweep < 32; ++sweep) {
+    double off = 0, diag = 0;
+    for (int i = 0; i < n; ++i) { diag += A[i * n + i] * A[i * n + i]; for (int j = i + 1; j < n; ++j) off += A[i * n + j] * A[i * n + j]; }
+    if (off <= 1e-32 * diag || off == 0) break;
+    for (int p = 0; p < n - 1; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        const double apq = A[p * n + q];
+        if (apq == 0) continue;
+        const double theta = (A[q * n + q] - A[p * n + p]) / (2 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::abs(theta) + std::sqrt(theta * theta + 1));
+        const double c = 1 / std::sqrt(t * t + 1), sn = t * c;
+        for (int r = 0; r < n; ++r) {            // A <- A J
+          const double arp = A[r * n + p], arq = A[r * n + q];
+          A[r * n + p] = c * arp - sn * arq;
+          A[r * n + q] = sn * arp + c * arq;
+        }
+        for (int r = 0; r < n; ++r) {            // A <- J^T A
+          const double apr = A[p * n + r], aqr = A[q * n + r];
+          A[p * n + r] = c * apr - sn * aqr;
+          A[q * n + r] = sn * apr + c * aqr;
+        }
+        for (int r = 0; r < n; ++r) {
+          const double vp = V[r * n + p], vq = V[r * n + q];
+          V[r * n + p] = c * vp - sn * vq;
+          V[r * n + q] = sn * vp + c * vq;
+        }
+      }
+  }
+}
+
+struct ProxSpectral : ProxSeparable {
+  int kind, fn, fn2d;      // kind: 0 singular_nx2, 1 eigen_2x2, 2 eigen_3x3, 3 eigen_nxn
+  vec coeffs[7];
+  ProxSpectral(int k, size_t i, size_t c, size_t d, bool il, bool ds, int f, int f2, const float* const* co, const size_t* len)
+      : ProxSeparable(i, c, d, il, ds), kind(k), fn(f), fn2d(f2) {
+    for (int j = 0; j < 7; ++j) coeffs[j].assign(co[j], co[j] + len[j]);
+  }
+  // one eigenvalue through the scaled Function1D (eigen_2x2.hpp:112-126)
+  double eig_prox(double lam, double tau, const float* c) const {
+    if (c[0] == 0 || c[2] == 0) return (lam - tau * c[3]) / (1 + tau * c[4]);
+    const double p = ((c[0] * (lam - c[3] * tau)) / (1. + tau * c[4])) - c[1];
+    const double step = (c[2] * c[0] * c[0] * tau) / (1. + tau * c[4]);
+    return (fn_eval(fn, static_cast<float>(p), static_cast<float>(step), c[5], c[6]) + c[1]) / c[0];
+  }
+  void eval_local(float* res, const float* arg, const float* td, float tau_scal, bool invert) override {
+#pragma omp parallel for schedule(static)
+    for (size_t tx = 0; tx < count; ++tx) {
+      float c[7];
+      for (int k = 0; k < 7; ++k) c[k] = coeffs[k].size() > 1 ? coeffs[k][tx] : coeffs[k][0];
+      const float td0 = td[at(tx, 0)];
+      const double tau = invert ? (1. / (tau_scal * td0)) : (tau_scal * td0);
+      if (kind == 0) {                                           // elem_operation_singular_nx2.hpp:41-150
+        const size_t n = dim / 2;
+        double d11 = 0., d12 = 0., d22 = 0.;
+        for (size_t i = 0; i < n; i++) {
+          const float a1 = arg[at(tx, i)], a2 = arg[at(tx, n + i)];
+          d11 += a1 * a1; d12 += a1 * a2; d22 += a2 * a2;
+        }
+        const double trace = d11 + d22, det = d11 * d22 - d12 * d12;
+        const double d = std::sqrt(std::max(0., 0.25 * trace * trace - det));
+        const double lmax = std::max(0., 0.5 * trace + d), lmin = std::max(0., 0.5 * trace - d);
+        const double smax = std::sqrt(lmax), smin = std::sqrt(lmin);
+        double s1, s2;
+        if (c[0] == 0 || c[2] == 0) {
+          s1 = (smax - tau * c[3]) / (1. + tau * c[4]);
+          s2 = (smin - tau * c[3]) / (1. + tau * c[4]);
+        } else {
+          const float y1 = ((c[0] * (smax - c[3] * tau)) / (1. + tau * c[4])) - c[1];
+          const float y2 = ((c[0] * (smin - c[3] * tau)) / (1. + tau * c[4])) - c[1];
+          const float step = (c[2] * c[0] * c[0] * tau) / (1. + tau * c[4]);
+          float x1, x2;
+          if (fn2d == 0) { x1 = fn_eval(fn, y1, step, c[5], c[6]); x2 = fn_eval(fn, y2, step, c[5], c[6]); }
+          else if (fn2d == 1) oracle_ind_l1_ball(y1, y2, x1, x2, c[5]);
+          else {                                                 // Function2DMoreau :85-101
+            float r1, r2;
+            oracle_ind_l1_ball(y1 / step, y2 / step, r1, r2, c[5]);
+            x1 = y1 - step * r1;
+            x2 = y2 - step * r2;
+          }
+          s1 = (x1 + c[1]) / c[0];
+          s2 = (x2 + c[1]) / c[0];
+        }
+        if (smax > 0) {
+          double v11, v12, v21, v22;                             // :97-123
+          if (d12 == 0.0) {
+            if (d11 >= d22) { v11 = 1; v21 = 0; v12 = 0; v22 = 1; } else { v11 = 0; v21 = 1; v12 = 1; v22 = 0; }
+          } else {
+            v11 = lmax - d22; v21 = d12;
+            const double l1 = std::hypot(v11, v21);
+            v11 /= l1; v21 /= l1;
+            v12 = lmin - d22; v22 = d12;
+            const double l2 = std::hypot(v12, v22);
+            v12 /= l2; v22 /= l2;
+          }
+          s1 /= smax;
+          s2 = (smin > 0.0) ? (s2 / smin) : 0.0;
+          const double t11 = s1 * v11 * v11 + s2 * v12 * v12, t12 = s1 * v11 * v21 + s2 * v12 * v22;
+          const double t21 = s1 * v21 * v11 + s2 * v22 * v12, t22 = s1 * v21 * v21 + s2 * v22 * v22;
+          for (size_t i = 0; i < n; i++) {
+            const float a1 = arg[at(tx, i)], a2 = arg[at(tx, n + i)];
+            res[at(tx, i)] = a1 * t11 + a2 * t21;
+            res[at(tx, n + i)] = a1 * t12 + a2 * t22;
+          }
+        } else {
+          for (size_t i = 0; i < 2 * n; i++) res[at(tx, i)] = 0;
+          res[at(tx, 0)] = s1;
+          res[at(tx, n + 1)] = s2;
+        }
+      } else if (kind == 1) {                                    // elem_operation_eigen_2x2.hpp:30-146
+        const double A = arg[at(tx, 0)], B = (arg[at(tx, 1)] + arg[at(tx, 2)]) / 2, C = arg[at(tx, 3)];
+        const double sm = A + C, df = A - C, rt = std::sqrt(df * df + 4.0 * B * B);
+        double rt1, rt2, cs, sn, t;
+        if (sm > 0.0) { rt1 = 0.5 * (sm + rt); t = 1.0 / rt1; rt2 = (A * t) * C - (B * t) * B; }
+        else if (sm < 0.0) { rt2 = 0.5 * (sm - rt); t = 1.0 / rt2; rt1 = (A * t) * C - (B * t) * B; }
+        else { rt1 = 0.5 * rt; rt2 = -0.5 * rt; }
+        cs = df > 0.0 ? df + rt : df - rt;
+        if (std::abs(cs) > 2.0 * std::abs(B)) { t = -2.0 * B / cs; sn = 1.0 / std::sqrt(1.0 + t * t); cs = t * sn; }
+        else if (std::abs(B) == 0.0) { cs = 1.0; sn = 0.0; }
+        else { t = -0.5 * cs / B; cs = 1.0 / std::sqrt(1.0 + t * t); sn = t * cs; }
+        if (df > 0.0) { t = cs; cs = -sn; sn = t; }
+        rt1 = eig_prox(rt1, tau, c);
+        rt2 = eig_prox(rt2, tau, c);
+        const double t11 = rt1 * cs * cs + rt2 * sn * sn, t12 = rt1 * cs * sn - sn * rt2 * cs, t22 = rt1 * sn * sn + rt2 * cs * cs;
+        res[at(tx, 0)] = t11; res[at(tx, 1)] = t12; res[at(tx, 2)] = t12; res[at(tx, 3)] = t22;
+      } else {                                                   // eigen_3x3 / eigen_nxn (see the note above)
+        int n = 1;
+        while ((size_t)n * n < dim) ++n;
+        std::vector<double> A((size_t)n * n), V;
+        for (int i = 0; i < n; ++i)
+          for (int j = i; j < n; ++j) {
+            const float u = arg[at(tx, i * n + j)], l = arg[at(tx, j * n + i)];
+            A[i * n + j] = A[j * n + i] = i == j ? static_cast<double>(u) : static_cast<double>(u + l) / 2.;
+          }
+        jacobi_eig(A, V, n);
+        std::vector<double> f(n);
+        for (int k = 0; k < n; ++k) f[k] = eig_prox(A[k * n + k], tau, c);
+        for (int i = 0; i < n; ++i)
+          for (int j = i; j < n; ++j) {
+            double t = 0;
+            for (int k = 0; k < n; ++k) t += V[i * n + k] * V[j * n + k] * f[k];
+            res[at(tx, i * n + j)] = t;
+            res[at(tx, j * n + i)] = t;
+          }
+      }
+    }
+  }
+};
+
 struct ProxSimplex : ProxSeparable {   // elem_operation_ind_simplex.hpp:47-115
   using ProxSeparable::ProxSeparable;
   void eval_local(float* res, const float* arg, const float*, float, bool) override {
@@ -1208,6 +1381,10 @@ int orc_prox_ind_sum_indexed(void* p, size_t idx, size_t size, size_t count, siz
 int orc_prox_ind_epi_conjquad_1d(void* p, size_t idx, size_t count, int il, int ds, const float* const* coeffs,
                                  const size_t* len) {
   return push(PP, std::make_shared<ProxIndEpiConjQuad1D>(idx, count, il != 0, ds != 0, coeffs, len));
+}
+int orc_prox_spectral(void* p, int kind, size_t idx, size_t count, size_t dim, int il, int ds, int fn, int fn2d,
+                      const float* const* coeffs, const size_t* len) {
+  return push(PP, std::make_shared<ProxSpectral>(kind, idx, count, dim, il != 0, ds != 0, fn, fn2d, coeffs, len));
 }
 int orc_prox_ind_soc(void* p, size_t idx, size_t count, size_t dim, int il, int ds) {
   return push(PP, std::make_shared<ProxIndSOC>(idx, count, dim, il != 0, ds != 0));

@@ -127,6 +127,8 @@ SIGNATURES = {
     "pb_prox_create_ind_sum_indexed": (C.c_int, [handle, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t,
                                                  C.POINTER(C.c_ulonglong), C.c_float, C.c_size_t, C.c_size_t,
                                                  C.POINTER(C.c_ulonglong), C.c_float, handle_p]),
+    "pb_prox_create_spectral": (C.c_int, [handle, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                          C.c_int, C.POINTER(c_float_p), c_size_p, handle_p]),
     "pb_prox_create_ind_epi_conjquad_1d": (C.c_int, [handle, C.c_size_t, C.c_size_t, C.c_int, C.c_int,
                                                      C.POINTER(c_float_p), c_size_p, handle_p]),
     "pb_prox_create_ind_halfspace": (C.c_int, [handle, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int,

@@ -391,6 +391,21 @@ class ProxIndSum(Prox):
             C.byref(self._h)))
 
 
+class ProxElemOperationSpectral(Prox):
+    """ProxElemOperation<T, ElemOperationSingularNx2 / Eigen2x2 / Eigen3x3 / EigenNxN> (elem_operation_singular_nx2.hpp,
+    elem_operation_eigen_*.hpp).  ``kind``: "singular_nx2", "eigen_2x2", "eigen_3x3", "eigen_nxn"; ``function`` is
+    a Function1D name, or for singular_nx2 also "ind_l1_ball" / "moreau:ind_l1_ball" (function_2d.hpp)."""
+    KINDS = {"singular_nx2": 0, "eigen_2x2": 1, "eigen_3x3": 2, "eigen_nxn": 3}
+
+    def __init__(self, ctx, kind, function, index, count, dim, interleaved, diagsteps, coeffs):
+        super().__init__(ctx)
+        keep, ptrs, lens = _coeff_arrays(coeffs)
+        fn2d = {"ind_l1_ball": 1, "moreau:ind_l1_ball": 2}.get(function, 0)
+        fn1d = 0 if fn2d else function_id(function[len("sum_1d:"):] if function.startswith("sum_1d:") else function)
+        check(lib.pb_prox_create_spectral(ctx._h, self.KINDS[kind], index, count, dim, int(interleaved), int(diagsteps),
+                                          fn1d, fn2d, ptrs, lens, C.byref(self._h)))
+
+
 class ProxIndEpiConjQuad1D(Prox):
     """ProxIndEpiConjQuad1D (the north star's "ProxEpiConjQuadr"; source external to the reference tree, parity
     unpinned): per (x, y) pair the projection onto the epigraph of the conjugate of a u^2 + b u + c on

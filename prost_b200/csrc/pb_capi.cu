@@ -338,6 +338,13 @@ int pb_prox_create_ind_sum_indexed(pb_context* c, size_t index, size_t size, siz
                                    const unsigned long long* inds2, float sum2, pb_prox** out) {
   PB_MAKE_PROX(pb::make_prox_ind_sum_indexed(&c->ctx, index, size, count, dim, inds, sum, count2, dim2, inds2, sum2));
 }
+int pb_prox_create_spectral(pb_context* c, int kind, size_t index, size_t count, size_t dim, int interleaved,
+                            int diagsteps, int function_1d, int function_2d, const float* const coeffs[7],
+                            const size_t coeff_len[7], pb_prox** out) {
+  PB_MAKE_PROX((require(coeffs && coeff_len, "NULL coefficients"),
+                pb::make_prox_spectral(&c->ctx, kind, index, count, dim, interleaved != 0, diagsteps != 0, function_1d,
+                                       function_2d, coeffs, coeff_len)));
+}
 int pb_prox_create_ind_epi_conjquad_1d(pb_context* c, size_t index, size_t count, int interleaved, int diagsteps,
                                        const float* const coeffs[5], const size_t coeff_len[5], pb_prox** out) {
   PB_MAKE_PROX((require(coeffs && coeff_len, "NULL coefficients"),

@@ -31,6 +31,7 @@ enum ProxKind : int {
   kProxIndSOC = 10,
   kProxIndSumIndexed = 11,
   kProxIndEpiConjQuad1D = 12,
+  kProxSpectral = 13,
 };
 
 // per-element vector or scalar (ElemOpCoefficients: prox_elem_operation.hpp:104-109)
@@ -374,6 +375,11 @@ std::shared_ptr<Prox> make_prox_ind_sum(Context* ctx, size_t index, size_t count
 std::shared_ptr<Prox> make_prox_ind_sum_indexed(Context* ctx, size_t index, size_t size, size_t count, size_t dim,
                                                 const unsigned long long* inds, float total, size_t count2,
                                                 size_t dim2, const unsigned long long* inds2, float total2);
+// spectral element operations (pb_spectral.cu): singular values of N x 2 matrices, eigenvalues of symmetric
+// 2 x 2 / 3 x 3 / n x n matrices (elem_operation_singular_nx2.hpp, elem_operation_eigen_{2x2,3x3,nxn}.hpp)
+std::shared_ptr<Prox> make_prox_spectral(Context* ctx, int kind, size_t index, size_t count, size_t dim,
+                                         bool interleaved, bool diagsteps, int function_1d, int function_2d,
+                                         const float* const coeffs[7], const size_t coeff_len[7]);
 // ProxIndEpiConjQuad1D (external to the reference tree, cmake/CustomSources.cmake.example:8-14; parity unpinned):
 // projection of (x, y) pairs onto the epigraph of the conjugate of a u^2 + b u + c restricted to [alpha, beta]
 std::shared_ptr<Prox> make_prox_ind_epi_conjquad_1d(Context* ctx, size_t index, size_t count, bool interleaved,

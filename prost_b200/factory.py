@@ -8,6 +8,8 @@ reference's mex registry names and argument order (matlab/+prost/private/factory
 ``data`` per name (same order as the cell arrays the MATLAB front end sends):
   elem_operation:1d:<fun>, elem_operation:norm2:<fun> : [count, dim, interleaved, [a,b,c,d,e,alpha,beta]]
   elem_operation:ind_simplex, elem_operation:ind_sum   : [count, dim, interleaved]
+  elem_operation:singular_nx2:{sum_1d:<fun>, ind_l1_ball, moreau:ind_l1_ball},
+  elem_operation:eigen_2x2|eigen_3x3|eigen_nxn:<fun>   : [count, dim, interleaved, [a,b,c,d,e,alpha,beta]]
   ind_epi_quad                                         : [count, dim, interleaved, [a, b, c]]
   ind_sum                                              : [dim, inds, sum(, dim2, inds2, sum2)]
   ind_epi_conjquad_1d                                  : [count, interleaved, [a, b, c, alpha, beta]]
@@ -31,6 +33,12 @@ def create_prox(ctx, desc):
     if name.startswith("elem_operation:norm2:"):
         count, dim, interleaved, coeffs = data
         return api.ProxElemOperationNorm2(ctx, name.split(":")[2], idx, count, dim, interleaved, diagsteps, coeffs)
+    for kind in ("singular_nx2", "eigen_2x2", "eigen_3x3", "eigen_nxn"):       # factory.cpp:49-102
+        prefix = f"elem_operation:{kind}:"
+        if name.startswith(prefix):
+            count, dim, interleaved, coeffs = data
+            return api.ProxElemOperationSpectral(ctx, kind, name[len(prefix):], idx, count, dim, interleaved, diagsteps,
+                                                 coeffs)
     if name == "elem_operation:ind_simplex":
         count, dim, interleaved = data[:3]
         return api.ProxElemOperationIndSimplex(ctx, idx, count, dim, interleaved, diagsteps)

@@ -228,6 +228,32 @@ def prox_ind_sum_indexed_cases(small=False):
     return cases
 
 
+def prox_spectral_cases(small=False):
+    """Spectral element operations: singular values of N x 2 matrices and eigenvalues of
+    symmetric 2 x 2 / 3 x 3 / n x n matrices (elem_operation_singular_nx2.hpp, elem_operation_eigen_*.hpp); the
+    reference's own tests project onto the PSD cone with 'ind_leq0' on -x (test_prox_sum_eigen_3x3.m)."""
+    r = rng(71)
+    cases = {}
+    n = 600 if not small else 23
+    psd = coeffs(a=-1, b=0, c=1)                  # ind_leq0(-x): projection onto the PSD cone
+    for kind, dim in (("eigen_2x2", 4), ("eigen_3x3", 9), ("eigen_nxn", 25), ("eigen_nxn", 16)):
+        for il in (True, False):
+            cases[f"{kind}_d{dim}_psd_il{int(il)}"] = ((f"elem_operation:{kind}:ind_leq0", 0, n * dim, False,
+                                                       [n, dim, il, psd]), n * dim)
+        cases[f"{kind}_d{dim}_abs"] = ((f"elem_operation:{kind}:abs", 0, n * dim, False,
+                                        [n, dim, True, coeffs(a=1, b=0.3, c=0.8)]), n * dim)
+        cases[f"{kind}_d{dim}_square_vec"] = ((f"elem_operation:{kind}:square", 7, n * dim, True,
+                                               [n, dim, True, coeffs(a=1, b=r.random(n), c=r.uniform(0.5, 2, n), d=0.1, e=0.2)]),
+                                              n * dim + 11)
+    for N in (2, 3, 8):
+        dim = 2 * N
+        for fun in ("sum_1d:abs", "sum_1d:square", "sum_1d:ind_box01", "ind_l1_ball", "moreau:ind_l1_ball"):
+            co = coeffs(a=1, b=0, c=1.3, alpha=0.7)
+            cases[f"singular_{N}x2_{fun.replace(':', '_')}"] = ((f"elem_operation:singular_nx2:{fun}", 0, n * dim, False,
+                                                                 [n, dim, N != 3, co]), n * dim)
+    return cases
+
+
 def prox_epi_conjquad_cases(small=False):
     """ind_epi_conjquad_1d (the north star's ProxEpiConjQuadr; parity unpinned, see prost_b200/csrc/pb_prox.cu):
     (x, y) pairs against the conjugate of a u^2 + b u + c on [alpha, beta]: per-pair and scalar coefficients, planar
@@ -273,6 +299,7 @@ def all_prox_cases(small=False):
     out.update({k: (v[0], v[1]) for k, v in prox_transform_cases(small).items()})
     out.update(prox_ind_sum_cases(small))
     out.update(prox_ind_sum_indexed_cases(small))
+    out.update(prox_spectral_cases(small))
     out.update(prox_projection_cases(small))
     return out
 

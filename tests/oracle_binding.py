@@ -44,6 +44,8 @@ lib.orc_prox_simplex.argtypes = [C.c_void_p, sz, sz, sz, C.c_int, C.c_int]
 lib.orc_prox_ind_sum.argtypes = [C.c_void_p, sz, sz, sz, C.c_int, C.c_int]
 lib.orc_prox_ind_sum_indexed.argtypes = [C.c_void_p, sz, sz, sz, sz, C.POINTER(C.c_ulonglong), C.c_float, sz, sz,
                                          C.POINTER(C.c_ulonglong), C.c_float]
+lib.orc_prox_spectral.argtypes = [C.c_void_p, C.c_int, sz, sz, sz, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(fp),
+                                  C.POINTER(sz)]
 lib.orc_prox_ind_epi_conjquad_1d.argtypes = [C.c_void_p, sz, sz, C.c_int, C.c_int, C.POINTER(fp), C.POINTER(sz)]
 lib.orc_prox_ind_halfspace.argtypes = [C.c_void_p, sz, sz, sz, C.c_int, C.c_int, fp, sz, fp, sz]
 lib.orc_prox_ind_soc.argtypes = [C.c_void_p, sz, sz, sz, C.c_int, C.c_int]
@@ -188,6 +190,18 @@ class OracleProblem:
                                                 float(data[2]), (b.size // d2) if two else 0, d2,
                                                 b.ctypes.data_as(u64p) if two else None,
                                                 float(data[5]) if two else 0.0)
+        for kind_id, kind in enumerate(("singular_nx2", "eigen_2x2", "eigen_3x3", "eigen_nxn")):
+            prefix = f"elem_operation:{kind}:"
+            if name.startswith(prefix):
+                count, dim, il, coeffs = data
+                fun = name[len(prefix):]
+                fn2d = {"ind_l1_ball": 1, "moreau:ind_l1_ball": 2}.get(fun, 0)
+                fn1d = 0 if fn2d else FUNCTIONS_1D.index(fun[len("sum_1d:"):] if fun.startswith("sum_1d:") else fun)
+                arrs = [_f32(c) for c in coeffs]
+                ptrs = (fp * 7)(*[_p(a) for a in arrs])
+                lens = (sz * 7)(*[a.size for a in arrs])
+                return lib.orc_prox_spectral(self.h, kind_id, idx, count, dim, int(il), int(diagsteps), fn1d, fn2d,
+                                             ptrs, lens)
         if name == "ind_epi_conjquad_1d":
             count, il, coeffs = data
             arrs = [_f32(np.atleast_1d(c)) for c in coeffs]

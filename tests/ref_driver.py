@@ -85,6 +85,12 @@ class _Writer:
             kind = "norm2" if ":norm2:" in name else "elem1d"
             cs = " ".join(self.coeff(c) for c in coeffs)
             return f"{kind} {name.split(':')[2]} {idx} {count} {dim} {int(il)} {int(ds)} {cs}"
+        for kind in ("singular_nx2", "eigen_2x2", "eigen_3x3", "eigen_nxn"):
+            prefix = f"elem_operation:{kind}:"
+            if name.startswith(prefix):
+                count, dim, il, coeffs = data
+                cs = " ".join(self.coeff(c) for c in coeffs)
+                return f"spectral {kind} {name[len(prefix):]} {idx} {count} {dim} {int(il)} {int(ds)} {cs}"
         if name == "elem_operation:ind_simplex":
             count, dim, il = data[:3]
             return f"simplex {idx} {count} {dim} {int(il)} {int(ds)}"

@@ -320,3 +320,77 @@ def test_prox_ind_epi_conjquad_1d_is_the_projection_onto_the_conjugate_epigraph(
                                                                 at(3, i), at(4, i))
             scale = max(1.0, abs(wx), abs(wy))
             assert abs(rx[i] - wx) <= 2e-4 * scale and abs(ry[i] - wy) <= 2e-4 * scale, (name, i, (rx[i], ry[i]), (wx, wy))
+
+
+def _spectral_closed_form(desc, arg):
+    """numpy restatement: T = V f(Lambda) V^T through eigh (eigen_*), U f(S) V^T through svd (singular_nx2), for the
+    functions whose scalar prox has an obvious closed form (the reference's tests do the same with MATLAB's eig)."""
+    name, idx, size, ds, (count, dim, il, co) = desc
+    kind, fun = name.split(":")[1], ":".join(name.split(":")[2:])
+    A = arg[idx:idx + size].astype(np.float64)
+    G = A.reshape(count, dim) if il else A.reshape(dim, count).T
+    at = lambda k, i: float(np.atleast_1d(co[k])[i if np.atleast_1d(co[k]).size > 1 else 0])
+    out = np.empty_like(G)
+    for i in range(count):
+        a, b, c, d, e, alpha = (at(k, i) for k in range(6))
+        tau = 0.7 * 1.0
+
+        def scalar_prox(lam):
+            # prox of c h(a x - b) + d x + (e/2) x^2 with step tau (elem_operation_1d.hpp:36-59)
+            p = a * (lam - d * tau) / (1 + tau * e) - b
+            step = c * a * a * tau / (1 + tau * e)
+            h = fun.split(":")[-1]
+            if h == "abs":
+                v = np.sign(p) * np.maximum(np.abs(p) - step, 0)
+            elif h == "square":
+                v = p / (1 + step)
+            elif h == "ind_leq0":
+                v = np.minimum(p, 0)
+            elif h == "ind_box01":
+                v = np.clip(p, 0, 1)
+            else:
+                raise KeyError(h)
+            return (v + b) / a
+
+        if kind == "singular_nx2":
+            n = dim // 2
+            M = np.stack([G[i, :n], G[i, n:]], axis=1)              # n x 2
+            U, S, Vt = np.linalg.svd(M, full_matrices=False)
+            if fun.startswith("sum_1d:"):
+                Sn = scalar_prox(S)
+            else:
+                # projection of the singular values onto the l1 ball of radius alpha (or its Moreau complement)
+                y = a * (S - d * tau) / (1 + tau * e) - b
+                step = c * a * a * tau / (1 + tau * e)
+
+                def l1proj(v, rad):
+                    if np.abs(v).sum() <= rad:
+                        return v.copy()
+                    u = np.sort(np.abs(v))[::-1]
+                    css = np.cumsum(u)
+                    k = np.nonzero(u * np.arange(1, len(u) + 1) > (css - rad))[0][-1]
+                    th = (css[k] - rad) / (k + 1.0)
+                    return np.sign(v) * np.maximum(np.abs(v) - th, 0)
+                x = l1proj(y, alpha) if fun == "ind_l1_ball" else y - step * l1proj(y / step, alpha)
+                Sn = (x + b) / a
+            R = (U * Sn) @ Vt
+            out[i] = np.concatenate([R[:, 0], R[:, 1]])
+        else:
+            n = int(round(np.sqrt(dim)))
+            M = G[i].reshape(n, n)
+            M = (M + M.T) / 2
+            w, V = np.linalg.eigh(M)
+            out[i] = ((V * scalar_prox(w)) @ V.T).reshape(-1)
+    return (out.reshape(-1) if il else out.T.reshape(-1))
+
+
+def test_spectral_proxes_match_numpy_closed_forms():
+    """Oracle pin for the spectral element operations: V f(Lambda) V^T with numpy's eigh / svd (the closed form of
+    test_prox_sum_eigen_2x2.m / _3x3.m / _nxn.m, which project onto the PSD cone and compare with eig at 1e-4)."""
+    r = np.random.default_rng(23)
+    for name, (desc, n) in cases.prox_spectral_cases(small=True).items():
+        arg = (3 * r.standard_normal(n)).astype(np.float32)
+        res = oracle_prox_eval(desc, arg, np.ones(n, np.float32), 0.7)
+        lo, hi = desc[1], desc[1] + desc[2]
+        want = _spectral_closed_form(desc, arg)
+        assert np.abs(res[lo:hi] - want).max() <= 1e-4 * max(1.0, np.abs(want).max()), name

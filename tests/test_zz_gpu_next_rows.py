@@ -134,6 +134,30 @@ def test_ind_sum_indexed_errors(ctx):
     assert "outside the prox range" in str(e.value)
 
 
+# ---- spectral element operations ---------------------------------------------------------
+SPEC_CASES = cases.prox_spectral_cases()
+
+
+@pytest.mark.parametrize("name", sorted(SPEC_CASES))
+def test_spectral_prox_matches_oracle_and_reference(ctx, name):
+    """singular_nx2 / eigen_2x2 / eigen_3x3 / eigen_nxn: the CUDA kernels (Sylvester's formula, Jacobi rotations)
+    against the oracle and the live reference (dlaev2-style 2 x 2, Kopp's 3 x 3, EISPACK n x n): same spectral
+    function, different eigen-solvers -> agreement to rounding, not bit for bit."""
+    desc, n = SPEC_CASES[name]
+    arg, tau_diag, tau = _inputs(name, n)
+    arg = (1.5 * arg).astype(np.float32)
+    for invert in (False, True):
+        got = pb.create_prox(ctx, desc).Eval(arg, tau_diag, tau, invert)
+        want = oracle_prox_eval(desc, arg, tau_diag, tau, invert)
+        lo, hi = desc[1], desc[1] + desc[2]
+        scale = max(1.0, float(np.abs(want[lo:hi]).max()))
+        assert np.abs(got[lo:hi] - want[lo:hi]).max() <= 2e-5 * scale, (name, invert)
+    if ref_driver.available():
+        got = pb.create_prox(ctx, desc).Eval(arg, tau_diag, tau)
+        ref = ref_driver.run_prox(desc, arg, tau_diag, tau)
+        assert np.abs(got[lo:hi] - ref[lo:hi]).max() <= 2e-5 * scale, name
+
+
 # ---- ind_epi_conjquad_1d: the north star's ProxEpiConjQuadr (source external to the reference tree) -------------
 CONJ_CASES = cases.prox_epi_conjquad_cases()
 
