@@ -442,41 +442,133 @@ class BlockDense : public Block {
 };
 
 // ---- Kronecker products with an identity (block_dense_kron_id.cu, block_id_kron_dense.cu) --------------
-// K is a small n_out x n_in matrix read through strides (so, si) so that one kernel serves K and K^T.
+// K is a small n_out x n_in matrix read through strides (so, si) so that one kernel serves K and K^T.  All four
+// products stream vectors of d * n floats with d in the millions: they are HBM bound as long as every vector element
+// crosses HBM once, so the kernels are organised around that (round 1's one-thread-per-output forms re-read the
+// input once per output row or per 8 rows and ran at 3 - 16 % of the HBM peak, profiles/r02_operators.md):
 //
-// kron(K, I_d):  res[o*d + k] += sum_i K(o, i) rhs[i*d + k].  This is the GEMM  Res (n_out x d) += K X (n_in x d)
-// with d in the millions and n_in, n_out in the tens: every thread owns one column k (coalesced across threads)
-// and kRowTile output rows in registers, K is read as warp-wide broadcasts, X once per row tile.  Same
-// summation order as the reference (i ascending, sum first, then += into the result).
-constexpr int kKronRowTile = 8;
+// kron(K, I_d):  res[o*d + k] (+)= sum_i K(o, i) rhs[i*d + k]  -- the GEMM  Res (n_out x d) = K X (n_in x d).
+//   A thread owns VEC consecutive columns k (128-bit loads / stores) and kKronRowTile output rows in registers; the
+//   CTA stages its rows of K in shared memory once (read back as 128-bit broadcasts), X streams through once per
+//   row tile (once in total for n_out <= 16).  Same summation order as the reference (i ascending, then += / =).
+constexpr int kKronRowTile = 16;
+constexpr int kKronSmemFloats = 8192;       // staged factor entries per CTA (32 KB)
 
+template <int VEC, bool SET>
 __global__ void __launch_bounds__(kBlock) kron_k_id_kernel(float* __restrict__ res, const float* __restrict__ rhs,
                                                            const float* __restrict__ K, uint32_t n_out, uint32_t n_in,
-                                                           size_t d, uint32_t so, uint32_t si,
+                                                           size_t d, uint32_t so, uint32_t si, bool k_in_smem,
                                                            const int* __restrict__ skip) {
   if (skip && *skip) return;
-  const size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  extern __shared__ __align__(16) float kron_smem[];          // Ks[i][r], r = row of the tile (fastest)
   const uint32_t o0 = blockIdx.y * kKronRowTile;
-  if (k >= d) return;
-  float acc[kKronRowTile];
-#pragma unroll
-  for (int r = 0; r < kKronRowTile; ++r) acc[r] = 0.f;
-  for (uint32_t i = 0; i < n_in; ++i) {
-    const float x = rhs[(size_t)i * d + k];
-#pragma unroll
-    for (int r = 0; r < kKronRowTile; ++r)
-      if (o0 + r < n_out) acc[r] += __ldg(K + (size_t)(o0 + r) * so + (size_t)i * si) * x;
+  if (k_in_smem) {
+    for (uint32_t e = threadIdx.x; e < n_in * kKronRowTile; e += blockDim.x) {
+      const uint32_t i = e / kKronRowTile, r = e % kKronRowTile;
+      kron_smem[e] = (o0 + r < n_out) ? K[(size_t)(o0 + r) * so + (size_t)i * si] : 0.f;
+    }
+    __syncthreads();
   }
+  const size_t k = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * VEC;
+  if (k >= d) return;
+  float acc[kKronRowTile][VEC];
 #pragma unroll
   for (int r = 0; r < kKronRowTile; ++r)
-    if (o0 + r < n_out) res[(size_t)(o0 + r) * d + k] += acc[r];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[r][v] = 0.f;
+  for (uint32_t i = 0; i < n_in; ++i) {
+    float x[VEC];
+    if (VEC == 4) {
+      const float4 t = *reinterpret_cast<const float4*>(rhs + (size_t)i * d + k);
+      x[0] = t.x; x[1 % VEC] = t.y; x[2 % VEC] = t.z; x[3 % VEC] = t.w;
+    } else {
+      x[0] = rhs[(size_t)i * d + k];
+    }
+    float kr[kKronRowTile];
+    if (k_in_smem) {
+#pragma unroll
+      for (int r = 0; r < kKronRowTile; r += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(kron_smem + i * kKronRowTile + r);
+        kr[r] = t.x; kr[r + 1] = t.y; kr[r + 2] = t.z; kr[r + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < kKronRowTile; ++r)
+        kr[r] = (o0 + r < n_out) ? __ldg(K + (size_t)(o0 + r) * so + (size_t)i * si) : 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < kKronRowTile; ++r)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[r][v] += kr[r] * x[v];
+  }
+#pragma unroll
+  for (int r = 0; r < kKronRowTile; ++r) {
+    if (o0 + r >= n_out) break;
+    float* out = res + (size_t)(o0 + r) * d + k;
+    if (VEC == 4) {
+      float4 t = SET ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(out);
+      t.x += acc[r][0]; t.y += acc[r][1 % VEC]; t.z += acc[r][2 % VEC]; t.w += acc[r][3 % VEC];
+      *reinterpret_cast<float4*>(out) = t;
+    } else {
+      out[0] = SET ? acc[r][0] : out[0] + acc[r][0];
+    }
+  }
 }
 
-// kron(I_d, K):  res[b*n_out + o] += sum_i K(o, i) rhs[b*n_in + i]  -- d independent small products
+// kron(I_d, K):  res[b*n_out + o] (+)= sum_i K(o, i) rhs[b*n_in + i]  -- d independent small products on contiguous
+// segments.  A CTA takes kIdTileB consecutive segments: their inputs are ONE contiguous run of memory, staged into
+// shared memory with coalesced loads next to the factor; thread (segment, o) then reads its K row (padded rows: no
+// bank conflicts between the o of a warp) and the segment's inputs as broadcasts, and the outputs of the tile are
+// again one contiguous run.
+// (warp tiles: every warp stages, computes and stores its own run of segments -- no CTA-wide barrier in the loop)
+template <bool SET>
 __global__ void __launch_bounds__(kBlock) kron_id_k_kernel(float* __restrict__ res, const float* __restrict__ rhs,
                                                            const float* __restrict__ K, uint32_t n_out, uint32_t n_in,
-                                                           size_t d, uint32_t so, uint32_t si,
+                                                           size_t d, uint32_t so, uint32_t si, uint32_t tile_b,
                                                            const int* __restrict__ skip) {
+  if (skip && *skip) return;
+  extern __shared__ __align__(16) float kron_smem[];
+  const uint32_t pitch = (n_out + 3u) & ~3u;                   // Ks[i][o], o fastest, rows padded to 4 (zeros)
+  const uint32_t groups = pitch / 4;                           // a lane owns 4 consecutive outputs of one segment
+  const uint32_t xp = n_in + 1;                                // padded segment pitch: conflict-free across segments
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+  float* Ks = kron_smem;
+  float* xs = kron_smem + (size_t)n_in * pitch + (size_t)warp * tile_b * xp;      // this warp's xs[segment][i]
+  for (uint32_t e = threadIdx.x; e < n_in * pitch; e += blockDim.x) {
+    const uint32_t i = e / pitch, o = e % pitch;
+    Ks[e] = o < n_out ? K[(size_t)o * so + (size_t)i * si] : 0.f;
+  }
+  __syncthreads();
+  const size_t stride = (size_t)gridDim.x * warps * tile_b;
+  for (size_t b0 = ((size_t)blockIdx.x * warps + warp) * tile_b; b0 < d; b0 += stride) {
+    const uint32_t nb = (uint32_t)min((size_t)tile_b, d - b0);
+    __syncwarp();                                              // previous tile consumed
+    for (uint32_t e = lane; e < nb * n_in; e += 32) xs[(e / n_in) * xp + e % n_in] = rhs[b0 * n_in + e];
+    __syncwarp();
+    for (uint32_t e = lane; e < nb * groups; e += 32) {
+      const uint32_t bl = e / groups, o0 = (e % groups) * 4;
+      const float* x = xs + bl * xp;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      for (uint32_t i = 0; i < n_in; ++i) {                    // one 128-bit K read + one x read per 4 FMAs
+        const float4 k4 = *reinterpret_cast<const float4*>(Ks + i * pitch + o0);
+        const float xv = x[i];
+        s0 += k4.x * xv; s1 += k4.y * xv; s2 += k4.z * xv; s3 += k4.w * xv;
+      }
+      float* out = res + (b0 + bl) * n_out + o0;
+      const float sv[4] = {s0, s1, s2, s3};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (o0 + j < n_out) out[j] = SET ? sv[j] : out[j] + sv[j];
+    }
+  }
+}
+
+// fall-back for factors that do not fit in shared memory: one thread per output element
+template <bool SET>
+__global__ void __launch_bounds__(kBlock) kron_id_k_big_kernel(float* __restrict__ res, const float* __restrict__ rhs,
+                                                               const float* __restrict__ K, uint32_t n_out,
+                                                               uint32_t n_in, size_t d, uint32_t so, uint32_t si,
+                                                               const int* __restrict__ skip) {
   if (skip && *skip) return;
   const size_t total = d * n_out;
   for (size_t tx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; tx < total; tx += (size_t)gridDim.x * blockDim.x) {
@@ -485,7 +577,7 @@ __global__ void __launch_bounds__(kBlock) kron_id_k_kernel(float* __restrict__ r
     const float* x = rhs + b * n_in;
     float sum = 0.f;
     for (uint32_t i = 0; i < n_in; ++i) sum += __ldg(K + (size_t)o * so + (size_t)i * si) * x[i];
-    res[tx] += sum;
+    res[tx] = SET ? sum : res[tx] + sum;
   }
 }
 
@@ -515,24 +607,57 @@ class BlockDenseKron : public Block {
     return sum;
   }
   size_t gpu_mem_amount() const override { return host_.size() * sizeof(float); }
-  void eval_local_add(float* res, const float* rhs) override { apply(res, rhs, false); }
-  void eval_adjoint_local_add(float* res, const float* rhs) override { apply(res, rhs, true); }
+  void eval_local_add(float* res, const float* rhs) override { apply(res, rhs, false, false); }
+  void eval_adjoint_local_add(float* res, const float* rhs) override { apply(res, rhs, true, false); }
+  bool eval_local_set(float* res, const float* rhs) override { apply(res, rhs, false, true); return true; }
+  bool eval_adjoint_local_set(float* res, const float* rhs) override { apply(res, rhs, true, true); return true; }
 
  private:
-  void apply(float* res, const float* rhs, bool transpose) {
+  template <class Kernel>
+  static void allow_smem(Kernel kernel, size_t bytes) {
+    if (bytes > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  }
+  void apply(float* res, const float* rhs, bool transpose, bool set) {
     if (mr_ == 0 || mc_ == 0) return;
     // K(o, i): column-major K[i*mr + o]; transposed K^T(o, i) = K[o*mr + i]
     const uint32_t n_out = (uint32_t)(transpose ? mc_ : mr_), n_in = (uint32_t)(transpose ? mr_ : mc_);
     const uint32_t so = transpose ? (uint32_t)mr_ : 1u, si = transpose ? 1u : (uint32_t)mr_;
+    cudaStream_t st = ctx_->stream;
+    const float* K = d_data_.data();
+    const int* skip = ctx_->skip_flag;
     if (!id_first_) {
-      const dim3 grid(grid_for(d_), (n_out + kKronRowTile - 1) / kKronRowTile);
+      const bool vec4 = d_ % 4 == 0 && ((reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(rhs)) & 15u) == 0;
+      const size_t threads = vec4 ? d_ / 4 : d_;
+      const dim3 grid(grid_for(threads), (n_out + kKronRowTile - 1) / kKronRowTile);
       if (grid.y > 65535u) fail(PB_ERR_UNSUPPORTED, "Kronecker block: factor too large for this kernel");
-      kron_k_id_kernel<<<grid, kBlock, 0, ctx_->stream>>>(res, rhs, d_data_.data(), n_out, n_in, d_, so, si,
-                                                          ctx_->skip_flag);
+      const bool in_smem = (size_t)n_in * kKronRowTile <= (size_t)kKronSmemFloats;
+      const size_t smem = in_smem ? (size_t)n_in * kKronRowTile * sizeof(float) : 0;
+#define PB_KRON(V, S) kron_k_id_kernel<V, S><<<grid, kBlock, smem, st>>>(res, rhs, K, n_out, n_in, d_, so, si, in_smem, skip)
+      if (vec4) { if (set) PB_KRON(4, true); else PB_KRON(4, false); }
+      else { if (set) PB_KRON(1, true); else PB_KRON(1, false); }
+#undef PB_KRON
     } else {
-      const unsigned grid = (unsigned)std::min<size_t>(grid_for(d_ * n_out), (size_t)ctx_->num_sms * 32);
-      kron_id_k_kernel<<<grid, kBlock, 0, ctx_->stream>>>(res, rhs, d_data_.data(), n_out, n_in, d_, so, si,
-                                                          ctx_->skip_flag);
+      const size_t k_floats = (size_t)n_in * ((n_out + 3u) & ~3u);
+      // segments per tile: about one output per thread and pass, bounded by the shared memory left for the inputs
+      // segments per warp tile: up to 32, bounded by ~4 KB of staged inputs per warp
+      const size_t warps = kBlock / 32;
+      const size_t tile_b = std::max<size_t>(1, std::min<size_t>(32, 1024 / std::max<uint32_t>(n_in, 1u)));
+      const size_t smem = (k_floats + warps * tile_b * (n_in + 1)) * sizeof(float);
+      if (smem <= 96 * 1024) {
+        const size_t tiles = (d_ + tile_b - 1) / tile_b;
+        const unsigned grid = (unsigned)std::min<size_t>((tiles + warps - 1) / warps, (size_t)ctx_->num_sms * 8);
+        if (set) {
+          allow_smem(kron_id_k_kernel<true>, smem);
+          kron_id_k_kernel<true><<<grid, kBlock, smem, st>>>(res, rhs, K, n_out, n_in, d_, so, si, (uint32_t)tile_b, skip);
+        } else {
+          allow_smem(kron_id_k_kernel<false>, smem);
+          kron_id_k_kernel<false><<<grid, kBlock, smem, st>>>(res, rhs, K, n_out, n_in, d_, so, si, (uint32_t)tile_b, skip);
+        }
+      } else {
+        const unsigned grid = (unsigned)std::min<size_t>(grid_for(d_ * n_out), (size_t)ctx_->num_sms * 32);
+        if (set) kron_id_k_big_kernel<true><<<grid, kBlock, 0, st>>>(res, rhs, K, n_out, n_in, d_, so, si, skip);
+        else kron_id_k_big_kernel<false><<<grid, kBlock, 0, st>>>(res, rhs, K, n_out, n_in, d_, so, si, skip);
+      }
     }
     PB_CHECK_LAUNCH();
     ctx_->launches++;
@@ -546,27 +671,84 @@ class BlockDenseKron : public Block {
 // ---- the same products for a sparse factor (block_sparse_kron_id.cu:28-52, block_id_kron_sparse.cu) -------
 // CSR of the factor (or of its transpose for the adjoint); entries of a row in ascending column order, so the sums
 // run in the reference's order.
-// kron(K, I_d):  res[o*d + k] += sum_{j in row o} val[j] rhs[ind[j]*d + k]     (k fastest: coalesced)
+// kron(K, I_d):  res[o*d + k] (+)= sum_{j in row o} val[j] rhs[ind[j]*d + k].  A thread owns VEC consecutive k of one
+// output row (128-bit loads of the referenced input rows, 128-bit store): contiguous d-segments are streamed by a
+// warp instead of one element per thread (block_sparse_kron_id.cu:27-52 is the design this replaces).
+template <int VEC, bool SET>
 __global__ void __launch_bounds__(kBlock) kron_sparse_id_kernel(float* __restrict__ res, const float* __restrict__ rhs,
                                                                 const int* __restrict__ ptr, const int* __restrict__ ind,
                                                                 const float* __restrict__ val, uint32_t n_out, size_t d,
                                                                 const int* __restrict__ skip) {
   if (skip && *skip) return;
-  const size_t total = d * n_out;
+  const size_t per_row = d / VEC, total = per_row * n_out;
   for (size_t tx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; tx < total; tx += (size_t)gridDim.x * blockDim.x) {
-    const size_t o = tx / d, k = tx - o * d;
-    float sum = 0.f;
+    const size_t o = tx / per_row, k = (tx - o * per_row) * VEC;
+    float sum[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) sum[v] = 0.f;
     const int stop = ptr[o + 1];
-    for (int j = ptr[o]; j < stop; ++j) sum += val[j] * rhs[(size_t)ind[j] * d + k];
-    res[tx] += sum;
+    for (int j = ptr[o]; j < stop; ++j) {
+      const float a = val[j];
+      const float* x = rhs + (size_t)ind[j] * d + k;
+      if (VEC == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(x);
+        sum[0] += a * t.x; sum[1 % VEC] += a * t.y; sum[2 % VEC] += a * t.z; sum[3 % VEC] += a * t.w;
+      } else {
+        sum[0] += a * x[0];
+      }
+    }
+    float* out = res + o * d + k;
+    if (VEC == 4) {
+      float4 t = SET ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(out);
+      t.x += sum[0]; t.y += sum[1 % VEC]; t.z += sum[2 % VEC]; t.w += sum[3 % VEC];
+      *reinterpret_cast<float4*>(out) = t;
+    } else {
+      out[0] = SET ? sum[0] : out[0] + sum[0];
+    }
   }
 }
 
-// kron(I_d, K):  res[b*n_out + o] += sum_{j in row o} val[j] rhs[b*n_in + ind[j]]
+// kron(I_d, K):  res[b*n_out + o] (+)= sum_{j in row o} val[j] rhs[b*n_in + ind[j]].  Like the dense form: a CTA stages
+// the inputs of tile_b consecutive segments (one contiguous run) in shared memory, the gathers then hit shared
+// memory and the tile's outputs are one contiguous run.
+template <bool SET>
 __global__ void __launch_bounds__(kBlock) kron_id_sparse_kernel(float* __restrict__ res, const float* __restrict__ rhs,
                                                                 const int* __restrict__ ptr, const int* __restrict__ ind,
                                                                 const float* __restrict__ val, uint32_t n_out,
-                                                                uint32_t n_in, size_t d, const int* __restrict__ skip) {
+                                                                uint32_t n_in, size_t d, uint32_t tile_b,
+                                                                const int* __restrict__ skip) {
+  if (skip && *skip) return;
+  extern __shared__ __align__(16) float kron_smem[];
+  const uint32_t xp = n_in + 1;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+  float* xs = kron_smem + (size_t)warp * tile_b * xp;          // this warp's xs[segment][i]
+  const size_t stride = (size_t)gridDim.x * warps * tile_b;
+  for (size_t b0 = ((size_t)blockIdx.x * warps + warp) * tile_b; b0 < d; b0 += stride) {
+    const uint32_t nb = (uint32_t)min((size_t)tile_b, d - b0);
+    __syncwarp();
+    for (uint32_t e = lane; e < nb * n_in; e += 32) xs[(e / n_in) * xp + e % n_in] = rhs[b0 * n_in + e];
+    __syncwarp();
+    for (uint32_t e = lane; e < nb * n_out; e += 32) {
+      const uint32_t bl = e / n_out, o = e % n_out;
+      const float* x = xs + bl * xp;
+      float sum = 0.f;
+      const int stop = ptr[o + 1];
+      for (int j = ptr[o]; j < stop; ++j) sum += val[j] * x[ind[j]];
+      float* out = res + b0 * n_out + e;
+      *out = SET ? sum : *out + sum;
+    }
+  }
+}
+
+// fall-back when a segment tile does not fit in shared memory
+template <bool SET>
+__global__ void __launch_bounds__(kBlock) kron_id_sparse_big_kernel(float* __restrict__ res,
+                                                                    const float* __restrict__ rhs,
+                                                                    const int* __restrict__ ptr,
+                                                                    const int* __restrict__ ind,
+                                                                    const float* __restrict__ val, uint32_t n_out,
+                                                                    uint32_t n_in, size_t d,
+                                                                    const int* __restrict__ skip) {
   if (skip && *skip) return;
   const size_t total = d * n_out;
   for (size_t tx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; tx < total; tx += (size_t)gridDim.x * blockDim.x) {
@@ -575,7 +757,7 @@ __global__ void __launch_bounds__(kBlock) kron_id_sparse_kernel(float* __restric
     float sum = 0.f;
     const int stop = ptr[o + 1];
     for (int j = ptr[o]; j < stop; ++j) sum += val[j] * x[ind[j]];
-    res[tx] += sum;
+    res[tx] = SET ? sum : res[tx] + sum;
   }
 }
 
@@ -631,22 +813,60 @@ class BlockSparseKron : public Block {
   size_t gpu_mem_amount() const override {
     return 2 * val_.size() * (sizeof(int32_t) + sizeof(float)) + (size_t)(m_ + n_ + 2) * sizeof(int32_t);
   }
-  void eval_local_add(float* res, const float* rhs) override { apply(res, rhs, d_ptr_, d_ind_, d_val_, m_, n_); }
+  void eval_local_add(float* res, const float* rhs) override { apply(res, rhs, d_ptr_, d_ind_, d_val_, m_, n_, false); }
   void eval_adjoint_local_add(float* res, const float* rhs) override {
-    apply(res, rhs, d_ptr_t_, d_ind_t_, d_val_t_, n_, m_);
+    apply(res, rhs, d_ptr_t_, d_ind_t_, d_val_t_, n_, m_, false);
+  }
+  bool eval_local_set(float* res, const float* rhs) override {
+    apply(res, rhs, d_ptr_, d_ind_, d_val_, m_, n_, true);
+    return true;
+  }
+  bool eval_adjoint_local_set(float* res, const float* rhs) override {
+    apply(res, rhs, d_ptr_t_, d_ind_t_, d_val_t_, n_, m_, true);
+    return true;
   }
 
  private:
   void apply(float* res, const float* rhs, const DeviceBuffer<int>& ptr, const DeviceBuffer<int>& ind,
-             const DeviceBuffer<float>& val, int n_out, int n_in) {
-    if (n_out == 0 || n_in == 0 || val.size() == 0) return;
-    const unsigned grid = (unsigned)std::min<size_t>(grid_for(d_ * (size_t)n_out), (size_t)ctx_->num_sms * 32);
-    if (!id_first_)
-      kron_sparse_id_kernel<<<grid, kBlock, 0, ctx_->stream>>>(res, rhs, ptr.data(), ind.data(), val.data(),
-                                                               (uint32_t)n_out, d_, ctx_->skip_flag);
-    else
-      kron_id_sparse_kernel<<<grid, kBlock, 0, ctx_->stream>>>(res, rhs, ptr.data(), ind.data(), val.data(),
-                                                               (uint32_t)n_out, (uint32_t)n_in, d_, ctx_->skip_flag);
+             const DeviceBuffer<float>& val, int n_out, int n_in, bool set) {
+    if (n_out == 0 || n_in == 0) return;
+    cudaStream_t st = ctx_->stream;
+    const int* skip = ctx_->skip_flag;
+    if (val.size() == 0) {                       // empty factor: K = 0
+      if (set) PB_CUDA(cudaMemsetAsync(res, 0, d_ * (size_t)n_out * sizeof(float), st));
+      return;
+    }
+    if (!id_first_) {
+      const bool vec4 = d_ % 4 == 0 && ((reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(rhs)) & 15u) == 0;
+      const size_t threads = (vec4 ? d_ / 4 : d_) * (size_t)n_out;
+      const unsigned grid = (unsigned)std::min<size_t>(grid_for(threads), (size_t)ctx_->num_sms * 32);
+#define PB_KRON(V, S) kron_sparse_id_kernel<V, S><<<grid, kBlock, 0, st>>>(res, rhs, ptr.data(), ind.data(), val.data(), (uint32_t)n_out, d_, skip)
+      if (vec4) { if (set) PB_KRON(4, true); else PB_KRON(4, false); }
+      else { if (set) PB_KRON(1, true); else PB_KRON(1, false); }
+#undef PB_KRON
+    } else {
+      const size_t warps = kBlock / 32;
+      const size_t tile_b = std::max<size_t>(1, std::min<size_t>(32, 1024 / (size_t)std::max(n_in, 1)));
+      const size_t smem = warps * tile_b * ((size_t)n_in + 1) * sizeof(float);
+      if (smem <= 48 * 1024) {
+        const size_t tiles = (d_ + tile_b - 1) / tile_b;
+        const unsigned grid = (unsigned)std::min<size_t>((tiles + warps - 1) / warps, (size_t)ctx_->num_sms * 8);
+        if (set)
+          kron_id_sparse_kernel<true><<<grid, kBlock, smem, st>>>(res, rhs, ptr.data(), ind.data(), val.data(),
+                                                                  (uint32_t)n_out, (uint32_t)n_in, d_, (uint32_t)tile_b, skip);
+        else
+          kron_id_sparse_kernel<false><<<grid, kBlock, smem, st>>>(res, rhs, ptr.data(), ind.data(), val.data(),
+                                                                   (uint32_t)n_out, (uint32_t)n_in, d_, (uint32_t)tile_b, skip);
+      } else {
+        const unsigned grid = (unsigned)std::min<size_t>(grid_for(d_ * (size_t)n_out), (size_t)ctx_->num_sms * 32);
+        if (set)
+          kron_id_sparse_big_kernel<true><<<grid, kBlock, 0, st>>>(res, rhs, ptr.data(), ind.data(), val.data(),
+                                                                   (uint32_t)n_out, (uint32_t)n_in, d_, skip);
+        else
+          kron_id_sparse_big_kernel<false><<<grid, kBlock, 0, st>>>(res, rhs, ptr.data(), ind.data(), val.data(),
+                                                                    (uint32_t)n_out, (uint32_t)n_in, d_, skip);
+      }
+    }
     PB_CHECK_LAUNCH();
     ctx_->launches++;
   }
@@ -729,12 +949,50 @@ void LinearOperator::initialize() {
   }
   if (overlap)
     fail(PB_ERR_INVALID, "Blocks are overlapping inside the linear operator. Recheck the indices.");
+  auto disjoint = [&](bool rows) {
+    std::vector<std::pair<size_t, size_t>> r;
+    for (auto& b : blocks_) {
+      const size_t lo = rows ? b->row() : b->col(), n = rows ? b->nrows() : b->ncols();
+      if (b->nrows() && b->ncols()) r.emplace_back(lo, lo + n);
+    }
+    std::sort(r.begin(), r.end());
+    for (size_t i = 1; i < r.size(); ++i)
+      if (r[i].first < r[i - 1].second) return false;
+    return true;
+  };
+  disjoint_rows_ = disjoint(true);
+  disjoint_cols_ = disjoint(false);
 }
 
 void LinearOperator::eval(float* d_result, const float* d_rhs, float beta, bool transpose, bool negate) {
   ctx_->bind();
   const size_t nout = transpose ? ncols_ : nrows_;
   if (nout == 0) return;
+  if (beta == 0.f && !negate && !ctx_->skip_flag && (transpose ? disjoint_cols_ : disjoint_rows_)) {
+    // nobody else writes a block's outputs: blocks that can overwrite do so, the others (and the gaps between the
+    // blocks) see zeros first
+    size_t covered = 0;      // outputs [0, covered) are dealt with; blocks are visited in output order
+    std::vector<Block*> order;
+    for (auto& b : blocks_) order.push_back(b.get());
+    std::sort(order.begin(), order.end(), [&](Block* a, Block* b) {
+      return (transpose ? a->col() : a->row()) < (transpose ? b->col() : b->row());
+    });
+    for (Block* b : order) {
+      if (b->nrows() == 0 || b->ncols() == 0) continue;
+      const size_t lo = transpose ? b->col() : b->row(), n = transpose ? b->ncols() : b->nrows();
+      if (lo > covered) PB_CUDA(cudaMemsetAsync(d_result + covered, 0, (lo - covered) * sizeof(float), ctx_->stream));
+      const bool done = transpose ? b->eval_adjoint_local_set(d_result + b->col(), d_rhs + b->row())
+                                  : b->eval_local_set(d_result + b->row(), d_rhs + b->col());
+      if (!done) {
+        PB_CUDA(cudaMemsetAsync(d_result + lo, 0, n * sizeof(float), ctx_->stream));
+        if (transpose) b->eval_adjoint_local_add(d_result + b->col(), d_rhs + b->row());
+        else b->eval_local_add(d_result + b->row(), d_rhs + b->col());
+      }
+      covered = std::max(covered, lo + n);
+    }
+    if (nout > covered) PB_CUDA(cudaMemsetAsync(d_result + covered, 0, (nout - covered) * sizeof(float), ctx_->stream));
+    return;
+  }
   if (beta == 0.f) {
     PB_CUDA(cudaMemsetAsync(d_result, 0, nout * sizeof(float), ctx_->stream));
   } else if (beta != 1.f) {

@@ -181,6 +181,13 @@ class Block {
   // d_res[0:ncols] += K^T d_rhs[0:nrows] (block.cu:58-68)
   virtual void eval_adjoint_local_add(float* d_res, const float* d_rhs) = 0;
 
+  // Optional: d_res[0:nrows] = K d_rhs (resp. d_res[0:ncols] = K^T d_rhs), i.e. the block OVERWRITES its output
+  // range instead of accumulating into it.  LinearOperator::eval uses it for beta = 0 when no other block writes the
+  // same outputs, which saves the zero fill and the read of the read-modify-write (two thirds of the output traffic
+  // of a block with few inputs per output).  Return false when not implemented.
+  virtual bool eval_local_set(float*, const float*) { return false; }
+  virtual bool eval_adjoint_local_set(float*, const float*) { return false; }
+
   // descriptor for pointwise evaluation inside fused kernels
   virtual BlockDesc desc() const;
 
@@ -231,6 +238,9 @@ class LinearOperator {
   Context* ctx_;
   std::vector<std::shared_ptr<Block>> blocks_;
   size_t nrows_ = 0, ncols_ = 0;
+  // the blocks' output ranges are pairwise disjoint (rows: forward, columns: adjoint): a block may then overwrite
+  // its outputs when beta = 0 (Block::eval_local_set)
+  bool disjoint_rows_ = false, disjoint_cols_ = false;
 };
 
 }  // namespace pb

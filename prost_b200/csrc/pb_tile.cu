@@ -528,23 +528,6 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// ---- slab edges (SLAB instantiation only; protocol in pb_stencil.cuh: RingHalo, pb_comm.cuh) ---------------
-__device__ __forceinline__ void ring_flag_wait(const unsigned* flag, unsigned seq, int* error) {
-  if (!flag || seq == 0) return;
-  if (error && *reinterpret_cast<volatile int*>(error)) return;   // sticky: one timeout poisons the solve
-  unsigned v;
-  unsigned long long t0 = 0;
-  for (unsigned spins = 0;; ++spins) {
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-    if ((int)(v - seq) >= 0) break;
-    if ((spins & 1023u) == 1023u) {
-      unsigned long long now;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 2000000000ull) { if (error) atomicExch(error, 1); break; }
-    }
-  }
-}
 // ---- flag-in-data halo lines (RingHalo, pb_stencil.cuh) --------------------------------------------------------
 // four rows = two 16-byte lines {v0, seq, v1, seq} {v2, seq, v3, seq}; volatile accesses go to L2, the point of
 // coherence for the neighbour's NVLink stores
