@@ -49,6 +49,14 @@ class ProxElemOperation : public ProxSeparableSum<T> {
                                            this->diagsteps_, &h));
       return h;
     }
+    if (ELEM_OPERATION::kKind == detail::kElemOpSpectral && coeffs_.size() < 7) {
+      // mass / comass norms: zero or one coefficient array (the cost); the ABI takes the usual seven
+      static const float defaults[7] = {1.f, 0.f, 1.f, 0.f, 0.f, 0.f, 0.f};
+      std::vector<std::vector<T> > padded(7);
+      for (int k = 0; k < 7; ++k) padded[k].assign(1, defaults[k]);
+      for (size_t k = 0; k < coeffs_.size(); ++k) padded[k] = coeffs_[k];
+      coeffs_.swap(padded);
+    }
     if (coeffs_.size() != 7) throw Exception("ProxElemOperation: expected 7 coefficient arrays.");
     const float* ptrs[7];
     size_t lens[7];

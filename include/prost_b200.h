@@ -195,7 +195,11 @@ int pb_prox_create_ind_sum_indexed(pb_context* ctx, size_t index, size_t size, s
  * coeffs = a, b, c, d, e, alpha, beta of c h(a x - b) + d x + (e/2) x^2, 1 or count entries each.
  * function_2d (singular_nx2 only): 0 = sum_1d:<function_1d>, 1 = ind_l1_ball, 2 = moreau:ind_l1_ball. */
 typedef enum pb_spectral_kind {
-  PB_SPECTRAL_SINGULAR_NX2 = 0, PB_SPECTRAL_EIGEN_2X2 = 1, PB_SPECTRAL_EIGEN_3X3 = 2, PB_SPECTRAL_EIGEN_NXN = 3
+  PB_SPECTRAL_SINGULAR_NX2 = 0, PB_SPECTRAL_EIGEN_2X2 = 1, PB_SPECTRAL_EIGEN_3X3 = 2, PB_SPECTRAL_EIGEN_NXN = 3,
+  /* ElemOperationMass4 / Mass5<conjugate> (elem_operation_mass_norm.hpp:17-186; mex names "elem_operation:mass4",
+   * "elem_operation:ind_comass4_ball", "...:mass5", "...:ind_comass5_ball"): prox of the mass norm of a 2-vector in
+   * R^4 (dim 6) / R^5 (dim 10) resp. projection onto the comass unit ball; coeffs[0] = cost (mass4 only) */
+  PB_SPECTRAL_MASS4 = 4, PB_SPECTRAL_COMASS4_BALL = 5, PB_SPECTRAL_MASS5 = 6, PB_SPECTRAL_COMASS5_BALL = 7
 } pb_spectral_kind;
 int pb_prox_create_spectral(pb_context* ctx, int kind, size_t index, size_t count, size_t dim, int interleaved,
                             int diagsteps, int function_1d, int function_2d, const float* const h_coeffs[7],

@@ -26,6 +26,7 @@
 //           | indsum <idx> <count> <dim> <interleaved> <diagsteps>
 //           | halfspace <idx> <count> <dim> <interleaved> <diagsteps> <a> <b>
 //           | spectral <singular_nx2|eigen_2x2|eigen_3x3|eigen_nxn> <fun> <idx> <count> <dim> <interleaved> <diagsteps> <7 coeffs>
+//           | massnorm <mass4|ind_comass4_ball|mass5|ind_comass5_ball> <idx> <count> <dim> <interleaved> <diagsteps> <cost>
 //           | indsumidx <idx> <size> <n_lists: 1|2> { <dim> <inds file (u64)> <n_inds> <sum> } x n_lists
 //           | soc <idx> <count> <dim> <interleaved> <diagsteps> <alpha>
 //           | epiquad <idx> <count> <dim> <interleaved> <diagsteps> <a> <b> <c>
@@ -82,6 +83,7 @@
 #include "prost/prox/elemop/elem_operation_eigen_3x3.hpp"
 #include "prost/prox/elemop/elem_operation_eigen_nxn.hpp"
 #include "prost/prox/elemop/function_2d.hpp"
+#include "prost/prox/elemop/elem_operation_mass_norm.hpp"
 #include "prost/prox/prox_ind_soc.hpp"
 #include "prost/prox/prox_transform.hpp"
 #include "prost/prox/prox_permute.hpp"
@@ -206,6 +208,20 @@ static std::shared_ptr<Prox<real>> parse_prox(std::istringstream& in) {
     }
     if (!p) { std::cerr << "unknown spectral operation " << op << " " << fun << std::endl; std::exit(2); }
     return std::shared_ptr<Prox<real>>(p);
+  }
+  if (kind == "massnorm") {
+    std::string op, cost;
+    size_t idx, count, dim;
+    int il, ds;
+    in >> op >> idx >> count >> dim >> il >> ds >> cost;
+    std::array<std::vector<real>, 1> c1;
+    c1[0] = coeff(cost);
+    if (op == "mass4") return std::shared_ptr<Prox<real>>(new ProxElemOperation<real, ElemOperationMass4<real, false>>(idx, count, dim, il, ds, c1));
+    if (op == "ind_comass4_ball") return std::shared_ptr<Prox<real>>(new ProxElemOperation<real, ElemOperationMass4<real, true>>(idx, count, dim, il, ds, c1));
+    if (op == "mass5") return std::shared_ptr<Prox<real>>(new ProxElemOperation<real, ElemOperationMass5<real, false>>(idx, count, dim, il, ds));
+    if (op == "ind_comass5_ball") return std::shared_ptr<Prox<real>>(new ProxElemOperation<real, ElemOperationMass5<real, true>>(idx, count, dim, il, ds));
+    std::cerr << "unknown mass norm " << op << std::endl;
+    std::exit(2);
   }
   if (kind == "indsumidx") {
     size_t idx, size;

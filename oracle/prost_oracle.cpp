@@ -516,7 +516,7 @@ static void jacobi_eig(std::vector<double>& A, std::vector<double>& V, int n) { 
 }
 
 struct ProxSpectral : ProxSeparable {
-  int kind, fn, fn2d;      // kind: 0 singular_nx2, 1 eigen_2x2, 2 eigen_3x3, 3 eigen_nxn
+  int kind, fn, fn2d;      // kind: 0 singular_nx2, 1 eigen_2x2, 2 eigen_3x3, 3 eigen_nxn, 4-7 mass4 / comass4 / mass5 / comass5
   vec coeffs[7];
   ProxSpectral(int k, size_t i, size_t c, size_t d, bool il, bool ds, int f, int f2, const float* const* co, const size_t* len)
       : ProxSeparable(i, c, d, il, ds), kind(k), fn(f), fn2d(f2) {
@@ -609,6 +609,37 @@ struct ProxSpectral : ProxSeparable {
         rt2 = eig_prox(rt2, tau, c);
         const double t11 = rt1 * cs * cs + rt2 * sn * sn, t12 = rt1 * cs * sn - sn * rt2 * cs, t22 = rt1 * sn * sn + rt2 * cs * cs;
         res[at(tx, 0)] = t11; res[at(tx, 1)] = t12; res[at(tx, 2)] = t12; res[at(tx, 3)] = t22;
+      } else if (kind >= 4) {                                    // mass4 / comass4 / mass5 / comass5
+        // elem_operation_mass_norm.hpp:17-186.  The reference tridiagonalises the skew-symmetric matrix M of the
+        // 2-vector and takes a 2 x 2 SVD; the prox is U f(Sigma) V^T = M h(M^T M), evaluated here through the
+        // symmetric eigenproblem of M^T M (pinned on numpy's svd and on the live reference).
+        const int nm = kind <= 5 ? 4 : 5;
+        const bool conj = kind == 5 || kind == 7;
+        const double tau_m = kind == 4 ? (invert ? (1. / (tau_scal * c[0] * td0)) : (tau_scal * c[0] * td0)) : tau;
+        std::vector<double> M((size_t)nm * nm, 0.0), S((size_t)nm * nm, 0.0), V;
+        int e = 0;
+        for (int i = 0; i < nm; ++i)
+          for (int j = i + 1; j < nm; ++j) { const double v = arg[at(tx, e++)]; M[i * nm + j] = v; M[j * nm + i] = -v; }
+        for (int i = 0; i < nm; ++i)
+          for (int j = 0; j < nm; ++j) { double t = 0; for (int k = 0; k < nm; ++k) t += M[k * nm + i] * M[k * nm + j]; S[i * nm + j] = t; }
+        jacobi_eig(S, V, nm);
+        std::vector<double> w(nm);
+        for (int k = 0; k < nm; ++k) {
+          const double sg = std::sqrt(std::max(S[k * nm + k], 0.0));
+          const double f = conj ? std::min(sg, 1.0) : std::max(sg - tau_m, 0.0);
+          w[k] = sg > 1e-150 ? f / sg : 0.0;
+        }
+        e = 0;
+        for (int i = 0; i < nm; ++i)
+          for (int j = i + 1; j < nm; ++j) {
+            double t = 0;
+            for (int l = 0; l < nm; ++l) {
+              double h = 0;
+              for (int k = 0; k < nm; ++k) h += V[l * nm + k] * V[j * nm + k] * w[k];
+              t += M[i * nm + l] * h;
+            }
+            res[at(tx, e++)] = t;
+          }
       } else {                                                   // eigen_3x3 / eigen_nxn (see the note above)
         int n = 1;
         while ((size_t)n * n < dim) ++n;

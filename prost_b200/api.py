@@ -395,10 +395,14 @@ class ProxElemOperationSpectral(Prox):
     """ProxElemOperation<T, ElemOperationSingularNx2 / Eigen2x2 / Eigen3x3 / EigenNxN> (elem_operation_singular_nx2.hpp,
     elem_operation_eigen_*.hpp).  ``kind``: "singular_nx2", "eigen_2x2", "eigen_3x3", "eigen_nxn"; ``function`` is
     a Function1D name, or for singular_nx2 also "ind_l1_ball" / "moreau:ind_l1_ball" (function_2d.hpp)."""
-    KINDS = {"singular_nx2": 0, "eigen_2x2": 1, "eigen_3x3": 2, "eigen_nxn": 3}
+    KINDS = {"singular_nx2": 0, "eigen_2x2": 1, "eigen_3x3": 2, "eigen_nxn": 3, "mass4": 4, "ind_comass4_ball": 5,
+             "mass5": 6, "ind_comass5_ball": 7}
 
     def __init__(self, ctx, kind, function, index, count, dim, interleaved, diagsteps, coeffs):
         super().__init__(ctx)
+        if self.KINDS[kind] >= 4:       # mass / comass norms: one optional coefficient (the cost of mass4)
+            cost = coeffs[0] if coeffs else [1.0]
+            coeffs, function = [cost, [0.0], [1.0], [0.0], [0.0], [0.0], [0.0]], "zero"
         keep, ptrs, lens = _coeff_arrays(coeffs)
         fn2d = {"ind_l1_ball": 1, "moreau:ind_l1_ball": 2}.get(function, 0)
         fn1d = 0 if fn2d else function_id(function[len("sum_1d:"):] if function.startswith("sum_1d:") else function)

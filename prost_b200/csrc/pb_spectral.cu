@@ -3,7 +3,8 @@
 // per group of a ProxSeparableSum.
 //
 // Reference: include/prost/prox/elemop/elem_operation_singular_nx2.hpp:32-150 (+ function_2d.hpp:28-101),
-// elem_operation_eigen_2x2.hpp:28-146, elem_operation_eigen_3x3.hpp:31-377, elem_operation_eigen_nxn.hpp;
+// elem_operation_eigen_2x2.hpp:28-146, elem_operation_eigen_3x3.hpp:31-377, elem_operation_eigen_nxn.hpp,
+// elem_operation_mass_norm.hpp:17-186;
 // mex names "elem_operation:singular_nx2:{sum_1d:<fun>, ind_l1_ball, moreau:ind_l1_ball}",
 // "elem_operation:eigen_{2x2,3x3,nxn}:<fun>" (factory.cpp:49-102).
 //
@@ -281,6 +282,70 @@ __global__ void __launch_bounds__(kBlock) spectral_eigen_nxn_kernel(const Spectr
   }
 }
 
+// ---- mass / comass norms of 2-vectors in R^4 and R^5 (elem_operation_mass_norm.hpp:17-186) ---------------------
+// The argument (6 resp. 10 numbers) is the upper triangle of a skew-symmetric matrix M; the mass norm is the sum of
+// its singular-value pairs, the prox shrinks them (comass ball: clamps them to 1).  With M = U Sigma V^T:
+// prox(M) = U f(Sigma) V^T = M h(M^T M),  h = V diag(f(sigma_k) / sigma_k) V^T  -- a spectral function of the
+// SYMMETRIC matrix M^T M, evaluated with the Jacobi rotations above (the reference tridiagonalises the skew matrix
+// with Householder / Givens steps and a 2 x 2 SVD, :40-83, :120-175).
+template <int NM, bool CONJ>
+__global__ void __launch_bounds__(kBlock) spectral_mass_kernel(const SpectralDesc p, float* __restrict__ res,
+                                                               const float* __restrict__ arg,
+                                                               const float* __restrict__ td, float tau_scal,
+                                                               bool invert) {
+  for (size_t tx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; tx < p.count; tx += (size_t)gridDim.x * blockDim.x) {
+    float c[7];
+    load7(p.coeffs, tx, c);
+    const float ts = NM == 4 ? tau_scal * c[0] : tau_scal;                 // weighted mass norm (:27)
+    const double tau = group_tau(ts, td[elem_at(p, tx, 0)], invert);
+    double M[NM][NM];
+    int e = 0;
+#pragma unroll
+    for (int i = 0; i < NM; ++i) {
+      M[i][i] = 0.0;
+#pragma unroll
+      for (int j = i + 1; j < NM; ++j) {
+        const double v = arg[elem_at(p, tx, e++)];
+        M[i][j] = v;
+        M[j][i] = -v;
+      }
+    }
+    double S[NM][NM], V[NM][NM];
+#pragma unroll
+    for (int i = 0; i < NM; ++i)
+#pragma unroll
+      for (int j = 0; j < NM; ++j) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < NM; ++k) t += M[k][i] * M[k][j];              // M^T M
+        S[i][j] = t;
+      }
+    jacobi_eig<NM>(S, V, NM);
+    double w[NM];
+#pragma unroll
+    for (int k = 0; k < NM; ++k) {
+      const double lam = fmax(S[k][k], 0.0), sg = sqrt(lam);
+      const double f = CONJ ? fmin(sg, 1.0) : fmax(sg - tau, 0.0);
+      w[k] = sg > 1e-150 ? f / sg : 0.0;
+    }
+    e = 0;
+#pragma unroll
+    for (int i = 0; i < NM; ++i)
+#pragma unroll
+      for (int j = i + 1; j < NM; ++j) {
+        double t = 0.0;                                                    // (M h)_{ij} = sum_l M_il h_lj
+#pragma unroll
+        for (int l = 0; l < NM; ++l) {
+          double h = 0.0;
+#pragma unroll
+          for (int k = 0; k < NM; ++k) h += V[l][k] * V[j][k] * w[k];
+          t += M[i][l] * h;
+        }
+        res[elem_at(p, tx, e++)] = static_cast<float>(t);
+      }
+  }
+}
+
 class ProxSpectral : public Prox {
  public:
   ProxSpectral(Context* ctx, int kind, size_t index, size_t count, size_t dim, bool interleaved, bool diagsteps,
@@ -315,6 +380,14 @@ class ProxSpectral : public Prox {
         desc_.n = n;
         break;
       }
+      case PB_SPECTRAL_MASS4:
+      case PB_SPECTRAL_COMASS4_BALL:
+        if (dim != 6) fail(PB_ERR_INVALID, "mass4 / ind_comass4_ball: dim must be 6");
+        break;
+      case PB_SPECTRAL_MASS5:
+      case PB_SPECTRAL_COMASS5_BALL:
+        if (dim != 10) fail(PB_ERR_INVALID, "mass5 / ind_comass5_ball: dim must be 10");
+        break;
       default: fail(PB_ERR_INVALID, "unknown spectral operation");
     }
     if (fn < 0 || fn >= PB_FUN_COUNT_) fail(PB_ERR_INVALID, "unknown Function1D");
@@ -355,6 +428,10 @@ class ProxSpectral : public Prox {
       case PB_SPECTRAL_EIGEN_2X2:
         spectral_eigen_2x2_kernel<<<grid, kBlock, 0, s>>>(desc_, res, arg, td, tau, invert);
         break;
+      case PB_SPECTRAL_MASS4: spectral_mass_kernel<4, false><<<grid, kBlock, 0, s>>>(desc_, res, arg, td, tau, invert); break;
+      case PB_SPECTRAL_COMASS4_BALL: spectral_mass_kernel<4, true><<<grid, kBlock, 0, s>>>(desc_, res, arg, td, tau, invert); break;
+      case PB_SPECTRAL_MASS5: spectral_mass_kernel<5, false><<<grid, kBlock, 0, s>>>(desc_, res, arg, td, tau, invert); break;
+      case PB_SPECTRAL_COMASS5_BALL: spectral_mass_kernel<5, true><<<grid, kBlock, 0, s>>>(desc_, res, arg, td, tau, invert); break;
       default:
         if (desc_.n <= 3) spectral_eigen_nxn_kernel<3><<<grid, kBlock, 0, s>>>(desc_, res, arg, td, tau, invert);
         else if (desc_.n <= 5) spectral_eigen_nxn_kernel<5><<<grid, kBlock, 0, s>>>(desc_, res, arg, td, tau, invert);

@@ -10,6 +10,7 @@ reference's mex registry names and argument order (matlab/+prost/private/factory
   elem_operation:ind_simplex, elem_operation:ind_sum   : [count, dim, interleaved]
   elem_operation:singular_nx2:{sum_1d:<fun>, ind_l1_ball, moreau:ind_l1_ball},
   elem_operation:eigen_2x2|eigen_3x3|eigen_nxn:<fun>   : [count, dim, interleaved, [a,b,c,d,e,alpha,beta]]
+  elem_operation:mass4|ind_comass4_ball|mass5|ind_comass5_ball : [count, dim, interleaved(, [cost])]
   ind_epi_quad                                         : [count, dim, interleaved, [a, b, c]]
   ind_sum                                              : [dim, inds, sum(, dim2, inds2, sum2)]
   ind_epi_conjquad_1d                                  : [count, interleaved, [a, b, c, alpha, beta]]
@@ -39,6 +40,11 @@ def create_prox(ctx, desc):
             count, dim, interleaved, coeffs = data
             return api.ProxElemOperationSpectral(ctx, kind, name[len(prefix):], idx, count, dim, interleaved, diagsteps,
                                                  coeffs)
+    if name in ("elem_operation:mass4", "elem_operation:ind_comass4_ball", "elem_operation:mass5",
+                "elem_operation:ind_comass5_ball"):          # +function/sum_mass_norm.m, sum_ind_comass_ball.m
+        count, dim, interleaved = data[:3]
+        return api.ProxElemOperationSpectral(ctx, name.split(":")[1], "zero", idx, count, dim, interleaved, diagsteps,
+                                             data[3] if len(data) > 3 else None)
     if name == "elem_operation:ind_simplex":
         count, dim, interleaved = data[:3]
         return api.ProxElemOperationIndSimplex(ctx, idx, count, dim, interleaved, diagsteps)

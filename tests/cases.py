@@ -245,6 +245,11 @@ def prox_spectral_cases(small=False):
         cases[f"{kind}_d{dim}_square_vec"] = ((f"elem_operation:{kind}:square", 7, n * dim, True,
                                                [n, dim, True, coeffs(a=1, b=r.random(n), c=r.uniform(0.5, 2, n), d=0.1, e=0.2)]),
                                               n * dim + 11)
+    for name, dim in (("mass4", 6), ("ind_comass4_ball", 6), ("mass5", 10), ("ind_comass5_ball", 10)):
+        for il in (True, False):
+            data = [n, dim, il] + ([[[1.0]]] if dim == 6 else [])
+            cases[f"{name}_il{int(il)}"] = ((f"elem_operation:{name}", 0, n * dim, False, data), n * dim)
+    cases["mass4_cost"] = (("elem_operation:mass4", 3, n * 6, False, [n, 6, True, [[0.4]]]), n * 6 + 5)
     for N in (2, 3, 8):
         dim = 2 * N
         for fun in ("sum_1d:abs", "sum_1d:square", "sum_1d:ind_box01", "ind_l1_ball", "moreau:ind_l1_ball"):

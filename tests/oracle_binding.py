@@ -202,6 +202,15 @@ class OracleProblem:
                 lens = (sz * 7)(*[a.size for a in arrs])
                 return lib.orc_prox_spectral(self.h, kind_id, idx, count, dim, int(il), int(diagsteps), fn1d, fn2d,
                                              ptrs, lens)
+        if name in ("elem_operation:mass4", "elem_operation:ind_comass4_ball", "elem_operation:mass5",
+                    "elem_operation:ind_comass5_ball"):
+            count, dim, il = data[:3]
+            kind_id = {"mass4": 4, "ind_comass4_ball": 5, "mass5": 6, "ind_comass5_ball": 7}[name.split(":")[1]]
+            cost = data[3][0] if len(data) > 3 else [1.0]
+            arrs = [_f32(np.atleast_1d(c)) for c in (cost, [0.0], [1.0], [0.0], [0.0], [0.0], [0.0])]
+            ptrs = (fp * 7)(*[_p(a) for a in arrs])
+            lens = (sz * 7)(*[a.size for a in arrs])
+            return lib.orc_prox_spectral(self.h, kind_id, idx, count, dim, int(il), int(diagsteps), 0, 0, ptrs, lens)
         if name == "ind_epi_conjquad_1d":
             count, il, coeffs = data
             arrs = [_f32(np.atleast_1d(c)) for c in coeffs]

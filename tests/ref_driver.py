@@ -91,6 +91,11 @@ class _Writer:
                 count, dim, il, coeffs = data
                 cs = " ".join(self.coeff(c) for c in coeffs)
                 return f"spectral {kind} {name[len(prefix):]} {idx} {count} {dim} {int(il)} {int(ds)} {cs}"
+        if name in ("elem_operation:mass4", "elem_operation:ind_comass4_ball", "elem_operation:mass5",
+                    "elem_operation:ind_comass5_ball"):
+            count, dim, il = data[:3]
+            cost = self.coeff(data[3][0]) if len(data) > 3 else "s:1.0"
+            return f"massnorm {name.split(':')[1]} {idx} {count} {dim} {int(il)} {int(ds)} {cost}"
         if name == "elem_operation:ind_simplex":
             count, dim, il = data[:3]
             return f"simplex {idx} {count} {dim} {int(il)} {int(ds)}"

@@ -325,8 +325,26 @@ def test_prox_ind_epi_conjquad_1d_is_the_projection_onto_the_conjugate_epigraph(
 def _spectral_closed_form(desc, arg):
     """numpy restatement: T = V f(Lambda) V^T through eigh (eigen_*), U f(S) V^T through svd (singular_nx2), for the
     functions whose scalar prox has an obvious closed form (the reference's tests do the same with MATLAB's eig)."""
-    name, idx, size, ds, (count, dim, il, co) = desc
+    name, idx, size, ds, data = desc
     kind, fun = name.split(":")[1], ":".join(name.split(":")[2:])
+    if kind in ("mass4", "ind_comass4_ball", "mass5", "ind_comass5_ball"):
+        # elem_operation_mass_norm.hpp: shrink (mass) or clamp to 1 (comass ball) the singular values of the skew matrix
+        count, dim, il = data[:3]
+        cost = float(np.atleast_1d(data[3][0])[0]) if len(data) > 3 else 1.0
+        nm = 4 if dim == 6 else 5
+        A = arg[idx:idx + size].astype(np.float64)
+        G = A.reshape(count, dim) if il else A.reshape(dim, count).T
+        out = np.empty_like(G)
+        iu = np.triu_indices(nm, 1)
+        for i in range(count):
+            M = np.zeros((nm, nm))
+            M[iu] = G[i]
+            M = M - M.T
+            U, S, Vt = np.linalg.svd(M)
+            Sn = np.minimum(S, 1.0) if "comass" in kind else np.maximum(S - 0.7 * (cost if nm == 4 else 1.0), 0)
+            out[i] = ((U * Sn) @ Vt)[iu]
+        return out.reshape(-1) if il else out.T.reshape(-1)
+    count, dim, il, co = data
     A = arg[idx:idx + size].astype(np.float64)
     G = A.reshape(count, dim) if il else A.reshape(dim, count).T
     at = lambda k, i: float(np.atleast_1d(co[k])[i if np.atleast_1d(co[k]).size > 1 else 0])
