@@ -204,6 +204,13 @@ typedef enum pb_spectral_kind {
 int pb_prox_create_spectral(pb_context* ctx, int kind, size_t index, size_t count, size_t dim, int interleaved,
                             int diagsteps, int function_1d, int function_2d, const float* const h_coeffs[7],
                             const size_t coeff_len[7], pb_prox** out);
+/* ProxIndRange(index, size, diagsteps) + setA(m, n, nnz, val, ptr, ind) + setAA(n, n, val) (prox_ind_range.hpp:37-50,
+ * prox_ind_range.cu:28-300; mex name "ind_range"): projection onto the range of the sparse m x n matrix A (CSC like
+ * BlockSparse::CreateFromCSC), x = A (A^T A)^{-1} A^T x0, with the dense column-major AA = A^T A (n <= 4096).
+ * m must equal size. */
+int pb_prox_create_ind_range(pb_context* ctx, size_t index, size_t size, int diagsteps, int m, int n, int nnz,
+                             const float* h_val, const int32_t* h_ptr, const int32_t* h_ind, const float* h_aa,
+                             pb_prox** out);
 /* ProxIndEpiConjQuad1D (north star: "ProxEpiConjQuadr"; mex name "ind_epi_conjquad_1d"): per (x, y) pair the
  * projection onto the epigraph of the conjugate of rho(u) = a u^2 + b u + c on [alpha, beta], a >= 0.  PARITY
  * UNPINNED: the reference only names the class (cmake/CustomSources.cmake.example:8-14, un-vendored repository

@@ -27,6 +27,7 @@
 //           | halfspace <idx> <count> <dim> <interleaved> <diagsteps> <a> <b>
 //           | spectral <singular_nx2|eigen_2x2|eigen_3x3|eigen_nxn> <fun> <idx> <count> <dim> <interleaved> <diagsteps> <7 coeffs>
 //           | massnorm <mass4|ind_comass4_ball|mass5|ind_comass5_ball> <idx> <count> <dim> <interleaved> <diagsteps> <cost>
+//           | indrange <idx> <size> <diagsteps> <m> <n> <nnz> <val file> <ptr file> <ind file> <AA file (n*n, column-major)>
 //           | indsumidx <idx> <size> <n_lists: 1|2> { <dim> <inds file (u64)> <n_inds> <sum> } x n_lists
 //           | soc <idx> <count> <dim> <interleaved> <diagsteps> <alpha>
 //           | epiquad <idx> <count> <dim> <interleaved> <diagsteps> <a> <b> <c>
@@ -78,6 +79,7 @@
 #include "prost/prox/prox_moreau.hpp"
 #include "prost/prox/prox_ind_halfspace.hpp"
 #include "prost/prox/prox_ind_sum.hpp"
+#include "prost/prox/prox_ind_range.hpp"
 #include "prost/prox/elemop/elem_operation_singular_nx2.hpp"
 #include "prost/prox/elemop/elem_operation_eigen_2x2.hpp"
 #include "prost/prox/elemop/elem_operation_eigen_3x3.hpp"
@@ -222,6 +224,17 @@ static std::shared_ptr<Prox<real>> parse_prox(std::istringstream& in) {
     if (op == "ind_comass5_ball") return std::shared_ptr<Prox<real>>(new ProxElemOperation<real, ElemOperationMass5<real, true>>(idx, count, dim, il, ds));
     std::cerr << "unknown mass norm " << op << std::endl;
     std::exit(2);
+  }
+  if (kind == "indrange") {
+    size_t idx, size;
+    int ds, m, n, nnz;
+    std::string fv, fp, fi, fa;
+    in >> idx >> size >> ds >> m >> n >> nnz >> fv >> fp >> fi >> fa;
+    ProxIndRange<real>* p = new ProxIndRange<real>(idx, size, ds != 0);
+    const std::vector<float> v32 = read_file<float>(fv, nnz), a32 = read_file<float>(fa, (size_t)n * n);
+    p->setA(m, n, nnz, std::vector<real>(v32.begin(), v32.end()), read_file<int32_t>(fp, n + 1), read_file<int32_t>(fi, nnz));
+    p->setAA(n, n, std::vector<real>(a32.begin(), a32.end()));
+    return std::shared_ptr<Prox<real>>(p);
   }
   if (kind == "indsumidx") {
     size_t idx, size;

@@ -874,6 +874,49 @@ struct ProxIndEpiConjQuad1D : ProxSeparable {
   }
 };
 
+// ProxIndRange (prox_ind_range.cu:28-300): x = A (A^T A)^{-1} A^T x0 with A sparse (CSC) and AA = A^T A dense.
+// The reference: csrmv with A^T (float), potrf / potrs of AA (float, cusolverDn), csrmv with A.  Restated with float
+// products accumulated per row like a CSR SpMV and a Cholesky solve in double (pinned on the closed form of
+// test_prox_ind_range.m at its 1e-4 and on the live reference).
+struct ProxIndRange : Prox {
+  int m, n;
+  std::vector<int> ptr, ind;       // CSC of A
+  vec val;
+  std::vector<double> L;           // Cholesky factor of AA, row-major lower
+  ProxIndRange(size_t i, size_t sz, bool ds, int m_, int n_, int nnz, const float* v, const int* p, const int* ix,
+               const float* aa)
+      : Prox(i, sz, ds), m(m_), n(n_), ptr(p, p + n_ + 1), ind(ix, ix + nnz), val(v, v + nnz), L((size_t)n_ * n_, 0.0) {
+    const size_t N = n;
+    for (size_t j = 0; j < N; ++j) {
+      double d = aa[j * N + j];
+      for (size_t k = 0; k < j; ++k) d -= L[j * N + k] * L[j * N + k];
+      L[j * N + j] = std::sqrt(d);
+      for (size_t r = j + 1; r < N; ++r) {
+        double t = aa[j * N + r];
+        for (size_t k = 0; k < j; ++k) t -= L[r * N + k] * L[j * N + k];
+        L[r * N + j] = t / L[j * N + j];
+      }
+    }
+  }
+  void eval_local(float* res, const float* arg, const float*, float, bool) override {
+    const size_t N = n;
+    std::vector<double> t(N);
+    for (size_t c = 0; c < N; ++c) {                               // A^T x0: column c of A dotted with x0
+      float acc = 0;
+      for (int k = ptr[c]; k < ptr[c + 1]; ++k) acc += val[k] * arg[ind[k]];
+      t[c] = acc;
+    }
+    for (size_t r = 0; r < N; ++r) { double v = t[r]; for (size_t k = 0; k < r; ++k) v -= L[r * N + k] * t[k]; t[r] = v / L[r * N + r]; }
+    for (size_t r = N; r-- > 0;) { double v = t[r]; for (size_t k = r + 1; k < N; ++k) v -= L[k * N + r] * t[k]; t[r] = v / L[r * N + r]; }
+    std::vector<double> out(m, 0.0);
+    for (size_t c = 0; c < N; ++c) {
+      const float tc = static_cast<float>(t[c]);
+      for (int k = ptr[c]; k < ptr[c + 1]; ++k) out[ind[k]] += static_cast<double>(val[k] * tc);
+    }
+    for (int r = 0; r < m; ++r) res[r] = static_cast<float>(out[r]);
+  }
+};
+
 struct ProxIndSOC : ProxSeparable {         // prox_ind_soc.cu:33-77: { (x, y) | |x|_2 <= y }, alpha = 1 only
   ProxIndSOC(size_t i, size_t c, size_t d, bool il, bool ds) : ProxSeparable(i, c, d, il, ds) {}
   void eval_local(float* res, const float* arg, const float*, float, bool) override {
@@ -1416,6 +1459,10 @@ int orc_prox_ind_epi_conjquad_1d(void* p, size_t idx, size_t count, int il, int 
 int orc_prox_spectral(void* p, int kind, size_t idx, size_t count, size_t dim, int il, int ds, int fn, int fn2d,
                       const float* const* coeffs, const size_t* len) {
   return push(PP, std::make_shared<ProxSpectral>(kind, idx, count, dim, il != 0, ds != 0, fn, fn2d, coeffs, len));
+}
+int orc_prox_ind_range(void* p, size_t idx, size_t size, int ds, int m, int n, int nnz, const float* val, const int* ptr,
+                       const int* ind, const float* aa) {
+  return push(PP, std::make_shared<ProxIndRange>(idx, size, ds != 0, m, n, nnz, val, ptr, ind, aa));
 }
 int orc_prox_ind_soc(void* p, size_t idx, size_t count, size_t dim, int il, int ds) {
   return push(PP, std::make_shared<ProxIndSOC>(idx, count, dim, il != 0, ds != 0));

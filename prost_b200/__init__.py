@@ -9,7 +9,7 @@ from .api import (ADMMOptions, Backend, Comm, BackendADMM, BackendPDHG, Block, B
                   BlockGradient2D, BlockGradient3D, BlockSparse, BlockZero, Context, LinearOperator,
                   PDHGOptions, Problem, ProstError, Prox, ProxElemOperation1D, ProxElemOperationIndSimplex,
                   ProxElemOperationIndSum, ProxElemOperationSpectral,
-                  ProxElemOperationNorm2, ProxIndEpiQuad, ProxIndEpiConjQuad1D, ProxIndHalfspace, ProxIndSum, ProxIndSOC, ProxMoreau, ProxPermute, ProxTransform, ProxZero, Solver,
+                  ProxElemOperationNorm2, ProxIndEpiQuad, ProxIndEpiConjQuad1D, ProxIndHalfspace, ProxIndRange, ProxIndSum, ProxIndSOC, ProxMoreau, ProxPermute, ProxTransform, ProxZero, Solver,
                   SolverOptions, admm_options, pdhg_options, solver_options)
 from .factory import create_block, create_linop, create_problem, create_prox
 from ._capi import LIB_PATH, lib

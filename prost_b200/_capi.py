@@ -129,6 +129,8 @@ SIGNATURES = {
                                                  C.POINTER(C.c_ulonglong), C.c_float, handle_p]),
     "pb_prox_create_spectral": (C.c_int, [handle, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int,
                                           C.c_int, C.POINTER(c_float_p), c_size_p, handle_p]),
+    "pb_prox_create_ind_range": (C.c_int, [handle, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, c_float_p,
+                                           c_i32_p, c_i32_p, c_float_p, handle_p]),
     "pb_prox_create_ind_epi_conjquad_1d": (C.c_int, [handle, C.c_size_t, C.c_size_t, C.c_int, C.c_int,
                                                      C.POINTER(c_float_p), c_size_p, handle_p]),
     "pb_prox_create_ind_halfspace": (C.c_int, [handle, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int,

@@ -410,6 +410,26 @@ class ProxElemOperationSpectral(Prox):
                                           fn1d, fn2d, ptrs, lens, C.byref(self._h)))
 
 
+class ProxIndRange(Prox):
+    """ProxIndRange<T>(index, size, diagsteps) with setA / setAA (prox_ind_range.hpp:37-50): projection onto the range
+    of the sparse matrix ``A``; ``AA`` = A^T A (dense) is computed here when not given."""
+
+    def __init__(self, ctx, index, size, diagsteps, A, AA=None):
+        import scipy.sparse as sp
+        super().__init__(ctx)
+        A = sp.csc_matrix(A)
+        A.sort_indices()
+        if AA is None:
+            AA = (A.T @ A).toarray()
+        val = _f32(A.data)
+        ptr = np.ascontiguousarray(A.indptr.astype(np.int32))
+        ind = np.ascontiguousarray(A.indices.astype(np.int32))
+        aa = np.ascontiguousarray(np.asarray(AA, dtype=np.float32).T).ravel()       # column-major
+        check(lib.pb_prox_create_ind_range(ctx._h, index, size, int(diagsteps), A.shape[0], A.shape[1], A.nnz, _fp(val),
+                                           ptr.ctypes.data_as(_capi.c_i32_p), ind.ctypes.data_as(_capi.c_i32_p),
+                                           _fp(aa), C.byref(self._h)))
+
+
 class ProxIndEpiConjQuad1D(Prox):
     """ProxIndEpiConjQuad1D (the north star's "ProxEpiConjQuadr"; source external to the reference tree, parity
     unpinned): per (x, y) pair the projection onto the epigraph of the conjugate of a u^2 + b u + c on

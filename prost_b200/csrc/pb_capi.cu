@@ -345,6 +345,10 @@ int pb_prox_create_spectral(pb_context* c, int kind, size_t index, size_t count,
                 pb::make_prox_spectral(&c->ctx, kind, index, count, dim, interleaved != 0, diagsteps != 0, function_1d,
                                        function_2d, coeffs, coeff_len)));
 }
+int pb_prox_create_ind_range(pb_context* c, size_t index, size_t size, int diagsteps, int m, int n, int nnz,
+                             const float* val, const int32_t* ptr, const int32_t* ind, const float* aa, pb_prox** out) {
+  PB_MAKE_PROX(pb::make_prox_ind_range(&c->ctx, index, size, diagsteps != 0, m, n, nnz, val, ptr, ind, aa));
+}
 int pb_prox_create_ind_epi_conjquad_1d(pb_context* c, size_t index, size_t count, int interleaved, int diagsteps,
                                        const float* const coeffs[5], const size_t coeff_len[5], pb_prox** out) {
   PB_MAKE_PROX((require(coeffs && coeff_len, "NULL coefficients"),

@@ -1,5 +1,6 @@
 // pb_prox.cu -- host-side prox objects and the unfused Prox::Eval path.
 #include "pb_prox.cuh"
+#include "pb_linop.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -719,6 +720,78 @@ class ProxIndEpiConjQuad1D : public ProxGroupProjection {
   DeviceBuffer<float> d_[5];
 };
 
+// ---- ProxIndRange (prox_ind_range.cu:28-300, prox_ind_range.hpp:37-50): projection onto the range of a sparse
+// m x n matrix A,  x = A (A^T A)^{-1} A^T x0,  with the dense AA = A^T A supplied by the caller.  tau is ignored.
+// The reference factors AA with cusolverDn potrf at Initialize and runs csrmv, potrs, csrmv per evaluation.  Here
+// (A^T A)^{-1} is formed ONCE on the host (Cholesky + triangular solves in double; AA is n x n with n in the
+// hundreds) and an evaluation is three fully parallel kernels: CSR SpMV with A^T, dense GEMV, CSR SpMV with A --
+// no sequential triangular solve on the device and no cuSOLVER / cuSPARSE dependency.
+class ProxIndRange : public Prox {
+ public:
+  ProxIndRange(Context* ctx, size_t index, size_t size, bool diagsteps, int m, int n, int nnz, const float* val,
+               const int32_t* ptr, const int32_t* ind, const float* aa)
+      : Prox(ctx, index, size, diagsteps), m_(m), n_(n) {
+    if (m < 0 || n < 0 || nnz < 0 || !ptr || (nnz > 0 && (!val || !ind)) || !aa)
+      fail(PB_ERR_INVALID, "ProxIndRange: bad matrix arguments");
+    if ((size_t)m != size) fail(PB_ERR_INVALID, "ProxIndRange: the number of rows of 'A' must equal the prox size");
+    if (n > 4096) fail(PB_ERR_UNSUPPORTED, "ProxIndRange: more than 4096 columns (host-side factorisation)");
+    // Cholesky AA = L L^T in double; same failure as an indefinite potrf
+    const size_t N = (size_t)n;
+    std::vector<double> L(N * N, 0.0);
+    for (size_t j = 0; j < N; ++j) {
+      double dsum = aa[j * N + j];
+      for (size_t k = 0; k < j; ++k) dsum -= L[j * N + k] * L[j * N + k];
+      if (!(dsum > 0.0)) fail(PB_ERR_INVALID, "ProxIndRange: matrix 'AA' is not positive definite");
+      const double ljj = std::sqrt(dsum);
+      L[j * N + j] = ljj;
+      for (size_t i = j + 1; i < N; ++i) {
+        double v = aa[j * N + i];                         // column-major, lower triangle: AA(i, j)
+        for (size_t k = 0; k < j; ++k) v -= L[i * N + k] * L[j * N + k];
+        L[i * N + j] = v / ljj;
+      }
+    }
+    // inverse by solving L L^T X = I column by column
+    std::vector<float> inv(N * N);
+    std::vector<double> col(N);
+    for (size_t c = 0; c < N; ++c) {
+      for (size_t i = 0; i < N; ++i) {                    // forward: L y = e_c
+        double v = i == c ? 1.0 : 0.0;
+        for (size_t k = 0; k < i; ++k) v -= L[i * N + k] * col[k];
+        col[i] = v / L[i * N + i];
+      }
+      for (size_t ii = N; ii-- > 0;) {                    // backward: L^T x = y
+        double v = col[ii];
+        for (size_t k = ii + 1; k < N; ++k) v -= L[k * N + ii] * col[k];
+        col[ii] = v / L[ii * N + ii];
+      }
+      for (size_t i = 0; i < N; ++i) inv[c * N + i] = static_cast<float>(col[i]);      // column-major
+    }
+    a_ = make_block_sparse_csc(ctx, 0, 0, m, n, nnz, val, ptr, ind);
+    inv_ = make_block_dense(ctx, 0, 0, N, N, inv.data());
+    t1_.resize(std::max<size_t>(N, 1));
+    t2_.resize(std::max<size_t>(N, 1));
+  }
+  int kind() const override { return kProxIndRange; }
+  size_t gpu_mem_amount() const override { return a_->gpu_mem_amount() + inv_->gpu_mem_amount() + 2 * (size_t)n_ * sizeof(float); }
+  void eval_local(float* res, const float* arg, const float*, float, bool) override {
+    ctx_->bind();
+    if (m_ == 0) return;
+    cudaStream_t s = ctx_->stream;
+    PB_CUDA(cudaMemsetAsync(t1_.data(), 0, (size_t)n_ * sizeof(float), s));
+    PB_CUDA(cudaMemsetAsync(t2_.data(), 0, (size_t)n_ * sizeof(float), s));
+    PB_CUDA(cudaMemsetAsync(res, 0, (size_t)m_ * sizeof(float), s));
+    if (n_ == 0) return;
+    a_->eval_adjoint_local_add(t1_.data(), arg);          // A^T x0
+    inv_->eval_local_add(t2_.data(), t1_.data());         // (A^T A)^{-1} .
+    a_->eval_local_add(res, t2_.data());                  // A .
+  }
+
+ private:
+  int m_, n_;
+  std::shared_ptr<Block> a_, inv_;
+  DeviceBuffer<float> t1_, t2_;
+};
+
 // ---- ProxTransform (prox_transform.cu:27-226): prox of  c f(a x - b) + <d, x> + (e/2)|x|^2  through the prox of f.
 // Same three element-wise steps around the inner prox as the reference, same float expressions.
 struct TransformCoeffs {
@@ -882,6 +955,11 @@ std::shared_ptr<Prox> make_prox_ind_sum_indexed(Context* ctx, size_t index, size
 std::shared_ptr<Prox> make_prox_ind_epi_conjquad_1d(Context* ctx, size_t index, size_t count, bool interleaved,
                                                     bool diagsteps, const float* const coeffs[5], const size_t len[5]) {
   return std::make_shared<ProxIndEpiConjQuad1D>(ctx, index, count, interleaved, diagsteps, coeffs, len);
+}
+
+std::shared_ptr<Prox> make_prox_ind_range(Context* ctx, size_t index, size_t size, bool diagsteps, int m, int n, int nnz,
+                                          const float* val, const int32_t* ptr, const int32_t* ind, const float* aa) {
+  return std::make_shared<ProxIndRange>(ctx, index, size, diagsteps, m, n, nnz, val, ptr, ind, aa);
 }
 
 std::shared_ptr<Prox> make_prox_ind_halfspace(Context* ctx, size_t index, size_t count, size_t dim, bool interleaved,

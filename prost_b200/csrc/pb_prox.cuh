@@ -32,6 +32,7 @@ enum ProxKind : int {
   kProxIndSumIndexed = 11,
   kProxIndEpiConjQuad1D = 12,
   kProxSpectral = 13,
+  kProxIndRange = 14,
 };
 
 // per-element vector or scalar (ElemOpCoefficients: prox_elem_operation.hpp:104-109)
@@ -380,6 +381,10 @@ std::shared_ptr<Prox> make_prox_ind_sum_indexed(Context* ctx, size_t index, size
 std::shared_ptr<Prox> make_prox_spectral(Context* ctx, int kind, size_t index, size_t count, size_t dim,
                                          bool interleaved, bool diagsteps, int function_1d, int function_2d,
                                          const float* const coeffs[7], const size_t coeff_len[7]);
+// ProxIndRange (prox_ind_range.hpp:37-50): projection onto the range of a sparse m x n matrix A given as CSC, with the
+// dense column-major AA = A^T A
+std::shared_ptr<Prox> make_prox_ind_range(Context* ctx, size_t index, size_t size, bool diagsteps, int m, int n, int nnz,
+                                          const float* val, const int32_t* ptr, const int32_t* ind, const float* aa);
 // ProxIndEpiConjQuad1D (external to the reference tree, cmake/CustomSources.cmake.example:8-14; parity unpinned):
 // projection of (x, y) pairs onto the epigraph of the conjugate of a u^2 + b u + c restricted to [alpha, beta]
 std::shared_ptr<Prox> make_prox_ind_epi_conjquad_1d(Context* ctx, size_t index, size_t count, bool interleaved,

@@ -14,6 +14,7 @@ reference's mex registry names and argument order (matlab/+prost/private/factory
   ind_epi_quad                                         : [count, dim, interleaved, [a, b, c]]
   ind_sum                                              : [dim, inds, sum(, dim2, inds2, sum2)]
   ind_epi_conjquad_1d                                  : [count, interleaved, [a, b, c, alpha, beta]]
+  ind_range                                            : [A (sparse), AA (dense A^T A)]
   ind_halfspace                                        : [count, dim, interleaved, [a, b]]
   ind_soc                                              : [count, dim, interleaved, alpha]
   moreau                                               : [child description]
@@ -58,6 +59,8 @@ def create_prox(ctx, desc):
     if name == "ind_epi_conjquad_1d":      # [count, interleaved, [a, b, c, alpha, beta]]  (source external, see api)
         count, interleaved, (a, b, c, alpha, beta) = data
         return api.ProxIndEpiConjQuad1D(ctx, idx, count, interleaved, diagsteps, a, b, c, alpha, beta)
+    if name == "ind_range":                # +function/ind_range.m: { A, AA }
+        return api.ProxIndRange(ctx, idx, size, diagsteps, data[0], data[1] if len(data) > 1 else None)
     if name == "ind_halfspace":
         count, dim, interleaved, (a, b) = data
         return api.ProxIndHalfspace(ctx, idx, count, dim, interleaved, diagsteps, a, b)

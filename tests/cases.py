@@ -259,6 +259,16 @@ def prox_spectral_cases(small=False):
     return cases
 
 
+def prox_ind_range_cases(small=False):
+    """ind_range (prox_ind_range.cu; test_prox_ind_range.m: A = sprandn(500, 250, 0.1), AA = A' * A)."""
+    m, n = (500, 250) if not small else (60, 25)
+    A = sp.random(m, n, density=0.1, random_state=7, format="csc", dtype=np.float32)
+    A.data = rng(73).standard_normal(A.nnz).astype(np.float32)
+    AA = (A.T @ A).toarray().astype(np.float32)
+    return {"ind_range": (("ind_range", 0, m, False, [A, AA]), m),
+            "ind_range_offset": (("ind_range", 11, m, False, [A, AA]), m + 20)}
+
+
 def prox_epi_conjquad_cases(small=False):
     """ind_epi_conjquad_1d (the north star's ProxEpiConjQuadr; parity unpinned, see prost_b200/csrc/pb_prox.cu):
     (x, y) pairs against the conjugate of a u^2 + b u + c on [alpha, beta]: per-pair and scalar coefficients, planar
@@ -305,6 +315,7 @@ def all_prox_cases(small=False):
     out.update(prox_ind_sum_cases(small))
     out.update(prox_ind_sum_indexed_cases(small))
     out.update(prox_spectral_cases(small))
+    out.update(prox_ind_range_cases(small))
     out.update(prox_projection_cases(small))
     return out
 

@@ -46,6 +46,8 @@ lib.orc_prox_ind_sum_indexed.argtypes = [C.c_void_p, sz, sz, sz, sz, C.POINTER(C
                                          C.POINTER(C.c_ulonglong), C.c_float]
 lib.orc_prox_spectral.argtypes = [C.c_void_p, C.c_int, sz, sz, sz, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(fp),
                                   C.POINTER(sz)]
+lib.orc_prox_ind_range.argtypes = [C.c_void_p, sz, sz, C.c_int, C.c_int, C.c_int, C.c_int, fp, C.POINTER(C.c_int),
+                                   C.POINTER(C.c_int), fp]
 lib.orc_prox_ind_epi_conjquad_1d.argtypes = [C.c_void_p, sz, sz, C.c_int, C.c_int, C.POINTER(fp), C.POINTER(sz)]
 lib.orc_prox_ind_halfspace.argtypes = [C.c_void_p, sz, sz, sz, C.c_int, C.c_int, fp, sz, fp, sz]
 lib.orc_prox_ind_soc.argtypes = [C.c_void_p, sz, sz, sz, C.c_int, C.c_int]
@@ -211,6 +213,18 @@ class OracleProblem:
             ptrs = (fp * 7)(*[_p(a) for a in arrs])
             lens = (sz * 7)(*[a.size for a in arrs])
             return lib.orc_prox_spectral(self.h, kind_id, idx, count, dim, int(il), int(diagsteps), 0, 0, ptrs, lens)
+        if name == "ind_range":
+            import scipy.sparse as sp
+            A = sp.csc_matrix(data[0])
+            A.sort_indices()
+            AA = np.asarray(data[1] if len(data) > 1 and data[1] is not None else (A.T @ A).toarray(), np.float32)
+            val = _f32(A.data)
+            ptr = np.ascontiguousarray(A.indptr.astype(np.int32))
+            ix = np.ascontiguousarray(A.indices.astype(np.int32))
+            aa = np.ascontiguousarray(AA.T).ravel()
+            ip = C.POINTER(C.c_int)
+            return lib.orc_prox_ind_range(self.h, idx, size, int(diagsteps), A.shape[0], A.shape[1], A.nnz, _p(val),
+                                          ptr.ctypes.data_as(ip), ix.ctypes.data_as(ip), _p(aa))
         if name == "ind_epi_conjquad_1d":
             count, il, coeffs = data
             arrs = [_f32(np.atleast_1d(c)) for c in coeffs]

@@ -105,6 +105,16 @@ class _Writer:
         if name == "ind_soc":
             count, dim, il = data[:3]
             return f"soc {idx} {count} {dim} {int(il)} {int(ds)} {float(data[3]) if len(data) > 3 else 1.0!r}"
+        if name == "ind_range":
+            import scipy.sparse as sp
+            A = sp.csc_matrix(data[0])
+            A.sort_indices()
+            AA = np.asarray(data[1] if len(data) > 1 and data[1] is not None else (A.T @ A).toarray(), np.float32)
+            fv, _ = self.arr(A.data, np.float32)
+            fp, _ = self.arr(A.indptr, np.int32)
+            fi, _ = self.arr(A.indices, np.int32)
+            fa, _ = self.arr(np.ascontiguousarray(AA.T), np.float32)
+            return f"indrange {idx} {size} {int(ds)} {A.shape[0]} {A.shape[1]} {A.nnz} {fv} {fp} {fi} {fa}"
         if name == "ind_sum":
             parts = [f"indsumidx {idx} {size} {len(data) // 3}"]
             for k in range(0, len(data), 3):

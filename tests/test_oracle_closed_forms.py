@@ -412,3 +412,17 @@ def test_spectral_proxes_match_numpy_closed_forms():
         lo, hi = desc[1], desc[1] + desc[2]
         want = _spectral_closed_form(desc, arg)
         assert np.abs(res[lo:hi] - want).max() <= 1e-4 * max(1.0, np.abs(want).max()), name
+
+
+def test_prox_ind_range_is_the_orthogonal_projection_onto_the_range():
+    """test_prox_ind_range.m: res == A * (L \\ (L' \\ (A' * arg))) at 1e-4 (norm); also idempotent and the residual is
+    orthogonal to the range."""
+    r = np.random.default_rng(29)
+    for name, (desc, n) in cases.prox_ind_range_cases(small=True).items():
+        A = desc[4][0].toarray().astype(np.float64)
+        lo, hi = desc[1], desc[1] + desc[2]
+        arg = r.standard_normal(n).astype(np.float32)
+        res = oracle_prox_eval(desc, arg, np.ones(n, np.float32), 1.0)
+        want = A @ np.linalg.solve(A.T @ A, A.T @ arg[lo:hi].astype(np.float64))
+        assert np.linalg.norm(res[lo:hi] - want) <= 1e-4 * max(1.0, np.linalg.norm(want)), name
+        assert np.abs(A.T @ (arg[lo:hi] - res[lo:hi])).max() <= 1e-3, name

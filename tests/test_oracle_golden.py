@@ -51,6 +51,10 @@ def test_oracle_prox_matches_reference(path):
     res = oracle_prox_eval(desc, g["arg"], g["tau_diag"], float(g["tau"]))
     lo, hi = desc[1], desc[1] + desc[2]
     jumpy = any(k in name for k in ("l0", "truncquad", "trunclin", "lq"))
+    if name.startswith("ind_range"):      # float potrf / potrs in the reference: test_prox_ind_range.m's own 1e-4 (norm)
+        want = g["res"][lo:hi]
+        assert np.linalg.norm(res[lo:hi] - want) <= 1e-4 * max(1.0, float(np.linalg.norm(want))), name
+        return
     bad = frac_bad(res[lo:hi], g["res"][lo:hi], 2e-5)
     assert bad <= (1e-2 if jumpy else 0.0), (name, bad)
 

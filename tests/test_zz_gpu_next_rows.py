@@ -158,6 +158,29 @@ def test_spectral_prox_matches_oracle_and_reference(ctx, name):
         assert np.abs(got[lo:hi] - ref[lo:hi]).max() <= 2e-5 * scale, name
 
 
+# ---- ind_range: projection onto the range of a sparse matrix ------------------------------
+RANGE_CASES = cases.prox_ind_range_cases()
+
+
+@pytest.mark.parametrize("name", sorted(RANGE_CASES))
+def test_ind_range_matches_oracle_closed_form_and_reference(ctx, name):
+    """x = A (A^T A)^{-1} A^T x0: three parallel kernels around a host-side inverse here, csrmv + potrs + csrmv in the
+    reference; test_prox_ind_range.m's closed form at its 1e-4 (norm), oracle and live reference likewise."""
+    desc, n = RANGE_CASES[name]
+    arg, tau_diag, tau = _inputs(name, n)
+    got = pb.create_prox(ctx, desc).Eval(arg, tau_diag, tau)
+    lo, hi = desc[1], desc[1] + desc[2]
+    A = desc[4][0].toarray().astype(np.float64)
+    want = A @ np.linalg.solve(A.T @ A, A.T @ arg[lo:hi].astype(np.float64))
+    scale = max(1.0, float(np.linalg.norm(want)))
+    assert np.linalg.norm(got[lo:hi] - want) <= 1e-4 * scale, name
+    orc = oracle_prox_eval(desc, arg, tau_diag, tau)
+    assert np.linalg.norm(got[lo:hi] - orc[lo:hi]) <= 1e-4 * scale, name
+    if ref_driver.available():
+        ref = ref_driver.run_prox(desc, arg, tau_diag, tau)
+        assert np.linalg.norm(got[lo:hi] - ref[lo:hi]) <= 1e-4 * scale, name
+
+
 # ---- ind_epi_conjquad_1d: the north star's ProxEpiConjQuadr (source external to the reference tree) -------------
 CONJ_CASES = cases.prox_epi_conjquad_cases()
 
