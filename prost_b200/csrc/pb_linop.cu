@@ -625,6 +625,14 @@ class BlockDenseKron : public Block {
     cudaStream_t st = ctx_->stream;
     const float* K = d_data_.data();
     const int* skip = ctx_->skip_flag;
+    if (KronTensorCore::supported(id_first_, n_out, n_in, d_, res, rhs)) {
+      KronTensorCore::Packed& f = tc_[transpose ? 1 : 0];
+      if (!f.ready) KronTensorCore::pack(ctx_, host_.data(), n_out, n_in, so, si, f);
+      KronTensorCore::launch(ctx_, id_first_, f, res, rhs, n_out, n_in, d_, set);
+      PB_CHECK_LAUNCH();
+      ctx_->launches++;
+      return;
+    }
     if (!id_first_) {
       const bool vec4 = d_ % 4 == 0 && ((reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(rhs)) & 15u) == 0;
       const size_t threads = vec4 ? d_ / 4 : d_;
@@ -666,6 +674,7 @@ class BlockDenseKron : public Block {
   size_t d_, mr_, mc_;
   std::vector<float> host_;
   DeviceBuffer<float> d_data_;
+  KronTensorCore::Packed tc_[2];      // forward / adjoint factor for the tensor-core path, packed on first use
 };
 
 // ---- the same products for a sparse factor (block_sparse_kron_id.cu:28-52, block_id_kron_sparse.cu) -------

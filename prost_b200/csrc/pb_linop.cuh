@@ -216,6 +216,23 @@ std::shared_ptr<Block> make_block_sparse_kron(Context* ctx, bool id_first, size_
 std::shared_ptr<Block> make_block_zero(Context* ctx, size_t row, size_t col, size_t nrows,
                                        size_t ncols);
 
+// Dense Kronecker products on the tensor cores (pb_kron_tc.cu): tcgen05.mma kind::tf32 with the 3 x TF32 split,
+// accumulators in TMEM.  `supported` decides per call (factor shape, alignment); BlockDenseKron falls back to its
+// fp32 kernels otherwise.
+struct KronTensorCore {
+  struct Packed {               // hi / lo parts of the factor in the shared-memory operand layout, zero padded
+    DeviceBuffer<float> hi, lo;
+    uint32_t n_pad = 0, k_pad = 0;
+    bool ready = false;
+  };
+  static bool supported(bool id_first, uint32_t n_out, uint32_t n_in, size_t d, const float* res, const float* rhs);
+  static size_t smem_bytes(bool id_first, uint32_t n_out, uint32_t n_pad, uint32_t k_pad);
+  // factor entries K(o, i) = k[o * so + i * si] (host memory)
+  static void pack(Context* ctx, const float* k, uint32_t n_out, uint32_t n_in, uint32_t so, uint32_t si, Packed& out);
+  static void launch(Context* ctx, bool id_first, const Packed& f, float* res, const float* rhs, uint32_t n_out,
+                     uint32_t n_in, size_t d, bool set);
+};
+
 // LinearOperator: include/prost/linop/linearoperator.hpp:36-90
 class LinearOperator {
  public:

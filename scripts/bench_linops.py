@@ -86,6 +86,8 @@ def main():
         time_op(f"dense_kron_id_16x32_d{npix}", [("dense_kron_id", 0, 0, [Kd, npix])], 0)
         time_op(f"id_kron_dense_16x32_d{npix}", [("id_kron_dense", 0, 0, [Kd, npix])], 0)
         time_op(f"dense_kron_id_64x64_d{npix // 4}", [("dense_kron_id", 0, 0, [K64, npix // 4])], 0)
+        time_op(f"dense_kron_id_64x64_d{npix}", [("dense_kron_id", 0, 0, [K64, npix])], 0)
+        time_op(f"id_kron_dense_64x64_d{npix}", [("id_kron_dense", 0, 0, [K64, npix])], 0)
     print(json.dumps({"peak_GBps": peak, "ops": out}), flush=True)
 
 

@@ -259,6 +259,44 @@ def prox_spectral_cases(small=False):
     return cases
 
 
+def linop_kron_tensor_core_cases():
+    """Dense Kronecker factors large enough for the tcgen05 path (pb_kron_tc.cu: n_in * n_out >= 512, n_in <= 64):
+    padding of both factor dimensions, tail tiles, more tiles than SMs, overlapping blocks (accumulating stores)."""
+    r = rng(43)
+    g = lambda m, n: r.standard_normal((m, n)).astype(np.float32)
+    K16 = g(16, 32)
+    return {
+        "dense_kron_id_64x64_d1000": [("dense_kron_id", 0, 0, [g(64, 64), 1000])],
+        "dense_kron_id_24x40_d516": [("dense_kron_id", 0, 0, [g(24, 40), 516])],
+        "dense_kron_id_130x27_d2052": [("dense_kron_id", 0, 0, [g(130, 27), 2052])],
+        "dense_kron_id_64x64_d57012": [("dense_kron_id", 0, 0, [g(64, 64), 57012])],
+        "dense_kron_id_16x32_2x2": [("dense_kron_id", rr * 16 * 260, cc * 32 * 260, [K16, 260]) for rr in (0, 1) for cc in (0, 1)],
+        "id_kron_dense_64x64_d1000": [("id_kron_dense", 0, 0, [g(64, 64), 1000])],
+        "id_kron_dense_20x36_d517": [("id_kron_dense", 0, 0, [g(20, 36), 517])],
+        "id_kron_dense_18x44_d300": [("id_kron_dense", 0, 0, [g(18, 44), 300])],
+        "id_kron_dense_64x64_d57013": [("id_kron_dense", 0, 0, [g(64, 64), 57013])],
+        "id_kron_dense_16x32_2x2": [("id_kron_dense", rr * 16 * 260, cc * 32 * 260, [K16, 260]) for rr in (0, 1) for cc in (0, 1)],
+    }
+
+
+def kron_apply_f64(blocks, v, transpose):
+    """Float64 product of a list of dense Kronecker blocks without forming the Kronecker matrix."""
+    m = max(row + K.shape[0] * d for (_, row, col, (K, d)) in blocks)
+    n = max(col + K.shape[1] * d for (_, row, col, (K, d)) in blocks)
+    out = np.zeros(n if transpose else m)
+    for (name, row, col, (K, d)) in blocks:
+        K = K.astype(np.float64)
+        A = K.T if transpose else K
+        src0, dst0 = (row, col) if transpose else (col, row)
+        seg = v[src0:src0 + A.shape[1] * d].astype(np.float64)
+        if name.startswith("id_"):
+            res = (seg.reshape(d, A.shape[1]) @ A.T).reshape(-1)
+        else:
+            res = (A @ seg.reshape(A.shape[1], d)).reshape(-1)
+        out[dst0:dst0 + res.size] += res
+    return out
+
+
 def prox_ind_range_cases(small=False):
     """ind_range (prox_ind_range.cu; test_prox_ind_range.m: A = sprandn(500, 250, 0.1), AA = A' * A)."""
     m, n = (500, 250) if not small else (60, 25)

@@ -158,6 +158,33 @@ def test_spectral_prox_matches_oracle_and_reference(ctx, name):
         assert np.abs(got[lo:hi] - ref[lo:hi]).max() <= 2e-5 * scale, name
 
 
+KRON_TC_CASES = cases.linop_kron_tensor_core_cases()
+
+
+@pytest.mark.parametrize("name", sorted(KRON_TC_CASES))
+def test_kron_tensor_core_path_keeps_fp32_parity(ctx, name):
+    """pb_kron_tc.cu: tcgen05 kind::tf32 with the 3 x TF32 split.  Same 1e-5 (max norm) as the fp32 kernels, against a
+    float64 product, the oracle and the live reference; forward, adjoint, overwrite and accumulate."""
+    from oracle_binding import OracleProblem
+    blocks = KRON_TC_CASES[name]
+    op = pb.create_linop(ctx, blocks)
+    m, n = op.nrows, op.ncols
+    r = np.random.default_rng(zlib.crc32(name.encode()))
+    x, y = r.standard_normal(n).astype(np.float32), r.standard_normal(m).astype(np.float32)
+    fwd, adj = op.Eval(x), op.EvalAdjoint(y)
+    wf, wa = cases.kron_apply_f64(blocks, x, False), cases.kron_apply_f64(blocks, y, True)
+    assert np.abs(fwd - wf).max() <= 1e-5 * max(1.0, float(np.abs(wf).max())), (name, np.abs(fwd - wf).max())
+    assert np.abs(adj - wa).max() <= 1e-5 * max(1.0, float(np.abs(wa).max())), (name, np.abs(adj - wa).max())
+    orc = OracleProblem(blocks=blocks)
+    assert np.abs(fwd - orc.linop(x, False)).max() <= 1e-5 * max(1.0, float(np.abs(wf).max())), name
+    assert np.abs(adj - orc.linop(y, True)).max() <= 1e-5 * max(1.0, float(np.abs(wa).max())), name
+    if ref_driver.available():
+        ref_f = ref_driver.run_linop(blocks, x, False)["res"]
+        ref_a = ref_driver.run_linop(blocks, y, True)["res"]
+        assert np.abs(fwd - ref_f).max() <= 1e-5 * max(1.0, float(np.abs(ref_f).max())), name
+        assert np.abs(adj - ref_a).max() <= 1e-5 * max(1.0, float(np.abs(ref_a).max())), name
+
+
 # ---- ind_range: projection onto the range of a sparse matrix (SURVEY.md 8(f) row 4) ------------------------------
 RANGE_CASES = cases.prox_ind_range_cases()
 
