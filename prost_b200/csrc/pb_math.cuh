@@ -191,31 +191,54 @@ __device__ __forceinline__ float elem1d_apply(int fn, float arg, float tau_scal,
 
 // ---- projection onto the epigraph of y >= alpha ||x||^2 (helper.hpp:44-105) ----------------
 // Returns the scale s such that x = s * x0 and writes y; `passthrough` is set when the
-// point is already inside (then x = x0, y = y0 exactly).  The reference evaluates the cubic
-// in T=float with double literals; the same mixed arithmetic is kept.
+// point is already inside (then x = x0, y = y0 exactly).
+//
+// Same cubic, same branches as the reference (Cardano for a non-negative discriminant, the trigonometric form
+// otherwise).  The reference evaluates it in float with powf(., 1.5), powf(., 1/3) and double-precision divisions;
+// that is ~300 issue slots per point and made the identity-row pass of the lifting config compute bound
+// (profiles/r02_lifting.md).  Here: t sqrtf(t) for t^1.5 and cbrtf for the cube root (both at least as accurate as
+// powf: <= 1 ulp), the exact float product for 2 alpha |x| (a double product of two floats rounded to float IS the
+// float product), one double multiply by 1/3 instead of the double division.  Differences against the reference's
+// expressions are of the order of one float ulp of v (tests: 1e-5 on iterates, 2e-5 on the projection itself).
 __device__ inline void project_epi_quad(float sq_norm_x0, float y0, float alpha, float& v_out,
                                         bool& inside) {
   inside = (y0 >= alpha * sq_norm_x0);
   v_out = 0.f;
   if (inside) return;
   const float norm_x0 = sqrtf(sq_norm_x0);
-  const float a = static_cast<float>(2.0 * static_cast<double>(alpha) * static_cast<double>(norm_x0));
+  const float a = __fmul_rn(2.f * alpha, norm_x0);
   const float b = static_cast<float>(
-      2.0 * (1.0 - 2.0 * static_cast<double>(alpha) * static_cast<double>(y0)) / 3.0);
-  float d, v;
+      (2.0 - 4.0 * static_cast<double>(alpha) * static_cast<double>(y0)) * (1.0 / 3.0));
+  float d, v, sq = 0.f;
   if (b < 0) {
-    const float sq = powf(-b, 1.5f);
+    sq = -b * sqrtf(-b);
     d = (a - sq) * (a + sq);
   } else {
     d = a * a + b * b * b;
   }
   if (d >= 0) {
-    const float c = powf(a + sqrtf(d), static_cast<float>(1. / 3.));
-    v = (static_cast<double>(fabsf(c)) > 1e-6) ? c - b / c : 0.f;
+    const float c = cbrtf(a + sqrtf(d));
+    v = (fabsf(c) > 1e-6f) ? c - b / c : 0.f;
   } else {
-    v = 2 * sqrtf(-b) * cosf(acosf(a / powf(-b, 1.5f)) / 3.f);
+    v = 2 * sqrtf(-b) * cosf(acosf(a / sq) * (1.f / 3.f));
   }
   v_out = v;
 }
+
+// x / d for a divisor that is used several times: when d is a power of two the quotient is the exact product with
+// 1 / d (built from the exponent bits), otherwise the IEEE division.  Bit-identical to x / d either way.
+struct SharedDivisor {
+  float d, r;
+  bool pow2;
+  __device__ __forceinline__ explicit SharedDivisor(float dv) : d(dv) {
+    const uint32_t bits = __float_as_uint(dv), e = (bits >> 23) & 0xffu;
+    pow2 = (bits & 0x007fffffu) == 0u && e >= 2u && e <= 252u;
+    r = __uint_as_float((bits & 0x80000000u) | ((254u - e) << 23));
+  }
+  __device__ __forceinline__ float operator()(float x) const { return pow2 ? x * r : x / d; }
+  __device__ __forceinline__ double quotient(double x) const {
+    return pow2 ? x * static_cast<double>(r) : x / static_cast<double>(d);
+  }
+};
 
 }  // namespace pb

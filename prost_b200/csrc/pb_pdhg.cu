@@ -198,6 +198,8 @@ __global__ void __launch_bounds__(kBlock) z_variable_kernel(float* __restrict__ 
 // per-tile release fences sit on the tile pipeline's critical path; PB_RING_ITERS=n enables them for experiments.
 constexpr int kRingItersDefault = 0;
 
+constexpr int kOverlapIdentityDefault = 0;
+
 class BackendPDHG : public Backend {
  public:
   BackendPDHG(Context* ctx, std::shared_ptr<Problem> prob, const pb_pdhg_options& opts,
@@ -206,6 +208,12 @@ class BackendPDHG : public Backend {
     if (opts_.residual_iter == 0) fail(PB_ERR_INVALID, "residual_iter must not be 0");
     if (opts_.stepsize_variant < PB_PDHG_ALG1 || opts_.stepsize_variant > PB_PDHG_BOYD)
       fail(PB_ERR_INVALID, "unknown PDHG step size variant");
+  }
+
+  ~BackendPDHG() override {
+    if (fork_ev_) cudaEventDestroy(fork_ev_);
+    if (join_ev_) cudaEventDestroy(join_ev_);
+    if (side_stream_) cudaStreamDestroy(side_stream_);
   }
 
   void initialize(const float* h_x0, size_t nx0, const float* h_y0, size_t ny0) override;
@@ -257,6 +265,10 @@ class BackendPDHG : public Backend {
   bool plan_fused();
   void iteration_fused();
   cudaEvent_t* prof_ev_ = nullptr;     // 4 events when profiling, else null
+  // identity-row dual pass beside the gradient-row pass (0 = off, else CTAs per SM for the identity pass)
+  int overlap_identity_ = 0;
+  cudaStream_t side_stream_ = nullptr;
+  cudaEvent_t fork_ev_ = nullptr, join_ev_ = nullptr;
   void iteration_unfused();
   PdhgState fetch_state();
   unsigned sgrid(size_t n) const { return (unsigned)std::min<size_t>(grid_for(n), (size_t)ctx_->num_sms * 32); }
@@ -331,6 +343,16 @@ void BackendPDHG::initialize(const float* h_x0, size_t nx0, const float* h_y0, s
 
   iteration_ = 0;
   halo_in_ll_ = false;
+  {
+    // PB_OVERLAP_IDENTITY: CTAs per SM of the identity-row pass while it runs beside the gradient-row pass (0: off)
+    static const int want = [] { const char* e = getenv("PB_OVERLAP_IDENTITY"); return e ? atoi(e) : kOverlapIdentityDefault; }();
+    overlap_identity_ = want > 0 ? want : 0;
+    if (overlap_identity_ && !side_stream_) {
+      PB_CUDA(cudaStreamCreateWithFlags(&side_stream_, cudaStreamNonBlocking));
+      PB_CUDA(cudaEventCreateWithFlags(&fork_ev_, cudaEventDisableTiming));
+      PB_CUDA(cudaEventCreateWithFlags(&join_ev_, cudaEventDisableTiming));
+    }
+  }
   PdhgState st{};
   st.tau = static_cast<float>(opts_.tau0);
   st.sigma = static_cast<float>(opts_.sigma0);
@@ -598,7 +620,32 @@ void BackendPDHG::iteration_fused() {
     if (prof_ev_) PB_CUDA(cudaEventRecord(prof_ev_[1], ctx_->stream));
 
     // dual pass: y_prev_ <- prox_f*(y_ + sigma S K(2x^{k+1} - x^k)) (theta-extrapolated), then swap
+    // Gradient rows + identity rows (the lifting config): the identity-row pass is bound by the arithmetic of its
+    // prox (epigraph projection), the gradient-row pass by HBM; they write disjoint rows of y.  On plain iterations
+    // the identity pass goes first, on a second stream with a few CTAs per SM, and the gradient pass fills the rest
+    // of every SM: the two run side by side instead of back to back (profiles/r02_lifting.md).
     off = 0;
+    const bool side_by_side = overlap_identity_ && !check && !prof_ev_ && f_descs_.size() == 2 && stencil_.ok &&
+                              stencil_.geom.has_id && f_descs_[1].index == stencil_.geom.id_row;
+    if (side_by_side) {
+      cudaStream_t main = ctx_->stream;
+      PB_CUDA(cudaEventRecord(fork_ev_, main));
+      PB_CUDA(cudaStreamWaitEvent(side_stream_, fork_ev_, 0));
+      ctx_->stream = side_stream_;
+      ctx_->identity_ctas_per_sm = overlap_identity_;
+      const unsigned gi = stencil_dual_launch(ctx_, stencil_, f_descs_[1], y_.data(), x_.data(), x_prev_.data(),
+                                              f_scale_[1], st, iteration_ == 0, false, part_p_.data(), y_prev_.data());
+      ctx_->identity_ctas_per_sm = 0;
+      ctx_->stream = main;
+      if (gi == 0) fail(PB_ERR_UNSUPPORTED, "identity-row pass not launched");
+      PB_CUDA(cudaEventRecord(join_ev_, side_stream_));
+      const unsigned gg = stencil_dual_launch(ctx_, stencil_, f_descs_[0], y_.data(), x_.data(), x_prev_.data(),
+                                              f_scale_[0], st, iteration_ == 0, false, part_p_.data(), y_prev_.data());
+      if (gg == 0)
+        fused_dual_launch(ctx_, f_descs_[0], blocks_, y_.data(), x_.data(), x_prev_.data(), f_scale_[0], st,
+                          iteration_ == 0, false, part_p_.data(), y_prev_.data());
+      PB_CUDA(cudaStreamWaitEvent(main, join_ev_, 0));
+    } else
     for (size_t i = 0; i < f_descs_.size(); ++i) {
       const ProxDesc& d = f_descs_[i];
       const ScaleRef Sd = f_scale_[i];

@@ -192,21 +192,23 @@ __device__ __forceinline__ void leaf_apply(const ProxDesc& p, uint32_t tx, float
       // components 0..dim-2 are x, component dim-1 is y.
       const float a = p.epi_a ? __ldg(p.epi_a + tx) : p.epi_a_val;
       const float c = p.epi_c ? __ldg(p.epi_c + tx) : p.epi_c_val;
+      const SharedDivisor by_2a(2 * a);       // b / (2a), v / (2a), sqb / (4a): exact reciprocal when a is 2^k
       float bb[CAP];
       float sqb = 0.f, sqx = 0.f, y0 = 0.f;
 #pragma unroll
       for (int i = 0; i < CAP; ++i) {
         bb[i] = 0.f;
         if (i < (int)dim - 1) {
-          bb[i] = __ldg(p.epi_b + tx + (size_t)p.count * i);
-          v[i] = v[i] + bb[i] / (2 * a);
-          sqb += bb[i] * bb[i];
+          const float b = __ldg(p.epi_b + tx + (size_t)p.count * i);
+          bb[i] = by_2a(b);
+          v[i] = v[i] + bb[i];
+          sqb += b * b;
           sqx += v[i] * v[i];
         } else if (i == (int)dim - 1) {
           y0 = v[i];
         }
       }
-      const float shift = sqb / (4 * a);
+      const float shift = by_2a.pow2 ? sqb * (0.5f * by_2a.r) : sqb / (4 * a);
       const float ys = y0 - c + shift;
       float vv;
       bool inside;
@@ -217,7 +219,7 @@ __device__ __forceinline__ void leaf_apply(const ProxDesc& p, uint32_t tx, float
       } else {
         const float norm = sqrtf(sqx);
         float sq_new = 0.f;
-        const double scale = static_cast<double>(vv) / (2.0 * static_cast<double>(a));
+        const double scale = by_2a.quotient(static_cast<double>(vv));
 #pragma unroll
         for (int i = 0; i < CAP; ++i)
           if (i < (int)dim - 1) {
@@ -228,7 +230,7 @@ __device__ __forceinline__ void leaf_apply(const ProxDesc& p, uint32_t tx, float
       }
 #pragma unroll
       for (int i = 0; i < CAP; ++i) {
-        if (i < (int)dim - 1) v[i] -= bb[i] / (2 * a);
+        if (i < (int)dim - 1) v[i] -= bb[i];
         else if (i == (int)dim - 1) v[i] = y + c - shift;
       }
       break;
