@@ -53,8 +53,12 @@ __global__ void __launch_bounds__(kBlock) csr_spmv_add_kernel(const int* __restr
   }
 }
 
-// CSR SpMV for short rows: `kGroup` lanes per row.
-template <int kGroup>
+// CSR SpMV for short rows: `kGroup` lanes per row, two rows per group and step.  With uniformly random columns the
+// kernel is bound by the L2 gather of x (one 32-byte sector per nonzero, profiles/r02_operators.md), i.e. by how many
+// gathers are in flight: a lane loads the (column, value) pairs of up to kUnroll of its entries of BOTH rows before
+// the first gather is issued, so 2 * kUnroll independent gathers leave each thread back to back (round 1's form had
+// one dependent ptr -> ind -> x chain per thread).
+template <int kGroup, int kUnroll>
 __global__ void __launch_bounds__(kBlock) csr_spmv_add_group_kernel(
     const int* __restrict__ ptr, const int* __restrict__ ind, const float* __restrict__ val,
     uint32_t nrows, float* __restrict__ res, const float* __restrict__ x, float sign,
@@ -64,17 +68,47 @@ __global__ void __launch_bounds__(kBlock) csr_spmv_add_group_kernel(
   const uint32_t groups_per_grid = (gridDim.x * blockDim.x) / kGroup;
   // all lanes of a warp iterate the same number of times so the shuffles stay converged
   const uint32_t first = (blockIdx.x * blockDim.x + threadIdx.x) / kGroup;
-  const uint32_t iters = (nrows + groups_per_grid - 1) / groups_per_grid;
+  const uint32_t iters = (nrows + 2 * groups_per_grid - 1) / (2 * groups_per_grid);
   for (uint32_t it = 0; it < iters; ++it) {
-    const uint32_t r = first + it * groups_per_grid;
-    float acc = 0.f;
-    if (r < nrows) {
-      const int beg = ptr[r], end = ptr[r + 1];
-      for (int k = beg + sub; k < end; k += kGroup) acc += val[k] * __ldg(x + ind[k]);
-    }
+    uint32_t r[2];
+    int k[2], end[2];
+    float acc[2] = {0.f, 0.f}, old[2] = {0.f, 0.f};
 #pragma unroll
-    for (int o = kGroup / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, kGroup);
-    if (sub == 0 && r < nrows) res[r] += sign * acc;
+    for (int j = 0; j < 2; ++j) {
+      r[j] = first + (2 * it + j) * groups_per_grid;
+      k[j] = end[j] = 0;
+      if (r[j] < nrows) {
+        k[j] = __ldg(ptr + r[j]) + (int)sub;
+        end[j] = __ldg(ptr + r[j] + 1);
+        if (sub == 0) old[j] = res[r[j]];
+      }
+    }
+    while (k[0] < end[0] || k[1] < end[1]) {
+      int c[2][kUnroll];
+      float v[2][kUnroll];
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const int kk = k[j] + u * kGroup;
+          const bool ok = kk < end[j];
+          c[j][u] = ok ? __ldcs(ind + kk) : 0;
+          v[j][u] = ok ? __ldcs(val + kk) : 0.f;
+        }
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) acc[j] += v[j][u] * __ldg(x + c[j][u]);
+      k[0] += kUnroll * kGroup;
+      k[1] += kUnroll * kGroup;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+#pragma unroll
+      for (int o = kGroup / 2; o > 0; o >>= 1) acc[j] += __shfl_down_sync(0xffffffffu, acc[j], o, kGroup);
+      if (sub == 0 && r[j] < nrows) res[r[j]] = old[j] + sign * acc[j];
+    }
   }
 }
 
@@ -348,14 +382,23 @@ class BlockSparse : public Block {
     if (rows == 0) return;
     const double avg = rows ? (double)nnz_ / (double)rows : 0.0;
     const unsigned cap = ctx_->num_sms * 16;
+    static const int variant = [] { const char* e = getenv("PB_SPMV_VARIANT"); return e ? atoi(e) : 0; }();
     if (avg <= 6.0) {
+      const unsigned grid = std::min<size_t>(grid_for(rows * 2), cap);
+      csr_spmv_add_group_kernel<4, 2><<<grid, kBlock, 0, ctx_->stream>>>(ptr.data(), ind.data(), val.data(),
+                                                                         (uint32_t)rows, res, x, 1.f, ctx_->skip_flag);
+    } else if (avg <= 16.0 && variant != 1) {
+      const unsigned grid = std::min<size_t>(grid_for(rows * 2), cap);
+      csr_spmv_add_group_kernel<4, 4><<<grid, kBlock, 0, ctx_->stream>>>(ptr.data(), ind.data(), val.data(),
+                                                                         (uint32_t)rows, res, x, 1.f, ctx_->skip_flag);
+    } else if (avg <= 32.0) {
       const unsigned grid = std::min<size_t>(grid_for(rows * 4), cap);
-      csr_spmv_add_group_kernel<4><<<grid, kBlock, 0, ctx_->stream>>>(ptr.data(), ind.data(), val.data(),
-                                                                      (uint32_t)rows, res, x, 1.f, ctx_->skip_flag);
-    } else if (avg <= 24.0) {
+      csr_spmv_add_group_kernel<8, 4><<<grid, kBlock, 0, ctx_->stream>>>(ptr.data(), ind.data(), val.data(),
+                                                                         (uint32_t)rows, res, x, 1.f, ctx_->skip_flag);
+    } else if (avg <= 128.0 && variant != 2) {
       const unsigned grid = std::min<size_t>(grid_for(rows * 8), cap);
-      csr_spmv_add_group_kernel<8><<<grid, kBlock, 0, ctx_->stream>>>(ptr.data(), ind.data(), val.data(),
-                                                                      (uint32_t)rows, res, x, 1.f, ctx_->skip_flag);
+      csr_spmv_add_group_kernel<16, 4><<<grid, kBlock, 0, ctx_->stream>>>(ptr.data(), ind.data(), val.data(),
+                                                                          (uint32_t)rows, res, x, 1.f, ctx_->skip_flag);
     } else {
       const unsigned grid = std::min<size_t>(grid_for(rows * 32), cap);
       csr_spmv_add_kernel<<<grid, kBlock, 0, ctx_->stream>>>(ptr.data(), ind.data(), val.data(),

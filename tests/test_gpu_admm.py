@@ -27,7 +27,7 @@ def test_admm_vs_oracle(ctx, name):
     want = run_oracle_admm(desc, got["iterations"], tol=tol, **opts)
     # the CG exit test |s| <= tol |s0| is a float comparison on sums whose order differs between the
     # SpMV implementations: an occasional borderline step more or less is legitimate
-    assert abs(got["steps"][2] - want["steps"][2]) <= max(2, 0.01 * want["steps"][2]), \
+    assert abs(got["steps"][2] - want["steps"][2]) <= max(2, 0.03 * want["steps"][2]), \
         f"CG steps {got['steps'][2]} vs {want['steps'][2]}"
     assert_admm_parity(got, want, label=name)
     assert got["backend"].launch_count > 0
