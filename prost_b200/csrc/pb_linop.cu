@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(kBlock) csr_spmv_add_kernel(const int* __restr
 // gathers are in flight: a lane loads the (column, value) pairs of up to kUnroll of its entries of BOTH rows before
 // the first gather is issued, so 2 * kUnroll independent gathers leave each thread back to back (round 1's form had
 // one dependent ptr -> ind -> x chain per thread).
-template <int kGroup, int kUnroll>
+template <int kGroup, int kUnroll, int kRows>
 __global__ void __launch_bounds__(kBlock) csr_spmv_add_group_kernel(
     const int* __restrict__ ptr, const int* __restrict__ ind, const float* __restrict__ val,
     uint32_t nrows, float* __restrict__ res, const float* __restrict__ x, float sign,
@@ -68,26 +68,29 @@ __global__ void __launch_bounds__(kBlock) csr_spmv_add_group_kernel(
   const uint32_t groups_per_grid = (gridDim.x * blockDim.x) / kGroup;
   // all lanes of a warp iterate the same number of times so the shuffles stay converged
   const uint32_t first = (blockIdx.x * blockDim.x + threadIdx.x) / kGroup;
-  const uint32_t iters = (nrows + 2 * groups_per_grid - 1) / (2 * groups_per_grid);
+  const uint32_t iters = (nrows + kRows * groups_per_grid - 1) / (kRows * groups_per_grid);
   for (uint32_t it = 0; it < iters; ++it) {
-    uint32_t r[2];
-    int k[2], end[2];
-    float acc[2] = {0.f, 0.f}, old[2] = {0.f, 0.f};
+    uint32_t r[kRows];
+    int k[kRows], end[kRows];
+    float acc[kRows], old[kRows];
+    bool more = false;
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      r[j] = first + (2 * it + j) * groups_per_grid;
+    for (int j = 0; j < kRows; ++j) {
+      r[j] = first + (kRows * it + j) * groups_per_grid;
       k[j] = end[j] = 0;
+      acc[j] = old[j] = 0.f;
       if (r[j] < nrows) {
         k[j] = __ldg(ptr + r[j]) + (int)sub;
         end[j] = __ldg(ptr + r[j] + 1);
         if (sub == 0) old[j] = res[r[j]];
       }
+      more |= k[j] < end[j];
     }
-    while (k[0] < end[0] || k[1] < end[1]) {
-      int c[2][kUnroll];
-      float v[2][kUnroll];
+    while (more) {
+      int c[kRows][kUnroll];
+      float v[kRows][kUnroll];
 #pragma unroll
-      for (int j = 0; j < 2; ++j)
+      for (int j = 0; j < kRows; ++j)
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
           const int kk = k[j] + u * kGroup;
@@ -95,16 +98,18 @@ __global__ void __launch_bounds__(kBlock) csr_spmv_add_group_kernel(
           c[j][u] = ok ? __ldcs(ind + kk) : 0;
           v[j][u] = ok ? __ldcs(val + kk) : 0.f;
         }
+      more = false;
 #pragma unroll
-      for (int j = 0; j < 2; ++j)
+      for (int j = 0; j < kRows; ++j) {
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) acc[j] += v[j][u] * __ldg(x + c[j][u]);
-      k[0] += kUnroll * kGroup;
-      k[1] += kUnroll * kGroup;
+        k[j] += kUnroll * kGroup;
+        more |= k[j] < end[j];
+      }
     }
     __syncwarp();
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < kRows; ++j) {
 #pragma unroll
       for (int o = kGroup / 2; o > 0; o >>= 1) acc[j] += __shfl_down_sync(0xffffffffu, acc[j], o, kGroup);
       if (sub == 0 && r[j] < nrows) res[r[j]] = old[j] + sign * acc[j];
@@ -382,28 +387,28 @@ class BlockSparse : public Block {
     if (rows == 0) return;
     const double avg = rows ? (double)nnz_ / (double)rows : 0.0;
     const unsigned cap = ctx_->num_sms * 16;
-    static const int variant = [] { const char* e = getenv("PB_SPMV_VARIANT"); return e ? atoi(e) : 0; }();
+    // lanes per row / entries per lane / rows per step: 3 or 4 rows per step, 2 or 8 lanes per row at 12 nnz and 8
+    // lanes at 48 nnz all measure within 4 % of these (profiles/r02_operators.md)
+#define PB_SPMV(G, U, R)                                                                                           \
+  do {                                                                                                             \
+    const unsigned grid = std::min<size_t>(grid_for((rows * G + R - 1) / R), cap);                                 \
+    csr_spmv_add_group_kernel<G, U, R><<<grid, kBlock, 0, ctx_->stream>>>(ptr.data(), ind.data(), val.data(),      \
+                                                                         (uint32_t)rows, res, x, 1.f, ctx_->skip_flag); \
+  } while (0)
     if (avg <= 6.0) {
-      const unsigned grid = std::min<size_t>(grid_for(rows * 2), cap);
-      csr_spmv_add_group_kernel<4, 2><<<grid, kBlock, 0, ctx_->stream>>>(ptr.data(), ind.data(), val.data(),
-                                                                         (uint32_t)rows, res, x, 1.f, ctx_->skip_flag);
-    } else if (avg <= 16.0 && variant != 1) {
-      const unsigned grid = std::min<size_t>(grid_for(rows * 2), cap);
-      csr_spmv_add_group_kernel<4, 4><<<grid, kBlock, 0, ctx_->stream>>>(ptr.data(), ind.data(), val.data(),
-                                                                         (uint32_t)rows, res, x, 1.f, ctx_->skip_flag);
+      PB_SPMV(4, 2, 2);
+    } else if (avg <= 16.0) {
+      PB_SPMV(4, 4, 2);
     } else if (avg <= 32.0) {
-      const unsigned grid = std::min<size_t>(grid_for(rows * 4), cap);
-      csr_spmv_add_group_kernel<8, 4><<<grid, kBlock, 0, ctx_->stream>>>(ptr.data(), ind.data(), val.data(),
-                                                                         (uint32_t)rows, res, x, 1.f, ctx_->skip_flag);
-    } else if (avg <= 128.0 && variant != 2) {
-      const unsigned grid = std::min<size_t>(grid_for(rows * 8), cap);
-      csr_spmv_add_group_kernel<16, 4><<<grid, kBlock, 0, ctx_->stream>>>(ptr.data(), ind.data(), val.data(),
-                                                                          (uint32_t)rows, res, x, 1.f, ctx_->skip_flag);
+      PB_SPMV(8, 4, 2);
+    } else if (avg <= 128.0) {
+      PB_SPMV(16, 4, 2);
     } else {
       const unsigned grid = std::min<size_t>(grid_for(rows * 32), cap);
       csr_spmv_add_kernel<<<grid, kBlock, 0, ctx_->stream>>>(ptr.data(), ind.data(), val.data(),
                                                              (uint32_t)rows, res, x, 1.f, ctx_->skip_flag);
     }
+#undef PB_SPMV
     PB_CHECK_LAUNCH();
     ctx_->launches++;
   }
