@@ -1,4 +1,4 @@
-// prost/prox/elemop/elem_operation_eigen_nxn.hpp -- ElemOperationEigenNxN<T, FUN_1D>: prox of sum_i h(lambda_i) of a symmetrised n x n matrix, n <= 8 here
+// prost/prox/elemop/elem_operation_eigen_nxn.hpp -- ElemOperationEigenNxN<T, FUN_1D>: prox of sum_i h(lambda_i) of a symmetrised n x n matrix, n <= 32 (the reference's N_MAX)
 // (reference: elem_operation_eigen_nxn.hpp).
 #ifndef PROST_ELEM_OPERATION_EIGEN_NXN_HPP_
 #define PROST_ELEM_OPERATION_EIGEN_NXN_HPP_

@@ -190,7 +190,7 @@ int pb_prox_create_ind_sum_indexed(pb_context* ctx, size_t index, size_t size, s
 /* Spectral element operations: ProxElemOperation<T, ElemOperationSingularNx2<T, FUN_2D>> (prox of
  * h(sigma_1) + h(sigma_2) / a Function2D of the singular values of an N x 2 matrix, dim = 2N,
  * elem_operation_singular_nx2.hpp:32-150, function_2d.hpp:28-101) and ElemOperationEigen2x2 / Eigen3x3 / EigenNxN
- * (prox of sum_i h(lambda_i) of the symmetrised matrix, dim = 4 / 9 / n^2 with n <= 8 here;
+ * (prox of sum_i h(lambda_i) of the symmetrised matrix, dim = 4 / 9 / n^2 with n <= 32, the reference's N_MAX;
  * elem_operation_eigen_2x2.hpp:94-146, elem_operation_eigen_3x3.hpp:302-377, elem_operation_eigen_nxn.hpp).
  * coeffs = a, b, c, d, e, alpha, beta of c h(a x - b) + d x + (e/2) x^2, 1 or count entries each.
  * function_2d (singular_nx2 only): 0 = sum_1d:<function_1d>, 1 = ind_l1_ball, 2 = moreau:ind_l1_ball. */

@@ -15,7 +15,7 @@
 // does not depend on the choice of eigenvectors, so
 //   * 2 x 2: Sylvester's formula  T = f(l2) I + (f(l1) - f(l2)) / (l1 - l2) (M - l2 I)  -- no eigenvectors, no
 //     branches on the rotation (the reference carries LAPACK's dlaev2 logic, eigen_2x2.hpp:30-92);
-//   * 3 x 3 and n x n (n <= 8): cyclic Jacobi rotations in double on registers / local memory, which are
+//   * 3 x 3 and n x n (n <= 8; run-time loops up to the reference's N_MAX = 32): cyclic Jacobi rotations in double on registers / local memory, which are
 //     unconditionally stable for (nearly) degenerate spectra (the reference uses Kopp's Cardano + cross-product
 //     routine with its threshold cascades for 3 x 3, :31-300, and EISPACK tred2 / tql2 for n x n).
 // Results agree with the reference to rounding (tests: numpy eigh / svd closed forms as in the reference's own
@@ -282,6 +282,78 @@ __global__ void __launch_bounds__(kBlock) spectral_eigen_nxn_kernel(const Spectr
   }
 }
 
+// 8 < n <= 32 (the reference's N_MAX, elem_operation_eigen_nxn.hpp:11): the same cyclic Jacobi iteration with run-time
+// loops on thread-local arrays (full symmetric storage).  Like the reference's tred2 / tql2 on double V[32][32] this
+// lives in local memory; such sizes are rare and far from any hot path.
+constexpr int kSpectralMaxN = 32;
+__global__ void __launch_bounds__(64) spectral_eigen_big_kernel(const SpectralDesc p, float* __restrict__ res,
+                                                                const float* __restrict__ arg,
+                                                                const float* __restrict__ td, float tau_scal,
+                                                                bool invert) {
+  for (size_t tx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; tx < p.count; tx += (size_t)gridDim.x * blockDim.x) {
+    const int n = static_cast<int>(p.n);
+    float c[7];
+    load7(p.coeffs, tx, c);
+    double A[kSpectralMaxN][kSpectralMaxN], V[kSpectralMaxN][kSpectralMaxN];
+#pragma unroll 1
+    for (int i = 0; i < n; ++i)
+#pragma unroll 1
+      for (int j = i; j < n; ++j) {
+        const float u = arg[elem_at(p, tx, i * n + j)], l = arg[elem_at(p, tx, j * n + i)];
+        A[i][j] = A[j][i] = i == j ? static_cast<double>(u) : static_cast<double>(u + l) / 2.;
+        V[i][j] = V[j][i] = i == j ? 1.0 : 0.0;
+      }
+#pragma unroll 1
+    for (int sweep = 0; sweep < 24; ++sweep) {
+      double off = 0.0, diag = 0.0;
+#pragma unroll 1
+      for (int i = 0; i < n; ++i) {
+        diag += A[i][i] * A[i][i];
+#pragma unroll 1
+        for (int j = i + 1; j < n; ++j) off += A[i][j] * A[i][j];
+      }
+      if (off <= 1e-32 * diag || off == 0.0) break;
+#pragma unroll 1
+      for (int pi = 0; pi < n - 1; ++pi)
+#pragma unroll 1
+        for (int q = pi + 1; q < n; ++q) {
+          const double apq = A[pi][q];
+          if (apq == 0.0) continue;
+          const double theta = (A[q][q] - A[pi][pi]) / (2.0 * apq);
+          const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+          const double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
+          A[pi][pi] -= t * apq;
+          A[q][q] += t * apq;
+          A[pi][q] = A[q][pi] = 0.0;
+#pragma unroll 1
+          for (int r = 0; r < n; ++r) {
+            if (r != pi && r != q) {
+              const double vp = A[r][pi], vq = A[r][q];
+              A[r][pi] = A[pi][r] = cs * vp - sn * vq;
+              A[r][q] = A[q][r] = sn * vp + cs * vq;
+            }
+            const double vp = V[r][pi], vq = V[r][q];
+            V[r][pi] = cs * vp - sn * vq;
+            V[r][q] = sn * vp + cs * vq;
+          }
+        }
+    }
+    const double tau = group_tau(tau_scal, td[elem_at(p, tx, 0)], invert);
+#pragma unroll 1
+    for (int k = 0; k < n; ++k) A[k][k] = eig_prox(p.fn, A[k][k], tau, c);     // f(lambda_k) in place
+#pragma unroll 1
+    for (int i = 0; i < n; ++i)
+#pragma unroll 1
+      for (int j = i; j < n; ++j) {
+        double t = 0.0;                               // T = V f(Lambda) V^T
+#pragma unroll 1
+        for (int k = 0; k < n; ++k) t += V[i][k] * V[j][k] * A[k][k];
+        res[elem_at(p, tx, i * n + j)] = static_cast<float>(t);
+        res[elem_at(p, tx, j * n + i)] = static_cast<float>(t);
+      }
+  }
+}
+
 // ---- mass / comass norms of 2-vectors in R^4 and R^5 (elem_operation_mass_norm.hpp:17-186) ---------------------
 // The argument (6 resp. 10 numbers) is the upper triangle of a skew-symmetric matrix M; the mass norm is the sum of
 // its singular-value pairs, the prox shrinks them (comass ball: clamps them to 1).  With M = U Sigma V^T:
@@ -376,7 +448,7 @@ class ProxSpectral : public Prox {
         uint32_t n = 1;
         while ((size_t)n * n < dim) ++n;
         if ((size_t)n * n != dim) fail(PB_ERR_INVALID, "eigen_nxn: dim must be a square number");
-        if (n > 8) fail(PB_ERR_UNSUPPORTED, "eigen_nxn: matrices larger than 8 x 8 are not supported");
+        if (n > 32) fail(PB_ERR_UNSUPPORTED, "eigen_nxn: matrices larger than 32 x 32 are not supported");  // N_MAX
         desc_.n = n;
         break;
       }
@@ -435,7 +507,9 @@ class ProxSpectral : public Prox {
       default:
         if (desc_.n <= 3) spectral_eigen_nxn_kernel<3><<<grid, kBlock, 0, s>>>(desc_, res, arg, td, tau, invert);
         else if (desc_.n <= 5) spectral_eigen_nxn_kernel<5><<<grid, kBlock, 0, s>>>(desc_, res, arg, td, tau, invert);
-        else spectral_eigen_nxn_kernel<8><<<grid, kBlock, 0, s>>>(desc_, res, arg, td, tau, invert);
+        else if (desc_.n <= 8) spectral_eigen_nxn_kernel<8><<<grid, kBlock, 0, s>>>(desc_, res, arg, td, tau, invert);
+        else spectral_eigen_big_kernel<<<(unsigned)std::min<size_t>((desc_.count + 63) / 64, (size_t)ctx_->num_sms * 8), 64, 0, s>>>(
+            desc_, res, arg, td, tau, invert);
         break;
     }
     PB_CHECK_LAUNCH();

@@ -245,6 +245,11 @@ def prox_spectral_cases(small=False):
         cases[f"{kind}_d{dim}_square_vec"] = ((f"elem_operation:{kind}:square", 7, n * dim, True,
                                                [n, dim, True, coeffs(a=1, b=r.random(n), c=r.uniform(0.5, 2, n), d=0.1, e=0.2)]),
                                               n * dim + 11)
+    # beyond the register kernels: 12 x 12 (run-time Jacobi loops; the reference allows up to N_MAX = 32)
+    nb = 40 if not small else 5
+    cases["eigen_nxn_d144_psd"] = (("elem_operation:eigen_nxn:ind_leq0", 0, nb * 144, False, [nb, 144, True, psd]), nb * 144)
+    cases["eigen_nxn_d144_abs_planar"] = (("elem_operation:eigen_nxn:abs", 0, nb * 144, False,
+                                          [nb, 144, False, coeffs(a=1, b=0.3, c=0.8)]), nb * 144)
     for name, dim in (("mass4", 6), ("ind_comass4_ball", 6), ("mass5", 10), ("ind_comass5_ball", 10)):
         for il in (True, False):
             data = [n, dim, il] + ([[[1.0]]] if dim == 6 else [])
