@@ -124,6 +124,7 @@ struct KronTcArgs {
   uint32_t n_out, n_in, n_out_pad, k_pad;
   size_t d;
   uint32_t tmem_cols;
+  uint32_t lag;               // 1 or 2: iterations between writing a tile's operands and draining its accumulator
   uint32_t stage_out;         // kron(I, K): results leave through a shared-memory tile (n_out % 4 == 0, n_out <= 64)
   uint32_t debug;             // timing experiments (results unusable): 1 no MMAs, 2 no result stores, 4 no X loads, 8 no split / smem stores
   const int* skip;
@@ -144,7 +145,7 @@ struct KronTcArgs {
 //
 // Roles: 16 worker warps (load -> split -> shared memory; TMEM -> HBM) and one MMA warp.  Per operand / accumulator
 // buffer b (two of each): workers arrive on full[b] after writing tile j's operands, the MMA warp waits for it, issues
-// the 3 * k_pad / 8 MMAs and commits them to done[b]; every worker waits for done[b] before it drains tile j, which
+// the 3 * k_pad / 8 MMAs and commits them to done[accumulator]; every worker waits for that before it drains tile j, which
 // is also what allows it to overwrite buffer b with tile j + 2.  No CTA-wide barrier inside the loop.
 template <bool IDFIRST, bool SET, int DEPTH>
 __global__ void __launch_bounds__(kTcThreads, 1) kron_tc_kernel(const KronTcArgs a) {
@@ -160,8 +161,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) kron_tc_kernel(const KronTcArgs
   uint8_t* const f_hi = tc_smem + 4 * xb;
   uint8_t* const f_lo = f_hi + fb;
   uint64_t* const full = reinterpret_cast<uint64_t*>(f_lo + fb);
-  uint64_t* const done = full + 2;
-  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(done + 2);
+  uint64_t* const done = full + 2;                        // one per accumulator (lag + 1 of them)
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(full + 6);
+  const uint32_t lag = a.lag, nacc = a.lag + 1;           // tiles between a tile's MMAs and its drain; accumulators
 
   for (uint32_t i = tid; i < fb / 16; i += kTcThreads) {
     reinterpret_cast<uint4*>(f_hi)[i] = __ldg(a.f_hi + i);
@@ -172,6 +174,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) kron_tc_kernel(const KronTcArgs
     tc_mbar_init(&full[1], kTcWorkerWarps);
     tc_mbar_init(&done[0], 1);
     tc_mbar_init(&done[1], 1);
+    tc_mbar_init(&done[2], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -202,14 +205,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) kron_tc_kernel(const KronTcArgs
       if (lane == 0) {
         const uint32_t xh = tc_smem_u32(x_hi0 + buf * 2 * xb);
         const uint64_t da_hi0 = tc_smem_desc(xh, 128u, sbo), da_lo0 = tc_smem_desc(xh + xb, 128u, sbo);
-        const uint32_t dst = tmem + buf * a.n_out_pad;
+        const uint32_t acc = j % nacc;
+        const uint32_t dst = tmem + acc * a.n_out_pad;
         for (uint32_t ko = 0; ko < ko_count && !(a.debug & 1u); ++ko) {
           const uint64_t step = ko * 16u;                      // 256 bytes per k-step, in 16-byte units
           tc_mma_tf32(dst, da_hi0 + step, db_hi0 + step, idesc, ko > 0);
           tc_mma_tf32(dst, da_lo0 + step, db_hi0 + step, idesc, 1u);
           tc_mma_tf32(dst, da_hi0 + step, db_lo0 + step, idesc, 1u);
         }
-        tc_commit(&done[buf]);
+        tc_commit(&done[j % nacc]);
       }
       __syncwarp();
     }
@@ -323,12 +327,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) kron_tc_kernel(const KronTcArgs
       }
     };
     // accumulator of tile t (TMEM half `buf`) -> HBM
-    auto drain = [&](size_t t, uint32_t buf, uint32_t parity) {
-      tc_mbar_wait(&done[buf], parity);
+    auto drain = [&](size_t t, uint32_t acc, uint32_t parity) {
+      tc_mbar_wait(&done[acc], parity);
       tc_fence_after();
       const size_t p0 = t * kTcPoints;
       const bool live = p0 + row < dd && !(a.debug & 2u);
-      const uint32_t taddr = tmem + ((32u * lb) << 16) + buf * a.n_out_pad;
+      const uint32_t taddr = tmem + ((32u * lb) << 16) + acc * a.n_out_pad;
       float* dst = staged ? reinterpret_cast<float*>(stg + (row * stride16 + (c_begin >> 2)) * 16u)
                           : out_col0 + (IDFIRST ? p0 * a.n_out : p0);
       const size_t cstep = (IDFIRST || staged) ? 1 : dd;              // distance between columns at dst
@@ -399,29 +403,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) kron_tc_kernel(const KronTcArgs
 #pragma unroll
     for (int s = 0; s < DEPTH; ++s)
       if (blockIdx.x + s * stride < tiles) load_tile(stage[s], blockIdx.x + s * stride);
-    size_t t = blockIdx.x, prev = 0;
+    // Tile j of this CTA: operand buffer j % 2, accumulator j % nacc; it is drained `lag` iterations after its
+    // operands were written, so that its MMAs (and their completion latency) are off the workers' critical path.
+    size_t t = blockIdx.x;
     uint32_t j = 0;
+    auto drain_seq = [&](uint32_t jt) { drain(blockIdx.x + (size_t)jt * stride, jt % nacc, (jt / nacc) & 1u); };
     while (t < tiles) {
 #pragma unroll
       for (int s = 0; s < DEPTH; ++s) {
         if (t < tiles) {
           const uint32_t buf = j & 1;
-          // buffer `buf` (operands and TMEM half) was last used by tile j - 2: this thread waited for its MMAs
-          // (done[buf]) and finished reading its accumulator in iteration j - 1
+          // operand buffer `buf` was last read by the MMAs of tile j - 2.  lag 1: this thread waited for them when
+          // it drained tile j - 2 in the previous iteration; lag 2: wait here (they finished long ago)
+          if (lag == 2 && j >= 2) tc_mbar_wait(&done[(j - 2) % nacc], ((j - 2) / nacc) & 1u);
           store_tile(stage[s], buf);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           tc_fence_before();
           __syncwarp();
           if (lane == 0) tc_mbar_arrive(&full[buf]);
           if (t + DEPTH * stride < tiles) load_tile(stage[s], t + DEPTH * stride);
-          if (j > 0) drain(prev, buf ^ 1, ((j - 1) >> 1) & 1);
-          prev = t;
+          if (j >= lag) drain_seq(j - lag);
           t += stride;
           ++j;
         }
       }
     }
-    if (j > 0) drain(prev, (j - 1) & 1, ((j - 1) >> 1) & 1);
+    for (uint32_t jt = j >= lag ? j - lag : 0; jt < j; ++jt) drain_seq(jt);
   }
   tc_fence_before();
   __syncthreads();
@@ -498,8 +505,10 @@ void KronTensorCore::launch(Context* ctx, bool id_first, const Packed& f, float*
   a.n_out_pad = f.n_pad;
   a.k_pad = f.k_pad;
   a.d = d;
+  static const int lag = tc_env("PB_KRON_TC_LAG", 1);          // 2 measures the same (profiles/r02_operators.md)
+  a.lag = (lag >= 2 && 3 * f.n_pad <= 512) ? 2u : 1u;        // 512 TMEM columns per SM
   uint32_t cols = 32;
-  while (cols < 2 * f.n_pad) cols *= 2;
+  while (cols < (a.lag + 1) * f.n_pad) cols *= 2;
   a.tmem_cols = cols;
   static const int debug = tc_env("PB_KRON_TC_DEBUG", 0);
   a.debug = (uint32_t)debug;
