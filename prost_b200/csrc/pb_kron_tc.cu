@@ -26,6 +26,8 @@
 #include <cstring>
 #include <vector>
 
+#include <cuda.h>
+
 #include "pb_common.cuh"
 #include "pb_linop.cuh"
 
@@ -125,6 +127,7 @@ struct KronTcArgs {
   size_t d;
   uint32_t tmem_cols;
   uint32_t lag;               // 1 or 2: iterations between writing a tile's operands and draining its accumulator
+  uint32_t tma_out;           // kron(K, I): results leave as one TMA tensor store per warp (32 points x its columns)
   uint32_t stage_out;         // kron(I, K): results leave through a shared-memory tile (n_out % 4 == 0, n_out <= 64)
   uint32_t debug;             // timing experiments (results unusable): 1 no MMAs, 2 no result stores, 4 no X loads, 8 no split / smem stores
   const int* skip;
@@ -148,7 +151,8 @@ struct KronTcArgs {
 // the 3 * k_pad / 8 MMAs and commits them to done[accumulator]; every worker waits for that before it drains tile j, which
 // is also what allows it to overwrite buffer b with tile j + 2.  No CTA-wide barrier inside the loop.
 template <bool IDFIRST, bool SET, int DEPTH>
-__global__ void __launch_bounds__(kTcThreads, 1) kron_tc_kernel(const KronTcArgs a) {
+__global__ void __launch_bounds__(kTcThreads, 1) kron_tc_kernel(const KronTcArgs a,
+                                                                const __grid_constant__ CUtensorMap out_map) {
   if (a.skip && *a.skip) return;
   extern __shared__ __align__(128) uint8_t tc_smem[];
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -293,7 +297,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) kron_tc_kernel(const KronTcArgs
     // 512 contiguous bytes per warp store; a lane-per-row store would touch 32 lines per instruction.
     const bool staged = IDFIRST && a.stage_out;
     const uint32_t q_per_row = a.n_out >> 2, stride16 = q_per_row | 1u;
-    uint8_t* const stg = reinterpret_cast<uint8_t*>(tmem_slot) + 64;
+    uint8_t* const stg = reinterpret_cast<uint8_t*>(full) + 128;
     uint32_t cp_soff[kTcUnits];
     if (staged) {
 #pragma unroll
@@ -333,6 +337,51 @@ __global__ void __launch_bounds__(kTcThreads, 1) kron_tc_kernel(const KronTcArgs
       const size_t p0 = t * kTcPoints;
       const bool live = p0 + row < dd && !(a.debug & 2u);
       const uint32_t taddr = tmem + ((32u * lb) << 16) + acc * a.n_out_pad;
+      if (!IDFIRST && a.tma_out) {
+        // kron(K, I) through TMA: the warp's 32 points x cols accumulators go to its own [cols][32] shared-memory tile
+        // (128 contiguous bytes per column: conflict-free) and leave as ONE tensor store (or add-reduction) instead of
+        // cols store instructions per thread with their 64-bit address arithmetic; out-of-range points / columns are
+        // clipped by the tensor map
+        float* const tile = reinterpret_cast<float*>(stg + warp * (cols * 128u));
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous store has read it
+        __syncwarp();
+        uint32_t c = 0;
+        for (; c + 16 <= cols; c += 16) {
+          float v[16];
+          tc_ld16(taddr + c_begin + c, v);
+#pragma unroll
+          for (uint32_t q = 0; q < 16; ++q) tile[(c + q) * 32 + lane] = v[q];
+        }
+        if (c + 8 <= cols) {
+          float v[8];
+          tc_ld8(taddr + c_begin + c, v);
+#pragma unroll
+          for (uint32_t q = 0; q < 8; ++q) tile[(c + q) * 32 + lane] = v[q];
+          c += 8;
+        }
+        if (c < cols) {
+          float v[4];
+          tc_ld4(taddr + c_begin + c, v);
+#pragma unroll
+          for (uint32_t q = 0; q < 4; ++q) tile[(c + q) * 32 + lane] = v[q];
+        }
+        tc_fence_before();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0 && !(a.debug & 2u)) {
+          const uint64_t map = reinterpret_cast<uint64_t>(&out_map);
+          const uint32_t src = tc_smem_u32(tile);
+          const int x = (int)(p0 + 32 * lb), y = (int)c_begin;
+          if (SET)
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                         ::"l"(map), "r"(x), "r"(y), "r"(src) : "memory");
+          else
+            asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];"
+                         ::"l"(map), "r"(x), "r"(y), "r"(src) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        return;
+      }
       float* dst = staged ? reinterpret_cast<float*>(stg + (row * stride16 + (c_begin >> 2)) * 16u)
                           : out_col0 + (IDFIRST ? p0 * a.n_out : p0);
       const size_t cstep = (IDFIRST || staged) ? 1 : dd;              // distance between columns at dst
@@ -429,6 +478,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) kron_tc_kernel(const KronTcArgs
       }
     }
     for (uint32_t jt = j >= lag ? j - lag : 0; jt < j; ++jt) drain_seq(jt);
+    if (!IDFIRST && a.tma_out && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -469,8 +519,39 @@ bool KronTensorCore::supported(bool id_first, uint32_t n_out, uint32_t n_in, siz
 
 static bool stages_output(bool id_first, uint32_t n_out) { return id_first && n_out % 4 == 0 && n_out <= 64; }
 
+typedef CUresult (*TcEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TcEncodeTiledFn tc_encode_fn() {
+  static TcEncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    cudaGetLastError();
+    return reinterpret_cast<TcEncodeTiledFn>(p);
+  }();
+  return fn;
+}
+// res of kron(K, I) as a 2-D tensor [n_out rows][d points]; box = 32 points x the columns of one warp
+static bool tc_out_map(float* res, size_t d, uint32_t n_out, uint32_t cols, CUtensorMap& m) {
+  static const int enabled = tc_env("PB_KRON_TC_TMA_OUT", 1);
+  if (!enabled || d % 4 != 0 || (reinterpret_cast<uintptr_t>(res) & 15u) != 0 || cols > 256 || d >= (1ull << 31)) return false;
+  TcEncodeTiledFn enc = tc_encode_fn();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)n_out};
+  const cuuint64_t strides[1] = {(cuuint64_t)d * 4};
+  const cuuint32_t box[2] = {32, cols};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, res, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 size_t KronTensorCore::smem_bytes(bool id_first, uint32_t n_out, uint32_t n_pad, uint32_t k_pad) {
-  const size_t staging = stages_output(id_first, n_out) ? (size_t)kTcPoints * ((n_out / 4) | 1u) * 16 : 0;
+  // output staging: kron(I, K) a padded 128 x n_out tile, kron(K, I) [n_pad][128] for the per-warp tensor stores
+  const size_t staging = stages_output(id_first, n_out) ? (size_t)kTcPoints * ((n_out / 4) | 1u) * 16
+                         : !id_first ? (size_t)n_pad * kTcPoints * 4 : 0;
   return 4 * (size_t)(k_pad / 8) * 4096 + 2 * (size_t)n_pad * k_pad * 4 + 128 + staging;
 }
 
@@ -515,12 +596,15 @@ void KronTensorCore::launch(Context* ctx, bool id_first, const Packed& f, float*
   a.skip = ctx->skip_flag;
   const size_t smem = smem_bytes(id_first, n_out, f.n_pad, f.k_pad);
   a.stage_out = stages_output(id_first, n_out) ? 1u : 0u;
+  CUtensorMap out_map;
+  std::memset(&out_map, 0, sizeof(out_map));
+  a.tma_out = (!id_first && tc_out_map(res, d, n_out, f.n_pad / 4, out_map)) ? 1u : 0u;
   const size_t tiles = (d + kTcPoints - 1) / kTcPoints;
   const unsigned grid = (unsigned)std::min<size_t>(tiles, (size_t)ctx->num_sms);
 #define PB_TC(I, S, D)                                                                                       \
   do {                                                                                                       \
     PB_CUDA(cudaFuncSetAttribute(kron_tc_kernel<I, S, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kron_tc_kernel<I, S, D><<<grid, kTcThreads, smem, ctx->stream>>>(a);                                     \
+    kron_tc_kernel<I, S, D><<<grid, kTcThreads, smem, ctx->stream>>>(a, out_map);                            \
   } while (0)
 #define PB_TC_D(I, S) do { if (depth <= 1) PB_TC(I, S, 1); else PB_TC(I, S, 2); } while (0)
   if (id_first) { if (set) PB_TC_D(true, true); else PB_TC_D(true, false); }
