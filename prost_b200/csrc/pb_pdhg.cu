@@ -442,6 +442,10 @@ void BackendPDHG::initialize(const float* h_x0, size_t nx0, const float* h_y0, s
     static const int ring_iters = [] { const char* e = getenv("PB_RING_ITERS"); return e ? atoi(e) : -1; }();
     const int dflt = kRingItersDefault;
     ring_iters_ = std::min(ring_iters >= 0 ? ring_iters : dflt, 32);
+    // one GPU only: bit-identical to single launches there (tests/test_gpu_ring_multi.py); on column slabs the
+    // multi-iteration launch did not complete in bring-up (profiles/r02_scaling.md), so slabs always take one
+    // iteration per launch
+    if (comm_) ring_iters_ = 0;
   }
   if (comm_) {
     // the halo protocol lives in the specialised stencil passes: one planar gradient operator

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Round-2 bring-up check for the EXPERIMENTAL multi-iteration ring launches (PB_RING_ITERS > 1, pb_tile.cu
 RingMulti): several non-refresh PDHG iterations per launch with per-tile dependencies instead of the kernel
-boundary.  Not part of the test-suite until it has run on a GPU.
+boundary.  tests/test_gpu_ring_multi.py runs it on one GPU; on column slabs the switch is ignored.
 
     python scripts/check_ring_multi.py                 # one GPU: bitwise comparison against single launches
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 scripts/check_ring_multi.py
