@@ -29,7 +29,22 @@ __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc, bo
   const int bytes = pred ? 4 : 0;                     // 0: nothing is read, the destination is zero-filled
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, bool pred) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  const int bytes = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Cooperative staging (COOP, plain iterations with ny % kStagedBlock == 0, slabs included): a CTA owns kStagedBlock
+// consecutive pixels of ONE image column, so every operand of a label is a contiguous, 16-byte aligned row of
+// kStagedBlock floats.  Instead of one 4-byte cp.async per thread, operand and label (with its own 64-bit address
+// arithmetic: ~40 of the ~100 instructions per pixel and label, profiles/r02_lifting.md), the CTA copies each row with
+// kStagedBlock / 4 16-byte cp.async: thread (label slot tid / 16, 16-byte piece tid % 16) issues ONE copy per operand
+// and chunk.  The shifted operands (down / up neighbour) are the same row read at +-1, plus one extra element.  Rows
+// are [4 pad][kStagedBlock][4 pad] floats; three chunk buffers and one CTA barrier per chunk (buffer (c + 1) % 3 was
+// last read for chunk c - 2, which every thread finished before the barrier of chunk c - 1).
+constexpr int kCoopRow = 64 + 8;
 
 // (K^T p)(pix, l) from the five staged values (grad_adj<1, false, HAS_ID, .>):
 //   a1 = p1[idx] (0 on the last column), a2 = p1[idx-ny] (0 / halo on column 0), a3 = p2[idx] (0 on the last
@@ -56,7 +71,7 @@ constexpr int kStagedChunk = 4;
 
 // ---- primal pass: x+ = proj_simplex( x - tau T K^T y ) over the L <= CAPL labels of a pixel -----------------
 // operands per label: x, p1, p1-left, p2, p2-up (+ identity rows) (+ the same dual operands of y_prev when CHECK)
-template <int CAPL, int LC, bool HAS_ID, bool CHECK, bool SLAB>
+template <int CAPL, int LC, bool HAS_ID, bool CHECK, bool SLAB, bool COOP = false>
 __global__ void __launch_bounds__(kStagedBlock, CHECK ? 2 : 8) grad_primal_simplex_staged_kernel(
     const GradGeom g, const ProxDesc p, const float* __restrict__ x, const float* __restrict__ y,
     const float* __restrict__ y_prev, const float Tval, const PdhgState* __restrict__ st, const int ktyprev_zero,
@@ -82,10 +97,17 @@ __global__ void __launch_bounds__(kStagedBlock, CHECK ? 2 : 8) grad_primal_simpl
     const bool left_in = xx > 0, left_halo = SLAB && !left_in && g.halo.has_left;
     const bool has3 = y0 + 1 != g.ny, has4 = y0 > 0;
     const bool prev = CHECK && !ktyprev_zero;
-    float* s = staged_smem + threadIdx.x;
+    static_assert(!COOP || (!CHECK && LC == 4 && kStagedBlock == 64), "cooperative staging: plain iterations");
+    constexpr int NBUF = COOP ? 3 : 2;
+    constexpr int RS = COOP ? kCoopRow : B;             // floats per (buffer, array, label slot) row
+    float* s = staged_smem + threadIdx.x + (COOP ? 4 : 0);
     // chunk buffer b, array a, label slot j of the chunk; (CHECK) keep[k][label]: xo, K^T y, K^T y_prev
-    auto at = [&](int b, int a, int j) -> float* { return s + ((b * NT + a) * LC + j) * B; };
+    auto at = [&](int b, int a, int j) -> float* { return s + ((b * NT + a) * LC + j) * RS; };
     float* keep = s + 2 * NT * LC * B;
+    // COOP: this thread copies 16-byte piece `ck` of the rows of label slot `jrow`
+    const uint32_t jrow = threadIdx.x >> 4, ck = threadIdx.x & 15u;
+    const uint32_t cta_pix = pix - threadIdx.x;        // first pixel of the CTA (same column)
+    const bool cta_first = y0 == threadIdx.x, cta_last = y0 - threadIdx.x + B == g.ny;
     auto stage_dual = [&](const float* __restrict__ q, const float* __restrict__ q_halo, int b, int a0, int j,
                           int li, uint32_t idx) {
       const float* q1 = q;
@@ -98,7 +120,24 @@ __global__ void __launch_bounds__(kStagedBlock, CHECK ? 2 : 8) grad_primal_simpl
       if (HAS_ID) cp_async4(at(b, a0 + 4, j), q + g.id_row + idx, true);
     };
     auto stage_chunk = [&](int c) {
-      const int b = c & 1;
+      const int b = c % NBUF;
+      if (COOP) {
+        const int li = c * LC + (int)jrow;
+        const bool ok = li < CAPL && li < nl;
+        const uint32_t eo = (ok ? li : 0) * g.nxny + cta_pix + 4 * ck;
+        float* const dst = staged_smem + ((b * NT) * LC + jrow) * RS + 4 + 4 * ck;   // array 0, this slot, this piece
+        cp_async16(dst, x + eo, ok);
+        if (has1) cp_async16(dst + 1 * LC * RS, y + eo, ok);
+        if (left_in) cp_async16(dst + 2 * LC * RS, y + eo - g.ny, ok);
+        else if (left_halo)         // column 0 of a slab: the left neighbour's last y.gx column, [label][ny]
+          cp_async16(dst + 2 * LC * RS, g.halo.in_a + (ok ? li : 0) * g.ny + (y0 - threadIdx.x) + 4 * ck, ok);
+        cp_async16(dst + 3 * LC * RS, y + g.plane + eo, ok);
+        if (HAS_ID) cp_async16(dst + 5 * LC * RS, y + g.id_row + eo, ok);
+        // p2 one pixel up of the CTA's first pixel (the previous CTA's last pixel, same column)
+        if (ck == 0) cp_async4(dst + 3 * LC * RS - 1, y + g.plane + eo - 1, ok && !cta_first);
+        cp_async_commit();
+        return;
+      }
 #pragma unroll
       for (int j = 0; j < LC; ++j) {
         const int li = c * LC + j;
@@ -118,7 +157,8 @@ __global__ void __launch_bounds__(kStagedBlock, CHECK ? 2 : 8) grad_primal_simpl
       if (c + 1 < NCH) stage_chunk(c + 1);
       else cp_async_commit();                          // empty group: uniform accounting for wait_group 1
       cp_async_wait_group<1>();
-      const int b = c & 1;
+      if (COOP) __syncthreads();
+      const int b = c % NBUF;
 #pragma unroll
       for (int j = 0; j < LC; ++j) {
         const int li = c * LC + j;
@@ -126,7 +166,13 @@ __global__ void __launch_bounds__(kStagedBlock, CHECK ? 2 : 8) grad_primal_simpl
           v[li] = 0.f;
           tdl[li] = Tval;
           if (li < nl) {
-            const float k = staged_adj<HAS_ID>(*at(b, 1, j), *at(b, 2, j), *at(b, 3, j), *at(b, 4, j),
+            // COOP: operands that do not exist (last column / row, first column / row) read as the zeros the
+            // per-thread copies stage for them
+            const float k = COOP ? staged_adj<HAS_ID>(has1 ? *at(b, 1, j) : 0.f,
+                                                      (left_in || left_halo) ? *at(b, 2, j) : 0.f,
+                                                      has3 ? *at(b, 3, j) : 0.f, has4 ? at(b, 3, j)[-1] : 0.f,
+                                                      HAS_ID ? *at(b, 5, j) : 0.f, g.id_factor)
+                                 : staged_adj<HAS_ID>(*at(b, 1, j), *at(b, 2, j), *at(b, 3, j), *at(b, 4, j),
                                                HAS_ID ? *at(b, 5, j) : 0.f, g.id_factor);
             const float xo = *at(b, 0, j);
             v[li] = primal_prox_arg(xo, tau, Tval, k);
@@ -169,16 +215,17 @@ __global__ void __launch_bounds__(kStagedBlock, CHECK ? 2 : 8) grad_primal_simpl
   }
 }
 
-inline size_t primal_staged_smem(int capl, int lc, bool has_id, bool check) {
+inline size_t primal_staged_smem(int capl, int lc, bool has_id, bool check, bool coop = false) {
   const int na = has_id ? 6 : 5;
   const int nt = na + (check ? na - 1 : 0);
+  if (coop) return static_cast<size_t>(3 * nt * lc) * kCoopRow * sizeof(float);
   return static_cast<size_t>(2 * nt * lc + (check ? 3 * capl : 0)) * kStagedBlock * sizeof(float);
 }
 
 // ---- dual pass on the gradient rows: y+ = prox_Norm2( y + sigma S ((1+theta) K x+ - theta K x) ) -----------
 // group = the 2L gradient components of a pixel (component c*L + l), scalar weights, uniform Sigma.
 // operands per label: x+ (centre, right, down), x (centre, right, down), y.gx, y.gy
-template <int CAPL, int LC, int FN, bool CHECK, bool SLAB>
+template <int CAPL, int LC, int FN, bool CHECK, bool SLAB, bool COOP = false>
 __global__ void __launch_bounds__(kStagedBlock, CHECK ? 2 : 6) grad_dual_norm2_staged_kernel(
     const GradGeom g, const ProxDesc p, const float* __restrict__ y, const float* __restrict__ xn,
     const float* __restrict__ xo, const float Sval, const PdhgState* __restrict__ st, const int kxprev_zero,
@@ -203,10 +250,17 @@ __global__ void __launch_bounds__(kStagedBlock, CHECK ? 2 : 6) grad_dual_norm2_s
     if (SLAB && edge) halo_wait(g.halo);
     const bool right_in = xx < g.nx - 1, right_halo = SLAB && !right_in && g.halo.has_right;
     const bool has_r = right_in || right_halo, has_d = y0 + 1 < g.ny;
-    float* s = staged_smem + threadIdx.x;
-    auto at = [&](int b, int a, int j) -> float* { return s + ((b * NT + a) * LC + j) * B; };
+    static_assert(!COOP || (!CHECK && LC == 4 && kStagedBlock == 64), "cooperative staging: plain iterations");
+    constexpr int NBUF = COOP ? 3 : 2;
+    constexpr int RS = COOP ? kCoopRow : B;             // floats per (buffer, array, label slot) row
+    float* s = staged_smem + threadIdx.x + (COOP ? 4 : 0);
+    auto at = [&](int b, int a, int j) -> float* { return s + ((b * NT + a) * LC + j) * RS; };
     // (CHECK) keep[k][label]: y.gx, y.gy, extrapolated K x (x, y), K x+ (x, y)
     float* keep = s + 2 * NT * LC * B;
+    // COOP: this thread copies 16-byte piece `ck` of the rows of label slot `jrow`
+    const uint32_t jrow = threadIdx.x >> 4, ck = threadIdx.x & 15u;
+    const uint32_t cta_pix = pix - threadIdx.x;        // first pixel of the CTA (same column)
+    const bool cta_last = y0 - threadIdx.x + B == g.ny;
     auto stage_primal = [&](const float* __restrict__ u, const float* __restrict__ u_halo, int b, int a0, int j,
                             int li, uint32_t idx) {
       cp_async4(at(b, a0 + 0, j), u + idx, true);
@@ -215,7 +269,33 @@ __global__ void __launch_bounds__(kStagedBlock, CHECK ? 2 : 6) grad_dual_norm2_s
       cp_async4(at(b, a0 + 2, j), has_d ? u + idx + 1 : u, has_d);
     };
     auto stage_chunk = [&](int c) {
-      const int b = c & 1;
+      const int b = c % NBUF;
+      if (COOP) {
+        const int li = c * LC + (int)jrow;
+        const bool ok = li < CAPL && li < nl;
+        const uint32_t eo = (ok ? li : 0) * g.nxny + cta_pix + 4 * ck;
+        float* const dst = staged_smem + ((b * NT) * LC + jrow) * RS + 4 + 4 * ck;   // array 0, this slot, this piece
+        // right neighbour column: inside the slab, or (last column of a slab) the right neighbour's column 0 of
+        // x+ / x, [label][ny]
+        const uint32_t ho = (ok ? li : 0) * g.ny + (y0 - threadIdx.x) + 4 * ck;
+        cp_async16(dst, xn + eo, ok);
+        if (right_in) cp_async16(dst + 1 * LC * RS, xn + eo + g.ny, ok);
+        else if (right_halo) cp_async16(dst + 1 * LC * RS, g.halo.in_a + ho, ok);
+        if (!kxprev_zero) {
+          cp_async16(dst + 3 * LC * RS, xo + eo, ok);
+          if (right_in) cp_async16(dst + 4 * LC * RS, xo + eo + g.ny, ok);
+          else if (right_halo) cp_async16(dst + 4 * LC * RS, g.halo.in_b + ho, ok);
+        }
+        cp_async16(dst + 6 * LC * RS, y + eo, ok);
+        cp_async16(dst + 7 * LC * RS, y + g.plane + eo, ok);
+        // x one pixel below the CTA's last pixel (the next CTA's first pixel, same column)
+        if (ck == 15) {
+          cp_async4(dst + 4, xn + eo + 4, ok && !cta_last);
+          if (!kxprev_zero) cp_async4(dst + 3 * LC * RS + 4, xo + eo + 4, ok && !cta_last);
+        }
+        cp_async_commit();
+        return;
+      }
 #pragma unroll
       for (int j = 0; j < LC; ++j) {
         const int li = c * LC + j;
@@ -233,7 +313,7 @@ __global__ void __launch_bounds__(kStagedBlock, CHECK ? 2 : 6) grad_dual_norm2_s
     auto k_of = [&](int b, int a0, int j, float& kx, float& ky) {
       const float c = *at(b, a0 + 0, j);
       kx = has_r ? *at(b, a0 + 1, j) - c : 0.f;
-      ky = has_d ? *at(b, a0 + 2, j) - c : 0.f;
+      ky = has_d ? (COOP ? at(b, a0 + 0, j)[1] : *at(b, a0 + 2, j)) - c : 0.f;
     };
     stage_chunk(0);
     float arg[CAP][1];
@@ -242,7 +322,8 @@ __global__ void __launch_bounds__(kStagedBlock, CHECK ? 2 : 6) grad_dual_norm2_s
       if (c + 1 < NCH) stage_chunk(c + 1);
       else cp_async_commit();
       cp_async_wait_group<1>();
-      const int b = c & 1;
+      if (COOP) __syncthreads();
+      const int b = c % NBUF;
 #pragma unroll
       for (int j = 0; j < LC; ++j) {
         const int li = c * LC + j;
@@ -304,7 +385,8 @@ __global__ void __launch_bounds__(kStagedBlock, CHECK ? 2 : 6) grad_dual_norm2_s
   }
 }
 
-inline size_t dual_staged_smem(int capl, int lc, bool check) {
+inline size_t dual_staged_smem(int capl, int lc, bool check, bool coop = false) {
+  if (coop) return static_cast<size_t>(3 * 8 * lc) * kCoopRow * sizeof(float);
   return static_cast<size_t>(2 * 8 * lc + (check ? 6 * capl : 0)) * kStagedBlock * sizeof(float);
 }
 

@@ -23,6 +23,9 @@ def cases():
         "tvl1": (lambda: syn.tvl1(40, 32, nc=3), dict(stepsize="boyd", residual_iter=5), 60),
         "tv3d": (lambda: syn.tv3d(14, 16, 6), dict(stepsize="alg1", residual_iter=5), 40),
         "lifting": (lambda: syn.lifting(18, 12, 6), dict(stepsize="boyd", residual_iter=5), 40),
+        # columns of 64 / 128 pixels: the staged passes copy their operands cooperatively, halo columns included
+        "lifting_coop": (lambda: syn.lifting(24, 64, 8), dict(stepsize="boyd", residual_iter=5), 40),
+        "lifting_coop128": (lambda: syn.lifting(16, 128, 6), dict(stepsize="alg1", residual_iter=6), 30),
         "rof_big": (lambda: syn.rof(1024, 512), dict(stepsize="alg1", residual_iter=10), 200),
         # one-pass ring kernel on slabs (pb_tile.cu, SLAB): several tile columns / rows per slab; slab width 63
         # puts the right edge column in a one-column tile (62 = 2 * 31), width 65 in the middle of one

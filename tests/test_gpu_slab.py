@@ -60,7 +60,7 @@ def test_world1_communicator():
     """A communicator of one rank: no neighbours, all-reduce is the identity."""
     if _gpus() < 1:
         pytest.skip("no GPU")
-    _check(_run(1, "p2p", "rof_vec4,lifting,rof_tiles65,rof_tiles_alg2"), None)
+    _check(_run(1, "p2p", "rof_vec4,lifting,lifting_coop,rof_tiles65,rof_tiles_alg2"), None)
 
 
 @pytest.mark.parametrize("halo", ["p2p", "nccl"])

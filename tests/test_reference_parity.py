@@ -92,6 +92,10 @@ PDHG_CASES = {
     "tv3d": (lambda: syn.tv3d(20, 24, 16), 200, dict(stepsize="boyd", residual_iter=10)),
     "lifting_L8": (lambda: syn.lifting(24, 20, 8), 200, dict(stepsize="boyd", residual_iter=10)),
     "lifting_L32": (lambda: syn.lifting(16, 12, 32), 100, dict(stepsize="boyd", residual_iter=10)),
+    # column height a multiple of 64: the staged passes copy their operands cooperatively (pb_stencil_staged.cuh);
+    # 128 rows = two CTAs per column (the +-1 row neighbours cross the CTA boundary), 5 / 6 columns incl. both edges
+    "lifting_coop_L32": (lambda: syn.lifting(5, 128, 32), 60, dict(stepsize="boyd", residual_iter=10)),
+    "lifting_coop_L8": (lambda: syn.lifting(6, 64, 8), 120, dict(stepsize="alg1", residual_iter=7)),
 }
 TOL4 = dict(tol_rel_primal=1e-4, tol_rel_dual=1e-4, tol_abs_primal=1e-4, tol_abs_dual=1e-4)
 
