@@ -305,6 +305,36 @@ __global__ void __launch_bounds__(kBlock) prox_pass_kernel(const ProxDesc p, con
   src.finish(r);
 }
 
+// Same pass for planar groups of dimension 2 (the (x, y) pairs of ProxIndEpiQuad on the identity rows of the lifting
+// config), four consecutive groups per thread: the two components of four neighbouring groups are 16 contiguous
+// bytes each, so arguments and results move as 128-bit vectors (a quarter of the load / store instructions and of
+// their address arithmetic; the pass is instruction bound, profiles/r02_lifting.md).  Same arithmetic per group.
+// Requires uniform step-size diagonals, count % 4 == 0 and 16-byte aligned rows (checked by the launcher).
+template <class Src, int KIND>
+__global__ void __launch_bounds__(kBlock) prox_pass_pairs4_kernel(const ProxDesc p, const Src src,
+                                                                  float* __restrict__ out, const float tdiag_val,
+                                                                  const bool invert) {
+  typename Src::Regs r;
+  const float tau = src.begin(r);
+  const uint32_t quads = p.count >> 2;
+  for (uint32_t q4 = blockIdx.x * blockDim.x + threadIdx.x; q4 < quads; q4 += gridDim.x * blockDim.x) {
+    const uint32_t tx = 4 * q4;
+    const uint32_t e0 = p.index + tx, e1 = e0 + p.count;
+    float a0[4], a1[4];
+    src.load4(r, e0, a0);
+    src.load4(r, e1, a1);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float v[2] = {a0[q], a1[q]}, td[2] = {tdiag_val, tdiag_val};
+      group_apply<2, KIND>(p, tx + q, v, td, tau, invert);
+      a0[q] = v[0];
+      a1[q] = v[1];
+    }
+    *reinterpret_cast<float4*>(out + e0) = make_float4(a0[0], a0[1], a0[2], a0[3]);
+    *reinterpret_cast<float4*>(out + e1) = make_float4(a1[0], a1[1], a1[2], a1[3]);
+  }
+}
+
 // argument read from memory: the unfused Prox::Eval path
 struct MemSource {
   const float* __restrict__ arg;

@@ -464,6 +464,20 @@ static void ident_launch_k(Context* ctx, unsigned grid, const GradGeom& g, const
     prox_pass_kernel<CAP, IdentityDualSource<CAP, true>, KIND><<<grid, kBlock, 0, ctx->stream>>>(d, src, y_out, S, false);
   } else {
     IdentityDualSource<CAP, false> src{y, x_new, x_old, S, st, g.id_factor, g.id_row, kxprev_zero, partials};
+    if constexpr (CAP == 2 && KIND == kProxEpiQuad) {
+      // (x, y) pairs, planar: four pairs per thread with 128-bit loads / stores when the rows are aligned
+      static const bool vec4 = [] { const char* e = getenv("PB_IDENT_VEC4"); return !e || atoi(e) != 0; }();
+      auto aligned = [](const float* ptr, size_t off) { return (reinterpret_cast<uintptr_t>(ptr + off) & 15u) == 0; };
+      const size_t e0 = d.index, e1 = (size_t)d.index + d.count;
+      if (vec4 && d.dim == 2 && !S.ptr && d.count % 4 == 0 && aligned(y, e0) && aligned(y, e1) && aligned(y_out, e0) &&
+          aligned(y_out, e1) && aligned(x_new, e0 - g.id_row) && aligned(x_new, e1 - g.id_row) &&
+          (kxprev_zero || (aligned(x_old, e0 - g.id_row) && aligned(x_old, e1 - g.id_row)))) {
+        const unsigned g4 = (unsigned)std::min<size_t>(grid_for(d.count / 4), (size_t)grid);
+        prox_pass_pairs4_kernel<IdentityDualSource<CAP, false>, KIND><<<g4, kBlock, 0, ctx->stream>>>(d, src, y_out, S.val,
+                                                                                                      false);
+        return;
+      }
+    }
     prox_pass_kernel<CAP, IdentityDualSource<CAP, false>, KIND><<<grid, kBlock, 0, ctx->stream>>>(d, src, y_out, S, false);
   }
 }

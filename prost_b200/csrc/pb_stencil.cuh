@@ -670,6 +670,20 @@ struct IdentityDualSource {
     if (CHECK) { r.yo[i] = yv; r.kx[i] = k1; r.kxe[i] = ext; }
     return dual_prox_arg(yv, r.sigma, S.at(e), ext);
   }
+  // four consecutive rows at once (prox_pass_pairs4_kernel; uniform S, no residual terms)
+  __device__ __forceinline__ void load4(Regs& r, uint32_t e, float (&out)[4]) const {
+    const float4 yv = *reinterpret_cast<const float4*>(y + e);
+    const float4 xn = *reinterpret_cast<const float4*>(x_new + (e - id_row));
+    float4 xo = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!kxprev_zero) xo = *reinterpret_cast<const float4*>(x_old + (e - id_row));
+    const float yy[4] = {yv.x, yv.y, yv.z, yv.w}, n4[4] = {xn.x, xn.y, xn.z, xn.w}, o4[4] = {xo.x, xo.y, xo.z, xo.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float k1 = __fmul_rn(n4[q], factor);
+      const float k0 = kxprev_zero ? 0.f : __fmul_rn(o4[q], factor);
+      out[q] = dual_prox_arg(yy[q], r.sigma, S.val, dual_extrapolate(r.theta, k1, k0));
+    }
+  }
   __device__ __forceinline__ void post(Regs& r, uint32_t e, int i, float yn) const {
     if (CHECK) {
       const float sq = sqrtf(S.at(e));

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Cooperative staging of the lifting passes (PB_STAGED_COOP, pb_stencil_staged.cuh) against the per-thread staging:
-the arithmetic is identical, so x, y, z, w and the residuals must match bit for bit.  The switch is read once per
+"""Cooperative staging of the lifting passes (PB_STAGED_COOP, pb_stencil_staged.cuh) and the four-pairs-per-thread
+identity-row pass (PB_IDENT_VEC4, prox_pass_pairs4_kernel) against the per-thread / per-pair forms: the arithmetic
+is identical, so x, y, z, w and the residuals must match bit for bit.  The switch is read once per
 process, so the script re-executes itself with both settings (tests/test_gpu_staged_coop.py runs it)."""
 import os
 import subprocess
@@ -39,7 +40,7 @@ def main():
     import numpy as np
     tmp = tempfile.mkdtemp(prefix="staged_coop_")
     for tag in ("0", "1"):
-        env = dict(os.environ, PB_STAGED_COOP=tag, PB_COOP_CHECK_DIR=tmp, PB_COOP_CHECK_TAG=tag)
+        env = dict(os.environ, PB_STAGED_COOP=tag, PB_IDENT_VEC4=tag, PB_COOP_CHECK_DIR=tmp, PB_COOP_CHECK_TAG=tag)
         p = subprocess.run([sys.executable, os.path.abspath(__file__)], env=env, capture_output=True, text=True, timeout=600)
         if p.returncode != 0:
             print(tag, p.stdout[-2000:], p.stderr[-2000:])
