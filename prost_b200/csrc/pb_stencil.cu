@@ -86,7 +86,8 @@ static bool staged_configure(Kernel kernel, size_t smem) {
 // cooperative 16-byte staging (pb_stencil_staged.cuh): plain iterations, CTAs aligned with image columns
 [[maybe_unused]] static bool staged_coop_ok(const GradGeom& g, bool check, std::initializer_list<const void*> arrays) {
   static const bool enabled = [] { const char* e = getenv("PB_STAGED_COOP"); return !e || atoi(e) != 0; }();
-  if (!enabled || check || g.ny % kStagedBlock != 0 || g.q != g.ny || g.plane % 4 != 0 || g.nxny % 4 != 0 ||
+  (void)check;
+  if (!enabled || g.ny % kStagedBlock != 0 || g.q != g.ny || g.plane % 4 != 0 || g.nxny % 4 != 0 ||
       (g.has_id && g.id_row % 4 != 0))
     return false;
   if ((g.halo.has_left || g.halo.has_right) &&
@@ -253,10 +254,10 @@ static bool simplex_staged_launch_k(Context* ctx, unsigned grid, const GradGeom&
                                     const float* y, const float* y_prev, float Tval, const PdhgState* st,
                                     bool ktyprev_zero, double* partials, float* x_out) {
   constexpr int LC = CAPL < kStagedChunk ? CAPL : kStagedChunk;
-  if constexpr (!CHECK && LC == 4) {
-    if (staged_coop_ok(g, false, {x, y, x_out})) {
-      auto coop = grad_primal_simplex_staged_kernel<CAPL, LC, HAS_ID, false, kSlab, true>;
-      const size_t csmem = primal_staged_smem(CAPL, LC, HAS_ID, false, true);
+  if constexpr (LC == 4) {
+    if (staged_coop_ok(g, CHECK, {x, y, y_prev, x_out})) {
+      auto coop = grad_primal_simplex_staged_kernel<CAPL, LC, HAS_ID, CHECK, kSlab, true>;
+      const size_t csmem = primal_staged_smem(CAPL, LC, HAS_ID, CHECK, true);
       static const bool cok = staged_configure(coop, csmem);
       if (cok) {
         coop<<<grid, kStagedBlock, csmem, ctx->stream>>>(g, d, x, y, y_prev, Tval, st, ktyprev_zero ? 1 : 0, partials,
@@ -332,10 +333,10 @@ static bool dual_staged_launch_k(Context* ctx, unsigned grid, const GradGeom& g,
                                  const float* x_new, const float* x_old, float Sval, const PdhgState* st,
                                  bool kxprev_zero, double* partials, float* y_out) {
   constexpr int LC = CAPL < kStagedChunk ? CAPL : kStagedChunk;
-  if constexpr (!CHECK && LC == 4) {
-    if (staged_coop_ok(g, false, {y, x_new, x_old, y_out})) {
-      auto coop = grad_dual_norm2_staged_kernel<CAPL, LC, FN, false, kSlab, true>;
-      const size_t csmem = dual_staged_smem(CAPL, LC, false, true);
+  if constexpr (LC == 4) {
+    if (staged_coop_ok(g, CHECK, {y, x_new, x_old, y_out})) {
+      auto coop = grad_dual_norm2_staged_kernel<CAPL, LC, FN, CHECK, kSlab, true>;
+      const size_t csmem = dual_staged_smem(CAPL, LC, CHECK, true);
       static const bool cok = staged_configure(coop, csmem);
       if (cok) {
         coop<<<grid, kStagedBlock, csmem, ctx->stream>>>(g, d, y, x_new, x_old, Sval, st, kxprev_zero ? 1 : 0, partials,

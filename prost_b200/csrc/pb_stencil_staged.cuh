@@ -36,7 +36,7 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, b
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// Cooperative staging (COOP, plain iterations with ny % kStagedBlock == 0, slabs included): a CTA owns kStagedBlock
+// Cooperative staging (COOP, columns of ny % kStagedBlock == 0 pixels, slabs and refresh iterations included): a CTA owns kStagedBlock
 // consecutive pixels of ONE image column, so every operand of a label is a contiguous, 16-byte aligned row of
 // kStagedBlock floats.  Instead of one 4-byte cp.async per thread, operand and label (with its own 64-bit address
 // arithmetic: ~40 of the ~100 instructions per pixel and label, profiles/r02_lifting.md), the CTA copies each row with
@@ -97,13 +97,15 @@ __global__ void __launch_bounds__(kStagedBlock, CHECK ? 2 : 8) grad_primal_simpl
     const bool left_in = xx > 0, left_halo = SLAB && !left_in && g.halo.has_left;
     const bool has3 = y0 + 1 != g.ny, has4 = y0 > 0;
     const bool prev = CHECK && !ktyprev_zero;
-    static_assert(!COOP || (!CHECK && LC == 4 && kStagedBlock == 64), "cooperative staging: plain iterations");
-    constexpr int NBUF = COOP ? 3 : 2;
+    static_assert(!COOP || (LC == 4 && kStagedBlock == 64), "cooperative staging: 4 label slots x 16 pieces = 64 threads");
+    // COOP: three chunk buffers and one barrier per chunk; the refresh variant (CHECK) keeps two buffers and pays a
+    // second barrier per chunk instead, because its keep[] columns already fill the shared memory
+    constexpr int NBUF = (COOP && !CHECK) ? 3 : 2;
     constexpr int RS = COOP ? kCoopRow : B;             // floats per (buffer, array, label slot) row
     float* s = staged_smem + threadIdx.x + (COOP ? 4 : 0);
     // chunk buffer b, array a, label slot j of the chunk; (CHECK) keep[k][label]: xo, K^T y, K^T y_prev
     auto at = [&](int b, int a, int j) -> float* { return s + ((b * NT + a) * LC + j) * RS; };
-    float* keep = s + 2 * NT * LC * B;
+    float* keep = staged_smem + NBUF * NT * LC * RS + threadIdx.x;
     // COOP: this thread copies 16-byte piece `ck` of the rows of label slot `jrow`
     const uint32_t jrow = threadIdx.x >> 4, ck = threadIdx.x & 15u;
     const uint32_t cta_pix = pix - threadIdx.x;        // first pixel of the CTA (same column)
@@ -135,6 +137,16 @@ __global__ void __launch_bounds__(kStagedBlock, CHECK ? 2 : 8) grad_primal_simpl
         if (HAS_ID) cp_async16(dst + 5 * LC * RS, y + g.id_row + eo, ok);
         // p2 one pixel up of the CTA's first pixel (the previous CTA's last pixel, same column)
         if (ck == 0) cp_async4(dst + 3 * LC * RS - 1, y + g.plane + eo - 1, ok && !cta_first);
+        if (prev) {                 // the same dual operands of y_prev (arrays NA ..)
+          float* const dp = dst + NA * LC * RS;
+          if (has1) cp_async16(dp, y_prev + eo, ok);
+          if (left_in) cp_async16(dp + 1 * LC * RS, y_prev + eo - g.ny, ok);
+          else if (left_halo)
+            cp_async16(dp + 1 * LC * RS, g.halo.in_b + (ok ? li : 0) * g.ny + (y0 - threadIdx.x) + 4 * ck, ok);
+          cp_async16(dp + 2 * LC * RS, y_prev + g.plane + eo, ok);
+          if (HAS_ID) cp_async16(dp + 4 * LC * RS, y_prev + g.id_row + eo, ok);
+          if (ck == 0) cp_async4(dp + 2 * LC * RS - 1, y_prev + g.plane + eo - 1, ok && !cta_first);
+        }
         cp_async_commit();
         return;
       }
@@ -179,7 +191,11 @@ __global__ void __launch_bounds__(kStagedBlock, CHECK ? 2 : 8) grad_primal_simpl
             if (CHECK) {
               float kp = 0.f;
               if (prev)
-                kp = staged_adj<HAS_ID>(*at(b, NA + 0, j), *at(b, NA + 1, j), *at(b, NA + 2, j), *at(b, NA + 3, j),
+                kp = COOP ? staged_adj<HAS_ID>(has1 ? *at(b, NA + 0, j) : 0.f,
+                                               (left_in || left_halo) ? *at(b, NA + 1, j) : 0.f,
+                                               has3 ? *at(b, NA + 2, j) : 0.f, has4 ? at(b, NA + 2, j)[-1] : 0.f,
+                                               HAS_ID ? *at(b, NA + 4, j) : 0.f, g.id_factor)
+                          : staged_adj<HAS_ID>(*at(b, NA + 0, j), *at(b, NA + 1, j), *at(b, NA + 2, j), *at(b, NA + 3, j),
                                         HAS_ID ? *at(b, NA + 4, j) : 0.f, g.id_factor);
               keep[(0 * CAPL + li) * B] = xo;
               keep[(1 * CAPL + li) * B] = k;
@@ -188,6 +204,7 @@ __global__ void __launch_bounds__(kStagedBlock, CHECK ? 2 : 8) grad_primal_simpl
           }
         }
       }
+      if (COOP && NBUF == 2) __syncthreads();           // buffer b is free for chunk c + 2
     }
     group_apply<CAPL, kProxSimplex, -1>(p, pix, v, tdl, tau, false);
     const float sq = sqrtf(Tval);
@@ -218,7 +235,9 @@ __global__ void __launch_bounds__(kStagedBlock, CHECK ? 2 : 8) grad_primal_simpl
 inline size_t primal_staged_smem(int capl, int lc, bool has_id, bool check, bool coop = false) {
   const int na = has_id ? 6 : 5;
   const int nt = na + (check ? na - 1 : 0);
-  if (coop) return static_cast<size_t>(3 * nt * lc) * kCoopRow * sizeof(float);
+  if (coop)
+    return static_cast<size_t>((check ? 2 : 3) * nt * lc) * kCoopRow * sizeof(float) +
+           static_cast<size_t>(check ? 3 * capl : 0) * kStagedBlock * sizeof(float);
   return static_cast<size_t>(2 * nt * lc + (check ? 3 * capl : 0)) * kStagedBlock * sizeof(float);
 }
 
@@ -250,13 +269,13 @@ __global__ void __launch_bounds__(kStagedBlock, CHECK ? 2 : 6) grad_dual_norm2_s
     if (SLAB && edge) halo_wait(g.halo);
     const bool right_in = xx < g.nx - 1, right_halo = SLAB && !right_in && g.halo.has_right;
     const bool has_r = right_in || right_halo, has_d = y0 + 1 < g.ny;
-    static_assert(!COOP || (!CHECK && LC == 4 && kStagedBlock == 64), "cooperative staging: plain iterations");
-    constexpr int NBUF = COOP ? 3 : 2;
+    static_assert(!COOP || (LC == 4 && kStagedBlock == 64), "cooperative staging: 4 label slots x 16 pieces = 64 threads");
+    constexpr int NBUF = (COOP && !CHECK) ? 3 : 2;      // see grad_primal_simplex_staged_kernel
     constexpr int RS = COOP ? kCoopRow : B;             // floats per (buffer, array, label slot) row
     float* s = staged_smem + threadIdx.x + (COOP ? 4 : 0);
     auto at = [&](int b, int a, int j) -> float* { return s + ((b * NT + a) * LC + j) * RS; };
     // (CHECK) keep[k][label]: y.gx, y.gy, extrapolated K x (x, y), K x+ (x, y)
-    float* keep = s + 2 * NT * LC * B;
+    float* keep = staged_smem + NBUF * NT * LC * RS + threadIdx.x;
     // COOP: this thread copies 16-byte piece `ck` of the rows of label slot `jrow`
     const uint32_t jrow = threadIdx.x >> 4, ck = threadIdx.x & 15u;
     const uint32_t cta_pix = pix - threadIdx.x;        // first pixel of the CTA (same column)
@@ -346,6 +365,7 @@ __global__ void __launch_bounds__(kStagedBlock, CHECK ? 2 : 6) grad_dual_norm2_s
           }
         }
       }
+      if (COOP && NBUF == 2) __syncthreads();           // buffer b is free for chunk c + 2
     }
     Coeffs7 c;
 #pragma unroll
@@ -386,7 +406,9 @@ __global__ void __launch_bounds__(kStagedBlock, CHECK ? 2 : 6) grad_dual_norm2_s
 }
 
 inline size_t dual_staged_smem(int capl, int lc, bool check, bool coop = false) {
-  if (coop) return static_cast<size_t>(3 * 8 * lc) * kCoopRow * sizeof(float);
+  if (coop)
+    return static_cast<size_t>((check ? 2 : 3) * 8 * lc) * kCoopRow * sizeof(float) +
+           static_cast<size_t>(check ? 6 * capl : 0) * kStagedBlock * sizeof(float);
   return static_cast<size_t>(2 * 8 * lc + (check ? 6 * capl : 0)) * kStagedBlock * sizeof(float);
 }
 
